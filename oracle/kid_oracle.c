@@ -1,0 +1,2324 @@
+/*
+ * kid_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE ONLY; see kid_oracle.h).
+ *
+ * Restates, routine by routine, the reference's per-timestep berg update.
+ * Citations: I: = /root/reference/src/icebergs.F90,
+ *            F: = /root/reference/src/icebergs_framework.F90.
+ * Bergs live in real per-cell doubly linked lists, as in the reference
+ * (F:416-423), so iteration and insertion order follow it by construction.
+ *
+ * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off; no FMA contraction so
+ * that the arithmetic is the plain IEEE sequence the Fortran source spells).
+ *
+ * Single-rank semantics of the FMS pieces that are outside the reference tree:
+ *  - mpp_update_domains: cyclic-x wrap copy of the E/W halos for compute rows;
+ *    N/S halos are left untouched (no neighbour) -- see halo_update_*().
+ *  - send_bergs_to_other_pes to "the next PE" of a cyclic-x domain: the berg is
+ *    re-homed in the cell ine-/+gni of the same row, exactly what a receiving
+ *    PE's unpack_berg_from_buffer2 (F:3634-3646) finds when >=2 PEs span x; the
+ *    berg's lon is NOT wrapped (the reference never wraps it either).
+ */
+#include "kid_oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* module constants, I:68-80 */
+#define RHO_ICE 916.7
+#define RHO_WATER 999.8
+#define RHO_AIR 1.1
+#define RHO_SEAWATER 1025.
+#define GRAVITY 9.8
+#define CD_AV 1.3
+#define CD_AH 0.0055
+#define CD_WV 0.9
+#define CD_WH 0.0012
+#define CD_IV 0.9
+
+typedef struct OBond {
+  struct OBond *prev_bond, *next_bond;
+  struct OBerg* other_berg;
+  int64_t other_id;
+  int32_t other_berg_ine, other_berg_jne;
+  double length;
+  double rel_rotation, tangd1, tangd2, nstress, sstress;
+  int32_t broken;
+  struct OBond* other_bond;
+  double F_x, F_y, Fd_x, Fd_y, T, T_d;
+} OBond;
+
+typedef struct OBerg {
+  struct OBerg *prev, *next;
+  double lon, lat, uvel, vvel, mass, thickness, width, length;
+  double axn, ayn, bxn, byn, uvel_prev, vvel_prev, uvel_old, vvel_old, lon_old, lat_old;
+  double start_lon, start_lat, start_day, start_mass, mass_scaling;
+  double mass_of_bits, mass_of_fl_bits, mass_of_fl_bergy_bits, fl_k, heat_density;
+  double halo_berg, static_berg;
+  int32_t start_year;
+  int64_t id;
+  int32_t ine, jne;
+  double xi, yj;
+  double uo, vo, ui, vi, ua, va, ssh_x, ssh_y, sst, sss, cn, hi, od;
+  OBond* first_bond;
+  double axn_fast, ayn_fast, bxn_fast, byn_fast;
+  int32_t conglom_id;
+  int32_t n_bonds;
+  double ang_vel, ang_accel, rot;
+} OBerg;
+
+struct Oracle {
+  KidParams p;
+  KidDomain d;
+  int nid, njd;            /* data-domain extents */
+  /* static grid (isd:ied,jsd:jed) */
+  double *lon, *lat, *lonc, *latc, *dx, *dy, *area, *msk, *cosr, *sinr, *ocean_depth;
+  /* forcing */
+  double *uo, *vo, *ui, *vi, *ua, *va, *ssh, *sst, *sss, *cn, *hi;
+  double *calving, *calving_hflx;
+  /* outputs / diagnostics */
+  double *floating_melt, *berg_melt, *melt_buoy, *melt_eros, *melt_conv;
+  double *bergy_src, *bergy_melt, *bergy_mass, *fl_bits_src, *fl_bits_melt;
+  double *melt_buoy_fl, *melt_eros_fl, *melt_conv_fl, *fl_parent_melt, *fl_child_melt;
+  double *stored_heat, *stored_ice /* (nid,njd,10) */, *real_calving, *tmp;
+  double *mass, *spread_mass, *spread_area, *ustar_iceberg, *spread_uvel, *spread_vvel;
+  int32_t* iceberg_counter_grd;
+  OBerg** list;
+  double minlon_c, maxlon_c;
+  int32_t current_year;
+  double current_yearday;
+  int visited;             /* "Visited" save variable, I:5110 */
+  int first_call_accum;    /* first_call in accumulate_calving I:6161 */
+  int restarted;
+  KidCounters cnt;
+  double dem_K_damp;
+  double constant_area, constant_radius;
+  double dem_tests_start_lon, dem_tests_end_lon;
+  int mts_part;
+  double mts_fast_dt;
+  int nthreads;
+  double tsec[4];
+  char err[512];
+  int fatal;
+  int warn_count;
+};
+
+#define IDX(o, i, j) ((size_t)((i) - (o)->d.isd) + (size_t)((j) - (o)->d.jsd) * (size_t)(o)->nid)
+#define G(o, a, i, j) ((o)->a[IDX(o, i, j)])
+
+static double now_sec(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+static void o_fatal(Oracle* o, const char* msg) {
+  if (!o->fatal) snprintf(o->err, sizeof(o->err), "%s", msg);
+  o->fatal = 1;
+}
+static void o_warn(Oracle* o, const char* msg) {
+  (void)msg;
+  o->warn_count++;
+}
+
+/* Fortran intrinsics */
+static inline double f_sign(double a, double b) { return (signbit(b) ? -fabs(a) : fabs(a)); }
+static inline double f_modulo(double a, double p) {
+  /* MODULO(a,p) = a - FLOOR(a/p)*p evaluated exactly (gfortran: fmod + sign fix-up) */
+  double r = fmod(a, p);
+  if (r != 0.0 && ((r < 0.0) != (p < 0.0))) r += p;
+  return r;
+}
+static inline double dmin(double a, double b) { return a < b ? a : b; }
+static inline double dmax(double a, double b) { return a > b ? a : b; }
+static inline int imin(int a, int b) { return a < b ? a : b; }
+static inline int imax(int a, int b) { return a > b ? a : b; }
+
+/* ------------------------------------------------------------------ ids */
+/* F:7276-7282 */
+int64_t oracle_id_from_2_ints(int32_t counter, int32_t ijhash) {
+  return (int64_t)counter * ((int64_t)1 << 32) + (int64_t)ijhash;
+}
+/* F:7285-7296 */
+void oracle_split_id(int64_t id, int32_t* counter, int32_t* ijhash) {
+  *counter = (int32_t)((uint64_t)id >> 32);
+  *ijhash = (int32_t)(id & 0xffffffffLL);
+}
+/* F:4431-4441 */
+double oracle_yearday(int32_t imon, int32_t iday, int32_t ihr, int32_t imin, int32_t isec) {
+  return (double)(imon - 1) * 31. + (double)(iday - 1) +
+         ((double)ihr + ((double)imin + (double)isec / 60.) / 60.) / 24.;
+}
+/* F:4224-4239 */
+static int32_t ij_component_of_id(const Oracle* o, int i, int j) {
+  int iNg = o->d.gni;
+  return i + (iNg * (j - 1));
+}
+/* F:4165-4179 */
+static int64_t generate_id(Oracle* o, int i, int j) {
+  G(o, iceberg_counter_grd, i, j) = G(o, iceberg_counter_grd, i, j) + 1;
+  return oracle_id_from_2_ints(G(o, iceberg_counter_grd, i, j), ij_component_of_id(o, i, j));
+}
+
+/* ------------------------------------------------------------ geometry */
+/* F:6558-6573 */
+double oracle_apply_modulo_around_point(double x, double y, double Lx) {
+  if (Lx > 0.) {
+    double Lx_2 = Lx / 2.;
+    return f_modulo(x - (y - Lx_2), Lx) + (y - Lx_2);
+  }
+  return x;
+}
+#define AMAP oracle_apply_modulo_around_point
+
+/* F:6163-6228 */
+static int sum_sign_dot_prod4(double x0, double y0, double x1, double y1, double x2, double y2,
+                              double x3, double y3, double x, double y, double Lx) {
+  double xx = AMAP(x, x0, Lx);
+  double xx0 = AMAP(x0, x0, Lx), xx1 = AMAP(x1, x0, Lx), xx2 = AMAP(x2, x0, Lx),
+         xx3 = AMAP(x3, x0, Lx);
+  double l0 = (xx - xx0) * (y1 - y0) - (y - y0) * (xx1 - xx0);
+  double l1 = (xx - xx1) * (y2 - y1) - (y - y1) * (xx2 - xx1);
+  double l2 = (xx - xx2) * (y3 - y2) - (y - y2) * (xx3 - xx2);
+  double l3 = (xx - xx3) * (y0 - y3) - (y - y3) * (xx0 - xx3);
+  /* S and E edges belong to the cell, N and W do not (F:6199-6206) */
+  double p0 = f_sign(1., l0); if (l0 == 0.) p0 = -0.5;
+  double p1 = f_sign(1., l1); if (l1 == 0.) p1 = 0.5;
+  double p2 = f_sign(1., l2); if (l2 == 0.) p2 = 0.5;
+  double p3 = f_sign(1., l3); if (l3 == 0.) p3 = -0.5;
+  if ((fabs(p0) + fabs(p2)) + (fabs(p1) + fabs(p3)) == fabs((p0 + p2) + (p1 + p3))) return 1;
+  return 0;
+}
+
+/* F:6231-6296 */
+static int sum_sign_dot_prod5(double x0, double y0, double x1, double y1, double x2, double y2,
+                              double x3, double y3, double x4, double y4, double x, double y,
+                              double Lx) {
+  double xx = AMAP(x, x0, Lx);
+  double xx0 = AMAP(x0, x0, Lx), xx1 = AMAP(x1, x0, Lx), xx2 = AMAP(x2, x0, Lx),
+         xx3 = AMAP(x3, x0, Lx), xx4 = AMAP(x4, x0, Lx);
+  double l0 = (xx - xx0) * (y1 - y0) - (y - y0) * (xx1 - xx0);
+  double l1 = (xx - xx1) * (y2 - y1) - (y - y1) * (xx2 - xx1);
+  double l2 = (xx - xx2) * (y3 - y2) - (y - y2) * (xx3 - xx2);
+  double l3 = (xx - xx3) * (y4 - y3) - (y - y3) * (xx4 - xx3);
+  double l4 = (xx - xx4) * (y0 - y4) - (y - y4) * (xx0 - xx4);
+  double p0 = f_sign(1., l0); if (l0 == 0.) p0 = 0.;
+  double p1 = f_sign(1., l1); if (l1 == 0.) p1 = 0.;
+  double p2 = f_sign(1., l2); if (l2 == 0.) p2 = 0.;
+  double p3 = f_sign(1., l3); if (l3 == 0.) p3 = 0.;
+  double p4 = f_sign(1., l4); if (l4 == 0.) p4 = 0.;
+  if (((fabs(p0) + fabs(p2)) + (fabs(p1) + fabs(p3))) + fabs(p4) -
+          fabs(((p0 + p2) + (p1 + p3)) + p4) < 0.5)
+    return 1;
+  return 0;
+}
+
+/* F:6076-6160 */
+static int is_point_in_cell(Oracle* o, double x, double y, int i, int j) {
+  const KidDomain* d = &o->d;
+  double Lx = o->p.Lx;
+  if (i - 1 < d->isd || i > d->ied || j - 1 < d->jsd || j > d->jed) {
+    o_fatal(o, "KID, is_point_in_cell: test is off the PE!");
+    return 0;
+  }
+  double a = AMAP(G(o, lon, i - 1, j - 1), x, Lx), b = AMAP(G(o, lon, i, j - 1), x, Lx),
+         c = AMAP(G(o, lon, i - 1, j), x, Lx), e = AMAP(G(o, lon, i, j), x, Lx);
+  double xlo = dmin(dmin(a, b), dmin(c, e));
+  double xhi = dmax(dmax(a, b), dmax(c, e));
+  double tol = 0.1;
+  if (x < (xlo - tol) || x > (xhi + tol)) return 0;
+  double y00 = G(o, lat, i - 1, j - 1), y10 = G(o, lat, i, j - 1), y01 = G(o, lat, i - 1, j),
+         y11 = G(o, lat, i, j);
+  double ylo = dmin(dmin(y00, y10), dmin(y01, y11));
+  double yhi = dmax(dmax(y00, y10), dmax(y01, y11));
+  if (y < ylo || y > yhi) return 0;
+  double x00 = G(o, lon, i - 1, j - 1), x10 = G(o, lon, i, j - 1), x01 = G(o, lon, i - 1, j),
+         x11 = G(o, lon, i, j);
+  int ll = o->p.grid_is_latlon;
+  if ((y11 > 89.999) && ll) {
+    return sum_sign_dot_prod5(x00, y00, x10, y10, x10, y11, x01, y11, x01, y01, x, y, Lx);
+  } else if ((y01 > 89.999) && ll) {
+    return sum_sign_dot_prod5(x00, y00, x10, y10, x11, y11, x11, y01, x00, y01, x, y, Lx);
+  } else if ((y00 > 89.999) && ll) {
+    return sum_sign_dot_prod5(x01, y00, x10, y00, x10, y10, x11, y11, x01, y01, x, y, Lx);
+  } else if ((y10 > 89.999) && ll) {
+    return sum_sign_dot_prod5(x00, y00, x00, y10, x11, y10, x11, y11, x01, y01, x, y, Lx);
+  }
+  return sum_sign_dot_prod4(x00, y00, x10, y10, x11, y11, x01, y01, x, y, Lx);
+}
+
+/* F:6439-6534 */
+static void calc_xiyj(Oracle* o, double x1, double x2, double x3, double x4, double y1, double y2,
+                      double y3, double y4, double x, double y, double* xi, double* yj, double Lx) {
+  double alpha = x2 - x1, delta = y2 - y1, beta = x4 - x1, epsilon = y4 - y1;
+  double gamma = (x3 - x1) - (alpha + beta);
+  double kappa = (y3 - y1) - (delta + epsilon);
+  double a = (kappa * beta - gamma * epsilon);
+  double dx = AMAP(x, x1, Lx) - x1;
+  double dy = y - y1;
+  double b = (delta * beta - alpha * epsilon) - (kappa * dx - gamma * dy);
+  double c = (alpha * dy - delta * dx);
+  if (fabs(a) > 1.e-12) {
+    double d = 0.25 * (b * b) - a * c;
+    if (d >= 0.) {
+      double yy1 = -(0.5 * b + sqrt(d)) / a;
+      double yy2 = -(0.5 * b - sqrt(d)) / a;
+      if (fabs(yy1 - 0.5) < fabs(yy2 - 0.5)) *yj = yy1; else *yj = yy2;
+    } else {
+      o_fatal(o, "KID, calc_xiyj: We have complex roots. The grid must be very distorted!");
+      *yj = 0.;
+    }
+  } else {
+    if (b != 0.) *yj = -c / b; else *yj = 0.;
+  }
+  a = (alpha + gamma * (*yj));
+  b = (delta + kappa * (*yj));
+  if (a != 0.) {
+    *xi = (dx - beta * (*yj)) / a;
+  } else if (b != 0.) {
+    *xi = (dy - epsilon * (*yj)) / b;
+  } else {
+    c = (epsilon * alpha - beta * delta) + (epsilon * gamma - beta * kappa) * (*yj);
+    if (c != 0.) {
+      *xi = (epsilon * dx - beta * dy) / c;
+    } else {
+      o_fatal(o, "KID, calc_xiyj: Can not invert either linear equaton for xi!");
+      *xi = 0.;
+    }
+  }
+}
+
+/* F:6540-6552 */
+static int is_point_within_xi_yj_bounds(double xi, double yj) {
+  if ((xi >= 0) && (xi < 1))
+    if ((yj >= 0) && (yj < 1)) return 1;
+  return 0;
+}
+
+/* F:6299-6436 */
+static int pos_within_cell(Oracle* o, double x, double y, int i, int j, double* xi, double* yj) {
+  const KidDomain* d = &o->d;
+  double Lx = o->p.Lx;
+  double pi_180 = o->p.pi / 180.;
+  *xi = -999.; *yj = -999.;
+  if (i - 1 < d->isd) return 0;
+  if (j - 1 < d->jsd) return 0;
+  if (i > d->ied) return 0;
+  if (j > d->jed) return 0;
+  double x1 = G(o, lon, i - 1, j - 1), y1 = G(o, lat, i - 1, j - 1);
+  double x2 = G(o, lon, i, j - 1), y2 = G(o, lat, i, j - 1);
+  double x3 = G(o, lon, i, j), y3 = G(o, lat, i, j);
+  double x4 = G(o, lon, i - 1, j), y4 = G(o, lat, i - 1, j);
+  if ((!o->p.grid_is_latlon) && (o->p.grid_is_regular)) {
+    double dx = fabs((G(o, lon, i, j) - G(o, lon, i - 1, j)));
+    double dy = fabs((G(o, lat, i, j) - G(o, lat, i, j - 1)));
+    x1 = G(o, lon, i, j) - (dx / 2);
+    y1 = G(o, lat, i, j) - (dy / 2);
+    double Delta_x = AMAP(x, x1, Lx) - x1;
+    *xi = ((Delta_x) / dx) + 0.5;
+    *yj = ((y - y1) / dy) + 0.5;
+  } else if ((dmax(dmax(y1, y2), dmax(y3, y4)) < 89.999) || (!o->p.grid_is_latlon)) {
+    calc_xiyj(o, x1, x2, x3, x4, y1, y2, y3, y4, x, y, xi, yj, Lx);
+  } else {
+    /* polar cell: tangent plane with co-latitude as radial coordinate F:6359-6405 */
+    double xx = (90. - y) * cos(x * pi_180);
+    double yy = (90. - y) * sin(x * pi_180);
+    double tx1 = (90. - y1) * cos(G(o, lon, i - 1, j - 1) * pi_180);
+    double ty1 = (90. - y1) * sin(G(o, lon, i - 1, j - 1) * pi_180);
+    double tx2 = (90. - y2) * cos(G(o, lon, i, j - 1) * pi_180);
+    double ty2 = (90. - y2) * sin(G(o, lon, i, j - 1) * pi_180);
+    double tx3 = (90. - y3) * cos(G(o, lon, i, j) * pi_180);
+    double ty3 = (90. - y3) * sin(G(o, lon, i, j) * pi_180);
+    double tx4 = (90. - y4) * cos(G(o, lon, i - 1, j) * pi_180);
+    double ty4 = (90. - y4) * sin(G(o, lon, i - 1, j) * pi_180);
+    calc_xiyj(o, tx1, tx2, tx3, tx4, ty1, ty2, ty3, ty4, xx, yy, xi, yj, Lx);
+    if (is_point_in_cell(o, x, y, i, j)) {
+      if (!is_point_within_xi_yj_bounds(*xi, *yj)) {
+        double fac = 2.1 * dmax(fabs(*xi - 0.5), fabs(*yj - 0.5));
+        fac = dmax(1., fac);
+        *xi = 0.5 + (*xi - 0.5) / fac;
+        *yj = 0.5 + (*yj - 0.5) / fac;
+      }
+    } else {
+      if (fabs(*xi - 0.5) < 0.5 && fabs(*yj - 0.5) < 0.5)
+        o_fatal(o, "KID, pos_within_cell: not in cell but coordinates <0.5!");
+    }
+  }
+  return is_point_in_cell(o, x, y, i, j);
+}
+
+/* F:7071-7088 */
+static double bilin(const Oracle* o, const double* fld, int i, int j, double xi, double yj) {
+  if (o->p.old_bug_bilin) {
+    return (fld[IDX(o, i, j)] * (1. - xi) + fld[IDX(o, i - 1, j)] * xi) * (1. - yj) +
+           (fld[IDX(o, i, j - 1)] * (1. - xi) + fld[IDX(o, i - 1, j - 1)] * xi) * yj;
+  }
+  return (fld[IDX(o, i, j)] * xi + fld[IDX(o, i - 1, j)] * (1. - xi)) * yj +
+         (fld[IDX(o, i, j - 1)] * xi + fld[IDX(o, i - 1, j - 1)] * (1. - xi)) * (1. - yj);
+}
+
+/* F:6011-6041 */
+static int find_cell(Oracle* o, double x, double y, int* oi, int* oj) {
+  const KidDomain* d = &o->d;
+  *oi = (int)floor((x - G(o, lon, d->isd, d->jsd)) /
+                   (G(o, lon, d->isd + 1, d->jsd + 1) - G(o, lon, d->isd, d->jsd))) + d->isd + 1;
+  *oj = (int)floor((y - G(o, lat, d->isd, d->jsd)) /
+                   (G(o, lat, d->isd + 1, d->jsd + 1) - G(o, lat, d->isd, d->jsd))) + d->jsd + 1;
+  if (*oi > d->isc - 1 && *oi < d->iec + 1 && *oj > d->jsc - 1 && *oj < d->jec + 1)
+    if (is_point_in_cell(o, x, y, *oi, *oj)) return 1;
+  *oi = -999; *oj = -999;
+  for (int j = d->jsc; j <= d->jec; j++)
+    for (int i = d->isc; i <= d->iec; i++)
+      if (is_point_in_cell(o, x, y, i, j)) { *oi = i; *oj = j; return 1; }
+  return 0;
+}
+
+/* F:6044-6073 */
+static int find_cell_wide(Oracle* o, double x, double y, int* oi, int* oj) {
+  const KidDomain* d = &o->d;
+  *oi = (int)floor((x - G(o, lon, d->isd, d->jsd)) /
+                   (G(o, lon, d->isd + 1, d->jsd + 1) - G(o, lon, d->isd, d->jsd))) + d->isd + 1;
+  *oj = (int)floor((y - G(o, lat, d->isd, d->jsd)) /
+                   (G(o, lat, d->isd + 1, d->jsd + 1) - G(o, lat, d->isd, d->jsd))) + d->jsd + 1;
+  if (!(*oi - 1 < d->isd || *oi > d->ied || *oj - 1 < d->jsd || *oj > d->jed))
+    if (is_point_in_cell(o, x, y, *oi, *oj)) return 1;
+  *oi = -999; *oj = -999;
+  for (int j = d->jsd + 1; j <= d->jed; j++)
+    for (int i = d->isd + 1; i <= d->ied; i++)
+      if (is_point_in_cell(o, x, y, i, j)) { *oi = i; *oj = j; return 1; }
+  return 0;
+}
+
+/* ------------------------------------------------------- list handling */
+/* F:4318-4359 */
+static int inorder(const OBerg* b1, const OBerg* b2) {
+  if (b1->start_year < b2->start_year) return 1; else if (b1->start_year > b2->start_year) return 0;
+  if (b1->start_day < b2->start_day) return 1; else if (b1->start_day > b2->start_day) return 0;
+  if (b1->start_mass < b2->start_mass) return 1; else if (b1->start_mass > b2->start_mass) return 0;
+  if (b1->start_lon < b2->start_lon) return 1; else if (b1->start_lon > b2->start_lon) return 0;
+  if (b1->start_lat < b2->start_lat) return 1; else if (b1->start_lat > b2->start_lat) return 0;
+  return 1;
+}
+
+/* F:4270-4313 with parallel_reprod=.true. (F:33) */
+static void insert_berg_into_list(OBerg** first, OBerg* nb) {
+  if (*first) {
+    if (inorder(nb, *first)) {
+      nb->next = *first; nb->prev = NULL; (*first)->prev = nb; *first = nb;
+    } else {
+      OBerg *this_ = *first, *prev = NULL;
+      while (this_) {
+        if (inorder(nb, this_)) break;
+        prev = this_; this_ = this_->next;
+      }
+      prev->next = nb; nb->prev = prev;
+      if (this_) this_->prev = nb;
+      nb->next = this_;
+    }
+  } else {
+    *first = nb; nb->next = NULL; nb->prev = NULL;
+  }
+}
+
+static void free_bonds(OBerg* b) {
+  OBond* c = b->first_bond;
+  while (c) { OBond* n = c->next_bond; free(c); c = n; }
+  b->first_bond = NULL;
+}
+
+/* F:3430-3465 */
+static void clear_berg_from_partners_bonds(Oracle* o, OBerg* berg) {
+  for (OBond* cb = berg->first_bond; cb; cb = cb->next_bond) {
+    OBerg* other = cb->other_berg;
+    if (other) {
+      OBond* mb = other->first_bond;
+      while (mb) {
+        if (mb->other_id == berg->id) {
+          mb->other_berg = NULL;
+          mb = NULL;
+          if (o->p.iceberg_bonds_on) if (other->n_bonds > 0) other->n_bonds--;
+        } else {
+          mb = mb->next_bond;
+        }
+      }
+    }
+  }
+}
+
+/* F:4481-4514 */
+static void delete_iceberg_from_list(Oracle* o, OBerg** first, OBerg* berg) {
+  if (berg->prev) berg->prev->next = berg->next; else *first = berg->next;
+  if (berg->next) berg->next->prev = berg->prev;
+  clear_berg_from_partners_bonds(o, berg);
+  free_bonds(berg);
+  free(berg);
+}
+
+static OBerg* new_berg_copy(const OBerg* vals) {
+  OBerg* b = (OBerg*)malloc(sizeof(OBerg));
+  *b = *vals;
+  b->prev = b->next = NULL;
+  return b;
+}
+
+/* F:1758-1797 */
+static void move_berg_between_cells(Oracle* o) {
+  const KidDomain* d = &o->d;
+  for (int grdj = d->jsd; grdj <= d->jed; grdj++)
+    for (int grdi = d->isd; grdi <= d->ied; grdi++) {
+      OBerg* this_ = G(o, list, grdi, grdj);
+      while (this_) {
+        if ((this_->ine != grdi) || (this_->jne != grdj)) {
+          OBerg* mv = this_;
+          this_ = this_->next;
+          if (mv->prev) mv->prev->next = mv->next; else G(o, list, grdi, grdj) = mv->next;
+          if (mv->next) mv->next->prev = mv->prev;
+          if (mv->ine < d->isd || mv->ine > d->ied || mv->jne < d->jsd || mv->jne > d->jed) {
+            o_fatal(o, "move_berg_between_cells: berg index outside data domain");
+            free_bonds(mv); free(mv);
+            continue;
+          }
+          insert_berg_into_list(&G(o, list, mv->ine, mv->jne), mv);
+        } else {
+          this_ = this_->next;
+        }
+      }
+    }
+}
+
+/* ------------------------------------------------ interpolation I:4718 */
+/* I:4903-4913 */
+static double ddx_ssh(const Oracle* o, int i, int j) {
+  double dxp = 0.5 * (G(o, dx, i + 1, j) + G(o, dx, i + 1, j - 1));
+  double dx0 = 0.5 * (G(o, dx, i, j) + G(o, dx, i, j - 1));
+  return 2. * (G(o, ssh, i + 1, j) - G(o, ssh, i, j)) / (dx0 + dxp) * G(o, msk, i + 1, j) *
+         G(o, msk, i, j);
+}
+/* I:4916-4926 */
+static double ddy_ssh(const Oracle* o, int i, int j) {
+  double dyp = 0.5 * (G(o, dy, i, j + 1) + G(o, dy, i - 1, j + 1));
+  double dy0 = 0.5 * (G(o, dy, i, j) + G(o, dy, i - 1, j));
+  return 2. * (G(o, ssh, i, j + 1) - G(o, ssh, i, j)) / (dy0 + dyp) * G(o, msk, i, j + 1) *
+         G(o, msk, i, j);
+}
+/* I:4953-4967 */
+static void rotate(double* u, double* v, double cos_rot, double sin_rot) {
+  double u_old = *u, v_old = *v;
+  *u = cos_rot * u_old + sin_rot * v_old;
+  *v = cos_rot * v_old - sin_rot * u_old;
+}
+
+/* F:7163-7252 */
+static double quad_interp_from_agrid(Oracle* o, const double* fld, double x, double y, int i, int j,
+                                     double xi, double yj) {
+  int is, ie, js, je;
+  int mind = 1; /* rev_mind=.false. F:59 */
+  double pi_180 = o->p.pi / 180.;
+  /* Fortran mod(i,2): sign follows i */
+  if ((i % 2) == mind) { if (xi >= 0.5) { is = i; ie = i + 2; } else { is = i - 2; ie = i; } }
+  else { is = i - 1; ie = i + 1; }
+  if ((j % 2) == mind) { if (yj >= 0.5) { js = j; je = j + 2; } else { js = j - 2; je = j; } }
+  else { js = j - 1; je = j + 1; }
+  double x1 = G(o, lonc, is, js), y1 = G(o, latc, is, js);
+  double x2 = G(o, lonc, ie, js), y2 = G(o, latc, ie, js);
+  double x3 = G(o, lonc, ie, je), y3 = G(o, latc, ie, je);
+  double x4 = G(o, lonc, is, je), y4 = G(o, latc, is, je);
+  double xloc, yloc;
+  if ((!o->p.grid_is_latlon) && (o->p.grid_is_regular)) {
+    double dx = fabs(x3 - x4), dy = fabs(y3 - y2);
+    x1 = x3 - (dx / 2); y1 = y3 - (dy / 2);
+    double Delta_x = AMAP(x, x1, o->p.Lx) - x1;
+    xloc = ((Delta_x) / dx) + 0.5; yloc = ((y - y1) / dy) + 0.5;
+  } else if ((dmax(dmax(y1, y2), dmax(y3, y4)) < 89.999) || (!o->p.grid_is_latlon)) {
+    calc_xiyj(o, x1, x2, x3, x4, y1, y2, y3, y4, x, y, &xloc, &yloc, o->p.Lx);
+  } else {
+    double xx = (90. - y) * cos(x * pi_180), yy = (90. - y) * sin(x * pi_180);
+    x1 = (90. - y1) * cos(G(o, lon, is, js) * pi_180); y1 = (90. - y1) * sin(G(o, lon, is, js) * pi_180);
+    x2 = (90. - y2) * cos(G(o, lon, ie, je) * pi_180); y2 = (90. - y2) * sin(G(o, lon, ie, je) * pi_180);
+    x3 = (90. - y3) * cos(G(o, lon, ie, je) * pi_180); y3 = (90. - y3) * sin(G(o, lon, ie, je) * pi_180);
+    x4 = (90. - y4) * cos(G(o, lon, is, je) * pi_180); y4 = (90. - y4) * sin(G(o, lon, is, je) * pi_180);
+    calc_xiyj(o, x1, x2, x3, x4, y1, y2, y3, y4, xx, yy, &xloc, &yloc, o->p.Lx);
+  }
+  xloc = xloc * 2 - 1; yloc = yloc * 2 - 1;
+  double xb[3], yb[3];
+  xb[0] = 0.5 * xloc * (xloc - 1); yb[0] = 0.5 * yloc * (yloc - 1);
+  xb[1] = (1 + xloc) * (1 - xloc); yb[1] = (1 + yloc) * (1 - yloc);
+  xb[2] = 0.5 * xloc * (xloc + 1); yb[2] = 0.5 * yloc * (yloc + 1);
+  /* sum() over the 3x3 array in Fortran array-element (column-major) order */
+  double s = 0.;
+  for (int b = 0; b < 3; b++)
+    for (int a = 0; a < 3; a++) s += xb[a] * yb[b] * fld[IDX(o, is + a, js + b)];
+  return s;
+}
+
+/* I:4718-4900 */
+static void interp_flds(Oracle* o, double x, double y, int i, int j, double xi, double yj,
+                        double rx, double ry, double* uo, double* vo, double* ui, double* vi,
+                        double* ua, double* va, double* ssh_x, double* ssh_y, double* sst,
+                        double* sss, double* cn, double* hi, double* od) {
+  (void)rx; (void)ry;
+  double cos_rot = bilin(o, o->cosr, i, j, xi, yj);
+  double sin_rot = bilin(o, o->sinr, i, j, xi, yj);
+  *uo = bilin(o, o->uo, i, j, xi, yj);
+  *vo = bilin(o, o->vo, i, j, xi, yj);
+  *ui = bilin(o, o->ui, i, j, xi, yj);
+  *vi = bilin(o, o->vi, i, j, xi, yj);
+  *ua = bilin(o, o->ua, i, j, xi, yj);
+  *va = bilin(o, o->va, i, j, xi, yj);
+  if (o->p.coastal_drift > 0.) {
+    double cd = o->p.coastal_drift;
+    *uo = *uo + cd * (G(o, msk, i + 1, j) - G(o, msk, i - 1, j)) * G(o, msk, i, j);
+    *ui = *ui + cd * (G(o, msk, i + 1, j) - G(o, msk, i - 1, j)) * G(o, msk, i, j);
+    *vo = *vo + cd * (G(o, msk, i, j + 1) - G(o, msk, i, j - 1)) * G(o, msk, i, j);
+    *vi = *vi + cd * (G(o, msk, i, j + 1) - G(o, msk, i, j - 1)) * G(o, msk, i, j);
+  }
+  /* tidal_drift needs the FMS Mersenne twister (external): rejected at create */
+  *sst = G(o, sst, i, j);
+  *sss = G(o, sss, i, j);
+  *cn = G(o, cn, i, j);
+  *hi = G(o, hi, i, j);
+  double hxp, hxm;
+  if (yj >= 0.5) {
+    hxp = (yj - 0.5) * ddx_ssh(o, i, j + 1) + (1.5 - yj) * ddx_ssh(o, i, j);
+    hxm = (yj - 0.5) * ddx_ssh(o, i - 1, j + 1) + (1.5 - yj) * ddx_ssh(o, i - 1, j);
+  } else {
+    hxp = (yj + 0.5) * ddx_ssh(o, i, j) + (0.5 - yj) * ddx_ssh(o, i, j - 1);
+    hxm = (yj + 0.5) * ddx_ssh(o, i - 1, j) + (0.5 - yj) * ddx_ssh(o, i - 1, j - 1);
+  }
+  *ssh_x = xi * hxp + (1. - xi) * hxm;
+  if (xi >= 0.5) {
+    hxp = (xi - 0.5) * ddy_ssh(o, i + 1, j) + (1.5 - xi) * ddy_ssh(o, i, j);
+    hxm = (xi - 0.5) * ddy_ssh(o, i + 1, j - 1) + (1.5 - xi) * ddy_ssh(o, i, j - 1);
+  } else {
+    hxp = (xi + 0.5) * ddy_ssh(o, i, j) + (0.5 - xi) * ddy_ssh(o, i - 1, j);
+    hxm = (xi + 0.5) * ddy_ssh(o, i, j - 1) + (0.5 - xi) * ddy_ssh(o, i - 1, j - 1);
+  }
+  *ssh_y = yj * hxp + (1. - yj) * hxm;
+  rotate(uo, vo, cos_rot, sin_rot);
+  rotate(ui, vi, cos_rot, sin_rot);
+  rotate(ua, va, cos_rot, sin_rot);
+  rotate(ssh_x, ssh_y, cos_rot, sin_rot);
+  if (*ssh_x != *ssh_x) *ssh_x = 0.;
+  if (*ssh_y != *ssh_y) *ssh_y = 0.;
+  if ((*uo != *uo) || (*vo != *vo) || (*ui != *ui) || (*vi != *vi) || (*ua != *ua) ||
+      (*va != *va) || (*sst != *sst) || (*sss != *sss) || (*cn != *cn) || (*hi != *hi)) {
+    o_fatal(o, "KID, interp fields: field interpaolations has NaNs");
+  }
+  if (od) {
+    if (o->p.mts) {
+      /* A68_test is a driver-specific hack (I:4885): not restated */
+      size_t n = (size_t)o->nid * o->njd;
+      for (size_t k = 0; k < n; k++) o->tmp[k] = o->ocean_depth[k] + o->ssh[k];
+      *od = quad_interp_from_agrid(o, o->tmp, x, y, i, j, xi, yj);
+    } else {
+      *od = G(o, ocean_depth, i, j) + G(o, ssh, i, j);
+    }
+  }
+}
+
+/* I:444-477 */
+static void convert_from_grid_to_meters(const Oracle* o, double lat_ref, double* dx_dlon,
+                                        double* dy_dlat) {
+  double pi = o->p.pi;
+  if (o->p.grid_is_latlon) {
+    *dx_dlon = (pi / 180.) * o->p.Rearth * cos((lat_ref) * (pi / 180.));
+    *dy_dlat = (pi / 180.) * o->p.Rearth;
+  } else { *dx_dlon = 1.; *dy_dlat = 1.; }
+}
+static void convert_from_meters_to_grid(const Oracle* o, double lat_ref, double* dlon_dx,
+                                        double* dlat_dy) {
+  double pi = o->p.pi;
+  if (o->p.grid_is_latlon) {
+    *dlon_dx = (180. / pi) / (o->p.Rearth * cos((lat_ref) * (pi / 180.)));
+    *dlat_dy = (180. / pi) / o->p.Rearth;
+  } else { *dlon_dx = 1.; *dlat_dy = 1.; }
+}
+
+/* ---------------------------------------------------- interactions I:480 */
+typedef struct IAcc { double IA_x, IA_y, P11, P12, P21, P22, Pu_x, Pu_y; } IAcc;
+
+/* I:611-804 */
+static void calculate_force(Oracle* o, OBerg* berg, OBerg* other, IAcc* A, double u0, double v0,
+                            double u1, double v1, int bonded, int has_c_crit, int c_crit_dist) {
+  const KidParams* p = &o->p;
+  if ((berg->id != other->id) && (berg->fl_k != -1) && (other->fl_k != -1)) {
+    double T1 = berg->thickness, lon1 = berg->lon_old, lat1 = berg->lat_old;
+    double T2 = other->thickness, lon2 = other->lon_old, lat2 = other->lat_old;
+    double u2 = other->uvel_old, v2 = other->vvel_old;
+    double A1, A2, M1, M2;
+    if (p->constant_interaction_LW && p->mts && bonded) {
+      A1 = p->constant_length * p->constant_width; M1 = A1 * T1 * p->rho_bergs;
+      A2 = A1; M2 = A2 * T2 * p->rho_bergs;
+    } else {
+      double L1 = berg->length, W1 = berg->width; M1 = berg->mass; A1 = L1 * W1;
+      double L2 = other->length, W2 = other->width; M2 = other->mass; A2 = L2 * W2;
+    }
+    double dlon = lon1 - lon2, dlat = lat1 - lat2;
+    double lat_ref = 0.5 * (lat1 + lat2), dx_dlon, dy_dlat;
+    convert_from_grid_to_meters(o, lat_ref, &dx_dlon, &dy_dlat);
+    double r_dist_x = dlon * dx_dlon, r_dist_y = dlat * dy_dlat;
+    double r_dist = sqrt((r_dist_x * r_dist_x) + (r_dist_y * r_dist_y));
+    double R1, R2;
+    if (p->hexagonal_icebergs) {
+      R1 = sqrt(A1 / (2. * sqrt(3.))); R2 = sqrt(A2 / (2. * sqrt(3.)));
+    } else if (p->iceberg_bonds_on) {
+      R1 = 0.5 * sqrt(A1); R2 = 0.5 * sqrt(A2);
+    } else {
+      R1 = sqrt(A1 / p->pi); R2 = sqrt(A2 / p->pi);
+    }
+    double M_min = dmin(M1, M2);
+    double crit_dist, spring_coef;
+    if (bonded) {
+      crit_dist = R1 + R2; spring_coef = p->spring_coef;
+    } else {
+      spring_coef = p->contact_spring_coef;
+      if (has_c_crit) {
+        if (c_crit_dist) { crit_dist = R1 + R2; spring_coef = p->spring_coef; }
+        else crit_dist = dmax(R1 + R2, p->contact_distance);
+      } else crit_dist = dmax(R1 + R2, p->contact_distance);
+    }
+    double radial_damping_coef = p->radial_damping_coef;
+    double tangental_damping_coef = p->tangental_damping_coef;
+    if (p->critical_interaction_damping_on) {
+      radial_damping_coef = 2. * sqrt(spring_coef);
+      if (p->tang_crit_int_damp_on) tangental_damping_coef = (2. * sqrt(spring_coef)) / 4;
+    }
+    int tbonded = bonded;
+    if (bonded && !(p->mts || (p->contact_distance > 0.) ||
+                    (p->contact_spring_coef != p->spring_coef))) {
+      if (!(r_dist > crit_dist)) tbonded = 0;
+    }
+    if ((r_dist > 0.) && (tbonded || (r_dist < crit_dist && !bonded))) {
+      double accel_spring = spring_coef * (M_min / M1) * (crit_dist - r_dist);
+      A->IA_x = A->IA_x + (accel_spring * (r_dist_x / r_dist));
+      A->IA_y = A->IA_y + (accel_spring * (r_dist_y / r_dist));
+      double r2 = r_dist * r_dist;
+      double P_11 = (r_dist_x * r_dist_x) / r2, P_12 = (r_dist_x * r_dist_y) / r2;
+      double P_21 = (r_dist_x * r_dist_y) / r2, P_22 = (r_dist_y * r_dist_y) / r2;
+      double p_ia_coef = radial_damping_coef * (M_min / M1);
+      if (p->scale_damping_by_pmag) {
+        double a1 = ((P_11 * (u2 - u1)) + (P_12 * (v2 - v1)));
+        double a2 = ((P_12 * (u2 - u1)) + (P_22 * (v2 - v1)));
+        double b1 = ((P_11 * (u2 - u0)) + (P_12 * (v2 - v0)));
+        double b2 = ((P_12 * (u2 - u0)) + (P_22 * (v2 - v0)));
+        p_ia_coef = p_ia_coef * (0.5 * (sqrt((a1 * a1) + (a2 * a2)) + sqrt((b1 * b1) + (b2 * b2))));
+      }
+      A->P11 += p_ia_coef * P_11; A->P12 += p_ia_coef * P_12;
+      A->P21 += p_ia_coef * P_21; A->P22 += p_ia_coef * P_22;
+      A->Pu_x += (p_ia_coef * ((P_11 * u2) + (P_12 * v2)));
+      A->Pu_y += (p_ia_coef * ((P_12 * u2) + (P_22 * v2)));
+      P_11 = 1 - P_11; P_12 = -P_12; P_21 = -P_21; P_22 = 1 - P_22;
+      p_ia_coef = tangental_damping_coef * (M_min / M1);
+      if (p->scale_damping_by_pmag) {
+        double a1 = ((P_11 * (u2 - u1)) + (P_12 * (v2 - v1)));
+        double a2 = ((P_12 * (u2 - u1)) + (P_22 * (v2 - v1)));
+        double b1 = ((P_11 * (u2 - u0)) + (P_12 * (v2 - v0)));
+        double b2 = ((P_12 * (u2 - u0)) + (P_22 * (v2 - v0)));
+        p_ia_coef = p_ia_coef * (0.5 * (sqrt((a1 * a1) + (a2 * a2)) + sqrt((b1 * b1) + (b2 * b2))));
+      }
+      A->P11 += p_ia_coef * P_11; A->P12 += p_ia_coef * P_12;
+      A->P21 += p_ia_coef * P_21; A->P22 += p_ia_coef * P_22;
+      A->Pu_x += (p_ia_coef * ((P_11 * u2) + (P_12 * v2)));
+      A->Pu_y += (p_ia_coef * ((P_12 * u2) + (P_22 * v2)));
+    }
+  }
+}
+
+/* I:480-607 */
+static void interactive_force(Oracle* o, OBerg* berg, IAcc* A, double u0, double v0, double u1,
+                              double v1) {
+  const KidParams* p = &o->p;
+  const KidDomain* d = &o->d;
+  memset(A, 0, sizeof(*A));
+  if (berg->fl_k == -1) return;
+  int nc_x = p->contact_cells_lon, nc_y = p->contact_cells_lat;
+  if (p->mts || (p->contact_distance > 0.) || (p->contact_spring_coef != p->spring_coef)) {
+    if ((!p->mts) || (p->mts && o->mts_part == 3)) {
+      if (p->iceberg_bonds_on) {
+        for (OBond* cb = berg->first_bond; cb; cb = cb->next_bond) {
+          OBerg* other = cb->other_berg;
+          if (!other) { o_fatal(o, "KID,bond interactions: unassosiated berg!"); continue; }
+          calculate_force(o, berg, other, A, u0, v0, u1, v1, 1, 0, 0);
+          other->id = -other->id;
+        }
+        for (int grdj = imax(berg->jne - 2, d->jsd + 1); grdj <= imin(berg->jne + 2, d->jed); grdj++)
+          for (int grdi = imax(berg->ine - 2, d->isd + 1); grdi <= imin(berg->ine + 2, d->ied); grdi++)
+            for (OBerg* ob = G(o, list, grdi, grdj); ob; ob = ob->next)
+              if (ob->id > 0 && ob->conglom_id == berg->conglom_id)
+                calculate_force(o, berg, ob, A, u0, v0, u1, v1, 0, 1, 1);
+        for (OBond* cb = berg->first_bond; cb; cb = cb->next_bond)
+          if (cb->other_berg) cb->other_berg->id = llabs(cb->other_berg->id);
+      }
+    }
+    if (!(p->mts && o->mts_part == 3)) {
+      for (int grdj = imax(berg->jne - nc_y, d->jsd); grdj <= imin(berg->jne + nc_y, d->jed); grdj++)
+        for (int grdi = imax(berg->ine - nc_x, d->isd); grdi <= imin(berg->ine + nc_x, d->ied); grdi++)
+          for (OBerg* ob = G(o, list, grdi, grdj); ob; ob = ob->next)
+            if (ob->conglom_id != berg->conglom_id)
+              calculate_force(o, berg, ob, A, u0, v0, u1, v1, 0, 0, 0);
+    }
+  } else {
+    for (int grdj = berg->jne - 1; grdj <= berg->jne + 1; grdj++)
+      for (int grdi = berg->ine - 1; grdi <= berg->ine + 1; grdi++) {
+        if (grdi < d->isd || grdi > d->ied || grdj < d->jsd || grdj > d->jed) continue; /* Fortran would be out of bounds */
+        for (OBerg* ob = G(o, list, grdi, grdj); ob; ob = ob->next)
+          calculate_force(o, berg, ob, A, u0, v0, u1, v1, 0, 0, 0);
+      }
+    if (p->iceberg_bonds_on) {
+      for (OBond* cb = berg->first_bond; cb; cb = cb->next_bond) {
+        OBerg* other = cb->other_berg;
+        if (!other) { o_fatal(o, "KID,bond interactions: unassosiated berg!"); continue; }
+        calculate_force(o, berg, other, A, u0, v0, u1, v1, 1, 0, 0);
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------ accel I:1950 */
+typedef struct Env { double uo, vo, ui, vi, ua, va, ssh_x, ssh_y, sst, sss, cn, hi, od; } Env;
+
+/* The arithmetic core of accel() once the environment is known: I:2002-2301,
+ * 2304-2323, 2436-2440.  `berg` may be NULL when called from oracle_accel_free
+ * (then interactions/bonds are off). */
+static void accel_core(Oracle* o, const KidParams* p, OBerg* berg, double M, double T, double W,
+                       double L, double lat, double uvel, double vvel, double uvel0, double vvel0,
+                       double dt, Env e, double loc_dx, double* ax, double* ay, double* axn,
+                       double* ayn, double* bxn, double* byn, int* speeding) {
+  const double Cr0 = 0.06;
+  int Runge_not_Verlet = p->runge_not_verlet;
+  int interactive = p->interactive_icebergs_on && berg != NULL;
+  int use_new_pc = p->use_new_predictive_corrective;
+  double alpha = 0.0, beta = 1.0, C_N = 0.0;
+  if (!Runge_not_Verlet) { alpha = 1.0; C_N = 1.0; beta = 1.0; use_new_pc = 1; }
+  double u_star = uvel0 + (*axn * (dt / 2.));
+  double v_star = vvel0 + (*ayn * (dt / 2.));
+  double uo = e.uo, vo = e.vo, ui = e.ui, vi = e.vi, ua = e.ua, va = e.va, ssh_x = e.ssh_x,
+         ssh_y = e.ssh_y, hi = e.hi, od = e.od;
+  double pi_180 = p->pi / 180.;
+  double f_cori;
+  if ((p->grid_is_latlon) && (!p->use_f_plane)) f_cori = (2. * p->omega) * sin(pi_180 * lat);
+  else f_cori = (2. * p->omega) * sin(pi_180 * p->lat_ref);
+  double D = (p->rho_bergs / RHO_SEAWATER) * T;
+  double F = T - D;
+  *axn = 0.; *ayn = 0.; *bxn = 0.; *byn = 0.;
+  hi = dmin(hi, D);
+  double D_hi = dmax(0., D - hi);
+  double groundfrac, c_gnd;
+  if (p->h_to_init_grounding > 0.0) {
+    groundfrac = 1.0 - (od - D) / p->h_to_init_grounding;
+    groundfrac = dmax(groundfrac, 0.0); groundfrac = dmin(groundfrac, 1.0);
+  } else {
+    if (D > od) groundfrac = 1.0; else groundfrac = 0.0;
+  }
+  if (groundfrac > 0.0) c_gnd = (p->cdrag_grounding * W * L * groundfrac) / M; else c_gnd = 0.0;
+  double uwave = ua - uo, vwave = va - vo;
+  double wmod = uwave * uwave + vwave * vwave;
+  double ampl = 0.5 * 0.02025 * wmod;
+  double Lwavelength = 0.32 * wmod;
+  double Lcutoff = 0.125 * Lwavelength;
+  double Ltop = 0.25 * Lwavelength;
+  double Cr = Cr0 * dmin(dmax(0., (L - Lcutoff) / ((Ltop - Lcutoff) + 1.e-30)), 1.);
+  double wave_rad = 0.5 * RHO_SEAWATER / M * Cr * GRAVITY * ampl * dmin(ampl, F) * (2. * W * L) / (W + L);
+  wmod = sqrt(ua * ua + va * va);
+  if (wmod != 0.) { uwave = ua / wmod; vwave = va / wmod; }
+  else { uwave = 0.; vwave = 0.; wave_rad = 0.; }
+  double dragfrac = 1.0;
+  if ((p->iceberg_bonds_on) && (p->internal_bergs_for_drag) && berg) {
+    double N_bonds = 0., N_max = 4.0;
+    if (p->hexagonal_icebergs) N_max = 6.0;
+    for (OBond* cb = berg->first_bond; cb; cb = cb->next_bond) {
+      if (p->dem) { if (cb->broken != 1) N_bonds += 1.0; } else N_bonds += 1.0;
+    }
+    dragfrac = ((N_max - N_bonds) / N_max);
+  }
+  double c_ocn = RHO_SEAWATER / M * p->ocean_drag_scale * (0.5 * CD_WV * dragfrac * W * (D_hi) + CD_WH * W * L);
+  double c_atm = RHO_AIR / M * (0.5 * CD_AV * dragfrac * W * F + CD_AH * W * L);
+  double c_ice;
+  if (fabs(hi) == 0.) c_ice = 0.; else c_ice = RHO_ICE / M * (0.5 * CD_IV * dragfrac * W * hi);
+  if (fabs(ui) + fabs(vi) == 0.) c_ice = 0.;
+  if (!Runge_not_Verlet) {
+    *axn = -GRAVITY * ssh_x + wave_rad * uwave;
+    *ayn = -GRAVITY * ssh_y + wave_rad * vwave;
+  } else {
+    *bxn = -GRAVITY * ssh_x + wave_rad * uwave;
+    *byn = -GRAVITY * ssh_y + wave_rad * vwave;
+  }
+  IAcc IA; memset(&IA, 0, sizeof(IA));
+  if (interactive) {
+    interactive_force(o, berg, &IA, uvel0, vvel0, uvel0, vvel0);
+    if (!Runge_not_Verlet) { *axn = *axn + IA.IA_x; *ayn = *ayn + IA.IA_y; }
+    else { *bxn = *bxn + IA.IA_x; *byn = *byn + IA.IA_y; }
+  }
+  if (alpha > 0.) {
+    if (C_N > 0.) { *axn = *axn + f_cori * v_star; *ayn = *ayn - f_cori * u_star; }
+    else { *bxn = *bxn + f_cori * v_star; *byn = *byn - f_cori * u_star; }
+  } else {
+    *bxn = *bxn + f_cori * vvel; *byn = *byn - f_cori * uvel;
+  }
+  double uveln, vveln;
+  if (use_new_pc) { uveln = uvel0; vveln = vvel0; } else { uveln = uvel; vveln = vvel; }
+  double us = uvel0, vs = vvel0;
+  double drag_ocn, drag_atm, drag_ice, drag_gnd, RHS_x, RHS_y, lambda, A11, A12, A21, A22, detA;
+  for (int itloop = 1; itloop <= 2; itloop++) {
+    if (itloop == 2) { us = uveln; vs = vveln; }
+    if (use_new_pc) {
+      drag_ocn = c_ocn * 0.5 * (sqrt((uveln - uo) * (uveln - uo) + (vveln - vo) * (vveln - vo)) +
+                                sqrt((uvel0 - uo) * (uvel0 - uo) + (vvel0 - vo) * (vvel0 - vo)));
+      drag_atm = c_atm * 0.5 * (sqrt((uveln - ua) * (uveln - ua) + (vveln - va) * (vveln - va)) +
+                                sqrt((uvel0 - ua) * (uvel0 - ua) + (vvel0 - va) * (vvel0 - va)));
+      drag_ice = c_ice * 0.5 * (sqrt((uveln - ui) * (uveln - ui) + (vveln - vi) * (vveln - vi)) +
+                                sqrt((uvel0 - ui) * (uvel0 - ui) + (vvel0 - vi) * (vvel0 - vi)));
+      drag_gnd = c_gnd;
+    } else {
+      us = 0.5 * (uveln + uvel); vs = 0.5 * (vveln + vvel);
+      drag_ocn = c_ocn * sqrt((us - uo) * (us - uo) + (vs - vo) * (vs - vo));
+      drag_atm = c_atm * sqrt((us - ua) * (us - ua) + (vs - va) * (vs - va));
+      drag_ice = c_ice * sqrt((us - ui) * (us - ui) + (vs - vi) * (vs - vi));
+      drag_gnd = c_gnd;
+    }
+    RHS_x = (*axn / 2) + *bxn;
+    RHS_y = (*ayn / 2) + *byn;
+    if (beta > 0.) {
+      RHS_x = RHS_x - drag_ocn * (u_star - uo) - drag_atm * (u_star - ua) - drag_ice * (u_star - ui) - drag_gnd * u_star;
+      RHS_y = RHS_y - drag_ocn * (v_star - vo) - drag_atm * (v_star - va) - drag_ice * (v_star - vi) - drag_gnd * v_star;
+    } else {
+      RHS_x = RHS_x - drag_ocn * (uvel - uo) - drag_atm * (uvel - ua) - drag_ice * (uvel - ui) - drag_gnd * uvel;
+      RHS_y = RHS_y - drag_ocn * (vvel - vo) - drag_atm * (vvel - va) - drag_ice * (vvel - vi) - drag_gnd * vvel;
+    }
+    if (interactive) {
+      if (itloop > 1) interactive_force(o, berg, &IA, uvel0, vvel0, us, vs);
+      if (beta > 0.) {
+        RHS_x = RHS_x - (((IA.P11 * u_star) + (IA.P12 * v_star)) - IA.Pu_x);
+        RHS_y = RHS_y - (((IA.P21 * u_star) + (IA.P22 * v_star)) - IA.Pu_y);
+      } else {
+        RHS_x = RHS_x - (((IA.P11 * uvel) + (IA.P12 * vvel)) - IA.Pu_x);
+        RHS_y = RHS_y - (((IA.P21 * uvel) + (IA.P22 * vvel)) - IA.Pu_y);
+      }
+    }
+    if (alpha + beta > 0.) {
+      if (p->only_interactive_forces) {
+        RHS_x = (IA.IA_x / 2) - (((IA.P11 * u_star) + (IA.P12 * v_star)) - IA.Pu_x);
+        RHS_y = (IA.IA_y / 2) - (((IA.P21 * u_star) + (IA.P22 * v_star)) - IA.Pu_y);
+        A11 = 1 + (dt * IA.P11); A12 = (dt * IA.P12); A21 = (dt * IA.P21); A22 = 1 + (dt * IA.P22);
+      } else {
+        lambda = drag_ocn + drag_atm + drag_ice + drag_gnd;
+        A11 = 1. + beta * dt * lambda;
+        A22 = 1. + beta * dt * lambda;
+        A12 = -alpha * dt * f_cori;
+        A21 = alpha * dt * f_cori;
+        if (C_N > 0.) { A12 = A12 / 2.; A21 = A21 / 2.; }
+        if (interactive) {
+          A11 = A11 + (dt * IA.P11); A12 = A12 + (dt * IA.P12);
+          A21 = A21 + (dt * IA.P21); A22 = A22 + (dt * IA.P22);
+        }
+      }
+      detA = 1. / ((A11 * A22) - (A12 * A21));
+      *ax = detA * (A22 * RHS_x - A12 * RHS_y);
+      *ay = detA * (A11 * RHS_y - A21 * RHS_x);
+    } else { *ax = RHS_x; *ay = RHS_y; }
+    uveln = u_star + dt * (*ax);
+    vveln = v_star + dt * (*ay);
+  }
+  if (p->only_interactive_forces) {
+    *axn = IA.IA_x; *ayn = IA.IA_y;
+  } else {
+    *axn = 0.; *ayn = 0.;
+    if (!Runge_not_Verlet) {
+      *axn = -GRAVITY * ssh_x + wave_rad * uwave;
+      *ayn = -GRAVITY * ssh_y + wave_rad * vwave;
+      if (interactive) { *axn = *axn + IA.IA_x; *ayn = *ayn + IA.IA_y; }
+    }
+    if (C_N > 0.) { *axn = *axn + f_cori * vveln; *ayn = *ayn - f_cori * uveln; }
+  }
+  *bxn = *ax - (*axn / 2); *byn = *ay - (*ayn / 2);
+  /* speed limit I:2304-2323: only counts tickets (scaled uveln/vveln are local) */
+  if ((p->speed_limit > 0.) || (p->speed_limit == -1.)) {
+    double speed = sqrt(uveln * uveln + vveln * vveln);
+    if (speed > 0.) {
+      double new_speed = loc_dx / dt * p->speed_limit;
+      if (new_speed < speed) if (p->speed_limit > 0.) (*speeding)++;
+    }
+  }
+  if (p->override_iceberg_velocities) { *ax = 0.0; *ay = 0.0; *axn = 0.0; *ayn = 0.0; *bxn = 0.0; *byn = 0.0; }
+}
+
+/* I:1950-2442 */
+static void accel(Oracle* o, OBerg* berg, int i, int j, double xi, double yj, double lat,
+                  double uvel, double vvel, double uvel0, double vvel0, double dt, double* ax,
+                  double* ay, double* axn, double* ayn, double* bxn, double* byn) {
+  Env e;
+  if (o->p.old_interp_flds_order) {
+    interp_flds(o, berg->lon, berg->lat, i, j, xi, yj, 0., 0., &e.uo, &e.vo, &e.ui, &e.vi, &e.ua,
+                &e.va, &e.ssh_x, &e.ssh_y, &e.sst, &e.sss, &e.cn, &e.hi, &e.od);
+  } else {
+    e.uo = berg->uo; e.vo = berg->vo; e.ua = berg->ua; e.va = berg->va; e.ui = berg->ui; e.vi = berg->vi;
+    e.ssh_x = berg->ssh_x; e.ssh_y = berg->ssh_y; e.sst = berg->sst; e.sss = berg->sss;
+    e.cn = berg->cn; e.hi = berg->hi; e.od = berg->od;
+  }
+  double loc_dx = 0.;
+  if ((o->p.speed_limit > 0.) || (o->p.speed_limit == -1.))
+    loc_dx = dmin(0.5 * (G(o, dx, i, j) + G(o, dx, i, j - 1)), 0.5 * (G(o, dy, i, j) + G(o, dy, i - 1, j)));
+  int speeding = 0;
+  accel_core(o, &o->p, berg, berg->mass, berg->thickness, berg->width, berg->length, lat, uvel, vvel,
+             uvel0, vvel0, dt, e, loc_dx, ax, ay, axn, ayn, bxn, byn, &speeding);
+  if (speeding) {
+#ifdef _OPENMP
+#pragma omp atomic
+#endif
+    o->cnt.nspeeding_tickets += speeding;
+  }
+}
+
+void oracle_accel_free(const KidParams* p, const double berg[8], const double acc_in[4],
+                       const double env[13], double out[6]) {
+  Env e = {env[0], env[1], env[2], env[3], env[4], env[5], env[6], env[7], env[8], env[9], env[10], env[11], env[12]};
+  double ax = 0, ay = 0, axn = acc_in[0], ayn = acc_in[1], bxn = acc_in[2], byn = acc_in[3];
+  int speeding = 0;
+  accel_core(NULL, p, NULL, berg[0], berg[1], berg[2], berg[3], berg[4], berg[5], berg[6], berg[5],
+             berg[6], p->dt, e, 0., &ax, &ay, &axn, &ayn, &bxn, &byn, &speeding);
+  out[0] = ax; out[1] = ay; out[2] = axn; out[3] = ayn; out[4] = bxn; out[5] = byn;
+}
+
+/* ------------------------------------------------- tangent plane I:7767 */
+/* I:7767-7780 */
+static void rotpos_from_tang(const Oracle* o, double x, double y, double* lon, double* lat) {
+  double r180_pi = 180. / o->p.pi;
+  double r = sqrt(x * x + y * y);
+  *lat = 90. - (r180_pi * r / o->p.Rearth);
+  *lon = r180_pi * acos(x / r) * f_sign(1., y);
+}
+/* I:7783-7798 */
+static void rotvec_to_tang(const Oracle* o, double lon, double uvel, double vvel, double* xdot,
+                           double* ydot) {
+  double pi_180 = o->p.pi / 180.;
+  double clon = cos(lon * pi_180), slon = sin(lon * pi_180);
+  *xdot = -slon * uvel - clon * vvel;
+  *ydot = clon * uvel - slon * vvel;
+}
+/* I:7801-7816 */
+static void rotvec_from_tang(const Oracle* o, double lon, double xdot, double ydot, double* uvel,
+                             double* vvel) {
+  double pi_180 = o->p.pi / 180.;
+  double clon = cos(lon * pi_180), slon = sin(lon * pi_180);
+  *uvel = -slon * xdot + clon * ydot;
+  *vvel = -clon * xdot - slon * ydot;
+}
+/* I:8066-8099 */
+static void rotpos_to_tang(Oracle* o, double lon, double lat, double* x, double* y) {
+  double pi_180 = o->p.pi / 180.;
+  if (lat > 90.) o_fatal(o, "KID, rotpos_to_tang: lat>90 already!");
+  if (lat == 90.) o_fatal(o, "KID, rotpos_to_tang: lat==90 already!");
+  double colat = 90. - lat;
+  double r = o->p.Rearth * (colat * pi_180);
+  *x = r * cos(lon * pi_180);
+  *y = r * sin(lon * pi_180);
+}
+
+/* ------------------------------------------ adjust_index_and_ground I:7819 */
+static void adjust_index_and_ground(Oracle* o, double* lon, double* lat, double* uvel, double* vvel,
+                                    int* i, int* j, double* xi, double* yj, int* bounced) {
+  (void)uvel; (void)vvel;
+  const KidDomain* d = &o->d;
+  const double posn_eps = 0.05;
+  *bounced = 0;
+  int i0 = *i, j0 = *j;
+  int lret = pos_within_cell(o, *lon, *lat, *i, *j, xi, yj);
+  if (lret) return;
+  /* the (debug-only) inm/jnm search I:7903-7936 is inactive: inm=i0, jnm=j0 */
+  int inm = i0, jnm = j0;
+  int icount = 0;
+  lret = pos_within_cell(o, *lon, *lat, i0, j0, xi, yj);
+  while (!lret && icount < 4) {
+    icount++;
+    if (*xi < 0.) {
+      if (*i > d->isd) {
+        if (G(o, msk, *i - 1, *j) > 0.) { if (*i > d->isd + 1) *i = *i - 1; }
+        else *bounced = 1;
+      }
+    } else if (*xi >= 1.) {
+      if (*i < d->ied) {
+        if (G(o, msk, *i + 1, *j) > 0.) { if (*i < d->ied) *i = *i + 1; }
+        else *bounced = 1;
+      }
+    }
+    if (*yj < 0.) {
+      if (*j > d->jsd) {
+        if (G(o, msk, *i, *j - 1) > 0.) { if (*j > d->jsd + 1) *j = *j - 1; }
+        else *bounced = 1;
+      }
+    } else if (*yj >= 1.) {
+      if (*j < d->jed) {
+        if (G(o, msk, *i, *j + 1) > 0.) { if (*j < d->jed) *j = *j + 1; }
+        else *bounced = 1;
+      }
+    }
+    if (*bounced) {
+      if (*xi >= 1.) *xi = 1. - posn_eps;
+      if (*xi < 0.) *xi = posn_eps;
+      if (*yj >= 1.) *yj = 1. - posn_eps;
+      if (*yj < 0.) *yj = posn_eps;
+      *lon = bilin(o, o->lon, *i, *j, *xi, *yj);
+      *lat = bilin(o, o->lat, *i, *j, *xi, *yj);
+    }
+    lret = pos_within_cell(o, *lon, *lat, *i, *j, xi, yj);
+  }
+  if (!*bounced && lret && G(o, msk, *i, *j) > 0.) return;
+  if (!*bounced && !lret) {
+    if (abs(*i - i0) + abs(*j - j0) == 0) {
+      if (o->p.use_roundoff_fix) {
+        *xi = (*xi - 0.5) * (1. - posn_eps) + 0.5;
+        *yj = (*yj - 0.5) * (1. - posn_eps) + 0.5;
+      }
+      o_warn(o, "KID, adjust: Berg did not move or bounce during iterations AND was not in cell. Adjusting!");
+      /* the explain call `lret=pos_within_cell(grd, lon, lat, inm, jnm, xi, yj, explain=.true.)`
+       * (I:8039) overwrites xi,yj with the values for cell (inm,jnm)=(i0,j0)=(i,j) */
+      lret = pos_within_cell(o, *lon, *lat, inm, jnm, xi, yj);
+    } else {
+      o_warn(o, "KID, adjust: Berg iterated many times without bouncing!");
+    }
+  }
+  if (*xi >= 1.) *xi = 1. - posn_eps;
+  if (*xi < 0.) *xi = posn_eps;
+  if (*yj > 1.) *yj = 1. - posn_eps;
+  if (*yj <= 0.) *yj = posn_eps;
+  *lon = bilin(o, o->lon, *i, *j, *xi, *yj);
+  *lat = bilin(o, o->lat, *i, *j, *xi, *yj);
+  lret = pos_within_cell(o, *lon, *lat, *i, *j, xi, yj);
+  if (!lret) o_warn(o, "KID, adjust: Should not get here! Berg is not in cell after adjustment");
+}
+
+/* ------------------------------------------------ verlet_stepping I:7203 */
+static void verlet_stepping(Oracle* o, OBerg* berg, double* axn, double* ayn, double* bxn,
+                            double* byn, double* uveln, double* vveln) {
+  double dt = o->p.dt, dt_2 = 0.5 * dt;
+  double lonn = berg->lon, latn = berg->lat;
+  *axn = berg->axn; *ayn = berg->ayn; *bxn = berg->bxn; *byn = berg->byn;
+  double uvel1 = berg->uvel, vvel1 = berg->vvel;
+  int i = berg->ine, j = berg->jne;
+  double xi = berg->xi, yj = berg->yj;
+  berg->uvel_prev = berg->uvel - dt_2 * berg->bxn;
+  berg->vvel_prev = berg->vvel - dt_2 * berg->byn;
+  double uvel3 = uvel1 + (dt_2 * (*axn));
+  double vvel3 = vvel1 + (dt_2 * (*ayn));
+  double ax1, ay1;
+  accel(o, berg, i, j, xi, yj, latn, uvel1, vvel1, uvel1, vvel1, dt, &ax1, &ay1, axn, ayn, bxn, byn);
+  int on_tangential_plane = 0;
+  if ((berg->lat > 89.) && (o->p.grid_is_latlon)) on_tangential_plane = 1;
+  if (on_tangential_plane) {
+    double xdot3, ydot3, xddot1, yddot1;
+    rotvec_to_tang(o, lonn, uvel3, vvel3, &xdot3, &ydot3);
+    rotvec_to_tang(o, lonn, ax1, ay1, &xddot1, &yddot1);
+    double xdotn = xdot3 + (dt * xddot1), ydotn = ydot3 + (dt * yddot1);
+    rotvec_from_tang(o, lonn, xdotn, ydotn, uveln, vveln);
+  } else {
+    *uveln = uvel3 + (dt * ax1); *vveln = vvel3 + (dt * ay1);
+  }
+}
+
+/* ----------------------------------------- update_verlet_position I:7684 */
+static void update_verlet_position(Oracle* o, OBerg* berg) {
+  double dt = o->p.dt, dt_2 = 0.5 * dt;
+  int on_tangential_plane = 0;
+  if ((berg->lat > 89.) && (o->p.grid_is_latlon)) on_tangential_plane = 1;
+  double lon1 = berg->lon, lat1 = berg->lat, x1 = 0, y1 = 0;
+  if (on_tangential_plane) rotpos_to_tang(o, lon1, lat1, &x1, &y1);
+  double dxdl1, dydl;
+  convert_from_meters_to_grid(o, lat1, &dxdl1, &dydl);
+  double uvel1 = berg->uvel, vvel1 = berg->vvel;
+  double axn = berg->axn, ayn = berg->ayn, bxn = berg->bxn, byn = berg->byn;
+  double uvel2 = uvel1 + (dt_2 * axn) + (dt_2 * bxn);
+  double vvel2 = vvel1 + (dt_2 * ayn) + (dt_2 * byn);
+  double xdot2 = 0, ydot2 = 0;
+  if (on_tangential_plane) rotvec_to_tang(o, lon1, uvel2, vvel2, &xdot2, &ydot2);
+  double u2 = uvel2 * dxdl1, v2 = vvel2 * dydl;
+  double lonn, latn;
+  if (on_tangential_plane) {
+    double xn = x1 + (dt * xdot2), yn = y1 + (dt * ydot2);
+    rotpos_from_tang(o, xn, yn, &lonn, &latn);
+  } else {
+    lonn = lon1 + (dt * u2); latn = lat1 + (dt * v2);
+  }
+  double uvel3 = uvel1 + (dt_2 * axn), vvel3 = vvel1 + (dt_2 * ayn);
+  int i = berg->ine, j = berg->jne, bounced;
+  double xi = berg->xi, yj = berg->yj;
+  adjust_index_and_ground(o, &lonn, &latn, &uvel3, &vvel3, &i, &j, &xi, &yj, &bounced);
+  if (bounced) {
+#ifdef _OPENMP
+#pragma omp atomic
+#endif
+    o->cnt.n_bounced++;
+  }
+  berg->lon = lonn; berg->lat = latn;
+  berg->ine = i; berg->jne = j;
+  berg->xi = xi; berg->yj = yj;
+}
+
+/* ------------------------------------------------ evolve_icebergs I:7081 */
+static void evolve_icebergs(Oracle* o) {
+  const KidDomain* d = &o->d;
+  int interactive = o->p.interactive_icebergs_on;
+  if (o->p.runge_not_verlet) { o_fatal(o, "oracle: Runge-Kutta stepping is not restated (Verlet only)"); return; }
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 4) num_threads(o->nthreads) if (o->nthreads > 1)
+#endif
+  for (int grdj = d->jsc; grdj <= d->jec; grdj++)
+    for (int grdi = d->isc; grdi <= d->iec; grdi++)
+      for (OBerg* berg = G(o, list, grdi, grdj); berg; berg = berg->next) {
+        if (berg->static_berg < 0.5) {
+          if (!is_point_in_cell(o, berg->lon, berg->lat, berg->ine, berg->jne))
+            o_warn(o, "evolve_iceberg, berg is not in proper starting cell");
+          double axn, ayn, bxn, byn, uveln, vveln;
+          verlet_stepping(o, berg, &axn, &ayn, &bxn, &byn, &uveln, &vveln);
+          if (o->p.override_iceberg_velocities) { uveln = o->p.u_override; vveln = o->p.v_override; }
+          berg->axn = axn; berg->ayn = ayn; berg->bxn = bxn; berg->byn = byn;
+          berg->uvel = uveln; berg->vvel = vveln;
+          if (!interactive) update_verlet_position(o, berg);
+        }
+      }
+  if (interactive) {
+    for (int grdj = d->jsc; grdj <= d->jec; grdj++)
+      for (int grdi = d->isc; grdi <= d->iec; grdi++)
+        for (OBerg* berg = G(o, list, grdi, grdj); berg; berg = berg->next)
+          if (berg->static_berg < 0.5) {
+            update_verlet_position(o, berg);
+            berg->uvel_old = berg->uvel; berg->vvel_old = berg->vvel;
+            berg->lon_old = berg->lon; berg->lat_old = berg->lat;
+          }
+  }
+}
+
+/* --------------------------------------------------------- rolling I:3307 */
+static void swap_d(double* x, double* y) { double t = *x; *x = *y; *y = t; }
+void oracle_rolling(const KidParams* p, double* Tn, double* Wn, double* Ln) {
+  const double Delta = 6.0;
+  double Dn = (p->rho_bergs / RHO_SEAWATER) * (*Tn);
+  if (Dn > 0.) {
+    if ((!p->use_updated_rolling_scheme) && (p->tip_parameter < 999.)) {
+      if (dmax(*Wn, *Ln) < sqrt(0.92 * (Dn * Dn) + 58.32 * Dn)) {
+        swap_d(Tn, Wn);
+        if (*Wn > *Ln) swap_d(Wn, Ln);
+      }
+    } else {
+      if (*Wn > *Ln) swap_d(Ln, Wn);
+      if ((!p->use_updated_rolling_scheme) && (p->tip_parameter >= 999.)) {
+        double q = p->rho_bergs / RHO_SEAWATER;
+        if (*Wn < sqrt((6.0 * q * (1 - q) * ((*Tn) * (*Tn))) - (12 * Delta * q * (*Tn)))) {
+          swap_d(Tn, Wn);
+          if (*Wn > *Ln) swap_d(Wn, Ln);
+        }
+      }
+      if (p->use_updated_rolling_scheme) {
+        double tip_parameter;
+        if (p->tip_parameter > 0.) tip_parameter = p->tip_parameter;
+        else tip_parameter = sqrt(6 * (p->rho_bergs / RHO_SEAWATER) * (1 - (p->rho_bergs / RHO_SEAWATER)));
+        if ((tip_parameter * (*Tn)) > *Wn) {
+          swap_d(Tn, Wn);
+          if (*Wn > *Ln) swap_d(Wn, Ln);
+        }
+      }
+    }
+  }
+}
+
+/* I:3370-3387 */
+static void fl_bits_dimensions(const Oracle* o, const OBerg* this_, double* L_fl, double* W_fl,
+                               double* T_fl) {
+  const double l_c = o->p.pi / (2. * sqrt(2.)), lw_c = 1. / (GRAVITY * RHO_SEAWATER);
+  const double B_c = 1. / (12. * (1. - pow(0.3, 2.)));
+  double l_w = pow(lw_c * o->p.fl_youngs * B_c * pow(this_->thickness, 3.), 0.25);
+  double l_b = l_c * l_w;
+  *L_fl = 3. * l_b; *W_fl = l_b;
+  *T_fl = this_->thickness;
+  oracle_rolling(&o->p, T_fl, W_fl, L_fl);
+}
+
+static int minloc_abs_diff(const double* a, double v) {
+  int k = 0; double best = fabs(a[0] - v);
+  for (int q = 1; q < KID_NCLASSES; q++) { double t = fabs(a[q] - v); if (t < best) { best = t; k = q; } }
+  return k;
+}
+
+/* -------------------------------------------------- thermodynamics I:2844 */
+static void thermodynamics(Oracle* o) {
+  const KidParams* p = &o->p;
+  const KidDomain* d = &o->d;
+  const double perday = 1. / 86400.;
+  const double l_c = p->pi / (2. * sqrt(2.)), lw_c = 1. / (GRAVITY * RHO_SEAWATER);
+  const double B_c = 1. / (12. * (1. - pow(0.3, 2.)));
+  double dt = p->dt;
+  double N_max = 4.0;
+  if (p->use_mixed_melting || p->allow_bergs_to_roll) N_max = p->hexagonal_icebergs ? 6.0 : 4.0;
+  double net_heat = 0.;
+  int64_t n_melted = 0, n_calved_fl = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 4) num_threads(o->nthreads) if (o->nthreads > 1) reduction(+ : net_heat, n_melted, n_calved_fl)
+#endif
+  for (int grdj = d->jsc - 1; grdj <= d->jec + 1; grdj++)
+    for (int grdi = d->isc - 1; grdi <= d->iec + 1; grdi++) {
+      OBerg* this_ = G(o, list, grdi, grdj);
+      while (this_) {
+        if (p->old_interp_flds_order || (!p->mts && !p->dem && this_->halo_berg >= 0.5)) {
+          interp_flds(o, this_->lon, this_->lat, this_->ine, this_->jne, this_->xi, this_->yj, 0., 0.,
+                      &this_->uo, &this_->vo, &this_->ui, &this_->vi, &this_->ua, &this_->va,
+                      &this_->ssh_x, &this_->ssh_y, &this_->sst, &this_->sss, &this_->cn, &this_->hi, NULL);
+        }
+        double SST = this_->sst;
+        double IC = dmin(1., this_->cn + p->sicn_shift);
+        double M = this_->mass, T = this_->thickness, W = this_->width, L = this_->length;
+        int i = this_->ine, j = this_->jne;
+        double Vol = T * W * L;
+        double dvo = sqrt((this_->uvel - this_->uo) * (this_->uvel - this_->uo) +
+                          (this_->vvel - this_->vo) * (this_->vvel - this_->vo));
+        double dva = sqrt((this_->ua - this_->uo) * (this_->ua - this_->uo) +
+                          (this_->va - this_->vo) * (this_->va - this_->vo));
+        double Ss = 1.5 * pow(dva, 0.5) + 0.1 * dva;
+        double Mv = dmax(7.62e-3 * SST + 1.29e-3 * (SST * SST), 0.) * perday;
+        double Mb = dmax(0.58 * pow(dvo, 0.8) * (SST + 4.0) / pow(L, 0.2), 0.) * perday;
+        double Me = dmax(1. / 12. * (SST + 2.) * Ss * (1 + cos(p->pi * (IC * IC * IC))), 0.) * perday;
+        double Mv_fl = 0., Me_fl = 0.;
+        if (this_->mass_of_fl_bits > 0.) { Mv_fl = Mv; Me_fl = Me; }
+        double N_bonds = 0.;
+        if (p->use_mixed_melting || p->allow_bergs_to_roll) {
+          N_bonds = 0.;
+          if (p->iceberg_bonds_on) N_bonds = this_->n_bonds;
+          if (this_->static_berg == 1) N_bonds = N_max;
+        }
+        /* melt_icebergs_as_ice_shelf / use_mixed_melting (find_basal_melt I:3492): second tier, rejected at create */
+        if (p->set_melt_rates_to_zero) { Mv = 0.0; Mb = 0.0; Me = 0.0; }
+        double Tn, nVol, Mnew1 = 0, Mnew2 = 0, Mnew, dMb, dMv, dMe, dM, Ln1 = 0, Wn1 = 0, Ln, Wn;
+        if (p->use_operator_splitting) {
+          Tn = dmax(T - Mb * dt, 0.);
+          nVol = Tn * W * L;
+          Mnew1 = (nVol / Vol) * M;
+          dMb = M - Mnew1;
+          Ln1 = dmax(L - Mv * dt, 0.);
+          Wn1 = dmax(W - Mv * dt, 0.);
+          nVol = Tn * Wn1 * Ln1;
+          Mnew2 = (nVol / Vol) * M;
+          dMv = Mnew1 - Mnew2;
+          Ln = dmax(Ln1 - Me * dt, 0.);
+          Wn = dmax(Wn1 - Me * dt, 0.);
+          nVol = Tn * Wn * Ln;
+          Mnew = (nVol / Vol) * M;
+          dMe = Mnew2 - Mnew;
+          dM = M - Mnew;
+        } else {
+          Ln = dmax(L - (Mv + Me) * (dt), 0.);
+          Wn = dmax(W - (Mv + Me) * (dt), 0.);
+          Tn = dmax(T - Mb * (dt), 0.);
+          nVol = Tn * Wn * Ln;
+          Mnew = (nVol / Vol) * M;
+          dM = M - Mnew;
+          dMb = (M / Vol) * (W * L) * Mb * dt;
+          dMe = (M / Vol) * (T * (W + L)) * Me * dt;
+          dMv = (M / Vol) * (T * (W + L)) * Mv * dt;
+        }
+        if (p->footloose) {
+          if (this_->fl_k >= 0) {
+            double l_b3 = 3. * l_c * pow(lw_c * p->fl_youngs * B_c * pow(Tn, 3.), 0.25);
+            if (L > l_b3) {
+              double fb = Tn * (1. - p->rho_bergs / RHO_SEAWATER);
+              double kd = Tn - fb;
+              if (W > l_b3) {
+                this_->fl_k = this_->fl_k + (dMe / fb - dMv / kd) / p->rho_bergs;
+                if (this_->fl_k < 0) this_->fl_k = 0;
+              } else {
+                double dMv_l = dMv * (Wn1 + W) / (2. * (Ln1 + W));
+                double dMe_l = dMe * (Wn + Wn1) / (2. * (Ln + Wn1));
+                this_->fl_k = this_->fl_k + (dMe_l / fb - dMv_l / kd) / p->rho_bergs;
+                if (this_->fl_k < 0) this_->fl_k = 0;
+              }
+            }
+          }
+        }
+        double Lfl = 0, Wfl = 0, Tfl = 0, Mfl, Volfl, Mb_fl, Tnfl = 0, nVolfl, Mnew1_fl, Mnew2_fl, Mnew_fl;
+        double dMb_fl, dMv_fl, dMe_fl, dMfl, Lnfl = 0, Wnfl = 0;
+        if (this_->mass_of_fl_bits > 0.) {
+          fl_bits_dimensions(o, this_, &Lfl, &Wfl, &Tfl);
+          Mfl = this_->mass_of_fl_bits;
+          Volfl = Lfl * Wfl * Tfl;
+          Mb_fl = dmax(0.58 * pow(dvo, 0.8) * (SST + 4.0) / pow(Lfl, 0.2), 0.) * perday;
+          Tnfl = dmax(Tfl - Mb_fl * dt, 0.);
+          if (p->use_operator_splitting) {
+            nVolfl = Tnfl * Wfl * Lfl;
+            Mnew1_fl = (nVolfl / Volfl) * Mfl;
+            dMb_fl = Mfl - Mnew1_fl;
+            Lnfl = dmax(Lfl - Mv_fl * dt, 0.);
+            Wnfl = dmax(Wfl - Mv_fl * dt, 0.);
+            nVolfl = Tnfl * Wnfl * Lnfl;
+            Mnew2_fl = (nVolfl / Volfl) * Mfl;
+            dMv_fl = Mnew1_fl - Mnew2_fl;
+            Lnfl = dmax(Lnfl - Me_fl * dt, 0.);
+            Wnfl = dmax(Wnfl - Me_fl * dt, 0.);
+            nVolfl = Tnfl * Wnfl * Lnfl;
+            Mnew_fl = (nVolfl / Volfl) * Mfl;
+            dMe_fl = Mnew2_fl - Mnew_fl;
+          } else {
+            Lnfl = dmax(Lfl - (Mv_fl + Me_fl) * dt, 0.);
+            Wnfl = dmax(Wfl - (Mv_fl + Me_fl) * dt, 0.);
+            nVolfl = Tnfl * Wnfl * Lnfl;
+            Mnew_fl = (nVolfl / Volfl) * Mfl;
+            dMb_fl = (Mfl / Volfl) * (Wfl * Lfl) * Mb_fl * dt;
+            dMe_fl = (Mfl / Volfl) * (Tfl * (Wfl + Lfl)) * Me_fl * dt;
+            dMv_fl = (Mfl / Volfl) * (Tfl * (Wfl + Lfl)) * Mv_fl * dt;
+          }
+          dMfl = Mfl - Mnew_fl;
+        } else {
+          dMfl = 0.; dMb_fl = 0.; dMv_fl = 0.; dMe_fl = 0.;
+          Mnew_fl = this_->mass_of_fl_bits;
+        }
+        double Abits, dMbitsE, dMbitsM, nMbits, Abits_fl, dMbitsE_fl, dMbitsM_fl, nMbits_fl;
+        if (p->bergy_bit_erosion_fraction > 0.) {
+          double Mbits = this_->mass_of_bits;
+          dMbitsE = p->bergy_bit_erosion_fraction * dMe;
+          nMbits = Mbits + dMbitsE;
+          double Lbits = dmin(dmin(L, W), dmin(T, 40.));
+          Abits = (Mbits / p->rho_bergs) / Lbits;
+          double Mbb = dmax(0.58 * pow(dvo, 0.8) * (SST + 2.0) / pow(Lbits, 0.2), 0.) * perday;
+          Mbb = p->rho_bergs * Abits * Mbb;
+          dMbitsM = dmin(Mbb * dt, nMbits);
+          nMbits = nMbits - dMbitsM;
+          if (Mnew == 0.) { dMbitsM = dMbitsM + nMbits; nMbits = 0.; }
+          if (this_->mass_of_fl_bits > 0.) {
+            double Mbits_fl = this_->mass_of_fl_bergy_bits;
+            dMbitsE_fl = p->bergy_bit_erosion_fraction * dMe_fl;
+            nMbits_fl = Mbits_fl + dMbitsE_fl;
+            double Lbits_fl = dmin(dmin(Lfl, Wfl), dmin(Tfl, 40.));
+            Abits_fl = (Mbits_fl / p->rho_bergs) / Lbits_fl;
+            double Mbb_fl = dmax(0.58 * pow(dvo, 0.8) * (SST + 2.0) / pow(Lbits_fl, 0.2), 0.) * perday;
+            Mbb_fl = p->rho_bergs * Abits_fl * Mbb_fl;
+            dMbitsM_fl = dmin(Mbb_fl * dt, nMbits_fl);
+            nMbits_fl = nMbits_fl - dMbitsM_fl;
+            if (Mnew_fl == 0.) { dMbitsM_fl = dMbitsM_fl + nMbits_fl; nMbits_fl = 0.; }
+          } else {
+            dMbitsE_fl = 0.; dMbitsM_fl = 0.; Abits_fl = 0.; nMbits_fl = 0.;
+          }
+        } else {
+          Abits = 0.; dMbitsE = 0.; dMbitsM = 0.; nMbits = this_->mass_of_bits;
+          Abits_fl = 0.; dMbitsE_fl = 0.; dMbitsM_fl = 0.; nMbits_fl = this_->mass_of_fl_bergy_bits;
+        }
+        (void)Abits; (void)Abits_fl;
+        double area = G(o, area, i, j);
+        if (area != 0.) {
+          double ms = this_->mass_scaling;
+          double melt = (dM - (dMbitsE - dMbitsM) + dMfl - (dMbitsE_fl - dMbitsM_fl)) / dt;
+          G(o, floating_melt, i, j) = G(o, floating_melt, i, j) + melt / area * ms;
+          /* melt_by_class (I:3119-3126) is a diagnostic keyed on a registered diag id: not restated */
+          (void)minloc_abs_diff;
+          melt = melt * this_->heat_density;
+          G(o, calving_hflx, i, j) = G(o, calving_hflx, i, j) + melt / area * ms;
+          net_heat = net_heat + melt * ms * dt;
+          melt = dM / dt;
+          G(o, berg_melt, i, j) = G(o, berg_melt, i, j) + melt / area * ms;
+          melt = (dMbitsE + dMbitsE_fl) / dt;
+          G(o, bergy_src, i, j) = G(o, bergy_src, i, j) + melt / area * ms;
+          melt = (dMbitsM + dMbitsM_fl) / dt;
+          G(o, bergy_melt, i, j) = G(o, bergy_melt, i, j) + melt / area * ms;
+          melt = dMfl / dt;
+          G(o, fl_bits_melt, i, j) = G(o, fl_bits_melt, i, j) + melt / area * ms;
+          if (p->melt_diagnostics) {
+            if (this_->fl_k >= 0) {
+              melt = (dM - (dMbitsE - dMbitsM)) / dt;
+              G(o, fl_parent_melt, i, j) += melt / area * ms;
+              melt = (dMfl - (dMbitsE_fl - dMbitsM_fl)) / dt;
+              G(o, fl_child_melt, i, j) += melt / area * ms;
+              melt = dMb / dt; G(o, melt_buoy, i, j) += melt / area * ms;
+              melt = dMe / dt; G(o, melt_eros, i, j) += melt / area * ms;
+              melt = dMv / dt; G(o, melt_conv, i, j) += melt / area * ms;
+              if (dMfl > 0) {
+                melt = dMb_fl / dt; G(o, melt_buoy_fl, i, j) += melt / area * ms;
+                melt = dMe_fl / dt; G(o, melt_eros_fl, i, j) += melt / area * ms;
+                melt = dMv_fl / dt; G(o, melt_conv_fl, i, j) += melt / area * ms;
+              }
+            } else {
+              melt = (dM - (dMbitsE - dMbitsM)) / dt;
+              G(o, fl_child_melt, i, j) += melt / area * ms;
+              melt = dMb / dt; G(o, melt_buoy_fl, i, j) += melt / area * ms;
+              melt = dMe / dt; G(o, melt_eros_fl, i, j) += melt / area * ms;
+              melt = dMv / dt; G(o, melt_conv_fl, i, j) += melt / area * ms;
+            }
+          }
+        } else {
+          o_fatal(o, "KID, thermodynamics: berg appears to have grounded!");
+        }
+        if (p->allow_bergs_to_roll && N_bonds == 0.) oracle_rolling(p, &Tn, &Wn, &Ln);
+        if (p->iceberg_melt_without_decay) {
+          /* find_melt_using_spread_mass is a spreading-row option: not restated */
+          Mnew = this_->mass; nMbits = this_->mass_of_bits;
+          Mnew_fl = this_->mass_of_fl_bits; nMbits_fl = this_->mass_of_fl_bergy_bits;
+          Tn = this_->thickness; Wn = this_->width; Ln = this_->length;
+        } else {
+          this_->mass = Mnew;
+          this_->mass_of_bits = nMbits;
+          this_->mass_of_fl_bits = Mnew_fl;
+          this_->mass_of_fl_bergy_bits = nMbits_fl;
+          this_->thickness = Tn;
+          this_->width = dmin(Wn, Ln);
+          this_->length = dmax(Wn, Ln);
+        }
+        OBerg* next = this_->next;
+        if (Mnew <= 0.) {
+          if (Mnew_fl > 0) {
+            n_calved_fl++;
+            this_->mass = Lnfl * Wnfl * Tnfl * p->rho_bergs;
+            this_->length = Lnfl; this_->width = Wnfl; this_->thickness = Tnfl;
+            nMbits_fl = nMbits_fl * this_->mass_scaling;
+            this_->mass_scaling = Mnew_fl * this_->mass_scaling / this_->mass;
+            this_->mass_of_bits = nMbits_fl / this_->mass_scaling;
+            this_->mass_of_fl_bits = 0.;
+            this_->mass_of_fl_bergy_bits = 0.;
+            this_->fl_k = -1.;
+            this_->start_year = o->current_year;
+            this_->start_day = o->current_yearday;
+            if (area != 0.)
+              G(o, fl_bits_src, i, j) = G(o, fl_bits_src, i, j) - this_->mass * this_->mass_scaling / (dt * area);
+          } else {
+            delete_iceberg_from_list(o, &G(o, list, grdi, grdj), this_);
+          }
+          n_melted++;
+        }
+        this_ = next;
+      }
+    }
+  o->cnt.net_heat_to_ocean += net_heat;
+  o->cnt.nbergs_melted += n_melted;
+  o->cnt.nbergs_calved_fl += n_calved_fl;
+}
+
+/* ------------------------------------------------------ calving I:6153 */
+static void accumulate_calving(Oracle* o) {
+  const KidDomain* d = &o->d;
+  const KidParams* p = &o->p;
+  size_t n2 = (size_t)o->nid * o->njd;
+  if (o->first_call_accum && !o->restarted) {
+    o->first_call_accum = 0;
+    for (int j = d->jsc; j <= d->jec; j++)
+      for (int i = d->isc; i <= d->iec; i++)
+        if (G(o, calving, i, j) != 0.) {
+          double s = 0.;
+          for (int k = 0; k < KID_NCLASSES; k++) s += o->stored_ice[IDX(o, i, j) + n2 * k];
+          G(o, stored_heat, i, j) = s * G(o, calving_hflx, i, j) * G(o, area, i, j) / G(o, calving, i, j);
+        }
+  }
+  double remaining_dist_s = 1., remaining_dist_n = 1.;
+  for (int k = 0; k < KID_NCLASSES; k++) {
+    for (size_t q = 0; q < n2; q++) {
+      if (o->lat[q] < 0.) o->stored_ice[q + n2 * k] = o->stored_ice[q + n2 * k] + p->dt * o->calving[q] * p->distribution_s[k];
+      else o->stored_ice[q + n2 * k] = o->stored_ice[q + n2 * k] + p->dt * o->calving[q] * p->distribution_n[k];
+    }
+    remaining_dist_s = remaining_dist_s - p->distribution_s[k];
+    remaining_dist_n = remaining_dist_n - p->distribution_n[k];
+  }
+  if (remaining_dist_s < 0. || remaining_dist_n < 0.) o_warn(o, "KID, accumulate_calving: calving is OVER distributed!");
+  for (size_t q = 0; q < n2; q++) {
+    double rd = (o->lat[q] < 0.) ? remaining_dist_s : remaining_dist_n;
+    o->calving[q] = o->calving[q] * rd;
+    o->tmp[q] = p->dt * o->calving_hflx[q] * o->area[q] * (1. - rd);
+    o->stored_heat[q] = o->stored_heat[q] + o->tmp[q];
+    o->calving_hflx[q] = o->calving_hflx[q] * rd;
+  }
+}
+
+/* I:6225-6402 */
+static void calve_icebergs(Oracle* o) {
+  const KidDomain* d = &o->d;
+  const KidParams* p = &o->p;
+  size_t n2 = (size_t)o->nid * o->njd;
+  memset(o->real_calving, 0, sizeof(double) * n2 * KID_NCLASSES);
+  for (int k = 0; k < KID_NCLASSES; k++)
+    for (int j = d->jsc; j <= d->jec; j++)
+      for (int i = d->isc; i <= d->iec; i++) {
+        double ddt = 0.;
+        double initial_mass, mass_scaling, initial_thickness, initial_width, initial_length;
+        if (G(o, lat, i, j) < 0.) {
+          initial_mass = p->initial_mass_s[k]; mass_scaling = p->mass_scaling_s[k];
+          initial_thickness = p->initial_thickness_s[k];
+          initial_width = sqrt(p->initial_mass_s[k] / (p->LoW_ratio * p->rho_bergs * p->initial_thickness_s[k])); /* F:1540 */
+        } else {
+          initial_mass = p->initial_mass_n[k]; mass_scaling = p->mass_scaling_n[k];
+          initial_thickness = p->initial_thickness_n[k];
+          initial_width = sqrt(p->initial_mass_n[k] / (p->LoW_ratio * p->rho_bergs * p->initial_thickness_n[k])); /* F:1549 */
+        }
+        initial_length = p->LoW_ratio * initial_width; /* F:1541 */
+        double* si = &o->stored_ice[IDX(o, i, j) + n2 * k];
+        while (*si >= initial_mass * mass_scaling) {
+          OBerg nb; memset(&nb, 0, sizeof(nb));
+          nb.lon = 0.25 * ((G(o, lon, i, j) + G(o, lon, i - 1, j - 1)) + (G(o, lon, i - 1, j) + G(o, lon, i, j - 1)));
+          nb.lat = 0.25 * ((G(o, lat, i, j) + G(o, lat, i - 1, j - 1)) + (G(o, lat, i - 1, j) + G(o, lat, i, j - 1)));
+          double xi, yj;
+          int lret = pos_within_cell(o, nb.lon, nb.lat, i, j, &xi, &yj);
+          if (!lret) { o_fatal(o, "KID, calve_icebergs: berg is not in the correct cell!"); return; }
+          nb.ine = i; nb.jne = j; nb.xi = xi; nb.yj = yj;
+          nb.uvel = 0.; nb.vvel = 0.;
+          nb.uvel_prev = 0.; nb.vvel_prev = 0.; nb.uvel_old = 0.; nb.vvel_old = 0.;
+          nb.lon_old = nb.lon; nb.lat_old = nb.lat;
+          nb.fl_k = 0.;
+          nb.mass = initial_mass; nb.thickness = initial_thickness;
+          nb.width = initial_width; nb.length = initial_length;
+          nb.start_lon = nb.lon; nb.start_lat = nb.lat;
+          nb.start_year = o->current_year;
+          nb.id = generate_id(o, i, j);
+          nb.start_day = o->current_yearday + ddt / 86400.;
+          nb.start_mass = initial_mass;
+          nb.mass_scaling = mass_scaling;
+          nb.heat_density = G(o, stored_heat, i, j) / (*si);
+          if (!p->old_interp_flds_order)
+            interp_flds(o, nb.lon, nb.lat, i, j, xi, yj, 0., 0., &nb.uo, &nb.vo, &nb.ui, &nb.vi, &nb.ua,
+                        &nb.va, &nb.ssh_x, &nb.ssh_y, &nb.sst, &nb.sss, &nb.cn, &nb.hi, &nb.od);
+          insert_berg_into_list(&G(o, list, i, j), new_berg_copy(&nb));
+          double calved_to_berg = initial_mass * mass_scaling;
+          double heat_to_berg = calved_to_berg * nb.heat_density;
+          G(o, stored_heat, i, j) = G(o, stored_heat, i, j) - heat_to_berg;
+          o->cnt.net_heat_to_bergs += heat_to_berg;
+          *si = *si - calved_to_berg;
+          o->cnt.net_calving_to_bergs += calved_to_berg;
+          o->real_calving[IDX(o, i, j) + n2 * k] += calved_to_berg / p->dt;
+          ddt = ddt - p->dt * 2. / 17.;
+          o->cnt.nbergs_calved++;
+        }
+      }
+}
+
+/* -------------------------- unpack (receiver side) F:3468-3703, single rank */
+static int place_received_berg(Oracle* o, OBerg* vals, int wrap_di) {
+  /* "These quantities no longer need to be passed between processors" F:3573-3577 */
+  vals->uvel_old = vals->uvel; vals->vvel_old = vals->vvel;
+  vals->lon_old = vals->lon; vals->lat_old = vals->lat;
+  const KidDomain* d = &o->d;
+  /* A receiving PE of a >=2-PE-wide cyclic domain does not contain the sender's
+   * index ine, its structured guess (F:5993) lands outside as well, and the scan
+   * (F:6002-6007) finds the periodic image cell ine -/+ gni.  Restated directly. */
+  int oi = vals->ine + wrap_di, oj = vals->jne;
+  int found = 0;
+  if (!(oi - 1 < d->isd || oi > d->ied || oj - 1 < d->jsd || oj > d->jed))
+    if (is_point_in_cell(o, vals->lon, vals->lat, oi, oj)) found = 1;
+  if (!found) found = find_cell_wide(o, vals->lon, vals->lat, &oi, &oj);
+  if (!found) { o_fatal(o, "KID, unpack_berg_from_buffer: can not find a cell to place berg in!"); return 0; }
+  vals->ine = oi; vals->jne = oj;
+  pos_within_cell(o, vals->lon, vals->lat, vals->ine, vals->jne, &vals->xi, &vals->yj);
+  insert_berg_into_list(&G(o, list, oi, oj), vals);
+  return 1;
+}
+
+/* F:2997-3247 for one rank */
+static void send_bergs_to_other_pes(Oracle* o) {
+  const KidDomain* d = &o->d;
+  int64_t nsent = 0, nrecv = 0;
+  /* E/W */
+  OBerg* inbox = NULL; /* singly linked through ->next, in pack order */
+  OBerg** tail = &inbox;
+  for (int grdj = d->jsd; grdj <= d->jed; grdj++)
+    for (int grdi = d->isd; grdi <= d->ied; grdi++) {
+      OBerg* this_ = G(o, list, grdi, grdj);
+      while (this_) {
+        OBerg* nx = this_->next;
+        if (this_->halo_berg < 0.5 && (this_->ine > d->iec || this_->ine < d->isc)) {
+          int east = this_->ine > d->iec;
+          if (this_->prev) this_->prev->next = this_->next; else G(o, list, grdi, grdj) = this_->next;
+          if (this_->next) this_->next->prev = this_->prev;
+          nsent++;
+          int pe = east ? d->pe_E : d->pe_W;
+          if (pe == d->rank) {
+            this_->prev = NULL; this_->next = NULL;
+            this_->conglom_id = east ? -d->gni : d->gni; /* scratch: wrap offset */
+            *tail = this_; tail = &this_->next;
+          } else {
+            clear_berg_from_partners_bonds(o, this_); free_bonds(this_); free(this_); /* NULL_PE: berg leaves the model */
+          }
+        }
+        this_ = nx;
+      }
+    }
+  while (inbox) {
+    OBerg* b = inbox; inbox = b->next; b->next = NULL;
+    int w = b->conglom_id; b->conglom_id = 0;
+    if (place_received_berg(o, b, w)) nrecv++; else { free_bonds(b); free(b); }
+  }
+  /* N/S */
+  inbox = NULL; tail = &inbox;
+  for (int grdj = d->jsd; grdj <= d->jed; grdj++)
+    for (int grdi = d->isd; grdi <= d->ied; grdi++) {
+      OBerg* this_ = G(o, list, grdi, grdj);
+      while (this_) {
+        OBerg* nx = this_->next;
+        if (this_->halo_berg < 0.5 && (this_->jne > d->jec || this_->jne < d->jsc)) {
+          int north = this_->jne > d->jec;
+          if (this_->prev) this_->prev->next = this_->next; else G(o, list, grdi, grdj) = this_->next;
+          if (this_->next) this_->next->prev = this_->prev;
+          nsent++;
+          int pe = north ? d->pe_N : d->pe_S;
+          if (pe == d->rank) { /* cyclic-y single rank (not used by the reference tests) */
+            o_fatal(o, "oracle: cyclic-y migration not restated");
+          }
+          clear_berg_from_partners_bonds(o, this_); free_bonds(this_); free(this_);
+        }
+        this_ = nx;
+      }
+    }
+  o->cnt.n_sent = nsent; o->cnt.n_received = nrecv;
+}
+
+/* F:5128-5169 */
+static void update_latlon(Oracle* o) {
+  const KidDomain* d = &o->d;
+  if (o->p.Lx > 0.) {
+    if ((G(o, lon, d->isc - 1, d->jsc - 1) == o->minlon_c) || (G(o, lon, d->iec, d->jec) == o->maxlon_c)) {
+      for (int grdj = d->jsd; grdj <= d->jed; grdj++)
+        for (int grdi = d->isd; grdi <= d->ied; grdi++)
+          for (OBerg* berg = G(o, list, grdi, grdj); berg; berg = berg->next)
+            if ((!o->p.mts) || (berg->halo_berg <= 1)) {
+              double dlon = berg->lon - berg->lon_old, dlat = berg->lat - berg->lat_old;
+              berg->lon = bilin(o, o->lon, berg->ine, berg->jne, berg->xi, berg->yj);
+              berg->lat = bilin(o, o->lat, berg->ine, berg->jne, berg->xi, berg->yj);
+              berg->lon_old = berg->lon - dlon;
+              berg->lat_old = berg->lat - dlat;
+              pos_within_cell(o, berg->lon, berg->lat, berg->ine, berg->jne, &berg->xi, &berg->yj);
+            }
+    }
+  }
+}
+
+static void delete_all_bergs_in_list(Oracle* o, int grdj, int grdi) {
+  OBerg* this_ = G(o, list, grdi, grdj);
+  while (this_) {
+    OBerg* k = this_; this_ = this_->next;
+    delete_iceberg_from_list(o, &G(o, list, grdi, grdj), k);
+  }
+}
+
+/* F:1800-2131 for one rank: halo copies are made only through the cyclic-x
+ * "neighbour" (self).  Bond lists are copied as (id, ine, jne) stubs and
+ * reconnected by connect_all_bonds (bond rows; phase 2 of the oracle). */
+static void oracle_copy_bonds(OBerg* dst, const OBerg* src);
+static void update_halo_icebergs(Oracle* o) {
+  const KidDomain* d = &o->d;
+  int hw = o->p.halo;
+  for (int grdj = d->jsd; grdj <= d->jsc - 1; grdj++) for (int grdi = d->isd; grdi <= d->ied; grdi++) delete_all_bergs_in_list(o, grdj, grdi);
+  for (int grdj = d->jec + 1; grdj <= d->jed; grdj++) for (int grdi = d->isd; grdi <= d->ied; grdi++) delete_all_bergs_in_list(o, grdj, grdi);
+  for (int grdj = d->jsd; grdj <= d->jed; grdj++) for (int grdi = d->isd; grdi <= d->isc - 1; grdi++) delete_all_bergs_in_list(o, grdj, grdi);
+  for (int grdj = d->jsd; grdj <= d->jed; grdj++) for (int grdi = d->iec + 1; grdi <= d->ied; grdi++) delete_all_bergs_in_list(o, grdj, grdi);
+  OBerg *inE = NULL, **tE = &inE, *inW = NULL, **tW = &inW;
+  if (d->pe_E == d->rank) {
+    for (int grdj = d->jsc; grdj <= d->jec; grdj++)
+      for (int grdi = d->iec - hw + 2; grdi <= d->iec; grdi++)
+        for (OBerg* b = G(o, list, grdi, grdj); b; b = b->next) {
+          OBerg* c = new_berg_copy(b); c->first_bond = NULL; oracle_copy_bonds(c, b);
+          c->halo_berg = 1.; *tE = c; tE = &c->next;
+        }
+  }
+  if (d->pe_W == d->rank) {
+    for (int grdj = d->jsc; grdj <= d->jec; grdj++)
+      for (int grdi = d->isc; grdi <= d->isc + hw - 1; grdi++)
+        for (OBerg* b = G(o, list, grdi, grdj); b; b = b->next) {
+          OBerg* c = new_berg_copy(b); c->first_bond = NULL; oracle_copy_bonds(c, b);
+          c->halo_berg = 1.; *tW = c; tW = &c->next;
+        }
+  }
+  /* received from west = what was sent east (wrap -gni), then from east */
+  while (inE) { OBerg* b = inE; inE = b->next; b->next = NULL; if (!place_received_berg(o, b, -d->gni)) { free_bonds(b); free(b); } }
+  while (inW) { OBerg* b = inW; inW = b->next; b->next = NULL; if (!place_received_berg(o, b, d->gni)) { free_bonds(b); free(b); } }
+  /* N/S: no neighbour on a single non-cyclic-y rank */
+}
+
+/* ----------------------------------------------------------- bonds (F:4818) */
+/* form_a_bond F:4818-4883: new bond goes to the FRONT of the berg's list */
+static OBond* form_a_bond(Oracle* o, OBerg* berg, int64_t other_id, int other_ine, int other_jne,
+                          OBerg* other_berg) {
+  (void)o;
+  if (berg->id == other_id) return NULL;
+  OBond* nb = (OBond*)calloc(1, sizeof(OBond));
+  nb->other_berg = other_berg;
+  nb->other_id = other_id;
+  nb->other_berg_ine = other_ine; nb->other_berg_jne = other_jne;
+  nb->length = 0.;
+  nb->next_bond = berg->first_bond;
+  if (berg->first_bond) berg->first_bond->prev_bond = nb;
+  berg->first_bond = nb;
+  return nb;
+}
+
+static void oracle_copy_bonds(OBerg* dst, const OBerg* src) {
+  /* pack order = list order; unpack forms each at the front => reversed (F:3336-3354, F:3677-3698) */
+  dst->first_bond = NULL;
+  for (const OBond* cb = src->first_bond; cb; cb = cb->next_bond) {
+    OBond* nb = (OBond*)calloc(1, sizeof(OBond));
+    *nb = *cb;
+    nb->other_berg = NULL; nb->other_bond = NULL; nb->prev_bond = NULL;
+    nb->next_bond = dst->first_bond;
+    if (dst->first_bond) dst->first_bond->prev_bond = nb;
+    dst->first_bond = nb;
+  }
+}
+
+/* ------------------------------------------- mpp_update_domains, one rank */
+static void halo_update(Oracle* o, double* f) {
+  const KidDomain* d = &o->d;
+  if (d->cyclic_x && d->pe_E == d->rank) {
+    int ni = d->iec - d->isc + 1;
+    for (int j = d->jsc; j <= d->jec; j++) {
+      for (int i = d->isd; i < d->isc; i++) f[IDX(o, i, j)] = f[IDX(o, i + ni, j)];
+      for (int i = d->iec + 1; i <= d->ied; i++) f[IDX(o, i, j)] = f[IDX(o, i - ni, j)];
+    }
+  }
+}
+
+static double* dalloc(size_t n, double v) {
+  double* a = (double*)malloc(sizeof(double) * n);
+  for (size_t k = 0; k < n; k++) a[k] = v;
+  return a;
+}
+
+const char* oracle_last_error(const Oracle* o) { return o ? o->err : "oracle: null handle"; }
+
+/* ice_bergs_framework_init F:641-1712 (grid part) */
+Oracle* oracle_create(const KidParams* p, const KidDomain* dom, int32_t year, double yearday,
+                      const double* lon, const double* lat, const double* wet, const double* dx,
+                      const double* dy, const double* area, const double* cos_rot,
+                      const double* sin_rot, const double* ocean_depth, int32_t fractional_area) {
+  Oracle* o = (Oracle*)calloc(1, sizeof(Oracle));
+  o->p = *p; o->d = *dom;
+  o->current_year = year; o->current_yearday = yearday;
+  o->first_call_accum = 1; o->nthreads = 1; o->mts_part = 1;
+  const KidDomain* d = &o->d;
+  o->nid = d->ied - d->isd + 1; o->njd = d->jed - d->jsd + 1;
+  size_t n2 = (size_t)o->nid * o->njd;
+  const double big_number = 1.0E15;
+  o->lon = dalloc(n2, big_number); o->lat = dalloc(n2, big_number);
+  o->lonc = dalloc(n2, 0.); o->latc = dalloc(n2, 0.);
+  o->dx = dalloc(n2, 0.); o->dy = dalloc(n2, 0.); o->area = dalloc(n2, 0.); o->msk = dalloc(n2, 0.);
+  o->cosr = dalloc(n2, 1.); o->sinr = dalloc(n2, 0.); o->ocean_depth = dalloc(n2, 0.);
+  double** z[] = {&o->uo, &o->vo, &o->ui, &o->vi, &o->ua, &o->va, &o->ssh, &o->sst, &o->sss, &o->cn, &o->hi,
+                  &o->calving, &o->calving_hflx, &o->floating_melt, &o->berg_melt, &o->melt_buoy,
+                  &o->melt_eros, &o->melt_conv, &o->bergy_src, &o->bergy_melt, &o->bergy_mass,
+                  &o->fl_bits_src, &o->fl_bits_melt, &o->melt_buoy_fl, &o->melt_eros_fl, &o->melt_conv_fl,
+                  &o->fl_parent_melt, &o->fl_child_melt, &o->stored_heat, &o->tmp, &o->mass,
+                  &o->spread_mass, &o->spread_area, &o->ustar_iceberg, &o->spread_uvel, &o->spread_vvel};
+  for (size_t k = 0; k < sizeof(z) / sizeof(z[0]); k++) *z[k] = dalloc(n2, 0.);
+  o->stored_ice = dalloc(n2 * KID_NCLASSES, 0.);
+  o->real_calving = dalloc(n2 * KID_NCLASSES, 0.);
+  o->iceberg_counter_grd = (int32_t*)calloc(n2, sizeof(int32_t));
+  o->list = (OBerg**)calloc(n2, sizeof(OBerg*));
+  if (p->runge_not_verlet) o_fatal(o, "oracle: only Verlet (Runge_not_Verlet=.false.) is restated");
+  if (p->tidal_drift > 0.) o_fatal(o, "oracle: tidal_drift needs the FMS random number stream (external)");
+  if (p->melt_icebergs_as_ice_shelf || p->use_mixed_melting) o_fatal(o, "oracle: ice-shelf melt (find_basal_melt) is second tier, not restated");
+  if (p->add_iceberg_thickness_to_ssh) o_fatal(o, "oracle: add_iceberg_thickness_to_SSH needs spread_mass (next row)");
+  int nic = d->iec - d->isc + 1, njc = d->jec - d->jsc + 1;
+  /* F:1021-1056 */
+  for (int j = d->jsc; j <= d->jec; j++)
+    for (int i = d->isc; i <= d->iec; i++) {
+      size_t s = (size_t)(i - d->isc) + (size_t)(j - d->jsc) * nic;
+      G(o, lon, i, j) = lon[s]; G(o, lat, i, j) = lat[s];
+      G(o, area, i, j) = area[s];
+      if (fractional_area) G(o, area, i, j) = area[s] * (4. * p->pi * p->radius * p->radius);
+      if (ocean_depth) G(o, ocean_depth, i, j) = ocean_depth[s];
+    }
+  for (int j = d->jsc - 1; j <= d->jec + 1; j++)
+    for (int i = d->isc - 1; i <= d->iec + 1; i++) {
+      size_t s = (size_t)(i - (d->isc - 1)) + (size_t)(j - (d->jsc - 1)) * (nic + 2);
+      G(o, dx, i, j) = dx[s]; G(o, dy, i, j) = dy[s]; G(o, msk, i, j) = wet[s];
+      G(o, cosr, i, j) = cos_rot[s]; G(o, sinr, i, j) = sin_rot[s];
+    }
+  (void)njc;
+  /* F:1058-1066 */
+  halo_update(o, o->lon); halo_update(o, o->lat); halo_update(o, o->dy); halo_update(o, o->dx);
+  halo_update(o, o->area); halo_update(o, o->msk); halo_update(o, o->cosr); halo_update(o, o->sinr);
+  halo_update(o, o->ocean_depth);
+  /* F:1068-1094 */
+  for (int j = d->jsc - 1; j >= d->jsd; j--) for (int i = d->isd; i <= d->ied; i++) {
+    if (G(o, lon, i, j) >= big_number) G(o, lon, i, j) = G(o, lon, i, j + 1);
+    if (G(o, lat, i, j) >= big_number) G(o, lat, i, j) = 2. * G(o, lat, i, j + 1) - G(o, lat, i, j + 2);
+  }
+  for (int j = d->jsc - 1; j >= d->jsd; j--) for (int i = d->isd; i <= d->ied; i++) {
+    if (G(o, lon, i, j) >= big_number) G(o, lon, i, j) = 2. * G(o, lon, i, j + 1) - G(o, lon, i, j + 2);
+    if (G(o, lat, i, j) >= big_number) G(o, lat, i, j) = 2. * G(o, lat, i, j + 1) - G(o, lat, i, j + 2);
+  }
+  for (int j = d->jec + 1; j <= d->jed; j++) for (int i = d->isd; i <= d->ied; i++) {
+    if (G(o, lon, i, j) >= big_number) G(o, lon, i, j) = 2. * G(o, lon, i, j - 1) - G(o, lon, i, j - 2);
+    if (G(o, lat, i, j) >= big_number) G(o, lat, i, j) = 2. * G(o, lat, i, j - 1) - G(o, lat, i, j - 2);
+  }
+  for (int i = d->isc - 1; i >= d->isd; i--) for (int j = d->jsd; j <= d->jed; j++) {
+    if (G(o, lon, i, j) >= big_number) G(o, lon, i, j) = 2. * G(o, lon, i + 1, j) - G(o, lon, i + 2, j);
+    if (G(o, lat, i, j) >= big_number) G(o, lat, i, j) = 2. * G(o, lat, i + 1, j) - G(o, lat, i + 2, j);
+  }
+  for (int i = d->iec + 1; i <= d->ied; i++) for (int j = d->jsd; j <= d->jed; j++) {
+    if (G(o, lon, i, j) >= big_number) G(o, lon, i, j) = 2. * G(o, lon, i - 1, j) - G(o, lon, i - 2, j);
+    if (G(o, lat, i, j) >= big_number) G(o, lat, i, j) = 2. * G(o, lat, i - 1, j) - G(o, lat, i - 2, j);
+  }
+  /* F:1113-1118 */
+  if ((!o->p.grid_is_latlon) && (o->p.Lx == 360.)) o->p.Lx = -1.;
+  double Lx = o->p.Lx;
+  /* F:1122-1143 */
+  if (Lx > 0.) {
+    int j = d->jsc;
+    for (int i = d->isc + 1; i <= d->ied; i++) {
+      double lon_mod = AMAP(G(o, lon, i, j), G(o, lon, i - 1, j), Lx);
+      if (fabs(G(o, lon, i, j) - lon_mod) > (Lx / 2.)) G(o, lon, i, j) = lon_mod;
+    }
+    for (int i = d->isc - 1; i >= d->isd; i--) {
+      double lon_mod = AMAP(G(o, lon, i, j), G(o, lon, i + 1, j), Lx);
+      if (fabs(G(o, lon, i, j) - lon_mod) > (Lx / 2.)) G(o, lon, i, j) = lon_mod;
+    }
+    for (j = d->jsc + 1; j <= d->jed; j++) for (int i = d->isd; i <= d->ied; i++) {
+      double lon_mod = AMAP(G(o, lon, i, j), G(o, lon, i, j - 1), Lx);
+      if (fabs(G(o, lon, i, j) - (lon_mod)) > (Lx / 2.)) G(o, lon, i, j) = lon_mod;
+    }
+    for (j = d->jsc - 1; j >= d->jsd; j--) for (int i = d->isd; i <= d->ied; i++) {
+      double lon_mod = AMAP(G(o, lon, i, j), G(o, lon, i, j + 1), Lx);
+      if (fabs(G(o, lon, i, j) - lon_mod) > (Lx / 2.)) G(o, lon, i, j) = lon_mod;
+    }
+  }
+  /* F:1148-1153 */
+  for (int j = d->jsd + 1; j <= d->jed; j++) for (int i = d->isd + 1; i <= d->ied; i++) {
+    G(o, lonc, i, j) = 0.25 * ((G(o, lon, i, j) + G(o, lon, i - 1, j - 1)) + (G(o, lon, i - 1, j) + G(o, lon, i, j - 1)));
+    G(o, latc, i, j) = 0.25 * ((G(o, lat, i, j) + G(o, lat, i - 1, j - 1)) + (G(o, lat, i - 1, j) + G(o, lat, i, j - 1)));
+  }
+  /* derived parameters: F:1264, F:1296-1301, F:1312, F:1433-1436, F:1453-1464, F:1483 */
+  KidParams* q = &o->p;
+  if (!q->iceberg_bonds_on) q->max_bonds = 0;
+  if (q->mts) {
+    if (q->mts_sub_steps == -1) { o->mts_fast_dt = 0.3 / sqrt(q->spring_coef); q->mts_sub_steps = (int)ceil(q->dt / o->mts_fast_dt); }
+    o->mts_fast_dt = q->dt / q->mts_sub_steps;
+  }
+  if (q->contact_spring_coef <= 0.) q->contact_spring_coef = q->spring_coef;
+  if (q->dem) q->explicit_inner_mts = 1;
+  o->dem_K_damp = 2. * q->dem_spring_coef / (3. * (1. - q->poisson * q->poisson));
+  if (q->constant_interaction_LW) {
+    o->constant_area = q->constant_length * q->constant_width;
+    if (q->hexagonal_icebergs) o->constant_radius = sqrt(o->constant_area / (2. * sqrt(3.)));
+    else if (q->iceberg_bonds_on) o->constant_radius = 0.5 * sqrt(o->constant_area);
+    else o->constant_radius = sqrt(o->constant_area / q->pi);
+  }
+  q->old_interp_flds_order = !(q->mts || q->dem || q->footloose);
+  /* contact cells F:1492-1519 */
+  if (q->contact_distance > 0) {
+    double pi_180 = q->pi / 180.;
+    double dx_dlon = 1, dy_dlat = 1;
+    if (q->grid_is_latlon) dy_dlat = pi_180 * q->Rearth;
+    int maxk = 0;
+    for (int j = d->jsd; j <= d->jed; j++) for (int i = d->isd; i <= d->ied; i++) {
+      if (q->grid_is_latlon) dx_dlon = pi_180 * q->Rearth * cos(G(o, lat, i, j) * pi_180);
+      double lon_ref = G(o, lon, i, j);
+      int k = 0;
+      while ((k + i) < d->ied) {
+        k++;
+        double ddx = (G(o, lon, k + i, j) - lon_ref) * dx_dlon;
+        if (k > maxk) maxk = k;
+        if (ddx >= q->contact_distance) break;
+      }
+    }
+    double ddy = (G(o, lat, d->isc, d->jsc + 1) - G(o, lat, d->isc, d->jsc)) * dy_dlat;
+    q->contact_cells_lon = imax(maxk, 1);
+    q->contact_cells_lat = imax((int)ceil(q->contact_distance / ddy), 1);
+  } else { q->contact_cells_lon = 1; q->contact_cells_lat = 1; }
+  /* F:1557-1559 (mpp_max/min over ranks == local on one rank) */
+  o->maxlon_c = G(o, lon, d->iec, d->jec); o->minlon_c = G(o, lon, d->isc - 1, d->jsc - 1);
+  return o;
+}
+
+void oracle_destroy(Oracle* o) {
+  if (!o) return;
+  size_t n2 = (size_t)o->nid * o->njd;
+  for (size_t k = 0; k < n2; k++) {
+    OBerg* b = o->list[k];
+    while (b) { OBerg* n = b->next; free_bonds(b); free(b); b = n; }
+  }
+  double* z[] = {o->lon, o->lat, o->lonc, o->latc, o->dx, o->dy, o->area, o->msk, o->cosr, o->sinr, o->ocean_depth,
+                 o->uo, o->vo, o->ui, o->vi, o->ua, o->va, o->ssh, o->sst, o->sss, o->cn, o->hi, o->calving,
+                 o->calving_hflx, o->floating_melt, o->berg_melt, o->melt_buoy, o->melt_eros, o->melt_conv,
+                 o->bergy_src, o->bergy_melt, o->bergy_mass, o->fl_bits_src, o->fl_bits_melt, o->melt_buoy_fl,
+                 o->melt_eros_fl, o->melt_conv_fl, o->fl_parent_melt, o->fl_child_melt, o->stored_heat,
+                 o->stored_ice, o->real_calving, o->tmp, o->mass, o->spread_mass, o->spread_area,
+                 o->ustar_iceberg, o->spread_uvel, o->spread_vvel};
+  for (size_t k = 0; k < sizeof(z) / sizeof(z[0]); k++) free(z[k]);
+  free(o->iceberg_counter_grd); free(o->list); free(o);
+}
+
+#define CGET(c, name, k, dflt) ((c)->name ? (c)->name[k] : (dflt))
+
+/* read_restart_bergs (fmsio:606-975): positions are re-located unless the file
+ * carries ine/jne (ignore_ij_restart=.false.), xi,yj recomputed fmsio:871,
+ * *_old set from current fmsio:828-831. */
+int32_t oracle_set_bergs(Oracle* o, int64_t n, const KidBergColumns* c) {
+  const KidDomain* d = &o->d;
+  for (int64_t k = 0; k < n; k++) {
+    OBerg b; memset(&b, 0, sizeof(b));
+    b.lon = c->lon[k]; b.lat = c->lat[k];
+    b.uvel = CGET(c, uvel, k, 0.); b.vvel = CGET(c, vvel, k, 0.);
+    b.mass = c->mass[k]; b.thickness = c->thickness[k]; b.width = c->width[k]; b.length = c->length[k];
+    b.axn = CGET(c, axn, k, 0.); b.ayn = CGET(c, ayn, k, 0.); b.bxn = CGET(c, bxn, k, 0.); b.byn = CGET(c, byn, k, 0.);
+    b.uvel_prev = CGET(c, uvel_prev, k, 0.); b.vvel_prev = CGET(c, vvel_prev, k, 0.);
+    b.start_lon = CGET(c, start_lon, k, b.lon); b.start_lat = CGET(c, start_lat, k, b.lat);
+    b.start_day = CGET(c, start_day, k, 0.); b.start_mass = CGET(c, start_mass, k, b.mass);
+    b.mass_scaling = CGET(c, mass_scaling, k, 1.); b.mass_of_bits = CGET(c, mass_of_bits, k, 0.);
+    b.mass_of_fl_bits = CGET(c, mass_of_fl_bits, k, 0.);
+    b.mass_of_fl_bergy_bits = CGET(c, mass_of_fl_bergy_bits, k, 0.);
+    b.fl_k = CGET(c, fl_k, k, 0.); b.heat_density = CGET(c, heat_density, k, 0.);
+    b.halo_berg = CGET(c, halo_berg, k, 0.); b.static_berg = CGET(c, static_berg, k, 0.);
+    b.start_year = CGET(c, start_year, k, 0);
+    b.axn_fast = CGET(c, axn_fast, k, 0.); b.ayn_fast = CGET(c, ayn_fast, k, 0.);
+    b.bxn_fast = CGET(c, bxn_fast, k, 0.); b.byn_fast = CGET(c, byn_fast, k, 0.);
+    b.ang_vel = CGET(c, ang_vel, k, 0.); b.ang_accel = CGET(c, ang_accel, k, 0.); b.rot = CGET(c, rot, k, 0.);
+    b.conglom_id = CGET(c, conglom_id, k, 0);
+    int have_ij = (c->ine && c->jne);
+    int found = 0;
+    if (have_ij) {
+      b.ine = c->ine[k]; b.jne = c->jne[k];
+      found = !(b.ine - 1 < d->isd || b.ine > d->ied || b.jne - 1 < d->jsd || b.jne > d->jed);
+    } else {
+      found = find_cell(o, b.lon, b.lat, &b.ine, &b.jne);
+    }
+    if (!found) continue; /* not on this rank */
+    if (b.ine < d->isc || b.ine > d->iec || b.jne < d->jsc || b.jne > d->jec) continue;
+    pos_within_cell(o, b.lon, b.lat, b.ine, b.jne, &b.xi, &b.yj);
+    if (c->id) b.id = c->id[k]; else b.id = generate_id(o, b.ine, b.jne);
+    b.uvel_old = CGET(c, uvel_old, k, b.uvel); b.vvel_old = CGET(c, vvel_old, k, b.vvel);
+    b.lon_old = CGET(c, lon_old, k, b.lon); b.lat_old = CGET(c, lat_old, k, b.lat);
+    insert_berg_into_list(&G(o, list, b.ine, b.jne), new_berg_copy(&b));
+  }
+  o->restarted = 1;
+  return o->fatal ? KID_ERR_STATE : KID_OK;
+}
+
+int64_t oracle_count_bergs(const Oracle* o, int32_t include_halo) {
+  const KidDomain* d = &o->d;
+  int64_t n = 0;
+  int j0 = include_halo ? d->jsd : d->jsc, j1 = include_halo ? d->jed : d->jec;
+  int i0 = include_halo ? d->isd : d->isc, i1 = include_halo ? d->ied : d->iec;
+  for (int j = j0; j <= j1; j++) for (int i = i0; i <= i1; i++)
+    for (const OBerg* b = G(o, list, i, j); b; b = b->next) n++;
+  return n;
+}
+
+#define CPUT(c, name, k, v) do { if ((c)->name) (c)->name[k] = (v); } while (0)
+
+int32_t oracle_get_bergs(const Oracle* o, int64_t* n, KidBergColumns* c, int32_t include_halo) {
+  const KidDomain* d = &o->d;
+  int64_t k = 0, cap = *n;
+  int j0 = include_halo ? d->jsd : d->jsc, j1 = include_halo ? d->jed : d->jec;
+  int i0 = include_halo ? d->isd : d->isc, i1 = include_halo ? d->ied : d->iec;
+  for (int j = j0; j <= j1; j++) for (int i = i0; i <= i1; i++)
+    for (const OBerg* b = G(o, list, i, j); b; b = b->next) {
+      if (k < cap) {
+        CPUT(c, lon, k, b->lon); CPUT(c, lat, k, b->lat); CPUT(c, uvel, k, b->uvel); CPUT(c, vvel, k, b->vvel);
+        CPUT(c, mass, k, b->mass); CPUT(c, thickness, k, b->thickness); CPUT(c, width, k, b->width); CPUT(c, length, k, b->length);
+        CPUT(c, axn, k, b->axn); CPUT(c, ayn, k, b->ayn); CPUT(c, bxn, k, b->bxn); CPUT(c, byn, k, b->byn);
+        CPUT(c, uvel_prev, k, b->uvel_prev); CPUT(c, vvel_prev, k, b->vvel_prev);
+        CPUT(c, uvel_old, k, b->uvel_old); CPUT(c, vvel_old, k, b->vvel_old); CPUT(c, lon_old, k, b->lon_old); CPUT(c, lat_old, k, b->lat_old);
+        CPUT(c, start_lon, k, b->start_lon); CPUT(c, start_lat, k, b->start_lat); CPUT(c, start_day, k, b->start_day); CPUT(c, start_mass, k, b->start_mass);
+        CPUT(c, mass_scaling, k, b->mass_scaling); CPUT(c, mass_of_bits, k, b->mass_of_bits);
+        CPUT(c, mass_of_fl_bits, k, b->mass_of_fl_bits); CPUT(c, mass_of_fl_bergy_bits, k, b->mass_of_fl_bergy_bits);
+        CPUT(c, fl_k, k, b->fl_k); CPUT(c, heat_density, k, b->heat_density);
+        CPUT(c, halo_berg, k, b->halo_berg); CPUT(c, static_berg, k, b->static_berg);
+        CPUT(c, xi, k, b->xi); CPUT(c, yj, k, b->yj);
+        CPUT(c, axn_fast, k, b->axn_fast); CPUT(c, ayn_fast, k, b->ayn_fast); CPUT(c, bxn_fast, k, b->bxn_fast); CPUT(c, byn_fast, k, b->byn_fast);
+        CPUT(c, ang_vel, k, b->ang_vel); CPUT(c, ang_accel, k, b->ang_accel); CPUT(c, rot, k, b->rot);
+        CPUT(c, uo, k, b->uo); CPUT(c, vo, k, b->vo); CPUT(c, ui, k, b->ui); CPUT(c, vi, k, b->vi);
+        CPUT(c, ua, k, b->ua); CPUT(c, va, k, b->va); CPUT(c, ssh_x, k, b->ssh_x); CPUT(c, ssh_y, k, b->ssh_y);
+        CPUT(c, sst, k, b->sst); CPUT(c, sss, k, b->sss); CPUT(c, cn, k, b->cn); CPUT(c, hi, k, b->hi); CPUT(c, od, k, b->od);
+        CPUT(c, start_year, k, b->start_year); CPUT(c, ine, k, b->ine); CPUT(c, jne, k, b->jne);
+        CPUT(c, n_bonds, k, b->n_bonds); CPUT(c, conglom_id, k, b->conglom_id);
+        CPUT(c, id, k, b->id);
+      }
+      k++;
+    }
+  *n = k;
+  return (k > cap) ? KID_ERR_CAPACITY : KID_OK;
+}
+
+int32_t oracle_set_calving_state(Oracle* o, const double* stored_ice, const double* stored_heat, const int32_t* counter) {
+  size_t n2 = (size_t)o->nid * o->njd;
+  if (stored_ice) memcpy(o->stored_ice, stored_ice, sizeof(double) * n2 * KID_NCLASSES);
+  if (stored_heat) memcpy(o->stored_heat, stored_heat, sizeof(double) * n2);
+  if (counter) memcpy(o->iceberg_counter_grd, counter, sizeof(int32_t) * n2);
+  o->restarted = 1;
+  return KID_OK;
+}
+int32_t oracle_get_calving_state(const Oracle* o, double* stored_ice, double* stored_heat, int32_t* counter) {
+  size_t n2 = (size_t)o->nid * o->njd;
+  if (stored_ice) memcpy(stored_ice, o->stored_ice, sizeof(double) * n2 * KID_NCLASSES);
+  if (stored_heat) memcpy(stored_heat, o->stored_heat, sizeof(double) * n2);
+  if (counter) memcpy(counter, o->iceberg_counter_grd, sizeof(int32_t) * n2);
+  return KID_OK;
+}
+
+/* I:8272-8296 */
+static void invert_tau_for_du(Oracle* o) {
+  size_t n2 = (size_t)o->nid * o->njd;
+  const double cd = 0.0015;
+  for (size_t k = 0; k < n2; k++) {
+    double tau2 = o->ua[k] * o->ua[k] + o->va[k] * o->va[k];
+    double cddvmod = sqrt(cd * sqrt(tau2));
+    if (cddvmod != 0.) { o->ua[k] = o->ua[k] / cddvmod; o->va[k] = o->va[k] / cddvmod; }
+    else { o->ua[k] = 0.; o->va[k] = 0.; }
+  }
+}
+
+/* forcing ingest, I:5125-5156 and I:5203-5383 */
+static void ingest_forcing(Oracle* o, const double* calving, const double* uo, const double* vo,
+                           const double* ui, const double* vi, const double* tauxa,
+                           const double* tauya, const double* ssh, const double* sst,
+                           const double* calving_hflx, const double* cn, const double* hi,
+                           int stagger, int stress_stagger, const double* sss) {
+  const KidDomain* d = &o->d;
+  size_t n2 = (size_t)o->nid * o->njd;
+  int nic = d->iec - d->isc + 1;
+  double* zero[] = {o->floating_melt, o->berg_melt, o->melt_buoy, o->melt_eros, o->melt_conv, o->bergy_src,
+                    o->bergy_melt, o->bergy_mass, o->fl_bits_src, o->fl_bits_melt, o->melt_buoy_fl,
+                    o->melt_eros_fl, o->melt_conv_fl, o->fl_parent_melt, o->fl_child_melt, o->mass,
+                    o->spread_area, o->ustar_iceberg, o->spread_uvel, o->spread_vvel};
+  for (size_t k = 0; k < sizeof(zero) / sizeof(zero[0]); k++) memset(zero[k], 0, sizeof(double) * n2);
+#define C2(a, i, j) a[(size_t)((i) - d->isc) + (size_t)((j) - d->jsc) * nic]
+#define C3(a, i, j) a[(size_t)((i) - (d->isc - 1)) + (size_t)((j) - (d->jsc - 1)) * (nic + 2)]
+  for (int j = d->jsc; j <= d->jec; j++) for (int i = d->isc; i <= d->iec; i++) {
+    G(o, calving_hflx, i, j) = C2(calving_hflx, i, j) * G(o, msk, i, j);
+    G(o, calving, i, j) = C2(calving, i, j) * G(o, msk, i, j);
+  }
+  /* tau_calving>0 (running mean) is host-side bookkeeping: not restated */
+  for (size_t k = 0; k < n2; k++) {
+    o->calving[k] = o->calving[k] * o->msk[k] * o->area[k];
+    o->calving_hflx[k] = o->calving_hflx[k] * o->msk[k];
+  }
+  if (stagger == KID_BGRID_NE) {
+    for (int j = d->jsc - 1; j <= d->jec + 1; j++) for (int i = d->isc - 1; i <= d->iec + 1; i++) {
+      G(o, uo, i, j) = C3(uo, i, j); G(o, vo, i, j) = C3(vo, i, j);
+    }
+    halo_update(o, o->uo); halo_update(o, o->vo);
+    for (int j = d->jsc - 1; j <= d->jec + 1; j++) for (int i = d->isc - 1; i <= d->iec + 1; i++) {
+      G(o, ui, i, j) = C3(ui, i, j); G(o, vi, i, j) = C3(vi, i, j);
+    }
+    halo_update(o, o->ui); halo_update(o, o->vi);
+  } else if (stagger == KID_CGRID_NE) {
+    /* I:5246-5259 with symmetric-memory offsets = 0 for (nic+2)-sized inputs: Iu = i-(isc-1)+1 */
+    for (int i = d->isc - 1; i <= d->iec; i++) for (int j = d->jsc - 1; j <= d->jec; j++) {
+      double mask = dmin(dmin(G(o, msk, i, j), G(o, msk, i + 1, j)), dmin(G(o, msk, i, j + 1), G(o, msk, i + 1, j + 1)));
+      G(o, uo, i, j) = mask * 0.5 * (C3(uo, i, j) + C3(uo, i, j + 1));
+      G(o, ui, i, j) = mask * 0.5 * (C3(ui, i, j) + C3(ui, i, j + 1));
+      G(o, vo, i, j) = mask * 0.5 * (C3(vo, i, j) + C3(vo, i + 1, j));
+      G(o, vi, i, j) = mask * 0.5 * (C3(vi, i, j) + C3(vi, i + 1, j));
+    }
+  } else o_fatal(o, "KID, iceberg_run: Unrecognized value of stagger!");
+  if (stress_stagger == KID_BGRID_NE) {
+    for (int j = d->jsc; j <= d->jec; j++) for (int i = d->isc; i <= d->iec; i++) {
+      G(o, ua, i, j) = C2(tauxa, i, j); G(o, va, i, j) = C2(tauya, i, j);
+    }
+  } else if (stress_stagger == KID_CGRID_NE || stress_stagger == KID_AGRID) {
+    double* ut = dalloc(n2, 0.); double* vt = dalloc(n2, 0.);
+    for (int j = d->jsc; j <= d->jec; j++) for (int i = d->isc; i <= d->iec; i++) {
+      ut[IDX(o, i, j)] = C2(tauxa, i, j); vt[IDX(o, i, j)] = C2(tauya, i, j);
+    }
+    halo_update(o, ut); halo_update(o, vt);
+    for (int i = d->isc - 1; i <= d->iec; i++) for (int j = d->jsc - 1; j <= d->jec; j++) {
+      double mask = dmin(dmin(G(o, msk, i, j), G(o, msk, i + 1, j)), dmin(G(o, msk, i, j + 1), G(o, msk, i + 1, j + 1)));
+      if (stress_stagger == KID_CGRID_NE) {
+        G(o, ua, i, j) = mask * 0.5 * (ut[IDX(o, i, j)] + ut[IDX(o, i, j + 1)]);
+        G(o, va, i, j) = mask * 0.5 * (vt[IDX(o, i, j)] + vt[IDX(o, i + 1, j)]);
+      } else {
+        G(o, ua, i, j) = mask * 0.25 * ((ut[IDX(o, i, j)] + ut[IDX(o, i + 1, j + 1)]) + (ut[IDX(o, i + 1, j)] + ut[IDX(o, i, j + 1)]));
+        G(o, va, i, j) = mask * 0.25 * ((vt[IDX(o, i, j)] + vt[IDX(o, i + 1, j + 1)]) + (vt[IDX(o, i + 1, j)] + vt[IDX(o, i, j + 1)]));
+      }
+    }
+    free(ut); free(vt);
+  } else o_fatal(o, "KID, iceberg_run: Unrecognized value of stress_stagger!");
+  halo_update(o, o->uo); halo_update(o, o->vo); halo_update(o, o->ui); halo_update(o, o->vi);
+  if (!o->p.tau_is_velocity) invert_tau_for_du(o);
+  halo_update(o, o->ua); halo_update(o, o->va);
+  for (int j = d->jsc - 1; j <= d->jec + 1; j++) for (int i = d->isc - 1; i <= d->iec + 1; i++) G(o, ssh, i, j) = C3(ssh, i, j);
+  halo_update(o, o->ssh);
+  double max_SST = -1e300;
+  for (int j = d->jsc; j <= d->jec; j++) for (int i = d->isc; i <= d->iec; i++) max_SST = dmax(max_SST, C2(sst, i, j) * G(o, msk, i, j));
+  for (int j = d->jsc; j <= d->jec; j++) for (int i = d->isc; i <= d->iec; i++)
+    G(o, sst, i, j) = (max_SST > 120.0) ? C2(sst, i, j) - 273.15 : C2(sst, i, j);
+  halo_update(o, o->sst);
+  for (int j = d->jsc - 1; j <= d->jec + 1; j++) for (int i = d->isc - 1; i <= d->iec + 1; i++) { G(o, cn, i, j) = C3(cn, i, j); }
+  halo_update(o, o->cn);
+  for (int j = d->jsc - 1; j <= d->jec + 1; j++) for (int i = d->isc - 1; i <= d->iec + 1; i++) { G(o, hi, i, j) = C3(hi, i, j); }
+  halo_update(o, o->hi);
+  for (int j = d->jsc; j <= d->jec; j++) for (int i = d->isc; i <= d->iec; i++) G(o, sss, i, j) = sss ? C2(sss, i, j) : -1.0;
+  for (size_t k = 0; k < n2; k++) {
+    if (o->msk[k] < 0.5) {
+      o->ua[k] = 0.0; o->va[k] = 0.0; o->uo[k] = 0.0; o->vo[k] = 0.0; o->ui[k] = 0.0; o->vi[k] = 0.0;
+      o->sst[k] = 0.0; o->sss[k] = 0.0; o->cn[k] = 0.0; o->hi[k] = 0.0;
+    }
+    double* f[] = {o->ua, o->va, o->uo, o->vo, o->ui, o->vi, o->sst, o->sss, o->cn, o->hi};
+    for (int q = 0; q < 10; q++) if (f[q][k] != f[q][k]) f[q][k] = 0.;
+  }
+#undef C2
+#undef C3
+}
+
+/* I:4673-4715 */
+static void interp_gridded_fields_to_bergs(Oracle* o) {
+  const KidDomain* d = &o->d;
+  int is, ie, js, je;
+  if (o->p.mts) { is = d->isc; ie = d->iec; js = d->jsc; je = d->jec; }
+  else { is = d->isc - 1; ie = d->iec + 1; js = d->jsc - 1; je = d->jec + 1; }
+  for (int grdj = js; grdj <= je; grdj++) for (int grdi = is; grdi <= ie; grdi++)
+    for (OBerg* b = G(o, list, grdi, grdj); b; b = b->next)
+      if (b->halo_berg < 0.5)
+        interp_flds(o, b->lon, b->lat, b->ine, b->jne, b->xi, b->yj, 0., 0., &b->uo, &b->vo, &b->ui, &b->vi,
+                    &b->ua, &b->va, &b->ssh_x, &b->ssh_y, &b->sst, &b->sss, &b->cn, &b->hi, &b->od);
+}
+
+static void oracle_bonds_first_visit(Oracle* o);
+static void oracle_connect_all_bonds(Oracle* o);
+static void oracle_evolve_icebergs_mts(Oracle* o);
+static void oracle_footloose_calving(Oracle* o);
+static void oracle_footloose_part2(Oracle* o);
+static void oracle_set_conglom_ids(Oracle* o);
+static void oracle_transfer_mts_bergs(Oracle* o);
+
+/* the hot path of icebergs_run, I:5389-5512 */
+static void step_core(Oracle* o) {
+  const KidParams* p = &o->p;
+  double t0 = now_sec();
+  accumulate_calving(o);
+  calve_icebergs(o);
+  if (!o->visited) {
+    o->visited = 1;
+    if (p->mts) { interp_gridded_fields_to_bergs(o); oracle_transfer_mts_bergs(o); }
+    else if ((p->contact_distance > 0.) || (p->contact_spring_coef != p->spring_coef)) oracle_set_conglom_ids(o);
+    if (p->iceberg_bonds_on) oracle_bonds_first_visit(o);
+  }
+  if ((!p->mts) && (!p->old_interp_flds_order)) interp_gridded_fields_to_bergs(o);
+  double t1 = now_sec();
+  if (!p->static_icebergs) {
+    if (p->mts) oracle_evolve_icebergs_mts(o); else evolve_icebergs(o);
+  }
+  move_berg_between_cells(o);
+  double t2 = now_sec();
+  send_bergs_to_other_pes(o);
+  if (p->footloose) oracle_footloose_calving(o);
+  if (p->mts) {
+    interp_gridded_fields_to_bergs(o);
+    oracle_transfer_mts_bergs(o);
+  } else {
+    if (p->interactive_icebergs_on || p->iceberg_bonds_on) {
+      update_halo_icebergs(o);
+      if (p->iceberg_bonds_on) oracle_connect_all_bonds(o);
+      else if (p->Lx > 0.) update_latlon(o);
+      if ((p->contact_distance > 0.) || (p->contact_spring_coef != p->spring_coef)) oracle_set_conglom_ids(o);
+    }
+    if (!p->old_interp_flds_order) interp_gridded_fields_to_bergs(o);
+  }
+  if (p->footloose) oracle_footloose_part2(o);
+  double t3 = now_sec();
+  thermodynamics(o);
+  double t4 = now_sec();
+  o->tsec[0] += t2 - t1; o->tsec[1] += t4 - t3; o->tsec[2] += (t1 - t0) + (t3 - t2);
+}
+
+int32_t oracle_run(Oracle* o, int32_t year, double yearday, double* calving, const double* uo,
+                   const double* vo, const double* ui, const double* vi, const double* tauxa,
+                   const double* tauya, const double* ssh, const double* sst, double* calving_hflx,
+                   const double* cn, const double* hi, int32_t stagger, int32_t stress_stagger,
+                   const double* sss, double* mass_berg, double* ustar_berg, double* area_berg) {
+  const KidDomain* d = &o->d;
+  int nic = d->iec - d->isc + 1;
+  if (o->fatal) return KID_ERR_STATE;
+  o->tsec[0] = o->tsec[1] = o->tsec[2] = 0.;
+  o->current_year = year; o->current_yearday = yearday;
+  o->nthreads = 1;
+  ingest_forcing(o, calving, uo, vo, ui, vi, tauxa, tauya, ssh, sst, calving_hflx, cn, hi, stagger, stress_stagger, sss);
+  step_core(o);
+  /* I:5654-5679 */
+  if (!o->p.passive_mode) {
+    for (int j = d->jsc; j <= d->jec; j++) for (int i = d->isc; i <= d->iec; i++) {
+      size_t s = (size_t)(i - d->isc) + (size_t)(j - d->jsc) * nic;
+      if (G(o, area, i, j) > 0.) calving[s] = G(o, calving, i, j) / G(o, area, i, j) + G(o, floating_melt, i, j);
+      else calving[s] = 0.;
+      calving_hflx[s] = G(o, calving_hflx, i, j);
+      if (mass_berg) mass_berg[s] = G(o, spread_mass, i, j);
+      if (ustar_berg) ustar_berg[s] = G(o, ustar_iceberg, i, j);
+      if (area_berg) area_berg[s] = G(o, spread_area, i, j);
+    }
+  }
+  return o->fatal ? KID_ERR_STATE : KID_OK;
+}
+
+int32_t oracle_step_again(Oracle* o, int32_t nsteps, int32_t year, double yearday, int32_t nthreads) {
+  size_t n2 = (size_t)o->nid * o->njd;
+  if (o->fatal) return KID_ERR_STATE;
+  o->tsec[0] = o->tsec[1] = o->tsec[2] = 0.;
+  o->current_year = year; o->current_yearday = yearday;
+  o->nthreads = nthreads > 1 ? nthreads : 1;
+  if (o->nthreads > 1 && (o->p.interactive_icebergs_on || o->p.iceberg_bonds_on)) o->nthreads = 1;
+  for (int s = 0; s < nsteps; s++) {
+    double* zero[] = {o->floating_melt, o->berg_melt, o->melt_buoy, o->melt_eros, o->melt_conv, o->bergy_src,
+                      o->bergy_melt, o->bergy_mass, o->fl_bits_src, o->fl_bits_melt, o->melt_buoy_fl,
+                      o->melt_eros_fl, o->melt_conv_fl, o->fl_parent_melt, o->fl_child_melt, o->calving,
+                      o->calving_hflx};
+    for (size_t k = 0; k < sizeof(zero) / sizeof(zero[0]); k++) memset(zero[k], 0, sizeof(double) * n2);
+    step_core(o);
+    if (o->fatal) break;
+  }
+  o->nthreads = 1;
+  return o->fatal ? KID_ERR_STATE : KID_OK;
+}
+
+void oracle_last_timing(const Oracle* o, double sec[4]) { for (int k = 0; k < 4; k++) sec[k] = o->tsec[k]; }
+
+static const double* field_ptr(const Oracle* o, int id) {
+  switch (id) {
+    case KID_FLD_FLOATING_MELT: return o->floating_melt; case KID_FLD_BERG_MELT: return o->berg_melt;
+    case KID_FLD_BERGY_SRC: return o->bergy_src; case KID_FLD_BERGY_MELT: return o->bergy_melt;
+    case KID_FLD_FL_BITS_MELT: return o->fl_bits_melt; case KID_FLD_FL_BITS_SRC: return o->fl_bits_src;
+    case KID_FLD_CALVING_HFLX: return o->calving_hflx; case KID_FLD_CALVING: return o->calving;
+    case KID_FLD_MELT_BUOY: return o->melt_buoy; case KID_FLD_MELT_EROS: return o->melt_eros;
+    case KID_FLD_MELT_CONV: return o->melt_conv; case KID_FLD_MELT_BUOY_FL: return o->melt_buoy_fl;
+    case KID_FLD_MELT_EROS_FL: return o->melt_eros_fl; case KID_FLD_MELT_CONV_FL: return o->melt_conv_fl;
+    case KID_FLD_FL_PARENT_MELT: return o->fl_parent_melt; case KID_FLD_FL_CHILD_MELT: return o->fl_child_melt;
+    case KID_FLD_UO: return o->uo; case KID_FLD_VO: return o->vo; case KID_FLD_UI: return o->ui;
+    case KID_FLD_VI: return o->vi; case KID_FLD_UA: return o->ua; case KID_FLD_VA: return o->va;
+    case KID_FLD_SSH: return o->ssh; case KID_FLD_SST: return o->sst; case KID_FLD_SSS: return o->sss;
+    case KID_FLD_CN: return o->cn; case KID_FLD_HI: return o->hi;
+    case KID_FLD_LON: return o->lon; case KID_FLD_LAT: return o->lat; case KID_FLD_LONC: return o->lonc;
+    case KID_FLD_LATC: return o->latc; case KID_FLD_DX: return o->dx; case KID_FLD_DY: return o->dy;
+    case KID_FLD_AREA: return o->area; case KID_FLD_MSK: return o->msk; case KID_FLD_COS: return o->cosr;
+    case KID_FLD_SIN: return o->sinr; case KID_FLD_OCEAN_DEPTH: return o->ocean_depth;
+    case KID_FLD_STORED_HEAT: return o->stored_heat; case KID_FLD_MASS: return o->mass;
+    case KID_FLD_BERGY_MASS: return o->bergy_mass; case KID_FLD_SPREAD_MASS: return o->spread_mass;
+    case KID_FLD_SPREAD_AREA: return o->spread_area; case KID_FLD_USTAR_ICEBERG: return o->ustar_iceberg;
+    case KID_FLD_SPREAD_UVEL: return o->spread_uvel; case KID_FLD_SPREAD_VVEL: return o->spread_vvel;
+    default: return NULL;
+  }
+}
+
+int32_t oracle_get_grid_field(const Oracle* o, int32_t field_id, double* out) {
+  const double* f = field_ptr(o, field_id);
+  if (!f) return KID_ERR_ARG;
+  memcpy(out, f, sizeof(double) * (size_t)o->nid * o->njd);
+  return KID_OK;
+}
+
+int32_t oracle_get_counters(const Oracle* o, KidCounters* c) {
+  *c = o->cnt;
+  c->nbergs = oracle_count_bergs(o, 0);
+  c->error_flags = o->fatal;
+  return KID_OK;
+}
+
+double oracle_bilin(const Oracle* o, int32_t field_id, int32_t i, int32_t j, double xi, double yj) {
+  const double* f = field_ptr(o, field_id);
+  return f ? bilin(o, f, i, j, xi, yj) : NAN;
+}
+int32_t oracle_is_point_in_cell(const Oracle* o, double x, double y, int32_t i, int32_t j) {
+  return is_point_in_cell((Oracle*)o, x, y, i, j);
+}
+int32_t oracle_pos_within_cell(const Oracle* o, double x, double y, int32_t i, int32_t j, double* xi, double* yj) {
+  return pos_within_cell((Oracle*)o, x, y, i, j, xi, yj);
+}
+int32_t oracle_find_cell(const Oracle* o, double x, double y, int32_t* oi, int32_t* oj) {
+  return find_cell((Oracle*)o, x, y, oi, oj);
+}
+int32_t oracle_find_cell_wide(const Oracle* o, double x, double y, int32_t* oi, int32_t* oj) {
+  return find_cell_wide((Oracle*)o, x, y, oi, oj);
+}
+
+/* bonds, MTS/DEM, footloose and the spreading-geometry known answers live in
+ * the second half of this translation unit */
+#include "kid_oracle_ext.inc"
