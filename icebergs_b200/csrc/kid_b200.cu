@@ -1,0 +1,1130 @@
+// kid_b200.cu -- C ABI of the B200-native KID hot path (include/kid_b200.h).
+//
+// Host side: handle management, grid derivation at init (ice_bergs_framework_init
+// F:1021-1153), forcing upload, kernel sequencing of one icebergs_run step
+// (I:5389-5512) and the restart-column marshalling.  All per-berg and per-cell
+// arithmetic of the step runs in the kernels of kid_kernels.cuh; there is no CPU
+// fallback: without a CUDA device every computing entry point fails with
+// KID_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kid_kernels.cuh"
+#include "kid_comm.cuh"
+
+using namespace kid;
+
+namespace {
+
+thread_local std::string g_init_error = "";
+
+enum { T_INTERFACE = 0, T_CALVING, T_MOMENTUM, T_COMM, T_THERMO, T_SORT, T_TOTAL, T_NPHASE };
+
+}  // namespace
+
+struct kid_handle {
+  KidParams p;
+  KidDomain d;
+  DevParams dp;
+  DevGrid g;
+  DevBergs b;
+  CalvingTables ct;
+  int nid = 0, njd = 0, nic = 0, njc = 0;
+  long long n2 = 0;
+  long long capacity = 0;
+  long long n_slots = 0;            // host mirror of the append cursor
+  void *spare8 = nullptr, *spare4 = nullptr, *spare1 = nullptr;
+  DevCounters* dcnt = nullptr;
+  DevCounters* hcnt = nullptr;      // pinned
+  unsigned long long* dflags = nullptr;   // [0] enc(max sst*msk) [1] any calving != 0 [2] alive count
+  unsigned long long* hflags = nullptr;   // pinned
+  int32_t *cell_count = nullptr, *cell_start = nullptr, *cell_fill = nullptr, *perm = nullptr;
+  int32_t *scan_sums = nullptr, *scan_total = nullptr;
+  std::vector<double*> field_allocs;
+  double* in_stage[13] = {nullptr};  // device staging of the icebergs_run inputs
+  double* out_stage[2] = {nullptr};
+  double *tmp_u = nullptr, *tmp_v = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[T_NPHASE + 2];
+  std::vector<cudaEvent_t> ev_pool;   // per-step (begin, after fused kernel, after sort) triples
+  int ev_used = 0;
+  double timing[8] = {0};
+  long long launches = 0;
+  int visited = 0, first_call_accum = 1, restarted = 0;
+  int calving_active = 0;
+  int steps_since_sort = 0, sort_interval = 16, sorted_once = 0;
+  int forcing_set = 0;
+  long long dirty_appended = 0;
+  std::string err;
+  bool fatal = false;
+};
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      h->err = std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call;               \
+      h->fatal = true;                                                                             \
+      return KID_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+static inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
+#define LAUNCH(h, kern, n, blk, ...)                                        \
+  do {                                                                      \
+    if ((n) > 0) {                                                          \
+      kern<<<nblk((n), (blk)), (blk), 0, (h)->stream>>>(__VA_ARGS__);       \
+      (h)->launches++;                                                      \
+    }                                                                       \
+  } while (0)
+
+// ------------------------------------------------------------------ params
+extern "C" void kid_default_params(KidParams* p) {
+  memset(p, 0, sizeof(*p));
+  p->abi_version = KID_ABI_VERSION;
+  p->halo = 4;
+  p->dt = 0.;
+  p->pi = 3.14159265358979323846;   // FMS constants_mod
+  p->omega = 7.292e-5;
+  p->radius = 6371.0e3;
+  p->hlf = 3.34e5;
+  p->grid_is_latlon = 1; p->grid_is_regular = 1;
+  p->Lx = 360.; p->Rearth = 6360000.;
+  p->runge_not_verlet = 1; p->old_bug_bilin = 1; p->use_roundoff_fix = 1;
+  p->old_interp_flds_order = 1;
+  p->rho_bergs = 850.;
+  p->ocean_drag_scale = 1.;
+  p->h_to_init_grounding = 100.;
+  p->critical_interaction_damping_on = 1; p->tang_crit_int_damp_on = 1; p->scale_damping_by_pmag = 1;
+  p->max_bonds = 6;
+  p->spring_coef = 1.e-8;
+  p->radial_damping_coef = 1.e-4; p->tangental_damping_coef = 2.e-5;
+  p->contact_cells_lon = 1; p->contact_cells_lat = 1;
+  p->length_for_manually_initialize_bonds = 1000.;
+  p->mts_sub_steps = -1;
+  p->convergence_tolerance = 1.e-8;
+  p->save_bond_forces = 1;
+  p->remove_unused_bergs = 1;
+  p->poisson = 0.3; p->dem_damping_coef = 0.1;
+  p->use_operator_splitting = 1; p->allow_bergs_to_roll = 1;
+  p->melt_cutoff = -1.;
+  p->displace_fl_bergs = 1; p->fl_bits_erosion_to_bergy_bits = 1;
+  p->fl_youngs = 1.e7; p->fl_strength = 250.; p->new_berg_from_fl_bits_mass_thres = 1.e12;
+  p->LoW_ratio = 1.5;
+  const double im[10] = {8.8e7, 4.1e8, 3.3e9, 1.8e10, 3.8e10, 7.5e10, 1.2e11, 2.2e11, 3.9e11, 7.4e11};
+  const double ds[10] = {0.24, 0.12, 0.15, 0.18, 0.12, 0.07, 0.03, 0.03, 0.03, 0.02};
+  const double sc[10] = {2000, 200, 50, 20, 10, 5, 2, 1, 1, 1};
+  const double th[10] = {40., 67., 133., 175., 250., 250., 250., 250., 250., 250.};
+  const double imn[10] = {4.58e8, 3.61e9, 1.22e10, 2.91e10, 5.09e10, 7.34e10, 1.15e11, 1.65e11, 2.94e11, 5.59e11};
+  const double dsn[10] = {0.14, 0.15, 0.20, 0.15, 0.08, 0.07, 0.05, 0.05, 0.05, 0.05};
+  const double scn[10] = {200, 50, 25, 13, 8, 5, 2, 1, 1, 1};
+  const double thn[10] = {80.4, 159.5, 240., 320., 360., 360., 360., 360., 360., 360.};
+  for (int k = 0; k < 10; k++) {
+    p->initial_mass_s[k] = im[k]; p->distribution_s[k] = ds[k]; p->mass_scaling_s[k] = sc[k]; p->initial_thickness_s[k] = th[k];
+    p->initial_mass_n[k] = imn[k]; p->distribution_n[k] = dsn[k]; p->mass_scaling_n[k] = scn[k]; p->initial_thickness_n[k] = thn[k];
+  }
+}
+
+extern "C" void kid_single_domain(KidDomain* d, int32_t gni, int32_t gnj, int32_t halo, int32_t cyclic_x,
+                                  int32_t cyclic_y, int32_t device) {
+  memset(d, 0, sizeof(*d));
+  d->gni = gni; d->gnj = gnj;
+  d->isc = 1; d->iec = gni; d->jsc = 1; d->jec = gnj;
+  d->isd = 1 - halo; d->ied = gni + halo; d->jsd = 1 - halo; d->jed = gnj + halo;
+  d->cyclic_x = cyclic_x; d->cyclic_y = cyclic_y;
+  d->rank = 0; d->nranks = 1; d->layout_x = 1; d->layout_y = 1;
+  d->pe_E = d->pe_W = cyclic_x ? 0 : -1;
+  d->pe_N = d->pe_S = cyclic_y ? 0 : -1;
+  d->device = device;
+  d->nccl_comm = nullptr;
+}
+
+// mpp_define_layout (idiv = nint(sqrt(npes*ni/nj)) decremented to a divisor) and an
+// even mpp_compute_extent; FMS is outside the reference tree (D:157-164, F:915-930).
+extern "C" int32_t kid_define_domain(KidDomain* d, int32_t gni, int32_t gnj, int32_t halo, int32_t cyclic_x,
+                                     int32_t cyclic_y, int32_t rank, int32_t nranks, int32_t device) {
+  if (nranks < 1 || rank < 0 || rank >= nranks) return KID_ERR_ARG;
+  memset(d, 0, sizeof(*d));
+  int idiv = (int)lround(sqrt((double)nranks * gni / gnj));
+  if (idiv < 1) idiv = 1;
+  while (nranks % idiv) idiv--;
+  int lx = idiv, ly = nranks / idiv;
+  int px = rank % lx, py = rank / lx;
+  auto extent = [](int n, int parts, int k, int* s, int* e) {
+    int base = n / parts, rem = n % parts;
+    int start = k * base + std::min(k, rem);
+    *s = start + 1; *e = start + base + (k < rem ? 1 : 0);
+  };
+  d->gni = gni; d->gnj = gnj;
+  extent(gni, lx, px, &d->isc, &d->iec);
+  extent(gnj, ly, py, &d->jsc, &d->jec);
+  d->isd = d->isc - halo; d->ied = d->iec + halo; d->jsd = d->jsc - halo; d->jed = d->jec + halo;
+  d->cyclic_x = cyclic_x; d->cyclic_y = cyclic_y;
+  d->rank = rank; d->nranks = nranks; d->layout_x = lx; d->layout_y = ly;
+  auto pe_of = [&](int qx, int qy) -> int {
+    if (qx < 0 || qx >= lx) { if (!cyclic_x) return -1; qx = (qx + lx) % lx; }
+    if (qy < 0 || qy >= ly) { if (!cyclic_y) return -1; qy = (qy + ly) % ly; }
+    return qx + lx * qy;
+  };
+  d->pe_E = pe_of(px + 1, py); d->pe_W = pe_of(px - 1, py);
+  d->pe_N = pe_of(px, py + 1); d->pe_S = pe_of(px, py - 1);
+  d->device = device;
+  d->nccl_comm = nullptr;
+  return KID_OK;
+}
+
+extern "C" const char* kid_version(void) { return "kid-b200 0.1 (sm_100a, fp64, abi 1)"; }
+
+extern "C" const char* kid_last_error(const kid_t* h) { return h ? h->err.c_str() : g_init_error.c_str(); }
+
+// ---------------------------------------------------------------- helpers
+static int fail(kid_t* h, int code, const std::string& msg) {
+  h->err = msg;
+  return code;
+}
+
+static double* dev_field(kid_t* h, long long n, double fill) {
+  double* p = nullptr;
+  if (cudaMalloc(&p, sizeof(double) * n) != cudaSuccess) return nullptr;
+  if (fill == 0.) cudaMemsetAsync(p, 0, sizeof(double) * n, h->stream);
+  else {
+    std::vector<double> v((size_t)n, fill);
+    cudaMemcpy(p, v.data(), sizeof(double) * n, cudaMemcpyHostToDevice);
+  }
+  h->field_allocs.push_back(p);
+  return p;
+}
+
+static void fill_dev_params(kid_t* h) {
+  const KidParams& p = h->p;
+  DevParams& q = h->dp;
+  memset(&q, 0, sizeof(q));
+  q.dt = p.dt; q.pi = p.pi; q.pi_180 = p.pi / 180.; q.omega2 = 2. * p.omega; q.Lx = p.Lx; q.Rearth = p.Rearth;
+  q.lat_ref = p.lat_ref; q.rho_bergs = p.rho_bergs; q.speed_limit = p.speed_limit; q.coastal_drift = p.coastal_drift;
+  q.ocean_drag_scale = p.ocean_drag_scale; q.cdrag_grounding = p.cdrag_grounding;
+  q.h_to_init_grounding = p.h_to_init_grounding; q.u_override = p.u_override; q.v_override = p.v_override;
+  q.bergy_bit_erosion_fraction = p.bergy_bit_erosion_fraction; q.sicn_shift = p.sicn_shift;
+  q.tip_parameter = p.tip_parameter; q.melt_cutoff = p.melt_cutoff;
+  q.spring_coef = p.spring_coef; q.contact_spring_coef = p.contact_spring_coef; q.contact_distance = p.contact_distance;
+  q.radial_damping_coef = p.radial_damping_coef; q.tangental_damping_coef = p.tangental_damping_coef;
+  q.fl_youngs = p.fl_youngs;
+  q.grid_is_latlon = p.grid_is_latlon; q.grid_is_regular = p.grid_is_regular; q.old_bug_bilin = p.old_bug_bilin;
+  q.use_roundoff_fix = p.use_roundoff_fix; q.use_f_plane = p.use_f_plane;
+  q.use_new_predictive_corrective = p.use_new_predictive_corrective;
+  q.only_interactive_forces = p.only_interactive_forces;
+  q.override_iceberg_velocities = p.override_iceberg_velocities;
+  q.old_interp_flds_order = p.old_interp_flds_order; q.interactive_icebergs_on = p.interactive_icebergs_on;
+  q.iceberg_bonds_on = p.iceberg_bonds_on; q.internal_bergs_for_drag = p.internal_bergs_for_drag;
+  q.hexagonal_icebergs = p.hexagonal_icebergs;
+  q.critical_interaction_damping_on = p.critical_interaction_damping_on;
+  q.tang_crit_int_damp_on = p.tang_crit_int_damp_on; q.scale_damping_by_pmag = p.scale_damping_by_pmag;
+  q.use_operator_splitting = p.use_operator_splitting; q.set_melt_rates_to_zero = p.set_melt_rates_to_zero;
+  q.allow_bergs_to_roll = p.allow_bergs_to_roll; q.use_updated_rolling_scheme = p.use_updated_rolling_scheme;
+  q.iceberg_melt_without_decay = p.iceberg_melt_without_decay; q.melt_diagnostics = p.melt_diagnostics;
+  q.footloose = p.footloose; q.mts = p.mts; q.dem = p.dem;
+  q.contact_cells_lon = p.contact_cells_lon; q.contact_cells_lat = p.contact_cells_lat; q.max_bonds = p.max_bonds;
+  q.passive_mode = p.passive_mode;
+}
+
+// Fortran MODULO / apply_modulo_around_point on the host, for the init-time
+// periodic-longitude fix F:1122-1143
+static double h_modulo(double a, double p) {
+  double r = fmod(a, p);
+  if (r != 0.0 && ((r < 0.0) != (p < 0.0))) r += p;
+  return r;
+}
+static double h_amap(double x, double y, double Lx) {
+  if (Lx > 0.) { double Lx_2 = Lx / 2.; return h_modulo(x - (y - Lx_2), Lx) + (y - Lx_2); }
+  return x;
+}
+
+// ------------------------------------------------------------------ init
+extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* dom, int32_t year, double yearday,
+                            int64_t capacity, const double* lon, const double* lat, const double* wet,
+                            const double* dx, const double* dy, const double* area, const double* cos_rot,
+                            const double* sin_rot, const double* ocean_depth, int32_t fractional_area) {
+  if (!hp || !pin || !dom || !lon || !lat || !wet || !dx || !dy || !area || !cos_rot || !sin_rot) {
+    g_init_error = "kid_init: null argument";
+    return KID_ERR_ARG;
+  }
+  if (pin->abi_version != KID_ABI_VERSION) { g_init_error = "kid_init: KidParams.abi_version mismatch"; return KID_ERR_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    cudaGetLastError();
+    g_init_error = "kid_init: no CUDA device (this library has no CPU fallback)";
+    return KID_ERR_NO_DEVICE;
+  }
+  if (dom->device < 0 || dom->device >= ndev) { g_init_error = "kid_init: bad device ordinal"; return KID_ERR_ARG; }
+  // what this build of the library does not implement is refused up front
+  const char* unsupported = nullptr;
+  if (pin->runge_not_verlet) unsupported = "Runge_not_Verlet=.true. (RK4) is not implemented: set runge_not_verlet=0";
+  else if (pin->tidal_drift > 0.) unsupported = "tidal_drift>0 needs the FMS random number stream";
+  else if (pin->use_mixed_melting || pin->melt_icebergs_as_ice_shelf) unsupported = "ice-shelf melt (find_basal_melt) is not implemented";
+  else if (pin->add_iceberg_thickness_to_ssh) unsupported = "add_iceberg_thickness_to_SSH is not implemented";
+  else if (pin->mts || pin->dem) unsupported = "MTS/DEM stepping is not implemented in this build";
+  else if (pin->iceberg_bonds_on) unsupported = "bonds are not implemented in this build";
+  else if (pin->interactive_icebergs_on) unsupported = "interactive_icebergs_on is not implemented in this build";
+  else if (pin->footloose) unsupported = "footloose calving is not implemented in this build";
+  else if (dom->cyclic_y) unsupported = "cyclic y is not implemented";
+  else if (pin->halo < 2) unsupported = "halo must be >= 2";
+  if (unsupported) { g_init_error = std::string("kid_init: ") + unsupported; return KID_ERR_UNSUPPORTED; }
+  if (dom->isd != dom->isc - pin->halo || dom->ied != dom->iec + pin->halo || dom->jsd != dom->jsc - pin->halo ||
+      dom->jed != dom->jec + pin->halo) { g_init_error = "kid_init: data domain must be compute domain +/- halo"; return KID_ERR_ARG; }
+  if (dom->nranks > 1 && !dom->nccl_comm) { g_init_error = "kid_init: nranks>1 needs KidDomain.nccl_comm"; return KID_ERR_ARG; }
+
+  kid_t* h = new kid_handle();
+  h->p = *pin; h->d = *dom;
+  if (cudaSetDevice(dom->device) != cudaSuccess) { g_init_error = "kid_init: cudaSetDevice failed"; delete h; return KID_ERR_CUDA; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, dom->device);
+  if (prop.major < 10) {
+    g_init_error = "kid_init: device is not sm_100a-class (this library carries sm_100a code only)";
+    delete h;
+    return KID_ERR_NO_DEVICE;
+  }
+  *hp = h;
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto& e : h->ev) CK(cudaEventCreate(&e));
+  const KidDomain* d = &h->d;
+  h->nid = d->ied - d->isd + 1; h->njd = d->jed - d->jsd + 1;
+  h->nic = d->iec - d->isc + 1; h->njc = d->jec - d->jsc + 1;
+  h->n2 = (long long)h->nid * h->njd;
+  const long long n2 = h->n2;
+  const int nid = h->nid, nic = h->nic;
+  // derived parameters, F:1264, F:1312, F:1483
+  KidParams* q = &h->p;
+  if (!q->iceberg_bonds_on) q->max_bonds = 0;
+  if (q->contact_spring_coef <= 0.) q->contact_spring_coef = q->spring_coef;
+  q->old_interp_flds_order = !(q->mts || q->dem || q->footloose);
+  // F:1113-1118
+  if ((!q->grid_is_latlon) && (q->Lx == 360.)) q->Lx = -1.;
+
+  // ---- grid derivation on the host, F:1021-1153 (init only)
+  auto IDX = [&](int i, int j) -> size_t { return (size_t)(i - d->isd) + (size_t)(j - d->jsd) * (size_t)nid; };
+  const double big_number = 1.0E15;
+  std::vector<double> glon(n2, big_number), glat(n2, big_number), glonc(n2, 0.), glatc(n2, 0.), gdx(n2, 0.),
+      gdy(n2, 0.), garea(n2, 0.), gmsk(n2, 0.), gcos(n2, 1.), gsin(n2, 0.), gdepth(n2, 0.);
+  for (int j = d->jsc; j <= d->jec; j++)
+    for (int i = d->isc; i <= d->iec; i++) {
+      size_t s = (size_t)(i - d->isc) + (size_t)(j - d->jsc) * nic;
+      glon[IDX(i, j)] = lon[s]; glat[IDX(i, j)] = lat[s];
+      garea[IDX(i, j)] = fractional_area ? area[s] * (4. * q->pi * q->radius * q->radius) : area[s];
+      if (ocean_depth) gdepth[IDX(i, j)] = ocean_depth[s];
+    }
+  for (int j = d->jsc - 1; j <= d->jec + 1; j++)
+    for (int i = d->isc - 1; i <= d->iec + 1; i++) {
+      size_t s = (size_t)(i - (d->isc - 1)) + (size_t)(j - (d->jsc - 1)) * (nic + 2);
+      gdx[IDX(i, j)] = dx[s]; gdy[IDX(i, j)] = dy[s]; gmsk[IDX(i, j)] = wet[s];
+      gcos[IDX(i, j)] = cos_rot[s]; gsin[IDX(i, j)] = sin_rot[s];
+    }
+  // mpp_update_domains F:1058-1066: one rank that is its own E/W neighbour wraps;
+  // ranks of a multi-rank layout get their halos from the caller-provided ring only
+  // (the wider static halo is extrapolated below, as on a non-periodic edge)
+  bool self_x = d->cyclic_x && d->pe_E == d->rank && d->pe_W == d->rank;
+  auto wrap = [&](std::vector<double>& f) {
+    if (!self_x) return;
+    for (int j = d->jsc; j <= d->jec; j++) {
+      for (int i = d->isd; i < d->isc; i++) f[IDX(i, j)] = f[IDX(i + nic, j)];
+      for (int i = d->iec + 1; i <= d->ied; i++) f[IDX(i, j)] = f[IDX(i - nic, j)];
+    }
+  };
+  wrap(glon); wrap(glat); wrap(gdy); wrap(gdx); wrap(garea); wrap(gmsk); wrap(gcos); wrap(gsin); wrap(gdepth);
+  // F:1068-1094: extrapolate lon/lat into halos that no neighbour filled
+  for (int j = d->jsc - 1; j >= d->jsd; j--) for (int i = d->isd; i <= d->ied; i++) {
+    if (glon[IDX(i, j)] >= big_number) glon[IDX(i, j)] = glon[IDX(i, j + 1)];
+    if (glat[IDX(i, j)] >= big_number) glat[IDX(i, j)] = 2. * glat[IDX(i, j + 1)] - glat[IDX(i, j + 2)];
+  }
+  for (int j = d->jec + 1; j <= d->jed; j++) for (int i = d->isd; i <= d->ied; i++) {
+    if (glon[IDX(i, j)] >= big_number) glon[IDX(i, j)] = 2. * glon[IDX(i, j - 1)] - glon[IDX(i, j - 2)];
+    if (glat[IDX(i, j)] >= big_number) glat[IDX(i, j)] = 2. * glat[IDX(i, j - 1)] - glat[IDX(i, j - 2)];
+  }
+  for (int i = d->isc - 1; i >= d->isd; i--) for (int j = d->jsd; j <= d->jed; j++) {
+    if (glon[IDX(i, j)] >= big_number) glon[IDX(i, j)] = 2. * glon[IDX(i + 1, j)] - glon[IDX(i + 2, j)];
+    if (glat[IDX(i, j)] >= big_number) glat[IDX(i, j)] = 2. * glat[IDX(i + 1, j)] - glat[IDX(i + 2, j)];
+  }
+  for (int i = d->iec + 1; i <= d->ied; i++) for (int j = d->jsd; j <= d->jed; j++) {
+    if (glon[IDX(i, j)] >= big_number) glon[IDX(i, j)] = 2. * glon[IDX(i - 1, j)] - glon[IDX(i - 2, j)];
+    if (glat[IDX(i, j)] >= big_number) glat[IDX(i, j)] = 2. * glat[IDX(i - 1, j)] - glat[IDX(i - 2, j)];
+  }
+  // F:1122-1143: make longitude monotone across the periodic seam
+  double Lx = q->Lx;
+  if (Lx > 0.) {
+    int j = d->jsc;
+    for (int i = d->isc + 1; i <= d->ied; i++) {
+      double lon_mod = h_amap(glon[IDX(i, j)], glon[IDX(i - 1, j)], Lx);
+      if (fabs(glon[IDX(i, j)] - lon_mod) > (Lx / 2.)) glon[IDX(i, j)] = lon_mod;
+    }
+    for (int i = d->isc - 1; i >= d->isd; i--) {
+      double lon_mod = h_amap(glon[IDX(i, j)], glon[IDX(i + 1, j)], Lx);
+      if (fabs(glon[IDX(i, j)] - lon_mod) > (Lx / 2.)) glon[IDX(i, j)] = lon_mod;
+    }
+    for (j = d->jsc + 1; j <= d->jed; j++) for (int i = d->isd; i <= d->ied; i++) {
+      double lon_mod = h_amap(glon[IDX(i, j)], glon[IDX(i, j - 1)], Lx);
+      if (fabs(glon[IDX(i, j)] - lon_mod) > (Lx / 2.)) glon[IDX(i, j)] = lon_mod;
+    }
+    for (j = d->jsc - 1; j >= d->jsd; j--) for (int i = d->isd; i <= d->ied; i++) {
+      double lon_mod = h_amap(glon[IDX(i, j)], glon[IDX(i, j + 1)], Lx);
+      if (fabs(glon[IDX(i, j)] - lon_mod) > (Lx / 2.)) glon[IDX(i, j)] = lon_mod;
+    }
+  }
+  // F:1148-1153
+  for (int j = d->jsd + 1; j <= d->jed; j++) for (int i = d->isd + 1; i <= d->ied; i++) {
+    glonc[IDX(i, j)] = 0.25 * ((glon[IDX(i, j)] + glon[IDX(i - 1, j - 1)]) + (glon[IDX(i - 1, j)] + glon[IDX(i, j - 1)]));
+    glatc[IDX(i, j)] = 0.25 * ((glat[IDX(i, j)] + glat[IDX(i - 1, j - 1)]) + (glat[IDX(i - 1, j)] + glat[IDX(i, j - 1)]));
+  }
+
+  // ---- device grid
+  DevGrid& g = h->g;
+  memset(&g, 0, sizeof(g));
+  g.isd = d->isd; g.ied = d->ied; g.jsd = d->jsd; g.jed = d->jed;
+  g.isc = d->isc; g.iec = d->iec; g.jsc = d->jsc; g.jec = d->jec;
+  g.nid = h->nid; g.njd = h->njd; g.gni = d->gni; g.gnj = d->gnj;
+  g.cyclic_x = d->cyclic_x; g.cyclic_y = d->cyclic_y;
+  g.pe_E_self = (d->pe_E == d->rank); g.pe_W_self = (d->pe_W == d->rank);
+  g.has_E = (d->pe_E >= 0 && d->pe_E != d->rank); g.has_W = (d->pe_W >= 0 && d->pe_W != d->rank);
+  g.has_N = (d->pe_N >= 0 && d->pe_N != d->rank); g.has_S = (d->pe_S >= 0 && d->pe_S != d->rank);
+  struct Up { double** dst; std::vector<double>* src; };
+  Up ups[] = {{&g.lon, &glon}, {&g.lat, &glat}, {&g.lonc, &glonc}, {&g.latc, &glatc}, {&g.dx, &gdx}, {&g.dy, &gdy},
+              {&g.area, &garea}, {&g.msk, &gmsk}, {&g.cosr, &gcos}, {&g.sinr, &gsin}, {&g.ocean_depth, &gdepth}};
+  for (auto& u : ups) {
+    *u.dst = dev_field(h, n2, 0.);
+    if (!*u.dst) return fail(h, KID_ERR_CUDA, "kid_init: out of device memory (grid)");
+    CK(cudaMemcpyAsync(*u.dst, u.src->data(), sizeof(double) * n2, cudaMemcpyHostToDevice, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  double** zf[] = {&g.uo, &g.vo, &g.ui, &g.vi, &g.ua, &g.va, &g.ssh, &g.sst, &g.sss, &g.cn, &g.hi, &g.calving,
+                   &g.calving_hflx, &g.floating_melt, &g.berg_melt, &g.bergy_src, &g.bergy_melt, &g.fl_bits_melt,
+                   &g.fl_bits_src, &g.melt_buoy, &g.melt_eros, &g.melt_conv, &g.melt_buoy_fl, &g.melt_eros_fl,
+                   &g.melt_conv_fl, &g.fl_parent_melt, &g.fl_child_melt, &g.stored_heat, &g.tmp, &h->tmp_u, &h->tmp_v};
+  for (auto z : zf) { *z = dev_field(h, n2, 0.); if (!*z) return fail(h, KID_ERR_CUDA, "kid_init: out of device memory (fields)"); }
+  g.stored_ice = dev_field(h, n2 * KID_NCLASSES, 0.);
+  g.real_calving = dev_field(h, n2 * KID_NCLASSES, 0.);
+  if (!g.stored_ice || !g.real_calving) return fail(h, KID_ERR_CUDA, "kid_init: out of device memory (calving)");
+  CK(cudaMalloc(&g.iceberg_counter_grd, sizeof(int32_t) * n2));
+  CK(cudaMemsetAsync(g.iceberg_counter_grd, 0, sizeof(int32_t) * n2, h->stream));
+  CK(cudaMalloc(&g.corner, sizeof(CornerRec) * n2));
+  CK(cudaMalloc(&g.cell, sizeof(CellRec) * n2));
+  CK(cudaMalloc(&g.lonlat, sizeof(LonLat) * n2));
+  for (int k = 0; k < 13; k++) CK(cudaMalloc(&h->in_stage[k], sizeof(double) * (size_t)(h->nic + 2) * (h->njc + 2)));
+  for (int k = 0; k < 2; k++) CK(cudaMalloc(&h->out_stage[k], sizeof(double) * (size_t)h->nic * h->njc));
+
+  // ---- berg store
+  h->capacity = capacity > 0 ? capacity : ((long long)1 << 20);
+  if (h->capacity > 2000000000LL) return fail(h, KID_ERR_ARG, "kid_init: capacity must be < 2^31");
+  DevBergs& b = h->b;
+  memset(&b, 0, sizeof(b));
+  b.capacity = h->capacity;
+  int ncols = q->interactive_icebergs_on ? (int)C_NINTER : (int)C_NBASE;
+  for (int c = 0; c < ncols; c++) CK(cudaMalloc(&b.f64[c], sizeof(double) * h->capacity));
+  CK(cudaMalloc(&b.id, sizeof(int64_t) * h->capacity));
+  CK(cudaMalloc(&b.ine, sizeof(int32_t) * h->capacity));
+  CK(cudaMalloc(&b.jne, sizeof(int32_t) * h->capacity));
+  CK(cudaMalloc(&b.start_year, sizeof(int32_t) * h->capacity));
+  CK(cudaMalloc(&b.flags, h->capacity));
+  CK(cudaMalloc(&b.halo_code, h->capacity));
+  CK(cudaMemsetAsync(b.flags, 0, h->capacity, h->stream));
+  CK(cudaMemsetAsync(b.halo_code, 0, h->capacity, h->stream));
+  CK(cudaMalloc(&h->spare8, 8 * h->capacity));
+  CK(cudaMalloc(&h->spare4, 4 * h->capacity));
+  CK(cudaMalloc(&h->spare1, h->capacity));
+  CK(cudaMalloc(&h->perm, sizeof(int32_t) * h->capacity));
+  CK(cudaMalloc(&h->cell_count, sizeof(int32_t) * n2));
+  CK(cudaMalloc(&h->cell_start, sizeof(int32_t) * n2));
+  CK(cudaMalloc(&h->cell_fill, sizeof(int32_t) * n2));
+  int nsb = (int)((n2 + KID_SCAN_ITEMS - 1) / KID_SCAN_ITEMS);
+  CK(cudaMalloc(&h->scan_sums, sizeof(int32_t) * (nsb + 1)));
+  CK(cudaMalloc(&h->scan_total, sizeof(int32_t)));
+  CK(cudaMalloc(&h->dcnt, sizeof(DevCounters)));
+  CK(cudaMemsetAsync(h->dcnt, 0, sizeof(DevCounters), h->stream));
+  CK(cudaMallocHost(&h->hcnt, sizeof(DevCounters)));
+  memset(h->hcnt, 0, sizeof(DevCounters));
+  CK(cudaMalloc(&h->dflags, 4 * sizeof(unsigned long long)));
+  CK(cudaMallocHost(&h->hflags, 4 * sizeof(unsigned long long)));
+
+  fill_dev_params(h);
+  h->dp.current_year = year; h->dp.current_yearday = yearday;
+  CalvingTables& ct = h->ct;
+  for (int k = 0; k < KID_NCLASSES; k++) {
+    ct.initial_mass_s[k] = q->initial_mass_s[k]; ct.distribution_s[k] = q->distribution_s[k];
+    ct.mass_scaling_s[k] = q->mass_scaling_s[k]; ct.initial_thickness_s[k] = q->initial_thickness_s[k];
+    ct.initial_mass_n[k] = q->initial_mass_n[k]; ct.distribution_n[k] = q->distribution_n[k];
+    ct.mass_scaling_n[k] = q->mass_scaling_n[k]; ct.initial_thickness_n[k] = q->initial_thickness_n[k];
+  }
+  ct.LoW_ratio = q->LoW_ratio; ct.rho_bergs = q->rho_bergs;
+  const char* si = getenv("KID_SORT_INTERVAL");
+  if (si && atoi(si) > 0) h->sort_interval = atoi(si);
+
+  LAUNCH(h, k_pack_lonlat, n2, 256, h->g, n2);
+  LAUNCH(h, k_pack_forcing, n2, 256, h->g, n2);
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  return KID_OK;
+}
+
+extern "C" int32_t kid_end(kid_t** hp) {
+  if (!hp || !*hp) return KID_ERR_ARG;
+  kid_t* h = *hp;
+  cudaSetDevice(h->d.device);
+  cudaStreamSynchronize(h->stream);
+  for (double* p : h->field_allocs) cudaFree(p);
+  cudaFree(h->g.iceberg_counter_grd); cudaFree(h->g.corner); cudaFree(h->g.cell); cudaFree(h->g.lonlat);
+  for (auto p : h->in_stage) cudaFree(p);
+  for (auto p : h->out_stage) cudaFree(p);
+  for (int c = 0; c < C_NCOLS; c++) cudaFree(h->b.f64[c]);
+  cudaFree(h->b.id); cudaFree(h->b.ine); cudaFree(h->b.jne); cudaFree(h->b.start_year);
+  cudaFree(h->b.flags); cudaFree(h->b.halo_code);
+  cudaFree(h->spare8); cudaFree(h->spare4); cudaFree(h->spare1); cudaFree(h->perm);
+  cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->cell_fill);
+  cudaFree(h->scan_sums); cudaFree(h->scan_total); cudaFree(h->dcnt); cudaFree(h->dflags);
+  cudaFreeHost(h->hcnt); cudaFreeHost(h->hflags);
+  for (auto& e : h->ev) cudaEventDestroy(e);
+  for (auto& e : h->ev_pool) cudaEventDestroy(e);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  *hp = nullptr;
+  return KID_OK;
+}
+
+static int check_device_errors(kid_t* h) {
+  // copies the counters back (synchronises the stream) and maps device-side fatal
+  // conditions to the messages the reference gives error_mesg(..., FATAL)
+  CK(cudaMemcpyAsync(h->hcnt, h->dcnt, sizeof(DevCounters), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  h->n_slots = (long long)h->hcnt->n_slots;
+  unsigned e = h->hcnt->error_flags;
+  if (e) {
+    h->fatal = true;
+    if (e & KID_DEVERR_GROUNDED) return fail(h, KID_ERR_STATE, "KID, thermodynamics: berg appears to have grounded!");
+    if (e & KID_DEVERR_COMPLEX_ROOTS) return fail(h, KID_ERR_STATE, "KID, calc_xiyj: We have complex roots. The grid must be very distorted!");
+    if (e & KID_DEVERR_NOT_INVERTIBLE) return fail(h, KID_ERR_STATE, "KID, calc_xiyj: Can not invert either linear equaton for xi!");
+    if (e & KID_DEVERR_OFF_PE) return fail(h, KID_ERR_STATE, "KID, is_point_in_cell: test is off the PE!");
+    if (e & KID_DEVERR_CAPACITY) return fail(h, KID_ERR_CAPACITY, "kid: berg store capacity exceeded");
+    if (e & KID_DEVERR_LOST_BERG) return fail(h, KID_ERR_STATE, "KID, unpack_berg_from_buffer: can not find a cell to place berg in!");
+    if (e & 64u) return fail(h, KID_ERR_STATE, "KID, interp fields: field interpaolations has NaNs");
+    if (e & 128u) return fail(h, KID_ERR_STATE, "KID, calve_icebergs: berg is not in the correct cell!");
+    return fail(h, KID_ERR_STATE, "kid: device error flag set");
+  }
+  return KID_OK;
+}
+
+// ------------------------------------------------------------------ sort
+template <typename T>
+static void gather_cols(kid_t* h, T** cols, int ncols, T** spare, long long n_new) {
+  // permutes columns one group at a time through the spare buffer: dst of a group is
+  // the spare of the previous one, so one extra column of memory suffices
+  for (int c = 0; c < ncols; c++) {
+    if (!cols[c]) continue;
+    GatherArgs<T, 1> a;
+    a.src[0] = cols[c]; a.dst[0] = *spare;
+    LAUNCH(h, (k_gather<T, 1>), n_new, 256, a, h->perm, n_new);
+    std::swap(cols[c], *spare);
+  }
+}
+
+static int sort_bergs(kid_t* h) {
+  long long n2 = h->n2, ns = h->n_slots;
+  if (ns <= 0) { h->steps_since_sort = 0; return KID_OK; }
+  CK(cudaMemsetAsync(h->cell_count, 0, sizeof(int32_t) * n2, h->stream));
+  CK(cudaMemsetAsync(h->cell_fill, 0, sizeof(int32_t) * n2, h->stream));
+  LAUNCH(h, k_hist, ns, 256, h->g, h->b.flags, h->b.ine, h->b.jne, ns, h->cell_count);
+  int nsb = (int)((n2 + KID_SCAN_ITEMS - 1) / KID_SCAN_ITEMS);
+  LAUNCH(h, k_scan_block, (long long)nsb * 256, 256, h->cell_count, h->cell_start, h->scan_sums, n2);
+  k_scan_sums<<<1, 1024, 0, h->stream>>>(h->scan_sums, nsb, h->scan_total); h->launches++;
+  LAUNCH(h, k_scan_add, n2, 256, h->cell_start, h->scan_sums, n2);
+  LAUNCH(h, k_rank, ns, 256, h->g, h->b.flags, h->b.ine, h->b.jne, ns, h->cell_start, h->cell_fill, h->perm);
+  LAUNCH(h, k_cell_order, n2, 128, h->cell_start, h->cell_count, n2, h->perm);
+  int32_t total = 0;
+  CK(cudaMemcpyAsync(&total, h->scan_total, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  long long n_new = total;
+  double* sp8 = (double*)h->spare8;
+  gather_cols<double>(h, h->b.f64, C_NCOLS, &sp8, n_new);
+  int64_t* spi = (int64_t*)sp8;
+  gather_cols<int64_t>(h, &h->b.id, 1, &spi, n_new);
+  h->spare8 = spi;
+  int32_t* sp4 = (int32_t*)h->spare4;
+  int32_t* icols[3] = {h->b.ine, h->b.jne, h->b.start_year};
+  gather_cols<int32_t>(h, icols, 3, &sp4, n_new);
+  h->b.ine = icols[0]; h->b.jne = icols[1]; h->b.start_year = icols[2];
+  h->spare4 = sp4;
+  uint8_t* sp1 = (uint8_t*)h->spare1;
+  CK(cudaMemsetAsync(sp1, 0, h->capacity, h->stream));
+  uint8_t* bcols[1] = {h->b.flags};
+  gather_cols<uint8_t>(h, bcols, 1, &sp1, n_new);
+  h->b.flags = bcols[0];
+  CK(cudaMemsetAsync(sp1, 0, h->capacity, h->stream));
+  bcols[0] = h->b.halo_code;
+  gather_cols<uint8_t>(h, bcols, 1, &sp1, n_new);
+  h->b.halo_code = bcols[0];
+  h->spare1 = sp1;
+  unsigned long long nn = (unsigned long long)n_new;
+  CK(cudaMemcpyAsync(&h->dcnt->n_slots, &nn, sizeof(nn), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->n_slots = n_new;
+  h->steps_since_sort = 0;
+  h->dirty_appended = 0;
+  h->sorted_once = 1;
+  return KID_OK;
+}
+
+extern "C" int32_t kid_sort_bergs(kid_t* h) {
+  if (!h) return KID_ERR_ARG;
+  cudaSetDevice(h->d.device);
+  return sort_bergs(h);
+}
+
+// ---------------------------------------------------------- berg columns
+namespace {
+struct ColMap { int col; double* KidBergColumns::*member; };
+const ColMap kColMap[] = {
+    {C_LON, &KidBergColumns::lon}, {C_LAT, &KidBergColumns::lat}, {C_UVEL, &KidBergColumns::uvel},
+    {C_VVEL, &KidBergColumns::vvel}, {C_AXN, &KidBergColumns::axn}, {C_AYN, &KidBergColumns::ayn},
+    {C_BXN, &KidBergColumns::bxn}, {C_BYN, &KidBergColumns::byn}, {C_UVEL_PREV, &KidBergColumns::uvel_prev},
+    {C_VVEL_PREV, &KidBergColumns::vvel_prev}, {C_XI, &KidBergColumns::xi}, {C_YJ, &KidBergColumns::yj},
+    {C_MASS, &KidBergColumns::mass}, {C_THICKNESS, &KidBergColumns::thickness}, {C_WIDTH, &KidBergColumns::width},
+    {C_LENGTH, &KidBergColumns::length}, {C_MASS_SCALING, &KidBergColumns::mass_scaling},
+    {C_MASS_OF_BITS, &KidBergColumns::mass_of_bits}, {C_HEAT_DENSITY, &KidBergColumns::heat_density},
+    {C_START_LON, &KidBergColumns::start_lon}, {C_START_LAT, &KidBergColumns::start_lat},
+    {C_START_DAY, &KidBergColumns::start_day}, {C_START_MASS, &KidBergColumns::start_mass},
+    {C_MASS_OF_FL_BITS, &KidBergColumns::mass_of_fl_bits},
+    {C_MASS_OF_FL_BERGY_BITS, &KidBergColumns::mass_of_fl_bergy_bits}, {C_FL_K, &KidBergColumns::fl_k},
+    {C_UVEL_OLD, &KidBergColumns::uvel_old}, {C_VVEL_OLD, &KidBergColumns::vvel_old},
+    {C_LON_OLD, &KidBergColumns::lon_old}, {C_LAT_OLD, &KidBergColumns::lat_old}};
+}  // namespace
+
+extern "C" int32_t kid_set_bergs(kid_t* h, int64_t n, const KidBergColumns* c) {
+  if (!h || !c || n < 0) return KID_ERR_ARG;
+  if (h->fatal) return KID_ERR_STATE;
+  if (n == 0) { h->restarted = 1; return KID_OK; }
+  if (!c->lon || !c->lat || !c->mass || !c->thickness || !c->width || !c->length)
+    return fail(h, KID_ERR_ARG, "kid_set_bergs: lon, lat, mass, thickness, width, length are required");
+  cudaSetDevice(h->d.device);
+  long long s0 = h->n_slots;
+  if (s0 + n > h->capacity) return fail(h, KID_ERR_CAPACITY, "kid_set_bergs: capacity exceeded");
+  DevBergs& b = h->b;
+  std::vector<double> tmp;
+  for (const ColMap& m : kColMap) {
+    double* dst = b.f64[m.col];
+    if (!dst) continue;
+    const double* src = c->*(m.member);
+    // reference defaults for absent columns (fmsio:742-860): start_* = current, mass_scaling = 1,
+    // *_old = current (fmsio:828-831), everything else 0
+    if (!src) {
+      if (m.col == C_START_LON || m.col == C_LON_OLD) src = c->lon;
+      else if (m.col == C_START_LAT || m.col == C_LAT_OLD) src = c->lat;
+      else if (m.col == C_START_MASS) src = c->mass;
+      else if (m.col == C_UVEL_OLD) src = c->uvel;
+      else if (m.col == C_VVEL_OLD) src = c->vvel;
+    }
+    if (src) {
+      CK(cudaMemcpyAsync(dst + s0, src, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    } else if (m.col == C_MASS_SCALING) {
+      tmp.assign((size_t)n, 1.);
+      CK(cudaMemcpyAsync(dst + s0, tmp.data(), sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+    } else {
+      CK(cudaMemsetAsync(dst + s0, 0, sizeof(double) * n, h->stream));
+    }
+  }
+  if (c->start_year) CK(cudaMemcpyAsync(b.start_year + s0, c->start_year, sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->stream));
+  else CK(cudaMemsetAsync(b.start_year + s0, 0, sizeof(int32_t) * n, h->stream));
+  int have_ij = (c->ine && c->jne) ? 1 : 0;
+  if (have_ij) {
+    CK(cudaMemcpyAsync(b.ine + s0, c->ine, sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(b.jne + s0, c->jne, sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (c->id) CK(cudaMemcpyAsync(b.id + s0, c->id, sizeof(int64_t) * n, cudaMemcpyHostToDevice, h->stream));
+  std::vector<uint8_t> fl((size_t)n), hc((size_t)n, 0);
+  for (int64_t k = 0; k < n; k++) {
+    uint8_t f = BF_ALIVE;
+    if (c->static_berg && c->static_berg[k] >= 0.5) f |= BF_STATIC;
+    if (c->halo_berg && c->halo_berg[k] >= 0.5) { f |= BF_HALO; hc[k] = (uint8_t)c->halo_berg[k]; }
+    fl[k] = f;
+  }
+  CK(cudaMemcpyAsync(b.flags + s0, fl.data(), n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(b.halo_code + s0, hc.data(), n, cudaMemcpyHostToDevice, h->stream));
+  LAUNCH(h, k_locate, (long long)n, 128, h->g, h->b, h->dp, h->dcnt, s0, s0 + n, have_ij);
+  if (!c->id) { k_generate_ids<<<1, 1, 0, h->stream>>>(h->g, h->b, s0, s0 + n); h->launches++; }
+  unsigned long long nn = (unsigned long long)(s0 + n);
+  CK(cudaMemcpyAsync(&h->dcnt->n_slots, &nn, sizeof(nn), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->n_slots = s0 + n;
+  h->restarted = 1;
+  int rc = check_device_errors(h);
+  if (rc) return rc;
+  return sort_bergs(h);
+}
+
+extern "C" int32_t kid_count_bergs(kid_t* h, int64_t* n) {
+  if (!h || !n) return KID_ERR_ARG;
+  cudaSetDevice(h->d.device);
+  CK(cudaMemsetAsync(h->dflags + 2, 0, sizeof(unsigned long long), h->stream));
+  LAUNCH(h, k_count_alive, h->n_slots, 256, h->b.flags, h->n_slots, 0, h->dflags + 2);
+  CK(cudaMemcpyAsync(h->hflags + 2, h->dflags + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *n = (int64_t)h->hflags[2];
+  return KID_OK;
+}
+
+extern "C" int32_t kid_get_bergs(kid_t* h, int64_t* n, KidBergColumns* c, int32_t include_halo) {
+  if (!h || !n || !c) return KID_ERR_ARG;
+  cudaSetDevice(h->d.device);
+  long long ns = h->n_slots;
+  int64_t cap = *n;
+  std::vector<uint8_t> fl((size_t)ns), hc((size_t)ns);
+  if (ns > 0) {
+    CK(cudaMemcpyAsync(fl.data(), h->b.flags, ns, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(hc.data(), h->b.halo_code, ns, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  std::vector<long long> keep;
+  keep.reserve((size_t)ns);
+  for (long long s = 0; s < ns; s++) {
+    uint8_t f = fl[s];
+    if ((f & BF_ALIVE) && !(f & BF_LEAVER) && (include_halo || !(f & BF_HALO))) keep.push_back(s);
+  }
+  int64_t nk = (int64_t)keep.size();
+  *n = nk;
+  if (nk > cap) return fail(h, KID_ERR_CAPACITY, "kid_get_bergs: caller arrays too small");
+  std::vector<double> tmp((size_t)ns);
+  for (const ColMap& m : kColMap) {
+    double* dst = c->*(m.member);
+    if (!dst) continue;
+    const double* src = h->b.f64[m.col];
+    if (!src) {   // columns this configuration does not carry read back as the reference would hold them
+      int alt = -1;
+      if (m.col == C_UVEL_OLD) alt = C_UVEL; else if (m.col == C_VVEL_OLD) alt = C_VVEL;
+      else if (m.col == C_LON_OLD) alt = C_LON; else if (m.col == C_LAT_OLD) alt = C_LAT;
+      if (alt < 0) { for (int64_t k = 0; k < nk; k++) dst[k] = 0.; continue; }
+      src = h->b.f64[alt];
+    }
+    CK(cudaMemcpy(tmp.data(), src, sizeof(double) * ns, cudaMemcpyDeviceToHost));
+    for (int64_t k = 0; k < nk; k++) dst[k] = tmp[(size_t)keep[k]];
+  }
+  double* zero_cols[] = {c->axn_fast, c->ayn_fast, c->bxn_fast, c->byn_fast, c->ang_vel, c->ang_accel, c->rot,
+                         c->uo, c->vo, c->ui, c->vi, c->ua, c->va, c->ssh_x, c->ssh_y, c->sst, c->sss, c->cn, c->hi, c->od};
+  for (double* z : zero_cols) if (z) for (int64_t k = 0; k < nk; k++) z[k] = 0.;
+  if (c->static_berg) for (int64_t k = 0; k < nk; k++) c->static_berg[k] = (fl[(size_t)keep[k]] & BF_STATIC) ? 1. : 0.;
+  if (c->halo_berg) for (int64_t k = 0; k < nk; k++) c->halo_berg[k] = (double)hc[(size_t)keep[k]];
+  std::vector<int32_t> ti((size_t)ns);
+  struct IC { int32_t* dst; const int32_t* src; } ics[] = {{c->ine, h->b.ine}, {c->jne, h->b.jne}, {c->start_year, h->b.start_year}};
+  for (auto& ic : ics) {
+    if (!ic.dst) continue;
+    CK(cudaMemcpy(ti.data(), ic.src, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost));
+    for (int64_t k = 0; k < nk; k++) ic.dst[k] = ti[(size_t)keep[k]];
+  }
+  if (c->n_bonds) for (int64_t k = 0; k < nk; k++) c->n_bonds[k] = 0;
+  if (c->conglom_id) for (int64_t k = 0; k < nk; k++) c->conglom_id[k] = 0;
+  if (c->id) {
+    std::vector<int64_t> tl((size_t)ns);
+    CK(cudaMemcpy(tl.data(), h->b.id, sizeof(int64_t) * ns, cudaMemcpyDeviceToHost));
+    for (int64_t k = 0; k < nk; k++) c->id[k] = tl[(size_t)keep[k]];
+  }
+  return KID_OK;
+}
+
+extern "C" int32_t kid_set_bonds(kid_t* h, int64_t nb, const KidBondColumns* c) {
+  (void)c;
+  if (!h) return KID_ERR_ARG;
+  if (nb == 0) return KID_OK;
+  return fail(h, KID_ERR_UNSUPPORTED, "kid_set_bonds: bonds are not implemented in this build");
+}
+extern "C" int32_t kid_get_bonds(kid_t* h, int64_t* nb, KidBondColumns* c) {
+  (void)c;
+  if (!h || !nb) return KID_ERR_ARG;
+  *nb = 0;
+  return KID_OK;
+}
+
+extern "C" int32_t kid_set_calving_state(kid_t* h, const double* stored_ice, const double* stored_heat,
+                                         const int32_t* counter) {
+  if (!h) return KID_ERR_ARG;
+  cudaSetDevice(h->d.device);
+  if (stored_ice) CK(cudaMemcpyAsync(h->g.stored_ice, stored_ice, sizeof(double) * h->n2 * KID_NCLASSES, cudaMemcpyHostToDevice, h->stream));
+  if (stored_heat) CK(cudaMemcpyAsync(h->g.stored_heat, stored_heat, sizeof(double) * h->n2, cudaMemcpyHostToDevice, h->stream));
+  if (counter) CK(cudaMemcpyAsync(h->g.iceberg_counter_grd, counter, sizeof(int32_t) * h->n2, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->restarted = 1;
+  if (stored_ice) h->calving_active = 1;
+  return KID_OK;
+}
+extern "C" int32_t kid_get_calving_state(kid_t* h, double* stored_ice, double* stored_heat, int32_t* counter) {
+  if (!h) return KID_ERR_ARG;
+  cudaSetDevice(h->d.device);
+  CK(cudaStreamSynchronize(h->stream));
+  if (stored_ice) CK(cudaMemcpy(stored_ice, h->g.stored_ice, sizeof(double) * h->n2 * KID_NCLASSES, cudaMemcpyDeviceToHost));
+  if (stored_heat) CK(cudaMemcpy(stored_heat, h->g.stored_heat, sizeof(double) * h->n2, cudaMemcpyDeviceToHost));
+  if (counter) CK(cudaMemcpy(counter, h->g.iceberg_counter_grd, sizeof(int32_t) * h->n2, cudaMemcpyDeviceToHost));
+  return KID_OK;
+}
+
+// ------------------------------------------------------------- forcing
+static void zero_flux_fields(kid_t* h, bool also_calving) {
+  DevGrid& g = h->g;
+  FieldList fl;
+  fl.n = 0;
+  double* base[] = {g.floating_melt, g.berg_melt, g.bergy_src, g.bergy_melt};
+  for (double* f : base) fl.f[fl.n++] = f;
+  if (h->p.footloose) { fl.f[fl.n++] = g.fl_bits_src; fl.f[fl.n++] = g.fl_bits_melt; }
+  if (h->p.melt_diagnostics) {
+    double* dg[] = {g.melt_buoy, g.melt_eros, g.melt_conv, g.melt_buoy_fl, g.melt_eros_fl, g.melt_conv_fl,
+                    g.fl_parent_melt, g.fl_child_melt};
+    for (double* f : dg) fl.f[fl.n++] = f;
+  }
+  if (also_calving) { fl.f[fl.n++] = g.calving; fl.f[fl.n++] = g.calving_hflx; }
+  LAUNCH(h, k_zero_fields, h->n2, 256, fl, h->n2);
+}
+
+static void halo_update(kid_t* h, std::initializer_list<double*> fields) {
+  // mpp_update_domains: on one rank that is its own E/W neighbour this is the cyclic
+  // wrap; ranks of a multi-rank layout receive the one-cell ring from the caller
+  // (icebergs_run's (nic+2,njc+2) arguments), which is all the free-drift path reads
+  if (!(h->g.pe_E_self && h->g.pe_W_self)) return;
+  FieldList fl;
+  fl.n = 0;
+  for (double* f : fields) fl.f[fl.n++] = f;
+  long long n = (long long)2 * h->p.halo * h->njc;
+  LAUNCH(h, k_halo_wrap_x, n, 128, h->g, fl);
+}
+
+// forcing ingest I:5203-5383
+static int ingest_forcing(kid_t* h, const double* calving, const double* uo, const double* vo, const double* ui,
+                          const double* vi, const double* tauxa, const double* tauya, const double* ssh,
+                          const double* sst, const double* calving_hflx, const double* cn, const double* hi,
+                          int stagger, int stress_stagger, const double* sss) {
+  if (!uo || !vo || !ui || !vi || !tauxa || !tauya || !ssh || !sst || !cn || !hi)
+    return fail(h, KID_ERR_ARG, "kid: null forcing array");
+  if (stagger != KID_BGRID_NE && stagger != KID_CGRID_NE) return fail(h, KID_ERR_ARG, "KID, iceberg_run: Unrecognized value of stagger!");
+  if (stress_stagger != KID_BGRID_NE && stress_stagger != KID_CGRID_NE && stress_stagger != KID_AGRID)
+    return fail(h, KID_ERR_ARG, "KID, iceberg_run: Unrecognized value of stress_stagger!");
+  DevGrid& g = h->g;
+  const long long n2 = h->n2;
+  const size_t nc = (size_t)h->nic * h->njc, nr = (size_t)(h->nic + 2) * (h->njc + 2);
+  const double* src[13] = {calving, uo, vo, ui, vi, tauxa, tauya, ssh, sst, calving_hflx, cn, hi, sss};
+  const size_t cnt[13] = {nc, nr, nr, nr, nr, nc, nc, nr, nc, nc, nr, nr, nc};
+  for (int k = 0; k < 13; k++)
+    if (src[k]) CK(cudaMemcpyAsync(h->in_stage[k], src[k], sizeof(double) * cnt[k], cudaMemcpyHostToDevice, h->stream));
+  double** st = h->in_stage;
+  zero_flux_fields(h, false);
+  CK(cudaMemsetAsync(h->dflags, 0, 2 * sizeof(unsigned long long), h->stream));
+  LAUNCH(h, k_copy_in, (long long)nc, 256, g, calving_hflx ? st[9] : nullptr, g.calving_hflx, 0, 1, 0.);
+  LAUNCH(h, k_copy_in, (long long)nc, 256, g, calving ? st[0] : nullptr, g.calving, 0, 1, 0.);
+  LAUNCH(h, k_calving_units, n2, 256, g, n2);
+  if (stagger == KID_BGRID_NE) {
+    LAUNCH(h, k_copy_in, (long long)nr, 256, g, st[1], g.uo, 1, 0, 0.);
+    LAUNCH(h, k_copy_in, (long long)nr, 256, g, st[2], g.vo, 1, 0, 0.);
+    LAUNCH(h, k_copy_in, (long long)nr, 256, g, st[3], g.ui, 1, 0, 0.);
+    LAUNCH(h, k_copy_in, (long long)nr, 256, g, st[4], g.vi, 1, 0, 0.);
+  } else {
+    LAUNCH(h, k_cgrid_vel, (long long)(h->nic + 1) * (h->njc + 1), 256, g, st[1], st[2], st[3], st[4]);
+  }
+  if (stress_stagger == KID_BGRID_NE) {
+    LAUNCH(h, k_copy_in, (long long)nc, 256, g, st[5], g.ua, 0, 0, 0.);
+    LAUNCH(h, k_copy_in, (long long)nc, 256, g, st[6], g.va, 0, 0, 0.);
+  } else {
+    CK(cudaMemsetAsync(h->tmp_u, 0, sizeof(double) * n2, h->stream));
+    CK(cudaMemsetAsync(h->tmp_v, 0, sizeof(double) * n2, h->stream));
+    LAUNCH(h, k_copy_in, (long long)nc, 256, g, st[5], h->tmp_u, 0, 0, 0.);
+    LAUNCH(h, k_copy_in, (long long)nc, 256, g, st[6], h->tmp_v, 0, 0, 0.);
+    halo_update(h, {h->tmp_u, h->tmp_v});
+    LAUNCH(h, k_stress_to_corners, (long long)(h->nic + 1) * (h->njc + 1), 256, g, h->tmp_u, h->tmp_v,
+           stress_stagger == KID_AGRID ? 1 : 0);
+  }
+  halo_update(h, {g.uo, g.vo, g.ui, g.vi});
+  if (!h->p.tau_is_velocity) LAUNCH(h, k_invert_tau, n2, 256, g, n2);
+  halo_update(h, {g.ua, g.va});
+  LAUNCH(h, k_copy_in, (long long)nr, 256, g, st[7], g.ssh, 1, 0, 0.);
+  halo_update(h, {g.ssh});
+  LAUNCH(h, k_sst_max, (long long)nc, 256, g, st[8], calving ? st[0] : nullptr, h->dflags);
+  LAUNCH(h, k_sst_in, (long long)nc, 256, g, st[8], h->dflags);
+  halo_update(h, {g.sst});
+  LAUNCH(h, k_copy_in, (long long)nr, 256, g, st[10], g.cn, 1, 0, 0.);
+  LAUNCH(h, k_copy_in, (long long)nr, 256, g, st[11], g.hi, 1, 0, 0.);
+  halo_update(h, {g.cn, g.hi});
+  LAUNCH(h, k_copy_in, (long long)nc, 256, g, sss ? st[12] : nullptr, g.sss, 0, 0, sss ? 0. : -1.0);
+  LAUNCH(h, k_scrub, n2, 256, g, n2);
+  LAUNCH(h, k_pack_forcing, n2, 256, g, n2);
+  CK(cudaMemcpyAsync(h->hflags, h->dflags, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  h->forcing_set = 1;
+  return KID_OK;
+}
+
+// ------------------------------------------------------------ one step
+template <bool FL, bool DG>
+static void launch_step(kid_t* h) {
+  LAUNCH(h, (k_step<FL, DG>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots);
+}
+
+static cudaEvent_t pool_event(kid_t* h) {
+  if (h->ev_used == (int)h->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->ev_pool.push_back(e);
+  }
+  return h->ev_pool[h->ev_used++];
+}
+
+// the hot path of icebergs_run, I:5389-5512
+static int step_core(kid_t* h) {
+  cudaStream_t s = h->stream;
+  CK(cudaEventRecord(h->ev[T_CALVING], s));
+  if (h->calving_active) {
+    int first = (h->first_call_accum && !h->restarted) ? 1 : 0;
+    h->first_call_accum = 0;
+    LAUNCH(h, k_accumulate_calving, h->n2, 256, h->g, h->ct, h->p.dt, first, h->n2);
+    LAUNCH(h, k_calve, (long long)h->nic * h->njc, 128, h->g, h->b, h->dp, h->ct, h->dcnt, h->n2);
+    CK(cudaMemcpyAsync(&h->hcnt->n_slots, &h->dcnt->n_slots, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    long long ns = (long long)h->hcnt->n_slots;
+    if (ns > h->capacity) return fail(h, KID_ERR_CAPACITY, "kid: berg store capacity exceeded by calving");
+    h->dirty_appended += ns - h->n_slots;
+    h->n_slots = ns;
+  }
+  h->first_call_accum = 0;
+  h->visited = 1;
+  CK(cudaEventRecord(h->ev[T_MOMENTUM], s));
+  cudaEvent_t e0 = pool_event(h), e1 = pool_event(h), e2 = pool_event(h);
+  CK(cudaEventRecord(e0, s));
+  if (!h->p.static_icebergs) {
+    if (h->p.melt_diagnostics) launch_step<false, true>(h); else launch_step<false, false>(h);
+  } else {
+    if (h->p.melt_diagnostics) { LAUNCH(h, (k_thermo_range<false, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, 0LL, h->n_slots, 1); }
+    else { LAUNCH(h, (k_thermo_range<false, false>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, 0LL, h->n_slots, 1); }
+  }
+  CK(cudaEventRecord(h->ev[T_SORT], s));
+  CK(cudaEventRecord(e1, s));
+  h->steps_since_sort++;
+  if (h->steps_since_sort >= h->sort_interval || h->dirty_appended > h->n_slots / 8) {
+    int rc = sort_bergs(h);
+    if (rc) return rc;
+  }
+  CK(cudaEventRecord(h->ev[T_TOTAL], s));
+  CK(cudaEventRecord(e2, s));
+  return KID_OK;
+}
+
+// timing[] of the last kid_run / kid_step_resident call, all steps of the call summed:
+// [0] interface (first step only) [1] calving (last step) [2] fused momentum+thermodynamics kernel
+// [5] sort [6] whole call [7] number of steps
+static void collect_timing(kid_t* h, cudaEvent_t first) {
+  float ms = 0;
+  for (int k = 0; k < 8; k++) h->timing[k] = 0;
+  if (cudaEventElapsedTime(&ms, h->ev[T_CALVING], h->ev[T_MOMENTUM]) == cudaSuccess) h->timing[1] = ms;
+  for (int k = 0; k + 2 < h->ev_used; k += 3) {
+    if (cudaEventElapsedTime(&ms, h->ev_pool[k], h->ev_pool[k + 1]) == cudaSuccess) h->timing[2] += ms;
+    if (cudaEventElapsedTime(&ms, h->ev_pool[k + 1], h->ev_pool[k + 2]) == cudaSuccess) h->timing[5] += ms;
+    h->timing[7] += 1;
+  }
+  if (h->ev_used >= 3 && cudaEventElapsedTime(&ms, first, h->ev_pool[0]) == cudaSuccess) h->timing[0] = ms;
+  if (cudaEventElapsedTime(&ms, first, h->ev[T_TOTAL]) == cudaSuccess) h->timing[6] = ms;
+  h->ev_used = 0;
+  cudaGetLastError();
+}
+
+extern "C" int32_t kid_set_forcing(kid_t* h, const double* calving, const double* uo, const double* vo,
+                                   const double* ui, const double* vi, const double* tauxa, const double* tauya,
+                                   const double* ssh, const double* sst, const double* calving_hflx,
+                                   const double* cn, const double* hi, int32_t stagger, int32_t stress_stagger,
+                                   const double* sss) {
+  if (!h) return KID_ERR_ARG;
+  if (h->fatal) return KID_ERR_STATE;
+  cudaSetDevice(h->d.device);
+  int rc = ingest_forcing(h, calving, uo, vo, ui, vi, tauxa, tauya, ssh, sst, calving_hflx, cn, hi, stagger, stress_stagger, sss);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->hflags[1]) h->calving_active = 1;
+  return KID_OK;
+}
+
+extern "C" int32_t kid_run(kid_t* h, int32_t year, double yearday, double* calving, const double* uo,
+                           const double* vo, const double* ui, const double* vi, const double* tauxa,
+                           const double* tauya, const double* ssh, const double* sst, double* calving_hflx,
+                           const double* cn, const double* hi, int32_t stagger, int32_t stress_stagger,
+                           const double* sss, double* mass_berg, double* ustar_berg, double* area_berg) {
+  if (!h || !calving || !calving_hflx) return KID_ERR_ARG;
+  if (h->fatal) return KID_ERR_STATE;
+  cudaSetDevice(h->d.device);
+  h->dp.current_year = year; h->dp.current_yearday = yearday;
+  h->ev_used = 0;
+  CK(cudaEventRecord(h->ev[T_NPHASE], h->stream));
+  int rc = ingest_forcing(h, calving, uo, vo, ui, vi, tauxa, tauya, ssh, sst, calving_hflx, cn, hi, stagger, stress_stagger, sss);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));      // hflags: is any calving coming in?
+  if (h->hflags[1]) h->calving_active = 1;
+  rc = step_core(h);
+  if (rc) return rc;
+  size_t nc = (size_t)h->nic * h->njc;
+  if (!h->p.passive_mode) {
+    LAUNCH(h, k_outputs, (long long)nc, 256, h->g, h->out_stage[0], h->out_stage[1]);
+    CK(cudaMemcpyAsync(calving, h->out_stage[0], sizeof(double) * nc, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(calving_hflx, h->out_stage[1], sizeof(double) * nc, cudaMemcpyDeviceToHost, h->stream));
+    // mass/ustar/area on the ocean grid come from the spreading rows; this
+    // build returns the zeroed fields icebergs_run starts from (I:5158-5166)
+    if (mass_berg) memset(mass_berg, 0, sizeof(double) * nc);
+    if (ustar_berg) memset(ustar_berg, 0, sizeof(double) * nc);
+    if (area_berg) memset(area_berg, 0, sizeof(double) * nc);
+  }
+  CK(cudaEventRecord(h->ev[T_NPHASE + 1], h->stream));
+  rc = check_device_errors(h);
+  collect_timing(h, h->ev[T_NPHASE]);
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, h->ev[T_NPHASE], h->ev[T_NPHASE + 1]) == cudaSuccess) h->timing[6] = ms;
+  // a step that brought no calving and calved nothing leaves the calving state inert
+  if (!h->hflags[1] && h->dirty_appended == 0) h->calving_active = 0;
+  return rc;
+}
+
+extern "C" int32_t kid_step_resident(kid_t* h, int32_t nsteps, int32_t year, double yearday) {
+  if (!h || nsteps < 0) return KID_ERR_ARG;
+  if (h->fatal) return KID_ERR_STATE;
+  if (!h->forcing_set) return fail(h, KID_ERR_STATE, "kid_step_resident: no forcing on the device yet (call kid_run or kid_set_forcing)");
+  cudaSetDevice(h->d.device);
+  h->dp.current_year = year; h->dp.current_yearday = yearday;
+  h->ev_used = 0;
+  CK(cudaEventRecord(h->ev[T_NPHASE], h->stream));
+  for (int s = 0; s < nsteps; s++) {
+    zero_flux_fields(h, true);
+    long long before = h->n_slots;
+    int rc = step_core(h);
+    if (rc) return rc;
+    if (h->calving_active && h->n_slots == before) h->calving_active = 0;   // no input, nothing left to calve
+  }
+  CK(cudaEventRecord(h->ev[T_NPHASE + 1], h->stream));
+  int rc = check_device_errors(h);
+  collect_timing(h, h->ev[T_NPHASE]);
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, h->ev[T_NPHASE], h->ev[T_NPHASE + 1]) == cudaSuccess) h->timing[6] = ms;
+  return rc;
+}
+
+extern "C" int32_t kid_last_timing(kid_t* h, double ms[8]) {
+  if (!h || !ms) return KID_ERR_ARG;
+  for (int k = 0; k < 8; k++) ms[k] = h->timing[k];
+  return KID_OK;
+}
+extern "C" int64_t kid_kernel_launches(kid_t* h) { return h ? h->launches : 0; }
+
+extern "C" int32_t kid_get_counters(kid_t* h, KidCounters* c) {
+  if (!h || !c) return KID_ERR_ARG;
+  cudaSetDevice(h->d.device);
+  CK(cudaMemcpyAsync(h->hcnt, h->dcnt, sizeof(DevCounters), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  memset(c, 0, sizeof(*c));
+  int64_t n = 0;
+  int rc = kid_count_bergs(h, &n);
+  if (rc) return rc;
+  c->nbergs = n;
+  c->nbergs_calved = (int64_t)h->hcnt->nbergs_calved;
+  c->nbergs_calved_fl = (int64_t)h->hcnt->nbergs_calved_fl;
+  c->nbergs_melted = (int64_t)h->hcnt->nbergs_melted;
+  c->nspeeding_tickets = (int64_t)h->hcnt->nspeeding;
+  c->n_sent = (int64_t)h->hcnt->n_leavers;
+  c->n_bounced = (int64_t)h->hcnt->n_bounced;
+  c->net_heat_to_ocean = h->hcnt->net_heat_to_ocean;
+  c->net_calving_to_bergs = h->hcnt->net_calving_to_bergs;
+  c->net_heat_to_bergs = h->hcnt->net_heat_to_bergs;
+  c->error_flags = (int32_t)h->hcnt->error_flags;
+  return KID_OK;
+}
+
+static const double* field_ptr(kid_t* h, int id) {
+  DevGrid& g = h->g;
+  switch (id) {
+    case KID_FLD_FLOATING_MELT: return g.floating_melt; case KID_FLD_BERG_MELT: return g.berg_melt;
+    case KID_FLD_BERGY_SRC: return g.bergy_src; case KID_FLD_BERGY_MELT: return g.bergy_melt;
+    case KID_FLD_FL_BITS_MELT: return g.fl_bits_melt; case KID_FLD_FL_BITS_SRC: return g.fl_bits_src;
+    case KID_FLD_CALVING_HFLX: return g.calving_hflx; case KID_FLD_CALVING: return g.calving;
+    case KID_FLD_MELT_BUOY: return g.melt_buoy; case KID_FLD_MELT_EROS: return g.melt_eros;
+    case KID_FLD_MELT_CONV: return g.melt_conv; case KID_FLD_MELT_BUOY_FL: return g.melt_buoy_fl;
+    case KID_FLD_MELT_EROS_FL: return g.melt_eros_fl; case KID_FLD_MELT_CONV_FL: return g.melt_conv_fl;
+    case KID_FLD_FL_PARENT_MELT: return g.fl_parent_melt; case KID_FLD_FL_CHILD_MELT: return g.fl_child_melt;
+    case KID_FLD_UO: return g.uo; case KID_FLD_VO: return g.vo; case KID_FLD_UI: return g.ui;
+    case KID_FLD_VI: return g.vi; case KID_FLD_UA: return g.ua; case KID_FLD_VA: return g.va;
+    case KID_FLD_SSH: return g.ssh; case KID_FLD_SST: return g.sst; case KID_FLD_SSS: return g.sss;
+    case KID_FLD_CN: return g.cn; case KID_FLD_HI: return g.hi;
+    case KID_FLD_LON: return g.lon; case KID_FLD_LAT: return g.lat; case KID_FLD_LONC: return g.lonc;
+    case KID_FLD_LATC: return g.latc; case KID_FLD_DX: return g.dx; case KID_FLD_DY: return g.dy;
+    case KID_FLD_AREA: return g.area; case KID_FLD_MSK: return g.msk; case KID_FLD_COS: return g.cosr;
+    case KID_FLD_SIN: return g.sinr; case KID_FLD_OCEAN_DEPTH: return g.ocean_depth;
+    case KID_FLD_STORED_HEAT: return g.stored_heat;
+    default: return nullptr;
+  }
+}
+
+extern "C" int32_t kid_get_grid_field(kid_t* h, int32_t field_id, double* out) {
+  if (!h || !out) return KID_ERR_ARG;
+  cudaSetDevice(h->d.device);
+  const double* f = field_ptr(h, field_id);
+  if (!f) {
+    if (field_id >= 0 && field_id < KID_FLD_COUNT_) {   // spreading-row fields: not produced by this build
+      memset(out, 0, sizeof(double) * h->n2);
+      return KID_OK;
+    }
+    return fail(h, KID_ERR_ARG, "kid_get_grid_field: unknown field id");
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(out, f, sizeof(double) * h->n2, cudaMemcpyDeviceToHost));
+  return KID_OK;
+}
+
+extern "C" int32_t kid_stock(kid_t* h, int32_t index, double* value) {
+  (void)index;
+  if (!h || !value) return KID_ERR_ARG;
+  return fail(h, KID_ERR_UNSUPPORTED, "kid_stock: icebergs_stock_pe is not implemented in this build");
+}
+extern "C" int32_t kid_incr_mass(kid_t* h, double* mass) {
+  (void)mass;
+  if (!h) return KID_ERR_ARG;
+  return fail(h, KID_ERR_UNSUPPORTED, "kid_incr_mass: icebergs_incr_mass needs the spreading rows (not in this build)");
+}
+
+extern "C" int32_t kid_synchronize(kid_t* h) {
+  if (!h) return KID_ERR_ARG;
+  cudaSetDevice(h->d.device);
+  CK(cudaStreamSynchronize(h->stream));
+  return KID_OK;
+}
+
+// ------------------------------------------------------------------ NCCL
+extern "C" int32_t kid_pack_width(void) { return (int32_t)PACK_W; }
+
+extern "C" int32_t kid_nccl_unique_id(char* out, int32_t nbytes) {
+  if (!out || nbytes < KID_NCCL_UNIQUE_ID_BYTES) return KID_ERR_ARG;
+  NcclApi& n = nccl();
+  if (!n.ok()) { g_init_error = "kid_nccl_unique_id: libnccl.so.2 could not be loaded"; return KID_ERR_COMM; }
+  ncclUniqueId id;
+  if (n.GetUniqueId(&id) != ncclSuccess_) { g_init_error = "ncclGetUniqueId failed"; return KID_ERR_COMM; }
+  memcpy(out, id.internal, KID_NCCL_UNIQUE_ID_BYTES);
+  return KID_OK;
+}
+
+extern "C" int32_t kid_nccl_init(void** comm, const char* idbytes, int32_t nbytes, int32_t nranks, int32_t rank,
+                                 int32_t device) {
+  if (!comm || !idbytes || nbytes < KID_NCCL_UNIQUE_ID_BYTES) return KID_ERR_ARG;
+  NcclApi& n = nccl();
+  if (!n.ok()) { g_init_error = "kid_nccl_init: libnccl.so.2 could not be loaded"; return KID_ERR_COMM; }
+  if (cudaSetDevice(device) != cudaSuccess) { g_init_error = "kid_nccl_init: cudaSetDevice failed"; return KID_ERR_CUDA; }
+  ncclUniqueId id;
+  memcpy(id.internal, idbytes, KID_NCCL_UNIQUE_ID_BYTES);
+  ncclComm_t c = nullptr;
+  int rc = n.CommInitRank(&c, nranks, id, rank);
+  if (rc != ncclSuccess_) {
+    g_init_error = std::string("ncclCommInitRank failed: ") + (n.GetErrorString ? n.GetErrorString(rc) : "?");
+    return KID_ERR_COMM;
+  }
+  *comm = (void*)c;
+  return KID_OK;
+}
+
+extern "C" int32_t kid_nccl_destroy(void* comm) {
+  if (!comm) return KID_OK;
+  NcclApi& n = nccl();
+  if (!n.ok() || !n.CommDestroy) return KID_ERR_COMM;
+  return n.CommDestroy((ncclComm_t)comm) == ncclSuccess_ ? KID_OK : KID_ERR_COMM;
+}

@@ -3,7 +3,7 @@
 // Storage: the reference keeps heap-allocated type(iceberg) nodes in per-cell
 // linked lists (F:290-359, F:416-423).  Here bergs are structure-of-arrays
 // columns in HBM indexed by slot, kept (periodically) sorted by cell so that a
-// warp's gathers fall in a handful of 32-byte sectors of the packed grid records.
+// warp's gathers fall in a handful of sectors of the packed grid records.
 //
 // Reference citations: I: = src/icebergs.F90, F: = src/icebergs_framework.F90.
 #pragma once
@@ -19,18 +19,31 @@ enum : uint8_t {
   BF_ALIVE = 1,      // slot holds a berg
   BF_STATIC = 2,     // static_berg >= 0.5   (F:323)
   BF_LEAVER = 4,     // left the rank's compute domain this step, awaiting migration
-  BF_HALO = 8        // halo copy (halo_berg >= 0.5; exact code in column halo_code)
+  BF_HALO = 8,       // halo copy (halo_berg >= 0.5)
+  BF_ARRIVAL = 16    // arrived by migration this step: thermodynamics still to do
 };
 
-// Scalars the kernels need, passed by value (lives in the constant bank).
+// module constants, I:68-80
+#define KID_RHO_ICE 916.7
+#define KID_RHO_WATER 999.8
+#define KID_RHO_AIR 1.1
+#define KID_RHO_SEAWATER 1025.
+#define KID_GRAVITY 9.8
+#define KID_CD_AV 1.3
+#define KID_CD_AH 0.0055
+#define KID_CD_WV 0.9
+#define KID_CD_WH 0.0012
+#define KID_CD_IV 0.9
+
+// Scalars the kernels need, passed by value as a __grid_constant__ parameter.
 struct DevParams {
-  double dt, pi, pi_180, omega2 /* 2*omega */, Lx, invLx, Rearth;
+  double dt, pi, pi_180, omega2 /* 2*omega */, Lx, Rearth;
   double lat_ref, rho_bergs, speed_limit, coastal_drift, ocean_drag_scale;
   double cdrag_grounding, h_to_init_grounding, u_override, v_override;
   double bergy_bit_erosion_fraction, sicn_shift, tip_parameter, melt_cutoff;
   double spring_coef, contact_spring_coef, contact_distance, radial_damping_coef, tangental_damping_coef;
-  double fl_youngs, rho_ratio /* rho_bergs/rho_seawater */;
-  double initial_mass_s[KID_NCLASSES], initial_mass_n[KID_NCLASSES];
+  double fl_youngs;
+  double current_yearday;
   int32_t grid_is_latlon, grid_is_regular, old_bug_bilin, use_roundoff_fix, use_f_plane;
   int32_t use_new_predictive_corrective, only_interactive_forces, override_iceberg_velocities;
   int32_t old_interp_flds_order, interactive_icebergs_on, iceberg_bonds_on, internal_bergs_for_drag;
@@ -38,61 +51,70 @@ struct DevParams {
   int32_t use_operator_splitting, set_melt_rates_to_zero, allow_bergs_to_roll, use_updated_rolling_scheme;
   int32_t iceberg_melt_without_decay, melt_diagnostics, footloose, mts, dem;
   int32_t contact_cells_lon, contact_cells_lat, max_bonds;
-  int32_t current_year; int32_t pad0;
-  double current_yearday;
+  int32_t current_year;
+  int32_t passive_mode;
 };
 
 // corner record: the 8 B-grid fields interp_flds bilinearly gathers (I:4757-4765)
 struct __align__(16) CornerRec { double uo, vo, ui, vi, ua, va, cosr, sinr; };
-// cell record: A-grid picks (I:4815-4818), od (I:4897), and what thermodynamics /
-// adjust_index_and_ground need from the cell
-struct __align__(16) CellRec { double sst, cn, hi, od, area, msk, sss, depth; };
+// cell record: A-grid picks (I:4815-4818), od (I:4897) and what thermodynamics /
+// adjust_index_and_ground need from the cell; ddx/ddy = ddx_ssh/ddy_ssh (I:4903-4926)
+struct __align__(16) CellRec { double sst, sss, cn, hi, od, area, ddx, ddy; };
 // corner position record
 struct __align__(16) LonLat { double lon, lat; };
 
 struct DevGrid {
   int32_t isd, ied, jsd, jed, isc, iec, jsc, jec, nid, njd, gni, gnj;
-  int32_t cyclic_x, cyclic_y, wrap_x_local /* cyclic x and this rank spans all of x */, pad;
+  int32_t cyclic_x, cyclic_y;
+  int32_t pe_E_self, pe_W_self;     // cyclic x and this rank is its own E/W neighbour
+  int32_t has_E, has_W, has_N, has_S;  // a neighbour rank exists in that direction
+  int32_t pad0, pad1;
   // static (data domain)
   double *lon, *lat, *lonc, *latc, *dx, *dy, *area, *msk, *cosr, *sinr, *ocean_depth;
   // forcing (data domain)
   double *uo, *vo, *ui, *vi, *ua, *va, *ssh, *sst, *sss, *cn, *hi;
   double *calving, *calving_hflx;
-  // packed per-step records for the hot kernel
+  // packed records for the hot kernel
   CornerRec* corner;
   CellRec* cell;
   LonLat* lonlat;
-  double *ddx, *ddy;   // ddx_ssh / ddy_ssh per cell (I:4903-4926)
   // flux / diagnostic outputs
   double *floating_melt, *berg_melt, *bergy_src, *bergy_melt, *fl_bits_melt, *fl_bits_src;
   double *melt_buoy, *melt_eros, *melt_conv, *melt_buoy_fl, *melt_eros_fl, *melt_conv_fl;
   double *fl_parent_melt, *fl_child_melt;
-  double *stored_heat, *stored_ice, *real_calving;
+  double *stored_heat, *stored_ice, *real_calving, *tmp;
   int32_t* iceberg_counter_grd;
 };
 
 // SoA berg store.  Columns follow F:290-359 (Appendix B of SURVEY.md).
+// The f64 columns are addressed through `f64[col]` so that generic code (sort
+// gather, pack/unpack, get/set) can loop over them.
+enum BergCol : int {
+  C_LON = 0, C_LAT, C_UVEL, C_VVEL, C_AXN, C_AYN, C_BXN, C_BYN, C_UVEL_PREV, C_VVEL_PREV,
+  C_XI, C_YJ, C_MASS, C_THICKNESS, C_WIDTH, C_LENGTH, C_MASS_SCALING, C_MASS_OF_BITS, C_HEAT_DENSITY,
+  C_START_LON, C_START_LAT, C_START_DAY, C_START_MASS,
+  C_MASS_OF_FL_BITS, C_MASS_OF_FL_BERGY_BITS, C_FL_K,
+  C_NBASE,                                       // columns always allocated
+  C_UVEL_OLD = C_NBASE, C_VVEL_OLD, C_LON_OLD, C_LAT_OLD,   // interactive
+  C_NINTER,
+  C_NCOLS = C_NINTER
+};
+
 struct DevBergs {
   int64_t capacity;
-  double *lon, *lat, *uvel, *vvel, *axn, *ayn, *bxn, *byn, *uvel_prev, *vvel_prev;
-  double *xi, *yj, *mass, *thickness, *width, *length, *mass_scaling, *mass_of_bits, *heat_density;
-  double *start_lon, *start_lat, *start_day, *start_mass;
-  double *mass_of_fl_bits, *mass_of_fl_bergy_bits, *fl_k;
-  double *uvel_old, *vvel_old, *lon_old, *lat_old;           // interactive only
-  double *env;                                                // 13 x capacity env cache (new interp order)
-  double *axn_fast, *ayn_fast, *bxn_fast, *byn_fast;          // mts
-  double *ang_vel, *ang_accel, *rot;                          // dem
+  double* f64[C_NCOLS];
   int64_t* id;
-  int32_t *ine, *jne, *start_year, *n_bonds, *conglom_id;
+  int32_t *ine, *jne, *start_year;
   uint8_t *flags, *halo_code;
 };
 
 // device-side counters (one struct in HBM per handle)
 struct DevCounters {
-  unsigned long long n_alive;        // slots in use (high-water mark = n_slots on host)
   unsigned long long nbergs_melted, nbergs_calved, nbergs_calved_fl, nspeeding, n_bounced;
-  unsigned long long n_leavers, n_lost;
-  unsigned long long n_slots;        // append cursor
+  unsigned long long n_leavers, n_lost, n_wrapped;
+  unsigned long long n_slots;        // append cursor (high-water mark of used slots)
+  unsigned long long n_alive;        // filled by the count kernel
+  unsigned long long n_cell_moves;   // bergs whose cell changed this step (sort heuristics)
   double net_heat_to_ocean, net_calving_to_bergs, net_heat_to_bergs;
   unsigned int error_flags;
   unsigned int warn_adjust;

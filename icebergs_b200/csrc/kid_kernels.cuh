@@ -1,0 +1,768 @@
+// kid_kernels.cuh -- the kernels of the B200 KID hot path (single translation unit:
+// included by kid_b200.cu).
+//
+//   k_step            fused evolve_icebergs (I:7081) + send_bergs_to_other_pes wrap
+//                     (F:2997, single-rank cyclic-x) + thermodynamics (I:2844): one
+//                     thread per berg slot, each column read once and written once,
+//                     melt fluxes scattered with warp-aggregated fp64 atomics.
+//   k_thermo_range    thermodynamics alone for a slot range (bergs that arrived by
+//                     migration after the fused kernel ran).
+//   k_hist/k_rank/k_cell_order/k_gather*   the cell-binned counting sort that replaces
+//                     move_berg_between_cells (F:1758) and the per-cell lists (F:416).
+//   k_ingest_* / k_pack_*   forcing ingest (I:5203-5383) and the packed grid records.
+//   k_accumulate_calving / k_calve   I:6153 / I:6225.
+#pragma once
+#include "kid_physics.cuh"
+
+namespace kid {
+
+#define KID_BLOCK 128
+
+// ------------------------------------------------------------------ helpers
+__device__ __forceinline__ double shfl_down_d(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+
+// Warp-aggregated scatter-add: lanes that hold the same key in a run of consecutive
+// lanes are reduced first (segmented suffix sum), the head lane of each run issues
+// one atomic.  All 32 lanes must call; key < 0 = nothing to add.
+struct SegInfo { int seg_end; bool head; };
+__device__ __forceinline__ SegInfo seg_info(long long key) {
+  int lane = threadIdx.x & 31;
+  long long prev = __shfl_up_sync(0xffffffffu, key, 1);
+  bool head = (lane == 0) || (key != prev);
+  unsigned heads = __ballot_sync(0xffffffffu, head);
+  unsigned above = (lane == 31) ? 0u : (heads >> (lane + 1));
+  SegInfo s;
+  s.seg_end = above ? (lane + 1 + (__ffs(above) - 1)) : 32;
+  s.head = head;
+  return s;
+}
+__device__ __forceinline__ double seg_sum(double v, const SegInfo& s) {
+  int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    double o = shfl_down_d(v, d);
+    if (lane + d < s.seg_end) v += o;
+  }
+  return v;
+}
+__device__ __forceinline__ void seg_scatter(double* __restrict__ fld, long long key, double v, const SegInfo& s) {
+  double t = seg_sum(v, s);
+  if (s.head && key >= 0 && t != 0.) atomicAdd(&fld[key], t);
+}
+
+__device__ __forceinline__ void warp_count_add(unsigned long long* ctr, bool pred) {
+  unsigned m = __ballot_sync(0xffffffffu, pred);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(ctr, (unsigned long long)__popc(m));
+}
+
+// send_bergs_to_other_pes (F:2997) seen from one berg.  Returns 0 = stays owned,
+// 1 = leaves to another rank, 2 = leaves the model (NULL_PE).  The cyclic-x wrap to
+// this same rank re-homes the berg as the receiving side's unpack does
+// (check_and_find_cell F:5973 then pos_within_cell, *_old reset F:3574-3577).
+__device__ __forceinline__ int route_berg(const DevGrid& g, const DevParams& p, double lon, double lat, int& i,
+                                          int& j, double& xi, double& yj, unsigned int* err,
+                                          unsigned long long* n_wrapped) {
+  if (i > g.iec || i < g.isc) {
+    bool east = i > g.iec;
+    bool self = east ? g.pe_E_self : g.pe_W_self;
+    bool has = east ? g.has_E : g.has_W;
+    if (self) {
+      int oi = i + (east ? -g.gni : g.gni), oj = j;
+      bool found = false;
+      if (cell_on_pe(g, oi, oj)) found = is_point_in_cell(g, p, lon, lat, oi, oj, err);
+      if (!found) found = find_cell_wide(g, p, lon, lat, &oi, &oj, err);
+      if (!found) { atomicOr(err, (unsigned)KID_DEVERR_LOST_BERG); return 2; }
+      i = oi; j = oj;
+      pos_within_cell(g, p, lon, lat, i, j, &xi, &yj, err);
+      atomicAdd(n_wrapped, 1ull);
+    } else if (has) {
+      return 1;
+    } else {
+      return 2;
+    }
+  }
+  if (j > g.jec || j < g.jsc) {
+    bool has = (j > g.jec) ? g.has_N : g.has_S;
+    return has ? 1 : 2;
+  }
+  return 0;
+}
+
+// per-berg scatter payload collected by the fused kernel
+struct Scatter { long long key; ThermoFlux fx; };
+
+template <bool FOOTLOOSE, bool DIAG>
+__device__ __forceinline__ void scatter_fluxes(const DevGrid& g, const Scatter& sc) {
+  SegInfo si = seg_info(sc.key);
+  seg_scatter(g.floating_melt, sc.key, sc.fx.floating_melt, si);
+  seg_scatter(g.calving_hflx, sc.key, sc.fx.calving_hflx, si);
+  seg_scatter(g.berg_melt, sc.key, sc.fx.berg_melt, si);
+  seg_scatter(g.bergy_src, sc.key, sc.fx.bergy_src, si);
+  seg_scatter(g.bergy_melt, sc.key, sc.fx.bergy_melt, si);
+  if (FOOTLOOSE) {
+    seg_scatter(g.fl_bits_melt, sc.key, sc.fx.fl_bits_melt, si);
+    seg_scatter(g.fl_bits_src, sc.key, sc.fx.fl_bits_src, si);
+  }
+  if (DIAG) {
+    seg_scatter(g.fl_parent_melt, sc.key, sc.fx.fl_parent_melt, si);
+    seg_scatter(g.fl_child_melt, sc.key, sc.fx.fl_child_melt, si);
+    seg_scatter(g.melt_buoy, sc.key, sc.fx.melt_buoy, si);
+    seg_scatter(g.melt_eros, sc.key, sc.fx.melt_eros, si);
+    seg_scatter(g.melt_conv, sc.key, sc.fx.melt_conv, si);
+    seg_scatter(g.melt_buoy_fl, sc.key, sc.fx.melt_buoy_fl, si);
+    seg_scatter(g.melt_eros_fl, sc.key, sc.fx.melt_eros_fl, si);
+    seg_scatter(g.melt_conv_fl, sc.key, sc.fx.melt_conv_fl, si);
+  }
+}
+
+// thermodynamics of the berg in slot s located at (i,j,xi,yj) moving with (uvel,vvel);
+// loads and stores only the columns thermodynamics touches.  Fills sc; returns the
+// TH_* outcome.
+template <bool FOOTLOOSE>
+__device__ __forceinline__ int thermo_slot(const DevGrid& g, const DevBergs& b, const DevParams& p, long long s,
+                                           uint8_t flags, int i, int j, double xi, double yj, double uvel,
+                                           double vvel, double M, double T, double W, double L, Scatter& sc,
+                                           DevCounters* cnt) {
+  Env e;
+  if (!interp_flds(g, p, i, j, xi, yj, e)) atomicOr(&cnt->error_flags, 64u);
+  size_t cidx = gidx(g, i, j);
+  double area = g.cell[cidx].area;
+  if (area == 0.) { atomicOr(&cnt->error_flags, (unsigned)KID_DEVERR_GROUNDED); return TH_KEEP; }
+  ThermoState st;
+  st.mass = M; st.thickness = T; st.width = W; st.length = L;
+  st.mass_scaling = b.f64[C_MASS_SCALING][s];
+  st.mass_of_bits = b.f64[C_MASS_OF_BITS][s];
+  st.heat_density = b.f64[C_HEAT_DENSITY][s];
+  if (FOOTLOOSE) {
+    st.mass_of_fl_bits = b.f64[C_MASS_OF_FL_BITS][s];
+    st.mass_of_fl_bergy_bits = b.f64[C_MASS_OF_FL_BERGY_BITS][s];
+    st.fl_k = b.f64[C_FL_K][s];
+  } else {
+    st.mass_of_fl_bits = 0.; st.mass_of_fl_bergy_bits = 0.; st.fl_k = 0.;
+  }
+  st.start_day = 0.; st.start_year = 0;
+  double N_bonds = 0.;
+  if (p.allow_bergs_to_roll) {
+    // N_bonds: I:2928-2944 (bond counts live with the bonded path; free bergs have none)
+    if (flags & BF_STATIC) N_bonds = p.hexagonal_icebergs ? 6.0 : 4.0;
+  }
+  double ms_in = st.mass_scaling;
+  int outcome = thermo_berg(p, e, uvel, vvel, area, N_bonds, st, sc.fx);
+  sc.key = (long long)cidx;
+  b.f64[C_MASS][s] = st.mass;
+  b.f64[C_THICKNESS][s] = st.thickness;
+  b.f64[C_WIDTH][s] = st.width;
+  b.f64[C_LENGTH][s] = st.length;
+  b.f64[C_MASS_OF_BITS][s] = st.mass_of_bits;
+  if (FOOTLOOSE) {
+    b.f64[C_MASS_OF_FL_BITS][s] = st.mass_of_fl_bits;
+    b.f64[C_MASS_OF_FL_BERGY_BITS][s] = st.mass_of_fl_bergy_bits;
+    b.f64[C_FL_K][s] = st.fl_k;
+    if (outcome == TH_BECAME_FL) {
+      b.f64[C_MASS_SCALING][s] = st.mass_scaling;
+      b.f64[C_START_DAY][s] = st.start_day;
+      b.start_year[s] = st.start_year;
+    }
+  }
+  (void)ms_in;
+  return outcome;
+}
+
+// ------------------------------------------------------------ fused step
+// One thread per slot.  MODE 0: dynamics + migration routing + thermodynamics.
+template <bool FOOTLOOSE, bool DIAG>
+__global__ void __launch_bounds__(KID_BLOCK)
+k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
+       const __grid_constant__ DevParams p, DevCounters* __restrict__ cnt, long long n_slots) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  uint8_t flags = (s < n_slots) ? b.flags[s] : (uint8_t)0;
+  bool owned = (flags & BF_ALIVE) && !(flags & BF_HALO);
+  Scatter sc;
+  sc.key = -1;
+  sc.fx.floating_melt = sc.fx.calving_hflx = sc.fx.berg_melt = sc.fx.bergy_src = sc.fx.bergy_melt = 0.;
+  sc.fx.fl_bits_melt = sc.fx.fl_bits_src = sc.fx.net_heat = 0.;
+  sc.fx.fl_parent_melt = sc.fx.fl_child_melt = sc.fx.melt_buoy = sc.fx.melt_eros = sc.fx.melt_conv = 0.;
+  sc.fx.melt_buoy_fl = sc.fx.melt_eros_fl = sc.fx.melt_conv_fl = 0.;
+  bool melted = false, became_fl = false, bounced = false, speeding = false, left = false, moved_cell = false;
+  if (owned) {
+    const double dt = p.dt, dt_2 = 0.5 * dt;
+    int i = b.ine[s], j = b.jne[s];
+    double lon = b.f64[C_LON][s], lat = b.f64[C_LAT][s];
+    double uvel = b.f64[C_UVEL][s], vvel = b.f64[C_VVEL][s];
+    double xi = b.f64[C_XI][s], yj = b.f64[C_YJ][s];
+    double M = b.f64[C_MASS][s], T = b.f64[C_THICKNESS][s], W = b.f64[C_WIDTH][s], L = b.f64[C_LENGTH][s];
+    if (!(flags & BF_STATIC)) {
+      double axn = b.f64[C_AXN][s], ayn = b.f64[C_AYN][s], bxn = b.f64[C_BXN][s], byn = b.f64[C_BYN][s];
+      // ---- verlet_stepping I:7203-7328
+      double uvel_prev = uvel - dt_2 * bxn;
+      double vvel_prev = vvel - dt_2 * byn;
+      double uvel3 = uvel + (dt_2 * axn);
+      double vvel3 = vvel + (dt_2 * ayn);
+      Env e;
+      if (!interp_flds(g, p, i, j, xi, yj, e)) atomicOr(&cnt->error_flags, 64u);
+      double ax1, ay1, un_l, vn_l;
+      IAcc ia0 = {0., 0., 0., 0., 0., 0., 0., 0.};
+      accel_core<false>(p, M, T, W, L, lat, uvel, vvel, uvel, vvel, dt, e, 1.0, ia0,
+                        [](double, double, IAcc&) {}, ax1, ay1, axn, ayn, bxn, byn, un_l, vn_l);
+      if ((p.speed_limit > 0.) || (p.speed_limit == -1.)) {   // I:2304-2323: only the ticket survives
+        double speed = sqrt(un_l * un_l + vn_l * vn_l);
+        if (speed > 0.) {
+          size_t c = gidx(g, i, j);
+          double loc_dx = fmin(0.5 * (g.dx[c] + g.dx[c - g.nid]), 0.5 * (g.dy[c] + g.dy[c - 1]));
+          double new_speed = loc_dx / dt * p.speed_limit;
+          if (new_speed < speed && p.speed_limit > 0.) speeding = true;
+        }
+      }
+      bool tang = (lat > 89.) && p.grid_is_latlon;
+      double uveln, vveln;
+      if (tang) tang_velocity(p, lon, uvel3, vvel3, ax1, ay1, dt, uveln, vveln);
+      else { uveln = uvel3 + (dt * ax1); vveln = vvel3 + (dt * ay1); }
+      if (p.override_iceberg_velocities) { uveln = p.u_override; vveln = p.v_override; }
+      uvel = uveln; vvel = vveln;      // evolve_icebergs I:7157-7162
+      // ---- update_verlet_position I:7684-7764 (uses the NEW velocity and accelerations)
+      double uvel2 = uvel + (dt_2 * axn) + (dt_2 * bxn);
+      double vvel2 = vvel + (dt_2 * ayn) + (dt_2 * byn);
+      double lonn, latn;
+      if (tang) {
+        tang_position(p, lon, lat, uvel2, vvel2, dt, lonn, latn);
+      } else {
+        double dxdl1, dydl;
+        convert_from_meters_to_grid(p, lat, dxdl1, dydl);
+        double u2 = uvel2 * dxdl1, v2 = vvel2 * dydl;
+        lonn = lon + (dt * u2); latn = lat + (dt * v2);
+      }
+      int i_old = i, j_old = j;
+      bounced = adjust_index_and_ground(g, p, lonn, latn, i, j, xi, yj, &cnt->error_flags, &cnt->warn_adjust);
+      moved_cell = (i != i_old) || (j != j_old);
+      lon = lonn; lat = latn;
+      b.f64[C_UVEL_PREV][s] = uvel_prev; b.f64[C_VVEL_PREV][s] = vvel_prev;
+      b.f64[C_AXN][s] = axn; b.f64[C_AYN][s] = ayn; b.f64[C_BXN][s] = bxn; b.f64[C_BYN][s] = byn;
+      b.f64[C_UVEL][s] = uvel; b.f64[C_VVEL][s] = vvel;
+      b.f64[C_LON][s] = lon; b.f64[C_LAT][s] = lat;
+    }
+    // ---- send_bergs_to_other_pes, F:2997
+    int route = 0;
+    if (i > g.iec || i < g.isc || j > g.jec || j < g.jsc)
+      route = route_berg(g, p, lon, lat, i, j, xi, yj, &cnt->error_flags, &cnt->n_wrapped);
+    if (!(flags & BF_STATIC) || route != 0) {
+      b.f64[C_XI][s] = xi; b.f64[C_YJ][s] = yj;
+      b.ine[s] = i; b.jne[s] = j;
+    }
+    if (route == 1) { left = true; b.flags[s] = flags | BF_LEAVER; }
+    else if (route == 2) { b.flags[s] = 0; }
+    else {
+      // ---- thermodynamics I:2844-3300 at the new position
+      int outcome = thermo_slot<FOOTLOOSE>(g, b, p, s, flags, i, j, xi, yj, uvel, vvel, M, T, W, L, sc, cnt);
+      if (outcome == TH_DELETE) { melted = true; b.flags[s] = 0; }
+      else if (outcome == TH_BECAME_FL) { melted = true; became_fl = true; }
+    }
+  }
+  scatter_fluxes<FOOTLOOSE, DIAG>(g, sc);
+  warp_count_add(&cnt->nbergs_melted, melted);
+  if (FOOTLOOSE) warp_count_add(&cnt->nbergs_calved_fl, became_fl);
+  warp_count_add(&cnt->n_bounced, bounced);
+  warp_count_add(&cnt->nspeeding, speeding);
+  warp_count_add(&cnt->n_leavers, left);
+  warp_count_add(&cnt->n_cell_moves, moved_cell);
+  // net_heat_to_ocean I:3130
+  double nh = sc.fx.net_heat;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) nh += shfl_down_d(nh, d);
+  if ((threadIdx.x & 31) == 0 && nh != 0.) atomicAdd(&cnt->net_heat_to_ocean, nh);
+}
+
+// thermodynamics alone over [s0, s1): bergs flagged BF_ARRIVAL (migration) or, with
+// all_owned, every owned berg (the split path used when interactions are on).
+template <bool FOOTLOOSE, bool DIAG>
+__global__ void __launch_bounds__(KID_BLOCK)
+k_thermo_range(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
+               const __grid_constant__ DevParams p, DevCounters* __restrict__ cnt, long long s0, long long s1,
+               int all_owned) {
+  long long s = s0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  uint8_t flags = (s < s1) ? b.flags[s] : (uint8_t)0;
+  bool todo = (flags & BF_ALIVE) && !(flags & BF_LEAVER) && (all_owned || (flags & BF_ARRIVAL));
+  if (!p.mts && !p.dem) { /* halo copies melt too, I:2890 */ } else if (flags & BF_HALO) todo = false;
+  Scatter sc;
+  sc.key = -1;
+  sc.fx.floating_melt = sc.fx.calving_hflx = sc.fx.berg_melt = sc.fx.bergy_src = sc.fx.bergy_melt = 0.;
+  sc.fx.fl_bits_melt = sc.fx.fl_bits_src = sc.fx.net_heat = 0.;
+  sc.fx.fl_parent_melt = sc.fx.fl_child_melt = sc.fx.melt_buoy = sc.fx.melt_eros = sc.fx.melt_conv = 0.;
+  sc.fx.melt_buoy_fl = sc.fx.melt_eros_fl = sc.fx.melt_conv_fl = 0.;
+  bool melted = false, became_fl = false;
+  if (todo) {
+    int i = b.ine[s], j = b.jne[s];
+    // thermodynamics covers jsc-1:jec+1 x isc-1:iec+1 only (I:2885)
+    if (i >= g.isc - 1 && i <= g.iec + 1 && j >= g.jsc - 1 && j <= g.jec + 1) {
+      double xi = b.f64[C_XI][s], yj = b.f64[C_YJ][s];
+      double uvel = b.f64[C_UVEL][s], vvel = b.f64[C_VVEL][s];
+      double M = b.f64[C_MASS][s], T = b.f64[C_THICKNESS][s], W = b.f64[C_WIDTH][s], L = b.f64[C_LENGTH][s];
+      int outcome = thermo_slot<FOOTLOOSE>(g, b, p, s, flags, i, j, xi, yj, uvel, vvel, M, T, W, L, sc, cnt);
+      if (outcome == TH_DELETE) { melted = true; flags = 0; }
+      else if (outcome == TH_BECAME_FL) { melted = true; became_fl = true; }
+    }
+    if (flags) flags &= ~BF_ARRIVAL;
+    b.flags[s] = flags;
+  }
+  scatter_fluxes<FOOTLOOSE, DIAG>(g, sc);
+  warp_count_add(&cnt->nbergs_melted, melted);
+  if (FOOTLOOSE) warp_count_add(&cnt->nbergs_calved_fl, became_fl);
+  double nh = sc.fx.net_heat;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) nh += shfl_down_d(nh, d);
+  if ((threadIdx.x & 31) == 0 && nh != 0.) atomicAdd(&cnt->net_heat_to_ocean, nh);
+}
+
+// ----------------------------------------------------------- cell-binned sort
+// key of a berg = linear index of its cell in the data domain; dead slots and
+// leavers (already packed for migration) are dropped, which compacts the store.
+__global__ void k_hist(const __grid_constant__ DevGrid g, const uint8_t* __restrict__ flags,
+                       const int32_t* __restrict__ ine, const int32_t* __restrict__ jne, long long n_slots,
+                       int32_t* __restrict__ cell_count) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  uint8_t f = flags[s];
+  if (!(f & BF_ALIVE) || (f & BF_LEAVER)) return;
+  atomicAdd(&cell_count[gidx(g, ine[s], jne[s])], 1);
+}
+
+// exclusive scan of int32 counts, three phases; 1024 items per block
+#define KID_SCAN_ITEMS 1024
+__global__ void __launch_bounds__(256) k_scan_block(const int32_t* __restrict__ in, int32_t* __restrict__ out,
+                                                    int32_t* __restrict__ block_sums, long long n) {
+  __shared__ int32_t sh[256];
+  long long base = (long long)blockIdx.x * KID_SCAN_ITEMS + threadIdx.x * 4;
+  int32_t v[4];
+  int32_t t = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { v[k] = (base + k < n) ? in[base + k] : 0; t += v[k]; }
+  sh[threadIdx.x] = t;
+  __syncthreads();
+  for (int d = 1; d < 256; d <<= 1) {
+    int32_t o = (threadIdx.x >= d) ? sh[threadIdx.x - d] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += o;
+    __syncthreads();
+  }
+  int32_t excl = sh[threadIdx.x] - t;
+  if (threadIdx.x == 255) block_sums[blockIdx.x] = sh[255];
+#pragma unroll
+  for (int k = 0; k < 4; k++) { if (base + k < n) out[base + k] = excl; excl += v[k]; }
+}
+__global__ void __launch_bounds__(1024) k_scan_sums(int32_t* __restrict__ block_sums, int nb, int32_t* total) {
+  // single block; serial over chunks of 1024
+  __shared__ int32_t sh[1024];
+  __shared__ int32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += 1024) {
+    int idx = base + threadIdx.x;
+    int32_t t = (idx < nb) ? block_sums[idx] : 0;
+    sh[threadIdx.x] = t;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+      int32_t o = (threadIdx.x >= d) ? sh[threadIdx.x - d] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += o;
+      __syncthreads();
+    }
+    if (idx < nb) block_sums[idx] = carry + sh[threadIdx.x] - t;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sh[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+__global__ void k_scan_add(int32_t* __restrict__ out, const int32_t* __restrict__ block_sums, long long n) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) out[k] += block_sums[k / KID_SCAN_ITEMS];
+}
+
+__global__ void k_rank(const __grid_constant__ DevGrid g, const uint8_t* __restrict__ flags,
+                       const int32_t* __restrict__ ine, const int32_t* __restrict__ jne, long long n_slots,
+                       const int32_t* __restrict__ cell_start, int32_t* __restrict__ cell_fill,
+                       int32_t* __restrict__ perm) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  uint8_t f = flags[s];
+  if (!(f & BF_ALIVE) || (f & BF_LEAVER)) return;
+  size_t c = gidx(g, ine[s], jne[s]);
+  int32_t pos = cell_start[c] + atomicAdd(&cell_fill[c], 1);
+  perm[pos] = (int32_t)s;
+}
+
+// makes the in-cell order deterministic and stable: ascending old slot
+__global__ void k_cell_order(const int32_t* __restrict__ cell_start, const int32_t* __restrict__ cell_count,
+                             long long ncell, int32_t* __restrict__ perm) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  int32_t n = cell_count[c];
+  if (n < 2) return;
+  int32_t* a = perm + cell_start[c];
+  for (int32_t k = 1; k < n; k++) {
+    int32_t v = a[k];
+    int32_t m = k - 1;
+    while (m >= 0 && a[m] > v) { a[m + 1] = a[m]; m--; }
+    a[m + 1] = v;
+  }
+}
+
+template <typename T, int NC>
+struct GatherArgs { const T* src[NC]; T* dst[NC]; };
+template <typename T, int NC>
+__global__ void __launch_bounds__(256) k_gather(const __grid_constant__ GatherArgs<T, NC> a,
+                                                const int32_t* __restrict__ perm, long long n) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int32_t s = perm[k];
+#pragma unroll
+  for (int c = 0; c < NC; c++)
+    if (a.src[c]) a.dst[c][k] = a.src[c][s];
+}
+
+// ------------------------------------------------------------ grid kernels
+struct FieldList { double* f[24]; int n; };
+__global__ void k_zero_fields(const __grid_constant__ FieldList fl, long long n2) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n2) return;
+  for (int q = 0; q < fl.n; q++) fl.f[q][k] = 0.;
+}
+
+// mpp_update_domains for one rank that is its own E/W neighbour: cyclic wrap of the
+// compute rows (see oracle/kid_oracle.c halo_update for the same single-rank semantics)
+__global__ void k_halo_wrap_x(const __grid_constant__ DevGrid g, const __grid_constant__ FieldList fl) {
+  int halo = g.isc - g.isd;
+  int nic = g.iec - g.isc + 1, njc = g.jec - g.jsc + 1;
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long per = (long long)2 * halo * njc;
+  if (k >= per) return;
+  int jj = (int)(k / (2 * halo)), hh = (int)(k % (2 * halo));
+  int j = g.jsc + jj;
+  int i, src;
+  if (hh < halo) { i = g.isd + hh; src = i + nic; } else { i = g.iec + 1 + (hh - halo); src = i - nic; }
+  for (int q = 0; q < fl.n; q++) fl.f[q][gidx(g, i, j)] = fl.f[q][gidx(g, src, j)];
+}
+
+// copy a caller array into the data-domain field: ring=0 -> (isc:iec,jsc:jec),
+// ring=1 -> (isc-1:iec+1,jsc-1:jec+1); optional multiply by msk
+__global__ void k_copy_in(const __grid_constant__ DevGrid g, const double* __restrict__ src, double* __restrict__ dst,
+                          int ring, int mul_msk, double add) {
+  int ni = g.iec - g.isc + 1 + 2 * ring, nj = g.jec - g.jsc + 1 + 2 * ring;
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= (long long)ni * nj) return;
+  int ii = (int)(k % ni), jj = (int)(k / ni);
+  size_t c = gidx(g, g.isc - ring + ii, g.jsc - ring + jj);
+  double v = src ? src[k] + add : add;
+  if (mul_msk) v = v * g.msk[c];
+  dst[c] = v;
+}
+
+// I:5221, I:5227: whole data domain
+__global__ void k_calving_units(const __grid_constant__ DevGrid g, long long n2) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n2) return;
+  g.calving[k] = g.calving[k] * g.msk[k] * g.area[k];
+  g.calving_hflx[k] = g.calving_hflx[k] * g.msk[k];
+}
+
+// C-grid velocities to B-grid corners, I:5244-5259 ((nic+2)-sized inputs: offsets 0)
+__global__ void k_cgrid_vel(const __grid_constant__ DevGrid g, const double* __restrict__ uo, const double* __restrict__ vo,
+                            const double* __restrict__ ui, const double* __restrict__ vi) {
+  int ni = g.iec - g.isc + 2, nj = g.jec - g.jsc + 2;   // isc-1..iec, jsc-1..jec
+  int nin = g.iec - g.isc + 3;
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= (long long)ni * nj) return;
+  int ii = (int)(k % ni), jj = (int)(k / ni);
+  int i = g.isc - 1 + ii, j = g.jsc - 1 + jj;
+  size_t c = gidx(g, i, j);
+  double mask = fmin(fmin(g.msk[c], g.msk[c + 1]), fmin(g.msk[c + g.nid], g.msk[c + g.nid + 1]));
+  size_t a = (size_t)ii + (size_t)jj * nin;
+  g.uo[c] = mask * 0.5 * (uo[a] + uo[a + nin]);
+  g.ui[c] = mask * 0.5 * (ui[a] + ui[a + nin]);
+  g.vo[c] = mask * 0.5 * (vo[a] + vo[a + 1]);
+  g.vi[c] = mask * 0.5 * (vi[a] + vi[a + 1]);
+}
+
+// wind stress from C-grid / A-grid temporaries (data-domain arrays ut, vt), I:5268-5313
+__global__ void k_stress_to_corners(const __grid_constant__ DevGrid g, const double* __restrict__ ut,
+                                    const double* __restrict__ vt, int agrid) {
+  int ni = g.iec - g.isc + 2, nj = g.jec - g.jsc + 2;
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= (long long)ni * nj) return;
+  int i = g.isc - 1 + (int)(k % ni), j = g.jsc - 1 + (int)(k / ni);
+  size_t c = gidx(g, i, j), nid = g.nid;
+  double mask = fmin(fmin(g.msk[c], g.msk[c + 1]), fmin(g.msk[c + nid], g.msk[c + nid + 1]));
+  if (!agrid) {
+    g.ua[c] = mask * 0.5 * (ut[c] + ut[c + nid]);
+    g.va[c] = mask * 0.5 * (vt[c] + vt[c + 1]);
+  } else {
+    g.ua[c] = mask * 0.25 * ((ut[c] + ut[c + nid + 1]) + (ut[c + 1] + ut[c + nid]));
+    g.va[c] = mask * 0.25 * ((vt[c] + vt[c + nid + 1]) + (vt[c + 1] + vt[c + nid]));
+  }
+}
+
+// invert_tau_for_du I:8272-8296
+__global__ void k_invert_tau(const __grid_constant__ DevGrid g, long long n2) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n2) return;
+  const double cd = 0.0015;
+  double u = g.ua[k], v = g.va[k];
+  double tau2 = u * u + v * v;
+  double cddvmod = sqrt(cd * sqrt(tau2));
+  if (cddvmod != 0.) { g.ua[k] = u / cddvmod; g.va[k] = v / cddvmod; }
+  else { g.ua[k] = 0.; g.va[k] = 0.; }
+}
+
+// max over the compute domain of sst*msk (I:5340) and "any calving != 0"; one block
+// per 256 cells, result via atomics on an ordered-int encoding
+__device__ __forceinline__ unsigned long long enc_f64(double v) {
+  unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double dec_f64(unsigned long long u) {
+  unsigned long long r = (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double((long long)r);
+#else
+  double d; memcpy(&d, &r, 8); return d;
+#endif
+}
+__global__ void k_sst_max(const __grid_constant__ DevGrid g, const double* __restrict__ sst,
+                          const double* __restrict__ calving, unsigned long long* __restrict__ out /*[2]*/) {
+  int ni = g.iec - g.isc + 1, nj = g.jec - g.jsc + 1;
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double v = -1e300; int anyc = 0;
+  if (k < (long long)ni * nj) {
+    size_t c = gidx(g, g.isc + (int)(k % ni), g.jsc + (int)(k / ni));
+    double t = sst[k] * g.msk[c];
+    if (t > v) v = t;
+    if (calving && calving[k] != 0.) anyc = 1;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) { v = fmax(v, shfl_down_d(v, d)); anyc |= __shfl_down_sync(0xffffffffu, anyc, d); }
+  if ((threadIdx.x & 31) == 0) { atomicMax(&out[0], enc_f64(v)); if (anyc) atomicOr(&out[1], 1ull); }
+}
+__global__ void k_sst_in(const __grid_constant__ DevGrid g, const double* __restrict__ sst,
+                         const unsigned long long* __restrict__ mx) {
+  int ni = g.iec - g.isc + 1, nj = g.jec - g.jsc + 1;
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= (long long)ni * nj) return;
+  size_t c = gidx(g, g.isc + (int)(k % ni), g.jsc + (int)(k / ni));
+  double max_SST = dec_f64(mx[0]);
+  g.sst[c] = (max_SST > 120.0) ? sst[k] - 273.15 : sst[k];
+}
+
+// I:5364-5383
+__global__ void k_scrub(const __grid_constant__ DevGrid g, long long n2) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n2) return;
+  double* f[10] = {g.ua, g.va, g.uo, g.vo, g.ui, g.vi, g.sst, g.sss, g.cn, g.hi};
+  bool land = g.msk[k] < 0.5;
+#pragma unroll
+  for (int q = 0; q < 10; q++) {
+    double v = f[q][k];
+    if (land) v = 0.0;
+    if (v != v) v = 0.;
+    f[q][k] = v;
+  }
+}
+
+__global__ void k_pack_lonlat(const __grid_constant__ DevGrid g, long long n2) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n2) return;
+  LonLat r; r.lon = g.lon[k]; r.lat = g.lat[k];
+  g.lonlat[k] = r;
+}
+
+// corner + cell records from the ingested fields; ddx_ssh/ddy_ssh I:4903-4926
+__global__ void k_pack_forcing(const __grid_constant__ DevGrid g, long long n2) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n2) return;
+  CornerRec r;
+  r.uo = g.uo[k]; r.vo = g.vo[k]; r.ui = g.ui[k]; r.vi = g.vi[k]; r.ua = g.ua[k]; r.va = g.va[k];
+  r.cosr = g.cosr[k]; r.sinr = g.sinr[k];
+  g.corner[k] = r;
+  int i = g.isd + (int)(k % g.nid), j = g.jsd + (int)(k / g.nid);
+  size_t nid = g.nid;
+  CellRec c;
+  c.sst = g.sst[k]; c.sss = g.sss[k]; c.cn = g.cn[k]; c.hi = g.hi[k];
+  c.od = g.ocean_depth[k] + g.ssh[k];
+  c.area = g.area[k];
+  double ddx = 0., ddy = 0.;
+  if (i + 1 <= g.ied && j - 1 >= g.jsd) {
+    double dxp = 0.5 * (g.dx[k + 1] + g.dx[k + 1 - nid]);
+    double dx0 = 0.5 * (g.dx[k] + g.dx[k - nid]);
+    ddx = 2. * (g.ssh[k + 1] - g.ssh[k]) / (dx0 + dxp) * g.msk[k + 1] * g.msk[k];
+  }
+  if (j + 1 <= g.jed && i - 1 >= g.isd) {
+    double dyp = 0.5 * (g.dy[k + nid] + g.dy[k - 1 + nid]);
+    double dy0 = 0.5 * (g.dy[k] + g.dy[k - 1]);
+    ddy = 2. * (g.ssh[k + nid] - g.ssh[k]) / (dy0 + dyp) * g.msk[k + nid] * g.msk[k];
+  }
+  c.ddx = ddx; c.ddy = ddy;
+  g.cell[k] = c;
+}
+
+// I:5654-5679: what icebergs_run hands back
+__global__ void k_outputs(const __grid_constant__ DevGrid g, double* __restrict__ calving_out,
+                          double* __restrict__ hflx_out) {
+  int ni = g.iec - g.isc + 1, nj = g.jec - g.jsc + 1;
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= (long long)ni * nj) return;
+  size_t c = gidx(g, g.isc + (int)(k % ni), g.jsc + (int)(k / ni));
+  double a = g.area[c];
+  calving_out[k] = (a > 0.) ? g.calving[c] / a + g.floating_melt[c] : 0.;
+  hflx_out[k] = g.calving_hflx[c];
+}
+
+// ------------------------------------------------------------- calving
+struct CalvingTables {
+  double initial_mass_s[KID_NCLASSES], distribution_s[KID_NCLASSES], mass_scaling_s[KID_NCLASSES],
+      initial_thickness_s[KID_NCLASSES];
+  double initial_mass_n[KID_NCLASSES], distribution_n[KID_NCLASSES], mass_scaling_n[KID_NCLASSES],
+      initial_thickness_n[KID_NCLASSES];
+  double LoW_ratio, rho_bergs;
+};
+
+// accumulate_calving I:6153-6222 (first_call: I:6175-6188)
+__global__ void k_accumulate_calving(const __grid_constant__ DevGrid g, const __grid_constant__ CalvingTables t,
+                                     double dt, int first_call, long long n2) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n2) return;
+  int i = g.isd + (int)(k % g.nid), j = g.jsd + (int)(k / g.nid);
+  bool south = g.lat[k] < 0.;
+  double calving = g.calving[k];
+  if (first_call && i >= g.isc && i <= g.iec && j >= g.jsc && j <= g.jec && calving != 0.) {
+    double s = 0.;
+    for (int q = 0; q < KID_NCLASSES; q++) s += g.stored_ice[k + n2 * q];
+    g.stored_heat[k] = s * g.calving_hflx[k] * g.area[k] / calving;
+  }
+  double rd_s = 1., rd_n = 1.;
+  for (int q = 0; q < KID_NCLASSES; q++) {
+    double dist = south ? t.distribution_s[q] : t.distribution_n[q];
+    g.stored_ice[k + n2 * q] = g.stored_ice[k + n2 * q] + dt * calving * dist;
+    rd_s = rd_s - t.distribution_s[q];
+    rd_n = rd_n - t.distribution_n[q];
+  }
+  double rd = south ? rd_s : rd_n;
+  g.calving[k] = calving * rd;
+  double hf = g.calving_hflx[k];
+  double tmp = dt * hf * g.area[k] * (1. - rd);
+  g.tmp[k] = tmp;
+  g.stored_heat[k] = g.stored_heat[k] + tmp;
+  g.calving_hflx[k] = hf * rd;
+}
+
+// calve_icebergs I:6225-6402: one thread per compute cell walks the classes in the
+// reference order, so ids (per-cell counter, F:4165-4177) and start_day offsets
+// (I:6381) are the reference's.
+__global__ void k_calve(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
+                        const __grid_constant__ DevParams p, const __grid_constant__ CalvingTables t,
+                        DevCounters* __restrict__ cnt, long long n2) {
+  int ni = g.iec - g.isc + 1, nj = g.jec - g.jsc + 1;
+  long long kk = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (kk >= (long long)ni * nj) return;
+  int i = g.isc + (int)(kk % ni), j = g.jsc + (int)(kk / ni);
+  size_t c = gidx(g, i, j);
+  bool south = g.lat[c] < 0.;
+  double calved_sum = 0., heat_sum = 0.;
+  unsigned long long ncalved = 0;
+  for (int k = 0; k < KID_NCLASSES; k++) {
+    g.real_calving[c + n2 * k] = 0.;
+    double initial_mass = south ? t.initial_mass_s[k] : t.initial_mass_n[k];
+    double mass_scaling = south ? t.mass_scaling_s[k] : t.mass_scaling_n[k];
+    double initial_thickness = south ? t.initial_thickness_s[k] : t.initial_thickness_n[k];
+    double* si = &g.stored_ice[c + n2 * k];
+    if (!(*si >= initial_mass * mass_scaling)) continue;
+    double initial_width = sqrt(initial_mass / (t.LoW_ratio * t.rho_bergs * initial_thickness));   // F:1540
+    double initial_length = t.LoW_ratio * initial_width;                                              // F:1541
+    double ddt = 0.;
+    while (*si >= initial_mass * mass_scaling) {
+      Quad q = load_quad(g, i, j);
+      double lon = 0.25 * ((q.x3 + q.x1) + (q.x4 + q.x2));
+      double lat = 0.25 * ((q.y3 + q.y1) + (q.y4 + q.y2));
+      double xi, yj;
+      bool lret = pos_within_cell(g, p, lon, lat, i, j, &xi, &yj, &cnt->error_flags);
+      if (!lret) { atomicOr(&cnt->error_flags, 128u); return; }
+      unsigned long long s = atomicAdd(&cnt->n_slots, 1ull);
+      if ((long long)s >= b.capacity) { atomicOr(&cnt->error_flags, (unsigned)KID_DEVERR_CAPACITY); return; }
+      for (int col = 0; col < C_NCOLS; col++) if (b.f64[col]) b.f64[col][s] = 0.;
+      b.f64[C_LON][s] = lon; b.f64[C_LAT][s] = lat;
+      b.f64[C_XI][s] = xi; b.f64[C_YJ][s] = yj;
+      if (b.f64[C_LON_OLD]) { b.f64[C_LON_OLD][s] = lon; b.f64[C_LAT_OLD][s] = lat; }
+      b.f64[C_MASS][s] = initial_mass; b.f64[C_THICKNESS][s] = initial_thickness;
+      b.f64[C_WIDTH][s] = initial_width; b.f64[C_LENGTH][s] = initial_length;
+      b.f64[C_START_LON][s] = lon; b.f64[C_START_LAT][s] = lat;
+      b.f64[C_START_DAY][s] = p.current_yearday + ddt / 86400.;
+      b.f64[C_START_MASS][s] = initial_mass;
+      b.f64[C_MASS_SCALING][s] = mass_scaling;
+      double heat_density = g.stored_heat[c] / (*si);
+      b.f64[C_HEAT_DENSITY][s] = heat_density;
+      b.start_year[s] = p.current_year;
+      b.ine[s] = i; b.jne[s] = j;
+      int32_t counter = g.iceberg_counter_grd[c] + 1;            // generate_id F:4165-4179
+      g.iceberg_counter_grd[c] = counter;
+      b.id[s] = (int64_t)counter * ((int64_t)1 << 32) + (int64_t)(i + g.gni * (j - 1));
+      b.halo_code[s] = 0;
+      b.flags[s] = BF_ALIVE;
+      double calved_to_berg = initial_mass * mass_scaling;
+      double heat_to_berg = calved_to_berg * heat_density;
+      g.stored_heat[c] = g.stored_heat[c] - heat_to_berg;
+      heat_sum += heat_to_berg;
+      *si = *si - calved_to_berg;
+      calved_sum += calved_to_berg;
+      g.real_calving[c + n2 * k] += calved_to_berg / p.dt;
+      ddt = ddt - p.dt * 2. / 17.;
+      ncalved++;
+    }
+  }
+  if (ncalved) {
+    atomicAdd(&cnt->nbergs_calved, ncalved);
+    atomicAdd(&cnt->net_calving_to_bergs, calved_sum);
+    atomicAdd(&cnt->net_heat_to_bergs, heat_sum);
+  }
+}
+
+// ------------------------------------------------------- restart ingest
+// read_restart_bergs (fmsio:606-975): locate the cell unless ine/jne came with the
+// file, keep only bergs of this rank's compute domain, recompute xi,yj, *_old = current.
+__global__ void k_locate(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
+                         const __grid_constant__ DevParams p, DevCounters* __restrict__ cnt, long long s0,
+                         long long s1, int have_ij) {
+  long long s = s0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= s1) return;
+  double lon = b.f64[C_LON][s], lat = b.f64[C_LAT][s];
+  int i, j;
+  bool found;
+  if (have_ij) { i = b.ine[s]; j = b.jne[s]; found = cell_on_pe(g, i, j); }
+  else found = find_cell(g, p, lon, lat, &i, &j, &cnt->error_flags);
+  if (!found || i < g.isc || i > g.iec || j < g.jsc || j > g.jec) { b.flags[s] = 0; return; }
+  double xi, yj;
+  pos_within_cell(g, p, lon, lat, i, j, &xi, &yj, &cnt->error_flags);
+  b.ine[s] = i; b.jne[s] = j;
+  b.f64[C_XI][s] = xi; b.f64[C_YJ][s] = yj;
+}
+
+// ids for restart files that carry none (legacy iceberg_num): generate_id in file
+// order (fmsio:841-845) -- inherently serial, one thread
+__global__ void k_generate_ids(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b, long long s0,
+                               long long s1) {
+  if (blockIdx.x || threadIdx.x) return;
+  for (long long s = s0; s < s1; s++) {
+    if (!(b.flags[s] & BF_ALIVE)) continue;
+    int i = b.ine[s], j = b.jne[s];
+    size_t c = gidx(g, i, j);
+    int32_t counter = g.iceberg_counter_grd[c] + 1;
+    g.iceberg_counter_grd[c] = counter;
+    b.id[s] = (int64_t)counter * ((int64_t)1 << 32) + (int64_t)(i + g.gni * (j - 1));
+  }
+}
+
+__global__ void k_count_alive(const uint8_t* __restrict__ flags, long long n_slots, int include_halo,
+                              unsigned long long* __restrict__ out) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool a = false;
+  if (s < n_slots) { uint8_t f = flags[s]; a = (f & BF_ALIVE) && !(f & BF_LEAVER) && (include_halo || !(f & BF_HALO)); }
+  warp_count_add(out, a);
+}
+
+}  // namespace kid

@@ -1,0 +1,156 @@
+"""Deterministic synthetic workload of BASELINE.md / SURVEY.md 8(d): a regular 1/4-degree
+lat-lon grid with analytic land mask and forcing, and seeded bergs.  Pure numpy input
+generation (no files); used by tests/ and bench.py.  Nothing here is on the hot path.
+
+All 2-D arrays are the reference's column-major (i, j) arrays = numpy shape (nj, ni).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+REARTH = 6.36e6  # F:44
+SEED = 20240521
+
+# F:787-790 (southern-hemisphere table; the reference default for both hemispheres' geometry
+# is taken per hemisphere by calve_icebergs, here bergs are seeded from the southern table)
+INITIAL_MASS = np.array([8.8e7, 4.1e8, 3.3e9, 1.8e10, 3.8e10, 7.5e10, 1.2e11, 2.2e11, 3.9e11, 7.4e11])
+MASS_SCALING = np.array([2000, 200, 50, 20, 10, 5, 2, 1, 1, 1], dtype=np.float64)
+INITIAL_THICKNESS = np.array([40., 67., 133., 175., 250., 250., 250., 250., 250., 250.])
+LOW_RATIO = 1.5
+RHO_BERGS = 850.
+
+
+def splitmix64(x: np.ndarray) -> np.ndarray:
+    """Counter-based RNG: splitmix64 finaliser of (seed + counter)."""
+    with np.errstate(over="ignore"):
+        z = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def u01(stream: int, idx: np.ndarray, seed: int = SEED) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        key = np.uint64(seed) * np.uint64(0x100000001B3) + np.uint64(stream) * np.uint64(0xD6E8FEB86659FD93)
+        r = splitmix64(idx.astype(np.uint64) * np.uint64(0x2545F4914F6CDD1D) + key)
+    return (r >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+class Grid:
+    """Regular lat-lon grid tile.  Cell (i,j) (global, 1-based) has its NE corner at
+    lon = i*dlon, lat = -90 + j*dlat (F:6325-6332)."""
+
+    def __init__(self, gni=1440, gnj=720, isc=1, iec=None, jsc=1, jec=None):
+        self.gni, self.gnj = gni, gnj
+        self.isc, self.iec = isc, gni if iec is None else iec
+        self.jsc, self.jec = jsc, gnj if jec is None else jec
+        self.dlon, self.dlat = 360.0 / gni, 180.0 / gnj
+
+    # index ranges
+    def _ij(self, ring):
+        i = np.arange(self.isc - ring, self.iec + ring + 1)
+        j = np.arange(self.jsc - ring, self.jec + ring + 1)
+        return np.meshgrid(i, j)  # (nj, ni)
+
+    def corner_lonlat(self, ring=0):
+        i, j = self._ij(ring)
+        return i * self.dlon, -90.0 + j * self.dlat
+
+    def centre_lonlat(self, ring=0):
+        lon, lat = self.corner_lonlat(ring)
+        return lon - 0.5 * self.dlon, lat - 0.5 * self.dlat
+
+    def wet(self, ring=1):
+        lonc, latc = self.centre_lonlat(ring)
+        lonm = np.mod(lonc, 360.0)
+        w = (np.abs(latc) < 80.0)
+        w &= ~((lonm > 20.0) & (lonm < 60.0) & (latc > -40.0) & (latc < 40.0))
+        w &= ~((lonm > 250.0) & (lonm < 300.0) & (latc > -50.0) & (latc < 60.0))
+        return w.astype(np.float64)
+
+    def init_args(self):
+        """Arguments of icebergs_init (I:92-117) for this tile."""
+        lon, lat = self.corner_lonlat(0)
+        lonr, latr = self.corner_lonlat(1)
+        _, latc = self.centre_lonlat(0)
+        rad = np.pi / 180.0
+        dx = REARTH * np.cos(latr * rad) * (self.dlon * rad)      # length of the cell's northern edge
+        dy = np.full_like(dx, REARTH * self.dlat * rad)
+        area = REARTH * np.cos(latc * rad) * (self.dlon * rad) * (REARTH * self.dlat * rad)
+        return dict(ice_lon=lon, ice_lat=lat, ice_wet=self.wet(1), ice_dx=np.abs(dx), ice_dy=dy,
+                    ice_area=np.abs(area), cos_rot=np.ones_like(dx), sin_rot=np.zeros_like(dx),
+                    ocean_depth=np.full_like(lon, 4000.0))
+
+    def forcing(self):
+        """Arguments of icebergs_run (I:5074-5096); winds are velocities (tau_is_velocity=T)."""
+        rad = np.pi / 180.0
+        lam_r, phi_r = [a * rad for a in self.corner_lonlat(1)]
+        lam_c, phi_c = [a * rad for a in self.corner_lonlat(0)]
+        lamc_r, phic_r = [a * rad for a in self.centre_lonlat(1)]
+        _, phic_deg = self.centre_lonlat(0)
+        _, phir_deg = self.centre_lonlat(1)
+        uo = 0.3 * np.cos(phi_r) * np.sin(2 * lam_r)
+        vo = 0.2 * np.sin(lam_r) * np.cos(3 * phi_r)
+        f = dict(uo=uo, vo=vo, ui=0.5 * uo, vi=0.5 * vo,
+                 tauxa=10.0 * np.cos(2 * phi_c), tauya=3.0 * np.sin(3 * lam_c),
+                 ssh=0.5 * np.sin(2 * lamc_r) * np.cos(3 * phic_r),
+                 sst=-1.5 + 4.0 * np.cos(phic_deg * rad) ** 2,
+                 sss=np.full_like(lam_c, 34.0))
+        cn = np.clip((np.abs(phir_deg) - 55.0) / 20.0, 0.0, 1.0)
+        f["cn"] = cn
+        f["hi"] = 1.5 * cn
+        f["calving"] = np.zeros_like(lam_c)
+        f["calving_hflx"] = np.zeros_like(lam_c)
+        return {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in f.items()}
+
+    def seed_bergs(self, n, stream=0, seed=SEED):
+        """n bergs uniformly over this tile's wet cells: (xi,yj) in U(.05,.95)^2,
+        class U{1..10}, LoW geometry (F:1540-1541), zero velocity, ids as generate_id F:4165-4177."""
+        wet = self.wet(0) > 0.5
+        jj, ii = np.nonzero(wet)
+        ncell = len(ii)
+        k = np.arange(n, dtype=np.uint64)
+        base = np.uint64(stream) << np.uint64(40)
+        c = np.minimum((u01(1, k + base, seed) * ncell).astype(np.int64), ncell - 1)
+        i = (ii[c] + self.isc).astype(np.int32)
+        j = (jj[c] + self.jsc).astype(np.int32)
+        xi = 0.05 + 0.9 * u01(2, k + base, seed)
+        yj = 0.05 + 0.9 * u01(3, k + base, seed)
+        cls = np.minimum((u01(4, k + base, seed) * 10).astype(np.int64), 9)
+        lon = (i - 1 + xi) * self.dlon
+        lat = -90.0 + (j - 1 + yj) * self.dlat
+        mass = INITIAL_MASS[cls]
+        thick = INITIAL_THICKNESS[cls]
+        width = np.sqrt(mass / (LOW_RATIO * RHO_BERGS * thick))
+        length = LOW_RATIO * width
+        # per-cell counter in generation order -> id = counter*2^32 + (i + gni*(j-1))
+        cell = (j.astype(np.int64) - 1) * self.gni + (i.astype(np.int64) - 1)
+        order = np.argsort(cell, kind="stable")
+        sc = cell[order]
+        first = np.r_[0, np.nonzero(np.diff(sc))[0] + 1]
+        start = np.repeat(first, np.diff(np.r_[first, n]))
+        counter = np.empty(n, dtype=np.int64)
+        counter[order] = np.arange(n) - start + 1
+        ident = counter * (1 << 32) + (i.astype(np.int64) + self.gni * (j.astype(np.int64) - 1))
+        z = np.zeros(n)
+        return dict(lon=lon, lat=lat, uvel=z.copy(), vvel=z.copy(), mass=mass.copy(), thickness=thick.copy(),
+                    width=width, length=length, axn=z.copy(), ayn=z.copy(), bxn=z.copy(), byn=z.copy(),
+                    start_lon=lon.copy(), start_lat=lat.copy(), start_day=(cls + 1) / 17.0,
+                    start_mass=mass.copy(), mass_scaling=MASS_SCALING[cls].copy(), mass_of_bits=z.copy(),
+                    heat_density=z.copy(), start_year=np.ones(n, dtype=np.int32), ine=i, jne=j,
+                    id=ident.astype(np.int64)), counter_grid(self, cell, n)
+
+
+def counter_grid(grid: Grid, cell, n):
+    """iceberg_counter_grd consistent with the seeded ids (global cell -> count)."""
+    cnt = np.bincount(cell, minlength=grid.gni * grid.gnj).astype(np.int32)
+    return cnt.reshape(grid.gnj, grid.gni)
+
+
+def workload_params(default_params, **over):
+    """Physics of the synthetic case: namelist defaults except Verlet stepping, bergy bits
+    on, wind passed as velocity (BASELINE.md 'Physics')."""
+    kw = dict(runge_not_verlet=0, bergy_bit_erosion_fraction=0.1, tau_is_velocity=1, old_bug_bilin=1,
+              Rearth=REARTH)
+    kw.update(over)
+    return default_params(**kw)

@@ -363,6 +363,23 @@ int32_t kid_synchronize(kid_t* h);
 
 int32_t kid_end(kid_t** h);
 
+/* ----------------------------------------------------------------------------
+ * Multi-rank plumbing (replaces mpp_send/mpp_recv of send_bergs_to_other_pes,
+ * F:3053-3194).  The Fortran shim has MPI but no NCCL binding, so the library
+ * wraps the three NCCL calls it needs: rank 0 calls kid_nccl_unique_id, the
+ * shim broadcasts the 128 bytes (MPI_Bcast / mpp_broadcast), every rank calls
+ * kid_nccl_init and stores the result in KidDomain.nccl_comm.  NCCL is loaded
+ * at run time (dlopen of libnccl.so.2): single-rank use needs no NCCL at all.
+ * -------------------------------------------------------------------------- */
+#define KID_NCCL_UNIQUE_ID_BYTES 128
+int32_t kid_nccl_unique_id(char* out, int32_t nbytes);
+int32_t kid_nccl_init(void** comm, const char* id, int32_t nbytes, int32_t nranks, int32_t rank,
+                      int32_t device);
+int32_t kid_nccl_destroy(void* comm);
+/* fp64 words one migrating berg occupies in the exchange buffer (reference: buffer_width F:21) */
+int32_t kid_pack_width(void);
+
+
 const char* kid_last_error(const kid_t* h);   /* h may be NULL: last init error */
 const char* kid_version(void);
 

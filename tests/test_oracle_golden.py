@@ -1,0 +1,100 @@
+"""Pins the CPU oracle against the reference's own portable known answers:
+bilin corner exactness (icebergs_framework.F90:7313-7316), the 64-bit id round trip
+(F:7319-7325), yearday (F:4431-4441), and structural invariants of the restated step."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import kid_oracle_py as O
+from common import Case, run_oracle
+from icebergs_b200 import _cdefs as D
+
+
+def test_id_round_trip_F7319():
+    L = O.lib()
+    i, c1 = 1440 * 1080, 2 ** 30 + 2 ** 4 + 1
+    ident = L.oracle_id_from_2_ints(c1, i)
+    assert ident == c1 * 2 ** 32 + i
+    c2, j = C.c_int32(), C.c_int32()
+    L.oracle_split_id(ident, C.byref(c2), C.byref(j))
+    assert (c2.value, j.value) == (c1, i)
+
+
+def test_yearday_F4431():
+    L = O.lib()
+    assert L.oracle_yearday(1, 1, 0, 0, 0) == 0.0
+    assert L.oracle_yearday(3, 2, 12, 0, 0) == 2 * 31 + 1 + 0.5
+
+
+@pytest.mark.parametrize("old_bug", [0])
+def test_bilin_corner_exactness_F7313(old_bug):
+    # unit_tests() runs with the corrected bilin (every shipped namelist sets old_bug_bilin=.false.)
+    case = Case(48, 24, 0, old_bug_bilin=old_bug)
+    o = case.make_oracle()
+    L = O.lib()
+    d = case.domain()
+    lon, lat = o.grid_field(D.KID_FLD_LON), o.grid_field(D.KID_FLD_LAT)
+    at = lambda f, i, j: f[j - d.jsd, i - d.isd]
+    i, j = d.isc, d.jsc
+    assert L.oracle_bilin(o._h, D.KID_FLD_LON, i, j, 0.0, 1.0) == at(lon, i - 1, j)
+    assert L.oracle_bilin(o._h, D.KID_FLD_LON, i, j, 1.0, 1.0) == at(lon, i, j)
+    assert L.oracle_bilin(o._h, D.KID_FLD_LAT, i, j, 1.0, 0.0) == at(lat, i, j - 1)
+    assert L.oracle_bilin(o._h, D.KID_FLD_LAT, i, j, 1.0, 1.0) == at(lat, i, j)
+
+
+def test_apply_modulo_around_point_F6558():
+    L = O.lib()
+    f = L.oracle_apply_modulo_around_point
+    assert f(370.0, 0.0, 360.0) == 10.0
+    assert f(-10.0, 350.0, 360.0) == 350.0
+    assert f(5.0, 5.0, -1.0) == 5.0          # non-periodic: identity
+    for x, y in [(0.1, 359.9), (359.9, 0.1), (720.5, 10.0)]:
+        r = f(x, y, 360.0)
+        assert abs(r - y) <= 180.0 and abs(((r - x) / 360.0) - round((r - x) / 360.0)) < 1e-12
+
+
+def test_cell_membership_edges_F6199():
+    # The half-valued sentinels at F:6203-6206 make two of the four edges part of the cell.  The
+    # comment above them says "South and East", but with the counter-clockwise corner order the
+    # cross products l0..l3 are all NEGATIVE inside, so the edges whose zero maps to a negative
+    # sentinel (p0 = S, p3 = W) are the inclusive ones.  The code is followed, not the comment.
+    case = Case(48, 24, 0, old_bug_bilin=0)
+    o = case.make_oracle()
+    L = O.lib()
+    i, j = 10, 12
+    dlon, dlat = 360.0 / 48, 180.0 / 24
+    x0, x1, y0, y1 = (i - 1) * dlon, i * dlon, -90 + (j - 1) * dlat, -90 + j * dlat
+    inside = lambda x, y: L.oracle_is_point_in_cell(o._h, x, y, i, j)
+    assert inside(0.5 * (x0 + x1), 0.5 * (y0 + y1))
+    assert inside(0.5 * (x0 + x1), y0) and not inside(0.5 * (x0 + x1), y1)
+    assert inside(x0, 0.5 * (y0 + y1)) and not inside(x1, 0.5 * (y0 + y1))
+
+
+def test_step_conserves_count_and_ids():
+    case = Case(96, 48, 3000)
+    o = case.make_oracle()
+    before = np.sort(o.get_bergs(["id"])["id"])
+    run_oracle(o, case)
+    after = o.get_bergs(["id", "ine", "jne", "lon", "lat"])
+    assert np.array_equal(np.sort(after["id"]), before)
+    # every berg sits in the cell that contains it
+    L = O.lib()
+    for k in range(0, len(after["id"]), 37):
+        assert L.oracle_is_point_in_cell(o._h, after["lon"][k], after["lat"][k], int(after["ine"][k]), int(after["jne"][k]))
+
+
+def test_melt_budget_closes():
+    # mass lost by the bergs (x mass_scaling) = what the grid received, I:3116-3133
+    case = Case(96, 48, 2000)
+    o = case.make_oracle()
+    names = ["id", "mass", "mass_of_bits", "mass_scaling"]
+    b0 = o.get_bergs(names)
+    run_oracle(o, case)
+    b1 = o.get_bergs(names)
+    o0 = np.argsort(b0["id"]); o1 = np.argsort(b1["id"])
+    lost = np.sum(((b0["mass"] + b0["mass_of_bits"])[o0] - (b1["mass"] + b1["mass_of_bits"])[o1]) * b0["mass_scaling"][o0])
+    fm = o.grid_field(D.KID_FLD_FLOATING_MELT)
+    area = o.grid_field(D.KID_FLD_AREA)
+    assert lost > 0
+    assert abs(np.sum(fm * area) * case.dt - lost) / lost < 1e-9
