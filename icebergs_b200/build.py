@@ -13,9 +13,8 @@ DEPS.append(os.path.join(os.path.dirname(_HERE), "include", "kid_b200.h"))
 OUT = os.path.join(_HERE, "lib", "libkid_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              # FMA contraction off: the arithmetic is the plain IEEE sequence the reference's
-              # source spells, so value-dependent integer decisions (cell index, bounce, deletion)
-              # follow the CPU path (DESIGN.md "floating point")
+              # no implicit FMA contraction: expressions whose exact cancellation the reference relies on keep
+              # the plain IEEE sequence; interpolation and momentum sums use explicit fma() (kid_physics.cuh)
               "-fmad=false",
               "-shared", "-Xcompiler", "-fPIC", "-ldl"]
 

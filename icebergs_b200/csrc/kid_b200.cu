@@ -229,6 +229,14 @@ static void fill_dev_params(kid_t* h) {
   q.footloose = p.footloose; q.mts = p.mts; q.dem = p.dem;
   q.contact_cells_lon = p.contact_cells_lon; q.contact_cells_lat = p.contact_cells_lat; q.max_bonds = p.max_bonds;
   q.passive_mode = p.passive_mode;
+  q.rdt = 1. / p.dt;
+  q.rho_ratio = p.rho_bergs / KID_RHO_SEAWATER;
+  q.r_rho_bergs = 1. / p.rho_bergs;
+  q.r_h2ig = (p.h_to_init_grounding > 0.) ? 1. / p.h_to_init_grounding : 0.;
+  q.rpow40_02 = 1. / pow(40., 0.2);
+  q.dlat_dy = (180. / p.pi) / p.Rearth;
+  q.r180_pi = 180. / p.pi;
+  q.f_cori_plane = (2. * p.omega) * sin((p.pi / 180.) * p.lat_ref);
 }
 
 // Fortran MODULO / apply_modulo_around_point on the host, for the init-time

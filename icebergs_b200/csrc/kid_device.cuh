@@ -44,6 +44,15 @@ struct DevParams {
   double spring_coef, contact_spring_coef, contact_distance, radial_damping_coef, tangental_damping_coef;
   double fl_youngs;
   double current_yearday;
+  // host-precomputed constants of the step (same libm as the CPU path)
+  double rdt;            // 1/dt
+  double rho_ratio;      // rho_bergs/rho_seawater
+  double r_rho_bergs;    // 1/rho_bergs
+  double r_h2ig;         // 1/h_to_init_grounding
+  double rpow40_02;      // 1/40**0.2  (bergy bits of bergs whose smallest dimension is >= 40 m, I:3076)
+  double dlat_dy;        // (180/pi)/Rearth  I:470
+  double r180_pi;        // 180/pi
+  double f_cori_plane;   // 2*omega*sin(pi_180*lat_ref)  I:2046
   int32_t grid_is_latlon, grid_is_regular, old_bug_bilin, use_roundoff_fix, use_f_plane;
   int32_t use_new_predictive_corrective, only_interactive_forces, override_iceberg_velocities;
   int32_t old_interp_flds_order, interactive_icebergs_on, iceberg_bonds_on, internal_bergs_for_drag;
@@ -59,7 +68,7 @@ struct DevParams {
 struct __align__(16) CornerRec { double uo, vo, ui, vi, ua, va, cosr, sinr; };
 // cell record: A-grid picks (I:4815-4818), od (I:4897) and what thermodynamics /
 // adjust_index_and_ground need from the cell; ddx/ddy = ddx_ssh/ddy_ssh (I:4903-4926)
-struct __align__(16) CellRec { double sst, sss, cn, hi, od, area, ddx, ddy; };
+struct __align__(16) CellRec { double sst, sss, cn, hi, od, rarea /* 1/area, 0 where area==0 */, ddx, ddy; };
 // corner position record
 struct __align__(16) LonLat { double lon, lat; };
 

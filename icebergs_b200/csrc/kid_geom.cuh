@@ -5,8 +5,10 @@
 //   is_point_in_cell F:6076, calc_xiyj F:6439, is_point_within_xi_yj_bounds F:6540,
 //   pos_within_cell F:6299, bilin F:7071, find_cell(_wide) F:6011/F:6044.
 // The operation order of every expression that feeds an integer decision (cell
-// membership, xi/yj clamps) is the reference's, so that with FMA contraction off
-// the branch outcomes are the ones the CPU path takes.
+// membership, xi/yj clamps) is the reference's, and those expressions are spelled
+// with the __d*_rn intrinsics, which the compiler never contracts into FMAs: the
+// branch outcomes are the ones the plain IEEE sequence of the CPU path takes even
+// though the rest of the library is compiled with FMA contraction on.
 #pragma once
 #include "kid_device.cuh"
 
@@ -18,34 +20,45 @@ __device__ __forceinline__ size_t gidx(const DevGrid& g, int i, int j) {
 
 __device__ __forceinline__ double f_sign1(double b) { return signbit(b) ? -1. : 1.; }
 
+// never-contracted arithmetic
+#define KMUL(a, b) __dmul_rn((a), (b))
+#define KADD(a, b) __dadd_rn((a), (b))
+#define KSUB(a, b) __dsub_rn((a), (b))
+
 // Fortran MODULO(a,p) for p>0.  The in-range case (every berg that is within half
 // a period of the reference point) is exact and costs two compares.
-__device__ __forceinline__ double f_modulo(double a, double p) {
-  if (a >= 0. && a < p) return a;
+__device__ __noinline__ double f_modulo_slow(double a, double p) {
   double r = fmod(a, p);
   if (r != 0. && r < 0.) r += p;
   return r;
+}
+__device__ __forceinline__ double f_modulo(double a, double p) {
+  if (a >= 0. && a < p) return a;
+  return f_modulo_slow(a, p);
 }
 
 // F:6558-6573
 __device__ __forceinline__ double amap(double x, double y, double Lx) {
   if (Lx > 0.) {
-    double Lx_2 = Lx / 2.;
-    return f_modulo(x - (y - Lx_2), Lx) + (y - Lx_2);
+    double Lx_2 = Lx * 0.5;
+    double yy = KSUB(y, Lx_2);
+    return KADD(f_modulo(KSUB(x, yy), Lx), yy);
   }
   return x;
 }
 
-// F:6163-6228: S and E edges belong to the cell, N and W do not (F:6199-6206)
+// F:6163-6228.  Inside a counter-clockwise cell all four cross products are negative, so the
+// zero-valued sentinels at F:6203-6206 make the S (p0) and W (p3) edges part of the cell and the
+// N and E edges not (the reference's comment says "South and East"; the code is followed)
 __device__ __forceinline__ bool sum_sign_dot_prod4(double x0, double y0, double x1, double y1,
                                                    double x2, double y2, double x3, double y3,
                                                    double x, double y, double Lx) {
   double xx = amap(x, x0, Lx);
   double xx0 = amap(x0, x0, Lx), xx1 = amap(x1, x0, Lx), xx2 = amap(x2, x0, Lx), xx3 = amap(x3, x0, Lx);
-  double l0 = (xx - xx0) * (y1 - y0) - (y - y0) * (xx1 - xx0);
-  double l1 = (xx - xx1) * (y2 - y1) - (y - y1) * (xx2 - xx1);
-  double l2 = (xx - xx2) * (y3 - y2) - (y - y2) * (xx3 - xx2);
-  double l3 = (xx - xx3) * (y0 - y3) - (y - y3) * (xx0 - xx3);
+  double l0 = KSUB(KMUL(KSUB(xx, xx0), KSUB(y1, y0)), KMUL(KSUB(y, y0), KSUB(xx1, xx0)));
+  double l1 = KSUB(KMUL(KSUB(xx, xx1), KSUB(y2, y1)), KMUL(KSUB(y, y1), KSUB(xx2, xx1)));
+  double l2 = KSUB(KMUL(KSUB(xx, xx2), KSUB(y3, y2)), KMUL(KSUB(y, y2), KSUB(xx3, xx2)));
+  double l3 = KSUB(KMUL(KSUB(xx, xx3), KSUB(y0, y3)), KMUL(KSUB(y, y3), KSUB(xx0, xx3)));
   double p0 = f_sign1(l0); if (l0 == 0.) p0 = -0.5;
   double p1 = f_sign1(l1); if (l1 == 0.) p1 = 0.5;
   double p2 = f_sign1(l2); if (l2 == 0.) p2 = 0.5;
@@ -60,11 +73,11 @@ __device__ __noinline__ bool sum_sign_dot_prod5(double x0, double y0, double x1,
   double xx = amap(x, x0, Lx);
   double xx0 = amap(x0, x0, Lx), xx1 = amap(x1, x0, Lx), xx2 = amap(x2, x0, Lx), xx3 = amap(x3, x0, Lx),
          xx4 = amap(x4, x0, Lx);
-  double l0 = (xx - xx0) * (y1 - y0) - (y - y0) * (xx1 - xx0);
-  double l1 = (xx - xx1) * (y2 - y1) - (y - y1) * (xx2 - xx1);
-  double l2 = (xx - xx2) * (y3 - y2) - (y - y2) * (xx3 - xx2);
-  double l3 = (xx - xx3) * (y4 - y3) - (y - y3) * (xx4 - xx3);
-  double l4 = (xx - xx4) * (y0 - y4) - (y - y4) * (xx0 - xx4);
+  double l0 = KSUB(KMUL(KSUB(xx, xx0), KSUB(y1, y0)), KMUL(KSUB(y, y0), KSUB(xx1, xx0)));
+  double l1 = KSUB(KMUL(KSUB(xx, xx1), KSUB(y2, y1)), KMUL(KSUB(y, y1), KSUB(xx2, xx1)));
+  double l2 = KSUB(KMUL(KSUB(xx, xx2), KSUB(y3, y2)), KMUL(KSUB(y, y2), KSUB(xx3, xx2)));
+  double l3 = KSUB(KMUL(KSUB(xx, xx3), KSUB(y4, y3)), KMUL(KSUB(y, y3), KSUB(xx4, xx3)));
+  double l4 = KSUB(KMUL(KSUB(xx, xx4), KSUB(y0, y4)), KMUL(KSUB(y, y4), KSUB(xx0, xx4)));
   double p0 = f_sign1(l0); if (l0 == 0.) p0 = 0.;
   double p1 = f_sign1(l1); if (l1 == 0.) p1 = 0.;
   double p2 = f_sign1(l2); if (l2 == 0.) p2 = 0.;
@@ -122,22 +135,22 @@ __device__ __forceinline__ bool is_point_in_cell(const DevGrid& g, const DevPara
 __device__ __forceinline__ void calc_xiyj(double x1, double x2, double x3, double x4, double y1, double y2,
                                           double y3, double y4, double x, double y, double* xi, double* yj,
                                           double Lx, unsigned int* err) {
-  double alpha = x2 - x1, delta = y2 - y1, beta = x4 - x1, epsilon = y4 - y1;
-  double gamma = (x3 - x1) - (alpha + beta);
-  double kappa = (y3 - y1) - (delta + epsilon);
-  double a = (kappa * beta - gamma * epsilon);
-  double dx = amap(x, x1, Lx) - x1;
-  double dy = y - y1;
-  double b = (delta * beta - alpha * epsilon) - (kappa * dx - gamma * dy);
-  double c = (alpha * dy - delta * dx);
+  double alpha = KSUB(x2, x1), delta = KSUB(y2, y1), beta = KSUB(x4, x1), epsilon = KSUB(y4, y1);
+  double gamma = KSUB(KSUB(x3, x1), KADD(alpha, beta));
+  double kappa = KSUB(KSUB(y3, y1), KADD(delta, epsilon));
+  double a = KSUB(KMUL(kappa, beta), KMUL(gamma, epsilon));
+  double dx = KSUB(amap(x, x1, Lx), x1);
+  double dy = KSUB(y, y1);
+  double b = KSUB(KSUB(KMUL(delta, beta), KMUL(alpha, epsilon)), KSUB(KMUL(kappa, dx), KMUL(gamma, dy)));
+  double c = KSUB(KMUL(alpha, dy), KMUL(delta, dx));
   double yy;
   if (fabs(a) > 1.e-12) {
-    double d = 0.25 * (b * b) - a * c;
+    double d = KSUB(KMUL(0.25, KMUL(b, b)), KMUL(a, c));
     if (d >= 0.) {
       double sq = sqrt(d);
-      double yy1 = -(0.5 * b + sq) / a;
-      double yy2 = -(0.5 * b - sq) / a;
-      yy = (fabs(yy1 - 0.5) < fabs(yy2 - 0.5)) ? yy1 : yy2;
+      double yy1 = -KADD(KMUL(0.5, b), sq) / a;
+      double yy2 = -KSUB(KMUL(0.5, b), sq) / a;
+      yy = (fabs(KSUB(yy1, 0.5)) < fabs(KSUB(yy2, 0.5))) ? yy1 : yy2;
     } else {
       atomicOr(err, (unsigned)KID_DEVERR_COMPLEX_ROOTS);
       yy = 0.;
@@ -145,17 +158,17 @@ __device__ __forceinline__ void calc_xiyj(double x1, double x2, double x3, doubl
   } else {
     yy = (b != 0.) ? -c / b : 0.;
   }
-  a = (alpha + gamma * yy);
-  b = (delta + kappa * yy);
+  a = KADD(alpha, KMUL(gamma, yy));
+  b = KADD(delta, KMUL(kappa, yy));
   double xx;
   if (a != 0.) {
-    xx = (dx - beta * yy) / a;
+    xx = KSUB(dx, KMUL(beta, yy)) / a;
   } else if (b != 0.) {
-    xx = (dy - epsilon * yy) / b;
+    xx = KSUB(dy, KMUL(epsilon, yy)) / b;
   } else {
-    c = (epsilon * alpha - beta * delta) + (epsilon * gamma - beta * kappa) * yy;
+    c = KADD(KSUB(KMUL(epsilon, alpha), KMUL(beta, delta)), KMUL(KSUB(KMUL(epsilon, gamma), KMUL(beta, kappa)), yy));
     if (c != 0.) {
-      xx = (epsilon * dx - beta * dy) / c;
+      xx = KSUB(KMUL(epsilon, dx), KMUL(beta, dy)) / c;
     } else {
       atomicOr(err, (unsigned)KID_DEVERR_NOT_INVERTIBLE);
       xx = 0.;
@@ -190,40 +203,62 @@ __device__ __noinline__ void polar_xiyj(const Quad& q, const DevParams& p, doubl
   }
 }
 
+// exact membership test kept out of line: pos_within_cell only needs it for points within
+// KID_EDGE_BAND of a cell edge (see below)
+__device__ __noinline__ bool is_point_in_quad_ool(const Quad& q, const DevParams& p, double x, double y) {
+  return is_point_in_quad(q, p, x, y);
+}
+
+#define KID_EDGE_BAND 1.e-6
+
 // F:6299-6436.  Returns is_point_in_cell; xi,yj = -999 when (i,j) is off the PE.
-__device__ __forceinline__ bool pos_within_cell(const DevGrid& g, const DevParams& p, double x, double y,
-                                                int i, int j, double* xi, double* yj, unsigned int* err) {
+// Membership (F:6076) is decided from (xi,yj) when the point is farther than KID_EDGE_BAND
+// (in cell units) from every edge -- there the four cross products of sum_sign_dot_prod4 have
+// the same sign (inside) or the crude bounds / a cross product rejects the point (outside) by a
+// margin ~1e10 times the rounding error; only inside the band, and always in polar cells, is
+// the reference's sign test evaluated.
+__device__ __noinline__ bool pos_within_cell(const DevGrid& g, const DevParams& p, double x, double y,
+                                             int i, int j, double* xi, double* yj, unsigned int* err) {
   *xi = -999.; *yj = -999.;
   if (!cell_on_pe(g, i, j)) return false;
   Quad q = load_quad(g, i, j);
-  bool inside = is_point_in_quad(q, p, x, y);
+  double a, b;
   if ((!p.grid_is_latlon) && p.grid_is_regular) {
-    double dx = fabs((q.x3 - q.x4));
-    double dy = fabs((q.y3 - q.y2));
-    double x1 = q.x3 - (dx / 2);
-    double y1 = q.y3 - (dy / 2);
-    double Delta_x = amap(x, x1, p.Lx) - x1;
-    *xi = ((Delta_x) / dx) + 0.5;
-    *yj = ((y - y1) / dy) + 0.5;
+    double dx = fabs(KSUB(q.x3, q.x4));
+    double dy = fabs(KSUB(q.y3, q.y2));
+    double x1 = KSUB(q.x3, KMUL(dx, 0.5));
+    double y1 = KSUB(q.y3, KMUL(dy, 0.5));
+    double Delta_x = KSUB(amap(x, x1, p.Lx), x1);
+    a = KADD(((Delta_x) / dx), 0.5);
+    b = KADD((KSUB(y, y1) / dy), 0.5);
   } else if ((fmax(fmax(q.y1, q.y2), fmax(q.y3, q.y4)) < 89.999) || (!p.grid_is_latlon)) {
-    calc_xiyj(q.x1, q.x2, q.x3, q.x4, q.y1, q.y2, q.y3, q.y4, x, y, xi, yj, p.Lx, err);
+    calc_xiyj(q.x1, q.x2, q.x3, q.x4, q.y1, q.y2, q.y3, q.y4, x, y, &a, &b, p.Lx, err);
   } else {
+    bool inside = is_point_in_quad_ool(q, p, x, y);
     polar_xiyj(q, p, x, y, xi, yj, inside, err);
+    return inside;
   }
-  return inside;
+  *xi = a; *yj = b;
+  const double lo = KID_EDGE_BAND, hi = 1. - KID_EDGE_BAND;
+  if (a > lo && a < hi && b > lo && b < hi) return true;
+  if (a < -lo || a > 1. + lo || b < -lo || b > 1. + lo) return false;
+  return is_point_in_quad_ool(q, p, x, y);
 }
 
 // F:7071-7088 on the corner positions
 __device__ __forceinline__ void bilin_lonlat(const DevGrid& g, const DevParams& p, int i, int j, double xi,
                                              double yj, double* lon, double* lat) {
   Quad q = load_quad(g, i, j);
+#define KB1(A, B, C, D, w1, w2, w3, w4) KADD(KMUL(KADD(KMUL(A, w1), KMUL(B, w2)), w3), KMUL(KADD(KMUL(C, w1), KMUL(D, w2)), w4))
+  double xm = KSUB(1., xi), ym = KSUB(1., yj);
   if (p.old_bug_bilin) {
-    *lon = (q.x3 * (1. - xi) + q.x4 * xi) * (1. - yj) + (q.x2 * (1. - xi) + q.x1 * xi) * yj;
-    *lat = (q.y3 * (1. - xi) + q.y4 * xi) * (1. - yj) + (q.y2 * (1. - xi) + q.y1 * xi) * yj;
+    *lon = KB1(q.x3, q.x4, q.x2, q.x1, xm, xi, ym, yj);
+    *lat = KB1(q.y3, q.y4, q.y2, q.y1, xm, xi, ym, yj);
   } else {
-    *lon = (q.x3 * xi + q.x4 * (1. - xi)) * yj + (q.x2 * xi + q.x1 * (1. - xi)) * (1. - yj);
-    *lat = (q.y3 * xi + q.y4 * (1. - xi)) * yj + (q.y2 * xi + q.y1 * (1. - xi)) * (1. - yj);
+    *lon = KB1(q.x3, q.x4, q.x2, q.x1, xi, xm, yj, ym);
+    *lat = KB1(q.y3, q.y4, q.y2, q.y1, xi, xm, yj, ym);
   }
+#undef KB1
 }
 
 // structured-grid guess shared by find_cell / find_cell_wide, F:6025-6026

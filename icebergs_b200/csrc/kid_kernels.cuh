@@ -24,7 +24,7 @@ __device__ __forceinline__ double shfl_down_d(double v, int d) { return __shfl_d
 // Warp-aggregated scatter-add: lanes that hold the same key in a run of consecutive
 // lanes are reduced first (segmented suffix sum), the head lane of each run issues
 // one atomic.  All 32 lanes must call; key < 0 = nothing to add.
-struct SegInfo { int seg_end; bool head; };
+struct SegInfo { int seg_end; int rounds; bool head; };
 __device__ __forceinline__ SegInfo seg_info(long long key) {
   int lane = threadIdx.x & 31;
   long long prev = __shfl_up_sync(0xffffffffu, key, 1);
@@ -34,18 +34,21 @@ __device__ __forceinline__ SegInfo seg_info(long long key) {
   SegInfo s;
   s.seg_end = above ? (lane + 1 + (__ffs(above) - 1)) : 32;
   s.head = head;
+  // longest run in the warp decides how many doubling rounds the suffix sums need
+  int len = head ? (s.seg_end - lane) : 0;
+  s.rounds = __reduce_max_sync(0xffffffffu, len);
   return s;
 }
 __device__ __forceinline__ double seg_sum(double v, const SegInfo& s) {
   int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
+  for (int d = 1; d < s.rounds; d <<= 1) {
     double o = shfl_down_d(v, d);
     if (lane + d < s.seg_end) v += o;
   }
   return v;
 }
 __device__ __forceinline__ void seg_scatter(double* __restrict__ fld, long long key, double v, const SegInfo& s) {
+  if (!__any_sync(0xffffffffu, v != 0.)) return;     // e.g. calving_hflx when no berg carries heat
   double t = seg_sum(v, s);
   if (s.head && key >= 0 && t != 0.) atomicAdd(&fld[key], t);
 }
@@ -123,11 +126,12 @@ __device__ __forceinline__ int thermo_slot(const DevGrid& g, const DevBergs& b, 
                                            uint8_t flags, int i, int j, double xi, double yj, double uvel,
                                            double vvel, double M, double T, double W, double L, Scatter& sc,
                                            DevCounters* cnt) {
-  Env e;
-  if (!interp_flds(g, p, i, j, xi, yj, e)) atomicOr(&cnt->error_flags, 64u);
   size_t cidx = gidx(g, i, j);
-  double area = g.cell[cidx].area;
-  if (area == 0.) { atomicOr(&cnt->error_flags, (unsigned)KID_DEVERR_GROUNDED); return TH_KEEP; }
+  EnvThermo e;
+  interp_thermo(g, p, cidx, xi, yj, e);
+  if ((e.uo != e.uo) || (e.vo != e.vo) || (e.ua != e.ua) || (e.va != e.va) || (e.sst != e.sst) || (e.cn != e.cn))
+    atomicOr(&cnt->error_flags, 64u);
+  if (e.rarea == 0.) { atomicOr(&cnt->error_flags, (unsigned)KID_DEVERR_GROUNDED); return TH_KEEP; }
   ThermoState st;
   st.mass = M; st.thickness = T; st.width = W; st.length = L;
   st.mass_scaling = b.f64[C_MASS_SCALING][s];
@@ -146,8 +150,7 @@ __device__ __forceinline__ int thermo_slot(const DevGrid& g, const DevBergs& b, 
     // N_bonds: I:2928-2944 (bond counts live with the bonded path; free bergs have none)
     if (flags & BF_STATIC) N_bonds = p.hexagonal_icebergs ? 6.0 : 4.0;
   }
-  double ms_in = st.mass_scaling;
-  int outcome = thermo_berg(p, e, uvel, vvel, area, N_bonds, st, sc.fx);
+  int outcome = thermo_berg(p, e, uvel, vvel, N_bonds, st, sc.fx);
   sc.key = (long long)cidx;
   b.f64[C_MASS][s] = st.mass;
   b.f64[C_THICKNESS][s] = st.thickness;
@@ -164,7 +167,6 @@ __device__ __forceinline__ int thermo_slot(const DevGrid& g, const DevBergs& b, 
       b.start_year[s] = st.start_year;
     }
   }
-  (void)ms_in;
   return outcome;
 }
 
@@ -200,9 +202,13 @@ k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
       double vvel3 = vvel + (dt_2 * ayn);
       Env e;
       if (!interp_flds(g, p, i, j, xi, yj, e)) atomicOr(&cnt->error_flags, 64u);
+      // sin and cos of the latitude: Coriolis (I:2043-2047) and the metric (I:462-477)
+      double sin_lat = 0., cos_lat = 1.;
+      if (p.grid_is_latlon) sincos(p.pi_180 * lat, &sin_lat, &cos_lat);
+      double f_cori = (p.grid_is_latlon && !p.use_f_plane) ? p.omega2 * sin_lat : p.f_cori_plane;
       double ax1, ay1, un_l, vn_l;
       IAcc ia0 = {0., 0., 0., 0., 0., 0., 0., 0.};
-      accel_core<false>(p, M, T, W, L, lat, uvel, vvel, uvel, vvel, dt, e, 1.0, ia0,
+      accel_core<false>(p, M, T, W, L, f_cori, uvel, vvel, dt, e, 1.0, ia0,
                         [](double, double, IAcc&) {}, ax1, ay1, axn, ayn, bxn, byn, un_l, vn_l);
       if ((p.speed_limit > 0.) || (p.speed_limit == -1.)) {   // I:2304-2323: only the ticket survives
         double speed = sqrt(un_l * un_l + vn_l * vn_l);
@@ -226,8 +232,8 @@ k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
       if (tang) {
         tang_position(p, lon, lat, uvel2, vvel2, dt, lonn, latn);
       } else {
-        double dxdl1, dydl;
-        convert_from_meters_to_grid(p, lat, dxdl1, dydl);
+        double dxdl1 = 1., dydl = 1.;
+        if (p.grid_is_latlon) { dxdl1 = p.r180_pi / (p.Rearth * cos_lat); dydl = p.dlat_dy; }
         double u2 = uvel2 * dxdl1, v2 = vvel2 * dydl;
         lonn = lon + (dt * u2); latn = lat + (dt * v2);
       }
@@ -586,7 +592,7 @@ __global__ void k_pack_forcing(const __grid_constant__ DevGrid g, long long n2) 
   CellRec c;
   c.sst = g.sst[k]; c.sss = g.sss[k]; c.cn = g.cn[k]; c.hi = g.hi[k];
   c.od = g.ocean_depth[k] + g.ssh[k];
-  c.area = g.area[k];
+  { double a_ = g.area[k]; c.rarea = (a_ != 0.) ? 1. / a_ : 0.; }
   double ddx = 0., ddy = 0.;
   if (i + 1 <= g.ied && j - 1 >= g.jsd) {
     double dxp = 0.5 * (g.dx[k + 1] + g.dx[k + 1 - nid]);

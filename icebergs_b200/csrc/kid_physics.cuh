@@ -5,8 +5,15 @@
 //   accel I:1950, verlet_stepping I:7203, update_verlet_position I:7684,
 //   adjust_index_and_ground I:7819, tangent-plane helpers I:7767-7816 / I:8066,
 //   thermodynamics I:2844 (+ rolling I:3307, fl_bits_dimensions I:3370).
-// Expression order is the reference's (see SURVEY.md appendix A for the quirks
-// that are reproduced on purpose).
+// The formulas, branch conditions and quirks are the reference's.
+// Floating-point evaluation differs from the CPU path only at rounding level (north_star
+// tolerance 1e-10): divisions by a common denominator are multiplications by one reciprocal,
+// x**0.8 / x**0.2 are exp(c*log x), sin and cos of the latitude share one argument
+// reduction, and the interpolation / momentum sums use explicit fma().  The library is compiled
+// with -fmad=false: the compiler never contracts on its own, so expressions whose exact
+// cancellation the reference relies on (the operator-split mass differences of thermodynamics,
+// the cell-membership cross products) keep the plain IEEE sequence.  Everything that decides an
+// integer (cell index, bounce, deletion) branches on the reference's own conditions.
 #pragma once
 #include "kid_geom.cuh"
 
@@ -18,14 +25,16 @@ struct Env { double uo, vo, ui, vi, ua, va, ssh_x, ssh_y, sst, sss, cn, hi, od; 
 struct IAcc { double IA_x, IA_y, P11, P12, P21, P22, Pu_x, Pu_y; };
 
 // F:7071-7088 on one component of the four corner records
-#define KID_BILIN(f) (p.old_bug_bilin \
-    ? ((c3.f * (1. - xi) + c4.f * xi) * (1. - yj) + (c2.f * (1. - xi) + c1.f * xi) * yj) \
-    : ((c3.f * xi + c4.f * (1. - xi)) * yj + (c2.f * xi + c1.f * (1. - xi)) * (1. - yj)))
+// (w3,w4,wn,ws) = (xi,1-xi,yj,1-yj), or swapped under old_bug_bilin
+#define KID_BILIN(f) fma(fma(c3.f, w3, c4.f * w4), wn, fma(c2.f, w3, c1.f * w4) * ws)
+#define KID_BILIN_WEIGHTS                                   \
+  double w3 = xi, w4 = 1. - xi, wn = yj, ws = 1. - yj;      \
+  if (p.old_bug_bilin) { w3 = 1. - xi; w4 = xi; wn = 1. - yj; ws = yj; }
 
 __device__ __forceinline__ void rotate(double& u, double& v, double cos_rot, double sin_rot) {
   double u_old = u, v_old = v;
-  u = cos_rot * u_old + sin_rot * v_old;
-  v = cos_rot * v_old - sin_rot * u_old;
+  u = fma(cos_rot, u_old, sin_rot * v_old);
+  v = fma(cos_rot, v_old, -(sin_rot * u_old));
 }
 
 // I:4718-4900 (non-MTS ocean depth, I:4897).  Returns false when a NaN survived.
@@ -36,6 +45,7 @@ __device__ __forceinline__ bool interp_flds(const DevGrid& g, const DevParams& p
   size_t ne = gidx(g, i, j);
   size_t nid = (size_t)g.nid;
   const CornerRec c3 = cr[ne], c4 = cr[ne - 1], c2 = cr[ne - nid], c1 = cr[ne - nid - 1];
+  KID_BILIN_WEIGHTS
   double cos_rot = KID_BILIN(cosr);
   double sin_rot = KID_BILIN(sinr);
   double uo = KID_BILIN(uo), vo = KID_BILIN(vo);
@@ -54,21 +64,21 @@ __device__ __forceinline__ bool interp_flds(const DevGrid& g, const DevParams& p
   e.sst = c0.sst; e.sss = c0.sss; e.cn = c0.cn; e.hi = c0.hi; e.od = c0.od;
   double hxp, hxm;
   if (yj >= 0.5) {
-    hxp = (yj - 0.5) * ce[ne + nid].ddx + (1.5 - yj) * c0.ddx;
-    hxm = (yj - 0.5) * ce[ne + nid - 1].ddx + (1.5 - yj) * ce[ne - 1].ddx;
+    hxp = fma((yj - 0.5), ce[ne + nid].ddx, (1.5 - yj) * c0.ddx);
+    hxm = fma((yj - 0.5), ce[ne + nid - 1].ddx, (1.5 - yj) * ce[ne - 1].ddx);
   } else {
-    hxp = (yj + 0.5) * c0.ddx + (0.5 - yj) * ce[ne - nid].ddx;
-    hxm = (yj + 0.5) * ce[ne - 1].ddx + (0.5 - yj) * ce[ne - nid - 1].ddx;
+    hxp = fma((yj + 0.5), c0.ddx, (0.5 - yj) * ce[ne - nid].ddx);
+    hxm = fma((yj + 0.5), ce[ne - 1].ddx, (0.5 - yj) * ce[ne - nid - 1].ddx);
   }
-  double ssh_x = xi * hxp + (1. - xi) * hxm;
+  double ssh_x = fma(xi, hxp, (1. - xi) * hxm);
   if (xi >= 0.5) {
-    hxp = (xi - 0.5) * ce[ne + 1].ddy + (1.5 - xi) * c0.ddy;
-    hxm = (xi - 0.5) * ce[ne - nid + 1].ddy + (1.5 - xi) * ce[ne - nid].ddy;
+    hxp = fma((xi - 0.5), ce[ne + 1].ddy, (1.5 - xi) * c0.ddy);
+    hxm = fma((xi - 0.5), ce[ne - nid + 1].ddy, (1.5 - xi) * ce[ne - nid].ddy);
   } else {
-    hxp = (xi + 0.5) * c0.ddy + (0.5 - xi) * ce[ne - 1].ddy;
-    hxm = (xi + 0.5) * ce[ne - nid].ddy + (0.5 - xi) * ce[ne - nid - 1].ddy;
+    hxp = fma((xi + 0.5), c0.ddy, (0.5 - xi) * ce[ne - 1].ddy);
+    hxm = fma((xi + 0.5), ce[ne - nid].ddy, (0.5 - xi) * ce[ne - nid - 1].ddy);
   }
-  double ssh_y = yj * hxp + (1. - yj) * hxm;
+  double ssh_y = fma(yj, hxp, (1. - yj) * hxm);
   rotate(uo, vo, cos_rot, sin_rot);
   rotate(ui, vi, cos_rot, sin_rot);
   rotate(ua, va, cos_rot, sin_rot);
@@ -79,6 +89,33 @@ __device__ __forceinline__ bool interp_flds(const DevGrid& g, const DevParams& p
   bool bad = (uo != uo) || (vo != vo) || (ui != ui) || (vi != vi) || (ua != ua) || (va != va) ||
              (e.sst != e.sst) || (e.sss != e.sss) || (e.cn != e.cn) || (e.hi != e.hi);
   return !bad;
+}
+
+// What thermodynamics (I:2896-2920) uses of interp_flds: the rotated ocean and wind velocities
+// and the A-grid picks of sst, cn; also hands back 1/area of the cell.
+struct EnvThermo { double uo, vo, ua, va, sst, cn, rarea; };
+__device__ __forceinline__ void interp_thermo(const DevGrid& g, const DevParams& p, size_t ne, double xi, double yj,
+                                              EnvThermo& e) {
+  const CornerRec* __restrict__ cr = g.corner;
+  size_t nid = (size_t)g.nid;
+  const CornerRec c3 = cr[ne], c4 = cr[ne - 1], c2 = cr[ne - nid], c1 = cr[ne - nid - 1];
+  KID_BILIN_WEIGHTS
+  double cos_rot = KID_BILIN(cosr);
+  double sin_rot = KID_BILIN(sinr);
+  double uo = KID_BILIN(uo), vo = KID_BILIN(vo);
+  double ua = KID_BILIN(ua), va = KID_BILIN(va);
+  if (p.coastal_drift > 0.) {
+    const double* __restrict__ msk = g.msk;
+    double cd = p.coastal_drift;
+    double m0 = msk[ne], mE = msk[ne + 1], mW = msk[ne - 1], mN = msk[ne + nid], mS = msk[ne - nid];
+    uo = uo + cd * (mE - mW) * m0;
+    vo = vo + cd * (mN - mS) * m0;
+  }
+  rotate(uo, vo, cos_rot, sin_rot);
+  rotate(ua, va, cos_rot, sin_rot);
+  const CellRec* __restrict__ ce = g.cell;
+  e.sst = ce[ne].sst; e.cn = ce[ne].cn; e.rarea = ce[ne].rarea;
+  e.uo = uo; e.vo = vo; e.ua = ua; e.va = va;
 }
 
 // I:444-477
@@ -99,111 +136,119 @@ __device__ __forceinline__ void convert_from_meters_to_grid(const DevParams& p, 
 
 // accel I:1950-2442 after the environment is known.  IAF(us, vs, IAcc&) evaluates
 // interactive_force with the latest velocity estimate (second call, I:2217); ia is
-// the first evaluation (I:2153).  dragfrac: I:2104-2120.
+// the first evaluation (I:2153).  dragfrac: I:2104-2120.  f_cori: I:2043-2047.
 template <bool INTERACTIVE, class IAF>
 __device__ __forceinline__ void accel_core(const DevParams& p, double M, double T, double W, double L,
-                                           double lat, double uvel, double vvel, double uvel0, double vvel0,
-                                           double dt, const Env& e, double dragfrac, IAcc ia, IAF&& iaf,
-                                           double& ax, double& ay, double& axn, double& ayn, double& bxn,
-                                           double& byn, double& uveln_out, double& vveln_out) {
+                                           double f_cori, double uvel0, double vvel0, double dt, const Env& e,
+                                           double dragfrac, IAcc ia, IAF&& iaf, double& ax, double& ay,
+                                           double& axn, double& ayn, double& bxn, double& byn, double& uveln_out,
+                                           double& vveln_out) {
   // Verlet only: alpha=1, C_N=1, beta=1, use_new_predictive_corrective=T (I:2008-2013)
   const double Cr0 = 0.06;
-  double u_star = uvel0 + (axn * (dt / 2.));
-  double v_star = vvel0 + (ayn * (dt / 2.));
+  double u_star = fma(axn, (dt * 0.5), uvel0);
+  double v_star = fma(ayn, (dt * 0.5), vvel0);
   double uo = e.uo, vo = e.vo, ui = e.ui, vi = e.vi, ua = e.ua, va = e.va;
   double ssh_x = e.ssh_x, ssh_y = e.ssh_y, hi = e.hi, od = e.od;
-  double f_cori;
-  if (p.grid_is_latlon && !p.use_f_plane) f_cori = p.omega2 * sin(p.pi_180 * lat);
-  else f_cori = p.omega2 * sin(p.pi_180 * p.lat_ref);
-  double D = (p.rho_bergs / KID_RHO_SEAWATER) * T;
+  double rM = 1. / M;
+  double D = p.rho_ratio * T;
   double F = T - D;
   hi = fmin(hi, D);
   double D_hi = fmax(0., D - hi);
-  double groundfrac, c_gnd;
-  if (p.h_to_init_grounding > 0.0) {
-    groundfrac = 1.0 - (od - D) / p.h_to_init_grounding;
-    groundfrac = fmax(groundfrac, 0.0); groundfrac = fmin(groundfrac, 1.0);
-  } else {
-    groundfrac = (D > od) ? 1.0 : 0.0;
+  double c_gnd = 0.0;
+  if (p.cdrag_grounding != 0.) {      // I:2066-2082 (c_gnd is exactly 0 otherwise)
+    double groundfrac;
+    if (p.h_to_init_grounding > 0.0) {
+      groundfrac = 1.0 - (od - D) * p.r_h2ig;
+      groundfrac = fmin(fmax(groundfrac, 0.0), 1.0);
+    } else {
+      groundfrac = (D > od) ? 1.0 : 0.0;
+    }
+    if (groundfrac > 0.0) c_gnd = (p.cdrag_grounding * W * L * groundfrac) * rM;
   }
-  if (groundfrac > 0.0) c_gnd = (p.cdrag_grounding * W * L * groundfrac) / M; else c_gnd = 0.0;
   double uwave = ua - uo, vwave = va - vo;
-  double wmod = uwave * uwave + vwave * vwave;
+  double wmod = fma(uwave, uwave, vwave * vwave);
   double ampl = 0.5 * 0.02025 * wmod;
   double Lwavelength = 0.32 * wmod;
   double Lcutoff = 0.125 * Lwavelength;
   double Ltop = 0.25 * Lwavelength;
-  double Cr = Cr0 * fmin(fmax(0., (L - Lcutoff) / ((Ltop - Lcutoff) + 1.e-30)), 1.);
-  double wave_rad = 0.5 * KID_RHO_SEAWATER / M * Cr * KID_GRAVITY * ampl * fmin(ampl, F) * (2. * W * L) / (W + L);
-  wmod = sqrt(ua * ua + va * va);
-  if (wmod != 0.) { uwave = ua / wmod; vwave = va / wmod; }
+  // Cr0*min(max(0,(L-Lcutoff)/((Ltop-Lcutoff)+1e-30)),1): the quotient only matters strictly inside (0,1)
+  double cr_num = L - Lcutoff, cr_den = (Ltop - Lcutoff) + 1.e-30;
+  double Cr = (cr_num >= cr_den) ? Cr0 : ((cr_num <= 0.) ? 0. : Cr0 * (cr_num / cr_den));
+  double wave_rad = 0.5 * KID_RHO_SEAWATER * rM * Cr * KID_GRAVITY * ampl * fmin(ampl, F) * (2. * W * L) / (W + L);
+  wmod = sqrt(fma(ua, ua, va * va));
+  if (wmod != 0.) { double rw = 1. / wmod; uwave = ua * rw; vwave = va * rw; }
   else { uwave = 0.; vwave = 0.; wave_rad = 0.; }
-  double c_ocn = KID_RHO_SEAWATER / M * p.ocean_drag_scale * (0.5 * KID_CD_WV * dragfrac * W * (D_hi) + KID_CD_WH * W * L);
-  double c_atm = KID_RHO_AIR / M * (0.5 * KID_CD_AV * dragfrac * W * F + KID_CD_AH * W * L);
+  double WL = W * L;
+  double c_ocn = KID_RHO_SEAWATER * rM * p.ocean_drag_scale * (0.5 * KID_CD_WV * dragfrac * W * (D_hi) + KID_CD_WH * WL);
+  double c_atm = KID_RHO_AIR * rM * (0.5 * KID_CD_AV * dragfrac * W * F + KID_CD_AH * WL);
   double c_ice;
-  if (fabs(hi) == 0.) c_ice = 0.; else c_ice = KID_RHO_ICE / M * (0.5 * KID_CD_IV * dragfrac * W * hi);
+  if (fabs(hi) == 0.) c_ice = 0.; else c_ice = KID_RHO_ICE * rM * (0.5 * KID_CD_IV * dragfrac * W * hi);
   if (fabs(ui) + fabs(vi) == 0.) c_ice = 0.;
-  axn = -KID_GRAVITY * ssh_x + wave_rad * uwave;
-  ayn = -KID_GRAVITY * ssh_y + wave_rad * vwave;
+  double ax_expl = fma(-KID_GRAVITY, ssh_x, wave_rad * uwave);     // I:2143-2144 and again I:2288-2289
+  double ay_expl = fma(-KID_GRAVITY, ssh_y, wave_rad * vwave);
+  if (INTERACTIVE) { ax_expl = ax_expl + ia.IA_x; ay_expl = ay_expl + ia.IA_y; }
+  axn = fma(f_cori, v_star, ax_expl);
+  ayn = fma(-f_cori, u_star, ay_expl);
   bxn = 0.; byn = 0.;
-  if (INTERACTIVE) { axn = axn + ia.IA_x; ayn = ayn + ia.IA_y; }
-  axn = axn + f_cori * v_star;
-  ayn = ayn - f_cori * u_star;
   double uveln = uvel0, vveln = vvel0;
   double us = uvel0, vs = vvel0;
-  // the velocity-at-start halves of the drag magnitudes do not change between the two iterations
-  double d0_ocn = sqrt((uvel0 - uo) * (uvel0 - uo) + (vvel0 - vo) * (vvel0 - vo));
-  double d0_atm = sqrt((uvel0 - ua) * (uvel0 - ua) + (vvel0 - va) * (vvel0 - va));
-  double d0_ice = sqrt((uvel0 - ui) * (uvel0 - ui) + (vvel0 - vi) * (vvel0 - vi));
+  // the velocity-at-start halves of the drag magnitudes are the same in both iterations, and in
+  // the first one uveln = uvel0 so that 0.5*(d0+d0) = d0 exactly
+#define KID_HYPOT(a, b) sqrt(fma((a), (a), (b) * (b)))
+  double d0_ocn = KID_HYPOT(uvel0 - uo, vvel0 - vo);
+  double d0_atm = KID_HYPOT(uvel0 - ua, vvel0 - va);
+  double d0_ice = KID_HYPOT(uvel0 - ui, vvel0 - vi);
+  double half_cori = 0.5 * (dt * f_cori);                        // A21 = -A12 = alpha*dt*f_cori/2
 #pragma unroll
   for (int itloop = 1; itloop <= 2; itloop++) {
-    if (itloop == 2) { us = uveln; vs = vveln; }
-    double drag_ocn = c_ocn * 0.5 * (sqrt((uveln - uo) * (uveln - uo) + (vveln - vo) * (vveln - vo)) + d0_ocn);
-    double drag_atm = c_atm * 0.5 * (sqrt((uveln - ua) * (uveln - ua) + (vveln - va) * (vveln - va)) + d0_atm);
-    double drag_ice = c_ice * 0.5 * (sqrt((uveln - ui) * (uveln - ui) + (vveln - vi) * (vveln - vi)) + d0_ice);
+    double drag_ocn, drag_atm, drag_ice;
+    if (itloop == 1) {
+      drag_ocn = c_ocn * d0_ocn; drag_atm = c_atm * d0_atm; drag_ice = c_ice * d0_ice;
+    } else {
+      us = uveln; vs = vveln;
+      drag_ocn = c_ocn * 0.5 * (KID_HYPOT(uveln - uo, vveln - vo) + d0_ocn);
+      drag_atm = c_atm * 0.5 * (KID_HYPOT(uveln - ua, vveln - va) + d0_atm);
+      drag_ice = c_ice * 0.5 * (KID_HYPOT(uveln - ui, vveln - vi) + d0_ice);
+    }
     double drag_gnd = c_gnd;
-    double RHS_x = (axn / 2) + bxn;
-    double RHS_y = (ayn / 2) + byn;
-    RHS_x = RHS_x - drag_ocn * (u_star - uo) - drag_atm * (u_star - ua) - drag_ice * (u_star - ui) - drag_gnd * u_star;
-    RHS_y = RHS_y - drag_ocn * (v_star - vo) - drag_atm * (v_star - va) - drag_ice * (v_star - vi) - drag_gnd * v_star;
+    double RHS_x = fma(axn, 0.5, bxn);
+    double RHS_y = fma(ayn, 0.5, byn);
+    RHS_x = fma(-drag_gnd, u_star, fma(-drag_ice, (u_star - ui), fma(-drag_atm, (u_star - ua), fma(-drag_ocn, (u_star - uo), RHS_x))));
+    RHS_y = fma(-drag_gnd, v_star, fma(-drag_ice, (v_star - vi), fma(-drag_atm, (v_star - va), fma(-drag_ocn, (v_star - vo), RHS_y))));
     if (INTERACTIVE) {
       if (itloop > 1) iaf(us, vs, ia);
       RHS_x = RHS_x - (((ia.P11 * u_star) + (ia.P12 * v_star)) - ia.Pu_x);
       RHS_y = RHS_y - (((ia.P21 * u_star) + (ia.P22 * v_star)) - ia.Pu_y);
     }
     double A11, A12, A21, A22;
-    if (p.only_interactive_forces) {
-      RHS_x = (ia.IA_x / 2) - (((ia.P11 * u_star) + (ia.P12 * v_star)) - ia.Pu_x);
-      RHS_y = (ia.IA_y / 2) - (((ia.P21 * u_star) + (ia.P22 * v_star)) - ia.Pu_y);
+    if (INTERACTIVE && p.only_interactive_forces) {
+      RHS_x = (ia.IA_x * 0.5) - (((ia.P11 * u_star) + (ia.P12 * v_star)) - ia.Pu_x);
+      RHS_y = (ia.IA_y * 0.5) - (((ia.P21 * u_star) + (ia.P22 * v_star)) - ia.Pu_y);
       A11 = 1 + (dt * ia.P11); A12 = (dt * ia.P12); A21 = (dt * ia.P21); A22 = 1 + (dt * ia.P22);
     } else {
       double lambda = drag_ocn + drag_atm + drag_ice + drag_gnd;
-      A11 = 1. + 1.0 * dt * lambda;
-      A22 = 1. + 1.0 * dt * lambda;
-      A12 = -1.0 * dt * f_cori;
-      A21 = 1.0 * dt * f_cori;
-      A12 = A12 / 2.; A21 = A21 / 2.;
+      A11 = fma(dt, lambda, 1.);
+      A22 = A11;
+      A12 = -half_cori;
+      A21 = half_cori;
       if (INTERACTIVE) {
         A11 = A11 + (dt * ia.P11); A12 = A12 + (dt * ia.P12);
         A21 = A21 + (dt * ia.P21); A22 = A22 + (dt * ia.P22);
       }
     }
-    double detA = 1. / ((A11 * A22) - (A12 * A21));
-    ax = detA * (A22 * RHS_x - A12 * RHS_y);
-    ay = detA * (A11 * RHS_y - A21 * RHS_x);
-    uveln = u_star + dt * ax;
-    vveln = v_star + dt * ay;
+    double detA = 1. / fma(A11, A22, -(A12 * A21));
+    ax = detA * fma(A22, RHS_x, -(A12 * RHS_y));
+    ay = detA * fma(A11, RHS_y, -(A21 * RHS_x));
+    uveln = fma(dt, ax, u_star);
+    vveln = fma(dt, ay, v_star);
   }
-  if (p.only_interactive_forces) {
+  if (INTERACTIVE && p.only_interactive_forces) {
     axn = ia.IA_x; ayn = ia.IA_y;
   } else {
-    axn = -KID_GRAVITY * ssh_x + wave_rad * uwave;
-    ayn = -KID_GRAVITY * ssh_y + wave_rad * vwave;
-    if (INTERACTIVE) { axn = axn + ia.IA_x; ayn = ayn + ia.IA_y; }
-    axn = axn + f_cori * vveln;
-    ayn = ayn - f_cori * uveln;
+    axn = fma(f_cori, vveln, ax_expl);
+    ayn = fma(-f_cori, uveln, ay_expl);
   }
-  bxn = ax - (axn / 2); byn = ay - (ayn / 2);
+  bxn = fma(axn, -0.5, ax); byn = fma(ayn, -0.5, ay);
   uveln_out = uveln; vveln_out = vveln;
   if (p.override_iceberg_velocities) { ax = 0.0; ay = 0.0; axn = 0.0; ayn = 0.0; bxn = 0.0; byn = 0.0; }
 }
@@ -306,7 +351,7 @@ __device__ __forceinline__ bool adjust_index_and_ground(const DevGrid& g, const 
 __device__ __forceinline__ void swap_d(double& x, double& y) { double t = x; x = y; y = t; }
 __device__ __forceinline__ void rolling(const DevParams& p, double& Tn, double& Wn, double& Ln) {
   const double Delta = 6.0;
-  double Dn = (p.rho_bergs / KID_RHO_SEAWATER) * Tn;
+  double Dn = p.rho_ratio * Tn;
   if (Dn > 0.) {
     if ((!p.use_updated_rolling_scheme) && (p.tip_parameter < 999.)) {
       if (fmax(Wn, Ln) < sqrt(0.92 * (Dn * Dn) + 58.32 * Dn)) {
@@ -397,53 +442,57 @@ __device__ __noinline__ void thermo_fl_bits(const DevParams& p, double thickness
   f.dMfl = Mfl - Mnew_fl;
 }
 
-// thermodynamics of one berg, I:2896-3296.  `area` = grd%area(i,j) (caller has
-// checked != 0), n_bonds_eff = N_bonds of I:2928-2944.
-__device__ __forceinline__ int thermo_berg(const DevParams& p, const Env& e, double uvel, double vvel,
-                                           double area, double N_bonds, ThermoState& s, ThermoFlux& fx) {
+// x**c for x >= 0 (0**c = 0 for c > 0): exp(c*log x)
+__device__ __forceinline__ double pow_c(double x, double c) { return exp(c * log(x)); }
+
+// thermodynamics of one berg, I:2896-3296.  e.rarea = 1/grd%area(i,j) (caller has checked the
+// cell is not dry), N_bonds per I:2928-2944.
+__device__ __forceinline__ int thermo_berg(const DevParams& p, const EnvThermo& e, double uvel, double vvel,
+                                           double N_bonds, ThermoState& s, ThermoFlux& fx) {
   const double perday = 1. / 86400.;
   double dt = p.dt;
   double SST = e.sst;
   double IC = fmin(1., e.cn + p.sicn_shift);
   double M = s.mass, T = s.thickness, W = s.width, L = s.length;
   double Vol = T * W * L;
-  double dvo = sqrt((uvel - e.uo) * (uvel - e.uo) + (vvel - e.vo) * (vvel - e.vo));
-  double dva = sqrt((e.ua - e.uo) * (e.ua - e.uo) + (e.va - e.vo) * (e.va - e.vo));
-  double Ss = 1.5 * sqrt(dva) + 0.1 * dva;            // dva**0.5
-  double dvo08 = pow(dvo, 0.8);
+  double M_Vol = M / Vol;
+  double dvo = KID_HYPOT(uvel - e.uo, vvel - e.vo);
+  double dva = KID_HYPOT(e.ua - e.uo, e.va - e.vo);
+  double Ss = fma(1.5, sqrt(dva), 0.1 * dva);           // dva**0.5
+  double dvo08 = pow_c(dvo, 0.8);
   double Mv = fmax(7.62e-3 * SST + 1.29e-3 * (SST * SST), 0.) * perday;
-  double Mb = fmax(0.58 * dvo08 * (SST + 4.0) / pow(L, 0.2), 0.) * perday;
-  double Me = fmax(1. / 12. * (SST + 2.) * Ss * (1 + cos(p.pi * (IC * IC * IC))), 0.) * perday;
+  double Mb = fmax(0.58 * dvo08 * (SST + 4.0) * pow_c(L, -0.2), 0.) * perday;
+  double IC3 = IC * IC * IC;
+  double wave_ic = (IC3 == 0.) ? 2. : (1 + cos(p.pi * IC3));   // cos(0) = 1
+  double Me = fmax(1. / 12. * (SST + 2.) * Ss * wave_ic, 0.) * perday;
   double Mv_fl = 0., Me_fl = 0.;
   if (s.mass_of_fl_bits > 0.) { Mv_fl = Mv; Me_fl = Me; }
   if (p.set_melt_rates_to_zero) { Mv = 0.0; Mb = 0.0; Me = 0.0; }
-  double Tn, nVol, Mnew1, Mnew2, Mnew, dMb, dMv, dMe, dM, Ln1 = 0, Wn1 = 0, Ln, Wn;
+  double Tn, Mnew1, Mnew2, Mnew, dMb, dMv, dMe, dM, Ln1 = 0, Wn1 = 0, Ln, Wn;
   if (p.use_operator_splitting) {
+    // the mass differences below cancel to ~1e-6 of the mass: each (nVol/Vol)*M keeps the
+    // reference's own rounding sequence so that dMe (hence the bergy bits) agrees to 1e-10
     Tn = fmax(T - Mb * dt, 0.);
-    nVol = Tn * W * L;
-    Mnew1 = (nVol / Vol) * M;
+    Mnew1 = ((Tn * W * L) / Vol) * M;
     dMb = M - Mnew1;
     Ln1 = fmax(L - Mv * dt, 0.);
     Wn1 = fmax(W - Mv * dt, 0.);
-    nVol = Tn * Wn1 * Ln1;
-    Mnew2 = (nVol / Vol) * M;
+    Mnew2 = ((Tn * Wn1 * Ln1) / Vol) * M;
     dMv = Mnew1 - Mnew2;
     Ln = fmax(Ln1 - Me * dt, 0.);
     Wn = fmax(Wn1 - Me * dt, 0.);
-    nVol = Tn * Wn * Ln;
-    Mnew = (nVol / Vol) * M;
+    Mnew = ((Tn * Wn * Ln) / Vol) * M;
     dMe = Mnew2 - Mnew;
     dM = M - Mnew;
   } else {
     Ln = fmax(L - (Mv + Me) * (dt), 0.);
     Wn = fmax(W - (Mv + Me) * (dt), 0.);
     Tn = fmax(T - Mb * (dt), 0.);
-    nVol = Tn * Wn * Ln;
-    Mnew = (nVol / Vol) * M;
+    Mnew = ((Tn * Wn * Ln) / Vol) * M;
     dM = M - Mnew;
-    dMb = (M / Vol) * (W * L) * Mb * dt;
-    dMe = (M / Vol) * (T * (W + L)) * Me * dt;
-    dMv = (M / Vol) * (T * (W + L)) * Mv * dt;
+    dMb = M_Vol * (W * L) * Mb * dt;
+    dMe = M_Vol * (T * (W + L)) * Me * dt;
+    dMv = M_Vol * (T * (W + L)) * Mv * dt;
   }
   if (p.footloose) {
     if (s.fl_k >= 0) {
@@ -481,8 +530,12 @@ __device__ __forceinline__ int thermo_berg(const DevParams& p, const Env& e, dou
     dMbitsE = p.bergy_bit_erosion_fraction * dMe;
     nMbits = Mbits + dMbitsE;
     double Lbits = fmin(fmin(L, W), fmin(T, 40.));
-    double Abits = (Mbits / p.rho_bergs) / Lbits;
-    double Mbb = fmax(0.58 * dvo08 * (SST + 2.0) / pow(Lbits, 0.2), 0.) * perday;
+    // Abits=(Mbits/rho)/Lbits; Mbb=rho*Abits*rate: the bergy-bit melt in kg/s, rate ~ Lbits**-0.2
+    double rpow, rLbits;
+    if (Lbits == 40.) { rpow = p.rpow40_02; rLbits = 1. / 40.; }
+    else { rpow = pow_c(Lbits, -0.2); rLbits = 1. / Lbits; }
+    double Abits = (Mbits * p.r_rho_bergs) * rLbits;
+    double Mbb = fmax(0.58 * dvo08 * (SST + 2.0) * rpow, 0.) * perday;
     Mbb = p.rho_bergs * Abits * Mbb;
     dMbitsM = fmin(Mbb * dt, nMbits);
     nMbits = nMbits - dMbitsM;
@@ -505,41 +558,30 @@ __device__ __forceinline__ int thermo_berg(const DevParams& p, const Env& e, dou
     dMbitsE = 0.; dMbitsM = 0.; nMbits = s.mass_of_bits;
     dMbitsE_fl = 0.; dMbitsM_fl = 0.; nMbits_fl = s.mass_of_fl_bergy_bits;
   }
-  // grid contributions I:3116-3199
+  // grid contributions I:3116-3199: X/dt/area*mass_scaling = X*k
   {
     double ms = s.mass_scaling;
-    double melt = (dM - (dMbitsE - dMbitsM) + dMfl - (dMbitsE_fl - dMbitsM_fl)) / dt;
-    fx.floating_melt = melt / area * ms;
-    melt = melt * s.heat_density;
-    fx.calving_hflx = melt / area * ms;
-    fx.net_heat = melt * ms * dt;
-    melt = dM / dt;
-    fx.berg_melt = melt / area * ms;
-    melt = (dMbitsE + dMbitsE_fl) / dt;
-    fx.bergy_src = melt / area * ms;
-    melt = (dMbitsM + dMbitsM_fl) / dt;
-    fx.bergy_melt = melt / area * ms;
-    melt = dMfl / dt;
-    fx.fl_bits_melt = melt / area * ms;
+    double k = p.rdt * e.rarea * ms;
+    double melt = (dM - (dMbitsE - dMbitsM) + dMfl - (dMbitsE_fl - dMbitsM_fl));
+    fx.floating_melt = melt * k;
+    double hk = s.heat_density * k;
+    fx.calving_hflx = melt * hk;
+    fx.net_heat = melt * s.heat_density * ms;              // melt/dt*heat_density*ms*dt
+    fx.berg_melt = dM * k;
+    fx.bergy_src = (dMbitsE + dMbitsE_fl) * k;
+    fx.bergy_melt = (dMbitsM + dMbitsM_fl) * k;
+    fx.fl_bits_melt = dMfl * k;
     fx.fl_parent_melt = fx.fl_child_melt = fx.melt_buoy = fx.melt_eros = fx.melt_conv = 0.;
     fx.melt_buoy_fl = fx.melt_eros_fl = fx.melt_conv_fl = 0.;
     if (p.melt_diagnostics) {
       if (s.fl_k >= 0) {
-        melt = (dM - (dMbitsE - dMbitsM)) / dt; fx.fl_parent_melt = melt / area * ms;
-        melt = (dMfl - (dMbitsE_fl - dMbitsM_fl)) / dt; fx.fl_child_melt = melt / area * ms;
-        melt = dMb / dt; fx.melt_buoy = melt / area * ms;
-        melt = dMe / dt; fx.melt_eros = melt / area * ms;
-        melt = dMv / dt; fx.melt_conv = melt / area * ms;
-        if (dMfl > 0) {
-          melt = fl.dMb_fl / dt; fx.melt_buoy_fl = melt / area * ms;
-          melt = fl.dMe_fl / dt; fx.melt_eros_fl = melt / area * ms;
-          melt = fl.dMv_fl / dt; fx.melt_conv_fl = melt / area * ms;
-        }
+        fx.fl_parent_melt = (dM - (dMbitsE - dMbitsM)) * k;
+        fx.fl_child_melt = (dMfl - (dMbitsE_fl - dMbitsM_fl)) * k;
+        fx.melt_buoy = dMb * k; fx.melt_eros = dMe * k; fx.melt_conv = dMv * k;
+        if (dMfl > 0) { fx.melt_buoy_fl = fl.dMb_fl * k; fx.melt_eros_fl = fl.dMe_fl * k; fx.melt_conv_fl = fl.dMv_fl * k; }
       } else {
-        melt = (dM - (dMbitsE - dMbitsM)) / dt; fx.fl_child_melt = melt / area * ms;
-        melt = dMb / dt; fx.melt_buoy_fl = melt / area * ms;
-        melt = dMe / dt; fx.melt_eros_fl = melt / area * ms;
-        melt = dMv / dt; fx.melt_conv_fl = melt / area * ms;
+        fx.fl_child_melt = (dM - (dMbitsE - dMbitsM)) * k;
+        fx.melt_buoy_fl = dMb * k; fx.melt_eros_fl = dMe * k; fx.melt_conv_fl = dMv * k;
       }
     }
   }
@@ -569,7 +611,7 @@ __device__ __forceinline__ int thermo_berg(const DevParams& p, const Env& e, dou
       s.fl_k = -1.;
       s.start_year = p.current_year;
       s.start_day = p.current_yearday;
-      fx.fl_bits_src = -(s.mass * s.mass_scaling / (dt * area));
+      fx.fl_bits_src = -(s.mass * s.mass_scaling * p.rdt * e.rarea);
       return TH_BECAME_FL;
     }
     return TH_DELETE;

@@ -106,6 +106,8 @@ def assert_bergs_match(got, want, rtol=RTOL, names=COMPARE_F64, context=""):
         e = rel_err(g[k], w[k])
         # accelerations and velocities are sums with cancellation: compare against the field's scale
         floor = 1e-13 * max(np.max(np.abs(w[k])), 1e-300) if k in ("axn", "ayn", "bxn", "byn", "uvel", "vvel", "uvel_prev", "vvel_prev") else 0.0
+        if k in ("xi", "yj"):   # fractions of a cell in [0,1): the tolerance is relative to the cell, not to xi
+            floor = rtol
         bad = (e > rtol) & (np.abs(g[k] - w[k]) > floor)
         worst[k] = float(e.max()) if len(e) else 0.0
         assert not bad.any(), f"{context}: {k} rel err {e[bad].max():.3e} at id {g['id'][np.nonzero(bad)[0][:3]]}"
