@@ -17,6 +17,9 @@
 namespace kid {
 
 #define KID_BLOCK 128
+#ifndef KID_MINBLOCKS
+#define KID_MINBLOCKS 5
+#endif
 
 // ------------------------------------------------------------------ helpers
 __device__ __forceinline__ double shfl_down_d(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
@@ -94,28 +97,88 @@ __device__ __forceinline__ int route_berg(const DevGrid& g, const DevParams& p, 
 // per-berg scatter payload collected by the fused kernel
 struct Scatter { long long key; ThermoFlux fx; };
 
+#ifndef KID_SCATTER_MODE
+#define KID_SCATTER_MODE 3
+#endif
+
+// run-sequential variant: every lane parks its value in shared memory, the head lane of each
+// run adds the run up in lane order (deterministic) and issues one atomic
+__device__ __forceinline__ void seg_scatter_smem(double* __restrict__ fld, long long key, double v, const SegInfo& s,
+                                                 double* __restrict__ sh /* 32 doubles of this warp */) {
+  if (!__any_sync(0xffffffffu, v != 0.)) return;
+  int lane = threadIdx.x & 31;
+  sh[lane] = v;
+  __syncwarp();
+  if (s.head && key >= 0) {
+    double t = v;
+    for (int k = lane + 1; k < s.seg_end; k++) t += sh[k];
+    if (t != 0.) atomicAdd(&fld[key], t);
+  }
+  __syncwarp();
+}
+
 template <bool FOOTLOOSE, bool DIAG>
 __device__ __forceinline__ void scatter_fluxes(const DevGrid& g, const Scatter& sc) {
+#if KID_SCATTER_MODE == 1 || KID_SCATTER_MODE == 3
+  // Adaptive aggregation (mode 3): a warp whose 32 bergs all sit in one cell (dense populations,
+  // the store is cell-sorted) reduces each flux with a butterfly and issues ONE atomic per field;
+  // a warp that straddles cells issues one reduction (RED.ADD.F64) per berg and field, which at
+  // ~13 bergs per cell is cheaper than a segmented shuffle tree (profiles/r1 notes).
+  {
+    long long k0 = __shfl_sync(0xffffffffu, sc.key, 0);
+    bool uniform = (KID_SCATTER_MODE == 3) && __all_sync(0xffffffffu, sc.key == k0);
+    double v[5] = {sc.fx.floating_melt, sc.fx.calving_hflx, sc.fx.berg_melt, sc.fx.bergy_src, sc.fx.bergy_melt};
+    double* f[5] = {g.floating_melt, g.calving_hflx, g.berg_melt, g.bergy_src, g.bergy_melt};
+    if (uniform) {
+      if (k0 >= 0) {
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+          double t = v[q];
+          if (!__any_sync(0xffffffffu, t != 0.)) continue;
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) t += shfl_down_d(t, d);
+          if ((threadIdx.x & 31) == 0 && t != 0.) atomicAdd(&f[q][k0], t);
+        }
+      }
+    } else if (sc.key >= 0) {
+#pragma unroll
+      for (int q = 0; q < 5; q++)
+        if (v[q] != 0.) atomicAdd(&f[q][sc.key], v[q]);
+    }
+  }
+  SegInfo si; si.seg_end = 32; si.rounds = 0; si.head = false;
+#define KID_SEG(fld, v) seg_scatter(fld, sc.key, v, si)
+  if (FOOTLOOSE || DIAG) si = seg_info(sc.key);
+#else
   SegInfo si = seg_info(sc.key);
-  seg_scatter(g.floating_melt, sc.key, sc.fx.floating_melt, si);
-  seg_scatter(g.calving_hflx, sc.key, sc.fx.calving_hflx, si);
-  seg_scatter(g.berg_melt, sc.key, sc.fx.berg_melt, si);
-  seg_scatter(g.bergy_src, sc.key, sc.fx.bergy_src, si);
-  seg_scatter(g.bergy_melt, sc.key, sc.fx.bergy_melt, si);
+#if KID_SCATTER_MODE == 2
+  __shared__ double sh_all[KID_BLOCK];
+  double* sh = sh_all + (threadIdx.x & ~31);
+#define KID_SEG(fld, v) seg_scatter_smem(fld, sc.key, v, si, sh)
+#else
+#define KID_SEG(fld, v) seg_scatter(fld, sc.key, v, si)
+#endif
+  KID_SEG(g.floating_melt, sc.fx.floating_melt);
+  KID_SEG(g.calving_hflx, sc.fx.calving_hflx);
+  KID_SEG(g.berg_melt, sc.fx.berg_melt);
+  KID_SEG(g.bergy_src, sc.fx.bergy_src);
+  KID_SEG(g.bergy_melt, sc.fx.bergy_melt);
+#endif
   if (FOOTLOOSE) {
-    seg_scatter(g.fl_bits_melt, sc.key, sc.fx.fl_bits_melt, si);
-    seg_scatter(g.fl_bits_src, sc.key, sc.fx.fl_bits_src, si);
+    KID_SEG(g.fl_bits_melt, sc.fx.fl_bits_melt);
+    KID_SEG(g.fl_bits_src, sc.fx.fl_bits_src);
   }
   if (DIAG) {
-    seg_scatter(g.fl_parent_melt, sc.key, sc.fx.fl_parent_melt, si);
-    seg_scatter(g.fl_child_melt, sc.key, sc.fx.fl_child_melt, si);
-    seg_scatter(g.melt_buoy, sc.key, sc.fx.melt_buoy, si);
-    seg_scatter(g.melt_eros, sc.key, sc.fx.melt_eros, si);
-    seg_scatter(g.melt_conv, sc.key, sc.fx.melt_conv, si);
-    seg_scatter(g.melt_buoy_fl, sc.key, sc.fx.melt_buoy_fl, si);
-    seg_scatter(g.melt_eros_fl, sc.key, sc.fx.melt_eros_fl, si);
-    seg_scatter(g.melt_conv_fl, sc.key, sc.fx.melt_conv_fl, si);
+    KID_SEG(g.fl_parent_melt, sc.fx.fl_parent_melt);
+    KID_SEG(g.fl_child_melt, sc.fx.fl_child_melt);
+    KID_SEG(g.melt_buoy, sc.fx.melt_buoy);
+    KID_SEG(g.melt_eros, sc.fx.melt_eros);
+    KID_SEG(g.melt_conv, sc.fx.melt_conv);
+    KID_SEG(g.melt_buoy_fl, sc.fx.melt_buoy_fl);
+    KID_SEG(g.melt_eros_fl, sc.fx.melt_eros_fl);
+    KID_SEG(g.melt_conv_fl, sc.fx.melt_conv_fl);
   }
+#undef KID_SEG
 }
 
 // thermodynamics of the berg in slot s located at (i,j,xi,yj) moving with (uvel,vvel);
@@ -173,7 +236,7 @@ __device__ __forceinline__ int thermo_slot(const DevGrid& g, const DevBergs& b, 
 // ------------------------------------------------------------ fused step
 // One thread per slot.  MODE 0: dynamics + migration routing + thermodynamics.
 template <bool FOOTLOOSE, bool DIAG>
-__global__ void __launch_bounds__(KID_BLOCK)
+__global__ void __launch_bounds__(KID_BLOCK, KID_MINBLOCKS)
 k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
        const __grid_constant__ DevParams p, DevCounters* __restrict__ cnt, long long n_slots) {
   long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -185,7 +248,7 @@ k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
   sc.fx.fl_bits_melt = sc.fx.fl_bits_src = sc.fx.net_heat = 0.;
   sc.fx.fl_parent_melt = sc.fx.fl_child_melt = sc.fx.melt_buoy = sc.fx.melt_eros = sc.fx.melt_conv = 0.;
   sc.fx.melt_buoy_fl = sc.fx.melt_eros_fl = sc.fx.melt_conv_fl = 0.;
-  bool melted = false, became_fl = false, bounced = false, speeding = false, left = false, moved_cell = false;
+  bool melted = false, became_fl = false, bounced = false, speeding = false, left = false;
   if (owned) {
     const double dt = p.dt, dt_2 = 0.5 * dt;
     int i = b.ine[s], j = b.jne[s];
@@ -237,9 +300,7 @@ k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
         double u2 = uvel2 * dxdl1, v2 = vvel2 * dydl;
         lonn = lon + (dt * u2); latn = lat + (dt * v2);
       }
-      int i_old = i, j_old = j;
       bounced = adjust_index_and_ground(g, p, lonn, latn, i, j, xi, yj, &cnt->error_flags, &cnt->warn_adjust);
-      moved_cell = (i != i_old) || (j != j_old);
       lon = lonn; lat = latn;
       b.f64[C_UVEL_PREV][s] = uvel_prev; b.f64[C_VVEL_PREV][s] = vvel_prev;
       b.f64[C_AXN][s] = axn; b.f64[C_AYN][s] = ayn; b.f64[C_BXN][s] = bxn; b.f64[C_BYN][s] = byn;
@@ -264,17 +325,21 @@ k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
     }
   }
   scatter_fluxes<FOOTLOOSE, DIAG>(g, sc);
-  warp_count_add(&cnt->nbergs_melted, melted);
-  if (FOOTLOOSE) warp_count_add(&cnt->nbergs_calved_fl, became_fl);
-  warp_count_add(&cnt->n_bounced, bounced);
-  warp_count_add(&cnt->nspeeding, speeding);
-  warp_count_add(&cnt->n_leavers, left);
-  warp_count_add(&cnt->n_cell_moves, moved_cell);
+  // event counters: one vote decides whether the warp has anything to report at all
+  if (__any_sync(0xffffffffu, melted | bounced | speeding | left)) {
+    warp_count_add(&cnt->nbergs_melted, melted);
+    if (FOOTLOOSE) warp_count_add(&cnt->nbergs_calved_fl, became_fl);
+    warp_count_add(&cnt->n_bounced, bounced);
+    warp_count_add(&cnt->nspeeding, speeding);
+    warp_count_add(&cnt->n_leavers, left);
+  }
   // net_heat_to_ocean I:3130
   double nh = sc.fx.net_heat;
+  if (__any_sync(0xffffffffu, nh != 0.)) {
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) nh += shfl_down_d(nh, d);
-  if ((threadIdx.x & 31) == 0 && nh != 0.) atomicAdd(&cnt->net_heat_to_ocean, nh);
+    for (int d = 16; d > 0; d >>= 1) nh += shfl_down_d(nh, d);
+    if ((threadIdx.x & 31) == 0 && nh != 0.) atomicAdd(&cnt->net_heat_to_ocean, nh);
+  }
 }
 
 // thermodynamics alone over [s0, s1): bergs flagged BF_ARRIVAL (migration) or, with

@@ -21,6 +21,35 @@ namespace kid {
 
 struct Env { double uo, vo, ui, vi, ua, va, ssh_x, ssh_y, sst, sss, cn, hi, od; };
 
+// Reciprocal and square root for the drag/melt-rate arithmetic: hardware seed (MUFU.RCP64H /
+// MUFU.RSQ64H, ~20 bits) refined by Newton / Goldschmidt steps to ~1 ulp, without the IEEE
+// corner-case paths of `/` and sqrt() (operands here are masses, lengths, speeds: positive,
+// normal range).  Geometry and the mass-difference sequence keep IEEE `/`.
+#ifndef KID_IEEE_DIVSQRT
+__device__ __forceinline__ double rcp_nr(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
+__device__ __forceinline__ double sqrt_nr(double x) {
+  if (!(x > 1.e-300)) return 0.;          // speeds/lengths: 0 stays 0 (and NaN is not expected here)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double g = x * y, h = 0.5 * y;
+  double r = fma(-g, h, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  r = fma(-g, h, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  return fma(fma(-g, g, x), h, g);
+}
+#else
+__device__ __forceinline__ double rcp_nr(double x) { return 1. / x; }
+__device__ __forceinline__ double sqrt_nr(double x) { return sqrt(x); }
+#endif
+
 // accumulated interaction terms of interactive_force (I:480): IA_x, IA_y, P_ia_*, P_ia_times_u_*
 struct IAcc { double IA_x, IA_y, P11, P12, P21, P22, Pu_x, Pu_y; };
 
@@ -149,7 +178,7 @@ __device__ __forceinline__ void accel_core(const DevParams& p, double M, double 
   double v_star = fma(ayn, (dt * 0.5), vvel0);
   double uo = e.uo, vo = e.vo, ui = e.ui, vi = e.vi, ua = e.ua, va = e.va;
   double ssh_x = e.ssh_x, ssh_y = e.ssh_y, hi = e.hi, od = e.od;
-  double rM = 1. / M;
+  double rM = rcp_nr(M);
   double D = p.rho_ratio * T;
   double F = T - D;
   hi = fmin(hi, D);
@@ -174,9 +203,9 @@ __device__ __forceinline__ void accel_core(const DevParams& p, double M, double 
   // Cr0*min(max(0,(L-Lcutoff)/((Ltop-Lcutoff)+1e-30)),1): the quotient only matters strictly inside (0,1)
   double cr_num = L - Lcutoff, cr_den = (Ltop - Lcutoff) + 1.e-30;
   double Cr = (cr_num >= cr_den) ? Cr0 : ((cr_num <= 0.) ? 0. : Cr0 * (cr_num / cr_den));
-  double wave_rad = 0.5 * KID_RHO_SEAWATER * rM * Cr * KID_GRAVITY * ampl * fmin(ampl, F) * (2. * W * L) / (W + L);
-  wmod = sqrt(fma(ua, ua, va * va));
-  if (wmod != 0.) { double rw = 1. / wmod; uwave = ua * rw; vwave = va * rw; }
+  double wave_rad = 0.5 * KID_RHO_SEAWATER * rM * Cr * KID_GRAVITY * ampl * fmin(ampl, F) * (2. * W * L) * rcp_nr(W + L);
+  wmod = sqrt_nr(fma(ua, ua, va * va));
+  if (wmod != 0.) { double rw = rcp_nr(wmod); uwave = ua * rw; vwave = va * rw; }
   else { uwave = 0.; vwave = 0.; wave_rad = 0.; }
   double WL = W * L;
   double c_ocn = KID_RHO_SEAWATER * rM * p.ocean_drag_scale * (0.5 * KID_CD_WV * dragfrac * W * (D_hi) + KID_CD_WH * WL);
@@ -194,7 +223,7 @@ __device__ __forceinline__ void accel_core(const DevParams& p, double M, double 
   double us = uvel0, vs = vvel0;
   // the velocity-at-start halves of the drag magnitudes are the same in both iterations, and in
   // the first one uveln = uvel0 so that 0.5*(d0+d0) = d0 exactly
-#define KID_HYPOT(a, b) sqrt(fma((a), (a), (b) * (b)))
+#define KID_HYPOT(a, b) sqrt_nr(fma((a), (a), (b) * (b)))
   double d0_ocn = KID_HYPOT(uvel0 - uo, vvel0 - vo);
   double d0_atm = KID_HYPOT(uvel0 - ua, vvel0 - va);
   double d0_ice = KID_HYPOT(uvel0 - ui, vvel0 - vi);
@@ -236,7 +265,7 @@ __device__ __forceinline__ void accel_core(const DevParams& p, double M, double 
         A21 = A21 + (dt * ia.P21); A22 = A22 + (dt * ia.P22);
       }
     }
-    double detA = 1. / fma(A11, A22, -(A12 * A21));
+    double detA = rcp_nr(fma(A11, A22, -(A12 * A21)));
     ax = detA * fma(A22, RHS_x, -(A12 * RHS_y));
     ay = detA * fma(A11, RHS_y, -(A21 * RHS_x));
     uveln = fma(dt, ax, u_star);
@@ -442,8 +471,25 @@ __device__ __noinline__ void thermo_fl_bits(const DevParams& p, double thickness
   f.dMfl = Mfl - Mnew_fl;
 }
 
-// x**c for x >= 0 (0**c = 0 for c > 0): exp(c*log x)
-__device__ __forceinline__ double pow_c(double x, double c) { return exp(c * log(x)); }
+// x**(-0.2) for x > 0 (I:2917 L**0.2, dvo**0.8 = dvo*dvo**(-0.2)): single-precision seed
+// (MUFU lg2/ex2, ~1e-6 relative) and two Newton steps on y^-5 = x, y <- y*(6 - x*y^5)/5, which
+// converge quadratically to fp64 rounding (~3e-16 relative).
+__device__ __forceinline__ double pow_m02(double x) {
+#ifdef KID_LIBM_POW
+  return exp(-0.2 * log(x));
+#else
+  double y = (double)__powf((float)x, -0.2f);
+#pragma unroll
+  for (int it = 0; it < 2; it++) {
+    double y2 = y * y;
+    double y5 = y2 * y2 * y;
+    y = (y * 0.2) * fma(-x, y5, 6.0);
+  }
+  return y;
+#endif
+}
+// x**0.8 for x >= 0
+__device__ __forceinline__ double pow_08(double x) { return (x > 1.e-30) ? x * pow_m02(x) : 0.; }
 
 // thermodynamics of one berg, I:2896-3296.  e.rarea = 1/grd%area(i,j) (caller has checked the
 // cell is not dry), N_bonds per I:2928-2944.
@@ -458,10 +504,10 @@ __device__ __forceinline__ int thermo_berg(const DevParams& p, const EnvThermo& 
   double M_Vol = M / Vol;
   double dvo = KID_HYPOT(uvel - e.uo, vvel - e.vo);
   double dva = KID_HYPOT(e.ua - e.uo, e.va - e.vo);
-  double Ss = fma(1.5, sqrt(dva), 0.1 * dva);           // dva**0.5
-  double dvo08 = pow_c(dvo, 0.8);
+  double Ss = fma(1.5, sqrt_nr(dva), 0.1 * dva);           // dva**0.5
+  double dvo08 = pow_08(dvo);
   double Mv = fmax(7.62e-3 * SST + 1.29e-3 * (SST * SST), 0.) * perday;
-  double Mb = fmax(0.58 * dvo08 * (SST + 4.0) * pow_c(L, -0.2), 0.) * perday;
+  double Mb = fmax(0.58 * dvo08 * (SST + 4.0) * pow_m02(L), 0.) * perday;
   double IC3 = IC * IC * IC;
   double wave_ic = (IC3 == 0.) ? 2. : (1 + cos(p.pi * IC3));   // cos(0) = 1
   double Me = fmax(1. / 12. * (SST + 2.) * Ss * wave_ic, 0.) * perday;
@@ -533,7 +579,7 @@ __device__ __forceinline__ int thermo_berg(const DevParams& p, const EnvThermo& 
     // Abits=(Mbits/rho)/Lbits; Mbb=rho*Abits*rate: the bergy-bit melt in kg/s, rate ~ Lbits**-0.2
     double rpow, rLbits;
     if (Lbits == 40.) { rpow = p.rpow40_02; rLbits = 1. / 40.; }
-    else { rpow = pow_c(Lbits, -0.2); rLbits = 1. / Lbits; }
+    else { rpow = pow_m02(Lbits); rLbits = 1. / Lbits; }
     double Abits = (Mbits * p.r_rho_bergs) * rLbits;
     double Mbb = fmax(0.58 * dvo08 * (SST + 2.0) * rpow, 0.) * perday;
     Mbb = p.rho_bergs * Abits * Mbb;
