@@ -35,6 +35,7 @@ struct kid_handle {
   DevBergs b;
   CalvingTables ct;
   int nid = 0, njd = 0, nic = 0, njc = 0;
+  int num_sms = 148;
   long long n2 = 0;
   long long capacity = 0;
   long long n_slots = 0;            // host mirror of the append cursor
@@ -423,6 +424,8 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
 
   // ---- berg store
   h->capacity = capacity > 0 ? capacity : ((long long)1 << 20);
+  h->capacity = (h->capacity + 2 * KID_BLOCK - 1) / KID_BLOCK * KID_BLOCK;   // whole tiles: the bulk copies of k_step read full tiles
+  h->num_sms = prop.multiProcessorCount;
   if (h->capacity > 2000000000LL) return fail(h, KID_ERR_ARG, "kid_init: capacity must be < 2^31");
   DevBergs& b = h->b;
   memset(&b, 0, sizeof(b));

@@ -187,7 +187,8 @@ __device__ __forceinline__ void scatter_fluxes(const DevGrid& g, const Scatter& 
 template <bool FOOTLOOSE>
 __device__ __forceinline__ int thermo_slot(const DevGrid& g, const DevBergs& b, const DevParams& p, long long s,
                                            uint8_t flags, int i, int j, double xi, double yj, double uvel,
-                                           double vvel, double M, double T, double W, double L, Scatter& sc,
+                                           double vvel, double M, double T, double W, double L, double mass_scaling,
+                                           double mass_of_bits, double heat_density, Scatter& sc,
                                            DevCounters* cnt) {
   size_t cidx = gidx(g, i, j);
   EnvThermo e;
@@ -197,9 +198,9 @@ __device__ __forceinline__ int thermo_slot(const DevGrid& g, const DevBergs& b, 
   if (e.rarea == 0.) { atomicOr(&cnt->error_flags, (unsigned)KID_DEVERR_GROUNDED); return TH_KEEP; }
   ThermoState st;
   st.mass = M; st.thickness = T; st.width = W; st.length = L;
-  st.mass_scaling = b.f64[C_MASS_SCALING][s];
-  st.mass_of_bits = b.f64[C_MASS_OF_BITS][s];
-  st.heat_density = b.f64[C_HEAT_DENSITY][s];
+  st.mass_scaling = mass_scaling;
+  st.mass_of_bits = mass_of_bits;
+  st.heat_density = heat_density;
   if (FOOTLOOSE) {
     st.mass_of_fl_bits = b.f64[C_MASS_OF_FL_BITS][s];
     st.mass_of_fl_bergy_bits = b.f64[C_MASS_OF_FL_BERGY_BITS][s];
@@ -234,14 +235,126 @@ __device__ __forceinline__ int thermo_slot(const DevGrid& g, const DevBergs& b, 
 }
 
 // ------------------------------------------------------------ fused step
-// One thread per slot.  MODE 0: dynamics + migration routing + thermodynamics.
+// One thread per berg slot; each warp is independent (no block-level synchronisation).  Memory
+// latency is the first-order cost of this kernel (profiles/r1 notes): every column load is issued
+// before the first use, the gathers of a berg's grid records depend only on (ine,jne) and are
+// issued or prefetched as soon as those arrive, so a warp pays two DRAM/L2 round trips
+// (columns, then grid records) instead of one per routine.
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// what one berg brings into the step
+struct BergIn {
+  double lon, lat, uvel, vvel, axn, ayn, bxn, byn, xi, yj, M, T, W, L, mass_scaling, mass_of_bits, heat_density;
+  int i, j;
+  uint8_t flags;
+};
+
+// evolve_icebergs (I:7081) + send_bergs_to_other_pes (F:2997) + thermodynamics (I:2844) for one berg
+template <bool FOOTLOOSE>
+__device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, const DevParams& p,
+                                          DevCounters* __restrict__ cnt, long long s, const BergIn& in, Scatter& sc,
+                                          bool& melted, bool& became_fl, bool& bounced, bool& speeding, bool& left) {
+  const double dt = p.dt, dt_2 = 0.5 * dt;
+  uint8_t flags = in.flags;
+  int i = in.i, j = in.j;
+  double lon = in.lon, lat = in.lat, uvel = in.uvel, vvel = in.vvel, xi = in.xi, yj = in.yj;
+  double M = in.M, T = in.T, W = in.W, L = in.L;
+  if (!(flags & BF_STATIC)) {
+    double axn = in.axn, ayn = in.ayn, bxn = in.bxn, byn = in.byn;
+    // ---- verlet_stepping I:7203-7328
+    double uvel_prev = uvel - dt_2 * bxn;
+    double vvel_prev = vvel - dt_2 * byn;
+    double uvel3 = uvel + (dt_2 * axn);
+    double vvel3 = vvel + (dt_2 * ayn);
+    Env e;
+    if (!interp_flds(g, p, i, j, xi, yj, e)) atomicOr(&cnt->error_flags, 64u);
+    // sin and cos of the latitude: Coriolis (I:2043-2047) and the metric (I:462-477)
+    double sin_lat = 0., cos_lat = 1.;
+    if (p.grid_is_latlon) sincos(p.pi_180 * lat, &sin_lat, &cos_lat);
+    double f_cori = (p.grid_is_latlon && !p.use_f_plane) ? p.omega2 * sin_lat : p.f_cori_plane;
+    double ax1, ay1, un_l, vn_l;
+    IAcc ia0 = {0., 0., 0., 0., 0., 0., 0., 0.};
+    accel_core<false>(p, M, T, W, L, f_cori, uvel, vvel, dt, e, 1.0, ia0,
+                      [](double, double, IAcc&) {}, ax1, ay1, axn, ayn, bxn, byn, un_l, vn_l);
+    if ((p.speed_limit > 0.) || (p.speed_limit == -1.)) {   // I:2304-2323: only the ticket survives
+      double speed = sqrt(un_l * un_l + vn_l * vn_l);
+      if (speed > 0.) {
+        size_t c = gidx(g, i, j);
+        double loc_dx = fmin(0.5 * (g.dx[c] + g.dx[c - g.nid]), 0.5 * (g.dy[c] + g.dy[c - 1]));
+        double new_speed = loc_dx / dt * p.speed_limit;
+        if (new_speed < speed && p.speed_limit > 0.) speeding = true;
+      }
+    }
+    bool tang = (lat > 89.) && p.grid_is_latlon;
+    double uveln, vveln;
+    if (tang) tang_velocity(p, lon, uvel3, vvel3, ax1, ay1, dt, uveln, vveln);
+    else { uveln = uvel3 + (dt * ax1); vveln = vvel3 + (dt * ay1); }
+    if (p.override_iceberg_velocities) { uveln = p.u_override; vveln = p.v_override; }
+    uvel = uveln; vvel = vveln;      // evolve_icebergs I:7157-7162
+    // ---- update_verlet_position I:7684-7764 (uses the NEW velocity and accelerations)
+    double uvel2 = uvel + (dt_2 * axn) + (dt_2 * bxn);
+    double vvel2 = vvel + (dt_2 * ayn) + (dt_2 * byn);
+    double lonn, latn;
+    if (tang) {
+      tang_position(p, lon, lat, uvel2, vvel2, dt, lonn, latn);
+    } else {
+      double dxdl1 = 1., dydl = 1.;
+      if (p.grid_is_latlon) { dxdl1 = p.r180_pi / (p.Rearth * cos_lat); dydl = p.dlat_dy; }
+      double u2 = uvel2 * dxdl1, v2 = vvel2 * dydl;
+      lonn = lon + (dt * u2); latn = lat + (dt * v2);
+    }
+    bounced = adjust_index_and_ground(g, p, lonn, latn, i, j, xi, yj, &cnt->error_flags, &cnt->warn_adjust);
+    lon = lonn; lat = latn;
+    b.f64[C_UVEL_PREV][s] = uvel_prev; b.f64[C_VVEL_PREV][s] = vvel_prev;
+    b.f64[C_AXN][s] = axn; b.f64[C_AYN][s] = ayn; b.f64[C_BXN][s] = bxn; b.f64[C_BYN][s] = byn;
+    b.f64[C_UVEL][s] = uvel; b.f64[C_VVEL][s] = vvel;
+    b.f64[C_LON][s] = lon; b.f64[C_LAT][s] = lat;
+  }
+  // ---- send_bergs_to_other_pes, F:2997
+  int route = 0;
+  if (i > g.iec || i < g.isc || j > g.jec || j < g.jsc)
+    route = route_berg(g, p, lon, lat, i, j, xi, yj, &cnt->error_flags, &cnt->n_wrapped);
+  if (!(flags & BF_STATIC) || route != 0) {
+    b.f64[C_XI][s] = xi; b.f64[C_YJ][s] = yj;
+    b.ine[s] = i; b.jne[s] = j;
+  }
+  if (route == 1) { left = true; b.flags[s] = flags | BF_LEAVER; }
+  else if (route == 2) { b.flags[s] = 0; }
+  else {
+    // ---- thermodynamics I:2844-3300 at the new position
+    int outcome = thermo_slot<FOOTLOOSE>(g, b, p, s, flags, i, j, xi, yj, uvel, vvel, M, T, W, L, in.mass_scaling,
+                                         in.mass_of_bits, in.heat_density, sc, cnt);
+    if (outcome == TH_DELETE) { melted = true; b.flags[s] = 0; }
+    else if (outcome == TH_BECAME_FL) { melted = true; became_fl = true; }
+  }
+}
+
 template <bool FOOTLOOSE, bool DIAG>
 __global__ void __launch_bounds__(KID_BLOCK, KID_MINBLOCKS)
 k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
        const __grid_constant__ DevParams p, DevCounters* __restrict__ cnt, long long n_slots) {
   long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  uint8_t flags = (s < n_slots) ? b.flags[s] : (uint8_t)0;
-  bool owned = (flags & BF_ALIVE) && !(flags & BF_HALO);
+  const bool in_range = s < n_slots;
+  const long long sl = in_range ? s : 0;          // out-of-range lanes read slot 0 and are masked by flags
+  // all column loads are issued unconditionally, ahead of the flags test (dead slots are rare and
+  // only live until the next sort)
+  BergIn in;
+  in.flags = b.flags[sl];
+  in.i = b.ine[sl]; in.j = b.jne[sl];
+  in.lon = b.f64[C_LON][sl]; in.lat = b.f64[C_LAT][sl];
+  in.uvel = b.f64[C_UVEL][sl]; in.vvel = b.f64[C_VVEL][sl];
+  in.axn = b.f64[C_AXN][sl]; in.ayn = b.f64[C_AYN][sl]; in.bxn = b.f64[C_BXN][sl]; in.byn = b.f64[C_BYN][sl];
+  in.xi = b.f64[C_XI][sl]; in.yj = b.f64[C_YJ][sl];
+  in.M = b.f64[C_MASS][sl]; in.T = b.f64[C_THICKNESS][sl]; in.W = b.f64[C_WIDTH][sl]; in.L = b.f64[C_LENGTH][sl];
+  in.mass_scaling = b.f64[C_MASS_SCALING][sl]; in.mass_of_bits = b.f64[C_MASS_OF_BITS][sl];
+  in.heat_density = b.f64[C_HEAT_DENSITY][sl];
+  if (!in_range) in.flags = 0;
+  bool owned = (in.flags & BF_ALIVE) && !(in.flags & BF_HALO);
+  if (owned && cell_on_pe(g, in.i, in.j)) {
+    // corner positions of the berg's cell (pos_within_cell, a few hundred instructions from now)
+    size_t ne = gidx(g, in.i, in.j);
+    prefetch_l1(&g.lonlat[ne - 1]); prefetch_l1(&g.lonlat[ne - (size_t)g.nid - 1]);
+  }
   Scatter sc;
   sc.key = -1;
   sc.fx.floating_melt = sc.fx.calving_hflx = sc.fx.berg_melt = sc.fx.bergy_src = sc.fx.bergy_melt = 0.;
@@ -249,81 +362,7 @@ k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
   sc.fx.fl_parent_melt = sc.fx.fl_child_melt = sc.fx.melt_buoy = sc.fx.melt_eros = sc.fx.melt_conv = 0.;
   sc.fx.melt_buoy_fl = sc.fx.melt_eros_fl = sc.fx.melt_conv_fl = 0.;
   bool melted = false, became_fl = false, bounced = false, speeding = false, left = false;
-  if (owned) {
-    const double dt = p.dt, dt_2 = 0.5 * dt;
-    int i = b.ine[s], j = b.jne[s];
-    double lon = b.f64[C_LON][s], lat = b.f64[C_LAT][s];
-    double uvel = b.f64[C_UVEL][s], vvel = b.f64[C_VVEL][s];
-    double xi = b.f64[C_XI][s], yj = b.f64[C_YJ][s];
-    double M = b.f64[C_MASS][s], T = b.f64[C_THICKNESS][s], W = b.f64[C_WIDTH][s], L = b.f64[C_LENGTH][s];
-    if (!(flags & BF_STATIC)) {
-      double axn = b.f64[C_AXN][s], ayn = b.f64[C_AYN][s], bxn = b.f64[C_BXN][s], byn = b.f64[C_BYN][s];
-      // ---- verlet_stepping I:7203-7328
-      double uvel_prev = uvel - dt_2 * bxn;
-      double vvel_prev = vvel - dt_2 * byn;
-      double uvel3 = uvel + (dt_2 * axn);
-      double vvel3 = vvel + (dt_2 * ayn);
-      Env e;
-      if (!interp_flds(g, p, i, j, xi, yj, e)) atomicOr(&cnt->error_flags, 64u);
-      // sin and cos of the latitude: Coriolis (I:2043-2047) and the metric (I:462-477)
-      double sin_lat = 0., cos_lat = 1.;
-      if (p.grid_is_latlon) sincos(p.pi_180 * lat, &sin_lat, &cos_lat);
-      double f_cori = (p.grid_is_latlon && !p.use_f_plane) ? p.omega2 * sin_lat : p.f_cori_plane;
-      double ax1, ay1, un_l, vn_l;
-      IAcc ia0 = {0., 0., 0., 0., 0., 0., 0., 0.};
-      accel_core<false>(p, M, T, W, L, f_cori, uvel, vvel, dt, e, 1.0, ia0,
-                        [](double, double, IAcc&) {}, ax1, ay1, axn, ayn, bxn, byn, un_l, vn_l);
-      if ((p.speed_limit > 0.) || (p.speed_limit == -1.)) {   // I:2304-2323: only the ticket survives
-        double speed = sqrt(un_l * un_l + vn_l * vn_l);
-        if (speed > 0.) {
-          size_t c = gidx(g, i, j);
-          double loc_dx = fmin(0.5 * (g.dx[c] + g.dx[c - g.nid]), 0.5 * (g.dy[c] + g.dy[c - 1]));
-          double new_speed = loc_dx / dt * p.speed_limit;
-          if (new_speed < speed && p.speed_limit > 0.) speeding = true;
-        }
-      }
-      bool tang = (lat > 89.) && p.grid_is_latlon;
-      double uveln, vveln;
-      if (tang) tang_velocity(p, lon, uvel3, vvel3, ax1, ay1, dt, uveln, vveln);
-      else { uveln = uvel3 + (dt * ax1); vveln = vvel3 + (dt * ay1); }
-      if (p.override_iceberg_velocities) { uveln = p.u_override; vveln = p.v_override; }
-      uvel = uveln; vvel = vveln;      // evolve_icebergs I:7157-7162
-      // ---- update_verlet_position I:7684-7764 (uses the NEW velocity and accelerations)
-      double uvel2 = uvel + (dt_2 * axn) + (dt_2 * bxn);
-      double vvel2 = vvel + (dt_2 * ayn) + (dt_2 * byn);
-      double lonn, latn;
-      if (tang) {
-        tang_position(p, lon, lat, uvel2, vvel2, dt, lonn, latn);
-      } else {
-        double dxdl1 = 1., dydl = 1.;
-        if (p.grid_is_latlon) { dxdl1 = p.r180_pi / (p.Rearth * cos_lat); dydl = p.dlat_dy; }
-        double u2 = uvel2 * dxdl1, v2 = vvel2 * dydl;
-        lonn = lon + (dt * u2); latn = lat + (dt * v2);
-      }
-      bounced = adjust_index_and_ground(g, p, lonn, latn, i, j, xi, yj, &cnt->error_flags, &cnt->warn_adjust);
-      lon = lonn; lat = latn;
-      b.f64[C_UVEL_PREV][s] = uvel_prev; b.f64[C_VVEL_PREV][s] = vvel_prev;
-      b.f64[C_AXN][s] = axn; b.f64[C_AYN][s] = ayn; b.f64[C_BXN][s] = bxn; b.f64[C_BYN][s] = byn;
-      b.f64[C_UVEL][s] = uvel; b.f64[C_VVEL][s] = vvel;
-      b.f64[C_LON][s] = lon; b.f64[C_LAT][s] = lat;
-    }
-    // ---- send_bergs_to_other_pes, F:2997
-    int route = 0;
-    if (i > g.iec || i < g.isc || j > g.jec || j < g.jsc)
-      route = route_berg(g, p, lon, lat, i, j, xi, yj, &cnt->error_flags, &cnt->n_wrapped);
-    if (!(flags & BF_STATIC) || route != 0) {
-      b.f64[C_XI][s] = xi; b.f64[C_YJ][s] = yj;
-      b.ine[s] = i; b.jne[s] = j;
-    }
-    if (route == 1) { left = true; b.flags[s] = flags | BF_LEAVER; }
-    else if (route == 2) { b.flags[s] = 0; }
-    else {
-      // ---- thermodynamics I:2844-3300 at the new position
-      int outcome = thermo_slot<FOOTLOOSE>(g, b, p, s, flags, i, j, xi, yj, uvel, vvel, M, T, W, L, sc, cnt);
-      if (outcome == TH_DELETE) { melted = true; b.flags[s] = 0; }
-      else if (outcome == TH_BECAME_FL) { melted = true; became_fl = true; }
-    }
-  }
+  if (owned) step_berg<FOOTLOOSE>(g, b, p, cnt, s, in, sc, melted, became_fl, bounced, speeding, left);
   scatter_fluxes<FOOTLOOSE, DIAG>(g, sc);
   // event counters: one vote decides whether the warp has anything to report at all
   if (__any_sync(0xffffffffu, melted | bounced | speeding | left)) {
@@ -367,7 +406,9 @@ k_thermo_range(const __grid_constant__ DevGrid g, const __grid_constant__ DevBer
       double xi = b.f64[C_XI][s], yj = b.f64[C_YJ][s];
       double uvel = b.f64[C_UVEL][s], vvel = b.f64[C_VVEL][s];
       double M = b.f64[C_MASS][s], T = b.f64[C_THICKNESS][s], W = b.f64[C_WIDTH][s], L = b.f64[C_LENGTH][s];
-      int outcome = thermo_slot<FOOTLOOSE>(g, b, p, s, flags, i, j, xi, yj, uvel, vvel, M, T, W, L, sc, cnt);
+      int outcome = thermo_slot<FOOTLOOSE>(g, b, p, s, flags, i, j, xi, yj, uvel, vvel, M, T, W, L,
+                                           b.f64[C_MASS_SCALING][s], b.f64[C_MASS_OF_BITS][s],
+                                           b.f64[C_HEAT_DENSITY][s], sc, cnt);
       if (outcome == TH_DELETE) { melted = true; flags = 0; }
       else if (outcome == TH_BECAME_FL) { melted = true; became_fl = true; }
     }

@@ -91,21 +91,28 @@ __device__ __forceinline__ bool interp_flds(const DevGrid& g, const DevParams& p
   }
   const CellRec c0 = ce[ne];
   e.sst = c0.sst; e.sss = c0.sss; e.cn = c0.cn; e.hi = c0.hi; e.od = c0.od;
+  // SSH slopes, I:4830-4860.  The neighbour picked depends on xi,yj >= 0.5; the loads do not
+  // wait for that decision: the address is selected, not the branch.
+  const bool yn = yj >= 0.5, xe = xi >= 0.5;
+  const size_t rj = yn ? ne + nid : ne - nid;      // row above or below
+  const size_t ri = xe ? ne + 1 : ne - 1;          // column east or west
+  const double ddx_j0 = c0.ddx, ddx_j0w = ce[ne - 1].ddx, ddx_j1 = ce[rj].ddx, ddx_j1w = ce[rj - 1].ddx;
+  const double ddy_i0 = c0.ddy, ddy_i0s = ce[ne - nid].ddy, ddy_i1 = ce[ri].ddy, ddy_i1s = ce[ri - nid].ddy;
   double hxp, hxm;
-  if (yj >= 0.5) {
-    hxp = fma((yj - 0.5), ce[ne + nid].ddx, (1.5 - yj) * c0.ddx);
-    hxm = fma((yj - 0.5), ce[ne + nid - 1].ddx, (1.5 - yj) * ce[ne - 1].ddx);
+  if (yn) {
+    hxp = fma((yj - 0.5), ddx_j1, (1.5 - yj) * ddx_j0);
+    hxm = fma((yj - 0.5), ddx_j1w, (1.5 - yj) * ddx_j0w);
   } else {
-    hxp = fma((yj + 0.5), c0.ddx, (0.5 - yj) * ce[ne - nid].ddx);
-    hxm = fma((yj + 0.5), ce[ne - 1].ddx, (0.5 - yj) * ce[ne - nid - 1].ddx);
+    hxp = fma((yj + 0.5), ddx_j0, (0.5 - yj) * ddx_j1);
+    hxm = fma((yj + 0.5), ddx_j0w, (0.5 - yj) * ddx_j1w);
   }
   double ssh_x = fma(xi, hxp, (1. - xi) * hxm);
-  if (xi >= 0.5) {
-    hxp = fma((xi - 0.5), ce[ne + 1].ddy, (1.5 - xi) * c0.ddy);
-    hxm = fma((xi - 0.5), ce[ne - nid + 1].ddy, (1.5 - xi) * ce[ne - nid].ddy);
+  if (xe) {
+    hxp = fma((xi - 0.5), ddy_i1, (1.5 - xi) * ddy_i0);
+    hxm = fma((xi - 0.5), ddy_i1s, (1.5 - xi) * ddy_i0s);
   } else {
-    hxp = fma((xi + 0.5), c0.ddy, (0.5 - xi) * ce[ne - 1].ddy);
-    hxm = fma((xi + 0.5), ce[ne - nid].ddy, (0.5 - xi) * ce[ne - nid - 1].ddy);
+    hxp = fma((xi + 0.5), ddy_i0, (0.5 - xi) * ddy_i1);
+    hxm = fma((xi + 0.5), ddy_i0s, (0.5 - xi) * ddy_i1s);
   }
   double ssh_y = fma(yj, hxp, (1. - yj) * hxm);
   rotate(uo, vo, cos_rot, sin_rot);

@@ -70,7 +70,7 @@ rows = list(csv.reader(open(src_csv)))
 hdr = rows[1]
 ci = {h: i for i, h in enumerate(hdr)}
 body = rows[2:2 + len(inst)]
-agg = collections.defaultdict(lambda: [0, 0, 0, 0])
+agg = collections.defaultdict(lambda: [0, 0, 0, 0, 0, 0, 0])
 tot_i = tot_s = 0
 nwarps = None
 for k, r in enumerate(body):
@@ -82,10 +82,14 @@ for k, r in enumerate(body):
     key = ("[sub] " + lab[:60]) if lab else func_of(f, l)
     a = agg[key]
     a[0] += ex; a[1] += sm; a[2] += 1
+    a[3] += int(r[ci['stall_long_sb']] or 0); a[4] += int(r[ci['stall_wait']] or 0); a[5] += int(r[ci['stall_no_inst']] or 0); a[6] += int(r[ci['stall_short_sb']] or 0)
     tot_i += ex; tot_s += sm
 print(f"static instr={len(inst)} executed warp-instr={tot_i} ({tot_i / nwarps:.0f} per warp, {nwarps} warps) samples={tot_s}")
-print(f"{'function':62s} {'exec%':>6s} {'/warp':>7s} {'smp%':>6s} {'static':>6s}")
+print(f"{'function':62s} {'exec%':>6s} {'/warp':>7s} {'smp%':>6s} {'static':>6s} {'longsb%':>7s} {'wait%':>6s} {'noinst%':>7s} {'shortsb%':>8s}")
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0]):
     if a[0] == 0 and a[2] < 50:
         continue
-    print(f"{k:62s} {100 * a[0] / tot_i:6.1f} {a[0] / nwarps:7.0f} {100 * a[1] / max(tot_s, 1):6.1f} {a[2]:6d}")
+    try:
+        print(f"{k:62s} {100 * a[0] / tot_i:6.1f} {a[0] / nwarps:7.0f} {100 * a[1] / max(tot_s, 1):6.1f} {a[2]:6d} {100 * a[3] / max(tot_s, 1):7.1f} {100 * a[4] / max(tot_s, 1):6.1f} {100 * a[5] / max(tot_s, 1):7.1f} {100 * a[6] / max(tot_s, 1):8.1f}")
+    except BrokenPipeError:
+        break
