@@ -63,3 +63,56 @@ enum PackSlot : int {
 };
 
 }  // namespace kid
+
+namespace kid {
+
+// layout of the ranks over the global grid (mpp_define_layout / mpp_compute_extent restated in
+// kid_define_domain): rank = px + lx*py owns columns xs[px]..xs[px+1]-1 and rows ys[py]..ys[py+1]-1
+#define KID_MAX_DIV 64
+struct DevLayout {
+  int32_t lx, ly, gni, gnj, cyclic_x, cyclic_y, rank, nranks;
+  int32_t xs[KID_MAX_DIV + 1], ys[KID_MAX_DIV + 1];
+};
+
+// owner of global cell (i,j); -1 = outside the model (NULL_PE).  i may be one period off.
+__device__ __forceinline__ int owner_rank(const DevLayout& L, int i, int j) {
+  if (i < 1 || i > L.gni) { if (!L.cyclic_x) return -1; i = ((i - 1) % L.gni + L.gni) % L.gni + 1; }
+  if (j < 1 || j > L.gnj) { if (!L.cyclic_y) return -1; j = ((j - 1) % L.gnj + L.gnj) % L.gnj + 1; }
+  int px = 0, py = 0;
+  while (px + 1 < L.lx && i >= L.xs[px + 1]) px++;
+  while (py + 1 < L.ly && j >= L.ys[py + 1]) py++;
+  return px + L.lx * py;
+}
+
+// pass 1: how many bergs leave for each rank (send_bergs_to_other_pes F:3024-3050, all directions at once)
+__global__ void k_count_leavers(const __grid_constant__ DevLayout L, const uint8_t* __restrict__ flags,
+                                const int32_t* __restrict__ ine, const int32_t* __restrict__ jne, long long n_slots,
+                                int32_t* __restrict__ counts /* [nranks] */) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  if (!(flags[s] & BF_LEAVER)) return;
+  int d = owner_rank(L, ine[s], jne[s]);
+  if (d >= 0 && d != L.rank) atomicAdd(&counts[d], 1);
+}
+
+// pass 2: pack_berg_into_buffer2 (F:3250) into the per-destination regions; the slot is freed
+__global__ void k_pack_leavers(const __grid_constant__ DevLayout L, const __grid_constant__ DevBergs b,
+                               long long n_slots, const int32_t* __restrict__ offsets /* [nranks] */,
+                               int32_t* __restrict__ cursor /* [nranks], zeroed */, double* __restrict__ sendbuf) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  uint8_t f = b.flags[s];
+  if (!(f & BF_LEAVER)) return;
+  int d = owner_rank(L, b.ine[s], b.jne[s]);
+  b.flags[s] = 0;
+  if (d < 0 || d == L.rank) return;          // left the model through an open boundary
+  int pos = offsets[d] + atomicAdd(&cursor[d], 1);
+  double* rec = sendbuf + (size_t)pos * PACK_W;
+#pragma unroll
+  for (int c = 0; c < C_NBASE; c++) rec[PK_F64_0 + c] = b.f64[c][s];
+  rec[PK_ID] = __longlong_as_double(b.id[s]);
+  rec[PK_INE_JNE] = __longlong_as_double(((long long)(unsigned)b.ine[s] << 32) | (unsigned)b.jne[s]);
+  rec[PK_YEAR_FLAGS] = __longlong_as_double(((long long)(unsigned)b.start_year[s] << 32) | (unsigned)(f & ~BF_LEAVER));
+}
+
+}  // namespace kid
