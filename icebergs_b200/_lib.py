@@ -21,6 +21,7 @@ EXPORTS = [
     "kid_kernel_launches", "kid_get_counters", "kid_get_grid_field", "kid_stock", "kid_incr_mass",
     "kid_sort_bergs", "kid_synchronize", "kid_end", "kid_last_error", "kid_version",
     "kid_nccl_unique_id", "kid_nccl_init", "kid_nccl_destroy", "kid_pack_width",
+    "kid_local_comm_create", "kid_local_comm_destroy", "kid_owner_rank",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -70,6 +71,9 @@ def load() -> C.CDLL:
     lib.kid_nccl_init.argtypes = [C.POINTER(_vp), C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     lib.kid_nccl_destroy.argtypes = [_vp]
     lib.kid_pack_width.argtypes = []
+    lib.kid_local_comm_create.argtypes = [C.POINTER(_vp), C.c_int32]
+    lib.kid_local_comm_destroy.argtypes = [_vp]
+    lib.kid_owner_rank.argtypes = [C.POINTER(D.KidDomain), C.c_int32, C.c_int32]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int:  # default: set explicit int32 status

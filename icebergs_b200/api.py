@@ -75,14 +75,20 @@ class Domain:
         return cls(d)
 
     @classmethod
-    def decomposed(cls, gni, gnj, rank, nranks, halo=4, cyclic_x=True, cyclic_y=False, device=0, comm=None):
+    def decomposed(cls, gni, gnj, rank, nranks, halo=4, cyclic_x=True, cyclic_y=False, device=0, comm=None,
+                   comm_kind=D.KID_COMM_NCCL):
         d = D.KidDomain()
         rc = lib().kid_define_domain(C.byref(d), gni, gnj, halo, int(cyclic_x), int(cyclic_y), rank, nranks, device)
         if rc:
             raise KidFatal(rc, "kid_define_domain failed")
         if comm is not None:
             d.nccl_comm = comm
+            d.comm_kind = comm_kind
         return cls(d)
+
+    def owner_rank(self, i, j) -> int:
+        """Rank that owns global cell (i, j) (-1 = outside the model, NULL_PE)."""
+        return lib().kid_owner_rank(C.byref(self.c), int(i), int(j))
 
     def __getattr__(self, k):
         return getattr(self.c, k)

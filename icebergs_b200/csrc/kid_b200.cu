@@ -61,6 +61,19 @@ struct kid_handle {
   int steps_since_sort = 0, sort_interval = 16, sorted_once = 0;
   int forcing_set = 0;
   long long dirty_appended = 0;
+  // ---- multi-rank (send_bergs_to_other_pes F:2997, mpp_update_domains)
+  DevLayout layout;
+  int comm_kind = 0;
+  void* comm = nullptr;                // ncclComm_t or LocalGroup*
+  int nbr[9];                          // rank in direction dir = (dx+1)+3*(dy+1); -1 = none
+  int32_t *leaver_dest = nullptr, *d_send_counts = nullptr, *d_cursor = nullptr, *d_offsets = nullptr;
+  int32_t *d_all_counts = nullptr, *h_all_counts = nullptr, *h_offsets = nullptr;
+  double *sendbuf = nullptr, *recvbuf = nullptr;
+  long long xbuf_cap = 0;              // bergs each exchange buffer holds
+  double *halo_send = nullptr, *halo_recv = nullptr;
+  long long halo_buf_cells = 0;        // cells x fields each halo buffer holds
+  HaloStrips hs_send, hs_recv;
+  long long n_sent_last = 0, n_recv_last = 0;
   std::string err;
   bool fatal = false;
 };
@@ -252,6 +265,208 @@ static double h_amap(double x, double y, double Lx) {
   return x;
 }
 
+
+// ------------------------------------------------------------------ comm
+// One message of an exchange.  Sends to a peer are posted in the caller's order and the peer's
+// receives from this rank in the same order (NCCL matches them by order, the in-process group by tag).
+struct XMsg { int peer; int tag; double* ptr; long long count; };
+
+static int comm_fail(kid_t* h, const std::string& m) { h->err = m; h->fatal = true; return KID_ERR_COMM; }
+
+static int comm_exchange(kid_t* h, const std::vector<XMsg>& sends, const std::vector<XMsg>& recvs) {
+  const int me = h->d.rank;
+  // messages to self (a rank that is its own cyclic neighbour): plain device copies, matched by tag
+  for (const XMsg& r : recvs) {
+    if (r.peer != me) continue;
+    for (const XMsg& s : sends)
+      if (s.peer == me && s.tag == r.tag) {
+        CK(cudaMemcpyAsync(r.ptr, s.ptr, sizeof(double) * (size_t)std::min(r.count, s.count), cudaMemcpyDeviceToDevice, h->stream));
+        break;
+      }
+  }
+  if (h->comm_kind == KID_COMM_NCCL) {
+    NcclApi& n = nccl();
+    ncclComm_t c = (ncclComm_t)h->comm;
+    bool any = false;
+    for (const XMsg& s : sends) if (s.peer != me && s.count > 0) any = true;
+    for (const XMsg& r : recvs) if (r.peer != me && r.count > 0) any = true;
+    if (!any) return KID_OK;
+    if (n.GroupStart() != ncclSuccess_) return comm_fail(h, "ncclGroupStart failed");
+    int rc = ncclSuccess_;
+    for (const XMsg& s : sends)
+      if (s.peer != me && s.count > 0 && rc == ncclSuccess_) rc = n.Send(s.ptr, (size_t)s.count, ncclFloat64_, s.peer, c, h->stream);
+    for (const XMsg& r : recvs)
+      if (r.peer != me && r.count > 0 && rc == ncclSuccess_) rc = n.Recv(r.ptr, (size_t)r.count, ncclFloat64_, r.peer, c, h->stream);
+    int rc2 = n.GroupEnd();
+    if (rc != ncclSuccess_ || rc2 != ncclSuccess_)
+      return comm_fail(h, std::string("NCCL send/recv failed: ") + (n.GetErrorString ? n.GetErrorString(rc != ncclSuccess_ ? rc : rc2) : "?"));
+    return KID_OK;
+  }
+  // in-process group
+  LocalGroup* G = (LocalGroup*)h->comm;
+  CK(cudaStreamSynchronize(h->stream));                 // my send buffers are complete
+  {
+    std::lock_guard<std::mutex> lk(G->m);
+    G->posted[me].clear();
+    for (const XMsg& s : sends)
+      if (s.peer != me && s.count > 0) G->posted[me].push_back({s.peer, s.tag, s.ptr, sizeof(double) * (size_t)s.count, h->d.device});
+  }
+  if (!G->barrier()) return comm_fail(h, "in-process group: rendezvous failed (a rank did not arrive)");
+  for (const XMsg& r : recvs) {
+    if (r.peer == me || r.count <= 0) continue;
+    const PostedMsg* m = nullptr;
+    { std::lock_guard<std::mutex> lk(G->m);
+      for (const PostedMsg& q : G->posted[r.peer]) if (q.dst == me && q.tag == r.tag) { m = &q; break; } }
+    if (!m || m->bytes != sizeof(double) * (size_t)r.count) return comm_fail(h, "in-process group: message mismatch");
+    if (m->device == h->d.device) CK(cudaMemcpyAsync(r.ptr, m->ptr, m->bytes, cudaMemcpyDeviceToDevice, h->stream));
+    else CK(cudaMemcpyPeerAsync(r.ptr, h->d.device, m->ptr, m->device, m->bytes, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  if (!G->barrier()) return comm_fail(h, "in-process group: rendezvous failed (a rank did not arrive)");
+  return KID_OK;
+}
+
+// every rank's per-destination send counts, gathered on the host: out[src*nranks + dst]
+static int comm_allgather_counts(kid_t* h, const int32_t* d_counts, int32_t* out) {
+  const int nr = h->d.nranks, me = h->d.rank;
+  if (h->comm_kind == KID_COMM_NCCL) {
+    NcclApi& n = nccl();
+    int rc = n.AllGather(d_counts, h->d_all_counts, (size_t)nr, ncclInt32_, (ncclComm_t)h->comm, h->stream);
+    if (rc != ncclSuccess_) return comm_fail(h, std::string("ncclAllGather failed: ") + (n.GetErrorString ? n.GetErrorString(rc) : "?"));
+    CK(cudaMemcpyAsync(out, h->d_all_counts, sizeof(int32_t) * nr * nr, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return KID_OK;
+  }
+  LocalGroup* G = (LocalGroup*)h->comm;
+  CK(cudaMemcpyAsync(out + (size_t)me * nr, d_counts, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  { std::lock_guard<std::mutex> lk(G->m); G->counts[me].assign(out + (size_t)me * nr, out + (size_t)(me + 1) * nr); }
+  if (!G->barrier()) return comm_fail(h, "in-process group: rendezvous failed (a rank did not arrive)");
+  { std::lock_guard<std::mutex> lk(G->m);
+    for (int r = 0; r < nr; r++) for (int q = 0; q < nr; q++) out[(size_t)r * nr + q] = G->counts[r][q]; }
+  if (!G->barrier()) return comm_fail(h, "in-process group: rendezvous failed (a rank did not arrive)");
+  return KID_OK;
+}
+
+static inline int dir_of(int dx, int dy) { return (dx + 1) + 3 * (dy + 1); }
+
+// strips of width w for the 8 directions: what this rank sends (compute cells next to the edge)
+// and where it receives (the halo cells beyond it)
+static void build_strips(kid_t* h, int w, HaloStrips& snd, HaloStrips& rcv) {
+  const KidDomain& d = h->d;
+  long long so = 0, ro = 0;
+  for (int dy = -1; dy <= 1; dy++)
+    for (int dx = -1; dx <= 1; dx++) {
+      int k = dir_of(dx, dy);
+      snd.i0[k] = snd.j0[k] = snd.ni[k] = snd.nj[k] = 0; rcv.i0[k] = rcv.j0[k] = rcv.ni[k] = rcv.nj[k] = 0;
+      snd.off[k] = so; rcv.off[k] = ro;
+      if (k == 4 || h->nbr[k] < 0) continue;
+      snd.ni[k] = rcv.ni[k] = dx ? w : h->nic;
+      snd.nj[k] = rcv.nj[k] = dy ? w : h->njc;
+      snd.i0[k] = dx > 0 ? d.iec - w + 1 : d.isc;
+      snd.j0[k] = dy > 0 ? d.jec - w + 1 : d.jsc;
+      rcv.i0[k] = dx > 0 ? d.iec + 1 : (dx < 0 ? d.isc - w : d.isc);
+      rcv.j0[k] = dy > 0 ? d.jec + 1 : (dy < 0 ? d.jsc - w : d.jsc);
+      so += (long long)snd.ni[k] * snd.nj[k];
+      ro += (long long)rcv.ni[k] * rcv.nj[k];
+    }
+}
+
+// mpp_update_domains of up to 16 data-domain fields, halo width = bergs%grd%halo
+static int halo_exchange(kid_t* h, double* const* fields, int nf) {
+  if (h->d.nranks <= 1 || nf <= 0) return KID_OK;
+  for (int f0 = 0; f0 < nf; f0 += 16) {
+    int m = std::min(16, nf - f0);
+    HaloFields fl;
+    for (int q = 0; q < 16; q++) fl.f[q] = q < m ? fields[f0 + q] : nullptr;
+    HaloStrips snd = h->hs_send, rcv = h->hs_recv;
+    snd.nf = rcv.nf = m;
+    if ((snd.off[8] + (long long)snd.ni[8] * snd.nj[8]) * m > h->halo_buf_cells) return fail(h, KID_ERR_CAPACITY, "kid: halo buffer too small");
+    dim3 grid(64, 9);
+    k_halo_pack<<<grid, 256, 0, h->stream>>>(h->g, snd, fl, h->halo_send, 0); h->launches++;
+    std::vector<XMsg> sends, recvs;
+    for (int k = 0; k < 9; k++) {
+      if (k == 4) continue;
+      if (h->nbr[k] >= 0) sends.push_back({h->nbr[k], k, h->halo_send + snd.off[k] * m, (long long)snd.ni[k] * snd.nj[k] * m});
+      int ok = 8 - k;      // the message a neighbour sent in direction k arrives in my halo on side 8-k
+      if (h->nbr[ok] >= 0) recvs.push_back({h->nbr[ok], k, h->halo_recv + rcv.off[ok] * m, (long long)rcv.ni[ok] * rcv.nj[ok] * m});
+    }
+    int rc = comm_exchange(h, sends, recvs);
+    if (rc) return rc;
+    k_halo_pack<<<grid, 256, 0, h->stream>>>(h->g, rcv, fl, h->halo_recv, 1); h->launches++;
+  }
+  return KID_OK;
+}
+
+// send_bergs_to_other_pes F:2997 between ranks: count, pack, exchange, unpack.  Returns the number
+// of bergs that arrived in n_recv; they occupy slots [n_slots, n_slots + n_recv) flagged BF_ARRIVAL.
+static int exchange_bergs(kid_t* h, long long* n_recv_out) {
+  const int nr = h->d.nranks, me = h->d.rank;
+  *n_recv_out = 0;
+  CK(cudaMemsetAsync(h->d_send_counts, 0, sizeof(int32_t) * nr, h->stream));
+  CK(cudaMemsetAsync(h->d_cursor, 0, sizeof(int32_t) * nr, h->stream));
+  k_leaver_dest<<<32, 256, 0, h->stream>>>(h->layout, h->b.ine, h->b.jne, h->b.leaver_list, h->dcnt, (int32_t)h->b.leaver_cap,
+                                          h->leaver_dest, h->d_send_counts); h->launches++;
+  int rc = comm_allgather_counts(h, h->d_send_counts, h->h_all_counts);
+  if (rc) return rc;
+  long long n_send = 0, n_recv = 0;
+  std::vector<XMsg> sends, recvs;
+  for (int q = 0; q < nr; q++) {
+    h->h_offsets[q] = (int32_t)n_send;
+    long long c = h->h_all_counts[(size_t)me * nr + q];
+    if (c > 0) sends.push_back({q, 100, h->sendbuf + (size_t)n_send * PACK_W, c * PACK_W});
+    n_send += c;
+  }
+  for (int q = 0; q < nr; q++) {
+    long long c = h->h_all_counts[(size_t)q * nr + me];
+    if (c > 0) recvs.push_back({q, 100, h->recvbuf + (size_t)n_recv * PACK_W, c * PACK_W});
+    n_recv += c;
+  }
+  if (n_send > h->xbuf_cap || n_recv > h->xbuf_cap) return fail(h, KID_ERR_CAPACITY, "kid: berg exchange buffer capacity exceeded");
+  if (h->n_slots + n_recv > h->capacity) return fail(h, KID_ERR_CAPACITY, "kid: berg store capacity exceeded by arrivals");
+  CK(cudaMemcpyAsync(h->d_offsets, h->h_offsets, sizeof(int32_t) * nr, cudaMemcpyHostToDevice, h->stream));
+  k_pack_leavers<<<32, 256, 0, h->stream>>>(h->b, h->b.leaver_list, h->leaver_dest, h->dcnt, (int32_t)h->b.leaver_cap, h->d_offsets,
+                                           h->d_cursor, h->sendbuf); h->launches++;
+  CK(cudaMemsetAsync(&h->dcnt->n_leaver_list, 0, sizeof(unsigned long long), h->stream));
+  rc = comm_exchange(h, sends, recvs);
+  if (rc) return rc;
+  if (n_recv > 0) {
+    LAUNCH(h, k_unpack_arrivals, n_recv, 128, h->g, h->b, h->dp, h->dcnt, h->recvbuf, n_recv, h->n_slots);
+    unsigned long long nn = (unsigned long long)(h->n_slots + n_recv);
+    CK(cudaMemcpyAsync(&h->dcnt->n_slots, &nn, sizeof(nn), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // nn is a stack variable
+  }
+  h->n_sent_last = n_send; h->n_recv_last = n_recv;
+  *n_recv_out = n_recv;
+  return KID_OK;
+}
+
+static void fill_layout(DevLayout& L, const KidDomain* d) {
+  memset(&L, 0, sizeof(L));
+  L.lx = std::max(1, d->layout_x); L.ly = std::max(1, d->layout_y);
+  L.gni = d->gni; L.gnj = d->gnj; L.cyclic_x = d->cyclic_x; L.cyclic_y = d->cyclic_y; L.rank = d->rank; L.nranks = d->nranks;
+  for (int k = 0; k <= L.lx && k <= KID_MAX_DIV; k++) L.xs[k] = k * (d->gni / L.lx) + std::min(k, d->gni % L.lx) + 1;
+  for (int k = 0; k <= L.ly && k <= KID_MAX_DIV; k++) L.ys[k] = k * (d->gnj / L.ly) + std::min(k, d->gnj % L.ly) + 1;
+}
+
+extern "C" int32_t kid_owner_rank(const KidDomain* d, int32_t i, int32_t j) {
+  if (!d || d->layout_x > KID_MAX_DIV || d->layout_y > KID_MAX_DIV) return -1;
+  DevLayout L;
+  fill_layout(L, d);
+  return owner_rank(L, i, j);
+}
+
+extern "C" int32_t kid_local_comm_create(void** group, int32_t nranks) {
+  if (!group || nranks < 1) return KID_ERR_ARG;
+  *group = (void*)new LocalGroup(nranks);
+  return KID_OK;
+}
+extern "C" int32_t kid_local_comm_destroy(void* group) {
+  if (!group) return KID_OK;
+  delete (LocalGroup*)group;
+  return KID_OK;
+}
+
 // ------------------------------------------------------------------ init
 extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* dom, int32_t year, double yearday,
                             int64_t capacity, const double* lon, const double* lat, const double* wet,
@@ -285,6 +500,13 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   if (dom->isd != dom->isc - pin->halo || dom->ied != dom->iec + pin->halo || dom->jsd != dom->jsc - pin->halo ||
       dom->jed != dom->jec + pin->halo) { g_init_error = "kid_init: data domain must be compute domain +/- halo"; return KID_ERR_ARG; }
   if (dom->nranks > 1 && !dom->nccl_comm) { g_init_error = "kid_init: nranks>1 needs KidDomain.nccl_comm"; return KID_ERR_ARG; }
+  if (dom->nranks > 1) {
+    if (dom->comm_kind != KID_COMM_NCCL && dom->comm_kind != KID_COMM_LOCAL) { g_init_error = "kid_init: unknown KidDomain.comm_kind"; return KID_ERR_ARG; }
+    if (dom->comm_kind == KID_COMM_NCCL && !nccl().ok()) { g_init_error = "kid_init: libnccl.so.2 could not be loaded"; return KID_ERR_COMM; }
+    if (dom->layout_x < 1 || dom->layout_y < 1 || dom->layout_x * dom->layout_y != dom->nranks || dom->layout_x > KID_MAX_DIV ||
+        dom->layout_y > KID_MAX_DIV) { g_init_error = "kid_init: bad layout"; return KID_ERR_ARG; }
+    if (dom->iec - dom->isc + 1 < pin->halo || dom->jec - dom->jsc + 1 < pin->halo) { g_init_error = "kid_init: a tile must be at least halo cells wide"; return KID_ERR_ARG; }
+  }
 
   kid_t* h = new kid_handle();
   h->p = *pin; h->d = *dom;
@@ -305,6 +527,32 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   h->n2 = (long long)h->nid * h->njd;
   const long long n2 = h->n2;
   const int nid = h->nid, nic = h->nic;
+  // ---- rank layout (mpp_define_layout / mpp_compute_extent as kid_define_domain restates them)
+  {
+    DevLayout& L = h->layout;
+    fill_layout(L, d);
+    int px = d->rank % L.lx, py = d->rank / L.lx;
+    if (d->nranks > 1 && (L.xs[px] != d->isc || L.xs[px + 1] - 1 != d->iec || L.ys[py] != d->jsc || L.ys[py + 1] - 1 != d->jec))
+      return fail(h, KID_ERR_ARG, "kid_init: compute domain does not match the layout (use kid_define_domain)");
+    for (int dy = -1; dy <= 1; dy++)
+      for (int dx = -1; dx <= 1; dx++) {
+        int qx = px + dx, qy = py + dy, r = -1;
+        bool ok = true;
+        if (qx < 0 || qx >= L.lx) { if (d->cyclic_x) qx = (qx + L.lx) % L.lx; else ok = false; }
+        if (qy < 0 || qy >= L.ly) { if (d->cyclic_y) qy = (qy + L.ly) % L.ly; else ok = false; }
+        if (ok) r = qx + L.lx * qy;
+        h->nbr[dir_of(dx, dy)] = (d->nranks > 1) ? r : -1;
+      }
+    h->nbr[4] = -1;
+    h->comm_kind = d->comm_kind; h->comm = d->nccl_comm;
+    if (d->nranks > 1) {
+      build_strips(h, pin->halo, h->hs_send, h->hs_recv);
+      long long cells = h->hs_send.off[8] + (long long)h->hs_send.ni[8] * h->hs_send.nj[8];
+      h->halo_buf_cells = cells * 16;
+      CK(cudaMalloc(&h->halo_send, sizeof(double) * h->halo_buf_cells));
+      CK(cudaMalloc(&h->halo_recv, sizeof(double) * h->halo_buf_cells));
+    }
+  }
   // derived parameters, F:1264, F:1312, F:1483
   KidParams* q = &h->p;
   if (!q->iceberg_bonds_on) q->max_bonds = 0;
@@ -343,6 +591,22 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
     }
   };
   wrap(glon); wrap(glat); wrap(gdy); wrap(gdx); wrap(garea); wrap(gmsk); wrap(gcos); wrap(gsin); wrap(gdepth);
+  if (d->nranks > 1) {
+    // mpp_update_domains of the static fields between ranks (F:1058-1066): through the device
+    std::vector<double>* st[9] = {&glon, &glat, &gdy, &gdx, &garea, &gmsk, &gcos, &gsin, &gdepth};
+    double* dv[9];
+    memset(&h->g, 0, sizeof(h->g));
+    h->g.isd = d->isd; h->g.jsd = d->jsd; h->g.nid = h->nid;
+    for (int k = 0; k < 9; k++) {
+      CK(cudaMalloc(&dv[k], sizeof(double) * n2));
+      CK(cudaMemcpyAsync(dv[k], st[k]->data(), sizeof(double) * n2, cudaMemcpyHostToDevice, h->stream));
+    }
+    int rc = halo_exchange(h, dv, 9);
+    if (rc) return rc;
+    for (int k = 0; k < 9; k++) CK(cudaMemcpyAsync(st[k]->data(), dv[k], sizeof(double) * n2, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < 9; k++) cudaFree(dv[k]);
+  }
   // F:1068-1094: extrapolate lon/lat into halos that no neighbour filled
   for (int j = d->jsc - 1; j >= d->jsd; j--) for (int i = d->isd; i <= d->ied; i++) {
     if (glon[IDX(i, j)] >= big_number) glon[IDX(i, j)] = glon[IDX(i, j + 1)];
@@ -444,6 +708,21 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   CK(cudaMalloc(&h->spare4, 4 * h->capacity));
   CK(cudaMalloc(&h->spare1, h->capacity));
   CK(cudaMalloc(&h->perm, sizeof(int32_t) * h->capacity));
+  if (d->nranks > 1) {
+    const int nr = d->nranks;
+    h->xbuf_cap = std::max<long long>(65536, h->capacity / 8);
+    b.leaver_cap = h->xbuf_cap;
+    CK(cudaMalloc(&b.leaver_list, sizeof(int32_t) * b.leaver_cap));
+    CK(cudaMalloc(&h->leaver_dest, sizeof(int32_t) * b.leaver_cap));
+    CK(cudaMalloc(&h->sendbuf, sizeof(double) * PACK_W * h->xbuf_cap));
+    CK(cudaMalloc(&h->recvbuf, sizeof(double) * PACK_W * h->xbuf_cap));
+    CK(cudaMalloc(&h->d_send_counts, sizeof(int32_t) * nr));
+    CK(cudaMalloc(&h->d_cursor, sizeof(int32_t) * nr));
+    CK(cudaMalloc(&h->d_offsets, sizeof(int32_t) * nr));
+    CK(cudaMalloc(&h->d_all_counts, sizeof(int32_t) * nr * nr));
+    CK(cudaMallocHost(&h->h_all_counts, sizeof(int32_t) * nr * nr));
+    CK(cudaMallocHost(&h->h_offsets, sizeof(int32_t) * nr));
+  }
   CK(cudaMalloc(&h->cell_count, sizeof(int32_t) * n2));
   CK(cudaMalloc(&h->cell_start, sizeof(int32_t) * n2));
   CK(cudaMalloc(&h->cell_fill, sizeof(int32_t) * n2));
@@ -493,6 +772,11 @@ extern "C" int32_t kid_end(kid_t** hp) {
   cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->cell_fill);
   cudaFree(h->scan_sums); cudaFree(h->scan_total); cudaFree(h->dcnt); cudaFree(h->dflags);
   cudaFreeHost(h->hcnt); cudaFreeHost(h->hflags);
+  cudaFree(h->b.leaver_list); cudaFree(h->leaver_dest); cudaFree(h->sendbuf); cudaFree(h->recvbuf);
+  cudaFree(h->d_send_counts); cudaFree(h->d_cursor); cudaFree(h->d_offsets); cudaFree(h->d_all_counts);
+  if (h->h_all_counts) cudaFreeHost(h->h_all_counts);
+  if (h->h_offsets) cudaFreeHost(h->h_offsets);
+  cudaFree(h->halo_send); cudaFree(h->halo_recv);
   for (auto& e : h->ev) cudaEventDestroy(e);
   for (auto& e : h->ev_pool) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
@@ -792,16 +1076,20 @@ static void zero_flux_fields(kid_t* h, bool also_calving) {
   LAUNCH(h, k_zero_fields, h->n2, 256, fl, h->n2);
 }
 
-static void halo_update(kid_t* h, std::initializer_list<double*> fields) {
+static int halo_update(kid_t* h, std::initializer_list<double*> fields) {
   // mpp_update_domains: on one rank that is its own E/W neighbour this is the cyclic
-  // wrap; ranks of a multi-rank layout receive the one-cell ring from the caller
-  // (icebergs_run's (nic+2,njc+2) arguments), which is all the free-drift path reads
-  if (!(h->g.pe_E_self && h->g.pe_W_self)) return;
+  // wrap; between ranks the strips travel (halo_exchange)
+  if (h->d.nranks > 1) {
+    std::vector<double*> v(fields);
+    return halo_exchange(h, v.data(), (int)v.size());
+  }
+  if (!(h->g.pe_E_self && h->g.pe_W_self)) return KID_OK;
   FieldList fl;
   fl.n = 0;
   for (double* f : fields) fl.f[fl.n++] = f;
   long long n = (long long)2 * h->p.halo * h->njc;
   LAUNCH(h, k_halo_wrap_x, n, 128, h->g, fl);
+  return KID_OK;
 }
 
 // forcing ingest I:5203-5383
@@ -822,6 +1110,14 @@ static int ingest_forcing(kid_t* h, const double* calving, const double* uo, con
   for (int k = 0; k < 13; k++)
     if (src[k]) CK(cudaMemcpyAsync(h->in_stage[k], src[k], sizeof(double) * cnt[k], cudaMemcpyHostToDevice, h->stream));
   double** st = h->in_stage;
+  // halo updates: immediate on one rank (cyclic wrap); between ranks the fields are independent of
+  // each other, so all strips travel in ONE exchange before the scrub
+  std::vector<double*> pending;
+  int hu_rc = KID_OK;
+  auto HU = [&](std::initializer_list<double*> f) {
+    if (h->d.nranks > 1) pending.insert(pending.end(), f.begin(), f.end());
+    else if (!hu_rc) hu_rc = halo_update(h, f);
+  };
   zero_flux_fields(h, false);
   CK(cudaMemsetAsync(h->dflags, 0, 2 * sizeof(unsigned long long), h->stream));
   LAUNCH(h, k_copy_in, (long long)nc, 256, g, calving_hflx ? st[9] : nullptr, g.calving_hflx, 0, 1, 0.);
@@ -843,22 +1139,24 @@ static int ingest_forcing(kid_t* h, const double* calving, const double* uo, con
     CK(cudaMemsetAsync(h->tmp_v, 0, sizeof(double) * n2, h->stream));
     LAUNCH(h, k_copy_in, (long long)nc, 256, g, st[5], h->tmp_u, 0, 0, 0.);
     LAUNCH(h, k_copy_in, (long long)nc, 256, g, st[6], h->tmp_v, 0, 0, 0.);
-    halo_update(h, {h->tmp_u, h->tmp_v});
+    { int rc_ = halo_update(h, {h->tmp_u, h->tmp_v}); if (rc_) return rc_; }
     LAUNCH(h, k_stress_to_corners, (long long)(h->nic + 1) * (h->njc + 1), 256, g, h->tmp_u, h->tmp_v,
            stress_stagger == KID_AGRID ? 1 : 0);
   }
-  halo_update(h, {g.uo, g.vo, g.ui, g.vi});
+  HU({g.uo, g.vo, g.ui, g.vi});
   if (!h->p.tau_is_velocity) LAUNCH(h, k_invert_tau, n2, 256, g, n2);
-  halo_update(h, {g.ua, g.va});
+  HU({g.ua, g.va});
   LAUNCH(h, k_copy_in, (long long)nr, 256, g, st[7], g.ssh, 1, 0, 0.);
-  halo_update(h, {g.ssh});
+  HU({g.ssh});
   LAUNCH(h, k_sst_max, (long long)nc, 256, g, st[8], calving ? st[0] : nullptr, h->dflags);
   LAUNCH(h, k_sst_in, (long long)nc, 256, g, st[8], h->dflags);
-  halo_update(h, {g.sst});
+  HU({g.sst});
   LAUNCH(h, k_copy_in, (long long)nr, 256, g, st[10], g.cn, 1, 0, 0.);
   LAUNCH(h, k_copy_in, (long long)nr, 256, g, st[11], g.hi, 1, 0, 0.);
-  halo_update(h, {g.cn, g.hi});
+  HU({g.cn, g.hi});
   LAUNCH(h, k_copy_in, (long long)nc, 256, g, sss ? st[12] : nullptr, g.sss, 0, 0, sss ? 0. : -1.0);
+  if (hu_rc) return hu_rc;
+  if (!pending.empty()) { int rc_ = halo_exchange(h, pending.data(), (int)pending.size()); if (rc_) return rc_; }
   LAUNCH(h, k_scrub, n2, 256, g, n2);
   LAUNCH(h, k_pack_forcing, n2, 256, g, n2);
   CK(cudaMemcpyAsync(h->hflags, h->dflags, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
@@ -900,13 +1198,27 @@ static int step_core(kid_t* h) {
   h->first_call_accum = 0;
   h->visited = 1;
   CK(cudaEventRecord(h->ev[T_MOMENTUM], s));
-  cudaEvent_t e0 = pool_event(h), e1 = pool_event(h), e2 = pool_event(h);
+  cudaEvent_t e0 = pool_event(h), ek = pool_event(h), e1 = pool_event(h), e2 = pool_event(h);
   CK(cudaEventRecord(e0, s));
   if (!h->p.static_icebergs) {
     if (h->p.melt_diagnostics) launch_step<false, true>(h); else launch_step<false, false>(h);
   } else {
     if (h->p.melt_diagnostics) { LAUNCH(h, (k_thermo_range<false, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, 0LL, h->n_slots, 1); }
     else { LAUNCH(h, (k_thermo_range<false, false>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, 0LL, h->n_slots, 1); }
+  }
+  CK(cudaEventRecord(ek, s));
+  if (h->d.nranks > 1) {
+    // send_bergs_to_other_pes F:2997; arrivals do their thermodynamics of this step here (I:5497)
+    long long n_recv = 0;
+    int rc = exchange_bergs(h, &n_recv);
+    if (rc) return rc;
+    if (n_recv > 0) {
+      long long s0 = h->n_slots, s1 = h->n_slots + n_recv;
+      if (h->p.melt_diagnostics) { LAUNCH(h, (k_thermo_range<false, true>), n_recv, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s0, s1, 0); }
+      else { LAUNCH(h, (k_thermo_range<false, false>), n_recv, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s0, s1, 0); }
+      h->n_slots = s1;
+      h->dirty_appended += n_recv;
+    }
   }
   CK(cudaEventRecord(h->ev[T_SORT], s));
   CK(cudaEventRecord(e1, s));
@@ -922,17 +1234,18 @@ static int step_core(kid_t* h) {
 
 // timing[] of the last kid_run / kid_step_resident call, all steps of the call summed:
 // [0] interface (first step only) [1] calving (last step) [2] fused momentum+thermodynamics kernel
-// [5] sort [6] whole call [7] number of steps
+// [3] berg migration between ranks (+ thermodynamics of the arrivals) [5] sort [6] whole call [7] number of steps
 static void collect_timing(kid_t* h, cudaEvent_t first) {
   float ms = 0;
   for (int k = 0; k < 8; k++) h->timing[k] = 0;
   if (cudaEventElapsedTime(&ms, h->ev[T_CALVING], h->ev[T_MOMENTUM]) == cudaSuccess) h->timing[1] = ms;
-  for (int k = 0; k + 2 < h->ev_used; k += 3) {
+  for (int k = 0; k + 3 < h->ev_used; k += 4) {
     if (cudaEventElapsedTime(&ms, h->ev_pool[k], h->ev_pool[k + 1]) == cudaSuccess) h->timing[2] += ms;
-    if (cudaEventElapsedTime(&ms, h->ev_pool[k + 1], h->ev_pool[k + 2]) == cudaSuccess) h->timing[5] += ms;
+    if (cudaEventElapsedTime(&ms, h->ev_pool[k + 1], h->ev_pool[k + 2]) == cudaSuccess) h->timing[3] += ms;
+    if (cudaEventElapsedTime(&ms, h->ev_pool[k + 2], h->ev_pool[k + 3]) == cudaSuccess) h->timing[5] += ms;
     h->timing[7] += 1;
   }
-  if (h->ev_used >= 3 && cudaEventElapsedTime(&ms, first, h->ev_pool[0]) == cudaSuccess) h->timing[0] = ms;
+  if (h->ev_used >= 4 && cudaEventElapsedTime(&ms, first, h->ev_pool[0]) == cudaSuccess) h->timing[0] = ms;
   if (cudaEventElapsedTime(&ms, first, h->ev[T_TOTAL]) == cudaSuccess) h->timing[6] = ms;
   h->ev_used = 0;
   cudaGetLastError();
@@ -1036,6 +1349,7 @@ extern "C" int32_t kid_get_counters(kid_t* h, KidCounters* c) {
   c->nbergs_melted = (int64_t)h->hcnt->nbergs_melted;
   c->nspeeding_tickets = (int64_t)h->hcnt->nspeeding;
   c->n_sent = (int64_t)h->hcnt->n_leavers;
+  c->n_received = (int64_t)h->hcnt->n_wrapped + h->n_recv_last;
   c->n_bounced = (int64_t)h->hcnt->n_bounced;
   c->net_heat_to_ocean = h->hcnt->net_heat_to_ocean;
   c->net_calving_to_bergs = h->hcnt->net_calving_to_bergs;

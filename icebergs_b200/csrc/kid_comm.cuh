@@ -4,7 +4,12 @@
 #pragma once
 #include <dlfcn.h>
 
-#include "kid_device.cuh"
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <vector>
+
+#include "kid_geom.cuh"
 
 namespace kid {
 
@@ -66,6 +71,7 @@ enum PackSlot : int {
 
 namespace kid {
 
+// ---------------------------------------------------------------- layout
 // layout of the ranks over the global grid (mpp_define_layout / mpp_compute_extent restated in
 // kid_define_domain): rank = px + lx*py owns columns xs[px]..xs[px+1]-1 and rows ys[py]..ys[py+1]-1
 #define KID_MAX_DIV 64
@@ -74,8 +80,8 @@ struct DevLayout {
   int32_t xs[KID_MAX_DIV + 1], ys[KID_MAX_DIV + 1];
 };
 
-// owner of global cell (i,j); -1 = outside the model (NULL_PE).  i may be one period off.
-__device__ __forceinline__ int owner_rank(const DevLayout& L, int i, int j) {
+// owner of global cell (i,j); -1 = outside the model (NULL_PE).  i may be any number of periods off.
+__host__ __device__ __forceinline__ int owner_rank(const DevLayout& L, int i, int j) {
   if (i < 1 || i > L.gni) { if (!L.cyclic_x) return -1; i = ((i - 1) % L.gni + L.gni) % L.gni + 1; }
   if (j < 1 || j > L.gnj) { if (!L.cyclic_y) return -1; j = ((j - 1) % L.gnj + L.gnj) % L.gnj + 1; }
   int px = 0, py = 0;
@@ -84,35 +90,140 @@ __device__ __forceinline__ int owner_rank(const DevLayout& L, int i, int j) {
   return px + L.lx * py;
 }
 
-// pass 1: how many bergs leave for each rank (send_bergs_to_other_pes F:3024-3050, all directions at once)
-__global__ void k_count_leavers(const __grid_constant__ DevLayout L, const uint8_t* __restrict__ flags,
-                                const int32_t* __restrict__ ine, const int32_t* __restrict__ jne, long long n_slots,
-                                int32_t* __restrict__ counts /* [nranks] */) {
-  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_slots) return;
-  if (!(flags[s] & BF_LEAVER)) return;
-  int d = owner_rank(L, ine[s], jne[s]);
-  if (d >= 0 && d != L.rank) atomicAdd(&counts[d], 1);
+// ------------------------------------------------- berg migration kernels
+// k_step appended the slot of every berg that left the tile to leaver_list (count in
+// cnt->n_leaver_list).  Pass 1: destination rank of each and the per-destination counts
+// (send_bergs_to_other_pes F:3024-3050, all directions at once: NVSwitch reaches any rank, so
+// the reference's E/W-then-N/S relay F:3103-3106 is not needed).
+__global__ void k_leaver_dest(const __grid_constant__ DevLayout L, const int32_t* __restrict__ ine,
+                              const int32_t* __restrict__ jne, const int32_t* __restrict__ list,
+                              const DevCounters* __restrict__ cnt, int32_t list_cap,
+                              int32_t* __restrict__ dest, int32_t* __restrict__ counts /* [nranks], zeroed */) {
+  long long n = (long long)cnt->n_leaver_list;
+  if (n > list_cap) n = list_cap;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+    int32_t s = list[k];
+    int d = owner_rank(L, ine[s], jne[s]);
+    if (d == L.rank) d = -1;                 // cannot happen (route_berg); never send to self
+    dest[k] = d;
+    if (d >= 0) atomicAdd(&counts[d], 1);
+  }
 }
 
 // pass 2: pack_berg_into_buffer2 (F:3250) into the per-destination regions; the slot is freed
-__global__ void k_pack_leavers(const __grid_constant__ DevLayout L, const __grid_constant__ DevBergs b,
-                               long long n_slots, const int32_t* __restrict__ offsets /* [nranks] */,
+// (delete_iceberg_from_list F:3040)
+__global__ void k_pack_leavers(const __grid_constant__ DevBergs b, const int32_t* __restrict__ list,
+                               const int32_t* __restrict__ dest, const DevCounters* __restrict__ cnt,
+                               int32_t list_cap, const int32_t* __restrict__ offsets /* [nranks] */,
                                int32_t* __restrict__ cursor /* [nranks], zeroed */, double* __restrict__ sendbuf) {
-  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_slots) return;
-  uint8_t f = b.flags[s];
-  if (!(f & BF_LEAVER)) return;
-  int d = owner_rank(L, b.ine[s], b.jne[s]);
-  b.flags[s] = 0;
-  if (d < 0 || d == L.rank) return;          // left the model through an open boundary
-  int pos = offsets[d] + atomicAdd(&cursor[d], 1);
-  double* rec = sendbuf + (size_t)pos * PACK_W;
+  long long n = (long long)cnt->n_leaver_list;
+  if (n > list_cap) n = list_cap;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+    int32_t s = list[k];
+    int d = dest[k];
+    uint8_t f = b.flags[s];
+    b.flags[s] = 0;
+    if (d < 0) continue;                     // left the model through an open boundary
+    int pos = offsets[d] + atomicAdd(&cursor[d], 1);
+    double* rec = sendbuf + (size_t)pos * PACK_W;
 #pragma unroll
-  for (int c = 0; c < C_NBASE; c++) rec[PK_F64_0 + c] = b.f64[c][s];
-  rec[PK_ID] = __longlong_as_double(b.id[s]);
-  rec[PK_INE_JNE] = __longlong_as_double(((long long)(unsigned)b.ine[s] << 32) | (unsigned)b.jne[s]);
-  rec[PK_YEAR_FLAGS] = __longlong_as_double(((long long)(unsigned)b.start_year[s] << 32) | (unsigned)(f & ~BF_LEAVER));
+    for (int c = 0; c < C_NBASE; c++) rec[PK_F64_0 + c] = b.f64[c][s];
+    rec[PK_ID] = __longlong_as_double(b.id[s]);
+    rec[PK_INE_JNE] = __longlong_as_double(((long long)(unsigned)b.ine[s] << 32) | (unsigned)b.jne[s]);
+    rec[PK_YEAR_FLAGS] = __longlong_as_double(((long long)(unsigned)b.start_year[s] << 32) | (unsigned)(f & ~BF_LEAVER));
+  }
 }
+
+// unpack_berg_from_buffer2 (F:3468): the berg keeps its lon/lat, its cell is re-found on this
+// rank's grid (check_and_find_cell F:5973: the sender's indices first -- shifted by one period when
+// the berg crossed the cyclic seam, which is the cell the reference's scan F:6002 finds -- then the
+// wide search F:3640), xi,yj are recomputed (F:3638) and *_old reset (F:3574-3577).  The berg is
+// flagged BF_ARRIVAL: its thermodynamics of this step runs here (k_thermo_range).
+__global__ void k_unpack_arrivals(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
+                                  const __grid_constant__ DevParams p, DevCounters* __restrict__ cnt,
+                                  const double* __restrict__ recvbuf, long long n_recv, long long s0) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_recv) return;
+  long long s = s0 + k;
+  const double* rec = recvbuf + (size_t)k * PACK_W;
+#pragma unroll
+  for (int c = 0; c < C_NBASE; c++) b.f64[c][s] = rec[PK_F64_0 + c];
+  double lon = rec[PK_F64_0 + C_LON], lat = rec[PK_F64_0 + C_LAT];
+  if (b.f64[C_UVEL_OLD]) {
+    b.f64[C_UVEL_OLD][s] = rec[PK_F64_0 + C_UVEL]; b.f64[C_VVEL_OLD][s] = rec[PK_F64_0 + C_VVEL];
+    b.f64[C_LON_OLD][s] = lon; b.f64[C_LAT_OLD][s] = lat;
+  }
+  b.id[s] = __double_as_longlong(rec[PK_ID]);
+  long long ij = __double_as_longlong(rec[PK_INE_JNE]), yf = __double_as_longlong(rec[PK_YEAR_FLAGS]);
+  int i = (int)(ij >> 32), j = (int)(ij & 0xffffffffll);
+  b.start_year[s] = (int32_t)(yf >> 32);
+  uint8_t f = (uint8_t)(yf & 0xff);
+  bool found = false;
+  int oi = i, oj = j;
+  if (cell_on_pe(g, oi, oj)) found = is_point_in_cell(g, p, lon, lat, oi, oj, &cnt->error_flags);
+  if (!found && g.cyclic_x) {
+    oi = (i > g.ied) ? i - g.gni : ((i - 1 < g.isd) ? i + g.gni : i);
+    if (oi != i && cell_on_pe(g, oi, oj)) found = is_point_in_cell(g, p, lon, lat, oi, oj, &cnt->error_flags);
+  }
+  if (!found) found = find_cell_wide(g, p, lon, lat, &oi, &oj, &cnt->error_flags);
+  if (!found) { atomicOr(&cnt->error_flags, (unsigned)KID_DEVERR_LOST_BERG); b.flags[s] = 0; return; }
+  double xi, yj;
+  pos_within_cell(g, p, lon, lat, oi, oj, &xi, &yj, &cnt->error_flags);
+  b.f64[C_XI][s] = xi; b.f64[C_YJ][s] = yj;
+  b.ine[s] = oi; b.jne[s] = oj;
+  b.halo_code[s] = 0;
+  b.flags[s] = (uint8_t)((f | BF_ALIVE | BF_ARRIVAL) & ~(BF_LEAVER | BF_HALO));
+}
+
+// ------------------------------------------------------- halo strips
+// mpp_update_domains (F:1058-1066, I:5321-5355) for a set of data-domain fields: the strip of
+// compute cells next to each of the 8 neighbours is packed, exchanged and written into the
+// matching halo strip.  dir = (dx+1) + 3*(dy+1), dir 4 unused.
+struct HaloStrips {
+  int32_t i0[9], j0[9], ni[9], nj[9];   // strip origin (global indices) and size, per direction
+  long long off[9];                      // offset of the strip in the buffer, in cells (x nf fields)
+  int32_t nf, pad;
+};
+struct HaloFields { double* f[16]; };
+
+__global__ void k_halo_pack(const __grid_constant__ DevGrid g, const __grid_constant__ HaloStrips st,
+                            const __grid_constant__ HaloFields fl, double* __restrict__ buf, int unpack) {
+  int dir = blockIdx.y;
+  if (dir == 4) return;
+  long long ncell = (long long)st.ni[dir] * st.nj[dir];
+  long long n = ncell * st.nf;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+    int q = (int)(k / ncell);
+    long long c = k - (long long)q * ncell;
+    int ii = (int)(c % st.ni[dir]), jj = (int)(c / st.ni[dir]);
+    size_t cell = gidx(g, st.i0[dir] + ii, st.j0[dir] + jj);
+    double* slot = buf + (size_t)st.off[dir] * st.nf + k;
+    if (unpack) fl.f[q][cell] = *slot; else *slot = fl.f[q][cell];
+  }
+}
+
+// ----------------------------------------------------- in-process group
+// Ranks that live in one process (one host thread per rank, e.g. several tiles on one GPU, or a
+// host without NCCL): buffers are exchanged with device-to-device copies after a rendezvous.
+struct PostedMsg { int dst, tag; const void* ptr; size_t bytes; int device; };
+struct LocalGroup {
+  int nranks = 0;
+  std::mutex m;
+  std::condition_variable cv;
+  int waiting = 0;
+  unsigned long long gen = 0;
+  bool failed = false;
+  std::vector<std::vector<PostedMsg>> posted;
+  std::vector<std::vector<int32_t>> counts;
+  explicit LocalGroup(int n) : nranks(n), posted(n), counts(n) {}
+  bool barrier() {
+    std::unique_lock<std::mutex> lk(m);
+    if (failed) return false;
+    unsigned long long g0 = gen;
+    if (++waiting == nranks) { waiting = 0; gen++; cv.notify_all(); return true; }
+    if (!cv.wait_for(lk, std::chrono::seconds(120), [&] { return gen != g0 || failed; })) { failed = true; cv.notify_all(); return false; }
+    return !failed;
+  }
+};
 
 }  // namespace kid

@@ -115,6 +115,8 @@ struct DevBergs {
   int64_t* id;
   int32_t *ine, *jne, *start_year;
   uint8_t *flags, *halo_code;
+  int32_t* leaver_list;       // slots of the bergs that left the tile this step (multi-rank only)
+  int64_t leaver_cap;
 };
 
 // device-side counters (one struct in HBM per handle)
@@ -124,6 +126,7 @@ struct DevCounters {
   unsigned long long n_slots;        // append cursor (high-water mark of used slots)
   unsigned long long n_alive;        // filled by the count kernel
   unsigned long long n_cell_moves;   // bergs whose cell changed this step (sort heuristics)
+  unsigned long long n_leaver_list;  // entries of DevBergs::leaver_list filled this step
   double net_heat_to_ocean, net_calving_to_bergs, net_heat_to_bergs;
   unsigned int error_flags;
   unsigned int warn_adjust;

@@ -318,7 +318,13 @@ __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, c
     b.f64[C_XI][s] = xi; b.f64[C_YJ][s] = yj;
     b.ine[s] = i; b.jne[s] = j;
   }
-  if (route == 1) { left = true; b.flags[s] = flags | BF_LEAVER; }
+  if (route == 1) {
+    left = true;
+    b.flags[s] = flags | BF_LEAVER;
+    unsigned long long k = atomicAdd(&cnt->n_leaver_list, 1ull);      // rare: a berg in a few thousand per step
+    if ((long long)k < b.leaver_cap) b.leaver_list[k] = (int32_t)s;
+    else atomicOr(&cnt->error_flags, (unsigned)KID_DEVERR_CAPACITY);
+  }
   else if (route == 2) { b.flags[s] = 0; }
   else {
     // ---- thermodynamics I:2844-3300 at the new position

@@ -58,6 +58,9 @@ enum {
  * us; the shim maps BGRID_NE/CGRID_NE/AGRID to these)  I:5119-5120 */
 enum { KID_BGRID_NE = 0, KID_CGRID_NE = 1, KID_AGRID = 2 };
 
+/* KidDomain.comm_kind */
+enum { KID_COMM_NCCL = 0, KID_COMM_LOCAL = 1 };
+
 /* stocks, icebergs_stock_pe I:8102 */
 enum { KID_ISTOCK_WATER = 0, KID_ISTOCK_HEAT = 1 };
 
@@ -209,8 +212,8 @@ typedef struct KidDomain {
   int32_t layout_x, layout_y;     /* ranks in i and j; rank = px + layout_x*py */
   int32_t pe_N, pe_S, pe_E, pe_W;
   int32_t device;                 /* CUDA device ordinal to use */
-  int32_t reserved;
-  void*   nccl_comm;              /* ncclComm_t or NULL (single rank) */
+  int32_t comm_kind;              /* KID_COMM_NCCL (0) or KID_COMM_LOCAL (1): what nccl_comm points to */
+  void*   nccl_comm;              /* ncclComm_t, or a kid_local_comm group, or NULL (single rank) */
 } KidDomain;
 
 /* ----------------------------------------------------------------------------
@@ -363,6 +366,11 @@ int32_t kid_synchronize(kid_t* h);
 
 int32_t kid_end(kid_t** h);
 
+/* rank that owns global cell (i,j) under d's layout; -1 = outside the model (NULL_PE).  i may be
+ * any number of periods off on a cyclic-x domain (send_bergs_to_other_pes F:3024-3050 routes by
+ * direction; here a berg goes straight to its owner). */
+int32_t kid_owner_rank(const KidDomain* d, int32_t i, int32_t j);
+
 /* ----------------------------------------------------------------------------
  * Multi-rank plumbing (replaces mpp_send/mpp_recv of send_bergs_to_other_pes,
  * F:3053-3194).  The Fortran shim has MPI but no NCCL binding, so the library
@@ -376,6 +384,13 @@ int32_t kid_nccl_unique_id(char* out, int32_t nbytes);
 int32_t kid_nccl_init(void** comm, const char* id, int32_t nbytes, int32_t nranks, int32_t rank,
                       int32_t device);
 int32_t kid_nccl_destroy(void* comm);
+/* In-process group: `nranks` handles that live in ONE process (one host thread per rank; several
+ * tiles on one GPU, or GPUs of a host without NCCL) exchange halos and migrating bergs with
+ * device-to-device copies after a rendezvous.  Every rank's kid_init / kid_run / kid_step_resident /
+ * kid_set_forcing must be called concurrently from its own thread, as MPI ranks would.
+ * Store the group in KidDomain.nccl_comm with comm_kind = KID_COMM_LOCAL. */
+int32_t kid_local_comm_create(void** group, int32_t nranks);
+int32_t kid_local_comm_destroy(void* group);
 /* fp64 words one migrating berg occupies in the exchange buffer (reference: buffer_width F:21) */
 int32_t kid_pack_width(void);
 

@@ -1,0 +1,169 @@
+"""Multi-rank path: the cell grid is decomposed like mpp_define_layout, bergs that
+leave a tile are packed on the device and shipped to their owner (send_bergs_to_other_pes
+F:2997), halos travel like mpp_update_domains.  Free-drifting bergs do not interact, so the
+union of the ranks' bergs must equal the SINGLE-rank CPU oracle on the same inputs.
+
+Ranks run as host threads of this process: on one GPU through the in-process group (device to
+device copies), on >= 2 GPUs through NCCL."""
+import numpy as np
+import pytest
+
+from common import COMPARE_F64, Case, assert_bergs_match, grid_rel, run_oracle
+from icebergs_b200 import _cdefs as D
+from icebergs_b200 import api, parallel
+from icebergs_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+NAMES = list(COMPARE_F64) + ["ine", "jne", "start_year", "id"]
+FLUX_FIELDS = (D.KID_FLD_FLOATING_MELT, D.KID_FLD_BERG_MELT, D.KID_FLD_BERGY_SRC, D.KID_FLD_BERGY_MELT)
+
+
+class Ranks:
+    """nranks library handles over one Case, driven like MPI ranks."""
+
+    def __init__(self, case, nranks, domain_of, run_ranks):
+        self.case, self.nranks, self.run_ranks = case, nranks, run_ranks
+        self.doms = [domain_of(r) for r in range(nranks)]
+        self.grids = [S.Grid(case.gni, case.gnj, d.isc, d.iec, d.jsc, d.jec) for d in self.doms]
+        parts = parallel.split_by_owner(case.bergs, self.doms)
+        self.h = [None] * nranks
+
+        def init(r):
+            d = self.doms[r]
+            b = api.icebergs_init(case.gni, case.gnj, case.dt, (1, 0.0), params=case.params(), domain=d,
+                                  capacity=case.capacity, **self.grids[r].init_args())
+            cnt = np.zeros((d.njd, d.nid), dtype=np.int32)
+            hl = case.halo
+            cnt[hl:hl + d.njc, hl:hl + d.nic] = case.counter[d.jsc - 1:d.jec, d.isc - 1:d.iec]
+            b.set_calving_state(iceberg_counter_grd=cnt)
+            b.set_bergs(**parts[r])
+            self.h[r] = b
+        run_ranks(init)
+
+    def step(self, over=None):
+        def one(r):
+            f = self.grids[r].forcing()
+            for k, v in (over or {}).items():
+                f[k] = np.full_like(f[k], v)
+            calving, hflx = f["calving"].copy(), f["calving_hflx"].copy()
+            api.icebergs_run(self.h[r], (1, 0.0), calving, f["uo"], f["vo"], f["ui"], f["vi"], f["tauxa"], f["tauya"],
+                             f["ssh"], f["sst"], hflx, f["cn"], f["hi"], sss=f["sss"])
+        self.run_ranks(one)
+
+    def resident(self, n):
+        self.run_ranks(lambda r: self.h[r].step_resident(n, 1, 0.0))
+
+    def bergs(self):
+        parts = [b.get_bergs(NAMES) for b in self.h]
+        return {k: np.concatenate([p[k] for p in parts]) for k in NAMES}
+
+    def owners_ok(self):
+        for r, b in enumerate(self.h):
+            g = b.get_bergs(["ine", "jne"])
+            d = self.doms[r]
+            if len(g["ine"]) and not ((g["ine"] >= d.isc) & (g["ine"] <= d.iec) & (g["jne"] >= d.jsc) & (g["jne"] <= d.jec)).all():
+                return False
+        return True
+
+    def field(self, fid):
+        """Stitches the compute domains of a grid field into the global (gnj, gni) array."""
+        out = np.zeros((self.case.gnj, self.case.gni))
+        hl = self.case.halo
+        for r, b in enumerate(self.h):
+            d = self.doms[r]
+            out[d.jsc - 1:d.jec, d.isc - 1:d.iec] = b.grid_field(fid)[hl:hl + d.njc, hl:hl + d.nic]
+        return out
+
+    def counters(self):
+        return [b.counters() for b in self.h]
+
+    def end(self):
+        for b in self.h:
+            api.icebergs_end(b)
+
+
+def check_against_oracle(case, ranks, steps, over, rtol):
+    o = case.make_oracle()
+    fast = {k: np.full_like(case.forcing[k], v) for k, v in (over or {}).items()}
+    moved = 0
+    for step in range(steps):
+        ranks.step(over)
+        run_oracle(o, case, **fast)
+        assert_bergs_match(ranks.bergs(), o.get_bergs(NAMES), rtol=rtol, context=f"{ranks.nranks} ranks, step {step}")
+        assert ranks.owners_ok(), "a rank holds a berg outside its compute domain"
+        moved += sum(c["n_sent"] for c in ranks.counters())
+        hl = case.halo
+        for fid in FLUX_FIELDS:
+            want = o.grid_field(fid)[hl:hl + case.gnj, hl:hl + case.gni]
+            assert grid_rel(ranks.field(fid), want) < 1e-9, f"grid field {fid} step {step}"
+    return moved
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_in_process_ranks_match_single_rank_oracle(nranks):
+    # half-day steps in a fast current: bergs cross tile edges (and the cyclic seam) every step but
+    # stay within the 4-cell walk of adjust_index_and_ground, whose data-domain clamps (I:7941-7998)
+    # would otherwise make an N-PE run of the reference itself differ from a 1-PE run
+    case = Case(96, 48, 12000, dt=43200.0, old_bug_bilin=0)
+    grp = parallel.LocalGroup(nranks)
+    ranks = Ranks(case, nranks, lambda r: grp.domain(case.gni, case.gnj, r, halo=case.halo), grp.run)
+    moved = check_against_oracle(case, ranks, 8, dict(uo=1.2, vo=0.15, tauxa=15.0), rtol=1e-8)
+    assert moved > 100, f"only {moved} bergs migrated: the case does not exercise the exchange"
+    ranks.end()
+    grp.close()
+
+
+def test_in_process_ranks_resident_steps_and_sort():
+    """Many resident steps (periodic cell sort compacts the slots the leavers freed)."""
+    case = Case(96, 48, 6000)
+    grp = parallel.LocalGroup(4)
+    ranks = Ranks(case, 4, lambda r: grp.domain(case.gni, case.gnj, r, halo=case.halo), grp.run)
+    o = case.make_oracle()
+    ranks.step(); run_oracle(o, case)
+    ranks.resident(40); o.step_again(40, 1, 0.0)
+    assert_bergs_match(ranks.bergs(), o.get_bergs(NAMES), rtol=1e-9, context="4 ranks, 41 steps")
+    assert ranks.owners_ok()
+    ranks.end()
+    grp.close()
+
+
+def test_nccl_ranks_match_single_rank_oracle():
+    """Same check over NCCL: one rank per GPU (threads of this process), needs >= 2 GPUs."""
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    nranks = 8 if ngpu >= 8 else (4 if ngpu >= 4 else 2)
+    case = Case(96, 48, 12000, dt=43200.0, old_bug_bilin=0)
+    uid = parallel.nccl_unique_id()
+    import threading
+    comms = [None] * nranks
+
+    def run_ranks(fn):
+        out, err = [None] * nranks, [None] * nranks
+
+        def work(r):
+            try:
+                out[r] = fn(r)
+            except BaseException as e:  # noqa: BLE001
+                err[r] = e
+        th = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        for e in err:
+            if e is not None:
+                raise e
+        return out
+
+    def mk(r):
+        comms[r] = parallel.nccl_comm(uid, nranks, r, r)
+    run_ranks(mk)
+    ranks = Ranks(case, nranks,
+                  lambda r: api.Domain.decomposed(case.gni, case.gnj, r, nranks, halo=case.halo, device=r, comm=comms[r]),
+                  run_ranks)
+    moved = check_against_oracle(case, ranks, 8, dict(uo=1.2, vo=0.15, tauxa=15.0), rtol=1e-8)
+    assert moved > 100
+    ranks.end()
+    for c in comms:
+        api.lib().kid_nccl_destroy(c)
