@@ -1,0 +1,272 @@
+!> Drop-in replacement of module ice_bergs (src/icebergs.F90:1-66) whose hot path runs in
+!! libkid_b200.so.  Keeps the public names and argument lists of the reference
+!! (icebergs_init I:92-117, icebergs_run I:5074-5096, icebergs_end I:8152, icebergs_stock_pe
+!! I:8102, icebergs_incr_mass I:6046, icebergs_save_restart I:8136) so the stand-alone driver
+!! (driver/icebergs_driver.F90:339-344, 386-392, 435, 444) and SIS/SIS2 link against it unchanged.
+!!
+!! Host-side work that stays in Fortran/FMS: namelist -> KidParams, mpp_define_domains ->
+!! KidDomain, get_date/yearday, NetCDF restart I/O (columns <-> kid_set_bergs/kid_get_bergs),
+!! diag_manager send_data of the fields fetched with kid_get_grid_field, error_mesg.
+!!
+!! NOT COMPILED IN THIS REPOSITORY'S CI: the image has no Fortran compiler.  The Python mirror
+!! icebergs_b200/api.py drives the same C ABI with Fortran-ordered arrays and is what the
+!! parity tests exercise.
+module ice_bergs
+  use, intrinsic :: iso_c_binding
+  use fms_mod, only: error_mesg, FATAL, open_namelist_file, check_nml_error, close_file
+  use mpp_mod, only: mpp_pe, mpp_npes, mpp_root_pe, mpp_broadcast
+  use mpp_domains_mod, only: domain2D, mpp_define_domains, mpp_get_compute_domain, mpp_get_data_domain, &
+                             mpp_get_neighbor_pe, NORTH, SOUTH, EAST, WEST, CYCLIC_GLOBAL_DOMAIN
+  use mpp_parameter_mod, only: BGRID_NE, CGRID_NE, AGRID
+  use time_manager_mod, only: time_type, get_date
+  implicit none ; private
+
+  include 'kid_b200_types.inc'     ! generated from include/kid_b200.h (integration/gen_fortran_types.py)
+
+  public :: icebergs, icebergs_init, icebergs_run, icebergs_end, icebergs_stock_pe, icebergs_incr_mass
+  public :: icebergs_save_restart
+
+  !> The opaque container the callers hold (type(icebergs), pointer :: bergs)
+  type :: icebergs
+    type(c_ptr) :: h = c_null_ptr          !< kid_t*
+    type(KidParams) :: p
+    type(KidDomain) :: dom
+    type(domain2D) :: domain
+    integer :: isc, iec, jsc, jec
+  end type icebergs
+
+  interface
+    subroutine kid_default_params(p) bind(C, name='kid_default_params')
+      import :: KidParams
+      type(KidParams), intent(out) :: p
+    end subroutine
+    function kid_init(h, p, dom, year, yearday, capacity, lon, lat, wet, dx, dy, area, cos_rot, sin_rot, &
+                      ocean_depth, fractional_area) bind(C, name='kid_init') result(rc)
+      import :: c_ptr, c_int32_t, c_int64_t, c_double, KidParams, KidDomain
+      type(c_ptr), intent(out) :: h
+      type(KidParams), intent(in) :: p
+      type(KidDomain), intent(in) :: dom
+      integer(c_int32_t), value :: year, fractional_area
+      real(c_double), value :: yearday
+      integer(c_int64_t), value :: capacity
+      real(c_double), intent(in) :: lon(*), lat(*), wet(*), dx(*), dy(*), area(*), cos_rot(*), sin_rot(*)
+      type(c_ptr), value :: ocean_depth          ! may be c_null_ptr
+      integer(c_int32_t) :: rc
+    end function
+    function kid_run(h, year, yearday, calving, uo, vo, ui, vi, tauxa, tauya, ssh, sst, calving_hflx, cn, hi, &
+                     stagger, stress_stagger, sss, mass_berg, ustar_berg, area_berg) bind(C, name='kid_run') result(rc)
+      import :: c_ptr, c_int32_t, c_double
+      type(c_ptr), value :: h
+      integer(c_int32_t), value :: year, stagger, stress_stagger
+      real(c_double), value :: yearday
+      real(c_double), intent(inout) :: calving(*), calving_hflx(*)
+      real(c_double), intent(in) :: uo(*), vo(*), ui(*), vi(*), tauxa(*), tauya(*), ssh(*), sst(*), cn(*), hi(*)
+      type(c_ptr), value :: sss, mass_berg, ustar_berg, area_berg   ! optional: c_null_ptr when absent
+      integer(c_int32_t) :: rc
+    end function
+    function kid_end(h) bind(C, name='kid_end') result(rc)
+      import :: c_ptr, c_int32_t
+      type(c_ptr), intent(inout) :: h
+      integer(c_int32_t) :: rc
+    end function
+    function kid_set_bergs(h, n, cols) bind(C, name='kid_set_bergs') result(rc)
+      import :: c_ptr, c_int32_t, c_int64_t, KidBergColumns
+      type(c_ptr), value :: h
+      integer(c_int64_t), value :: n
+      type(KidBergColumns), intent(in) :: cols
+      integer(c_int32_t) :: rc
+    end function
+    function kid_get_bergs(h, n, cols, include_halo) bind(C, name='kid_get_bergs') result(rc)
+      import :: c_ptr, c_int32_t, c_int64_t, KidBergColumns
+      type(c_ptr), value :: h
+      integer(c_int64_t), intent(inout) :: n
+      type(KidBergColumns), intent(inout) :: cols
+      integer(c_int32_t), value :: include_halo
+      integer(c_int32_t) :: rc
+    end function
+    function kid_set_calving_state(h, stored_ice, stored_heat, counter) bind(C, name='kid_set_calving_state') result(rc)
+      import :: c_ptr, c_int32_t
+      type(c_ptr), value :: h, stored_ice, stored_heat, counter
+      integer(c_int32_t) :: rc
+    end function
+    function kid_get_grid_field(h, field_id, out) bind(C, name='kid_get_grid_field') result(rc)
+      import :: c_ptr, c_int32_t, c_double
+      type(c_ptr), value :: h
+      integer(c_int32_t), value :: field_id
+      real(c_double), intent(out) :: out(*)
+      integer(c_int32_t) :: rc
+    end function
+    function kid_stock(h, index, value) bind(C, name='kid_stock') result(rc)
+      import :: c_ptr, c_int32_t, c_double
+      type(c_ptr), value :: h
+      integer(c_int32_t), value :: index
+      real(c_double), intent(out) :: value
+      integer(c_int32_t) :: rc
+    end function
+    function kid_incr_mass(h, mass) bind(C, name='kid_incr_mass') result(rc)
+      import :: c_ptr, c_int32_t, c_double
+      type(c_ptr), value :: h
+      real(c_double), intent(inout) :: mass(*)
+      integer(c_int32_t) :: rc
+    end function
+    function kid_nccl_unique_id(buf, nbytes) bind(C, name='kid_nccl_unique_id') result(rc)
+      import :: c_char, c_int32_t
+      character(kind=c_char), intent(out) :: buf(*)
+      integer(c_int32_t), value :: nbytes
+      integer(c_int32_t) :: rc
+    end function
+    function kid_nccl_init(comm, id, nbytes, nranks, rank, device) bind(C, name='kid_nccl_init') result(rc)
+      import :: c_ptr, c_char, c_int32_t
+      type(c_ptr), intent(out) :: comm
+      character(kind=c_char), intent(in) :: id(*)
+      integer(c_int32_t), value :: nbytes, nranks, rank, device
+      integer(c_int32_t) :: rc
+    end function
+    function kid_last_error(h) bind(C, name='kid_last_error') result(msg)
+      import :: c_ptr
+      type(c_ptr), value :: h
+      type(c_ptr) :: msg
+    end function
+  end interface
+
+contains
+
+  !> error_mesg(..., FATAL) with the library's message (the library never aborts by itself)
+  subroutine check(bergs_h, rc, routine)
+    type(c_ptr), intent(in) :: bergs_h
+    integer(c_int32_t), intent(in) :: rc
+    character(len=*), intent(in) :: routine
+    character(kind=c_char), pointer :: s(:)
+    character(len=512) :: msg
+    integer :: k
+    if (rc == KID_OK) return
+    call c_f_pointer(kid_last_error(bergs_h), s, [512])
+    msg = ' '
+    do k = 1, 512
+      if (s(k) == c_null_char) exit
+      msg(k:k) = s(k)
+    enddo
+    call error_mesg(routine, trim(msg), FATAL)
+  end subroutine check
+
+  !> I:92-117.  The namelist read (F:825-879) fills type(KidParams); the FMS domain fills KidDomain.
+  subroutine icebergs_init(bergs, gni, gnj, layout, io_layout, axes, dom_x_flags, dom_y_flags, &
+                           dt, Time, ice_lon, ice_lat, ice_wet, ice_dx, ice_dy, ice_area, &
+                           cos_rot, sin_rot, ocean_depth, maskmap, fractional_area)
+    type(icebergs), pointer :: bergs
+    integer, intent(in) :: gni, gnj, layout(2), io_layout(2), axes(2), dom_x_flags, dom_y_flags
+    real, intent(in) :: dt
+    type(time_type), intent(in) :: Time
+    real, dimension(:,:), intent(in) :: ice_lon, ice_lat, ice_wet, ice_dx, ice_dy, ice_area, cos_rot, sin_rot
+    real, dimension(:,:), intent(in), optional, target :: ocean_depth
+    logical, intent(in), optional :: maskmap(:,:), fractional_area
+    integer :: iyr, imon, iday, ihr, imin, isec, frac
+    character(kind=c_char) :: uid(KID_NCCL_UNIQUE_ID_BYTES)
+    type(c_ptr) :: depth_ptr
+
+    allocate(bergs)
+    call kid_default_params(bergs%p)
+    call read_icebergs_nml(bergs%p)           ! namelist icebergs_nml -> KidParams fields of the same name (F:825-856)
+    bergs%p%dt = dt
+    ! domain exactly as the reference defines it (F:915-930)
+    call mpp_define_domains((/1,gni,1,gnj/), layout, bergs%domain, maskmap=maskmap, xflags=dom_x_flags, &
+                            yflags=dom_y_flags, xhalo=bergs%p%halo, yhalo=bergs%p%halo, name='diamond')
+    call mpp_get_compute_domain(bergs%domain, bergs%dom%isc, bergs%dom%iec, bergs%dom%jsc, bergs%dom%jec)
+    call mpp_get_data_domain(bergs%domain, bergs%dom%isd, bergs%dom%ied, bergs%dom%jsd, bergs%dom%jed)
+    call mpp_get_neighbor_pe(bergs%domain, NORTH, bergs%dom%pe_N)
+    call mpp_get_neighbor_pe(bergs%domain, SOUTH, bergs%dom%pe_S)
+    call mpp_get_neighbor_pe(bergs%domain, EAST, bergs%dom%pe_E)
+    call mpp_get_neighbor_pe(bergs%domain, WEST, bergs%dom%pe_W)
+    bergs%dom%gni = gni ; bergs%dom%gnj = gnj
+    bergs%dom%cyclic_x = merge(1, 0, iand(dom_x_flags, CYCLIC_GLOBAL_DOMAIN) /= 0)
+    bergs%dom%cyclic_y = merge(1, 0, iand(dom_y_flags, CYCLIC_GLOBAL_DOMAIN) /= 0)
+    bergs%dom%rank = mpp_pe() - mpp_root_pe() ; bergs%dom%nranks = mpp_npes()
+    bergs%dom%layout_x = layout(1) ; bergs%dom%layout_y = layout(2)
+    bergs%dom%device = local_device_ordinal()  ! e.g. rank modulo GPUs per node
+    bergs%dom%comm_kind = KID_COMM_NCCL
+    bergs%dom%nccl_comm = c_null_ptr
+    if (mpp_npes() > 1) then                   ! NCCL bootstrap over the MPI the host already has
+      if (mpp_pe() == mpp_root_pe()) call check(c_null_ptr, kid_nccl_unique_id(uid, KID_NCCL_UNIQUE_ID_BYTES), 'KID, icebergs_init')
+      call mpp_broadcast(uid, KID_NCCL_UNIQUE_ID_BYTES, mpp_root_pe())
+      call check(c_null_ptr, kid_nccl_init(bergs%dom%nccl_comm, uid, KID_NCCL_UNIQUE_ID_BYTES, mpp_npes(), &
+                                           bergs%dom%rank, bergs%dom%device), 'KID, icebergs_init')
+    endif
+    call get_date(Time, iyr, imon, iday, ihr, imin, isec)
+    frac = 0 ; if (present(fractional_area)) frac = merge(1, 0, fractional_area)
+    depth_ptr = c_null_ptr ; if (present(ocean_depth)) depth_ptr = c_loc(ocean_depth)
+    call check(bergs%h, kid_init(bergs%h, bergs%p, bergs%dom, iyr, yearday(imon, iday, ihr, imin, isec), &
+               int(0, c_int64_t), ice_lon, ice_lat, ice_wet, ice_dx, ice_dy, ice_area, cos_rot, sin_rot, &
+               depth_ptr, frac), 'KID, icebergs_init')
+    ! read_restart_calving / read_restart_bergs (IO:606-975, IO:1432-1530) stay on the host: the NetCDF
+    ! columns go to kid_set_calving_state / kid_set_bergs unchanged (names as IO:261-337)
+    call read_restart_into_library(bergs, Time)
+  end subroutine icebergs_init
+
+  !> I:5074-5096
+  subroutine icebergs_run(bergs, time, calving, uo, vo, ui, vi, tauxa, tauya, ssh, sst, calving_hflx, cn, hi, &
+                          stagger, stress_stagger, sss, mass_berg, ustar_berg, area_berg)
+    type(icebergs), pointer :: bergs
+    type(time_type), intent(in) :: time
+    real, dimension(:,:), intent(inout) :: calving, calving_hflx
+    real, dimension(:,:), intent(in) :: uo, vo, ui, vi, tauxa, tauya, ssh, sst, cn, hi
+    integer, optional, intent(in) :: stagger, stress_stagger
+    real, dimension(:,:), optional, intent(in), target :: sss
+    real, dimension(:,:), optional, pointer :: mass_berg, ustar_berg, area_berg
+    integer :: iyr, imon, iday, ihr, imin, isec, vel_stagger, str_stagger
+    type(c_ptr) :: p_sss, p_m, p_u, p_a
+    vel_stagger = BGRID_NE ; if (present(stagger)) vel_stagger = stagger
+    str_stagger = vel_stagger ; if (present(stress_stagger)) str_stagger = stress_stagger
+    p_sss = c_null_ptr ; if (present(sss)) p_sss = c_loc(sss)
+    p_m = c_null_ptr ; p_u = c_null_ptr ; p_a = c_null_ptr
+    if (present(mass_berg)) then ; if (associated(mass_berg)) p_m = c_loc(mass_berg) ; endif
+    if (present(ustar_berg)) then ; if (associated(ustar_berg)) p_u = c_loc(ustar_berg) ; endif
+    if (present(area_berg)) then ; if (associated(area_berg)) p_a = c_loc(area_berg) ; endif
+    call get_date(time, iyr, imon, iday, ihr, imin, isec)
+    call check(bergs%h, kid_run(bergs%h, iyr, yearday(imon, iday, ihr, imin, isec), calving, uo, vo, ui, vi, &
+               tauxa, tauya, ssh, sst, calving_hflx, cn, hi, kid_stagger(vel_stagger), kid_stagger(str_stagger), &
+               p_sss, p_m, p_u, p_a), 'KID, icebergs_run')
+    ! diagnostics: kid_get_grid_field(KID_FLD_*) -> send_data, as I:5520-5650
+  end subroutine icebergs_run
+
+  integer(c_int32_t) function kid_stagger(s)
+    integer, intent(in) :: s
+    kid_stagger = KID_BGRID_NE
+    if (s == CGRID_NE) kid_stagger = KID_CGRID_NE
+    if (s == AGRID) kid_stagger = KID_AGRID
+  end function kid_stagger
+
+  !> F:4431-4441
+  real function yearday(imon, iday, ihr, imin, isec)
+    integer, intent(in) :: imon, iday, ihr, imin, isec
+    yearday = float(imon-1)*31. + float(iday-1) + (float(ihr) + (float(imin) + float(isec)/60.)/60.)/24.
+  end function yearday
+
+  !> I:8152: write restarts from kid_get_bergs columns (IO:261-337), then free the device state
+  subroutine icebergs_end(bergs)
+    type(icebergs), pointer :: bergs
+    if (.not. associated(bergs)) return
+    call icebergs_save_restart(bergs)
+    call check(bergs%h, kid_end(bergs%h), 'KID, icebergs_end')
+    deallocate(bergs)
+  end subroutine icebergs_end
+
+  !> I:8102
+  subroutine icebergs_stock_pe(bergs, index, value)
+    type(icebergs), pointer :: bergs
+    integer, intent(in) :: index
+    real, intent(out) :: value
+    call check(bergs%h, kid_stock(bergs%h, int(index - 1, c_int32_t), value), 'KID, icebergs_stock_pe')
+  end subroutine icebergs_stock_pe
+
+  !> I:6046
+  subroutine icebergs_incr_mass(bergs, mass, Time)
+    type(icebergs), pointer :: bergs
+    real, dimension(bergs%isc:bergs%iec, bergs%jsc:bergs%jec), intent(inout) :: mass
+    type(time_type), intent(in), optional :: Time
+    call check(bergs%h, kid_incr_mass(bergs%h, mass), 'KID, icebergs_incr_mass')
+  end subroutine icebergs_incr_mass
+
+  ! read_icebergs_nml, read_restart_into_library, icebergs_save_restart, local_device_ordinal:
+  ! host-side FMS/NetCDF code taken over from icebergs_framework.F90 / icebergs_fmsio.F90 unchanged
+  ! except that the berg columns are handed to / fetched from the library instead of the linked lists.
+end module ice_bergs
