@@ -2,6 +2,8 @@
 bilin corner exactness (icebergs_framework.F90:7313-7316), the 64-bit id round trip
 (F:7319-7325), yearday (F:4431-4441), and structural invariants of the restated step."""
 import ctypes as C
+import json
+import os
 
 import numpy as np
 import pytest
@@ -11,11 +13,16 @@ from common import Case, run_oracle
 from icebergs_b200 import _cdefs as D
 
 
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+KNOWN = json.load(open(os.path.join(GOLDEN, "known_answers.json")))
+
+
 def test_id_round_trip_F7319():
     L = O.lib()
-    i, c1 = 1440 * 1080, 2 ** 30 + 2 ** 4 + 1
+    k = KNOWN["id_round_trip"]
+    i, c1 = k["i"], k["counter"]
     ident = L.oracle_id_from_2_ints(c1, i)
-    assert ident == c1 * 2 ** 32 + i
+    assert ident == k["id"] == c1 * 2 ** 32 + i
     c2, j = C.c_int32(), C.c_int32()
     L.oracle_split_id(ident, C.byref(c2), C.byref(j))
     assert (c2.value, j.value) == (c1, i)
@@ -23,8 +30,8 @@ def test_id_round_trip_F7319():
 
 def test_yearday_F4431():
     L = O.lib()
-    assert L.oracle_yearday(1, 1, 0, 0, 0) == 0.0
-    assert L.oracle_yearday(3, 2, 12, 0, 0) == 2 * 31 + 1 + 0.5
+    for mon, day, hr, mi, sec, want in KNOWN["yearday"]["cases"]:
+        assert L.oracle_yearday(mon, day, hr, mi, sec) == want
 
 
 @pytest.mark.parametrize("old_bug", [0])
@@ -98,3 +105,27 @@ def test_melt_budget_closes():
     area = o.grid_field(D.KID_FLD_AREA)
     assert lost > 0
     assert abs(np.sum(fm * area) * case.dt - lost) / lost < 1e-9
+
+
+def test_oracle_regression_fixture():
+    """tests/golden/oracle_step_48x24.npz (made by tests/golden/make_golden.py with this oracle):
+    freezes the restated arithmetic -- not a reference pin."""
+    from common import COMPARE_F64, by_id
+    fx = np.load(os.path.join(GOLDEN, "oracle_step_48x24.npz"))
+    case = Case(48, 24, 400)
+    o = case.make_oracle()
+    run_oracle(o, case)
+    o.step_again(3, 1, 0.0)
+    b = by_id(o.get_bergs(list(COMPARE_F64) + ["ine", "jne", "start_year", "id"]))
+    for k in fx.files:
+        if b[k].dtype.kind == "i":
+            assert np.array_equal(b[k], fx[k]), k
+        else:
+            assert np.allclose(b[k], fx[k], rtol=1e-13, atol=0), k
+
+
+def test_calving_tables_F787():
+    p = Case(48, 24, 0).params()
+    t = KNOWN["calving_tables"]
+    for name in ("initial_mass_s", "distribution_s", "mass_scaling_s", "initial_thickness_s"):
+        assert list(getattr(p, name)) == t[name]
