@@ -251,6 +251,7 @@ static void fill_dev_params(kid_t* h) {
   q.dlat_dy = (180. / p.pi) / p.Rearth;
   q.r180_pi = 180. / p.pi;
   q.f_cori_plane = (2. * p.omega) * sin((p.pi / 180.) * p.lat_ref);
+  q.rect_add = ((!p.grid_is_latlon) && p.grid_is_regular) ? 0.5 : 0.;
 }
 
 // Fortran MODULO / apply_modulo_around_point on the host, for the init-time
@@ -683,6 +684,7 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   CK(cudaMalloc(&g.corner, sizeof(CornerRec) * n2));
   CK(cudaMalloc(&g.cell, sizeof(CellRec) * n2));
   CK(cudaMalloc(&g.lonlat, sizeof(LonLat) * n2));
+  CK(cudaMalloc(&g.rect, sizeof(RectCell) * n2));
   for (int k = 0; k < 13; k++) CK(cudaMalloc(&h->in_stage[k], sizeof(double) * (size_t)(h->nic + 2) * (h->njc + 2)));
   for (int k = 0; k < 2; k++) CK(cudaMalloc(&h->out_stage[k], sizeof(double) * (size_t)h->nic * h->njc));
 
@@ -750,6 +752,7 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   if (si && atoi(si) > 0) h->sort_interval = atoi(si);
 
   LAUNCH(h, k_pack_lonlat, n2, 256, h->g, n2);
+  LAUNCH(h, k_pack_rect, n2, 256, h->g, h->dp, n2);
   LAUNCH(h, k_pack_forcing, n2, 256, h->g, n2);
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
@@ -762,7 +765,7 @@ extern "C" int32_t kid_end(kid_t** hp) {
   cudaSetDevice(h->d.device);
   cudaStreamSynchronize(h->stream);
   for (double* p : h->field_allocs) cudaFree(p);
-  cudaFree(h->g.iceberg_counter_grd); cudaFree(h->g.corner); cudaFree(h->g.cell); cudaFree(h->g.lonlat);
+  cudaFree(h->g.iceberg_counter_grd); cudaFree(h->g.corner); cudaFree(h->g.cell); cudaFree(h->g.lonlat); cudaFree(h->g.rect);
   for (auto p : h->in_stage) cudaFree(p);
   for (auto p : h->out_stage) cudaFree(p);
   for (int c = 0; c < C_NCOLS; c++) cudaFree(h->b.f64[c]);

@@ -53,6 +53,7 @@ struct DevParams {
   double dlat_dy;        // (180/pi)/Rearth  I:470
   double r180_pi;        // 180/pi
   double f_cori_plane;   // 2*omega*sin(pi_180*lat_ref)  I:2046
+  double rect_add;       // 0.5 on the regular Cartesian path of pos_within_cell (F:6331), else 0
   int32_t grid_is_latlon, grid_is_regular, old_bug_bilin, use_roundoff_fix, use_f_plane;
   int32_t use_new_predictive_corrective, only_interactive_forces, override_iceberg_velocities;
   int32_t old_interp_flds_order, interactive_icebergs_on, iceberg_bonds_on, internal_bergs_for_drag;
@@ -71,6 +72,11 @@ struct __align__(16) CornerRec { double uo, vo, ui, vi, ua, va, cosr, sinr; };
 struct __align__(16) CellRec { double sst, sss, cn, hi, od, rarea /* 1/area, 0 where area==0 */, ddx, ddy; };
 // corner position record
 struct __align__(16) LonLat { double lon, lat; };
+// Cells that are exact rectangles in (lon,lat) (every cell of a regular grid away from the pole):
+// calc_xiyj (F:6439) degenerates to xi = dx/alpha, yj = dy/epsilon, the regular Cartesian path
+// (F:6325-6332) to xi = dx/|alpha| + 0.5.  x1,y1 = reference corner (SW, or the cell centre for the
+// Cartesian path), ralpha/reps = the reciprocals.  ralpha = NaN: not such a cell, take the general path.
+struct __align__(16) RectCell { double x1, y1, ralpha, reps; };
 
 struct DevGrid {
   int32_t isd, ied, jsd, jed, isc, iec, jsc, jec, nid, njd, gni, gnj;
@@ -87,6 +93,7 @@ struct DevGrid {
   CornerRec* corner;
   CellRec* cell;
   LonLat* lonlat;
+  RectCell* rect;
   // flux / diagnostic outputs
   double *floating_melt, *berg_melt, *bergy_src, *bergy_melt, *fl_bits_melt, *fl_bits_src;
   double *melt_buoy, *melt_eros, *melt_conv, *melt_buoy_fl, *melt_eros_fl, *melt_conv_fl;

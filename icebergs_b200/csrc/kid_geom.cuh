@@ -217,8 +217,8 @@ __device__ __noinline__ bool is_point_in_quad_ool(const Quad& q, const DevParams
 // the same sign (inside) or the crude bounds / a cross product rejects the point (outside) by a
 // margin ~1e10 times the rounding error; only inside the band, and always in polar cells, is
 // the reference's sign test evaluated.
-__device__ __noinline__ bool pos_within_cell(const DevGrid& g, const DevParams& p, double x, double y,
-                                             int i, int j, double* xi, double* yj, unsigned int* err) {
+__device__ __noinline__ bool pos_within_cell_general(const DevGrid& g, const DevParams& p, double x, double y,
+                                                     int i, int j, double* xi, double* yj, unsigned int* err) {
   *xi = -999.; *yj = -999.;
   if (!cell_on_pe(g, i, j)) return false;
   Quad q = load_quad(g, i, j);
@@ -243,6 +243,46 @@ __device__ __noinline__ bool pos_within_cell(const DevGrid& g, const DevParams& 
   if (a > lo && a < hi && b > lo && b < hi) return true;
   if (a < -lo || a > 1. + lo || b < -lo || b > 1. + lo) return false;
   return is_point_in_quad_ool(q, p, x, y);
+}
+
+// rectangle record of cell k (linear index) from the corner positions; launched once at init
+__device__ __forceinline__ RectCell make_rect(const DevGrid& g, const DevParams& p, int i, int j) {
+  RectCell r;
+  r.x1 = 0.; r.y1 = 0.; r.reps = 0.;
+  r.ralpha = __longlong_as_double(0x7ff8000000000000ll);
+  if (!cell_on_pe(g, i, j)) return r;
+  Quad q = load_quad(g, i, j);
+  if ((!p.grid_is_latlon) && p.grid_is_regular) {
+    double dx = fabs(KSUB(q.x3, q.x4)), dy = fabs(KSUB(q.y3, q.y2));
+    if (!(dx > 0.) || !(dy > 0.)) return r;
+    r.x1 = KSUB(q.x3, KMUL(dx, 0.5)); r.y1 = KSUB(q.y3, KMUL(dy, 0.5));
+    r.ralpha = 1. / dx; r.reps = 1. / dy;
+    return r;
+  }
+  if (!((fmax(fmax(q.y1, q.y2), fmax(q.y3, q.y4)) < 89.999) || (!p.grid_is_latlon))) return r;   // polar: F:6359
+  double alpha = KSUB(q.x2, q.x1), delta = KSUB(q.y2, q.y1), beta = KSUB(q.x4, q.x1), epsilon = KSUB(q.y4, q.y1);
+  double gamma = KSUB(KSUB(q.x3, q.x1), KADD(alpha, beta));
+  double kappa = KSUB(KSUB(q.y3, q.y1), KADD(delta, epsilon));
+  if (delta != 0. || beta != 0. || gamma != 0. || kappa != 0. || !(alpha > 0.) || !(epsilon > 0.)) return r;
+  r.x1 = q.x1; r.y1 = q.y1;
+  r.ralpha = 1. / alpha; r.reps = 1. / epsilon;
+  return r;
+}
+
+// pos_within_cell with the rectangle shortcut in line and everything else out of line
+__device__ __forceinline__ bool pos_within_cell(const DevGrid& g, const DevParams& p, double x, double y,
+                                                int i, int j, double* xi, double* yj, unsigned int* err) {
+  if (cell_on_pe(g, i, j)) {
+    const RectCell rc = g.rect[gidx(g, i, j)];
+    if (rc.ralpha == rc.ralpha) {
+      double a = KADD(KMUL(KSUB(amap(x, rc.x1, p.Lx), rc.x1), rc.ralpha), p.rect_add);
+      double b = KADD(KMUL(KSUB(y, rc.y1), rc.reps), p.rect_add);
+      const double lo = KID_EDGE_BAND, hi = 1. - KID_EDGE_BAND;
+      if (a > lo && a < hi && b > lo && b < hi) { *xi = a; *yj = b; return true; }
+      if (a < -lo || a > 1. + lo || b < -lo || b > 1. + lo) { *xi = a; *yj = b; return false; }
+    }
+  }
+  return pos_within_cell_general(g, p, x, y, i, j, xi, yj, err);
 }
 
 // F:7071-7088 on the corner positions

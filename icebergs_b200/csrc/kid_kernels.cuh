@@ -270,7 +270,7 @@ __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, c
     if (!interp_flds(g, p, i, j, xi, yj, e)) atomicOr(&cnt->error_flags, 64u);
     // sin and cos of the latitude: Coriolis (I:2043-2047) and the metric (I:462-477)
     double sin_lat = 0., cos_lat = 1.;
-    if (p.grid_is_latlon) sincos(p.pi_180 * lat, &sin_lat, &cos_lat);
+    if (p.grid_is_latlon) sincos_halfpi(p.pi_180 * lat, &sin_lat, &cos_lat);
     double f_cori = (p.grid_is_latlon && !p.use_f_plane) ? p.omega2 * sin_lat : p.f_cori_plane;
     double ax1, ay1, un_l, vn_l;
     IAcc ia0 = {0., 0., 0., 0., 0., 0., 0., 0.};
@@ -359,7 +359,7 @@ k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
   if (owned && cell_on_pe(g, in.i, in.j)) {
     // corner positions of the berg's cell (pos_within_cell, a few hundred instructions from now)
     size_t ne = gidx(g, in.i, in.j);
-    prefetch_l1(&g.lonlat[ne - 1]); prefetch_l1(&g.lonlat[ne - (size_t)g.nid - 1]);
+    prefetch_l1(&g.rect[ne]);
   }
   Scatter sc;
   sc.key = -1;
@@ -689,6 +689,13 @@ __global__ void k_pack_lonlat(const __grid_constant__ DevGrid g, long long n2) {
   if (k >= n2) return;
   LonLat r; r.lon = g.lon[k]; r.lat = g.lat[k];
   g.lonlat[k] = r;
+}
+// after k_pack_lonlat: the rectangle records of pos_within_cell
+__global__ void k_pack_rect(const __grid_constant__ DevGrid g, const __grid_constant__ DevParams p, long long n2) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n2) return;
+  int i = g.isd + (int)(k % g.nid), j = g.jsd + (int)(k / g.nid);
+  g.rect[k] = make_rect(g, p, i, j);
 }
 
 // corner + cell records from the ingested fields; ddx_ssh/ddy_ssh I:4903-4926

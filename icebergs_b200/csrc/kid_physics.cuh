@@ -29,8 +29,7 @@ struct Env { double uo, vo, ui, vi, ua, va, ssh_x, ssh_y, sst, sss, cn, hi, od; 
 __device__ __forceinline__ double rcp_nr(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  r = fma(r, fma(-x, r, 1.0), r);
-  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);      // seed ~2^-20 -> 2^-40 -> 2^-80
   r = fma(r, fma(-x, r, 1.0), r);
   return r;
 }
@@ -39,9 +38,7 @@ __device__ __forceinline__ double sqrt_nr(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   double g = x * y, h = 0.5 * y;
-  double r = fma(-g, h, 0.5);
-  g = fma(g, r, g); h = fma(h, r, h);
-  r = fma(-g, h, 0.5);
+  double r = fma(-g, h, 0.5);          // seed ~2^-20 -> 2^-40, the last line -> 2^-80
   g = fma(g, r, g); h = fma(h, r, h);
   return fma(fma(-g, g, x), h, g);
 }
@@ -49,6 +46,38 @@ __device__ __forceinline__ double sqrt_nr(double x) {
 __device__ __forceinline__ double rcp_nr(double x) { return 1. / x; }
 __device__ __forceinline__ double sqrt_nr(double x) { return sqrt(x); }
 #endif
+
+// sin and cos for |x| <= pi/2 (x = pi/180*lat): Taylor polynomials in x^2 to x^23 / x^24,
+// truncation < 1e-20, rounding a few ulp -- no argument reduction, no slow path
+__device__ __forceinline__ void sincos_halfpi(double x, double* s, double* c) {
+  if (!(fabs(x) <= 1.5708)) { sincos(x, s, c); return; }
+  const double z = x * x;
+  double ps = -1. / 25852016738884976640000.;            // -1/23!
+  ps = fma(ps, z, 1. / 51090942171709440000.);            //  1/21!
+  ps = fma(ps, z, -1. / 121645100408832000.);             // -1/19!
+  ps = fma(ps, z, 1. / 355687428096000.);                 //  1/17!
+  ps = fma(ps, z, -1. / 1307674368000.);                  // -1/15!
+  ps = fma(ps, z, 1. / 6227020800.);                      //  1/13!
+  ps = fma(ps, z, -1. / 39916800.);                       // -1/11!
+  ps = fma(ps, z, 1. / 362880.);                          //  1/9!
+  ps = fma(ps, z, -1. / 5040.);                           // -1/7!
+  ps = fma(ps, z, 1. / 120.);                             //  1/5!
+  ps = fma(ps, z, -1. / 6.);                              // -1/3!
+  *s = fma(x * z, ps, x);
+  double pc = 1. / 620448401733239439360000.;             //  1/24!
+  pc = fma(pc, z, -1. / 1124000727777607680000.);         // -1/22!
+  pc = fma(pc, z, 1. / 2432902008176640000.);             //  1/20!
+  pc = fma(pc, z, -1. / 6402373705728000.);               // -1/18!
+  pc = fma(pc, z, 1. / 20922789888000.);                  //  1/16!
+  pc = fma(pc, z, -1. / 87178291200.);                    // -1/14!
+  pc = fma(pc, z, 1. / 479001600.);                       //  1/12!
+  pc = fma(pc, z, -1. / 3628800.);                        // -1/10!
+  pc = fma(pc, z, 1. / 40320.);                           //  1/8!
+  pc = fma(pc, z, -1. / 720.);                            // -1/6!
+  pc = fma(pc, z, 1. / 24.);                              //  1/4!
+  pc = fma(pc, z, -0.5);
+  *c = fma(pc, z, 1.);
+}
 
 // accumulated interaction terms of interactive_force (I:480): IA_x, IA_y, P_ia_*, P_ia_times_u_*
 struct IAcc { double IA_x, IA_y, P11, P12, P21, P22, Pu_x, Pu_y; };
