@@ -60,6 +60,7 @@ struct kid_handle {
   int calving_active = 0;
   int steps_since_sort = 0, sort_interval = 16, sorted_once = 0;
   int forcing_set = 0;
+  int no_rotation = 0;
   long long dirty_appended = 0;
   // ---- multi-rank (send_bergs_to_other_pes F:2997, mpp_update_domains)
   DevLayout layout;
@@ -526,6 +527,7 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   h->nid = d->ied - d->isd + 1; h->njd = d->jed - d->jsd + 1;
   h->nic = d->iec - d->isc + 1; h->njc = d->jec - d->jsc + 1;
   h->n2 = (long long)h->nid * h->njd;
+  if (h->n2 * KID_NCLASSES >= 2000000000LL) return fail(h, KID_ERR_ARG, "kid_init: the data domain must have fewer than 2e8 cells per rank");
   const long long n2 = h->n2;
   const int nid = h->nid, nic = h->nic;
   // ---- rank layout (mpp_define_layout / mpp_compute_extent as kid_define_domain restates them)
@@ -652,6 +654,12 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
     glatc[IDX(i, j)] = 0.25 * ((glat[IDX(i, j)] + glat[IDX(i - 1, j - 1)]) + (glat[IDX(i - 1, j)] + glat[IDX(i, j - 1)]));
   }
 
+  // rotate() is the identity when the grid is aligned with lon/lat everywhere
+  {
+    bool ident = true;
+    for (long long k = 0; k < n2 && ident; k++) ident = (gcos[k] == 1.) && (gsin[k] == 0.);
+    h->no_rotation = ident ? 1 : 0;
+  }
   // ---- device grid
   DevGrid& g = h->g;
   memset(&g, 0, sizeof(g));
@@ -739,6 +747,7 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   CK(cudaMallocHost(&h->hflags, 4 * sizeof(unsigned long long)));
 
   fill_dev_params(h);
+  h->dp.no_rotation = h->no_rotation;
   h->dp.current_year = year; h->dp.current_yearday = yearday;
   CalvingTables& ct = h->ct;
   for (int k = 0; k < KID_NCLASSES; k++) {

@@ -63,6 +63,7 @@ struct DevParams {
   int32_t contact_cells_lon, contact_cells_lat, max_bonds;
   int32_t current_year;
   int32_t passive_mode;
+  int32_t no_rotation;   // cos_rot == 1 and sin_rot == 0 on the whole data domain: rotate() (I:4953) is the identity
 };
 
 // corner record: the 8 B-grid fields interp_flds bilinearly gathers (I:4757-4765)

@@ -14,8 +14,9 @@
 
 namespace kid {
 
-__device__ __forceinline__ size_t gidx(const DevGrid& g, int i, int j) {
-  return (size_t)(i - g.isd) + (size_t)(j - g.jsd) * (size_t)g.nid;
+// linear index of cell (i,j) in the data domain (32-bit: kid_init refuses grids of 2^31 cells)
+__device__ __forceinline__ int gidx(const DevGrid& g, int i, int j) {
+  return (i - g.isd) + (j - g.jsd) * g.nid;
 }
 
 __device__ __forceinline__ double f_sign1(double b) { return signbit(b) ? -1. : 1.; }
@@ -92,7 +93,7 @@ struct Quad { double x1, y1, x2, y2, x3, y3, x4, y4; };
 
 __device__ __forceinline__ Quad load_quad(const DevGrid& g, int i, int j) {
   const LonLat* __restrict__ ll = g.lonlat;
-  size_t ne = gidx(g, i, j);
+  int ne = gidx(g, i, j);
   LonLat c3 = ll[ne], c4 = ll[ne - 1], c2 = ll[ne - g.nid], c1 = ll[ne - g.nid - 1];
   Quad q;
   q.x1 = c1.lon; q.y1 = c1.lat; q.x2 = c2.lon; q.y2 = c2.lat;

@@ -190,7 +190,7 @@ __device__ __forceinline__ int thermo_slot(const DevGrid& g, const DevBergs& b, 
                                            double vvel, double M, double T, double W, double L, double mass_scaling,
                                            double mass_of_bits, double heat_density, Scatter& sc,
                                            DevCounters* cnt) {
-  size_t cidx = gidx(g, i, j);
+  const int cidx = gidx(g, i, j);
   EnvThermo e;
   interp_thermo(g, p, cidx, xi, yj, e);
   if ((e.uo != e.uo) || (e.vo != e.vo) || (e.ua != e.ua) || (e.va != e.va) || (e.sst != e.sst) || (e.cn != e.cn))
@@ -299,7 +299,7 @@ __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, c
       tang_position(p, lon, lat, uvel2, vvel2, dt, lonn, latn);
     } else {
       double dxdl1 = 1., dydl = 1.;
-      if (p.grid_is_latlon) { dxdl1 = p.r180_pi / (p.Rearth * cos_lat); dydl = p.dlat_dy; }
+      if (p.grid_is_latlon) { dxdl1 = p.r180_pi * rcp_nr(p.Rearth * cos_lat); dydl = p.dlat_dy; }
       double u2 = uvel2 * dxdl1, v2 = vvel2 * dydl;
       lonn = lon + (dt * u2); latn = lat + (dt * v2);
     }
@@ -358,7 +358,7 @@ k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
   bool owned = (in.flags & BF_ALIVE) && !(in.flags & BF_HALO);
   if (owned && cell_on_pe(g, in.i, in.j)) {
     // corner positions of the berg's cell (pos_within_cell, a few hundred instructions from now)
-    size_t ne = gidx(g, in.i, in.j);
+    int ne = gidx(g, in.i, in.j);
     prefetch_l1(&g.rect[ne]);
   }
   Scatter sc;

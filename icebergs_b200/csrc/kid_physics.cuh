@@ -25,6 +25,11 @@ struct Env { double uo, vo, ui, vi, ua, va, ssh_x, ssh_y, sst, sss, cn, hi, od; 
 // MUFU.RSQ64H, ~20 bits) refined by Newton / Goldschmidt steps to ~1 ulp, without the IEEE
 // corner-case paths of `/` and sqrt() (operands here are masses, lengths, speeds: positive,
 // normal range).  Geometry and the mass-difference sequence keep IEEE `/`.
+// max/min of ordinary numbers: one compare + select (fmax/fmin also order NaNs and signed zeros,
+// which costs several more instructions per call; the operands here are never NaN)
+__device__ __forceinline__ double kmax(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double kmin(double a, double b) { return a < b ? a : b; }
+
 #ifndef KID_IEEE_DIVSQRT
 __device__ __forceinline__ double rcp_nr(double x) {
   double r;
@@ -33,8 +38,11 @@ __device__ __forceinline__ double rcp_nr(double x) {
   r = fma(r, fma(-x, r, 1.0), r);
   return r;
 }
+// branch-free: x = 0 is nudged to 1e-300 (an exact no-op for any x >= 1e-284), so sqrt_nr(0) = 1e-150
+// instead of 0 -- every caller either tests the radicand itself for zero (wind speed, I:2096) or
+// only scales terms that vanish with it
 __device__ __forceinline__ double sqrt_nr(double x) {
-  if (!(x > 1.e-300)) return 0.;          // speeds/lengths: 0 stays 0 (and NaN is not expected here)
+  x = x + 1.e-300;
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   double g = x * y, h = 0.5 * y;
@@ -100,12 +108,12 @@ __device__ __forceinline__ bool interp_flds(const DevGrid& g, const DevParams& p
                                             double yj, Env& e) {
   const CornerRec* __restrict__ cr = g.corner;
   const CellRec* __restrict__ ce = g.cell;
-  size_t ne = gidx(g, i, j);
-  size_t nid = (size_t)g.nid;
+  const int ne = gidx(g, i, j);
+  const int nid = g.nid;
   const CornerRec c3 = cr[ne], c4 = cr[ne - 1], c2 = cr[ne - nid], c1 = cr[ne - nid - 1];
   KID_BILIN_WEIGHTS
-  double cos_rot = KID_BILIN(cosr);
-  double sin_rot = KID_BILIN(sinr);
+  double cos_rot = 1., sin_rot = 0.;
+  if (!p.no_rotation) { cos_rot = KID_BILIN(cosr); sin_rot = KID_BILIN(sinr); }
   double uo = KID_BILIN(uo), vo = KID_BILIN(vo);
   double ui = KID_BILIN(ui), vi = KID_BILIN(vi);
   double ua = KID_BILIN(ua), va = KID_BILIN(va);
@@ -123,8 +131,8 @@ __device__ __forceinline__ bool interp_flds(const DevGrid& g, const DevParams& p
   // SSH slopes, I:4830-4860.  The neighbour picked depends on xi,yj >= 0.5; the loads do not
   // wait for that decision: the address is selected, not the branch.
   const bool yn = yj >= 0.5, xe = xi >= 0.5;
-  const size_t rj = yn ? ne + nid : ne - nid;      // row above or below
-  const size_t ri = xe ? ne + 1 : ne - 1;          // column east or west
+  const int rj = yn ? ne + nid : ne - nid;         // row above or below
+  const int ri = xe ? ne + 1 : ne - 1;             // column east or west
   const double ddx_j0 = c0.ddx, ddx_j0w = ce[ne - 1].ddx, ddx_j1 = ce[rj].ddx, ddx_j1w = ce[rj - 1].ddx;
   const double ddy_i0 = c0.ddy, ddy_i0s = ce[ne - nid].ddy, ddy_i1 = ce[ri].ddy, ddy_i1s = ce[ri - nid].ddy;
   double hxp, hxm;
@@ -144,10 +152,12 @@ __device__ __forceinline__ bool interp_flds(const DevGrid& g, const DevParams& p
     hxm = fma((xi + 0.5), ddy_i0s, (0.5 - xi) * ddy_i1s);
   }
   double ssh_y = fma(yj, hxp, (1. - yj) * hxm);
-  rotate(uo, vo, cos_rot, sin_rot);
-  rotate(ui, vi, cos_rot, sin_rot);
-  rotate(ua, va, cos_rot, sin_rot);
-  rotate(ssh_x, ssh_y, cos_rot, sin_rot);
+  if (!p.no_rotation) {
+    rotate(uo, vo, cos_rot, sin_rot);
+    rotate(ui, vi, cos_rot, sin_rot);
+    rotate(ua, va, cos_rot, sin_rot);
+    rotate(ssh_x, ssh_y, cos_rot, sin_rot);
+  }
   if (ssh_x != ssh_x) ssh_x = 0.;
   if (ssh_y != ssh_y) ssh_y = 0.;
   e.uo = uo; e.vo = vo; e.ui = ui; e.vi = vi; e.ua = ua; e.va = va; e.ssh_x = ssh_x; e.ssh_y = ssh_y;
@@ -159,14 +169,12 @@ __device__ __forceinline__ bool interp_flds(const DevGrid& g, const DevParams& p
 // What thermodynamics (I:2896-2920) uses of interp_flds: the rotated ocean and wind velocities
 // and the A-grid picks of sst, cn; also hands back 1/area of the cell.
 struct EnvThermo { double uo, vo, ua, va, sst, cn, rarea; };
-__device__ __forceinline__ void interp_thermo(const DevGrid& g, const DevParams& p, size_t ne, double xi, double yj,
+__device__ __forceinline__ void interp_thermo(const DevGrid& g, const DevParams& p, int ne, double xi, double yj,
                                               EnvThermo& e) {
   const CornerRec* __restrict__ cr = g.corner;
-  size_t nid = (size_t)g.nid;
+  const int nid = g.nid;
   const CornerRec c3 = cr[ne], c4 = cr[ne - 1], c2 = cr[ne - nid], c1 = cr[ne - nid - 1];
   KID_BILIN_WEIGHTS
-  double cos_rot = KID_BILIN(cosr);
-  double sin_rot = KID_BILIN(sinr);
   double uo = KID_BILIN(uo), vo = KID_BILIN(vo);
   double ua = KID_BILIN(ua), va = KID_BILIN(va);
   if (p.coastal_drift > 0.) {
@@ -176,8 +184,11 @@ __device__ __forceinline__ void interp_thermo(const DevGrid& g, const DevParams&
     uo = uo + cd * (mE - mW) * m0;
     vo = vo + cd * (mN - mS) * m0;
   }
-  rotate(uo, vo, cos_rot, sin_rot);
-  rotate(ua, va, cos_rot, sin_rot);
+  if (!p.no_rotation) {
+    double cos_rot = KID_BILIN(cosr), sin_rot = KID_BILIN(sinr);
+    rotate(uo, vo, cos_rot, sin_rot);
+    rotate(ua, va, cos_rot, sin_rot);
+  }
   const CellRec* __restrict__ ce = g.cell;
   e.sst = ce[ne].sst; e.cn = ce[ne].cn; e.rarea = ce[ne].rarea;
   e.uo = uo; e.vo = vo; e.ua = ua; e.va = va;
@@ -217,14 +228,14 @@ __device__ __forceinline__ void accel_core(const DevParams& p, double M, double 
   double rM = rcp_nr(M);
   double D = p.rho_ratio * T;
   double F = T - D;
-  hi = fmin(hi, D);
-  double D_hi = fmax(0., D - hi);
+  hi = kmin(hi, D);
+  double D_hi = kmax(0., D - hi);
   double c_gnd = 0.0;
   if (p.cdrag_grounding != 0.) {      // I:2066-2082 (c_gnd is exactly 0 otherwise)
     double groundfrac;
     if (p.h_to_init_grounding > 0.0) {
       groundfrac = 1.0 - (od - D) * p.r_h2ig;
-      groundfrac = fmin(fmax(groundfrac, 0.0), 1.0);
+      groundfrac = kmin(kmax(groundfrac, 0.0), 1.0);
     } else {
       groundfrac = (D > od) ? 1.0 : 0.0;
     }
@@ -239,9 +250,10 @@ __device__ __forceinline__ void accel_core(const DevParams& p, double M, double 
   // Cr0*min(max(0,(L-Lcutoff)/((Ltop-Lcutoff)+1e-30)),1): the quotient only matters strictly inside (0,1)
   double cr_num = L - Lcutoff, cr_den = (Ltop - Lcutoff) + 1.e-30;
   double Cr = (cr_num >= cr_den) ? Cr0 : ((cr_num <= 0.) ? 0. : Cr0 * (cr_num / cr_den));
-  double wave_rad = 0.5 * KID_RHO_SEAWATER * rM * Cr * KID_GRAVITY * ampl * fmin(ampl, F) * (2. * W * L) * rcp_nr(W + L);
-  wmod = sqrt_nr(fma(ua, ua, va * va));
-  if (wmod != 0.) { double rw = rcp_nr(wmod); uwave = ua * rw; vwave = va * rw; }
+  double wave_rad = 0.5 * KID_RHO_SEAWATER * rM * Cr * KID_GRAVITY * ampl * kmin(ampl, F) * (2. * W * L) * rcp_nr(W + L);
+  double wmod2 = fma(ua, ua, va * va);
+  wmod = sqrt_nr(wmod2);
+  if (wmod2 != 0.) { double rw = rcp_nr(wmod); uwave = ua * rw; vwave = va * rw; }
   else { uwave = 0.; vwave = 0.; wave_rad = 0.; }
   double WL = W * L;
   double c_ocn = KID_RHO_SEAWATER * rM * p.ocean_drag_scale * (0.5 * KID_CD_WV * dragfrac * W * (D_hi) + KID_CD_WH * WL);
@@ -419,7 +431,12 @@ __device__ __forceinline__ void rolling(const DevParams& p, double& Tn, double& 
   double Dn = p.rho_ratio * Tn;
   if (Dn > 0.) {
     if ((!p.use_updated_rolling_scheme) && (p.tip_parameter < 999.)) {
-      if (fmax(Wn, Ln) < sqrt(0.92 * (Dn * Dn) + 58.32 * Dn)) {
+      // max(W,L) < sqrt(X): decided on the squares unless the two sides agree to 1e-12, where the
+      // reference's own sqrt-then-compare is evaluated
+      double mx = kmax(Wn, Ln), X = 0.92 * (Dn * Dn) + 58.32 * Dn, m2 = mx * mx;
+      bool tip = m2 < X * (1. - 1.e-12);
+      if (!tip && m2 <= X * (1. + 1.e-12)) tip = mx < sqrt(X);
+      if (tip) {
         swap_d(Tn, Wn);
         if (Wn > Ln) swap_d(Wn, Ln);
       }
@@ -477,26 +494,26 @@ __device__ __noinline__ void thermo_fl_bits(const DevParams& p, double thickness
   double Lfl = f.Lfl, Wfl = f.Wfl, Tfl = f.Tfl;
   double Mfl = mass_of_fl_bits;
   double Volfl = Lfl * Wfl * Tfl;
-  double Mb_fl = fmax(0.58 * dvo08 * (SST + 4.0) / pow(Lfl, 0.2), 0.) * perday;
-  double Tnfl = fmax(Tfl - Mb_fl * dt, 0.);
+  double Mb_fl = kmax(0.58 * dvo08 * (SST + 4.0) / pow(Lfl, 0.2), 0.) * perday;
+  double Tnfl = kmax(Tfl - Mb_fl * dt, 0.);
   double Lnfl, Wnfl, nVolfl, Mnew_fl;
   if (p.use_operator_splitting) {
     nVolfl = Tnfl * Wfl * Lfl;
     double Mnew1_fl = (nVolfl / Volfl) * Mfl;
     f.dMb_fl = Mfl - Mnew1_fl;
-    Lnfl = fmax(Lfl - Mv_fl * dt, 0.);
-    Wnfl = fmax(Wfl - Mv_fl * dt, 0.);
+    Lnfl = kmax(Lfl - Mv_fl * dt, 0.);
+    Wnfl = kmax(Wfl - Mv_fl * dt, 0.);
     nVolfl = Tnfl * Wnfl * Lnfl;
     double Mnew2_fl = (nVolfl / Volfl) * Mfl;
     f.dMv_fl = Mnew1_fl - Mnew2_fl;
-    Lnfl = fmax(Lnfl - Me_fl * dt, 0.);
-    Wnfl = fmax(Wnfl - Me_fl * dt, 0.);
+    Lnfl = kmax(Lnfl - Me_fl * dt, 0.);
+    Wnfl = kmax(Wnfl - Me_fl * dt, 0.);
     nVolfl = Tnfl * Wnfl * Lnfl;
     Mnew_fl = (nVolfl / Volfl) * Mfl;
     f.dMe_fl = Mnew2_fl - Mnew_fl;
   } else {
-    Lnfl = fmax(Lfl - (Mv_fl + Me_fl) * dt, 0.);
-    Wnfl = fmax(Wfl - (Mv_fl + Me_fl) * dt, 0.);
+    Lnfl = kmax(Lfl - (Mv_fl + Me_fl) * dt, 0.);
+    Wnfl = kmax(Wfl - (Mv_fl + Me_fl) * dt, 0.);
     nVolfl = Tnfl * Wnfl * Lnfl;
     Mnew_fl = (nVolfl / Volfl) * Mfl;
     f.dMb_fl = (Mfl / Volfl) * (Wfl * Lfl) * Mb_fl * dt;
@@ -514,7 +531,11 @@ __device__ __forceinline__ double pow_m02(double x) {
 #ifdef KID_LIBM_POW
   return exp(-0.2 * log(x));
 #else
-  double y = (double)__powf((float)x, -0.2f);
+  float xf = (float)x, lf, ef;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lf) : "f"(xf));
+  lf = lf * -0.2f;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ef) : "f"(lf));
+  double y = (double)ef;
 #pragma unroll
   for (int it = 0; it < 2; it++) {
     double y2 = y * y;
@@ -534,7 +555,7 @@ __device__ __forceinline__ int thermo_berg(const DevParams& p, const EnvThermo& 
   const double perday = 1. / 86400.;
   double dt = p.dt;
   double SST = e.sst;
-  double IC = fmin(1., e.cn + p.sicn_shift);
+  double IC = kmin(1., e.cn + p.sicn_shift);
   double M = s.mass, T = s.thickness, W = s.width, L = s.length;
   double Vol = T * W * L;
   double M_Vol = M / Vol;
@@ -542,11 +563,11 @@ __device__ __forceinline__ int thermo_berg(const DevParams& p, const EnvThermo& 
   double dva = KID_HYPOT(e.ua - e.uo, e.va - e.vo);
   double Ss = fma(1.5, sqrt_nr(dva), 0.1 * dva);           // dva**0.5
   double dvo08 = pow_08(dvo);
-  double Mv = fmax(7.62e-3 * SST + 1.29e-3 * (SST * SST), 0.) * perday;
-  double Mb = fmax(0.58 * dvo08 * (SST + 4.0) * pow_m02(L), 0.) * perday;
+  double Mv = kmax(7.62e-3 * SST + 1.29e-3 * (SST * SST), 0.) * perday;
+  double Mb = kmax(0.58 * dvo08 * (SST + 4.0) * pow_m02(L), 0.) * perday;
   double IC3 = IC * IC * IC;
   double wave_ic = (IC3 == 0.) ? 2. : (1 + cos(p.pi * IC3));   // cos(0) = 1
-  double Me = fmax(1. / 12. * (SST + 2.) * Ss * wave_ic, 0.) * perday;
+  double Me = kmax(1. / 12. * (SST + 2.) * Ss * wave_ic, 0.) * perday;
   double Mv_fl = 0., Me_fl = 0.;
   if (s.mass_of_fl_bits > 0.) { Mv_fl = Mv; Me_fl = Me; }
   if (p.set_melt_rates_to_zero) { Mv = 0.0; Mb = 0.0; Me = 0.0; }
@@ -554,22 +575,22 @@ __device__ __forceinline__ int thermo_berg(const DevParams& p, const EnvThermo& 
   if (p.use_operator_splitting) {
     // the mass differences below cancel to ~1e-6 of the mass: each (nVol/Vol)*M keeps the
     // reference's own rounding sequence so that dMe (hence the bergy bits) agrees to 1e-10
-    Tn = fmax(T - Mb * dt, 0.);
+    Tn = kmax(T - Mb * dt, 0.);
     Mnew1 = ((Tn * W * L) / Vol) * M;
     dMb = M - Mnew1;
-    Ln1 = fmax(L - Mv * dt, 0.);
-    Wn1 = fmax(W - Mv * dt, 0.);
+    Ln1 = kmax(L - Mv * dt, 0.);
+    Wn1 = kmax(W - Mv * dt, 0.);
     Mnew2 = ((Tn * Wn1 * Ln1) / Vol) * M;
     dMv = Mnew1 - Mnew2;
-    Ln = fmax(Ln1 - Me * dt, 0.);
-    Wn = fmax(Wn1 - Me * dt, 0.);
+    Ln = kmax(Ln1 - Me * dt, 0.);
+    Wn = kmax(Wn1 - Me * dt, 0.);
     Mnew = ((Tn * Wn * Ln) / Vol) * M;
     dMe = Mnew2 - Mnew;
     dM = M - Mnew;
   } else {
-    Ln = fmax(L - (Mv + Me) * (dt), 0.);
-    Wn = fmax(W - (Mv + Me) * (dt), 0.);
-    Tn = fmax(T - Mb * (dt), 0.);
+    Ln = kmax(L - (Mv + Me) * (dt), 0.);
+    Wn = kmax(W - (Mv + Me) * (dt), 0.);
+    Tn = kmax(T - Mb * (dt), 0.);
     Mnew = ((Tn * Wn * Ln) / Vol) * M;
     dM = M - Mnew;
     dMb = M_Vol * (W * L) * Mb * dt;
@@ -611,26 +632,26 @@ __device__ __forceinline__ int thermo_berg(const DevParams& p, const EnvThermo& 
     double Mbits = s.mass_of_bits;
     dMbitsE = p.bergy_bit_erosion_fraction * dMe;
     nMbits = Mbits + dMbitsE;
-    double Lbits = fmin(fmin(L, W), fmin(T, 40.));
+    double Lbits = kmin(kmin(L, W), kmin(T, 40.));
     // Abits=(Mbits/rho)/Lbits; Mbb=rho*Abits*rate: the bergy-bit melt in kg/s, rate ~ Lbits**-0.2
     double rpow, rLbits;
     if (Lbits == 40.) { rpow = p.rpow40_02; rLbits = 1. / 40.; }
     else { rpow = pow_m02(Lbits); rLbits = 1. / Lbits; }
     double Abits = (Mbits * p.r_rho_bergs) * rLbits;
-    double Mbb = fmax(0.58 * dvo08 * (SST + 2.0) * rpow, 0.) * perday;
+    double Mbb = kmax(0.58 * dvo08 * (SST + 2.0) * rpow, 0.) * perday;
     Mbb = p.rho_bergs * Abits * Mbb;
-    dMbitsM = fmin(Mbb * dt, nMbits);
+    dMbitsM = kmin(Mbb * dt, nMbits);
     nMbits = nMbits - dMbitsM;
     if (Mnew == 0.) { dMbitsM = dMbitsM + nMbits; nMbits = 0.; }
     if (has_fl) {
       double Mbits_fl = s.mass_of_fl_bergy_bits;
       dMbitsE_fl = p.bergy_bit_erosion_fraction * fl.dMe_fl;
       nMbits_fl = Mbits_fl + dMbitsE_fl;
-      double Lbits_fl = fmin(fmin(fl.Lfl, fl.Wfl), fmin(fl.Tfl, 40.));
+      double Lbits_fl = kmin(kmin(fl.Lfl, fl.Wfl), kmin(fl.Tfl, 40.));
       double Abits_fl = (Mbits_fl / p.rho_bergs) / Lbits_fl;
-      double Mbb_fl = fmax(0.58 * dvo08 * (SST + 2.0) / pow(Lbits_fl, 0.2), 0.) * perday;
+      double Mbb_fl = kmax(0.58 * dvo08 * (SST + 2.0) / pow(Lbits_fl, 0.2), 0.) * perday;
       Mbb_fl = p.rho_bergs * Abits_fl * Mbb_fl;
-      dMbitsM_fl = fmin(Mbb_fl * dt, nMbits_fl);
+      dMbitsM_fl = kmin(Mbb_fl * dt, nMbits_fl);
       nMbits_fl = nMbits_fl - dMbitsM_fl;
       if (Mnew_fl == 0.) { dMbitsM_fl = dMbitsM_fl + nMbits_fl; nMbits_fl = 0.; }
     } else {
@@ -677,8 +698,8 @@ __device__ __forceinline__ int thermo_berg(const DevParams& p, const EnvThermo& 
     s.mass_of_fl_bits = Mnew_fl;
     s.mass_of_fl_bergy_bits = nMbits_fl;
     s.thickness = Tn;
-    s.width = fmin(Wn, Ln);
-    s.length = fmax(Wn, Ln);
+    s.width = kmin(Wn, Ln);
+    s.length = kmax(Wn, Ln);
   }
   if (Mnew <= 0.) {
     if (Mnew_fl > 0) {
