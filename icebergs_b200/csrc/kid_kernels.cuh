@@ -243,8 +243,11 @@ __device__ __forceinline__ int thermo_slot(const DevGrid& g, const DevBergs& b, 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // what one berg brings into the step
+// (lon and the thermodynamics-only columns are prefetched into L1 by k_step and loaded at their
+// first use: they would otherwise sit in registers through the momentum solve, where the register
+// file is the limit on resident warps)
 struct BergIn {
-  double lon, lat, uvel, vvel, axn, ayn, bxn, byn, xi, yj, M, T, W, L, mass_scaling, mass_of_bits, heat_density;
+  double lat, uvel, vvel, axn, ayn, bxn, byn, xi, yj, M, T, W, L;
   int i, j;
   uint8_t flags;
 };
@@ -257,13 +260,13 @@ __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, c
   const double dt = p.dt, dt_2 = 0.5 * dt;
   uint8_t flags = in.flags;
   int i = in.i, j = in.j;
-  double lon = in.lon, lat = in.lat, uvel = in.uvel, vvel = in.vvel, xi = in.xi, yj = in.yj;
+  double lon = 0., lat = in.lat, uvel = in.uvel, vvel = in.vvel, xi = in.xi, yj = in.yj;
   double M = in.M, T = in.T, W = in.W, L = in.L;
   if (!(flags & BF_STATIC)) {
     double axn = in.axn, ayn = in.ayn, bxn = in.bxn, byn = in.byn;
     // ---- verlet_stepping I:7203-7328
-    double uvel_prev = uvel - dt_2 * bxn;
-    double vvel_prev = vvel - dt_2 * byn;
+    b.f64[C_UVEL_PREV][s] = uvel - dt_2 * bxn;
+    b.f64[C_VVEL_PREV][s] = vvel - dt_2 * byn;
     double uvel3 = uvel + (dt_2 * axn);
     double vvel3 = vvel + (dt_2 * ayn);
     Env e;
@@ -287,6 +290,7 @@ __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, c
     }
     bool tang = (lat > 89.) && p.grid_is_latlon;
     double uveln, vveln;
+    lon = b.f64[C_LON][s];
     if (tang) tang_velocity(p, lon, uvel3, vvel3, ax1, ay1, dt, uveln, vveln);
     else { uveln = uvel3 + (dt * ax1); vveln = vvel3 + (dt * ay1); }
     if (p.override_iceberg_velocities) { uveln = p.u_override; vveln = p.v_override; }
@@ -294,6 +298,8 @@ __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, c
     // ---- update_verlet_position I:7684-7764 (uses the NEW velocity and accelerations)
     double uvel2 = uvel + (dt_2 * axn) + (dt_2 * bxn);
     double vvel2 = vvel + (dt_2 * ayn) + (dt_2 * byn);
+    b.f64[C_AXN][s] = axn; b.f64[C_AYN][s] = ayn; b.f64[C_BXN][s] = bxn; b.f64[C_BYN][s] = byn;
+    b.f64[C_UVEL][s] = uvel; b.f64[C_VVEL][s] = vvel;
     double lonn, latn;
     if (tang) {
       tang_position(p, lon, lat, uvel2, vvel2, dt, lonn, latn);
@@ -305,10 +311,9 @@ __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, c
     }
     bounced = adjust_index_and_ground(g, p, lonn, latn, i, j, xi, yj, &cnt->error_flags, &cnt->warn_adjust);
     lon = lonn; lat = latn;
-    b.f64[C_UVEL_PREV][s] = uvel_prev; b.f64[C_VVEL_PREV][s] = vvel_prev;
-    b.f64[C_AXN][s] = axn; b.f64[C_AYN][s] = ayn; b.f64[C_BXN][s] = bxn; b.f64[C_BYN][s] = byn;
-    b.f64[C_UVEL][s] = uvel; b.f64[C_VVEL][s] = vvel;
     b.f64[C_LON][s] = lon; b.f64[C_LAT][s] = lat;
+  } else if (i > g.iec || i < g.isc || j > g.jec || j < g.jsc) {
+    lon = b.f64[C_LON][s];
   }
   // ---- send_bergs_to_other_pes, F:2997
   int route = 0;
@@ -328,8 +333,9 @@ __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, c
   else if (route == 2) { b.flags[s] = 0; }
   else {
     // ---- thermodynamics I:2844-3300 at the new position
-    int outcome = thermo_slot<FOOTLOOSE>(g, b, p, s, flags, i, j, xi, yj, uvel, vvel, M, T, W, L, in.mass_scaling,
-                                         in.mass_of_bits, in.heat_density, sc, cnt);
+    int outcome = thermo_slot<FOOTLOOSE>(g, b, p, s, flags, i, j, xi, yj, uvel, vvel, M, T, W, L,
+                                         b.f64[C_MASS_SCALING][s], b.f64[C_MASS_OF_BITS][s], b.f64[C_HEAT_DENSITY][s],
+                                         sc, cnt);
     if (outcome == TH_DELETE) { melted = true; b.flags[s] = 0; }
     else if (outcome == TH_BECAME_FL) { melted = true; became_fl = true; }
   }
@@ -347,13 +353,13 @@ k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
   BergIn in;
   in.flags = b.flags[sl];
   in.i = b.ine[sl]; in.j = b.jne[sl];
-  in.lon = b.f64[C_LON][sl]; in.lat = b.f64[C_LAT][sl];
+  in.lat = b.f64[C_LAT][sl];
   in.uvel = b.f64[C_UVEL][sl]; in.vvel = b.f64[C_VVEL][sl];
   in.axn = b.f64[C_AXN][sl]; in.ayn = b.f64[C_AYN][sl]; in.bxn = b.f64[C_BXN][sl]; in.byn = b.f64[C_BYN][sl];
   in.xi = b.f64[C_XI][sl]; in.yj = b.f64[C_YJ][sl];
   in.M = b.f64[C_MASS][sl]; in.T = b.f64[C_THICKNESS][sl]; in.W = b.f64[C_WIDTH][sl]; in.L = b.f64[C_LENGTH][sl];
-  in.mass_scaling = b.f64[C_MASS_SCALING][sl]; in.mass_of_bits = b.f64[C_MASS_OF_BITS][sl];
-  in.heat_density = b.f64[C_HEAT_DENSITY][sl];
+  prefetch_l1(&b.f64[C_LON][sl]); prefetch_l1(&b.f64[C_MASS_SCALING][sl]);
+  prefetch_l1(&b.f64[C_MASS_OF_BITS][sl]); prefetch_l1(&b.f64[C_HEAT_DENSITY][sl]);
   if (!in_range) in.flags = 0;
   bool owned = (in.flags & BF_ALIVE) && !(in.flags & BF_HALO);
   if (owned && cell_on_pe(g, in.i, in.j)) {
