@@ -190,6 +190,23 @@ class Icebergs:
         self._check(lib().kid_get_bergs(self.handle, C.byref(m), C.byref(c), int(include_halo)))
         return {k: v[: m.value].copy() for k, v in keep.items()}
 
+    def set_bonds(self, **cols):
+        """read_restart_bonds (columns of bonds_iceberg.res.nc, fmsio:473-493); with no columns and
+        manually_initialize_bonds the bonds come from initialize_iceberg_bonds (I:356-441)."""
+        n = len(cols["first_id"]) if cols else 0
+        c, keep = make_columns(n, cls=D.KidBondColumns, **cols)
+        self._check(lib().kid_set_bonds(self.handle, n, C.byref(c)))
+
+    def get_bonds(self) -> dict:
+        n = C.c_int64(0)
+        self._check(lib().kid_get_bonds(self.handle, C.byref(n), None))
+        cap = max(n.value, 1)
+        names = {"first_id", "other_id", "first_ine", "first_jne", "other_ine", "other_jne", "length"}
+        c, keep = make_columns(cap, want=names, cls=D.KidBondColumns)
+        m = C.c_int64(cap)
+        self._check(lib().kid_get_bonds(self.handle, C.byref(m), C.byref(c)))
+        return {k: v[: m.value].copy() for k, v in keep.items()}
+
     def set_calving_state(self, stored_ice=None, stored_heat=None, iceberg_counter_grd=None):
         d = self.domain
         si = _f64(stored_ice, (D.KID_NCLASSES, d.njd, d.nid), "stored_ice")

@@ -16,6 +16,7 @@
 
 #include "kid_kernels.cuh"
 #include "kid_comm.cuh"
+#include "kid_interact.cuh"
 
 using namespace kid;
 
@@ -75,6 +76,13 @@ struct kid_handle {
   long long halo_buf_cells = 0;        // cells x fields each halo buffer holds
   HaloStrips hs_send, hs_recv;
   long long n_sent_last = 0, n_recv_last = 0;
+  // ---- interactions (I:480-804): ghost copies (update_halo_icebergs F:1800) and bonds
+  double *gsend = nullptr, *grecv = nullptr;
+  long long ghost_cap = 0;
+  int ghost_rec_w = 0;
+  int32_t *d_gcounts = nullptr, *d_goffsets = nullptr, *d_gcursor = nullptr;   // [9]
+  int tables_valid = 0, bond_lengths_set = 0;                // cell_start/cell_count describe the current slot order
+  void* spare_b8 = nullptr;            // spare column for the bond arrays (8 B entries)
   std::string err;
   bool fatal = false;
 };
@@ -286,6 +294,7 @@ static int comm_exchange(kid_t* h, const std::vector<XMsg>& sends, const std::ve
         break;
       }
   }
+  if (h->d.nranks == 1) return KID_OK;
   if (h->comm_kind == KID_COMM_NCCL) {
     NcclApi& n = nccl();
     ncclComm_t c = (ncclComm_t)h->comm;
@@ -329,23 +338,30 @@ static int comm_exchange(kid_t* h, const std::vector<XMsg>& sends, const std::ve
 }
 
 // every rank's per-destination send counts, gathered on the host: out[src*nranks + dst]
-static int comm_allgather_counts(kid_t* h, const int32_t* d_counts, int32_t* out) {
+// (w values per rank: w = nranks for the migration counts, 9 for the per-direction ghost counts)
+static int comm_allgather_counts(kid_t* h, const int32_t* d_counts, int32_t* out, int w = 0) {
   const int nr = h->d.nranks, me = h->d.rank;
+  if (w <= 0) w = nr;
+  if (nr == 1) {
+    CK(cudaMemcpyAsync(out, d_counts, sizeof(int32_t) * w, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return KID_OK;
+  }
   if (h->comm_kind == KID_COMM_NCCL) {
     NcclApi& n = nccl();
-    int rc = n.AllGather(d_counts, h->d_all_counts, (size_t)nr, ncclInt32_, (ncclComm_t)h->comm, h->stream);
+    int rc = n.AllGather(d_counts, h->d_all_counts, (size_t)w, ncclInt32_, (ncclComm_t)h->comm, h->stream);
     if (rc != ncclSuccess_) return comm_fail(h, std::string("ncclAllGather failed: ") + (n.GetErrorString ? n.GetErrorString(rc) : "?"));
-    CK(cudaMemcpyAsync(out, h->d_all_counts, sizeof(int32_t) * nr * nr, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(out, h->d_all_counts, sizeof(int32_t) * nr * w, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return KID_OK;
   }
   LocalGroup* G = (LocalGroup*)h->comm;
-  CK(cudaMemcpyAsync(out + (size_t)me * nr, d_counts, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(out + (size_t)me * w, d_counts, sizeof(int32_t) * w, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  { std::lock_guard<std::mutex> lk(G->m); G->counts[me].assign(out + (size_t)me * nr, out + (size_t)(me + 1) * nr); }
+  { std::lock_guard<std::mutex> lk(G->m); G->counts[me].assign(out + (size_t)me * w, out + (size_t)(me + 1) * w); }
   if (!G->barrier()) return comm_fail(h, "in-process group: rendezvous failed (a rank did not arrive)");
   { std::lock_guard<std::mutex> lk(G->m);
-    for (int r = 0; r < nr; r++) for (int q = 0; q < nr; q++) out[(size_t)r * nr + q] = G->counts[r][q]; }
+    for (int r = 0; r < nr; r++) for (int q = 0; q < w; q++) out[(size_t)r * w + q] = G->counts[r][q]; }
   if (!G->barrier()) return comm_fail(h, "in-process group: rendezvous failed (a rank did not arrive)");
   return KID_OK;
 }
@@ -493,9 +509,13 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   else if (pin->use_mixed_melting || pin->melt_icebergs_as_ice_shelf) unsupported = "ice-shelf melt (find_basal_melt) is not implemented";
   else if (pin->add_iceberg_thickness_to_ssh) unsupported = "add_iceberg_thickness_to_SSH is not implemented";
   else if (pin->mts || pin->dem) unsupported = "MTS/DEM stepping is not implemented in this build";
-  else if (pin->iceberg_bonds_on) unsupported = "bonds are not implemented in this build";
-  else if (pin->interactive_icebergs_on) unsupported = "interactive_icebergs_on is not implemented in this build";
+  else if ((pin->interactive_icebergs_on || pin->iceberg_bonds_on) &&
+           (pin->contact_distance > 0. || (pin->contact_spring_coef > 0. && pin->contact_spring_coef != pin->spring_coef)))
+    unsupported = "contact_distance>0 / contact_spring_coef != spring_coef (conglomerate contact search) is not implemented in this build";
+  else if (pin->iceberg_bonds_on && !pin->interactive_icebergs_on) unsupported = "iceberg_bonds_on needs interactive_icebergs_on";
+  else if (pin->iceberg_bonds_on && (pin->max_bonds < 1 || pin->max_bonds > 12)) unsupported = "max_bonds must be 1..12";
   else if (pin->footloose) unsupported = "footloose calving is not implemented in this build";
+  else if (pin->iceberg_bonds_on && dom->nranks > 1) unsupported = "bonds across ranks are not implemented in this build";
   else if (dom->cyclic_y) unsupported = "cyclic y is not implemented";
   else if (pin->halo < 2) unsupported = "halo must be >= 2";
   if (unsupported) { g_init_error = std::string("kid_init: ") + unsupported; return KID_ERR_UNSUPPORTED; }
@@ -544,7 +564,7 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
         if (qx < 0 || qx >= L.lx) { if (d->cyclic_x) qx = (qx + L.lx) % L.lx; else ok = false; }
         if (qy < 0 || qy >= L.ly) { if (d->cyclic_y) qy = (qy + L.ly) % L.ly; else ok = false; }
         if (ok) r = qx + L.lx * qy;
-        h->nbr[dir_of(dx, dy)] = (d->nranks > 1) ? r : -1;
+        h->nbr[dir_of(dx, dy)] = r;
       }
     h->nbr[4] = -1;
     h->comm_kind = d->comm_kind; h->comm = d->nccl_comm;
@@ -718,6 +738,34 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   CK(cudaMalloc(&h->spare4, 4 * h->capacity));
   CK(cudaMalloc(&h->spare1, h->capacity));
   CK(cudaMalloc(&h->perm, sizeof(int32_t) * h->capacity));
+  {
+    const int nr = d->nranks, w = std::max(nr, 9);
+    CK(cudaMallocHost(&h->h_all_counts, sizeof(int32_t) * nr * w));
+    if (nr > 1) CK(cudaMalloc(&h->d_all_counts, sizeof(int32_t) * nr * w));
+  }
+  if (q->interactive_icebergs_on) {
+    b.max_bonds = q->iceberg_bonds_on ? q->max_bonds : 0;
+    if (b.max_bonds > 0) {
+      size_t nb = (size_t)h->capacity * b.max_bonds;
+      CK(cudaMalloc(&b.bond_other_id, sizeof(int64_t) * nb));
+      CK(cudaMalloc(&b.bond_other_slot, sizeof(int32_t) * nb));
+      CK(cudaMalloc(&b.bond_other_ine, sizeof(int32_t) * nb));
+      CK(cudaMalloc(&b.bond_other_jne, sizeof(int32_t) * nb));
+      CK(cudaMalloc(&b.bond_length, sizeof(double) * nb));
+      CK(cudaMemsetAsync(b.bond_other_id, 0, sizeof(int64_t) * nb, h->stream));
+      CK(cudaMemsetAsync(b.bond_other_slot, 0xff, sizeof(int32_t) * nb, h->stream));
+      CK(cudaMemsetAsync(b.bond_other_ine, 0, sizeof(int32_t) * nb, h->stream));
+      CK(cudaMemsetAsync(b.bond_other_jne, 0, sizeof(int32_t) * nb, h->stream));
+      CK(cudaMemsetAsync(b.bond_length, 0, sizeof(double) * nb, h->stream));
+    }
+    h->ghost_rec_w = PACK_W + 3 * b.max_bonds;
+    h->ghost_cap = std::max<long long>(4096, h->capacity / 2);
+    CK(cudaMalloc(&h->gsend, sizeof(double) * h->ghost_rec_w * h->ghost_cap));
+    CK(cudaMalloc(&h->grecv, sizeof(double) * h->ghost_rec_w * h->ghost_cap));
+    CK(cudaMalloc(&h->d_gcounts, sizeof(int32_t) * 9));
+    CK(cudaMalloc(&h->d_goffsets, sizeof(int32_t) * 9));
+    CK(cudaMalloc(&h->d_gcursor, sizeof(int32_t) * 9));
+  }
   if (d->nranks > 1) {
     const int nr = d->nranks;
     h->xbuf_cap = std::max<long long>(65536, h->capacity / 8);
@@ -729,8 +777,6 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
     CK(cudaMalloc(&h->d_send_counts, sizeof(int32_t) * nr));
     CK(cudaMalloc(&h->d_cursor, sizeof(int32_t) * nr));
     CK(cudaMalloc(&h->d_offsets, sizeof(int32_t) * nr));
-    CK(cudaMalloc(&h->d_all_counts, sizeof(int32_t) * nr * nr));
-    CK(cudaMallocHost(&h->h_all_counts, sizeof(int32_t) * nr * nr));
     CK(cudaMallocHost(&h->h_offsets, sizeof(int32_t) * nr));
   }
   CK(cudaMalloc(&h->cell_count, sizeof(int32_t) * n2));
@@ -789,6 +835,9 @@ extern "C" int32_t kid_end(kid_t** hp) {
   if (h->h_all_counts) cudaFreeHost(h->h_all_counts);
   if (h->h_offsets) cudaFreeHost(h->h_offsets);
   cudaFree(h->halo_send); cudaFree(h->halo_recv);
+  cudaFree(h->gsend); cudaFree(h->grecv); cudaFree(h->d_gcounts); cudaFree(h->d_goffsets); cudaFree(h->d_gcursor);
+  cudaFree(h->b.bond_other_id); cudaFree(h->b.bond_other_slot); cudaFree(h->b.bond_other_ine);
+  cudaFree(h->b.bond_other_jne); cudaFree(h->b.bond_length);
   for (auto& e : h->ev) cudaEventDestroy(e);
   for (auto& e : h->ev_pool) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
@@ -815,6 +864,8 @@ static int check_device_errors(kid_t* h) {
     if (e & KID_DEVERR_LOST_BERG) return fail(h, KID_ERR_STATE, "KID, unpack_berg_from_buffer: can not find a cell to place berg in!");
     if (e & 64u) return fail(h, KID_ERR_STATE, "KID, interp fields: field interpaolations has NaNs");
     if (e & 128u) return fail(h, KID_ERR_STATE, "KID, calve_icebergs: berg is not in the correct cell!");
+    if (e & 256u) return fail(h, KID_ERR_STATE, "KID, connect_all_bonds: A non-halo bond is missing!!!");
+    if (e & 512u) return fail(h, KID_ERR_CAPACITY, "kid: a berg has more than max_bonds bonds");
     return fail(h, KID_ERR_STATE, "kid: device error flag set");
   }
   return KID_OK;
@@ -836,8 +887,8 @@ static void gather_cols(kid_t* h, T** cols, int ncols, T** spare, long long n_ne
 
 static int sort_bergs(kid_t* h) {
   long long n2 = h->n2, ns = h->n_slots;
-  if (ns <= 0) { h->steps_since_sort = 0; return KID_OK; }
   CK(cudaMemsetAsync(h->cell_count, 0, sizeof(int32_t) * n2, h->stream));
+  if (ns <= 0) { h->steps_since_sort = 0; h->tables_valid = 1; return KID_OK; }
   CK(cudaMemsetAsync(h->cell_fill, 0, sizeof(int32_t) * n2, h->stream));
   LAUNCH(h, k_hist, ns, 256, h->g, h->b.flags, h->b.ine, h->b.jne, ns, h->cell_count);
   int nsb = (int)((n2 + KID_SCAN_ITEMS - 1) / KID_SCAN_ITEMS);
@@ -870,6 +921,25 @@ static int sort_bergs(kid_t* h) {
   gather_cols<uint8_t>(h, bcols, 1, &sp1, n_new);
   h->b.halo_code = bcols[0];
   h->spare1 = sp1;
+  if (h->b.max_bonds > 0) {
+    // bond entries travel with their berg; partners are re-resolved by connect_bonds() (slots changed)
+    const long long cap = h->capacity;
+    for (int k = 0; k < h->b.max_bonds; k++) {
+      { GatherArgs<int64_t, 1> a; a.src[0] = h->b.bond_other_id + k * cap; a.dst[0] = (int64_t*)h->spare8;
+        LAUNCH(h, (k_gather<int64_t, 1>), n_new, 256, a, h->perm, n_new);
+        CK(cudaMemcpyAsync(h->b.bond_other_id + k * cap, h->spare8, sizeof(int64_t) * n_new, cudaMemcpyDeviceToDevice, h->stream)); }
+      { GatherArgs<double, 1> a; a.src[0] = h->b.bond_length + k * cap; a.dst[0] = (double*)h->spare8;
+        LAUNCH(h, (k_gather<double, 1>), n_new, 256, a, h->perm, n_new);
+        CK(cudaMemcpyAsync(h->b.bond_length + k * cap, h->spare8, sizeof(double) * n_new, cudaMemcpyDeviceToDevice, h->stream)); }
+      int32_t* i32s[2] = {h->b.bond_other_ine + k * cap, h->b.bond_other_jne + k * cap};
+      for (int32_t* col : i32s) {
+        GatherArgs<int32_t, 1> a; a.src[0] = col; a.dst[0] = (int32_t*)h->spare4;
+        LAUNCH(h, (k_gather<int32_t, 1>), n_new, 256, a, h->perm, n_new);
+        CK(cudaMemcpyAsync(col, h->spare4, sizeof(int32_t) * n_new, cudaMemcpyDeviceToDevice, h->stream));
+      }
+    }
+  }
+  h->tables_valid = 1;
   unsigned long long nn = (unsigned long long)n_new;
   CK(cudaMemcpyAsync(&h->dcnt->n_slots, &nn, sizeof(nn), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -877,6 +947,75 @@ static int sort_bergs(kid_t* h) {
   h->steps_since_sort = 0;
   h->dirty_appended = 0;
   h->sorted_once = 1;
+  return KID_OK;
+}
+
+
+// ------------------------------------------------------- ghosts and bonds
+// update_halo_icebergs F:1800-2131: the halo copies are dropped and rebuilt from the owners'
+// current state; a copy goes straight to each of the 8 neighbours whose halo covers the berg's
+// cell (the reference relays corners through the E/W neighbour, F:1976-2006).
+static int rebuild_ghosts(kid_t* h) {
+  const int me = h->d.rank;
+  LAUNCH(h, k_clear_halo, h->n_slots, 256, h->b.flags, h->n_slots);
+  GhostPlan gp;
+  for (int k = 0; k < 9; k++) gp.nbr[k] = h->nbr[k];
+  gp.hw = h->p.halo; gp.isc = h->d.isc; gp.iec = h->d.iec; gp.jsc = h->d.jsc; gp.jec = h->d.jec;
+  CK(cudaMemsetAsync(h->d_gcounts, 0, sizeof(int32_t) * 9, h->stream));
+  CK(cudaMemsetAsync(h->d_gcursor, 0, sizeof(int32_t) * 9, h->stream));
+  LAUNCH(h, k_ghost_count, h->n_slots, 256, gp, h->b.flags, h->b.ine, h->b.jne, h->n_slots, h->d_gcounts);
+  int rc = comm_allgather_counts(h, h->d_gcounts, h->h_all_counts, 9);
+  if (rc) return rc;
+  int32_t off[9];
+  long long n_send = 0, n_recv = 0;
+  std::vector<XMsg> sends, recvs;
+  const int w = h->ghost_rec_w;
+  for (int k = 0; k < 9; k++) {
+    off[k] = (int32_t)n_send;
+    long long c = (k == 4) ? 0 : h->h_all_counts[(size_t)me * 9 + k];
+    if (c > 0) sends.push_back({h->nbr[k], k, h->gsend + (size_t)n_send * w, c * w});
+    n_send += c;
+  }
+  for (int k = 0; k < 9; k++) {      // what the neighbour on side 8-k sent in its direction k
+    int src = (k == 4) ? -1 : h->nbr[8 - k];
+    if (src < 0) continue;
+    long long c = h->h_all_counts[(size_t)src * 9 + k];
+    if (c > 0) recvs.push_back({src, k, h->grecv + (size_t)n_recv * w, c * w});
+    n_recv += c;
+  }
+  if (n_send > h->ghost_cap || n_recv > h->ghost_cap) return fail(h, KID_ERR_CAPACITY, "kid: ghost buffer capacity exceeded");
+  if (h->n_slots + n_recv > h->capacity) return fail(h, KID_ERR_CAPACITY, "kid: berg store capacity exceeded by halo copies");
+  CK(cudaMemcpyAsync(h->d_goffsets, off, sizeof(off), cudaMemcpyHostToDevice, h->stream));
+  if (n_send > 0) LAUNCH(h, k_ghost_pack, h->n_slots, 128, gp, h->b, h->n_slots, h->d_goffsets, h->d_gcursor, h->gsend, w);
+  CK(cudaStreamSynchronize(h->stream));     // off[] is a stack array
+  rc = comm_exchange(h, sends, recvs);
+  if (rc) return rc;
+  if (n_recv > 0) {
+    LAUNCH(h, k_ghost_unpack, n_recv, 128, h->g, h->b, h->dp, h->dcnt, h->grecv, n_recv, h->n_slots, w);
+    h->n_slots += n_recv;
+    unsigned long long nn = (unsigned long long)h->n_slots;
+    CK(cudaMemcpyAsync(&h->dcnt->n_slots, &nn, sizeof(nn), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  h->tables_valid = 0;
+  return KID_OK;
+}
+
+static int sort_bergs(kid_t* h);
+
+// the tail of an interactive step (I:5463-5478): halo copies, update_latlon (inside
+// connect_all_bonds F:4994 when bonds are on, directly otherwise), re-sort, reconnect bonds
+static int refresh_interactive_state(kid_t* h) {
+  int rc = rebuild_ghosts(h);
+  if (rc) return rc;
+  bool edge = (h->d.isc == 1) || (h->d.iec == h->d.gni);      // rank touches min/max lon, F:5143
+  if (h->p.Lx > 0. && edge) LAUNCH(h, k_update_latlon, h->n_slots, 128, h->g, h->b, h->dp, h->dcnt, h->n_slots);
+  rc = sort_bergs(h);
+  if (rc) return rc;
+  if (h->b.max_bonds > 0) {
+    CellTable ct{h->cell_start, h->cell_count};
+    LAUNCH(h, k_connect_bonds, h->n_slots, 128, h->g, h->b, ct, h->dcnt, h->n_slots);
+  }
   return KID_OK;
 }
 
@@ -1036,16 +1175,120 @@ extern "C" int32_t kid_get_bergs(kid_t* h, int64_t* n, KidBergColumns* c, int32_
   return KID_OK;
 }
 
+// read_restart_bonds (fmsio:1282-1430) / initialize_iceberg_bonds (I:356-441), then the sequence of
+// icebergs_init I:150-167: halo copies, (second manual pass over owners + copies), connect_all_bonds.
 extern "C" int32_t kid_set_bonds(kid_t* h, int64_t nb, const KidBondColumns* c) {
-  (void)c;
-  if (!h) return KID_ERR_ARG;
-  if (nb == 0) return KID_OK;
-  return fail(h, KID_ERR_UNSUPPORTED, "kid_set_bonds: bonds are not implemented in this build");
+  if (!h || nb < 0) return KID_ERR_ARG;
+  if (h->fatal) return KID_ERR_STATE;
+  if (!h->p.iceberg_bonds_on) {
+    if (nb == 0) return KID_OK;
+    return fail(h, KID_ERR_STATE, "kid_set_bonds: iceberg_bonds_on is off");
+  }
+  cudaSetDevice(h->d.device);
+  DevBergs& b = h->b;
+  const long long cap = h->capacity, ns = h->n_slots;
+  const int mb = b.max_bonds;
+  int rc = KID_OK;
+  if (nb > 0) {
+    if (!c || !c->first_id || !c->other_id) return fail(h, KID_ERR_ARG, "kid_set_bonds: first_id and other_id are required");
+    // host-side placement: file order per berg; form_a_bond puts each new bond at the front (F:4818), i.e.
+    // entry k is the k-th bond of the berg in file order and the list is walked from the last entry
+    std::vector<int64_t> ids((size_t)ns);
+    std::vector<uint8_t> fl((size_t)ns);
+    std::vector<int32_t> bi((size_t)ns), bj((size_t)ns);
+    CK(cudaMemcpy(ids.data(), b.id, sizeof(int64_t) * ns, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(fl.data(), b.flags, ns, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(bi.data(), b.ine, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(bj.data(), b.jne, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost));
+    std::vector<std::pair<int64_t, long long>> by_id;
+    for (long long s = 0; s < ns; s++) if ((fl[s] & BF_ALIVE) && !(fl[s] & BF_HALO)) by_id.push_back({ids[s], s});
+    std::sort(by_id.begin(), by_id.end());
+    auto slot_of = [&](int64_t id) -> long long {
+      auto it = std::lower_bound(by_id.begin(), by_id.end(), std::make_pair(id, (long long)-1));
+      return (it != by_id.end() && it->first == id) ? it->second : -1;
+    };
+    std::vector<int64_t> oid((size_t)cap * mb, 0);
+    std::vector<int32_t> oi((size_t)cap * mb, 0), oj((size_t)cap * mb, 0), osl((size_t)cap * mb, -1);
+    std::vector<double> len((size_t)cap * mb, 0.);
+    std::vector<int> fill((size_t)ns, 0);
+    for (int64_t k = 0; k < nb; k++) {
+      long long s = slot_of(c->first_id[k]);
+      if (s < 0) continue;                       // a bond of a berg that lives on another rank
+      if (c->first_id[k] == c->other_id[k]) continue;
+      if (fill[s] >= mb) return fail(h, KID_ERR_CAPACITY, "kid_set_bonds: a berg has more than max_bonds bonds");
+      size_t e = (size_t)fill[s]++ * cap + s;
+      oid[e] = c->other_id[k];
+      long long o = slot_of(c->other_id[k]);
+      oi[e] = c->other_ine ? c->other_ine[k] : (o >= 0 ? bi[o] : 0);
+      oj[e] = c->other_jne ? c->other_jne[k] : (o >= 0 ? bj[o] : 0);
+      len[e] = c->length ? c->length[k] : 0.;
+    }
+    CK(cudaMemcpy(b.bond_other_id, oid.data(), sizeof(int64_t) * oid.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b.bond_other_ine, oi.data(), sizeof(int32_t) * oi.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b.bond_other_jne, oj.data(), sizeof(int32_t) * oj.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b.bond_other_slot, osl.data(), sizeof(int32_t) * osl.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b.bond_length, len.data(), sizeof(double) * len.size(), cudaMemcpyHostToDevice));
+  } else if (h->p.manually_initialize_bonds) {
+    LAUNCH(h, k_init_bonds, ns, 64, h->g, h->b, h->dp, h->dcnt, ns, h->p.length_for_manually_initialize_bonds,
+           h->p.manually_initialize_bonds_from_radii);
+  }
+  rc = rebuild_ghosts(h);                        // update_halo_icebergs I:157
+  if (rc) return rc;
+  if (nb == 0 && h->p.manually_initialize_bonds) {
+    rc = sort_bergs(h);
+    if (rc) return rc;
+    LAUNCH(h, k_init_bonds, h->n_slots, 64, h->g, h->b, h->dp, h->dcnt, h->n_slots, h->p.length_for_manually_initialize_bonds,
+           h->p.manually_initialize_bonds_from_radii);     // second pass: bonds to the halo copies, I:158
+  }
+  rc = refresh_interactive_state(h);             // update_halo_icebergs + connect_all_bonds, I:162-163
+  if (rc) return rc;
+  h->bond_lengths_set = 0;
+  return check_device_errors(h);
 }
+
 extern "C" int32_t kid_get_bonds(kid_t* h, int64_t* nb, KidBondColumns* c) {
-  (void)c;
   if (!h || !nb) return KID_ERR_ARG;
+  cudaSetDevice(h->d.device);
+  const int64_t room = *nb;
   *nb = 0;
+  DevBergs& b = h->b;
+  const int mb = b.max_bonds;
+  if (mb == 0) return KID_OK;
+  const long long cap = h->capacity, ns = h->n_slots;
+  CK(cudaStreamSynchronize(h->stream));
+  std::vector<int64_t> ids((size_t)ns), oid((size_t)cap * mb);
+  std::vector<uint8_t> fl((size_t)ns);
+  std::vector<int32_t> bi((size_t)ns), bj((size_t)ns), oi((size_t)cap * mb), oj((size_t)cap * mb);
+  std::vector<double> len((size_t)cap * mb);
+  CK(cudaMemcpy(ids.data(), b.id, sizeof(int64_t) * ns, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(fl.data(), b.flags, ns, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(bi.data(), b.ine, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(bj.data(), b.jne, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(oid.data(), b.bond_other_id, sizeof(int64_t) * oid.size(), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(oi.data(), b.bond_other_ine, sizeof(int32_t) * oi.size(), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(oj.data(), b.bond_other_jne, sizeof(int32_t) * oj.size(), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(len.data(), b.bond_length, sizeof(double) * len.size(), cudaMemcpyDeviceToHost));
+  int64_t n = 0;
+  for (long long s = 0; s < ns; s++) {
+    if (!(fl[s] & BF_ALIVE) || (fl[s] & (BF_HALO | BF_LEAVER))) continue;
+    for (int k = mb - 1; k >= 0; k--) {          // list order: newest first
+      size_t e = (size_t)k * cap + s;
+      if (oid[e] == 0) continue;
+      if (c && n < room) {
+        if (c->first_id) c->first_id[n] = ids[s];
+        if (c->other_id) c->other_id[n] = oid[e];
+        if (c->first_ine) c->first_ine[n] = bi[s];
+        if (c->first_jne) c->first_jne[n] = bj[s];
+        if (c->other_ine) c->other_ine[n] = oi[e];
+        if (c->other_jne) c->other_jne[n] = oj[e];
+        if (c->length) c->length[n] = len[e];
+        if (c->broken) c->broken[n] = 0;
+      }
+      n++;
+    }
+  }
+  *nb = n;
+  if (c && n > room) return fail(h, KID_ERR_CAPACITY, "kid_get_bonds: caller arrays too small");
   return KID_OK;
 }
 
@@ -1204,6 +1447,7 @@ static int step_core(kid_t* h) {
     CK(cudaStreamSynchronize(s));
     long long ns = (long long)h->hcnt->n_slots;
     if (ns > h->capacity) return fail(h, KID_ERR_CAPACITY, "kid: berg store capacity exceeded by calving");
+    if (ns != h->n_slots) h->tables_valid = 0;
     h->dirty_appended += ns - h->n_slots;
     h->n_slots = ns;
   }
@@ -1212,8 +1456,27 @@ static int step_core(kid_t* h) {
   CK(cudaEventRecord(h->ev[T_MOMENTUM], s));
   cudaEvent_t e0 = pool_event(h), ek = pool_event(h), e1 = pool_event(h), e2 = pool_event(h);
   CK(cudaEventRecord(e0, s));
+  const bool ia = h->p.interactive_icebergs_on != 0;
+  if (ia) {
+    // the neighbour search walks the cell tables of the sort: appended bergs (calving) invalidate them
+    if (!h->tables_valid) {
+      int rc = sort_bergs(h);
+      if (rc) return rc;
+      if (h->b.max_bonds > 0) { CellTable ct{h->cell_start, h->cell_count}; LAUNCH(h, k_connect_bonds, h->n_slots, 128, h->g, h->b, ct, h->dcnt, h->n_slots); }
+    }
+    if (h->b.max_bonds > 0 && !h->bond_lengths_set) {      // first visit, I:5420
+      LAUNCH(h, k_orig_bond_length, h->n_slots, 128, h->b, h->n_slots);
+      h->bond_lengths_set = 1;
+    }
+  }
   if (!h->p.static_icebergs) {
-    if (h->p.melt_diagnostics) launch_step<false, true>(h); else launch_step<false, false>(h);
+    if (ia) {
+      CellTable ct{h->cell_start, h->cell_count};
+      LAUNCH(h, k_ia_velocity, h->n_slots, KID_BLOCK, h->g, h->b, h->dp, ct, h->dcnt, h->n_slots);
+      if (h->p.melt_diagnostics) { LAUNCH(h, (k_step<false, true, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
+      else { LAUNCH(h, (k_step<false, false, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
+      if (h->b.max_bonds > 0) LAUNCH(h, k_bond_address_update, h->n_slots, 128, h->b, h->n_slots);
+    } else if (h->p.melt_diagnostics) launch_step<false, true>(h); else launch_step<false, false>(h);
   } else {
     if (h->p.melt_diagnostics) { LAUNCH(h, (k_thermo_range<false, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, 0LL, h->n_slots, 1); }
     else { LAUNCH(h, (k_thermo_range<false, false>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, 0LL, h->n_slots, 1); }
@@ -1230,12 +1493,16 @@ static int step_core(kid_t* h) {
       else { LAUNCH(h, (k_thermo_range<false, false>), n_recv, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s0, s1, 0); }
       h->n_slots = s1;
       h->dirty_appended += n_recv;
+      h->tables_valid = 0;
     }
   }
   CK(cudaEventRecord(h->ev[T_SORT], s));
   CK(cudaEventRecord(e1, s));
   h->steps_since_sort++;
-  if (h->steps_since_sort >= h->sort_interval || h->dirty_appended > h->n_slots / 8) {
+  if (ia) {
+    int rc = refresh_interactive_state(h);
+    if (rc) return rc;
+  } else if (h->steps_since_sort >= h->sort_interval || h->dirty_appended > h->n_slots / 8) {
     int rc = sort_bergs(h);
     if (rc) return rc;
   }

@@ -125,6 +125,12 @@ struct DevBergs {
   uint8_t *flags, *halo_code;
   int32_t* leaver_list;       // slots of the bergs that left the tile this step (multi-rank only)
   int64_t leaver_cap;
+  // bonds, type(bond) F:362-386: max_bonds half-bonds per berg, entry k of slot s at [k*capacity + s];
+  // other_id == 0 marks an empty entry, other_slot is re-resolved after every sort (connect_all_bonds F:4963)
+  int32_t max_bonds, pad_;
+  int64_t* bond_other_id;
+  int32_t *bond_other_slot, *bond_other_ine, *bond_other_jne;
+  double* bond_length;
 };
 
 // device-side counters (one struct in HBM per handle)

@@ -1,0 +1,402 @@
+// kid_interact.cuh -- berg-berg interactions of the single-time-step (STS) scheme.
+//
+//   calculate_force     I:611-804   spring + damping projectors between two elements
+//   interactive_force   I:480-607   3x3 neighbour sweep over the cell-sorted store (+ bond loop)
+//   k_ia_velocity       first sweep of evolve_icebergs (I:7106-7175) with interactions on:
+//                       verlet_stepping/accel for every owned berg, positions untouched
+//   (the second sweep -- update_verlet_position, *_old refresh I:7182-7197 -- send_bergs and
+//    thermodynamics run in k_step<.., SPLIT=true>)
+//   k_clear_halo / k_ghost_* / k_update_latlon   update_halo_icebergs F:1800, update_latlon F:5128
+//
+// The per-cell linked lists of the reference are the cell_start/cell_count tables of the counting
+// sort: in interactive runs the store is re-sorted every step, so the bergs of a cell are a
+// contiguous slot range.  In-cell order is ascending previous slot, not the reference's
+// (start_year, start_day, ...) order (F:4318): only the rounding of the force sums depends on it.
+#pragma once
+#include "kid_physics.cuh"
+
+namespace kid {
+
+struct CellTable { const int32_t* start; const int32_t* count; };
+
+// I:611-804.  s = primary berg, o = other berg (slots).
+__device__ __forceinline__ void calculate_force(const DevBergs& b, const DevParams& p, long long s, long long o,
+                                                IAcc& A, double u0, double v0, double u1, double v1, bool bonded) {
+  if (b.id[s] == b.id[o]) return;
+  if (b.f64[C_FL_K][s] == -1. || b.f64[C_FL_K][o] == -1.) return;
+  double lon1 = b.f64[C_LON_OLD][s], lat1 = b.f64[C_LAT_OLD][s];
+  double lon2 = b.f64[C_LON_OLD][o], lat2 = b.f64[C_LAT_OLD][o];
+  double u2 = b.f64[C_UVEL_OLD][o], v2 = b.f64[C_VVEL_OLD][o];
+  double M1 = b.f64[C_MASS][s], A1 = b.f64[C_LENGTH][s] * b.f64[C_WIDTH][s];
+  double M2 = b.f64[C_MASS][o], A2 = b.f64[C_LENGTH][o] * b.f64[C_WIDTH][o];
+  double dlon = lon1 - lon2, dlat = lat1 - lat2;
+  double lat_ref = 0.5 * (lat1 + lat2), dx_dlon, dy_dlat;
+  convert_from_grid_to_meters(p, lat_ref, dx_dlon, dy_dlat);
+  double r_dist_x = dlon * dx_dlon, r_dist_y = dlat * dy_dlat;
+  double r_dist = sqrt((r_dist_x * r_dist_x) + (r_dist_y * r_dist_y));
+  double R1, R2;
+  if (p.hexagonal_icebergs) { R1 = sqrt(A1 / (2. * sqrt(3.))); R2 = sqrt(A2 / (2. * sqrt(3.))); }
+  else if (p.iceberg_bonds_on) { R1 = 0.5 * sqrt(A1); R2 = 0.5 * sqrt(A2); }
+  else { R1 = sqrt(A1 / p.pi); R2 = sqrt(A2 / p.pi); }
+  double M_min = M1 < M2 ? M1 : M2;
+  double crit_dist, spring_coef;
+  if (bonded) { crit_dist = R1 + R2; spring_coef = p.spring_coef; }
+  else { spring_coef = p.contact_spring_coef; crit_dist = fmax(R1 + R2, p.contact_distance); }
+  double radial_damping_coef = p.radial_damping_coef, tangental_damping_coef = p.tangental_damping_coef;
+  if (p.critical_interaction_damping_on) {
+    radial_damping_coef = 2. * sqrt(spring_coef);
+    if (p.tang_crit_int_damp_on) tangental_damping_coef = (2. * sqrt(spring_coef)) / 4;
+  }
+  bool tbonded = bonded;
+  // STS with contact_distance = 0 and one spring constant: a bond only pulls (I:741-748)
+  if (bonded && !(r_dist > crit_dist)) tbonded = false;
+  if ((r_dist > 0.) && (tbonded || (r_dist < crit_dist && !bonded))) {
+    double accel_spring = spring_coef * (M_min / M1) * (crit_dist - r_dist);
+    A.IA_x = A.IA_x + (accel_spring * (r_dist_x / r_dist));
+    A.IA_y = A.IA_y + (accel_spring * (r_dist_y / r_dist));
+    double r2 = r_dist * r_dist;
+    double P_11 = (r_dist_x * r_dist_x) / r2, P_12 = (r_dist_x * r_dist_y) / r2, P_22 = (r_dist_y * r_dist_y) / r2;
+    double P_21 = P_12;
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {
+      double p_ia_coef = (pass == 0 ? radial_damping_coef : tangental_damping_coef) * (M_min / M1);
+      if (p.scale_damping_by_pmag) {
+        double a1 = ((P_11 * (u2 - u1)) + (P_12 * (v2 - v1))), a2 = ((P_12 * (u2 - u1)) + (P_22 * (v2 - v1)));
+        double b1 = ((P_11 * (u2 - u0)) + (P_12 * (v2 - v0))), b2 = ((P_12 * (u2 - u0)) + (P_22 * (v2 - v0)));
+        p_ia_coef = p_ia_coef * (0.5 * (sqrt((a1 * a1) + (a2 * a2)) + sqrt((b1 * b1) + (b2 * b2))));
+      }
+      A.P11 = A.P11 + p_ia_coef * P_11; A.P12 = A.P12 + p_ia_coef * P_12;
+      A.P21 = A.P21 + p_ia_coef * P_21; A.P22 = A.P22 + p_ia_coef * P_22;
+      A.Pu_x = A.Pu_x + (p_ia_coef * ((P_11 * u2) + (P_12 * v2)));
+      A.Pu_y = A.Pu_y + (p_ia_coef * ((P_12 * u2) + (P_22 * v2)));
+      P_11 = 1 - P_11; P_12 = -P_12; P_21 = -P_21; P_22 = 1 - P_22;      // normal -> tangential projector
+    }
+  }
+}
+
+// I:480-607, the branch for STS with contact_distance = 0 and one spring constant (I:577-605)
+__device__ __forceinline__ void interactive_force(const DevGrid& g, const DevBergs& b, const DevParams& p,
+                                                  const CellTable& ct, long long s, int i, int j, IAcc& A,
+                                                  double u0, double v0, double u1, double v1) {
+  A.IA_x = A.IA_y = A.P11 = A.P12 = A.P21 = A.P22 = A.Pu_x = A.Pu_y = 0.;
+  if (b.f64[C_FL_K][s] == -1.) return;
+  for (int grdj = j - 1; grdj <= j + 1; grdj++)
+    for (int grdi = i - 1; grdi <= i + 1; grdi++) {
+      if (grdi < g.isd || grdi > g.ied || grdj < g.jsd || grdj > g.jed) continue;
+      int c = gidx(g, grdi, grdj);
+      int n = ct.count[c];
+      long long o0 = ct.start[c];
+      for (int k = 0; k < n; k++) calculate_force(b, p, s, o0 + k, A, u0, v0, u1, v1, false);
+    }
+  if (p.iceberg_bonds_on) {
+    // bonds were formed at the front of the list (F:4818): newest first
+    for (int k = b.max_bonds - 1; k >= 0; k--) {
+      long long slot = (long long)k * b.capacity + s;
+      if (b.bond_other_id[slot] == 0) continue;
+      int32_t o = b.bond_other_slot[slot];
+      if (o < 0) continue;        // unmatched halo bond (connect_all_bonds F:5059: not an error for halo bergs)
+      calculate_force(b, p, s, o, A, u0, v0, u1, v1, true);
+    }
+  }
+}
+
+// first sweep of evolve_icebergs with interactions on: I:7106-7175 (verlet_stepping I:7203, accel I:1950)
+__global__ void __launch_bounds__(KID_BLOCK)
+k_ia_velocity(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
+              const __grid_constant__ DevParams p, const CellTable ct, DevCounters* __restrict__ cnt, long long n_slots) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  uint8_t flags = b.flags[s];
+  if (!(flags & BF_ALIVE) || (flags & (BF_HALO | BF_STATIC))) return;
+  const double dt = p.dt, dt_2 = 0.5 * dt;
+  int i = b.ine[s], j = b.jne[s];
+  double lon = b.f64[C_LON][s], lat = b.f64[C_LAT][s], uvel = b.f64[C_UVEL][s], vvel = b.f64[C_VVEL][s];
+  double axn = b.f64[C_AXN][s], ayn = b.f64[C_AYN][s], bxn = b.f64[C_BXN][s], byn = b.f64[C_BYN][s];
+  double xi = b.f64[C_XI][s], yj = b.f64[C_YJ][s];
+  double M = b.f64[C_MASS][s], T = b.f64[C_THICKNESS][s], W = b.f64[C_WIDTH][s], L = b.f64[C_LENGTH][s];
+  double uvel_prev = uvel - dt_2 * bxn, vvel_prev = vvel - dt_2 * byn;
+  double uvel3 = uvel + (dt_2 * axn), vvel3 = vvel + (dt_2 * ayn);
+  Env e;
+  if (!interp_flds(g, p, i, j, xi, yj, e)) atomicOr(&cnt->error_flags, 64u);
+  double sin_lat = 0., cos_lat = 1.;
+  if (p.grid_is_latlon) sincos_halfpi(p.pi_180 * lat, &sin_lat, &cos_lat);
+  double f_cori = (p.grid_is_latlon && !p.use_f_plane) ? p.omega2 * sin_lat : p.f_cori_plane;
+  double dragfrac = 1.0;
+  if (p.iceberg_bonds_on && p.internal_bergs_for_drag) {       // I:2104-2120
+    double N_bonds = 0., N_max = p.hexagonal_icebergs ? 6.0 : 4.0;
+    for (int k = 0; k < b.max_bonds; k++) if (b.bond_other_id[(long long)k * b.capacity + s] != 0) N_bonds += 1.0;
+    dragfrac = ((N_max - N_bonds) / N_max);
+  }
+  IAcc ia;
+  interactive_force(g, b, p, ct, s, i, j, ia, uvel, vvel, uvel, vvel);      // I:2153
+  double ax1, ay1, un_l, vn_l;
+  const double u0 = uvel, v0 = vvel;
+  accel_core<true>(p, M, T, W, L, f_cori, uvel, vvel, dt, e, dragfrac, ia,
+                   [&](double us, double vs, IAcc& q) { interactive_force(g, b, p, ct, s, i, j, q, u0, v0, us, vs); },   // I:2217
+                   ax1, ay1, axn, ayn, bxn, byn, un_l, vn_l);
+  if ((p.speed_limit > 0.) || (p.speed_limit == -1.)) {
+    double speed = sqrt(un_l * un_l + vn_l * vn_l);
+    if (speed > 0.) {
+      int c = gidx(g, i, j);
+      double loc_dx = fmin(0.5 * (g.dx[c] + g.dx[c - g.nid]), 0.5 * (g.dy[c] + g.dy[c - 1]));
+      double new_speed = loc_dx / dt * p.speed_limit;
+      if (new_speed < speed && p.speed_limit > 0.) atomicAdd(&cnt->nspeeding, 1ull);
+    }
+  }
+  bool tang = (lat > 89.) && p.grid_is_latlon;
+  double uveln, vveln;
+  if (tang) tang_velocity(p, lon, uvel3, vvel3, ax1, ay1, dt, uveln, vveln);
+  else { uveln = uvel3 + (dt * ax1); vveln = vvel3 + (dt * ay1); }
+  if (p.override_iceberg_velocities) { uveln = p.u_override; vveln = p.v_override; }
+  b.f64[C_UVEL_PREV][s] = uvel_prev; b.f64[C_VVEL_PREV][s] = vvel_prev;
+  b.f64[C_AXN][s] = axn; b.f64[C_AYN][s] = ayn; b.f64[C_BXN][s] = bxn; b.f64[C_BYN][s] = byn;
+  b.f64[C_UVEL][s] = uveln; b.f64[C_VVEL][s] = vveln;
+}
+
+// ---------------------------------------------------------------- ghosts
+// update_halo_icebergs F:1800: step 1, clear the halo copies
+__global__ void k_clear_halo(uint8_t* __restrict__ flags, long long n_slots) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  if (flags[s] & BF_HALO) flags[s] = 0;
+}
+
+// Which of the 8 neighbours get a copy of a berg in cell (i,j): the strips of F:1896-1912 (E/W)
+// and F:1976-2006 (N/S, over the data-domain columns so that corner copies travel too).
+struct GhostPlan {
+  int32_t nbr[9];            // rank per direction, -1 none
+  int32_t hw, isc, iec, jsc, jec;
+};
+__device__ __forceinline__ bool ghost_goes(const GhostPlan& gp, int dir, int i, int j) {
+  int dx = dir % 3 - 1, dy = dir / 3 - 1;
+  if (gp.nbr[dir] < 0) return false;
+  if (dx > 0 && !(i >= gp.iec - gp.hw + 2)) return false;
+  if (dx < 0 && !(i <= gp.isc + gp.hw - 1)) return false;
+  if (dy > 0 && !(j >= gp.jec - gp.hw + 2)) return false;
+  if (dy < 0 && !(j <= gp.jsc + gp.hw - 1)) return false;
+  return true;
+}
+
+__global__ void k_ghost_count(const __grid_constant__ GhostPlan gp, const uint8_t* __restrict__ flags,
+                              const int32_t* __restrict__ ine, const int32_t* __restrict__ jne, long long n_slots,
+                              int32_t* __restrict__ counts /* [9] */) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  uint8_t f = flags[s];
+  if (!(f & BF_ALIVE) || (f & (BF_HALO | BF_LEAVER))) return;
+  int i = ine[s], j = jne[s];
+  for (int dir = 0; dir < 9; dir++)
+    if (dir != 4 && ghost_goes(gp, dir, i, j)) atomicAdd(&counts[dir], 1);
+}
+
+// pack_berg_into_buffer2 with halo_berg = 1 (F:1902-1905); bonds travel as (other_id, other ine/jne, length)
+__global__ void k_ghost_pack(const __grid_constant__ GhostPlan gp, const __grid_constant__ DevBergs b, long long n_slots,
+                             const int32_t* __restrict__ offsets /* [9] */, int32_t* __restrict__ cursor /* [9] */,
+                             double* __restrict__ sendbuf, int rec_w) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  uint8_t f = b.flags[s];
+  if (!(f & BF_ALIVE) || (f & (BF_HALO | BF_LEAVER))) return;
+  int i = b.ine[s], j = b.jne[s];
+  for (int dir = 0; dir < 9; dir++) {
+    if (dir == 4 || !ghost_goes(gp, dir, i, j)) continue;
+    int pos = offsets[dir] + atomicAdd(&cursor[dir], 1);
+    double* rec = sendbuf + (size_t)pos * rec_w;
+    for (int c = 0; c < C_NBASE; c++) rec[PK_F64_0 + c] = b.f64[c][s];
+    rec[PK_ID] = __longlong_as_double(b.id[s]);
+    rec[PK_INE_JNE] = __longlong_as_double(((long long)(unsigned)i << 32) | (unsigned)j);
+    rec[PK_YEAR_FLAGS] = __longlong_as_double(((long long)(unsigned)b.start_year[s] << 32) | (unsigned)f);
+    for (int k = 0; k < b.max_bonds; k++) {
+      long long slot = (long long)k * b.capacity + s;
+      double* br = rec + PACK_W + 3 * k;
+      br[0] = __longlong_as_double(b.bond_other_id[slot]);
+      br[1] = __longlong_as_double(((long long)(unsigned)b.bond_other_ine[slot] << 32) | (unsigned)b.bond_other_jne[slot]);
+      br[2] = b.bond_length[slot];
+    }
+  }
+}
+
+// unpack_berg_from_buffer2 F:3468 for halo copies: cell re-found, xi/yj recomputed, *_old = current
+__global__ void k_ghost_unpack(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
+                               const __grid_constant__ DevParams p, DevCounters* __restrict__ cnt,
+                               const double* __restrict__ recvbuf, long long n_recv, long long s0, int rec_w) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_recv) return;
+  long long s = s0 + k;
+  const double* rec = recvbuf + (size_t)k * rec_w;
+  for (int c = 0; c < C_NBASE; c++) b.f64[c][s] = rec[PK_F64_0 + c];
+  double lon = rec[PK_F64_0 + C_LON], lat = rec[PK_F64_0 + C_LAT];
+  if (b.f64[C_UVEL_OLD]) {
+    b.f64[C_UVEL_OLD][s] = rec[PK_F64_0 + C_UVEL]; b.f64[C_VVEL_OLD][s] = rec[PK_F64_0 + C_VVEL];
+    b.f64[C_LON_OLD][s] = lon; b.f64[C_LAT_OLD][s] = lat;
+  }
+  b.id[s] = __double_as_longlong(rec[PK_ID]);
+  long long ij = __double_as_longlong(rec[PK_INE_JNE]), yf = __double_as_longlong(rec[PK_YEAR_FLAGS]);
+  int i = (int)(ij >> 32), j = (int)(ij & 0xffffffffll);
+  b.start_year[s] = (int32_t)(yf >> 32);
+  uint8_t f = (uint8_t)(yf & 0xff);
+  for (int q = 0; q < b.max_bonds; q++) {
+    long long slot = (long long)q * b.capacity + s;
+    const double* br = rec + PACK_W + 3 * q;
+    b.bond_other_id[slot] = __double_as_longlong(br[0]);
+    long long oij = __double_as_longlong(br[1]);
+    b.bond_other_ine[slot] = (int)(oij >> 32); b.bond_other_jne[slot] = (int)(oij & 0xffffffffll);
+    b.bond_length[slot] = br[2];
+    b.bond_other_slot[slot] = -1;
+  }
+  // A copy that crossed the periodic seam lives one period away from its owner: the periodic image
+  // of the sender's cell is tried first (it is the cell a receiving PE that does not hold the owner's
+  // cell finds, F:5973-6008; on one PE that is its own neighbour the owner's cell would match too).
+  bool found = false;
+  int oi = i, oj = j;
+  if (g.cyclic_x) {
+    for (int sh = -1; sh <= 1 && !found; sh += 2) {
+      oi = i + sh * g.gni;
+      if (cell_on_pe(g, oi, oj)) found = is_point_in_cell(g, p, lon, lat, oi, oj, &cnt->error_flags);
+    }
+  }
+  if (!found) { oi = i; if (cell_on_pe(g, oi, oj)) found = is_point_in_cell(g, p, lon, lat, oi, oj, &cnt->error_flags); }
+  if (!found) found = find_cell_wide(g, p, lon, lat, &oi, &oj, &cnt->error_flags);
+  if (!found) { b.flags[s] = 0; return; }      // a copy nobody needs (F:3668 is FATAL for owned bergs only in practice)
+  double xi, yj;
+  pos_within_cell(g, p, lon, lat, oi, oj, &xi, &yj, &cnt->error_flags);
+  b.f64[C_XI][s] = xi; b.f64[C_YJ][s] = yj;
+  b.ine[s] = oi; b.jne[s] = oj;
+  b.halo_code[s] = 1;
+  b.flags[s] = (uint8_t)((f | BF_ALIVE | BF_HALO) & ~(BF_LEAVER | BF_ARRIVAL));
+}
+
+// update_latlon F:5128-5169: positions re-derived from (cell, xi, yj) so that copies across the
+// periodic seam carry the coordinates of the halo cell they sit in
+__global__ void k_update_latlon(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
+                                const __grid_constant__ DevParams p, DevCounters* __restrict__ cnt, long long n_slots) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  uint8_t f = b.flags[s];
+  if (!(f & BF_ALIVE) || (f & BF_LEAVER)) return;
+  int i = b.ine[s], j = b.jne[s];
+  if (!cell_on_pe(g, i, j)) return;
+  double lon = b.f64[C_LON][s], lat = b.f64[C_LAT][s];
+  double dlon = lon - b.f64[C_LON_OLD][s], dlat = lat - b.f64[C_LAT_OLD][s];
+  double xi = b.f64[C_XI][s], yj = b.f64[C_YJ][s];
+  bilin_lonlat(g, p, i, j, xi, yj, &lon, &lat);
+  b.f64[C_LON][s] = lon; b.f64[C_LAT][s] = lat;
+  b.f64[C_LON_OLD][s] = lon - dlon; b.f64[C_LAT_OLD][s] = lat - dlat;
+  pos_within_cell(g, p, lon, lat, i, j, &xi, &yj, &cnt->error_flags);
+  b.f64[C_XI][s] = xi; b.f64[C_YJ][s] = yj;
+}
+
+}  // namespace kid
+
+namespace kid {
+
+// ------------------------------------------------------------------ bonds
+// bond_address_update F:4887-4915: the (ine,jne) hint of every connected bond follows its partner
+__global__ void k_bond_address_update(const __grid_constant__ DevBergs b, long long n_slots) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots || !(b.flags[s] & BF_ALIVE)) return;
+  for (int k = 0; k < b.max_bonds; k++) {
+    long long slot = (long long)k * b.capacity + s;
+    if (b.bond_other_id[slot] == 0) continue;
+    int32_t o = b.bond_other_slot[slot];
+    if (o < 0) continue;
+    b.bond_other_ine[slot] = b.ine[o]; b.bond_other_jne[slot] = b.jne[o];
+  }
+}
+
+__device__ __forceinline__ int find_id_in_cell(const DevGrid& g, const DevBergs& b, const CellTable& ct, int i, int j,
+                                               int64_t id) {
+  if (!((i > g.isd - 1) && (i < g.ied + 1) && (j > g.jsd - 1) && (j < g.jed + 1))) return -1;
+  int c = gidx(g, i, j);
+  int n = ct.count[c], o0 = ct.start[c];
+  for (int k = 0; k < n; k++) if (b.id[o0 + k] == id) return o0 + k;
+  return -1;
+}
+
+// connect_all_bonds F:4963-5125 on the freshly sorted store: every bond looks its partner up in the
+// hinted cell, then around the hint, then in the 5x5 cells around the berg (updating the hint)
+__global__ void k_connect_bonds(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
+                                const CellTable ct, DevCounters* __restrict__ cnt, long long n_slots) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots || !(b.flags[s] & BF_ALIVE)) return;
+  for (int k = 0; k < b.max_bonds; k++) {
+    long long slot = (long long)k * b.capacity + s;
+    int64_t oid = b.bond_other_id[slot];
+    if (oid == 0) continue;
+    int i = b.bond_other_ine[slot], j = b.bond_other_jne[slot];
+    int o = find_id_in_cell(g, b, ct, i, j, oid);
+    if (o < 0) {
+      for (int jj = j - 1; jj <= j + 1 && o < 0; jj++)
+        for (int ii = i - 1; ii <= i + 1 && o < 0; ii++)
+          if (ii != i || jj != j) o = find_id_in_cell(g, b, ct, ii, jj, oid);
+    }
+    if (o < 0) {
+      int bi = b.ine[s], bj = b.jne[s];
+      for (int jj = bj - 2; jj <= bj + 2 && o < 0; jj++)
+        for (int ii = bi - 2; ii <= bi + 2 && o < 0; ii++) {
+          o = find_id_in_cell(g, b, ct, ii, jj, oid);
+          if (o >= 0) { b.bond_other_ine[slot] = ii; b.bond_other_jne[slot] = jj; }
+        }
+    }
+    b.bond_other_slot[slot] = o;
+    if (o < 0 && !(b.flags[s] & BF_HALO)) atomicOr(&cnt->error_flags, 256u);   // 'A non-halo bond is missing!!!' F:5063
+  }
+}
+
+// initialize_iceberg_bonds I:356-441: O(N^2) distance test over every berg of the data domain, in the
+// reference's outer/inner order (cells j-major, bergs in list order) so that each berg's bond list
+// has the reference's order.  One thread per berg; the inner loop walks the sorted store.
+__global__ void k_init_bonds(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
+                             const __grid_constant__ DevParams p, DevCounters* __restrict__ cnt, long long n_slots,
+                             double bond_length_crit, int from_radii) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots || !(b.flags[s] & BF_ALIVE)) return;
+  double lon1 = b.f64[C_LON][s], lat1 = b.f64[C_LAT][s];
+  double rdenom = p.hexagonal_icebergs ? 1. / (2. * sqrt(3.)) : 1. / 4.;
+  for (long long o = 0; o < n_slots; o++) {
+    if (!(b.flags[o] & BF_ALIVE) || b.id[o] == b.id[s]) continue;
+    bool already = false;
+    int nfree = -1;
+    for (int k = 0; k < b.max_bonds; k++) {
+      int64_t oid = b.bond_other_id[(long long)k * b.capacity + s];
+      if (oid == b.id[o]) already = true;
+      if (oid == 0 && nfree < 0) nfree = k;
+    }
+    if (already) continue;
+    double lon2 = b.f64[C_LON][o], lat2 = b.f64[C_LAT][o];
+    double dlon = lon1 - lon2, dlat = lat1 - lat2, dx_dlon, dy_dlat;
+    convert_from_grid_to_meters(p, 0.5 * (lat1 + lat2), dx_dlon, dy_dlat);
+    double rx = dlon * dx_dlon, ry = dlat * dy_dlat;
+    double r_dist = sqrt((rx * rx) + (ry * ry));
+    bool bond;
+    if (from_radii) {
+      double radius1 = sqrt(b.f64[C_LENGTH][s] * b.f64[C_WIDTH][s] * rdenom);
+      double radius2 = sqrt(b.f64[C_LENGTH][o] * b.f64[C_WIDTH][o] * rdenom);
+      bond = r_dist < 1.25 * (radius1 + radius2);
+    } else bond = r_dist < bond_length_crit;
+    if (!bond) continue;
+    if (nfree < 0) { atomicOr(&cnt->error_flags, 512u); continue; }      // more than max_bonds partners
+    long long slot = (long long)nfree * b.capacity + s;
+    b.bond_other_id[slot] = b.id[o];
+    b.bond_other_slot[slot] = (int32_t)o;
+    b.bond_other_ine[slot] = b.ine[o]; b.bond_other_jne[slot] = b.jne[o];
+    b.bond_length[slot] = 0.;
+  }
+}
+
+// orig_bond_length F:4589-4614 (first visit, I:5420): bond%length = current separation of the pair
+// in grid units (degrees or metres, whatever lon/lat are)
+__global__ void k_orig_bond_length(const __grid_constant__ DevBergs b, long long n_slots) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots || !(b.flags[s] & BF_ALIVE)) return;
+  for (int k = 0; k < b.max_bonds; k++) {
+    long long slot = (long long)k * b.capacity + s;
+    if (b.bond_other_id[slot] == 0) continue;
+    int32_t o = b.bond_other_slot[slot];
+    if (o < 0) continue;
+    double dl = b.f64[C_LON][s] - b.f64[C_LON][o], dp = b.f64[C_LAT][s] - b.f64[C_LAT][o];
+    b.bond_length[slot] = sqrt((dl * dl) + (dp * dp));
+  }
+}
+
+}  // namespace kid

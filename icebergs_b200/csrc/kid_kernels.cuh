@@ -211,7 +211,8 @@ __device__ __forceinline__ int thermo_slot(const DevGrid& g, const DevBergs& b, 
   st.start_day = 0.; st.start_year = 0;
   double N_bonds = 0.;
   if (p.allow_bergs_to_roll) {
-    // N_bonds: I:2928-2944 (bond counts live with the bonded path; free bergs have none)
+    // N_bonds: I:2928-2944 (this%n_bonds = the length of the bond list, assign_n_bonds F:4617)
+    for (int k = 0; k < b.max_bonds; k++) if (b.bond_other_id[(long long)k * b.capacity + s] != 0) N_bonds += 1.0;
     if (flags & BF_STATIC) N_bonds = p.hexagonal_icebergs ? 6.0 : 4.0;
   }
   int outcome = thermo_berg(p, e, uvel, vvel, N_bonds, st, sc.fx);
@@ -253,7 +254,9 @@ struct BergIn {
 };
 
 // evolve_icebergs (I:7081) + send_bergs_to_other_pes (F:2997) + thermodynamics (I:2844) for one berg
-template <bool FOOTLOOSE>
+// SPLIT: the velocity solve already ran (k_ia_velocity, interactions on): this is the second sweep of
+// evolve_icebergs I:7182-7197 (position, *_old refresh) followed by send_bergs and thermodynamics
+template <bool FOOTLOOSE, bool SPLIT>
 __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, const DevParams& p,
                                           DevCounters* __restrict__ cnt, long long s, const BergIn& in, Scatter& sc,
                                           bool& melted, bool& became_fl, bool& bounced, bool& speeding, bool& left) {
@@ -264,42 +267,47 @@ __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, c
   double M = in.M, T = in.T, W = in.W, L = in.L;
   if (!(flags & BF_STATIC)) {
     double axn = in.axn, ayn = in.ayn, bxn = in.bxn, byn = in.byn;
-    // ---- verlet_stepping I:7203-7328
-    b.f64[C_UVEL_PREV][s] = uvel - dt_2 * bxn;
-    b.f64[C_VVEL_PREV][s] = vvel - dt_2 * byn;
-    double uvel3 = uvel + (dt_2 * axn);
-    double vvel3 = vvel + (dt_2 * ayn);
-    Env e;
-    if (!interp_flds(g, p, i, j, xi, yj, e)) atomicOr(&cnt->error_flags, 64u);
-    // sin and cos of the latitude: Coriolis (I:2043-2047) and the metric (I:462-477)
     double sin_lat = 0., cos_lat = 1.;
     if (p.grid_is_latlon) sincos_halfpi(p.pi_180 * lat, &sin_lat, &cos_lat);
-    double f_cori = (p.grid_is_latlon && !p.use_f_plane) ? p.omega2 * sin_lat : p.f_cori_plane;
-    double ax1, ay1, un_l, vn_l;
-    IAcc ia0 = {0., 0., 0., 0., 0., 0., 0., 0.};
-    accel_core<false>(p, M, T, W, L, f_cori, uvel, vvel, dt, e, 1.0, ia0,
-                      [](double, double, IAcc&) {}, ax1, ay1, axn, ayn, bxn, byn, un_l, vn_l);
-    if ((p.speed_limit > 0.) || (p.speed_limit == -1.)) {   // I:2304-2323: only the ticket survives
-      double speed = sqrt(un_l * un_l + vn_l * vn_l);
-      if (speed > 0.) {
-        size_t c = gidx(g, i, j);
-        double loc_dx = fmin(0.5 * (g.dx[c] + g.dx[c - g.nid]), 0.5 * (g.dy[c] + g.dy[c - 1]));
-        double new_speed = loc_dx / dt * p.speed_limit;
-        if (new_speed < speed && p.speed_limit > 0.) speeding = true;
+    const bool tang = (lat > 89.) && p.grid_is_latlon;
+    if (!SPLIT) {
+      // ---- verlet_stepping I:7203-7328
+      b.f64[C_UVEL_PREV][s] = uvel - dt_2 * bxn;
+      b.f64[C_VVEL_PREV][s] = vvel - dt_2 * byn;
+      double uvel3 = uvel + (dt_2 * axn);
+      double vvel3 = vvel + (dt_2 * ayn);
+      Env e;
+      if (!interp_flds(g, p, i, j, xi, yj, e)) atomicOr(&cnt->error_flags, 64u);
+      double f_cori = (p.grid_is_latlon && !p.use_f_plane) ? p.omega2 * sin_lat : p.f_cori_plane;
+      double ax1, ay1, un_l, vn_l;
+      IAcc ia0 = {0., 0., 0., 0., 0., 0., 0., 0.};
+      accel_core<false>(p, M, T, W, L, f_cori, uvel, vvel, dt, e, 1.0, ia0,
+                        [](double, double, IAcc&) {}, ax1, ay1, axn, ayn, bxn, byn, un_l, vn_l);
+      if ((p.speed_limit > 0.) || (p.speed_limit == -1.)) {   // I:2304-2323: only the ticket survives
+        double speed = sqrt(un_l * un_l + vn_l * vn_l);
+        if (speed > 0.) {
+          size_t c = gidx(g, i, j);
+          double loc_dx = fmin(0.5 * (g.dx[c] + g.dx[c - g.nid]), 0.5 * (g.dy[c] + g.dy[c - 1]));
+          double new_speed = loc_dx / dt * p.speed_limit;
+          if (new_speed < speed && p.speed_limit > 0.) speeding = true;
+        }
       }
+      double uveln, vveln;
+      lon = b.f64[C_LON][s];
+      if (tang) tang_velocity(p, lon, uvel3, vvel3, ax1, ay1, dt, uveln, vveln);
+      else { uveln = uvel3 + (dt * ax1); vveln = vvel3 + (dt * ay1); }
+      if (p.override_iceberg_velocities) { uveln = p.u_override; vveln = p.v_override; }
+      uvel = uveln; vvel = vveln;      // evolve_icebergs I:7157-7162
+    } else {
+      lon = b.f64[C_LON][s];
     }
-    bool tang = (lat > 89.) && p.grid_is_latlon;
-    double uveln, vveln;
-    lon = b.f64[C_LON][s];
-    if (tang) tang_velocity(p, lon, uvel3, vvel3, ax1, ay1, dt, uveln, vveln);
-    else { uveln = uvel3 + (dt * ax1); vveln = vvel3 + (dt * ay1); }
-    if (p.override_iceberg_velocities) { uveln = p.u_override; vveln = p.v_override; }
-    uvel = uveln; vvel = vveln;      // evolve_icebergs I:7157-7162
     // ---- update_verlet_position I:7684-7764 (uses the NEW velocity and accelerations)
     double uvel2 = uvel + (dt_2 * axn) + (dt_2 * bxn);
     double vvel2 = vvel + (dt_2 * ayn) + (dt_2 * byn);
-    b.f64[C_AXN][s] = axn; b.f64[C_AYN][s] = ayn; b.f64[C_BXN][s] = bxn; b.f64[C_BYN][s] = byn;
-    b.f64[C_UVEL][s] = uvel; b.f64[C_VVEL][s] = vvel;
+    if (!SPLIT) {
+      b.f64[C_AXN][s] = axn; b.f64[C_AYN][s] = ayn; b.f64[C_BXN][s] = bxn; b.f64[C_BYN][s] = byn;
+      b.f64[C_UVEL][s] = uvel; b.f64[C_VVEL][s] = vvel;
+    }
     double lonn, latn;
     if (tang) {
       tang_position(p, lon, lat, uvel2, vvel2, dt, lonn, latn);
@@ -312,6 +320,10 @@ __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, c
     bounced = adjust_index_and_ground(g, p, lonn, latn, i, j, xi, yj, &cnt->error_flags, &cnt->warn_adjust);
     lon = lonn; lat = latn;
     b.f64[C_LON][s] = lon; b.f64[C_LAT][s] = lat;
+    if (SPLIT) {      // I:7189-7194
+      b.f64[C_UVEL_OLD][s] = uvel; b.f64[C_VVEL_OLD][s] = vvel;
+      b.f64[C_LON_OLD][s] = lon; b.f64[C_LAT_OLD][s] = lat;
+    }
   } else if (i > g.iec || i < g.isc || j > g.jec || j < g.jsc) {
     lon = b.f64[C_LON][s];
   }
@@ -341,7 +353,7 @@ __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, c
   }
 }
 
-template <bool FOOTLOOSE, bool DIAG>
+template <bool FOOTLOOSE, bool DIAG, bool SPLIT = false>
 __global__ void __launch_bounds__(KID_BLOCK, KID_MINBLOCKS)
 k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
        const __grid_constant__ DevParams p, DevCounters* __restrict__ cnt, long long n_slots) {
@@ -374,7 +386,7 @@ k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
   sc.fx.fl_parent_melt = sc.fx.fl_child_melt = sc.fx.melt_buoy = sc.fx.melt_eros = sc.fx.melt_conv = 0.;
   sc.fx.melt_buoy_fl = sc.fx.melt_eros_fl = sc.fx.melt_conv_fl = 0.;
   bool melted = false, became_fl = false, bounced = false, speeding = false, left = false;
-  if (owned) step_berg<FOOTLOOSE>(g, b, p, cnt, s, in, sc, melted, became_fl, bounced, speeding, left);
+  if (owned) step_berg<FOOTLOOSE, SPLIT>(g, b, p, cnt, s, in, sc, melted, became_fl, bounced, speeding, left);
   scatter_fluxes<FOOTLOOSE, DIAG>(g, sc);
   // event counters: one vote decides whether the warp has anything to report at all
   if (__any_sync(0xffffffffu, melted | bounced | speeding | left)) {

@@ -154,3 +154,90 @@ def workload_params(default_params, **over):
               Rearth=REARTH)
     kw.update(over)
     return default_params(**kw)
+
+
+class CartesianGrid:
+    """The stand-alone driver's test grid (driver/icebergs_driver.F90:274-286): gridres-metre
+    square cells, lon(i,j) = gridres*i, lat(i,j) = gridres*j, all ocean, 1000 m deep."""
+
+    def __init__(self, ni=20, nj=20, gridres=1.0e3, isc=1, iec=None, jsc=1, jec=None):
+        self.gni, self.gnj, self.res = ni, nj, gridres
+        self.isc, self.iec = isc, ni if iec is None else iec
+        self.jsc, self.jec = jsc, nj if jec is None else jec
+
+    def _ij(self, ring):
+        i = np.arange(self.isc - ring, self.iec + ring + 1)
+        j = np.arange(self.jsc - ring, self.jec + ring + 1)
+        return np.meshgrid(i, j)
+
+    def init_args(self):
+        i0, j0 = self._ij(0)
+        i1, _ = self._ij(1)
+        one0, one1 = np.ones(i0.shape), np.ones(i1.shape)
+        return dict(ice_lon=self.res * i0, ice_lat=self.res * j0, ice_wet=one1.copy(), ice_dx=self.res * one1,
+                    ice_dy=self.res * one1, ice_area=self.res * self.res * one0, cos_rot=one1.copy(),
+                    sin_rot=0.0 * one1, ocean_depth=1000.0 * one0)
+
+    def forcing(self, ibuo=0.2, ibvo=0.2, sst=-2.0, collision_test=True):
+        """D:218-229; collision_test: the meridional current converges on lat = mid (D:313-327)."""
+        i0, j0 = self._ij(0)
+        i1, j1 = self._ij(1)
+        lon1, lat1 = self.res * i1, self.res * j1
+        uo = np.full(i1.shape, ibuo)
+        vo = np.full(i1.shape, ibvo)
+        if collision_test:
+            mid = 10.0e3
+            vo = np.where((lon1 > mid) | (lon1 <= 0.0) | (lat1 == mid), 0.0, np.where(lat1 > mid, -ibvo, ibvo))
+        z0, z1 = np.zeros(i0.shape), np.zeros(i1.shape)
+        f = dict(uo=uo, vo=vo, ui=z1.copy(), vi=z1.copy(), tauxa=z0.copy(), tauya=z0.copy(), ssh=z1.copy(),
+                 sst=np.full(i0.shape, sst), sss=np.full(i0.shape, 34.0), cn=z1.copy(), hi=z1.copy(),
+                 calving=z0.copy(), calving_hflx=z0.copy())
+        return {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in f.items()}
+
+
+def collision_bergs(gridres=1.0e3, n=20, h_ice=300.0, rho_ice=918.0):
+    """The two 8-element conglomerates of tests/collision_tests (README: 16 bergs): a 1 km-radius
+    disc of 300 m thick ice centred on (4.5 km, 4.5 km), hex-packed with elements of radius
+    R = sqrt(3)/2 * 0.45 * gridres (initialize_bergs_in_pattern.py:826-836, :1795-1801), mirrored about
+    y = n*gridres/2 (:905-914).  Element area 2*sqrt(3)*R^2 (:663-671), width = length = sqrt(area),
+    mass = thickness * rho_ice * area with the script's rho_ice = 918 (:196, :638)."""
+    R = np.sqrt(3.0) / 2.0 * 0.45 * gridres
+    xc = (np.arange(n) + 0.5) * gridres
+    X, Y = np.meshgrid(xc, xc)
+    ice = ((X - 4500.0) ** 2 + (Y - 4500.0) ** 2) <= 1000.0 ** 2
+    pts = []
+    for j in range(3 * n):
+        for i in range(3 * n):
+            x = (2.0 / np.sqrt(3.0)) * R + np.sqrt(3.0) * R * i
+            y = R + (i % 2) * R + 2.0 * R * j
+            if x >= n * gridres or y >= n * gridres:
+                continue
+            if ice[int(y // gridres), int(x // gridres)]:
+                pts.append((x, y))
+    pts = np.array(pts)
+    x = np.r_[pts[:, 0], pts[:, 0]]
+    y = np.r_[pts[:, 1], n * gridres - pts[:, 1]]
+    m = len(x)
+    area = 2.0 * np.sqrt(3.0) * R * R
+    w = np.full(m, np.sqrt(area))
+    z = np.zeros(m)
+    return dict(lon=x, lat=y, uvel=z.copy(), vvel=z.copy(), mass=np.full(m, h_ice * rho_ice * area),
+                thickness=np.full(m, h_ice), width=w.copy(), length=w.copy(), axn=z.copy(), ayn=z.copy(),
+                bxn=z.copy(), byn=z.copy(), start_lon=x.copy(), start_lat=y.copy(), start_day=z.copy(),
+                start_mass=np.full(m, h_ice * rho_ice * area), mass_scaling=np.ones(m), mass_of_bits=z.copy(),
+                heat_density=z.copy(), start_year=np.zeros(m, dtype=np.int32))
+
+
+def collision_params(default_params, **over):
+    """&icebergs_nml of tests/collision_tests/input_KID.nml (the values that reach the hot path)."""
+    kw = dict(halo=3, Lx=20000.0, grid_is_latlon=0, grid_is_regular=1, hexagonal_icebergs=1, rho_bergs=850.0,
+              spring_coef=1.0e-5, radial_damping_coef=1.0e-4, tangental_damping_coef=2.0e-5,
+              critical_interaction_damping_on=1, LoW_ratio=1.5, bergy_bit_erosion_fraction=0.0, sicn_shift=0.0,
+              use_operator_splitting=1, speed_limit=0.0, tip_parameter=0.0, coastal_drift=0.4, tidal_drift=0.0,
+              runge_not_verlet=0, allow_bergs_to_roll=1, use_updated_rolling_scheme=1, melt_cutoff=10.0,
+              apply_thickness_cutoff_to_gridded_melt=1, apply_thickness_cutoff_to_bergs_melt=1,
+              set_melt_rates_to_zero=1, iceberg_bonds_on=1, interactive_icebergs_on=1, only_interactive_forces=0,
+              use_new_predictive_corrective=1, max_bonds=6, manually_initialize_bonds=1,
+              length_for_manually_initialize_bonds=800.0, use_roundoff_fix=1, old_bug_bilin=0, tau_is_velocity=0)
+    kw.update(over)
+    return default_params(**kw)

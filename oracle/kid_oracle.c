@@ -2171,6 +2171,7 @@ static void oracle_footloose_calving(Oracle* o);
 static void oracle_footloose_part2(Oracle* o);
 static void oracle_set_conglom_ids(Oracle* o);
 static void oracle_transfer_mts_bergs(Oracle* o);
+static void oracle_bond_address_update(Oracle* o);
 
 /* the hot path of icebergs_run, I:5389-5512 */
 static void step_core(Oracle* o) {
@@ -2191,6 +2192,7 @@ static void step_core(Oracle* o) {
   }
   move_berg_between_cells(o);
   double t2 = now_sec();
+  if (p->iceberg_bonds_on) oracle_bond_address_update(o);
   send_bergs_to_other_pes(o);
   if (p->footloose) oracle_footloose_calving(o);
   if (p->mts) {

@@ -41,6 +41,8 @@ def lib():
         L.oracle_count_bergs.argtypes = [_vp, C.c_int32]
         L.oracle_count_bergs.restype = C.c_int64
         L.oracle_get_bergs.argtypes = [_vp, C.POINTER(C.c_int64), C.POINTER(D.KidBergColumns), C.c_int32]
+        L.oracle_set_bonds.argtypes = [_vp, C.c_int64, C.POINTER(D.KidBondColumns)]
+        L.oracle_get_bonds.argtypes = [_vp, C.POINTER(C.c_int64), C.POINTER(D.KidBondColumns)]
         L.oracle_set_calving_state.argtypes = [_vp, _vp, _vp, _vp]
         L.oracle_get_calving_state.argtypes = [_vp, _vp, _vp, _vp]
         L.oracle_run.argtypes = [_vp, C.c_int32, C.c_double] + [_vp] * 12 + [C.c_int32, C.c_int32] + [_vp] * 4
@@ -82,10 +84,11 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(_vp)
 
 
-def make_columns(n, want=None, **arrays):
-    cols = D.KidBergColumns()
+def make_columns(n, want=None, cls=None, **arrays):
+    cls = cls or D.KidBergColumns
+    cols = cls()
     keep = {}
-    for name, ctype in D.KidBergColumns._fields_:
+    for name, ctype in cls._fields_:
         a = arrays.get(name)
         base = ctype._type_
         dt = {C.c_double: np.float64, C.c_int32: np.int32, C.c_int64: np.int64}[base]
@@ -147,6 +150,21 @@ class Oracle:
         c, keep = make_columns(cap, want=set(names))
         m = C.c_int64(cap)
         self._ok(lib().oracle_get_bergs(self._h, C.byref(m), C.byref(c), int(include_halo)))
+        return {k: v[: m.value].copy() for k, v in keep.items()}
+
+    def set_bonds(self, **cols):
+        n = len(cols["first_id"]) if cols else 0
+        c, keep = make_columns(n, cls=D.KidBondColumns, **cols)
+        self._ok(lib().oracle_set_bonds(self._h, n, C.byref(c)))
+
+    def get_bonds(self):
+        n = C.c_int64(0)
+        lib().oracle_get_bonds(self._h, C.byref(n), None)
+        cap = max(n.value, 1)
+        names = {"first_id", "other_id", "first_ine", "first_jne", "other_ine", "other_jne", "length"}
+        c, keep = make_columns(cap, want=names, cls=D.KidBondColumns)
+        m = C.c_int64(cap)
+        self._ok(lib().oracle_get_bonds(self._h, C.byref(m), C.byref(c)))
         return {k: v[: m.value].copy() for k, v in keep.items()}
 
     def set_calving_state(self, stored_ice=None, stored_heat=None, iceberg_counter_grd=None):

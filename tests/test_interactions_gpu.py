@@ -1,0 +1,116 @@
+"""Interacting bergs: interactive_force / calculate_force
+(I:480-804), STS bonds (initialize_iceberg_bonds I:356, connect_all_bonds F:4963), halo copies
+(update_halo_icebergs F:1800) and update_latlon (F:5128) -- the CUDA path against the CPU oracle on
+the stand-alone driver's Cartesian test grid (BASELINE configs[0]: tests/collision_tests)."""
+import numpy as np
+import pytest
+
+import kid_oracle_py as O
+from common import COMPARE_F64, assert_bergs_match, by_id, rel_err
+from icebergs_b200 import api
+from icebergs_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+NAMES = list(COMPARE_F64) + ["ine", "jne", "start_year", "id", "uvel_old", "vvel_old", "lon_old", "lat_old"]
+F64 = tuple(COMPARE_F64) + ("uvel_old", "vvel_old", "lon_old", "lat_old")
+
+
+class Pair:
+    def __init__(self, bergs, params, grid=None, dt=60.0, capacity=4096, bonds=True, forcing=None):
+        self.grid = grid or S.CartesianGrid()
+        g = self.grid
+        self.dt = dt
+        self.f = forcing or g.forcing()
+        dom = lambda: api.Domain.single(g.gni, g.gnj, halo=params().halo, cyclic_x=True)
+        self.b = api.icebergs_init(g.gni, g.gnj, dt, (1, 0.0), params=params(), domain=dom(), capacity=capacity, **g.init_args())
+        self.o = O.Oracle(g.gni, g.gnj, dt, (1, 0.0), params=params(), domain=dom(), **g.init_args())
+        self.b.set_bergs(**bergs)
+        self.o.set_bergs(**bergs)
+        if bonds:
+            self.b.set_bonds()
+            self.o.set_bonds()
+        self.k = 0
+
+    def step(self, n=1):
+        f = self.f
+        for _ in range(n):
+            t = (1, self.k * self.dt / 86400.0)
+            for who in (self.b, self.o):
+                c, h = f["calving"].copy(), f["calving_hflx"].copy()
+                args = (t, c, f["uo"], f["vo"], f["ui"], f["vi"], f["tauxa"], f["tauya"], f["ssh"], f["sst"], h, f["cn"], f["hi"])
+                if who is self.b:
+                    api.icebergs_run(who, *args, sss=f["sss"])
+                else:
+                    who.run(*args, sss=f["sss"])
+            self.k += 1
+
+    def check(self, context, rtol=1e-10):
+        # elements of a conglomerate sit exactly at the critical distance (touching hexagons), where the
+        # spring is zero and rounding decides whether the pair counts as in contact: accelerations below
+        # 1e-13 m/s2 (forces of ~1e-5 N on 4e10 kg elements) are noise
+        return assert_bergs_match(self.b.get_bergs(NAMES), self.o.get_bergs(NAMES), rtol=rtol, names=F64, context=context,
+                                  acc_floor=1e-13)
+
+    def end(self):
+        api.icebergs_end(self.b)
+        self.o.close()
+
+
+def bond_set(d):
+    return sorted(zip(d["first_id"].tolist(), d["other_id"].tolist()))
+
+
+def test_collision_test_bonds_and_first_steps():
+    """tests/collision_tests (KID scheme): two bonded 8-element conglomerates, 16 bergs."""
+    params = lambda: S.collision_params(api.default_params)
+    p = Pair(S.collision_bergs(), params)
+    assert p.b.count_bergs() == 16 == p.o.count_bergs()          # README:16-22 '#= 16'
+    gb, ob = p.b.get_bonds(), p.o.get_bonds()
+    assert bond_set(gb) == bond_set(ob) and len(gb["first_id"]) == 36
+    p.check("after bond initialisation")
+    p.step(1)
+    p.check("one step", rtol=1e-10)
+    p.step(49)
+    p.check("50 steps", rtol=1e-9)
+    p.end()
+
+
+def test_collision_test_through_contact():
+    """The conglomerates meet at y = 10 km after ~350 steps of 60 s: contact forces, damping
+    projectors and the pull-only STS bonds all act.  Berg count and cells stay bit-exact."""
+    params = lambda: S.collision_params(api.default_params)
+    p = Pair(S.collision_bergs(), params)
+    closest = []
+    for k in range(12):
+        p.step(50)
+        w = p.check(f"{50 * (k + 1)} steps", rtol=1e-7)
+        g = by_id(p.b.get_bergs(["id", "lat"]))
+        closest.append(float(np.min(g["lat"][8:]) - np.max(g["lat"][:8])))
+    assert min(closest) < 800.0, f"conglomerates never came into contact: {closest}"
+    assert p.b.count_bergs() == 16
+    p.end()
+
+
+def test_unbonded_contact_in_a_crowd():
+    """No bonds: 1500 elements dropped at random on the 20 km periodic box push each other apart
+    (contact springs + damping) while drifting across the periodic seam (ghost copies, F:1800)."""
+    rng = np.random.default_rng(11)
+    n = 800
+    base = S.collision_bergs()
+    cols = {k: np.resize(v, n).copy() for k, v in base.items()}
+    cols["lon"] = rng.uniform(50.0, 19950.0, n)
+    cols["lat"] = rng.uniform(1050.0, 18950.0, n)
+    cols["start_lon"], cols["start_lat"] = cols["lon"].copy(), cols["lat"].copy()
+    cols["start_day"] = rng.uniform(0.0, 300.0, n)       # distinct sort keys (F:4318)
+    params = lambda: S.collision_params(api.default_params, iceberg_bonds_on=0, manually_initialize_bonds=0, max_bonds=0)
+    g = S.CartesianGrid()
+    p = Pair(cols, params, grid=g, bonds=False, forcing=g.forcing(ibuo=0.6, ibvo=0.0, collision_test=False), capacity=16384)
+    p.check("ingest")
+    for k in range(6):
+        p.step(10)
+        p.check(f"{10 * (k + 1)} steps", rtol=1e-8)
+    co, cg = p.o.counters(), p.b.counters()
+    assert co["n_received"] > 0, "no berg crossed the periodic seam"
+    assert p.b.count_bergs() == p.o.count_bergs()
+    p.end()
