@@ -443,7 +443,7 @@ static int exchange_bergs(kid_t* h, long long* n_recv_out) {
   if (n_send > h->xbuf_cap || n_recv > h->xbuf_cap) return fail(h, KID_ERR_CAPACITY, "kid: berg exchange buffer capacity exceeded");
   if (h->n_slots + n_recv > h->capacity) return fail(h, KID_ERR_CAPACITY, "kid: berg store capacity exceeded by arrivals");
   CK(cudaMemcpyAsync(h->d_offsets, h->h_offsets, sizeof(int32_t) * nr, cudaMemcpyHostToDevice, h->stream));
-  k_pack_leavers<<<32, 256, 0, h->stream>>>(h->b, h->b.leaver_list, h->leaver_dest, h->dcnt, (int32_t)h->b.leaver_cap, h->d_offsets,
+  k_pack_leavers<<<32, 256, 0, h->stream>>>(h->layout, h->b, h->b.leaver_list, h->leaver_dest, h->dcnt, (int32_t)h->b.leaver_cap, h->d_offsets,
                                            h->d_cursor, h->sendbuf); h->launches++;
   CK(cudaMemsetAsync(&h->dcnt->n_leaver_list, 0, sizeof(unsigned long long), h->stream));
   rc = comm_exchange(h, sends, recvs);
@@ -961,6 +961,7 @@ static int rebuild_ghosts(kid_t* h) {
   GhostPlan gp;
   for (int k = 0; k < 9; k++) gp.nbr[k] = h->nbr[k];
   gp.hw = h->p.halo; gp.isc = h->d.isc; gp.iec = h->d.iec; gp.jsc = h->d.jsc; gp.jec = h->d.jec;
+  gp.gni = h->d.gni; gp.cyclic_x = h->d.cyclic_x;
   CK(cudaMemsetAsync(h->d_gcounts, 0, sizeof(int32_t) * 9, h->stream));
   CK(cudaMemsetAsync(h->d_gcursor, 0, sizeof(int32_t) * 9, h->stream));
   LAUNCH(h, k_ghost_count, h->n_slots, 256, gp, h->b.flags, h->b.ine, h->b.jne, h->n_slots, h->d_gcounts);

@@ -112,7 +112,7 @@ __global__ void k_leaver_dest(const __grid_constant__ DevLayout L, const int32_t
 
 // pass 2: pack_berg_into_buffer2 (F:3250) into the per-destination regions; the slot is freed
 // (delete_iceberg_from_list F:3040)
-__global__ void k_pack_leavers(const __grid_constant__ DevBergs b, const int32_t* __restrict__ list,
+__global__ void k_pack_leavers(const __grid_constant__ DevLayout L, const __grid_constant__ DevBergs b, const int32_t* __restrict__ list,
                                const int32_t* __restrict__ dest, const DevCounters* __restrict__ cnt,
                                int32_t list_cap, const int32_t* __restrict__ offsets /* [nranks] */,
                                int32_t* __restrict__ cursor /* [nranks], zeroed */, double* __restrict__ sendbuf) {
@@ -129,7 +129,9 @@ __global__ void k_pack_leavers(const __grid_constant__ DevBergs b, const int32_t
 #pragma unroll
     for (int c = 0; c < C_NBASE; c++) rec[PK_F64_0 + c] = b.f64[c][s];
     rec[PK_ID] = __longlong_as_double(b.id[s]);
-    rec[PK_INE_JNE] = __longlong_as_double(((long long)(unsigned)b.ine[s] << 32) | (unsigned)b.jne[s]);
+    int ci = b.ine[s];       // the owner's own index of the cell: one period off when the berg crossed the seam
+    if (L.cyclic_x && (ci < 1 || ci > L.gni)) ci = ((ci - 1) % L.gni + L.gni) % L.gni + 1;
+    rec[PK_INE_JNE] = __longlong_as_double(((long long)(unsigned)ci << 32) | (unsigned)b.jne[s]);
     rec[PK_YEAR_FLAGS] = __longlong_as_double(((long long)(unsigned)b.start_year[s] << 32) | (unsigned)(f & ~BF_LEAVER));
   }
 }
@@ -162,8 +164,10 @@ __global__ void k_unpack_arrivals(const __grid_constant__ DevGrid g, const __gri
   int oi = i, oj = j;
   if (cell_on_pe(g, oi, oj)) found = is_point_in_cell(g, p, lon, lat, oi, oj, &cnt->error_flags);
   if (!found && g.cyclic_x) {
-    oi = (i > g.ied) ? i - g.gni : ((i - 1 < g.isd) ? i + g.gni : i);
-    if (oi != i && cell_on_pe(g, oi, oj)) found = is_point_in_cell(g, p, lon, lat, oi, oj, &cnt->error_flags);
+    for (int sh = -1; sh <= 1 && !found; sh += 2) {
+      oi = i + sh * g.gni;
+      if (cell_on_pe(g, oi, oj)) found = is_point_in_cell(g, p, lon, lat, oi, oj, &cnt->error_flags);
+    }
   }
   if (!found) found = find_cell_wide(g, p, lon, lat, &oi, &oj, &cnt->error_flags);
   if (!found) { atomicOr(&cnt->error_flags, (unsigned)KID_DEVERR_LOST_BERG); b.flags[s] = 0; return; }

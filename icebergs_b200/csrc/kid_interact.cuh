@@ -166,6 +166,7 @@ __global__ void k_clear_halo(uint8_t* __restrict__ flags, long long n_slots) {
 struct GhostPlan {
   int32_t nbr[9];            // rank per direction, -1 none
   int32_t hw, isc, iec, jsc, jec;
+  int32_t gni, cyclic_x;
 };
 __device__ __forceinline__ bool ghost_goes(const GhostPlan& gp, int dir, int i, int j) {
   int dx = dir % 3 - 1, dy = dir / 3 - 1;
@@ -204,7 +205,10 @@ __global__ void k_ghost_pack(const __grid_constant__ GhostPlan gp, const __grid_
     double* rec = sendbuf + (size_t)pos * rec_w;
     for (int c = 0; c < C_NBASE; c++) rec[PK_F64_0 + c] = b.f64[c][s];
     rec[PK_ID] = __longlong_as_double(b.id[s]);
-    rec[PK_INE_JNE] = __longlong_as_double(((long long)(unsigned)i << 32) | (unsigned)j);
+    // the copy's cell on the receiving side: one period away when the message crosses the cyclic seam
+    int dx = dir % 3 - 1, ci = i;
+    if (gp.cyclic_x) { if (dx > 0 && gp.iec == gp.gni) ci = i - gp.gni; else if (dx < 0 && gp.isc == 1) ci = i + gp.gni; }
+    rec[PK_INE_JNE] = __longlong_as_double(((long long)(unsigned)ci << 32) | (unsigned)j);
     rec[PK_YEAR_FLAGS] = __longlong_as_double(((long long)(unsigned)b.start_year[s] << 32) | (unsigned)f);
     for (int k = 0; k < b.max_bonds; k++) {
       long long slot = (long long)k * b.capacity + s;
@@ -244,18 +248,17 @@ __global__ void k_ghost_unpack(const __grid_constant__ DevGrid g, const __grid_c
     b.bond_length[slot] = br[2];
     b.bond_other_slot[slot] = -1;
   }
-  // A copy that crossed the periodic seam lives one period away from its owner: the periodic image
-  // of the sender's cell is tried first (it is the cell a receiving PE that does not hold the owner's
-  // cell finds, F:5973-6008; on one PE that is its own neighbour the owner's cell would match too).
+  // check_and_find_cell F:5973: the cell the sender named (already the periodic image when the copy
+  // crossed the seam, k_ghost_pack), then its other images, then the scan
   bool found = false;
   int oi = i, oj = j;
-  if (g.cyclic_x) {
+  if (cell_on_pe(g, oi, oj)) found = is_point_in_cell(g, p, lon, lat, oi, oj, &cnt->error_flags);
+  if (!found && g.cyclic_x) {
     for (int sh = -1; sh <= 1 && !found; sh += 2) {
       oi = i + sh * g.gni;
       if (cell_on_pe(g, oi, oj)) found = is_point_in_cell(g, p, lon, lat, oi, oj, &cnt->error_flags);
     }
   }
-  if (!found) { oi = i; if (cell_on_pe(g, oi, oj)) found = is_point_in_cell(g, p, lon, lat, oi, oj, &cnt->error_flags); }
   if (!found) found = find_cell_wide(g, p, lon, lat, &oi, &oj, &cnt->error_flags);
   if (!found) { b.flags[s] = 0; return; }      // a copy nobody needs (F:3668 is FATAL for owned bergs only in practice)
   double xi, yj;

@@ -167,3 +167,67 @@ def test_nccl_ranks_match_single_rank_oracle():
     ranks.end()
     for c in comms:
         api.lib().kid_nccl_destroy(c)
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_interacting_bergs_across_ranks(nranks):
+    """Contact forces across tile edges: halo copies travel between ranks (update_halo_icebergs
+    F:1800), owners migrate (F:2997), and the union must still equal the single-rank oracle."""
+    import kid_oracle_py as O
+    rng = np.random.default_rng(5)
+    n = 600
+    base = S.collision_bergs()
+    cols = {k: np.resize(v, n).copy() for k, v in base.items()}
+    # Without bonds the reference builds no halo copies before the first step (I:150-167), so on N PEs the
+    # first step misses contacts across tile edges that one PE sees: nobody starts within contact range
+    # (2 x 390 m) of a tile edge or of the seam; from step 2 on the copies exist in every decomposition.
+    def away(m):
+        x = rng.uniform(0.0, 1.0, m)
+        return np.where(x < 0.5, 1000.0 + x * 2.0 * 8000.0, 11000.0 + (x - 0.5) * 2.0 * 8000.0)
+    cols["lon"], cols["lat"] = away(n), away(n)
+    cols["start_lon"], cols["start_lat"] = cols["lon"].copy(), cols["lat"].copy()
+    cols["start_day"] = rng.uniform(0.0, 300.0, n)
+    params = lambda: S.collision_params(api.default_params, iceberg_bonds_on=0, manually_initialize_bonds=0, max_bonds=0)
+    g0 = S.CartesianGrid()
+    dom0 = api.Domain.single(20, 20, halo=3, cyclic_x=True)
+    o = O.Oracle(20, 20, 60.0, (1, 0.0), params=params(), domain=dom0, **g0.init_args())
+    o.set_bergs(**cols)
+    ref0 = o.get_bergs(["id", "ine", "jne", "lon"])           # ids are generated in file order (legacy iceberg_num)
+    cols = dict(cols, id=np.zeros(n, dtype=np.int64), ine=np.zeros(n, dtype=np.int32), jne=np.zeros(n, dtype=np.int32))
+    order = {float(x): k for k, x in enumerate(ref0["lon"])}
+    for k in range(n):
+        q = order[float(cols["lon"][k])]
+        cols["id"][k], cols["ine"][k], cols["jne"][k] = ref0["id"][q], ref0["ine"][q], ref0["jne"][q]
+    grp = parallel.LocalGroup(nranks)
+    doms = [grp.domain(20, 20, r, halo=3) for r in range(nranks)]
+    grids = [S.CartesianGrid(20, 20, 1.0e3, d.isc, d.iec, d.jsc, d.jec) for d in doms]
+    parts = parallel.split_by_owner(cols, doms)
+    hs = [None] * nranks
+
+    def init(r):
+        hs[r] = api.icebergs_init(20, 20, 60.0, (1, 0.0), params=params(), domain=doms[r], capacity=8192, **grids[r].init_args())
+        hs[r].set_bergs(**parts[r])
+    grp.run(init)
+    f0 = g0.forcing(ibuo=0.6, ibvo=0.1, collision_test=False)
+
+    def one(r):
+        f = grids[r].forcing(ibuo=0.6, ibvo=0.1, collision_test=False)
+        c, h = f["calving"].copy(), f["calving_hflx"].copy()
+        api.icebergs_run(hs[r], (1, 0.0), c, f["uo"], f["vo"], f["ui"], f["vi"], f["tauxa"], f["tauya"], f["ssh"], f["sst"], h,
+                         f["cn"], f["hi"], sss=f["sss"])
+    names = list(COMPARE_F64) + ["ine", "jne", "start_year", "id"]
+    moved = 0
+    for step in range(80):
+        grp.run(one)
+        c, h = f0["calving"].copy(), f0["calving_hflx"].copy()
+        o.run((1, 0.0), c, f0["uo"], f0["vo"], f0["ui"], f0["vi"], f0["tauxa"], f0["tauya"], f0["ssh"], f0["sst"], h, f0["cn"],
+              f0["hi"], sss=f0["sss"])
+        moved += sum(b.counters()["n_sent"] for b in hs)
+        if step % 10 == 9:
+            got = [b.get_bergs(names) for b in hs]
+            got = {k: np.concatenate([p[k] for p in got]) for k in names}
+            assert_bergs_match(got, o.get_bergs(names), rtol=1e-8, context=f"{nranks} ranks, interacting, step {step}", acc_floor=1e-13)
+    assert moved > 5
+    for b in hs:
+        api.icebergs_end(b)
+    grp.close()
