@@ -1421,9 +1421,19 @@ static int ingest_forcing(kid_t* h, const double* calving, const double* uo, con
 }
 
 // ------------------------------------------------------------ one step
+// the namelist matches what the LEAN kernel instances assume (kid_physics.cuh PF())
+static bool lean_config(const kid_t* h) {
+  const KidParams& p = h->p;
+  return p.grid_is_latlon && !p.use_f_plane && h->no_rotation && p.coastal_drift == 0. && p.speed_limit == 0. &&
+         p.cdrag_grounding == 0. && !p.override_iceberg_velocities && p.use_operator_splitting && !p.set_melt_rates_to_zero &&
+         !p.footloose && !p.melt_diagnostics && p.allow_bergs_to_roll && !p.use_updated_rolling_scheme && p.tip_parameter < 999. &&
+         !p.iceberg_melt_without_decay && !p.only_interactive_forces && !getenv("KID_NO_LEAN");
+}
+
 template <bool FL, bool DG>
 static void launch_step(kid_t* h) {
-  LAUNCH(h, (k_step<FL, DG>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots);
+  if (!FL && !DG && lean_config(h)) { LAUNCH(h, (k_step<false, false, false, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
+  else { LAUNCH(h, (k_step<FL, DG>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
 }
 
 static cudaEvent_t pool_event(kid_t* h) {

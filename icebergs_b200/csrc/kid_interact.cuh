@@ -131,7 +131,7 @@ k_ia_velocity(const __grid_constant__ DevGrid g, const __grid_constant__ DevBerg
   interactive_force(g, b, p, ct, s, i, j, ia, uvel, vvel, uvel, vvel);      // I:2153
   double ax1, ay1, un_l, vn_l;
   const double u0 = uvel, v0 = vvel;
-  accel_core<true>(p, M, T, W, L, f_cori, uvel, vvel, dt, e, dragfrac, ia,
+  accel_core<true, false>(p, M, T, W, L, f_cori, uvel, vvel, dt, e, dragfrac, ia,
                    [&](double us, double vs, IAcc& q) { interactive_force(g, b, p, ct, s, i, j, q, u0, v0, us, vs); },   // I:2217
                    ax1, ay1, axn, ayn, bxn, byn, un_l, vn_l);
   if ((p.speed_limit > 0.) || (p.speed_limit == -1.)) {

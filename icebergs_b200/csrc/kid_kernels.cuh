@@ -184,7 +184,7 @@ __device__ __forceinline__ void scatter_fluxes(const DevGrid& g, const Scatter& 
 // thermodynamics of the berg in slot s located at (i,j,xi,yj) moving with (uvel,vvel);
 // loads and stores only the columns thermodynamics touches.  Fills sc; returns the
 // TH_* outcome.
-template <bool FOOTLOOSE>
+template <bool FOOTLOOSE, bool LEAN = false>
 __device__ __forceinline__ int thermo_slot(const DevGrid& g, const DevBergs& b, const DevParams& p, long long s,
                                            uint8_t flags, int i, int j, double xi, double yj, double uvel,
                                            double vvel, double M, double T, double W, double L, double mass_scaling,
@@ -192,7 +192,7 @@ __device__ __forceinline__ int thermo_slot(const DevGrid& g, const DevBergs& b, 
                                            DevCounters* cnt) {
   const int cidx = gidx(g, i, j);
   EnvThermo e;
-  interp_thermo(g, p, cidx, xi, yj, e);
+  interp_thermo<LEAN>(g, p, cidx, xi, yj, e);
   if ((e.uo != e.uo) || (e.vo != e.vo) || (e.ua != e.ua) || (e.va != e.va) || (e.sst != e.sst) || (e.cn != e.cn))
     atomicOr(&cnt->error_flags, 64u);
   if (e.rarea == 0.) { atomicOr(&cnt->error_flags, (unsigned)KID_DEVERR_GROUNDED); return TH_KEEP; }
@@ -210,12 +210,12 @@ __device__ __forceinline__ int thermo_slot(const DevGrid& g, const DevBergs& b, 
   }
   st.start_day = 0.; st.start_year = 0;
   double N_bonds = 0.;
-  if (p.allow_bergs_to_roll) {
+  if (PF(allow_bergs_to_roll, 1)) {
     // N_bonds: I:2928-2944 (this%n_bonds = the length of the bond list, assign_n_bonds F:4617)
     for (int k = 0; k < b.max_bonds; k++) if (b.bond_other_id[(long long)k * b.capacity + s] != 0) N_bonds += 1.0;
     if (flags & BF_STATIC) N_bonds = p.hexagonal_icebergs ? 6.0 : 4.0;
   }
-  int outcome = thermo_berg(p, e, uvel, vvel, N_bonds, st, sc.fx);
+  int outcome = thermo_berg<LEAN>(p, e, uvel, vvel, N_bonds, st, sc.fx);
   sc.key = (long long)cidx;
   b.f64[C_MASS][s] = st.mass;
   b.f64[C_THICKNESS][s] = st.thickness;
@@ -256,7 +256,7 @@ struct BergIn {
 // evolve_icebergs (I:7081) + send_bergs_to_other_pes (F:2997) + thermodynamics (I:2844) for one berg
 // SPLIT: the velocity solve already ran (k_ia_velocity, interactions on): this is the second sweep of
 // evolve_icebergs I:7182-7197 (position, *_old refresh) followed by send_bergs and thermodynamics
-template <bool FOOTLOOSE, bool SPLIT>
+template <bool FOOTLOOSE, bool SPLIT, bool LEAN = false>
 __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, const DevParams& p,
                                           DevCounters* __restrict__ cnt, long long s, const BergIn& in, Scatter& sc,
                                           bool& melted, bool& became_fl, bool& bounced, bool& speeding, bool& left) {
@@ -268,8 +268,8 @@ __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, c
   if (!(flags & BF_STATIC)) {
     double axn = in.axn, ayn = in.ayn, bxn = in.bxn, byn = in.byn;
     double sin_lat = 0., cos_lat = 1.;
-    if (p.grid_is_latlon) sincos_halfpi(p.pi_180 * lat, &sin_lat, &cos_lat);
-    const bool tang = (lat > 89.) && p.grid_is_latlon;
+    if (PF(grid_is_latlon, 1)) sincos_halfpi(p.pi_180 * lat, &sin_lat, &cos_lat);
+    const bool tang = (lat > 89.) && PF(grid_is_latlon, 1);
     if (!SPLIT) {
       // ---- verlet_stepping I:7203-7328
       b.f64[C_UVEL_PREV][s] = uvel - dt_2 * bxn;
@@ -277,26 +277,26 @@ __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, c
       double uvel3 = uvel + (dt_2 * axn);
       double vvel3 = vvel + (dt_2 * ayn);
       Env e;
-      if (!interp_flds(g, p, i, j, xi, yj, e)) atomicOr(&cnt->error_flags, 64u);
-      double f_cori = (p.grid_is_latlon && !p.use_f_plane) ? p.omega2 * sin_lat : p.f_cori_plane;
+      if (!interp_flds<LEAN>(g, p, i, j, xi, yj, e)) atomicOr(&cnt->error_flags, 64u);
+      double f_cori = (PF(grid_is_latlon, 1) && !PF(use_f_plane, 0)) ? p.omega2 * sin_lat : p.f_cori_plane;
       double ax1, ay1, un_l, vn_l;
       IAcc ia0 = {0., 0., 0., 0., 0., 0., 0., 0.};
-      accel_core<false>(p, M, T, W, L, f_cori, uvel, vvel, dt, e, 1.0, ia0,
+      accel_core<false, LEAN>(p, M, T, W, L, f_cori, uvel, vvel, dt, e, 1.0, ia0,
                         [](double, double, IAcc&) {}, ax1, ay1, axn, ayn, bxn, byn, un_l, vn_l);
-      if ((p.speed_limit > 0.) || (p.speed_limit == -1.)) {   // I:2304-2323: only the ticket survives
+      if ((PF(speed_limit, 0.) > 0.) || (PF(speed_limit, 0.) == -1.)) {   // I:2304-2323: only the ticket survives
         double speed = sqrt(un_l * un_l + vn_l * vn_l);
         if (speed > 0.) {
           size_t c = gidx(g, i, j);
           double loc_dx = fmin(0.5 * (g.dx[c] + g.dx[c - g.nid]), 0.5 * (g.dy[c] + g.dy[c - 1]));
-          double new_speed = loc_dx / dt * p.speed_limit;
-          if (new_speed < speed && p.speed_limit > 0.) speeding = true;
+          double new_speed = loc_dx / dt * PF(speed_limit, 0.);
+          if (new_speed < speed && PF(speed_limit, 0.) > 0.) speeding = true;
         }
       }
       double uveln, vveln;
       lon = b.f64[C_LON][s];
       if (tang) tang_velocity(p, lon, uvel3, vvel3, ax1, ay1, dt, uveln, vveln);
       else { uveln = uvel3 + (dt * ax1); vveln = vvel3 + (dt * ay1); }
-      if (p.override_iceberg_velocities) { uveln = p.u_override; vveln = p.v_override; }
+      if (PF(override_iceberg_velocities, 0)) { uveln = p.u_override; vveln = p.v_override; }
       uvel = uveln; vvel = vveln;      // evolve_icebergs I:7157-7162
     } else {
       lon = b.f64[C_LON][s];
@@ -313,7 +313,7 @@ __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, c
       tang_position(p, lon, lat, uvel2, vvel2, dt, lonn, latn);
     } else {
       double dxdl1 = 1., dydl = 1.;
-      if (p.grid_is_latlon) { dxdl1 = p.r180_pi * rcp_nr(p.Rearth * cos_lat); dydl = p.dlat_dy; }
+      if (PF(grid_is_latlon, 1)) { dxdl1 = p.r180_pi * rcp_nr(p.Rearth * cos_lat); dydl = p.dlat_dy; }
       double u2 = uvel2 * dxdl1, v2 = vvel2 * dydl;
       lonn = lon + (dt * u2); latn = lat + (dt * v2);
     }
@@ -345,7 +345,7 @@ __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, c
   else if (route == 2) { b.flags[s] = 0; }
   else {
     // ---- thermodynamics I:2844-3300 at the new position
-    int outcome = thermo_slot<FOOTLOOSE>(g, b, p, s, flags, i, j, xi, yj, uvel, vvel, M, T, W, L,
+    int outcome = thermo_slot<FOOTLOOSE, LEAN>(g, b, p, s, flags, i, j, xi, yj, uvel, vvel, M, T, W, L,
                                          b.f64[C_MASS_SCALING][s], b.f64[C_MASS_OF_BITS][s], b.f64[C_HEAT_DENSITY][s],
                                          sc, cnt);
     if (outcome == TH_DELETE) { melted = true; b.flags[s] = 0; }
@@ -353,7 +353,7 @@ __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, c
   }
 }
 
-template <bool FOOTLOOSE, bool DIAG, bool SPLIT = false>
+template <bool FOOTLOOSE, bool DIAG, bool SPLIT = false, bool LEAN = false>
 __global__ void __launch_bounds__(KID_BLOCK, KID_MINBLOCKS)
 k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
        const __grid_constant__ DevParams p, DevCounters* __restrict__ cnt, long long n_slots) {
@@ -386,7 +386,7 @@ k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
   sc.fx.fl_parent_melt = sc.fx.fl_child_melt = sc.fx.melt_buoy = sc.fx.melt_eros = sc.fx.melt_conv = 0.;
   sc.fx.melt_buoy_fl = sc.fx.melt_eros_fl = sc.fx.melt_conv_fl = 0.;
   bool melted = false, became_fl = false, bounced = false, speeding = false, left = false;
-  if (owned) step_berg<FOOTLOOSE, SPLIT>(g, b, p, cnt, s, in, sc, melted, became_fl, bounced, speeding, left);
+  if (owned) step_berg<FOOTLOOSE, SPLIT, LEAN>(g, b, p, cnt, s, in, sc, melted, became_fl, bounced, speeding, left);
   scatter_fluxes<FOOTLOOSE, DIAG>(g, sc);
   // event counters: one vote decides whether the warp has anything to report at all
   if (__any_sync(0xffffffffu, melted | bounced | speeding | left)) {

@@ -21,6 +21,13 @@ namespace kid {
 
 struct Env { double uo, vo, ui, vi, ua, va, ssh_x, ssh_y, sst, sss, cn, hi, od; };
 
+// LEAN instances of the hot functions take the namelist switches below as compile-time constants
+// (the values of the default free-drift configuration: lat-lon grid aligned with the axes, no f-plane,
+// no coastal drift / speed limit / grounding drag / velocity override, operator-split melt, default
+// rolling scheme, no footloose, no melt diagnostics); kid_init picks them when the parameters match
+// (lean_config()), otherwise the generic instances read every switch at run time.
+#define PF(field, leanval) (LEAN ? (leanval) : (p.field))
+
 // Reciprocal and square root for the drag/melt-rate arithmetic: hardware seed (MUFU.RCP64H /
 // MUFU.RSQ64H, ~20 bits) refined by Newton / Goldschmidt steps to ~1 ulp, without the IEEE
 // corner-case paths of `/` and sqrt() (operands here are masses, lengths, speeds: positive,
@@ -104,6 +111,7 @@ __device__ __forceinline__ void rotate(double& u, double& v, double cos_rot, dou
 }
 
 // I:4718-4900 (non-MTS ocean depth, I:4897).  Returns false when a NaN survived.
+template <bool LEAN = false>
 __device__ __forceinline__ bool interp_flds(const DevGrid& g, const DevParams& p, int i, int j, double xi,
                                             double yj, Env& e) {
   const CornerRec* __restrict__ cr = g.corner;
@@ -113,13 +121,13 @@ __device__ __forceinline__ bool interp_flds(const DevGrid& g, const DevParams& p
   const CornerRec c3 = cr[ne], c4 = cr[ne - 1], c2 = cr[ne - nid], c1 = cr[ne - nid - 1];
   KID_BILIN_WEIGHTS
   double cos_rot = 1., sin_rot = 0.;
-  if (!p.no_rotation) { cos_rot = KID_BILIN(cosr); sin_rot = KID_BILIN(sinr); }
+  if (!PF(no_rotation, 1)) { cos_rot = KID_BILIN(cosr); sin_rot = KID_BILIN(sinr); }
   double uo = KID_BILIN(uo), vo = KID_BILIN(vo);
   double ui = KID_BILIN(ui), vi = KID_BILIN(vi);
   double ua = KID_BILIN(ua), va = KID_BILIN(va);
-  if (p.coastal_drift > 0.) {
+  if (PF(coastal_drift, 0.) > 0.) {
     const double* __restrict__ msk = g.msk;
-    double cd = p.coastal_drift;
+    double cd = PF(coastal_drift, 0.);
     double m0 = msk[ne], mE = msk[ne + 1], mW = msk[ne - 1], mN = msk[ne + nid], mS = msk[ne - nid];
     uo = uo + cd * (mE - mW) * m0;
     ui = ui + cd * (mE - mW) * m0;
@@ -152,7 +160,7 @@ __device__ __forceinline__ bool interp_flds(const DevGrid& g, const DevParams& p
     hxm = fma((xi + 0.5), ddy_i0s, (0.5 - xi) * ddy_i1s);
   }
   double ssh_y = fma(yj, hxp, (1. - yj) * hxm);
-  if (!p.no_rotation) {
+  if (!PF(no_rotation, 1)) {
     rotate(uo, vo, cos_rot, sin_rot);
     rotate(ui, vi, cos_rot, sin_rot);
     rotate(ua, va, cos_rot, sin_rot);
@@ -169,6 +177,7 @@ __device__ __forceinline__ bool interp_flds(const DevGrid& g, const DevParams& p
 // What thermodynamics (I:2896-2920) uses of interp_flds: the rotated ocean and wind velocities
 // and the A-grid picks of sst, cn; also hands back 1/area of the cell.
 struct EnvThermo { double uo, vo, ua, va, sst, cn, rarea; };
+template <bool LEAN = false>
 __device__ __forceinline__ void interp_thermo(const DevGrid& g, const DevParams& p, int ne, double xi, double yj,
                                               EnvThermo& e) {
   const CornerRec* __restrict__ cr = g.corner;
@@ -177,14 +186,14 @@ __device__ __forceinline__ void interp_thermo(const DevGrid& g, const DevParams&
   KID_BILIN_WEIGHTS
   double uo = KID_BILIN(uo), vo = KID_BILIN(vo);
   double ua = KID_BILIN(ua), va = KID_BILIN(va);
-  if (p.coastal_drift > 0.) {
+  if (PF(coastal_drift, 0.) > 0.) {
     const double* __restrict__ msk = g.msk;
-    double cd = p.coastal_drift;
+    double cd = PF(coastal_drift, 0.);
     double m0 = msk[ne], mE = msk[ne + 1], mW = msk[ne - 1], mN = msk[ne + nid], mS = msk[ne - nid];
     uo = uo + cd * (mE - mW) * m0;
     vo = vo + cd * (mN - mS) * m0;
   }
-  if (!p.no_rotation) {
+  if (!PF(no_rotation, 1)) {
     double cos_rot = KID_BILIN(cosr), sin_rot = KID_BILIN(sinr);
     rotate(uo, vo, cos_rot, sin_rot);
     rotate(ua, va, cos_rot, sin_rot);
@@ -213,7 +222,7 @@ __device__ __forceinline__ void convert_from_meters_to_grid(const DevParams& p, 
 // accel I:1950-2442 after the environment is known.  IAF(us, vs, IAcc&) evaluates
 // interactive_force with the latest velocity estimate (second call, I:2217); ia is
 // the first evaluation (I:2153).  dragfrac: I:2104-2120.  f_cori: I:2043-2047.
-template <bool INTERACTIVE, class IAF>
+template <bool INTERACTIVE, bool LEAN = false, class IAF>
 __device__ __forceinline__ void accel_core(const DevParams& p, double M, double T, double W, double L,
                                            double f_cori, double uvel0, double vvel0, double dt, const Env& e,
                                            double dragfrac, IAcc ia, IAF&& iaf, double& ax, double& ay,
@@ -231,7 +240,7 @@ __device__ __forceinline__ void accel_core(const DevParams& p, double M, double 
   hi = kmin(hi, D);
   double D_hi = kmax(0., D - hi);
   double c_gnd = 0.0;
-  if (p.cdrag_grounding != 0.) {      // I:2066-2082 (c_gnd is exactly 0 otherwise)
+  if (PF(cdrag_grounding, 0.) != 0.) {      // I:2066-2082 (c_gnd is exactly 0 otherwise)
     double groundfrac;
     if (p.h_to_init_grounding > 0.0) {
       groundfrac = 1.0 - (od - D) * p.r_h2ig;
@@ -239,7 +248,7 @@ __device__ __forceinline__ void accel_core(const DevParams& p, double M, double 
     } else {
       groundfrac = (D > od) ? 1.0 : 0.0;
     }
-    if (groundfrac > 0.0) c_gnd = (p.cdrag_grounding * W * L * groundfrac) * rM;
+    if (groundfrac > 0.0) c_gnd = (PF(cdrag_grounding, 0.) * W * L * groundfrac) * rM;
   }
   double uwave = ua - uo, vwave = va - vo;
   double wmod = fma(uwave, uwave, vwave * vwave);
@@ -298,7 +307,7 @@ __device__ __forceinline__ void accel_core(const DevParams& p, double M, double 
       RHS_y = RHS_y - (((ia.P21 * u_star) + (ia.P22 * v_star)) - ia.Pu_y);
     }
     double A11, A12, A21, A22;
-    if (INTERACTIVE && p.only_interactive_forces) {
+    if (INTERACTIVE && PF(only_interactive_forces, 0)) {
       RHS_x = (ia.IA_x * 0.5) - (((ia.P11 * u_star) + (ia.P12 * v_star)) - ia.Pu_x);
       RHS_y = (ia.IA_y * 0.5) - (((ia.P21 * u_star) + (ia.P22 * v_star)) - ia.Pu_y);
       A11 = 1 + (dt * ia.P11); A12 = (dt * ia.P12); A21 = (dt * ia.P21); A22 = 1 + (dt * ia.P22);
@@ -319,7 +328,7 @@ __device__ __forceinline__ void accel_core(const DevParams& p, double M, double 
     uveln = fma(dt, ax, u_star);
     vveln = fma(dt, ay, v_star);
   }
-  if (INTERACTIVE && p.only_interactive_forces) {
+  if (INTERACTIVE && PF(only_interactive_forces, 0)) {
     axn = ia.IA_x; ayn = ia.IA_y;
   } else {
     axn = fma(f_cori, vveln, ax_expl);
@@ -327,7 +336,7 @@ __device__ __forceinline__ void accel_core(const DevParams& p, double M, double 
   }
   bxn = fma(axn, -0.5, ax); byn = fma(ayn, -0.5, ay);
   uveln_out = uveln; vveln_out = vveln;
-  if (p.override_iceberg_velocities) { ax = 0.0; ay = 0.0; axn = 0.0; ayn = 0.0; bxn = 0.0; byn = 0.0; }
+  if (PF(override_iceberg_velocities, 0)) { ax = 0.0; ay = 0.0; axn = 0.0; ayn = 0.0; bxn = 0.0; byn = 0.0; }
 }
 
 // tangent plane helpers I:7767-7816, I:8066-8099 (lat > 89 only)
@@ -426,11 +435,12 @@ __device__ __forceinline__ bool adjust_index_and_ground(const DevGrid& g, const 
 
 // I:3307-3364
 __device__ __forceinline__ void swap_d(double& x, double& y) { double t = x; x = y; y = t; }
+template <bool LEAN = false>
 __device__ __forceinline__ void rolling(const DevParams& p, double& Tn, double& Wn, double& Ln) {
   const double Delta = 6.0;
   double Dn = p.rho_ratio * Tn;
   if (Dn > 0.) {
-    if ((!p.use_updated_rolling_scheme) && (p.tip_parameter < 999.)) {
+    if ((!PF(use_updated_rolling_scheme, 0)) && (LEAN || p.tip_parameter < 999.)) {
       // max(W,L) < sqrt(X): decided on the squares unless the two sides agree to 1e-12, where the
       // reference's own sqrt-then-compare is evaluated
       double mx = kmax(Wn, Ln), X = 0.92 * (Dn * Dn) + 58.32 * Dn, m2 = mx * mx;
@@ -442,14 +452,14 @@ __device__ __forceinline__ void rolling(const DevParams& p, double& Tn, double& 
       }
     } else {
       if (Wn > Ln) swap_d(Ln, Wn);
-      if ((!p.use_updated_rolling_scheme) && (p.tip_parameter >= 999.)) {
+      if ((!PF(use_updated_rolling_scheme, 0)) && (!LEAN && p.tip_parameter >= 999.)) {
         double q = p.rho_bergs / KID_RHO_SEAWATER;
         if (Wn < sqrt((6.0 * q * (1 - q) * (Tn * Tn)) - (12 * Delta * q * Tn))) {
           swap_d(Tn, Wn);
           if (Wn > Ln) swap_d(Wn, Ln);
         }
       }
-      if (p.use_updated_rolling_scheme) {
+      if (PF(use_updated_rolling_scheme, 0)) {
         double tip_parameter;
         if (p.tip_parameter > 0.) tip_parameter = p.tip_parameter;
         else tip_parameter = sqrt(6 * (p.rho_bergs / KID_RHO_SEAWATER) * (1 - (p.rho_bergs / KID_RHO_SEAWATER)));
@@ -550,6 +560,7 @@ __device__ __forceinline__ double pow_08(double x) { return (x > 1.e-30) ? x * p
 
 // thermodynamics of one berg, I:2896-3296.  e.rarea = 1/grd%area(i,j) (caller has checked the
 // cell is not dry), N_bonds per I:2928-2944.
+template <bool LEAN = false>
 __device__ __forceinline__ int thermo_berg(const DevParams& p, const EnvThermo& e, double uvel, double vvel,
                                            double N_bonds, ThermoState& s, ThermoFlux& fx) {
   const double perday = 1. / 86400.;
@@ -570,9 +581,9 @@ __device__ __forceinline__ int thermo_berg(const DevParams& p, const EnvThermo& 
   double Me = kmax(1. / 12. * (SST + 2.) * Ss * wave_ic, 0.) * perday;
   double Mv_fl = 0., Me_fl = 0.;
   if (s.mass_of_fl_bits > 0.) { Mv_fl = Mv; Me_fl = Me; }
-  if (p.set_melt_rates_to_zero) { Mv = 0.0; Mb = 0.0; Me = 0.0; }
+  if (PF(set_melt_rates_to_zero, 0)) { Mv = 0.0; Mb = 0.0; Me = 0.0; }
   double Tn, Mnew1, Mnew2, Mnew, dMb, dMv, dMe, dM, Ln1 = 0, Wn1 = 0, Ln, Wn;
-  if (p.use_operator_splitting) {
+  if (PF(use_operator_splitting, 1)) {
     // the mass differences below cancel to ~1e-6 of the mass: each (nVol/Vol)*M keeps the
     // reference's own rounding sequence so that dMe (hence the bergy bits) agrees to 1e-10
     Tn = kmax(T - Mb * dt, 0.);
@@ -597,7 +608,7 @@ __device__ __forceinline__ int thermo_berg(const DevParams& p, const EnvThermo& 
     dMe = M_Vol * (T * (W + L)) * Me * dt;
     dMv = M_Vol * (T * (W + L)) * Mv * dt;
   }
-  if (p.footloose) {
+  if (PF(footloose, 0)) {
     if (s.fl_k >= 0) {
       const double l_c = p.pi / (2. * sqrt(2.)), lw_c = 1. / (KID_GRAVITY * KID_RHO_SEAWATER);
       const double B_c = 1. / (12. * (1. - pow(0.3, 2.)));
@@ -676,7 +687,7 @@ __device__ __forceinline__ int thermo_berg(const DevParams& p, const EnvThermo& 
     fx.fl_bits_melt = dMfl * k;
     fx.fl_parent_melt = fx.fl_child_melt = fx.melt_buoy = fx.melt_eros = fx.melt_conv = 0.;
     fx.melt_buoy_fl = fx.melt_eros_fl = fx.melt_conv_fl = 0.;
-    if (p.melt_diagnostics) {
+    if (PF(melt_diagnostics, 0)) {
       if (s.fl_k >= 0) {
         fx.fl_parent_melt = (dM - (dMbitsE - dMbitsM)) * k;
         fx.fl_child_melt = (dMfl - (dMbitsE_fl - dMbitsM_fl)) * k;
@@ -689,8 +700,8 @@ __device__ __forceinline__ int thermo_berg(const DevParams& p, const EnvThermo& 
     }
   }
   fx.fl_bits_src = 0.;
-  if (p.allow_bergs_to_roll && N_bonds == 0.) rolling(p, Tn, Wn, Ln);
-  if (p.iceberg_melt_without_decay) {
+  if (PF(allow_bergs_to_roll, 1) && N_bonds == 0.) rolling<LEAN>(p, Tn, Wn, Ln);
+  if (PF(iceberg_melt_without_decay, 0)) {
     Mnew = s.mass; Mnew_fl = s.mass_of_fl_bits; nMbits_fl = s.mass_of_fl_bergy_bits;
   } else {
     s.mass = Mnew;
