@@ -278,7 +278,7 @@ def main():
                        "l2_policy": f"inputs larger than L2 ({B_BERG * n_per / 1e9:.2f} GB of berg state per step vs 126 MB L2)",
                        "timed_region": "kid_step_resident(K): fused dyn+thermo kernel, flux-field zeroing, periodic cell sort"
                                        + (", NCCL migration" if multi else ""),
-                       "wall_ms_per_step": wall_ms / args.steps, "sort_interval": int(os.environ.get("KID_SORT_INTERVAL", "16"))},
+                       "wall_ms_per_step": wall_ms / args.steps, "sort_interval": int(os.environ.get("KID_SORT_INTERVAL", "32"))},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "k_step (fused evolve+thermodynamics)",
                          "alg_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms},

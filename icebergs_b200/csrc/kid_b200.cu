@@ -59,7 +59,7 @@ struct kid_handle {
   long long launches = 0;
   int visited = 0, first_call_accum = 1, restarted = 0;
   int calving_active = 0;
-  int steps_since_sort = 0, sort_interval = 16, sorted_once = 0;
+  int steps_since_sort = 0, sort_interval = 32, sorted_once = 0;
   int forcing_set = 0;
   int no_rotation = 0;
   long long dirty_appended = 0;

@@ -353,6 +353,38 @@ __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, c
   }
 }
 
+#ifndef KID_PF_DIST
+#define KID_PF_DIST 0      // measured slower with 740..4096 (profiles/r1_notes.md): off
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// The tile a CTA KID_PF_DIST blocks ahead will read is pulled into L2 now (one 128-byte line per
+// thread): its column loads then pay an L2 round trip instead of a DRAM one.  No registers, no
+// extra DRAM traffic (the later loads hit the prefetched lines).
+__device__ __forceinline__ void prefetch_tile_ahead(const DevBergs& b, long long n_slots) {
+#if KID_PF_DIST > 0
+  const long long t0 = ((long long)blockIdx.x + KID_PF_DIST) * KID_BLOCK;
+  if (t0 + KID_BLOCK > n_slots) return;
+  constexpr int cols[17] = {C_LAT, C_UVEL, C_VVEL, C_AXN, C_AYN, C_BXN, C_BYN, C_XI, C_YJ, C_MASS, C_THICKNESS,
+                            C_WIDTH, C_LENGTH, C_LON, C_MASS_SCALING, C_MASS_OF_BITS, C_HEAT_DENSITY};
+  constexpr int lines8 = KID_BLOCK * 8 / 128;        // 128-byte lines of one fp64 column of the tile
+  for (int k = threadIdx.x; k < 17 * lines8 + 2 * (lines8 / 2) + 1; k += KID_BLOCK) {
+    if (k < 17 * lines8) {
+      int c = k / lines8, l = k % lines8;
+      const double* col = b.f64[0];
+#pragma unroll
+      for (int q = 0; q < 17; q++) if (c == q) col = b.f64[cols[q]];
+      prefetch_l2(col + t0 + l * 16);
+    } else {
+      int r = k - 17 * lines8;
+      if (r < lines8 / 2) prefetch_l2(b.ine + t0 + r * 32);
+      else if (r < lines8) prefetch_l2(b.jne + t0 + (r - lines8 / 2) * 32);
+      else prefetch_l2(b.flags + t0);
+    }
+  }
+#endif
+}
+
 template <bool FOOTLOOSE, bool DIAG, bool SPLIT = false, bool LEAN = false>
 __global__ void __launch_bounds__(KID_BLOCK, KID_MINBLOCKS)
 k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
@@ -360,6 +392,7 @@ k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
   long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = s < n_slots;
   const long long sl = in_range ? s : 0;          // out-of-range lanes read slot 0 and are masked by flags
+  if (!SPLIT) prefetch_tile_ahead(b, n_slots);
   // all column loads are issued unconditionally, ahead of the flags test (dead slots are rare and
   // only live until the next sort)
   BergIn in;
