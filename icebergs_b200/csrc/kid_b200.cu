@@ -235,7 +235,7 @@ static void fill_dev_params(kid_t* h) {
   q.tip_parameter = p.tip_parameter; q.melt_cutoff = p.melt_cutoff;
   q.spring_coef = p.spring_coef; q.contact_spring_coef = p.contact_spring_coef; q.contact_distance = p.contact_distance;
   q.radial_damping_coef = p.radial_damping_coef; q.tangental_damping_coef = p.tangental_damping_coef;
-  q.fl_youngs = p.fl_youngs;
+  q.fl_youngs = p.fl_youngs; q.new_berg_from_fl_bits_mass_thres = p.new_berg_from_fl_bits_mass_thres;
   q.grid_is_latlon = p.grid_is_latlon; q.grid_is_regular = p.grid_is_regular; q.old_bug_bilin = p.old_bug_bilin;
   q.use_roundoff_fix = p.use_roundoff_fix; q.use_f_plane = p.use_f_plane;
   q.use_new_predictive_corrective = p.use_new_predictive_corrective;
@@ -514,7 +514,8 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
     unsupported = "contact_distance>0 / contact_spring_coef != spring_coef (conglomerate contact search) is not implemented in this build";
   else if (pin->iceberg_bonds_on && !pin->interactive_icebergs_on) unsupported = "iceberg_bonds_on needs interactive_icebergs_on";
   else if (pin->iceberg_bonds_on && (pin->max_bonds < 1 || pin->max_bonds > 12)) unsupported = "max_bonds must be 1..12";
-  else if (pin->footloose) unsupported = "footloose calving is not implemented in this build";
+  else if (pin->footloose && pin->displace_fl_bergs) unsupported = "displace_fl_bergs needs the FMS random number stream: set displace_fl_bergs=0";
+  else if (pin->footloose && dom->nranks > 1) unsupported = "footloose calving across ranks is not implemented in this build";
   else if (pin->iceberg_bonds_on && dom->nranks > 1) unsupported = "bonds across ranks are not implemented in this build";
   else if (dom->cyclic_y) unsupported = "cyclic y is not implemented";
   else if (pin->halo < 2) unsupported = "halo must be >= 2";
@@ -866,6 +867,8 @@ static int check_device_errors(kid_t* h) {
     if (e & 128u) return fail(h, KID_ERR_STATE, "KID, calve_icebergs: berg is not in the correct cell!");
     if (e & 256u) return fail(h, KID_ERR_STATE, "KID, connect_all_bonds: A non-halo bond is missing!!!");
     if (e & 512u) return fail(h, KID_ERR_CAPACITY, "kid: a berg has more than max_bonds bonds");
+    if (e & 1024u) return fail(h, KID_ERR_STATE, "KID,footloose_calving: Bonded footloose calving not yet fully implemented!");
+    if (e & 2048u) return fail(h, KID_ERR_STATE, "KID,footloose_calving: non-edge element has fully calved from footloose mechanism");
     return fail(h, KID_ERR_STATE, "kid: device error flag set");
   }
   return KID_OK;
@@ -896,7 +899,7 @@ static int sort_bergs(kid_t* h) {
   k_scan_sums<<<1, 1024, 0, h->stream>>>(h->scan_sums, nsb, h->scan_total); h->launches++;
   LAUNCH(h, k_scan_add, n2, 256, h->cell_start, h->scan_sums, n2);
   LAUNCH(h, k_rank, ns, 256, h->g, h->b.flags, h->b.ine, h->b.jne, ns, h->cell_start, h->cell_fill, h->perm);
-  LAUNCH(h, k_cell_order, n2, 128, h->cell_start, h->cell_count, n2, h->perm);
+  LAUNCH(h, k_cell_order, n2, 128, h->b, h->cell_start, h->cell_count, n2, h->perm, h->p.footloose ? 1 : 0);
   int32_t total = 0;
   CK(cudaMemcpyAsync(&total, h->scan_total, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -1480,17 +1483,17 @@ static int step_core(kid_t* h) {
       h->bond_lengths_set = 1;
     }
   }
+  const bool fl = h->p.footloose != 0, dg = h->p.melt_diagnostics != 0;
   if (!h->p.static_icebergs) {
     if (ia) {
       CellTable ct{h->cell_start, h->cell_count};
       LAUNCH(h, k_ia_velocity, h->n_slots, KID_BLOCK, h->g, h->b, h->dp, ct, h->dcnt, h->n_slots);
-      if (h->p.melt_diagnostics) { LAUNCH(h, (k_step<false, true, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
+      if (fl) { LAUNCH(h, (k_step<true, false, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
+      else if (dg) { LAUNCH(h, (k_step<false, true, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
       else { LAUNCH(h, (k_step<false, false, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
       if (h->b.max_bonds > 0) LAUNCH(h, k_bond_address_update, h->n_slots, 128, h->b, h->n_slots);
-    } else if (h->p.melt_diagnostics) launch_step<false, true>(h); else launch_step<false, false>(h);
-  } else {
-    if (h->p.melt_diagnostics) { LAUNCH(h, (k_thermo_range<false, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, 0LL, h->n_slots, 1); }
-    else { LAUNCH(h, (k_thermo_range<false, false>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, 0LL, h->n_slots, 1); }
+    } else if (fl) { LAUNCH(h, (k_step<true, false, false>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
+    else if (dg) launch_step<false, true>(h); else launch_step<false, false>(h);
   }
   CK(cudaEventRecord(ek, s));
   if (h->d.nranks > 1) {
@@ -1507,12 +1510,40 @@ static int step_core(kid_t* h) {
       h->tables_valid = 0;
     }
   }
+  if (fl) {
+    // footloose_calving I:5455 (after send_bergs): per-cell walk in the reference's list order
+    int rc = sort_bergs(h);
+    if (rc) return rc;
+    CellTable ct{h->cell_start, h->cell_count};
+    FlConsts fc;
+    const double e1 = exp(0.25 * h->p.pi), drho = KID_RHO_SEAWATER - h->p.rho_bergs, sigmay = h->p.fl_strength * 1000;
+    fc.lfootparam = e1 * KID_RHO_SEAWATER * sigmay / (6 * h->p.rho_bergs * KID_GRAVITY * drho);
+    fc.l_c = h->p.pi / (2. * sqrt(2.)); fc.lw_c = 1. / (KID_GRAVITY * KID_RHO_SEAWATER);
+    fc.B_c = h->p.fl_youngs / (12. * (1. - pow(0.3, 2.)));
+    LAUNCH(h, k_footloose, (long long)h->nic * h->njc, 64, h->g, h->b, h->dp, fc, ct, h->dcnt, h->p.fl_style_fl_bits,
+           h->p.new_berg_from_fl_bits_mass_thres);
+    CK(cudaMemcpyAsync(&h->hcnt->n_slots, &h->dcnt->n_slots, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    long long ns = (long long)h->hcnt->n_slots;
+    if (ns > h->capacity) return fail(h, KID_ERR_CAPACITY, "kid: berg store capacity exceeded by footloose calving");
+    if (ns != h->n_slots) { h->tables_valid = 0; h->n_slots = ns; }
+  }
   CK(cudaEventRecord(h->ev[T_SORT], s));
   CK(cudaEventRecord(e1, s));
   h->steps_since_sort++;
   if (ia) {
     int rc = refresh_interactive_state(h);
     if (rc) return rc;
+    if (fl) { CellTable ct{h->cell_start, h->cell_count}; LAUNCH(h, k_fl_interactivity, h->n_slots, 128, h->g, h->b, h->dp, ct, h->n_slots); }
+  }
+  if (fl || h->p.static_icebergs) {
+    // thermodynamics I:5497 on its own: footloose calving sits between the move and the melt
+    if (fl && dg) { LAUNCH(h, (k_thermo_range<true, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, 0LL, h->n_slots, 1); }
+    else if (fl) { LAUNCH(h, (k_thermo_range<true, false>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, 0LL, h->n_slots, 1); }
+    else if (dg) { LAUNCH(h, (k_thermo_range<false, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, 0LL, h->n_slots, 1); }
+    else { LAUNCH(h, (k_thermo_range<false, false>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, 0LL, h->n_slots, 1); }
+  }
+  if (ia) {
   } else if (h->steps_since_sort >= h->sort_interval || h->dirty_appended > h->n_slots / 8) {
     int rc = sort_bergs(h);
     if (rc) return rc;

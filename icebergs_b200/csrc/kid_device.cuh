@@ -42,7 +42,7 @@ struct DevParams {
   double cdrag_grounding, h_to_init_grounding, u_override, v_override;
   double bergy_bit_erosion_fraction, sicn_shift, tip_parameter, melt_cutoff;
   double spring_coef, contact_spring_coef, contact_distance, radial_damping_coef, tangental_damping_coef;
-  double fl_youngs;
+  double fl_youngs, new_berg_from_fl_bits_mass_thres;
   double current_yearday;
   // host-precomputed constants of the step (same libm as the CPU path)
   double rdt;            // 1/dt

@@ -403,3 +403,173 @@ __global__ void k_orig_bond_length(const __grid_constant__ DevBergs b, long long
 }
 
 }  // namespace kid
+
+namespace kid {
+
+// ----------------------------------------------------------------- footloose
+// footloose_calving I:2503-2734 + calve_fl_icebergs I:6405-6569 (displace_fl_bergs off: the
+// displacement draws from the FMS random stream).  One thread per compute cell walks the cell's bergs
+// in store order -- the store is sorted with the reference's list key (k_cell_order keyed) -- so the
+// per-cell id counter (generate_id F:4165) hands out the reference's ids.
+struct FlConsts { double lfootparam, l_c, lw_c, B_c; };
+
+__device__ __forceinline__ long long fl_new_child(const DevGrid& g, const DevBergs& b, const DevParams& p,
+                                                  DevCounters* __restrict__ cnt, long long ps, double k, double l_b,
+                                                  bool from_bits) {
+  unsigned long long s = atomicAdd(&cnt->n_slots, 1ull);
+  if ((long long)s >= b.capacity) { atomicOr(&cnt->error_flags, (unsigned)KID_DEVERR_CAPACITY); return -1; }
+  for (int c = 0; c < C_NCOLS; c++) if (b.f64[c]) b.f64[c][s] = b.f64[c][ps];      // lon, lat, xi, yj, velocities, accelerations, ...
+  double len, wid, thk, mass, ms, mob = 0.;
+  if (from_bits) {
+    // fl_bits_dimensions I:3370-3387
+    const double l_c = p.pi / (2. * sqrt(2.)), lw_c = 1. / (KID_GRAVITY * KID_RHO_SEAWATER);
+    const double B_c = 1. / (12. * (1. - pow(0.3, 2.)));
+    double l_w = pow(lw_c * p.fl_youngs * B_c * pow(b.f64[C_THICKNESS][ps], 3.), 0.25);
+    double lb = l_c * l_w;
+    len = 3. * lb; wid = lb; thk = b.f64[C_THICKNESS][ps];
+    rolling(p, thk, wid, len);
+    mass = thk * len * wid * p.rho_bergs;
+    ms = k * p.new_berg_from_fl_bits_mass_thres / mass;
+    double pms = b.f64[C_MASS_SCALING][ps];
+    double percent_fl = (mass * ms) / (b.f64[C_MASS_OF_FL_BITS][ps] * pms);
+    mob = (percent_fl * b.f64[C_MASS_OF_FL_BERGY_BITS][ps] * pms) / ms;
+    b.f64[C_MASS_OF_FL_BERGY_BITS][ps] = (1 - percent_fl) * b.f64[C_MASS_OF_FL_BERGY_BITS][ps];
+    b.f64[C_MASS_OF_FL_BITS][ps] = b.f64[C_MASS_OF_FL_BITS][ps] - k * p.new_berg_from_fl_bits_mass_thres / pms;
+  } else {
+    len = l_b * 3.; wid = l_b; thk = b.f64[C_THICKNESS][ps];
+    mass = wid * len * thk * p.rho_bergs;
+    ms = b.f64[C_MASS_SCALING][ps] * k;
+  }
+  b.f64[C_LENGTH][s] = len; b.f64[C_WIDTH][s] = wid; b.f64[C_THICKNESS][s] = thk; b.f64[C_MASS][s] = mass;
+  b.f64[C_MASS_SCALING][s] = ms; b.f64[C_MASS_OF_BITS][s] = mob;
+  b.f64[C_START_LON][s] = b.f64[C_LON][ps]; b.f64[C_START_LAT][s] = b.f64[C_LAT][ps];
+  b.f64[C_START_DAY][s] = p.current_yearday;
+  b.f64[C_MASS_OF_FL_BITS][s] = 0.; b.f64[C_MASS_OF_FL_BERGY_BITS][s] = 0.;
+  b.f64[C_FL_K][s] = -1.0;
+  b.start_year[s] = p.current_year;
+  int i = b.ine[ps], j = b.jne[ps];
+  b.ine[s] = i; b.jne[s] = j;
+  int c = gidx(g, i, j);
+  int32_t counter = g.iceberg_counter_grd[c] + 1;            // generate_id F:4165-4179, the parent's cell
+  g.iceberg_counter_grd[c] = counter;
+  b.id[s] = (int64_t)counter * ((int64_t)1 << 32) + (int64_t)(i + g.gni * (j - 1));
+  b.halo_code[s] = 0;
+  b.flags[s] = (uint8_t)(BF_ALIVE | (b.flags[ps] & BF_STATIC));
+  for (int q = 0; q < b.max_bonds; q++) { b.bond_other_id[(long long)q * b.capacity + s] = 0; b.bond_other_slot[(long long)q * b.capacity + s] = -1; }
+  return (long long)s;
+}
+
+__global__ void k_footloose(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
+                            const __grid_constant__ DevParams p, const __grid_constant__ FlConsts fc, const CellTable ct,
+                            DevCounters* __restrict__ cnt, int fl_style_fl_bits, double mass_thres) {
+  int ni = g.iec - g.isc + 1, nj = g.jec - g.jsc + 1;
+  long long kk = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (kk >= (long long)ni * nj) return;
+  int grdi = g.isc + (int)(kk % ni), grdj = g.jsc + (int)(kk / ni);
+  int cell = gidx(g, grdi, grdj);
+  int n = ct.count[cell], s0 = ct.start[cell];
+  double l_b = 0., c = 0.;
+  unsigned long long ncalved = 0;
+  double area = g.area[cell];
+  for (int q = 0; q < n; q++) {
+    long long s = s0 + q;
+    uint8_t f = b.flags[s];
+    if (!(f & BF_ALIVE) || (f & (BF_HALO | BF_LEAVER))) continue;
+    double fl_k = b.f64[C_FL_K][s];
+    double ms = b.f64[C_MASS_SCALING][s];
+    if (!((f & BF_STATIC) || fl_k < 0)) {
+      double T = b.f64[C_THICKNESS][s], W = b.f64[C_WIDTH][s], L = b.f64[C_LENGTH][s];
+      double N_bonds = 0;
+      for (int k = 0; k < b.max_bonds; k++) if (b.bond_other_id[(long long)k * b.capacity + s] != 0) N_bonds += 1.0;
+      if (N_bonds > 0) { atomicOr(&cnt->error_flags, 1024u); return; }      // 'Bonded footloose calving not yet fully implemented!' I:2567
+      double l_w = pow(fc.lw_c * fc.B_c * pow(T, 3.), 0.25);
+      l_b = fc.l_c * l_w;
+      double l_b3 = 3 * l_b, Lmin, Wmin, max_k, k, foot_area;
+      c = ceil((L - l_b3) / l_b3); Lmin = L - c * l_b3;
+      c = ceil((W - l_b3) / l_b3); Wmin = W - c * l_b3;
+      max_k = fmax(floor((L * W - Lmin * Wmin) / (l_b3 * l_b)), 0.);
+      if (max_k == 0) k = 0;
+      else {
+        double foot_l = fc.lfootparam * T / l_w;
+        foot_area = foot_l * l_b3;
+        k = floor(fl_k / foot_area);
+        if (k > max_k) k = max_k;
+        fl_k = fl_k - k * foot_area;
+        b.f64[C_FL_K][s] = fl_k;
+      }
+      if (k > 0) {
+        double ds, Ln, Wn;
+        if (c > 0) {
+          ds = 0.5 * ((L + W) - sqrt(pow(L + W, 2.) - 4. * (l_b3 * l_b * k)));
+          Ln = L - ds; Wn = W - ds;
+          if (Wn < Wmin) { Ln = Ln * (1 - (Wmin - Wn) / Wmin); Wn = Wmin; }
+        } else {
+          ds = k * 3. * pow(l_b, 2.) / W;
+          Ln = L - ds; Wn = W;
+        }
+        double dA = L * W - Ln * Wn;
+        if (!fl_style_fl_bits) {
+          fl_new_child(g, b, p, cnt, s, k, l_b, false);
+          ncalved++;
+        } else {
+          double dM_fl_bits = p.rho_bergs * T * dA;
+          b.f64[C_MASS_OF_FL_BITS][s] = b.f64[C_MASS_OF_FL_BITS][s] + dM_fl_bits;
+          if (area != 0.) g.fl_bits_src[cell] = g.fl_bits_src[cell] + dM_fl_bits / (p.dt * area) * ms;
+        }
+        if (Ln <= 0 || Wn <= 0) {
+          atomicOr(&cnt->error_flags, 2048u);       // 'non-edge element has fully calved from footloose mechanism' I:2648
+          return;
+        }
+        if (p.allow_bergs_to_roll) rolling(p, T, Wn, Ln);
+        b.f64[C_THICKNESS][s] = T; b.f64[C_WIDTH][s] = Wn; b.f64[C_LENGTH][s] = Ln;
+        b.f64[C_MASS][s] = Ln * Wn * T * p.rho_bergs;
+      }
+    }
+    if (b.f64[C_MASS_OF_FL_BITS][s] * ms > mass_thres) {
+      double k = floor(b.f64[C_MASS_OF_FL_BITS][s] * ms / mass_thres);
+      fl_new_child(g, b, p, cnt, s, k, l_b, true);
+      ncalved++;
+      if (area != 0.) g.fl_bits_src[cell] = g.fl_bits_src[cell] - k * mass_thres / (p.dt * area);
+    }
+  }
+  if (ncalved) atomicAdd(&cnt->nbergs_calved_fl, ncalved);
+}
+
+// adjust_fl_berg_interactivity I:2765-2841: a child (fl_k = -1) becomes interactive (-2) once no
+// other berg is within contact range
+__global__ void k_fl_interactivity(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
+                                   const __grid_constant__ DevParams p, const CellTable ct, long long n_slots) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots || !(b.flags[s] & BF_ALIVE) || b.f64[C_FL_K][s] != -1.) return;
+  int nc_x = p.contact_cells_lon, nc_y = p.contact_cells_lat;
+  bool radial = (nc_x == 1 && nc_y == 1);
+  double rdenom = p.hexagonal_icebergs ? 1. / (2. * sqrt(3.)) : (p.iceberg_bonds_on ? 1. / 4. : 1. / p.pi);
+  double crit_dist = p.contact_distance * p.contact_distance;
+  double lat1 = b.f64[C_LAT][s], lon1 = b.f64[C_LON][s];
+  double R1 = radial ? sqrt(b.f64[C_LENGTH][s] * b.f64[C_WIDTH][s] * rdenom) : 0.;
+  int gi = b.ine[s], gj = b.jne[s];
+  bool contact = false;
+  for (int j2 = max(gj - nc_y, g.jsd + 1); j2 <= min(gj + nc_y, g.jed) && !contact; j2++)
+    for (int i2 = max(gi - nc_x, g.isd + 1); i2 <= min(gi + nc_x, g.ied) && !contact; i2++) {
+      int c = gidx(g, i2, j2);
+      int n = ct.count[c], o0 = ct.start[c];
+      for (int k = 0; k < n; k++) {
+        long long o = o0 + k;
+        if (b.id[o] == b.id[s]) continue;
+        double lat2 = b.f64[C_LAT][o], lon2 = b.f64[C_LON][o], dlon = lon2 - lon1, dlat = lat2 - lat1, r_dist;
+        if (radial) {
+          double R2 = sqrt(b.f64[C_LENGTH][o] * b.f64[C_WIDTH][o] * rdenom);
+          crit_dist = pow(fmax(R1 + R2, p.contact_distance), 2.);
+        }
+        if (p.grid_is_latlon) {
+          double lat_ref = 0.5 * (lat1 + lat2);
+          double dx_dlon = p.pi_180 * p.Rearth * cos(lat_ref * p.pi_180), dy_dlat = p.pi_180 * p.Rearth;
+          r_dist = pow(dlon * dx_dlon, 2.) + pow(dlat * dy_dlat, 2.);
+        } else r_dist = dlon * dlon + dlat * dlat;
+        if (r_dist < crit_dist) { contact = true; break; }
+      }
+    }
+  if (!contact) b.f64[C_FL_K][s] = -2.;
+}
+
+}  // namespace kid

@@ -343,7 +343,7 @@ __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, c
     else atomicOr(&cnt->error_flags, (unsigned)KID_DEVERR_CAPACITY);
   }
   else if (route == 2) { b.flags[s] = 0; }
-  else {
+  else if (!FOOTLOOSE) {      // (with footloose on, thermodynamics follows footloose_calving: I:5455, I:5497)
     // ---- thermodynamics I:2844-3300 at the new position
     int outcome = thermo_slot<FOOTLOOSE, LEAN>(g, b, p, s, flags, i, j, xi, yj, uvel, vvel, M, T, W, L,
                                          b.f64[C_MASS_SCALING][s], b.f64[C_MASS_OF_BITS][s], b.f64[C_HEAT_DENSITY][s],
@@ -559,9 +559,24 @@ __global__ void k_rank(const __grid_constant__ DevGrid g, const uint8_t* __restr
   perm[pos] = (int32_t)s;
 }
 
-// makes the in-cell order deterministic and stable: ascending old slot
-__global__ void k_cell_order(const int32_t* __restrict__ cell_start, const int32_t* __restrict__ cell_count,
-                             long long ncell, int32_t* __restrict__ perm) {
+// the reference's list key, inorder() F:4318-4358: (start_year, start_day, start_mass, start_lon,
+// start_lat) ascending; equal keys keep their previous order
+__device__ __forceinline__ bool key_before(const DevBergs& b, int32_t x, int32_t y) {
+  int32_t ya = b.start_year[x], yb = b.start_year[y];
+  if (ya != yb) return ya < yb;
+  const int cols[4] = {C_START_DAY, C_START_MASS, C_START_LON, C_START_LAT};
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    double va = b.f64[cols[q]][x], vb = b.f64[cols[q]][y];
+    if (va != vb) return va < vb;
+  }
+  return x < y;
+}
+
+// makes the in-cell order deterministic and stable: ascending old slot, or (keyed) the order of the
+// reference's per-cell lists -- needed where that order decides an integer (ids of footloose children)
+__global__ void k_cell_order(const __grid_constant__ DevBergs b, const int32_t* __restrict__ cell_start,
+                             const int32_t* __restrict__ cell_count, long long ncell, int32_t* __restrict__ perm, int keyed) {
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncell) return;
   int32_t n = cell_count[c];
@@ -570,7 +585,8 @@ __global__ void k_cell_order(const int32_t* __restrict__ cell_start, const int32
   for (int32_t k = 1; k < n; k++) {
     int32_t v = a[k];
     int32_t m = k - 1;
-    while (m >= 0 && a[m] > v) { a[m + 1] = a[m]; m--; }
+    if (keyed) { while (m >= 0 && key_before(b, v, a[m])) { a[m + 1] = a[m]; m--; } }
+    else { while (m >= 0 && a[m] > v) { a[m + 1] = a[m]; m--; } }
     a[m + 1] = v;
   }
 }

@@ -241,3 +241,41 @@ def collision_params(default_params, **over):
               length_for_manually_initialize_bonds=800.0, use_roundoff_fix=1, old_bug_bilin=0, tau_is_velocity=0)
     kw.update(over)
     return default_params(**kw)
+
+
+def footloose_bergs(grdres=5000.0):
+    """tests/footloose_tests/makeberg/makeberg.py:245-274: two elements side by side at y = 10000.1."""
+    radius = (np.sqrt(3.0) / 2.0) * (0.45 * grdres)
+    area = (3.0 * np.sqrt(3.0) / 2.0) * ((4.0 / 3.0) * radius ** 2)
+    w = np.sqrt(area)
+    x = np.array([10000.1 - radius, 10000.1 + radius])
+    y = np.array([10000.1, 10000.1])
+    z = np.zeros(2)
+    m = np.full(2, 300.0 * 850.0 * area)
+    return dict(lon=x, lat=y, uvel=z.copy(), vvel=z.copy(), mass=m, thickness=np.full(2, 300.0), width=np.full(2, w),
+                length=np.full(2, w), axn=z.copy(), ayn=z.copy(), bxn=z.copy(), byn=z.copy(), start_lon=x.copy(),
+                start_lat=y.copy(), start_day=z.copy(), start_mass=m.copy(), mass_scaling=np.ones(2), mass_of_bits=z.copy(),
+                heat_density=z.copy(), start_year=np.zeros(2, dtype=np.int32))
+
+
+def footloose_params(default_params, **over):
+    """&icebergs_nml of tests/footloose_tests/input.nml (values that reach the hot path); the child
+    displacement needs the FMS random stream and is off here."""
+    kw = dict(halo=3, Lx=20000.0, grid_is_latlon=0, grid_is_regular=1, rho_bergs=850.0, spring_coef=1.0e-5,
+              bergy_bit_erosion_fraction=1.0, use_operator_splitting=1, coastal_drift=0.0, runge_not_verlet=0,
+              melt_cutoff=10.0, apply_thickness_cutoff_to_gridded_melt=1, apply_thickness_cutoff_to_bergs_melt=1,
+              allow_bergs_to_roll=1, use_updated_rolling_scheme=1, tip_parameter=0.0, set_melt_rates_to_zero=0,
+              iceberg_bonds_on=0, interactive_icebergs_on=0, use_new_predictive_corrective=1, passive_mode=1,
+              old_bug_bilin=0, use_roundoff_fix=1, footloose=1, displace_fl_bergs=0, fl_style_fl_bits=1,
+              fl_youngs=1.0e8, fl_strength=250.0, new_berg_from_fl_bits_mass_thres=3.0e11, tau_is_velocity=0)
+    kw.update(over)
+    return default_params(**kw)
+
+
+def footloose_forcing(grid, ibuo=1.0, ibvo=0.1, ibua=-1.0, sst=-0.5):
+    """driver forcing with fl_test=.true.: vo changes sign east of x = 10 km (D:309-311)."""
+    f = grid.forcing(ibuo=ibuo, ibvo=ibvo, sst=sst, collision_test=False)
+    i1, _ = grid._ij(1)
+    f["vo"] = np.ascontiguousarray(np.where(grid.res * i1 > 10000.0, -ibvo, ibvo), dtype=np.float64)
+    f["tauxa"] = np.full_like(f["tauxa"], ibua)
+    return f

@@ -129,3 +129,26 @@ def test_calving_tables_F787():
     t = KNOWN["calving_tables"]
     for name in ("initial_mass_s", "distribution_s", "mass_scaling_s", "initial_thickness_s"):
         assert list(getattr(p, name)) == t[name]
+
+
+def test_footloose_test_ends_with_12_bergs():
+    """Known answer of the reference's footloose test (tests/footloose_tests/input.nml:1, restart
+    checksum line '#=12'): two 3.6 km elements, 192 h of 10 s steps, fl_style='fl_bits' -- the two
+    parents plus ten bergs made from footloose bits.  The child displacement (FMS random stream) is off
+    here; it moves children, it does not change how many there are."""
+    from icebergs_b200 import api
+    from icebergs_b200 import synthetic as S
+    g = S.CartesianGrid()
+    dom = api.Domain.single(20, 20, halo=3, cyclic_x=True)
+    o = O.Oracle(20, 20, 10.0, (1, 0.0), params=S.footloose_params(api.default_params), domain=dom, **g.init_args())
+    o.set_bergs(**S.footloose_bergs())
+    f = S.footloose_forcing(g)
+    c, h = f["calving"].copy(), f["calving_hflx"].copy()
+    o.run((1, 0.0), c, f["uo"], f["vo"], f["ui"], f["vi"], f["tauxa"], f["tauya"], f["ssh"], f["sst"], h, f["cn"], f["hi"])
+    nsteps, done = int(192 * 3600 / 10), 1
+    while done < nsteps:
+        n = min(8640, nsteps - done)
+        o.step_again(n, 1, done * 10.0 / 86400.0)
+        done += n
+    assert o.count_bergs() == KNOWN["restart_counts"]["footloose"] == 12
+    assert o.counters()["nbergs_calved_fl"] == 10
