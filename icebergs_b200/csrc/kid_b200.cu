@@ -139,6 +139,8 @@ extern "C" void kid_default_params(KidParams* p) {
   p->displace_fl_bergs = 1; p->fl_bits_erosion_to_bergy_bits = 1;
   p->fl_youngs = 1.e7; p->fl_strength = 250.; p->new_berg_from_fl_bits_mass_thres = 1.e12;
   p->LoW_ratio = 1.5;
+  p->use_three_equation_model = 1; p->const_gamma = 1; p->gamma_t_3eq = 0.022; p->ustar_icebergs_bg = 0.001;
+  p->utide_icebergs = 0.; p->cdrag_icebergs = 1.5e-3;
   const double im[10] = {8.8e7, 4.1e8, 3.3e9, 1.8e10, 3.8e10, 7.5e10, 1.2e11, 2.2e11, 3.9e11, 7.4e11};
   const double ds[10] = {0.24, 0.12, 0.15, 0.18, 0.12, 0.07, 0.03, 0.03, 0.03, 0.02};
   const double sc[10] = {2000, 200, 50, 20, 10, 5, 2, 1, 1, 1};
@@ -235,6 +237,12 @@ static void fill_dev_params(kid_t* h) {
   q.tip_parameter = p.tip_parameter; q.melt_cutoff = p.melt_cutoff;
   q.spring_coef = p.spring_coef; q.contact_spring_coef = p.contact_spring_coef; q.contact_distance = p.contact_distance;
   q.radial_damping_coef = p.radial_damping_coef; q.tangental_damping_coef = p.tangental_damping_coef;
+  q.use_mixed_melting = p.use_mixed_melting; q.melt_icebergs_as_ice_shelf = p.melt_icebergs_as_ice_shelf;
+  q.use_three_equation_model = p.use_three_equation_model; q.const_gamma = p.const_gamma;
+  q.use_mixed_layer_salinity_for_thermo = p.use_mixed_layer_salinity_for_thermo;
+  q.apply_thickness_cutoff_to_bergs_melt = p.apply_thickness_cutoff_to_bergs_melt;
+  q.gamma_t_3eq = p.gamma_t_3eq; q.ustar_icebergs_bg = p.ustar_icebergs_bg; q.utide_icebergs = p.utide_icebergs;
+  q.cdrag_icebergs = p.cdrag_icebergs; q.omega = p.omega;
   q.fl_youngs = p.fl_youngs; q.new_berg_from_fl_bits_mass_thres = p.new_berg_from_fl_bits_mass_thres;
   q.grid_is_latlon = p.grid_is_latlon; q.grid_is_regular = p.grid_is_regular; q.old_bug_bilin = p.old_bug_bilin;
   q.use_roundoff_fix = p.use_roundoff_fix; q.use_f_plane = p.use_f_plane;
@@ -506,7 +514,6 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   const char* unsupported = nullptr;
   if (pin->runge_not_verlet) unsupported = "Runge_not_Verlet=.true. (RK4) is not implemented: set runge_not_verlet=0";
   else if (pin->tidal_drift > 0.) unsupported = "tidal_drift>0 needs the FMS random number stream";
-  else if (pin->use_mixed_melting || pin->melt_icebergs_as_ice_shelf) unsupported = "ice-shelf melt (find_basal_melt) is not implemented";
   else if (pin->add_iceberg_thickness_to_ssh) unsupported = "add_iceberg_thickness_to_SSH is not implemented";
   else if (pin->mts || pin->dem) unsupported = "MTS/DEM stepping is not implemented in this build";
   else if ((pin->interactive_icebergs_on || pin->iceberg_bonds_on) &&
@@ -1430,7 +1437,8 @@ static bool lean_config(const kid_t* h) {
   return p.grid_is_latlon && !p.use_f_plane && h->no_rotation && p.coastal_drift == 0. && p.speed_limit == 0. &&
          p.cdrag_grounding == 0. && !p.override_iceberg_velocities && p.use_operator_splitting && !p.set_melt_rates_to_zero &&
          !p.footloose && !p.melt_diagnostics && p.allow_bergs_to_roll && !p.use_updated_rolling_scheme && p.tip_parameter < 999. &&
-         !p.iceberg_melt_without_decay && !p.only_interactive_forces && !getenv("KID_NO_LEAN");
+         !p.iceberg_melt_without_decay && !p.only_interactive_forces && !p.use_mixed_melting && !p.melt_icebergs_as_ice_shelf &&
+         !getenv("KID_NO_LEAN");
 }
 
 template <bool FL, bool DG>

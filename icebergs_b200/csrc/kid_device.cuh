@@ -43,6 +43,7 @@ struct DevParams {
   double bergy_bit_erosion_fraction, sicn_shift, tip_parameter, melt_cutoff;
   double spring_coef, contact_spring_coef, contact_distance, radial_damping_coef, tangental_damping_coef;
   double fl_youngs, new_berg_from_fl_bits_mass_thres;
+  double gamma_t_3eq, ustar_icebergs_bg, utide_icebergs, cdrag_icebergs, omega;   // find_basal_melt I:3492
   double current_yearday;
   // host-precomputed constants of the step (same libm as the CPU path)
   double rdt;            // 1/dt
@@ -63,6 +64,8 @@ struct DevParams {
   int32_t contact_cells_lon, contact_cells_lat, max_bonds;
   int32_t current_year;
   int32_t passive_mode;
+  int32_t use_mixed_melting, melt_icebergs_as_ice_shelf, use_three_equation_model, const_gamma;
+  int32_t use_mixed_layer_salinity_for_thermo, apply_thickness_cutoff_to_bergs_melt;
   int32_t no_rotation;   // cos_rot == 1 and sin_rot == 0 on the whole data domain: rotate() (I:4953) is the identity
 };
 

@@ -210,12 +210,16 @@ __device__ __forceinline__ int thermo_slot(const DevGrid& g, const DevBergs& b, 
   }
   st.start_day = 0.; st.start_year = 0;
   double N_bonds = 0.;
-  if (PF(allow_bergs_to_roll, 1)) {
+  ShelfIn sh = {0., 0., 0.};
+  if (!LEAN && (p.melt_icebergs_as_ice_shelf || p.use_mixed_melting)) {
+    sh.lat = b.f64[C_LAT][s]; sh.sss = g.cell[cidx].sss; sh.ocean_depth = g.ocean_depth[cidx];
+  }
+  if (PF(allow_bergs_to_roll, 1) || (!LEAN && p.use_mixed_melting)) {
     // N_bonds: I:2928-2944 (this%n_bonds = the length of the bond list, assign_n_bonds F:4617)
     for (int k = 0; k < b.max_bonds; k++) if (b.bond_other_id[(long long)k * b.capacity + s] != 0) N_bonds += 1.0;
     if (flags & BF_STATIC) N_bonds = p.hexagonal_icebergs ? 6.0 : 4.0;
   }
-  int outcome = thermo_berg<LEAN>(p, e, uvel, vvel, N_bonds, st, sc.fx);
+  int outcome = thermo_berg<LEAN>(p, e, uvel, vvel, N_bonds, st, sc.fx, sh);
   sc.key = (long long)cidx;
   b.f64[C_MASS][s] = st.mass;
   b.f64[C_THICKNESS][s] = st.thickness;

@@ -472,6 +472,91 @@ __device__ __forceinline__ void rolling(const DevParams& p, double& Tn, double& 
   }
 }
 
+// find_basal_melt I:3492-3826 (+ calculate_TFreeze I:3790, calculate_density I:3805): ice-shelf style
+// two-/three-equation basal melt.  Out of line: only the use_mixed_melting / melt_icebergs_as_ice_shelf
+// namelists reach it.
+__device__ __noinline__ double find_basal_melt(const DevParams& p, double dvo, double lat, double salt, double temp,
+                                               double thickness) {
+  const double VK = 0.40, ZETA_N = 0.052, RC = 0.20, c2_3 = 2.0 / 3.0;
+  const double dR0_dT = -0.038357, dR0_dS = 0.805876, RHO_T0_S0 = 999.910681, Salin_Ice = 0.0;
+  const double kd_molec_salt = 8.02e-10, kd_molec_temp = 1.41e-7, kv_molec = 1.95e-6;
+  const double Cp_ml = 3974.0, LF = 3.335e5, p_atm = 101325;
+  const double dTFr_dp = -7.53E-08, dTFr_dS = -0.0573, TFr_S0_P0 = 0.0832;
+  double density_ice = p.rho_bergs, Rho0 = KID_RHO_SEAWATER, Hml = 10.;
+  double p_int = p_atm + (KID_GRAVITY * thickness * density_ice);
+  double Rhoml = RHO_T0_S0 + dR0_dT * temp + dR0_dS * salt;
+  double I_ZETA_N = 1.0 / ZETA_N, I_LF = 1.0 / LF;
+  double SC = kv_molec / kd_molec_salt, PR = kv_molec / kd_molec_temp, I_VK = 1.0 / VK;
+  double RhoCp = Rho0 * Cp_ml;
+  double Gam_mol_t = 12.5 * pow(PR, c2_3) - 6, Gam_mol_s = 12.5 * pow(SC, c2_3) - 6;
+  double ustar = sqrt(p.cdrag_icebergs * (dvo * dvo + p.utide_icebergs * p.utide_icebergs));
+  double ustar_h = fmax(p.ustar_icebergs_bg, ustar);
+  double pi_180 = p.pi / 180., f_cori;
+  if (p.grid_is_latlon && !p.use_f_plane) f_cori = (2. * p.omega) * sin(pi_180 * lat);
+  else f_cori = (2. * p.omega) * sin(pi_180 * p.lat_ref);
+  double absf = fabs(f_cori), hBL_neut;
+  if ((absf * Hml <= VK * ustar_h) || (absf == 0.)) hBL_neut = Hml; else hBL_neut = (VK * ustar_h) / absf;
+  double hBL_neut_h_molec = ZETA_N * ((hBL_neut * ustar_h) / (5.0 * kv_molec));
+  double ln_neut = 0.0; if (hBL_neut_h_molec > 1.0) ln_neut = log(hBL_neut_h_molec);
+  double tfreeze, Gam_turb, I_Gam_T = 0., I_Gam_S = 0., wT_flux, t_flux, lprec = 0.;
+  bool out_of_bounds = false;
+  if (p.use_three_equation_model) {
+    double Sbdry = salt, Sb_max = 0., Sb_min = 0.;
+    bool Sb_max_set = false, Sb_min_set = false;
+    double dB_dS = (KID_GRAVITY / Rhoml) * dR0_dS, dB_dT = (KID_GRAVITY / Rhoml) * dR0_dT;
+    for (int it1 = 1; it1 <= 20; it1++) {
+      tfreeze = (TFr_S0_P0 + dTFr_dS * Sbdry) + dTFr_dp * p_int;
+      double dT_ustar = (temp - tfreeze) * ustar_h, dS_ustar = (salt - Sbdry) * ustar_h;
+      if (p.const_gamma) { I_Gam_T = p.gamma_t_3eq; I_Gam_S = p.gamma_t_3eq / 35.; }
+      else {
+        Gam_turb = I_VK * (ln_neut + (0.5 * I_ZETA_N - 1.0));
+        I_Gam_T = 1.0 / (Gam_mol_t + Gam_turb); I_Gam_S = 1.0 / (Gam_mol_s + Gam_turb);
+      }
+      wT_flux = dT_ustar * I_Gam_T;
+      double wB_flux = dB_dS * (dS_ustar * I_Gam_S) + dB_dT * wT_flux;
+      if (wB_flux > 0.0) {
+        double n_star_term = (ZETA_N / RC) * (hBL_neut * VK) / pow(ustar_h, 3.);
+        // the reference's inner loop (it3 = 1,30) never feeds its Newton estimate back into wB_flux:
+        // every pass recomputes the same numbers, so one pass gives its result
+        double I_n_star = sqrt(1.0 + n_star_term * wB_flux);
+        if (hBL_neut_h_molec > I_n_star * I_n_star) Gam_turb = I_VK * ((ln_neut - 2.0 * log(I_n_star)) + (0.5 * I_ZETA_N * I_n_star - 1.0));
+        else Gam_turb = I_VK * (0.5 * I_ZETA_N * I_n_star - 1.0);
+        if (p.const_gamma) { I_Gam_T = p.gamma_t_3eq; I_Gam_S = p.gamma_t_3eq / 35.; }
+        else { I_Gam_T = 1.0 / (Gam_mol_t + Gam_turb); I_Gam_S = 1.0 / (Gam_mol_s + Gam_turb); }
+        wT_flux = dT_ustar * I_Gam_T;
+      }
+      t_flux = RhoCp * wT_flux;
+      double exch_vel_s = ustar_h * I_Gam_S;
+      lprec = I_LF * t_flux;
+      double mass_exch = exch_vel_s * Rho0;
+      double Sbdry_it = (salt * mass_exch + Salin_Ice * lprec) / (mass_exch + lprec);
+      double dS_it = Sbdry_it - Sbdry;
+      if (fabs(dS_it) < 1e-4 * (0.5 * (salt + Sbdry + 1.e-10))) break;
+      if (dS_it < 0.0) {
+        if (Sb_max_set && (Sbdry > Sb_max)) { out_of_bounds = true; break; }
+        Sb_max = Sbdry; Sb_max_set = true;
+      } else {
+        if (Sb_min_set && (Sbdry < Sb_min)) { out_of_bounds = true; break; }
+        Sb_min = Sbdry; Sb_min_set = true;
+      }
+      Sbdry = Sbdry_it;                                  // I:3758 overwrites the false-position estimate
+    }
+  }
+  if ((!p.use_three_equation_model) || out_of_bounds) {
+    tfreeze = (TFr_S0_P0 + dTFr_dS * salt) + dTFr_dp * p_int;
+    Gam_turb = I_VK * (ln_neut + (0.5 * I_ZETA_N - 1.0));
+    I_Gam_T = 1.0 / (Gam_mol_t + Gam_turb);
+    double exch_vel_t = ustar_h * I_Gam_T;
+    wT_flux = exch_vel_t * (temp - tfreeze);
+    t_flux = RhoCp * wT_flux;
+    lprec = I_LF * t_flux;
+  }
+  return lprec / density_ice;
+}
+
+// what the ice-shelf melt options additionally need of the berg and its cell (I:2945-2956)
+struct ShelfIn { double lat, sss, ocean_depth; };
+
 // per-berg state thermodynamics reads and writes
 struct ThermoState {
   double mass, thickness, width, length, mass_scaling, mass_of_bits, mass_of_fl_bits, mass_of_fl_bergy_bits;
@@ -562,7 +647,7 @@ __device__ __forceinline__ double pow_08(double x) { return (x > 1.e-30) ? x * p
 // cell is not dry), N_bonds per I:2928-2944.
 template <bool LEAN = false>
 __device__ __forceinline__ int thermo_berg(const DevParams& p, const EnvThermo& e, double uvel, double vvel,
-                                           double N_bonds, ThermoState& s, ThermoFlux& fx) {
+                                           double N_bonds, ThermoState& s, ThermoFlux& fx, const ShelfIn& sh) {
   const double perday = 1. / 86400.;
   double dt = p.dt;
   double SST = e.sst;
@@ -581,6 +666,20 @@ __device__ __forceinline__ int thermo_berg(const DevParams& p, const EnvThermo& 
   double Me = kmax(1. / 12. * (SST + 2.) * Ss * wave_ic, 0.) * perday;
   double Mv_fl = 0., Me_fl = 0.;
   if (s.mass_of_fl_bits > 0.) { Mv_fl = Mv; Me_fl = Me; }
+  if (!LEAN && (p.melt_icebergs_as_ice_shelf || p.use_mixed_melting)) {      // I:2945-2968
+    double SSS = p.use_mixed_layer_salinity_for_thermo ? sh.sss : 35.0;
+    double Ms = kmax(find_basal_melt(p, dvo, sh.lat, SSS, SST, T), 0.);
+    if ((p.melt_cutoff >= 0.) && p.apply_thickness_cutoff_to_bergs_melt) {
+      double Dn = (p.rho_bergs / KID_RHO_SEAWATER) * T;
+      if ((sh.ocean_depth - Dn) < p.melt_cutoff) Ms = 0.;
+    }
+    if (p.use_mixed_melting) {
+      double N_max = p.hexagonal_icebergs ? 6.0 : 4.0;
+      Me = ((N_max - N_bonds) / N_max) * (Mv + Me);
+      Mv = 0.0;
+      Mb = (((N_max - N_bonds) / N_max) * (Mb)) + (N_bonds / N_max) * Ms;
+    } else { Mv = 0.0; Me = 0.0; Mb = Ms; }
+  }
   if (PF(set_melt_rates_to_zero, 0)) { Mv = 0.0; Mb = 0.0; Me = 0.0; }
   double Tn, Mnew1, Mnew2, Mnew, dMb, dMv, dMe, dM, Ln1 = 0, Wn1 = 0, Ln, Wn;
   if (PF(use_operator_splitting, 1)) {

@@ -171,8 +171,8 @@ typedef struct KidParams {
   int32_t allow_bergs_to_roll;    /* F:752 (T) */
   int32_t use_updated_rolling_scheme; /* F:738 (F) */
   int32_t iceberg_melt_without_decay; /* F:744 */
-  int32_t use_mixed_melting;      /* F:734 (unsupported: second tier, must be 0) */
-  int32_t melt_icebergs_as_ice_shelf; /* F:743 (unsupported: second tier, must be 0) */
+  int32_t use_mixed_melting;      /* F:734 */
+  int32_t melt_icebergs_as_ice_shelf; /* F:743 */
   int32_t apply_thickness_cutoff_to_bergs_melt;   /* F:737 */
   int32_t apply_thickness_cutoff_to_gridded_melt; /* F:736 */
   int32_t melt_diagnostics;       /* 1 => fill melt_buoy/eros/conv(+_fl), fl_parent/child_melt
@@ -196,6 +196,16 @@ typedef struct KidParams {
   double mass_scaling_s[KID_NCLASSES], initial_thickness_s[KID_NCLASSES];
   double initial_mass_n[KID_NCLASSES], distribution_n[KID_NCLASSES];
   double mass_scaling_n[KID_NCLASSES], initial_thickness_n[KID_NCLASSES];
+  /* ice-shelf style basal melt, find_basal_melt I:3492-3826 (used with use_mixed_melting /
+   * melt_icebergs_as_ice_shelf) */
+  int32_t use_three_equation_model;            /* F:742 (T) */
+  int32_t const_gamma;                         /* F:719 (T) */
+  int32_t use_mixed_layer_salinity_for_thermo; /* F:740 (F) */
+  int32_t pad0_;
+  double gamma_t_3eq;                          /* F:717 (0.022) */
+  double ustar_icebergs_bg;                    /* F:715 (0.001) */
+  double utide_icebergs;                       /* F:714 (0.) */
+  double cdrag_icebergs;                       /* F:716 (1.5e-3) */
 } KidParams;
 
 /* ----------------------------------------------------------------------------

@@ -1192,6 +1192,105 @@ static void evolve_icebergs(Oracle* o) {
   }
 }
 
+/* ------------------------------------------- find_basal_melt I:3492-3826 */
+static double calculate_TFreeze(double S, double pres) {          /* I:3790-3802 */
+  const double dTFr_dp = -7.53E-08, dTFr_dS = -0.0573, TFr_S0_P0 = 0.0832;
+  return (TFr_S0_P0 + dTFr_dS * S) + dTFr_dp * pres;
+}
+static double find_basal_melt(const Oracle* o, double dvo, double lat, double salt, double temp,
+                              int Use_three_equation_model, double thickness) {
+  const KidParams* p = &o->p;
+  const double VK = 0.40, ZETA_N = 0.052, RC = 0.20, c2_3 = 2.0 / 3.0;
+  const double dR0_dT = -0.038357, dR0_dS = 0.805876, RHO_T0_S0 = 999.910681, Salin_Ice = 0.0;
+  const double kd_molec_salt = 8.02e-10, kd_molec_temp = 1.41e-7, kv_molec = 1.95e-6;
+  const double Cp_ml = 3974.0, LF = 3.335e5, gamma_t = 0.0, p_atm = 101325;
+  double density_ice = p->rho_bergs, Rho0 = RHO_SEAWATER, Hml = 10.;
+  double p_int = p_atm + (GRAVITY * thickness * density_ice);
+  double Rhoml = RHO_T0_S0 + dR0_dT * temp + dR0_dS * salt;      /* calculate_density I:3805-3816 */
+  double I_ZETA_N = 1.0 / ZETA_N, I_LF = 1.0 / LF;
+  double SC = kv_molec / kd_molec_salt, PR = kv_molec / kd_molec_temp, I_VK = 1.0 / VK;
+  double RhoCp = Rho0 * Cp_ml;
+  double Gam_mol_t = 12.5 * pow(PR, c2_3) - 6, Gam_mol_s = 12.5 * pow(SC, c2_3) - 6;
+  double ustar = sqrt(p->cdrag_icebergs * (dvo * dvo + p->utide_icebergs * p->utide_icebergs));
+  double ustar_h = dmax(p->ustar_icebergs_bg, ustar);
+  double pi_180 = p->pi / 180., f_cori;
+  if (p->grid_is_latlon && !p->use_f_plane) f_cori = (2. * p->omega) * sin(pi_180 * lat);
+  else f_cori = (2. * p->omega) * sin(pi_180 * p->lat_ref);
+  double absf = fabs(f_cori), hBL_neut;
+  if ((absf * Hml <= VK * ustar_h) || (absf == 0.)) hBL_neut = Hml; else hBL_neut = (VK * ustar_h) / absf;
+  double hBL_neut_h_molec = ZETA_N * ((hBL_neut * ustar_h) / (5.0 * kv_molec));
+  double ln_neut = 0.0; if (hBL_neut_h_molec > 1.0) ln_neut = log(hBL_neut_h_molec);
+  double tfreeze, Gam_turb, I_Gam_T = 0., I_Gam_S = 0., wT_flux, t_flux, lprec = 0.;
+  int out_of_bounds = 0;
+  if (Use_three_equation_model) {
+    double Sbdry = salt, Sb_max = 0., Sb_min = 0., dS_min = 0., dS_max = 0.;
+    int Sb_max_set = 0, Sb_min_set = 0;
+    double dB_dS = (GRAVITY / Rhoml) * dR0_dS, dB_dT = (GRAVITY / Rhoml) * dR0_dT;
+    for (int it1 = 1; it1 <= 20; it1++) {
+      tfreeze = calculate_TFreeze(Sbdry, p_int);
+      double dT_ustar = (temp - tfreeze) * ustar_h, dS_ustar = (salt - Sbdry) * ustar_h;
+      if (p->const_gamma) { I_Gam_T = p->gamma_t_3eq; I_Gam_S = p->gamma_t_3eq / 35.; }
+      else {
+        Gam_turb = I_VK * (ln_neut + (0.5 * I_ZETA_N - 1.0));
+        I_Gam_T = 1.0 / (Gam_mol_t + Gam_turb); I_Gam_S = 1.0 / (Gam_mol_s + Gam_turb);
+      }
+      wT_flux = dT_ustar * I_Gam_T;
+      double wB_flux = dB_dS * (dS_ustar * I_Gam_S) + dB_dT * wT_flux;
+      if (wB_flux > 0.0) {
+        double n_star_term = (ZETA_N / RC) * (hBL_neut * VK) / pow(ustar_h, 3);
+        for (int it3 = 1; it3 <= 30; it3++) {
+          double I_n_star = sqrt(1.0 + n_star_term * wB_flux);
+          double dIns_dwB = 0.5 * n_star_term / I_n_star, dG_dwB;
+          if (hBL_neut_h_molec > I_n_star * I_n_star) {
+            Gam_turb = I_VK * ((ln_neut - 2.0 * log(I_n_star)) + (0.5 * I_ZETA_N * I_n_star - 1.0));
+            dG_dwB = I_VK * (-2.0 / I_n_star + (0.5 * I_ZETA_N)) * dIns_dwB;
+          } else {
+            Gam_turb = I_VK * (0.5 * I_ZETA_N * I_n_star - 1.0);
+            dG_dwB = I_VK * (0.5 * I_ZETA_N) * dIns_dwB;
+          }
+          if (p->const_gamma) { I_Gam_T = p->gamma_t_3eq; I_Gam_S = p->gamma_t_3eq / 35.; }
+          else { I_Gam_T = 1.0 / (Gam_mol_t + Gam_turb); I_Gam_S = 1.0 / (Gam_mol_s + Gam_turb); }
+          wT_flux = dT_ustar * I_Gam_T;
+          double wB_flux_new = dB_dS * (dS_ustar * I_Gam_S) + dB_dT * wT_flux;
+          double DwB = wB_flux_new - wB_flux;
+          if (fabs(wB_flux_new - wB_flux) < 1e-4 * (fabs(wB_flux_new) + fabs(wB_flux))) break;
+          double dDwB_dwB_in = -dG_dwB * (dB_dS * (dS_ustar * I_Gam_S * I_Gam_S) + dB_dT * (dT_ustar * I_Gam_T * I_Gam_T)) - 1.0;
+          wB_flux_new = wB_flux - DwB / dDwB_dwB_in;     /* (the reference never feeds this back into wB_flux) */
+          (void)wB_flux_new;
+        }
+      }
+      t_flux = RhoCp * wT_flux;
+      double exch_vel_s = ustar_h * I_Gam_S;
+      lprec = I_LF * t_flux;
+      double mass_exch = exch_vel_s * Rho0;
+      double Sbdry_it = (salt * mass_exch + Salin_Ice * lprec) / (mass_exch + lprec);
+      double dS_it = Sbdry_it - Sbdry;
+      if (fabs(dS_it) < 1e-4 * (0.5 * (salt + Sbdry + 1.e-10))) break;
+      if (dS_it < 0.0) {
+        if (Sb_max_set && (Sbdry > Sb_max)) { out_of_bounds = 1; break; }
+        Sb_max = Sbdry; dS_max = dS_it; Sb_max_set = 1;
+      } else {
+        if (Sb_min_set && (Sbdry < Sb_min)) { out_of_bounds = 1; break; }
+        Sb_min = Sbdry; dS_min = dS_it; Sb_min_set = 1;
+      }
+      if (Sb_min_set && Sb_max_set) Sbdry = Sb_min + (Sb_max - Sb_min) * (dS_min / (dS_min - dS_max));
+      else Sbdry = Sbdry_it;
+      Sbdry = Sbdry_it;                                  /* I:3758: the false-position estimate is overwritten */
+    }
+  }
+  if ((!Use_three_equation_model) || out_of_bounds) {
+    tfreeze = calculate_TFreeze(salt, p_int);
+    Gam_turb = I_VK * (ln_neut + (0.5 * I_ZETA_N - 1.0));
+    I_Gam_T = 1.0 / (Gam_mol_t + Gam_turb);
+    double exch_vel_t = ustar_h * I_Gam_T;
+    if (gamma_t > 0.0) exch_vel_t = gamma_t;
+    wT_flux = exch_vel_t * (temp - tfreeze);
+    t_flux = RhoCp * wT_flux;
+    lprec = I_LF * t_flux;
+  }
+  return lprec / density_ice;
+}
+
 /* --------------------------------------------------------- rolling I:3307 */
 static void swap_d(double* x, double* y) { double t = *x; *x = *y; *y = t; }
 void oracle_rolling(const KidParams* p, double* Tn, double* Wn, double* Ln) {
@@ -1288,7 +1387,21 @@ static void thermodynamics(Oracle* o) {
           if (p->iceberg_bonds_on) N_bonds = this_->n_bonds;
           if (this_->static_berg == 1) N_bonds = N_max;
         }
-        /* melt_icebergs_as_ice_shelf / use_mixed_melting (find_basal_melt I:3492): second tier, rejected at create */
+        if (p->melt_icebergs_as_ice_shelf || p->use_mixed_melting) {      /* I:2945-2968 */
+          double SSS = this_->sss;
+          if (!p->use_mixed_layer_salinity_for_thermo) SSS = 35.0;
+          double Ms = find_basal_melt(o, dvo, this_->lat, SSS, SST, p->use_three_equation_model, T);
+          Ms = dmax(Ms, 0.);
+          if ((p->melt_cutoff >= 0.) && p->apply_thickness_cutoff_to_bergs_melt) {
+            double Dn = (p->rho_bergs / RHO_SEAWATER) * this_->thickness;
+            if ((G(o, ocean_depth, i, j) - Dn) < p->melt_cutoff) Ms = 0.;
+          }
+          if (p->use_mixed_melting) {
+            Me = ((N_max - N_bonds) / N_max) * (Mv + Me);
+            Mv = 0.0;
+            Mb = (((N_max - N_bonds) / N_max) * (Mb)) + (N_bonds / N_max) * Ms;
+          } else { Mv = 0.0; Me = 0.0; Mb = Ms; }
+        }
         if (p->set_melt_rates_to_zero) { Mv = 0.0; Mb = 0.0; Me = 0.0; }
         double Tn, nVol, Mnew1 = 0, Mnew2 = 0, Mnew, dMb, dMv, dMe, dM, Ln1 = 0, Wn1 = 0, Ln, Wn;
         if (p->use_operator_splitting) {
@@ -1805,7 +1918,6 @@ Oracle* oracle_create(const KidParams* p, const KidDomain* dom, int32_t year, do
   o->list = (OBerg**)calloc(n2, sizeof(OBerg*));
   if (p->runge_not_verlet) o_fatal(o, "oracle: only Verlet (Runge_not_Verlet=.false.) is restated");
   if (p->tidal_drift > 0.) o_fatal(o, "oracle: tidal_drift needs the FMS random number stream (external)");
-  if (p->melt_icebergs_as_ice_shelf || p->use_mixed_melting) o_fatal(o, "oracle: ice-shelf melt (find_basal_melt) is second tier, not restated");
   if (p->add_iceberg_thickness_to_ssh) o_fatal(o, "oracle: add_iceberg_thickness_to_SSH needs spread_mass (next row)");
   int nic = d->iec - d->isc + 1, njc = d->jec - d->jsc + 1;
   /* F:1021-1056 */

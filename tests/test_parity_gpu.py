@@ -168,3 +168,27 @@ def test_full_size_properties():
     fm, area = b.grid_field(D.KID_FLD_FLOATING_MELT), b.grid_field(D.KID_FLD_AREA)
     assert abs(np.sum(fm * area) * case.dt - lost) / lost < 1e-9
     api.icebergs_end(b)
+
+
+@pytest.mark.parametrize("over", [
+    dict(melt_icebergs_as_ice_shelf=1),                                            # 3-equation, constant gamma (defaults)
+    dict(melt_icebergs_as_ice_shelf=1, const_gamma=0),                             # 3-equation, turbulent exchange
+    dict(melt_icebergs_as_ice_shelf=1, use_three_equation_model=0),                # 2-equation
+    dict(use_mixed_melting=1, const_gamma=0, use_mixed_layer_salinity_for_thermo=1, melt_cutoff=10.0,
+         apply_thickness_cutoff_to_bergs_melt=1),
+])
+def test_ice_shelf_style_basal_melt(over):
+    """find_basal_melt (I:3492-3826): the two-/three-equation melt of melt_icebergs_as_ice_shelf and
+    use_mixed_melting replaces / blends the basal melt rate."""
+    case = Case(96, 48, 6000, dt=86400.0, **over)
+    b, o = both(case)
+    warm = dict(sst=np.full_like(case.forcing["sst"], 1.5))
+    for step in range(3):
+        run_gpu(b, case, **warm)
+        run_oracle(o, case, **warm)
+        compare_state(b, o, f"ice-shelf melt {over} step {step}", rtol=1e-9)
+    for fid in FLUX_FIELDS:
+        assert grid_rel(b.grid_field(fid), o.grid_field(fid)) < 1e-9
+    m0 = case.bergs["mass"].sum()
+    assert b.get_bergs(["mass"])["mass"].sum() < 0.999 * m0       # the basal melt did act
+    api.icebergs_end(b)
