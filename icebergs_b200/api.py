@@ -207,6 +207,16 @@ class Icebergs:
         self._check(lib().kid_get_bonds(self.handle, C.byref(m), C.byref(c)))
         return {k: v[: m.value].copy() for k, v in keep.items()}
 
+    def stock_pe(self, index) -> float:
+        """icebergs_stock_pe, I:8102 (index = KID_ISTOCK_WATER or KID_ISTOCK_HEAT)."""
+        v = C.c_double(0.0)
+        self._check(lib().kid_stock(self.handle, int(index), C.byref(v)))
+        return v.value
+
+    def incr_mass(self, mass):
+        """icebergs_incr_mass, I:6046: mass (njc, nic) += spread berg mass (kg/m2)."""
+        self._check(lib().kid_incr_mass(self.handle, _ptr(mass)))
+
     def set_calving_state(self, stored_ice=None, stored_heat=None, iceberg_counter_grd=None):
         d = self.domain
         si = _f64(stored_ice, (D.KID_NCLASSES, d.njd, d.nid), "stored_ice")

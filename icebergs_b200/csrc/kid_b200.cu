@@ -17,6 +17,7 @@
 #include "kid_kernels.cuh"
 #include "kid_comm.cuh"
 #include "kid_interact.cuh"
+#include "kid_spread.cuh"
 
 using namespace kid;
 
@@ -83,6 +84,9 @@ struct kid_handle {
   int32_t *d_gcounts = nullptr, *d_goffsets = nullptr, *d_gcursor = nullptr;   // [9]
   int tables_valid = 0, bond_lengths_set = 0;                // cell_start/cell_count describe the current slot order
   void* spare_b8 = nullptr;            // spare column for the bond arrays (8 B entries)
+  SpreadFields sf;                     // mass / area / momentum on the ocean grid
+  SpreadParams sp;
+  double* out_stage3[3] = {nullptr, nullptr, nullptr};
   std::string err;
   bool fatal = false;
 };
@@ -141,6 +145,7 @@ extern "C" void kid_default_params(KidParams* p) {
   p->LoW_ratio = 1.5;
   p->use_three_equation_model = 1; p->const_gamma = 1; p->gamma_t_3eq = 0.022; p->ustar_icebergs_bg = 0.001;
   p->utide_icebergs = 0.; p->cdrag_icebergs = 1.5e-3;
+  p->add_weight_to_ocean = 1; p->use_old_spreading = 1; p->rotate_icebergs_for_mass_spreading = 1;
   const double im[10] = {8.8e7, 4.1e8, 3.3e9, 1.8e10, 3.8e10, 7.5e10, 1.2e11, 2.2e11, 3.9e11, 7.4e11};
   const double ds[10] = {0.24, 0.12, 0.15, 0.18, 0.12, 0.07, 0.03, 0.03, 0.03, 0.02};
   const double sc[10] = {2000, 200, 50, 20, 10, 5, 2, 1, 1, 1};
@@ -524,6 +529,7 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   else if (pin->footloose && pin->displace_fl_bergs) unsupported = "displace_fl_bergs needs the FMS random number stream: set displace_fl_bergs=0";
   else if (pin->footloose && dom->nranks > 1) unsupported = "footloose calving across ranks is not implemented in this build";
   else if (pin->iceberg_bonds_on && dom->nranks > 1) unsupported = "bonds across ranks are not implemented in this build";
+  else if (pin->time_average_weight && pin->add_weight_to_ocean) unsupported = "time_average_weight is not implemented";
   else if (dom->cyclic_y) unsupported = "cyclic y is not implemented";
   else if (pin->halo < 2) unsupported = "halo must be >= 2";
   if (unsupported) { g_init_error = std::string("kid_init: ") + unsupported; return KID_ERR_UNSUPPORTED; }
@@ -712,6 +718,23 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
                    &g.fl_bits_src, &g.melt_buoy, &g.melt_eros, &g.melt_conv, &g.melt_buoy_fl, &g.melt_eros_fl,
                    &g.melt_conv_fl, &g.fl_parent_melt, &g.fl_child_melt, &g.stored_heat, &g.tmp, &h->tmp_u, &h->tmp_v};
   for (auto z : zf) { *z = dev_field(h, n2, 0.); if (!*z) return fail(h, KID_ERR_CUDA, "kid_init: out of device memory (fields)"); }
+  {
+    SpreadFields& sf = h->sf;
+    double** nine[] = {&sf.mass_on_ocean, &sf.area_on_ocean, &sf.uvel_on_ocean, &sf.vvel_on_ocean};
+    for (auto z : nine) { *z = dev_field(h, n2 * 9, 0.); if (!*z) return fail(h, KID_ERR_CUDA, "kid_init: out of device memory (spreading)"); }
+    double** one[] = {&sf.mass, &sf.bergy_mass, &sf.spread_mass, &sf.spread_area, &sf.spread_uvel, &sf.spread_vvel, &sf.ustar_iceberg};
+    for (auto z : one) { *z = dev_field(h, n2, 0.); if (!*z) return fail(h, KID_ERR_CUDA, "kid_init: out of device memory (spreading)"); }
+    SpreadParams& sp = h->sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.grounding_fraction = q->grounding_fraction; sp.clipping_depth = q->clipping_depth; sp.initial_orientation = q->initial_orientation;
+    sp.cdrag_icebergs = q->cdrag_icebergs; sp.utide_icebergs = q->utide_icebergs; sp.ustar_icebergs_bg = q->ustar_icebergs_bg;
+    sp.melt_cutoff = q->melt_cutoff;
+    sp.add_weight = (q->add_weight_to_ocean && !q->time_average_weight) ? 1 : 0;
+    sp.use_old_spreading = q->use_old_spreading; sp.rotate = q->rotate_icebergs_for_mass_spreading;
+    sp.diag = (q->pass_fields_to_ocean_model || q->melt_diagnostics) ? 1 : 0;
+    sp.apply_cutoff_gridded = q->apply_thickness_cutoff_to_gridded_melt;
+    for (int k = 0; k < 3; k++) CK(cudaMalloc(&h->out_stage3[k], sizeof(double) * (size_t)h->nic * h->njc));
+  }
   g.stored_ice = dev_field(h, n2 * KID_NCLASSES, 0.);
   g.real_calving = dev_field(h, n2 * KID_NCLASSES, 0.);
   if (!g.stored_ice || !g.real_calving) return fail(h, KID_ERR_CUDA, "kid_init: out of device memory (calving)");
@@ -831,6 +854,7 @@ extern "C" int32_t kid_end(kid_t** hp) {
   cudaFree(h->g.iceberg_counter_grd); cudaFree(h->g.corner); cudaFree(h->g.cell); cudaFree(h->g.lonlat); cudaFree(h->g.rect);
   for (auto p : h->in_stage) cudaFree(p);
   for (auto p : h->out_stage) cudaFree(p);
+  for (auto p : h->out_stage3) cudaFree(p);
   for (int c = 0; c < C_NCOLS; c++) cudaFree(h->b.f64[c]);
   cudaFree(h->b.id); cudaFree(h->b.ine); cudaFree(h->b.jne); cudaFree(h->b.start_year);
   cudaFree(h->b.flags); cudaFree(h->b.halo_code);
@@ -875,6 +899,7 @@ static int check_device_errors(kid_t* h) {
     if (e & 256u) return fail(h, KID_ERR_STATE, "KID, connect_all_bonds: A non-halo bond is missing!!!");
     if (e & 512u) return fail(h, KID_ERR_CAPACITY, "kid: a berg has more than max_bonds bonds");
     if (e & 1024u) return fail(h, KID_ERR_STATE, "KID,footloose_calving: Bonded footloose calving not yet fully implemented!");
+    if (e & 4096u) return fail(h, KID_ERR_STATE, "KID, hexagonal spreading: All the mass is not being used!!!");
     if (e & 2048u) return fail(h, KID_ERR_STATE, "KID,footloose_calving: non-edge element has fully calved from footloose mechanism");
     return fail(h, KID_ERR_STATE, "kid: device error flag set");
   }
@@ -1456,6 +1481,37 @@ static cudaEvent_t pool_event(kid_t* h) {
   return h->ev_pool[h->ev_used++];
 }
 
+// create_gridded_icebergs_fields I:3390-3489: berg mass / area / momentum on the ocean grid
+static int spread_fields(kid_t* h) {
+  const long long n2 = h->n2;
+  SpreadFields& sf = h->sf;
+  // nothing asked for: no weight on the ocean (add_weight_to_ocean) and no diagnostics registered (I:5049-5062)
+  if (!h->sp.add_weight && !h->sp.diag) return KID_OK;
+  CK(cudaMemsetAsync(sf.mass, 0, sizeof(double) * n2, h->stream));
+  CK(cudaMemsetAsync(sf.bergy_mass, 0, sizeof(double) * n2, h->stream));
+  double* n1[] = {sf.spread_mass, sf.spread_area, sf.spread_uvel, sf.spread_vvel, sf.ustar_iceberg};
+  for (double* f : n1) CK(cudaMemsetAsync(f, 0, sizeof(double) * n2, h->stream));
+  double* nine[] = {sf.mass_on_ocean, sf.area_on_ocean, sf.uvel_on_ocean, sf.vvel_on_ocean};
+  if (h->sp.add_weight) for (double* f : nine) CK(cudaMemsetAsync(f, 0, sizeof(double) * n2 * 9, h->stream));
+  LAUNCH(h, k_spread_bergs, h->n_slots, 128, h->g, h->b, h->dp, h->sp, sf, h->dcnt, h->n_slots, n2);
+  if (!h->sp.add_weight) return KID_OK;
+  // mpp_update_domains(var_on_ocean) I:6105, all 36 layers
+  std::vector<double*> layers;
+  for (double* f : nine) for (int k = 0; k < 9; k++) layers.push_back(f + n2 * k);
+  if (h->d.nranks > 1) { int rc = halo_exchange(h, layers.data(), (int)layers.size()); if (rc) return rc; }
+  else if (h->g.pe_E_self && h->g.pe_W_self) {
+    for (size_t k0 = 0; k0 < layers.size(); k0 += 18) {
+      FieldList fl; fl.n = 0;
+      for (size_t k = k0; k < std::min(layers.size(), k0 + 18); k++) fl.f[fl.n++] = layers[k];
+      long long n = (long long)2 * h->p.halo * h->njc;
+      LAUNCH(h, k_halo_wrap_x, n, 128, h->g, fl);
+    }
+  }
+  LAUNCH(h, k_sum_spread, (long long)h->nic * h->njc, 128, h->g, h->sp, sf, n2);
+  if (h->sp.apply_cutoff_gridded) LAUNCH(h, k_thickness_cutoff, n2, 256, h->g, h->dp, h->sp, sf, n2);
+  return KID_OK;
+}
+
 // the hot path of icebergs_run, I:5389-5512
 static int step_core(kid_t* h) {
   cudaStream_t s = h->stream;
@@ -1556,6 +1612,7 @@ static int step_core(kid_t* h) {
     int rc = sort_bergs(h);
     if (rc) return rc;
   }
+  { int rc = spread_fields(h); if (rc) return rc; }
   CK(cudaEventRecord(h->ev[T_TOTAL], s));
   CK(cudaEventRecord(e2, s));
   return KID_OK;
@@ -1617,11 +1674,14 @@ extern "C" int32_t kid_run(kid_t* h, int32_t year, double yearday, double* calvi
     LAUNCH(h, k_outputs, (long long)nc, 256, h->g, h->out_stage[0], h->out_stage[1]);
     CK(cudaMemcpyAsync(calving, h->out_stage[0], sizeof(double) * nc, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(calving_hflx, h->out_stage[1], sizeof(double) * nc, cudaMemcpyDeviceToHost, h->stream));
-    // mass/ustar/area on the ocean grid come from the spreading rows; this
-    // build returns the zeroed fields icebergs_run starts from (I:5158-5166)
-    if (mass_berg) memset(mass_berg, 0, sizeof(double) * nc);
-    if (ustar_berg) memset(ustar_berg, 0, sizeof(double) * nc);
-    if (area_berg) memset(area_berg, 0, sizeof(double) * nc);
+    // I:5663-5678
+    const double* src3[3] = {h->sf.spread_mass, h->sf.ustar_iceberg, h->sf.spread_area};
+    double* dst3[3] = {(mass_berg && h->p.add_weight_to_ocean) ? mass_berg : nullptr, ustar_berg, area_berg};
+    for (int k = 0; k < 3; k++) {
+      if (!dst3[k]) continue;
+      LAUNCH(h, k_copy_out, (long long)nc, 256, h->g, src3[k], h->out_stage3[k]);
+      CK(cudaMemcpyAsync(dst3[k], h->out_stage3[k], sizeof(double) * nc, cudaMemcpyDeviceToHost, h->stream));
+    }
   }
   CK(cudaEventRecord(h->ev[T_NPHASE + 1], h->stream));
   rc = check_device_errors(h);
@@ -1707,6 +1767,10 @@ static const double* field_ptr(kid_t* h, int id) {
     case KID_FLD_AREA: return g.area; case KID_FLD_MSK: return g.msk; case KID_FLD_COS: return g.cosr;
     case KID_FLD_SIN: return g.sinr; case KID_FLD_OCEAN_DEPTH: return g.ocean_depth;
     case KID_FLD_STORED_HEAT: return g.stored_heat;
+    case KID_FLD_MASS: return h->sf.mass; case KID_FLD_BERGY_MASS: return h->sf.bergy_mass;
+    case KID_FLD_SPREAD_MASS: return h->sf.spread_mass; case KID_FLD_SPREAD_AREA: return h->sf.spread_area;
+    case KID_FLD_USTAR_ICEBERG: return h->sf.ustar_iceberg; case KID_FLD_SPREAD_UVEL: return h->sf.spread_uvel;
+    case KID_FLD_SPREAD_VVEL: return h->sf.spread_vvel;
     default: return nullptr;
   }
 }
@@ -1727,15 +1791,35 @@ extern "C" int32_t kid_get_grid_field(kid_t* h, int32_t field_id, double* out) {
   return KID_OK;
 }
 
+// icebergs_stock_pe I:8102-8128
 extern "C" int32_t kid_stock(kid_t* h, int32_t index, double* value) {
-  (void)index;
   if (!h || !value) return KID_ERR_ARG;
-  return fail(h, KID_ERR_UNSUPPORTED, "kid_stock: icebergs_stock_pe is not implemented in this build");
+  cudaSetDevice(h->d.device);
+  *value = 0.0;
+  if (index != KID_ISTOCK_WATER && index != KID_ISTOCK_HEAT) return KID_OK;
+  double* acc = h->out_stage3[0];
+  CK(cudaMemsetAsync(acc, 0, 2 * sizeof(double), h->stream));
+  long long n = std::max<long long>(h->n_slots, (long long)h->nic * h->njc);
+  LAUNCH(h, k_stock, n, 256, h->g, h->b, h->n_slots, h->n2, acc);
+  double host[2] = {0., 0.};
+  CK(cudaMemcpyAsync(host, acc, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  double total = host[1] + host[0];
+  *value = (index == KID_ISTOCK_WATER) ? total : -total * h->p.hlf;
+  return KID_OK;
 }
+// icebergs_incr_mass I:6046-6075
 extern "C" int32_t kid_incr_mass(kid_t* h, double* mass) {
-  (void)mass;
-  if (!h) return KID_ERR_ARG;
-  return fail(h, KID_ERR_UNSUPPORTED, "kid_incr_mass: icebergs_incr_mass needs the spreading rows (not in this build)");
+  if (!h || !mass) return KID_ERR_ARG;
+  if (!h->p.add_weight_to_ocean || h->p.passive_mode) return KID_OK;
+  cudaSetDevice(h->d.device);
+  size_t nc = (size_t)h->nic * h->njc;
+  std::vector<double> tmp(nc);
+  LAUNCH(h, k_copy_out, (long long)nc, 256, h->g, h->sf.spread_mass, h->out_stage3[0]);
+  CK(cudaMemcpyAsync(tmp.data(), h->out_stage3[0], sizeof(double) * nc, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (size_t k = 0; k < nc; k++) mass[k] = mass[k] + tmp[k];
+  return KID_OK;
 }
 
 extern "C" int32_t kid_synchronize(kid_t* h) {

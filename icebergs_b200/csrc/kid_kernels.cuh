@@ -810,6 +810,34 @@ __global__ void k_outputs(const __grid_constant__ DevGrid g, double* __restrict_
   hflx_out[k] = g.calving_hflx[c];
 }
 
+// sum_mass F:6606-6633 over the owned bergs and sum(stored_ice) over the compute domain (icebergs_stock_pe I:8102)
+__global__ void k_stock(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b, long long n_slots, long long n2,
+                        double* __restrict__ out /* [2]: berg mass, stored ice */) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double m = 0., st = 0.;
+  if (s < n_slots) {
+    uint8_t f = b.flags[s];
+    if ((f & BF_ALIVE) && !(f & (BF_HALO | BF_LEAVER)))
+      m = (b.f64[C_MASS][s] + b.f64[C_MASS_OF_BITS][s] + b.f64[C_MASS_OF_FL_BITS][s] + b.f64[C_MASS_OF_FL_BERGY_BITS][s]) * b.f64[C_MASS_SCALING][s];
+  }
+  int ni = g.iec - g.isc + 1, nj = g.jec - g.jsc + 1;
+  if (s < (long long)ni * nj) {
+    int c = gidx(g, g.isc + (int)(s % ni), g.jsc + (int)(s / ni));
+    for (int k = 0; k < KID_NCLASSES; k++) st += g.stored_ice[c + n2 * k];
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) { m += shfl_down_d(m, d); st += shfl_down_d(st, d); }
+  if ((threadIdx.x & 31) == 0) { if (m != 0.) atomicAdd(&out[0], m); if (st != 0.) atomicAdd(&out[1], st); }
+}
+
+// compute-domain slice of a data-domain field (what icebergs_run hands back, I:5663-5678)
+__global__ void k_copy_out(const __grid_constant__ DevGrid g, const double* __restrict__ src, double* __restrict__ dst) {
+  int ni = g.iec - g.isc + 1, nj = g.jec - g.jsc + 1;
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= (long long)ni * nj) return;
+  dst[k] = src[gidx(g, g.isc + (int)(k % ni), g.jsc + (int)(k / ni))];
+}
+
 // ------------------------------------------------------------- calving
 struct CalvingTables {
   double initial_mass_s[KID_NCLASSES], distribution_s[KID_NCLASSES], mass_scaling_s[KID_NCLASSES],

@@ -151,7 +151,9 @@ def workload_params(default_params, **over):
     """Physics of the synthetic case: namelist defaults except Verlet stepping, bergy bits
     on, wind passed as velocity (BASELINE.md 'Physics')."""
     kw = dict(runge_not_verlet=0, bergy_bit_erosion_fraction=0.1, tau_is_velocity=1, old_bug_bilin=1,
-              Rearth=REARTH)
+              Rearth=REARTH,
+              # the metric is dyn+thermo (SURVEY 8d): spreading the berg mass onto the ocean grid (8f1) is off
+              add_weight_to_ocean=0)
     kw.update(over)
     return default_params(**kw)
 
@@ -238,7 +240,8 @@ def collision_params(default_params, **over):
               apply_thickness_cutoff_to_gridded_melt=1, apply_thickness_cutoff_to_bergs_melt=1,
               set_melt_rates_to_zero=1, iceberg_bonds_on=1, interactive_icebergs_on=1, only_interactive_forces=0,
               use_new_predictive_corrective=1, max_bonds=6, manually_initialize_bonds=1,
-              length_for_manually_initialize_bonds=800.0, use_roundoff_fix=1, old_bug_bilin=0, tau_is_velocity=0)
+              length_for_manually_initialize_bonds=800.0, use_roundoff_fix=1, old_bug_bilin=0, tau_is_velocity=0,
+              add_weight_to_ocean=1, use_old_spreading=0, rotate_icebergs_for_mass_spreading=1, pass_fields_to_ocean_model=0)
     kw.update(over)
     return default_params(**kw)
 
@@ -267,7 +270,8 @@ def footloose_params(default_params, **over):
               allow_bergs_to_roll=1, use_updated_rolling_scheme=1, tip_parameter=0.0, set_melt_rates_to_zero=0,
               iceberg_bonds_on=0, interactive_icebergs_on=0, use_new_predictive_corrective=1, passive_mode=1,
               old_bug_bilin=0, use_roundoff_fix=1, footloose=1, displace_fl_bergs=0, fl_style_fl_bits=1,
-              fl_youngs=1.0e8, fl_strength=250.0, new_berg_from_fl_bits_mass_thres=3.0e11, tau_is_velocity=0)
+              fl_youngs=1.0e8, fl_strength=250.0, new_berg_from_fl_bits_mass_thres=3.0e11, tau_is_velocity=0,
+              add_weight_to_ocean=0)
     kw.update(over)
     return default_params(**kw)
 

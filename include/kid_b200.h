@@ -206,6 +206,16 @@ typedef struct KidParams {
   double ustar_icebergs_bg;                    /* F:715 (0.001) */
   double utide_icebergs;                       /* F:714 (0.) */
   double cdrag_icebergs;                       /* F:716 (1.5e-3) */
+  /* mass / area / momentum spread onto the ocean grid, I:3895-4100, I:4970-5011, I:6077-6150 */
+  int32_t add_weight_to_ocean;                 /* F:721 (T) */
+  int32_t time_average_weight;                 /* F:723 (F); T is not implemented */
+  int32_t use_old_spreading;                   /* F:778 (T) */
+  int32_t rotate_icebergs_for_mass_spreading;  /* F:750 (T) */
+  int32_t pass_fields_to_ocean_model;          /* F:739 (F): also fill spread_area / spread_uvel / spread_vvel / ustar */
+  int32_t pad1_;
+  double grounding_fraction;                   /* F:730 (0.) */
+  double clipping_depth;                       /* F:227 (0.) */
+  double initial_orientation;                  /* F:713 (0.) degrees */
 } KidParams;
 
 /* ----------------------------------------------------------------------------

@@ -87,6 +87,7 @@ struct Oracle {
   double *melt_buoy_fl, *melt_eros_fl, *melt_conv_fl, *fl_parent_melt, *fl_child_melt;
   double *stored_heat, *stored_ice /* (nid,njd,10) */, *real_calving, *tmp;
   double *mass, *spread_mass, *spread_area, *ustar_iceberg, *spread_uvel, *spread_vvel;
+  double *mass_on_ocean, *area_on_ocean, *uvel_on_ocean, *vvel_on_ocean;   /* (nid,njd,9) */
   int32_t* iceberg_counter_grd;
   OBerg** list;
   double minlon_c, maxlon_c;
@@ -1192,6 +1193,151 @@ static void evolve_icebergs(Oracle* o) {
   }
 }
 
+#include "kid_oracle_hex.inc"
+
+static void halo_update(Oracle* o, double* f);
+static void fl_bits_dimensions(const Oracle* o, const OBerg* this_, double* L_fl, double* W_fl, double* T_fl);
+
+/* find_orientation_using_iceberg_bonds I:3829-3893 */
+static void find_orientation_using_iceberg_bonds(Oracle* o, const OBerg* berg, double* orientation) {
+  const KidDomain* d = &o->d;
+  const double pi = o->p.pi;
+  double bond_count = 0., Average_angle = 0.;
+  if (((berg->ine > d->isd) && (berg->ine < d->ied)) && ((berg->jne >= d->jsd) && (berg->jne <= d->jed))) {
+    double lat1 = berg->lat, lon1 = berg->lon;
+    for (const OBond* cb = berg->first_bond; cb; cb = cb->next_bond) {
+      const OBerg* ob = cb->other_berg;
+      if (!ob) continue;
+      double dlat = ob->lat - lat1, dlon = ob->lon - lon1, dx_dlon, dy_dlat, angle;
+      convert_from_grid_to_meters(o, 0.5 * (lat1 + ob->lat), &dx_dlon, &dy_dlat);
+      double rx = dlon * dx_dlon, ry = dlat * dy_dlat;
+      if (rx == 0.) angle = pi / 2.;
+      else {
+        angle = atan(ry / rx);
+        angle = ((pi / 2.) - (*orientation * (pi / 180.))) - angle;
+        angle = f_modulo(angle, pi / 3.);
+      }
+      bond_count += 1.; Average_angle += angle;
+    }
+    if (bond_count > 0) Average_angle = Average_angle / bond_count; else Average_angle = 0.;
+    *orientation = f_modulo(Average_angle, pi / 3.);
+  }
+}
+
+/* spread_mass_across_ocean_cells I:3895-4100 (+ spread_variable_across_cells I:4103-4133) */
+static void spread_mass_across_ocean_cells(Oracle* o, const OBerg* berg, int i, int j, double x, double y, double Mberg,
+                                           double Mbits, double scaling, double Area, double Tn) {
+  const KidParams* p = &o->p;
+  const double rho_seawater = 1035.;     /* the local value of this routine, I:3919 */
+  size_t n2 = (size_t)o->nid * o->njd;
+  double Mass_berg = Mberg, Mfl = berg->mass_of_fl_bits, Mbits_fl = berg->mass_of_fl_bergy_bits;
+  if (p->grounding_fraction > 0.) {
+    double Hocean = p->grounding_fraction * (G(o, ocean_depth, i, j) + G(o, ssh, i, j));
+    double Dn = (p->rho_bergs / rho_seawater) * Tn;
+    if (Dn > Hocean) Mass_berg = Mass_berg * dmin(1., Hocean / Dn);
+    if (Mfl > 0.) {
+      double Lfl, Wfl, Tfl;
+      fl_bits_dimensions(o, berg, &Lfl, &Wfl, &Tfl);
+      Dn = (p->rho_bergs / rho_seawater) * Tfl;
+      if (Dn > Hocean) Mfl = Mfl * dmin(1., Hocean / Dn);
+    }
+  }
+  Mass_berg = Mass_berg + Mfl;
+  double Mass = (Mass_berg + Mbits + Mbits_fl) * scaling;
+  if (p->clipping_depth > 0.) Mass = dmin(Mass, p->clipping_depth * G(o, area, i, j) * rho_seawater);
+  double msk9[9], w[9], I_fraction_used, orientation = p->initial_orientation;
+  for (int dj = -1; dj <= 1; dj++) for (int di = -1; di <= 1; di++) msk9[(dj + 1) * 3 + (di + 1)] = G(o, msk, i + di, j + dj);
+  if (p->hexagonal_icebergs && p->iceberg_bonds_on && p->rotate_icebergs_for_mass_spreading)
+    find_orientation_using_iceberg_bonds(o, berg, &orientation);
+  if (!kh_spread_weights(p->hexagonal_icebergs, p->use_old_spreading, x, y, Area, G(o, area, i, j), msk9, orientation, p->pi,
+                         berg->static_berg == 1, w, &I_fraction_used)) {
+    o_fatal(o, "KID, hexagonal spreading: All the mass is not being used!!!");
+    return;
+  }
+  size_t c = IDX(o, i, j);
+  for (int k = 0; k < 9; k++) {
+    o->mass_on_ocean[c + n2 * k] = o->mass_on_ocean[c + n2 * k] + (w[k] * Mass * I_fraction_used);
+    o->area_on_ocean[c + n2 * k] = o->area_on_ocean[c + n2 * k] + (w[k] * (Area * scaling) * I_fraction_used);
+    o->uvel_on_ocean[c + n2 * k] = o->uvel_on_ocean[c + n2 * k] + (w[k] * (berg->uvel * Area * scaling) * I_fraction_used);
+    o->vvel_on_ocean[c + n2 * k] = o->vvel_on_ocean[c + n2 * k] + (w[k] * (berg->vvel * Area * scaling) * I_fraction_used);
+  }
+}
+
+/* calculate_mass_on_ocean I:4970-5011 (+ the mass / bergy_mass parts of calculate_sum_over_bergs_diagnositcs I:5014-5071) */
+static void calculate_mass_on_ocean(Oracle* o, int with_diagnostics) {
+  const KidParams* p = &o->p;
+  const KidDomain* d = &o->d;
+  size_t n2 = (size_t)o->nid * o->njd;
+  memset(o->mass_on_ocean, 0, sizeof(double) * n2 * 9); memset(o->area_on_ocean, 0, sizeof(double) * n2 * 9);
+  memset(o->uvel_on_ocean, 0, sizeof(double) * n2 * 9); memset(o->vvel_on_ocean, 0, sizeof(double) * n2 * 9);
+  for (int grdj = d->jsc - 1; grdj <= d->jec + 1; grdj++) for (int grdi = d->isc - 1; grdi <= d->iec + 1; grdi++)
+    for (OBerg* berg = G(o, list, grdi, grdj); berg; berg = berg->next) {
+      if (!(berg->halo_berg < 2 || !p->mts)) continue;
+      int i = berg->ine, j = berg->jne;
+      if (!(G(o, area, i, j) > 0.)) continue;
+      if (p->add_weight_to_ocean && !p->time_average_weight)
+        spread_mass_across_ocean_cells(o, berg, i, j, berg->xi, berg->yj, berg->mass, berg->mass_of_bits, berg->mass_scaling,
+                                       berg->length * berg->width, berg->thickness);
+      if (with_diagnostics) {
+        int diag = p->pass_fields_to_ocean_model || p->melt_diagnostics;      /* "id_mass > 0", I:5049 */
+        if (diag) G(o, mass, i, j) = G(o, mass, i, j) + berg->mass / G(o, area, i, j) * berg->mass_scaling;
+        if (diag || p->add_weight_to_ocean)                                    /* I:5061 */
+          G(o, bergy_mass, i, j) = G(o, bergy_mass, i, j) + (berg->mass_of_bits + berg->mass_of_fl_bergy_bits) / G(o, area, i, j) * berg->mass_scaling;
+      }
+    }
+}
+
+/* sum_up_spread_fields I:6077-6150 (no tripolar fold: parity_x = 1 everywhere) */
+static void sum_up_spread_fields(Oracle* o, double* field /* data-domain array, compute part filled */, double* var9, int is_area) {
+  const KidDomain* d = &o->d;
+  size_t n2 = (size_t)o->nid * o->njd;
+  for (int k = 0; k < 9; k++) halo_update(o, var9 + n2 * k);
+#define V9(i, j, k) var9[IDX(o, i, j) + n2 * ((k) - 1)]
+  for (int j = d->jsc; j <= d->jec; j++) for (int i = d->isc; i <= d->iec; i++) {
+    double dmda = V9(i, j, 5) + (((V9(i - 1, j - 1, 9) + V9(i + 1, j + 1, 1)) + (V9(i + 1, j - 1, 7) + V9(i - 1, j + 1, 3))) +
+                                  ((V9(i - 1, j, 6) + V9(i + 1, j, 4)) + (V9(i, j - 1, 8) + V9(i, j + 1, 2))));
+    if (G(o, area, i, j) > 0) dmda = dmda / G(o, area, i, j) * G(o, msk, i, j);
+    if (is_area) dmda = dmin(dmda, 1.0);
+    field[IDX(o, i, j)] = dmda;
+  }
+#undef V9
+}
+
+/* create_gridded_icebergs_fields I:3390-3489 (find_melt_using_spread_mass is refused at create) */
+static void create_gridded_icebergs_fields(Oracle* o) {
+  const KidParams* p = &o->p;
+  const KidDomain* d = &o->d;
+  size_t n2 = (size_t)o->nid * o->njd;
+  int diag = p->pass_fields_to_ocean_model || p->melt_diagnostics;
+  if (!diag && !(p->add_weight_to_ocean && !p->time_average_weight)) return;   /* every field below stays zero */
+  memset(o->mass, 0, sizeof(double) * n2); memset(o->bergy_mass, 0, sizeof(double) * n2);
+  calculate_mass_on_ocean(o, 1);
+  memset(o->spread_uvel, 0, sizeof(double) * n2); memset(o->spread_vvel, 0, sizeof(double) * n2);
+  memset(o->spread_area, 0, sizeof(double) * n2); memset(o->spread_mass, 0, sizeof(double) * n2);
+  if (diag) {
+    sum_up_spread_fields(o, o->spread_uvel, o->uvel_on_ocean, 0);
+    sum_up_spread_fields(o, o->spread_vvel, o->vvel_on_ocean, 0);
+    sum_up_spread_fields(o, o->spread_area, o->area_on_ocean, 1);
+  }
+  sum_up_spread_fields(o, o->spread_mass, o->mass_on_ocean, 0);
+  memset(o->ustar_iceberg, 0, sizeof(double) * n2);
+  if (diag)
+    for (int j = d->jsc; j <= d->jec; j++) for (int i = d->isc; i <= d->iec; i++) {
+      double dvo = sqrt(pow(G(o, spread_uvel, i, j) - G(o, uo, i, j), 2) + pow(G(o, spread_vvel, i, j) - G(o, vo, i, j), 2));
+      double ustar = sqrt(p->cdrag_icebergs * (dvo * dvo + p->utide_icebergs * p->utide_icebergs));
+      double ustar_h = dmax(p->ustar_icebergs_bg, ustar);
+      if (G(o, spread_area, i, j) == 0.0) ustar_h = 0.;
+      G(o, ustar_iceberg, i, j) = ustar_h;
+    }
+  if (p->apply_thickness_cutoff_to_gridded_melt)
+    for (int i = d->isd; i <= d->ied; i++) for (int j = d->jsd; j <= d->jed; j++)
+      if ((p->melt_cutoff >= 0.) && (G(o, spread_area, i, j) > 0.)) {
+        double ave_thickness = G(o, spread_mass, i, j) / (G(o, spread_area, i, j) * p->rho_bergs);
+        double ave_draft = ave_thickness * (p->rho_bergs / RHO_SEAWATER);
+        if ((G(o, ocean_depth, i, j) - ave_draft) < p->melt_cutoff) { G(o, floating_melt, i, j) = 0.0; G(o, calving_hflx, i, j) = 0.0; }
+      }
+}
+
 /* ------------------------------------------- find_basal_melt I:3492-3826 */
 static double calculate_TFreeze(double S, double pres) {          /* I:3790-3802 */
   const double dTFr_dp = -7.53E-08, dTFr_dS = -0.0573, TFr_S0_P0 = 0.0832;
@@ -1914,6 +2060,9 @@ Oracle* oracle_create(const KidParams* p, const KidDomain* dom, int32_t year, do
   for (size_t k = 0; k < sizeof(z) / sizeof(z[0]); k++) *z[k] = dalloc(n2, 0.);
   o->stored_ice = dalloc(n2 * KID_NCLASSES, 0.);
   o->real_calving = dalloc(n2 * KID_NCLASSES, 0.);
+  o->mass_on_ocean = dalloc(n2 * 9, 0.); o->area_on_ocean = dalloc(n2 * 9, 0.);
+  o->uvel_on_ocean = dalloc(n2 * 9, 0.); o->vvel_on_ocean = dalloc(n2 * 9, 0.);
+  if (p->time_average_weight) o_fatal(o, "oracle: time_average_weight is not restated");
   o->iceberg_counter_grd = (int32_t*)calloc(n2, sizeof(int32_t));
   o->list = (OBerg**)calloc(n2, sizeof(OBerg*));
   if (p->runge_not_verlet) o_fatal(o, "oracle: only Verlet (Runge_not_Verlet=.false.) is restated");
@@ -2045,7 +2194,8 @@ void oracle_destroy(Oracle* o) {
                  o->bergy_src, o->bergy_melt, o->bergy_mass, o->fl_bits_src, o->fl_bits_melt, o->melt_buoy_fl,
                  o->melt_eros_fl, o->melt_conv_fl, o->fl_parent_melt, o->fl_child_melt, o->stored_heat,
                  o->stored_ice, o->real_calving, o->tmp, o->mass, o->spread_mass, o->spread_area,
-                 o->ustar_iceberg, o->spread_uvel, o->spread_vvel};
+                 o->ustar_iceberg, o->spread_uvel, o->spread_vvel, o->mass_on_ocean, o->area_on_ocean,
+                 o->uvel_on_ocean, o->vvel_on_ocean};
   for (size_t k = 0; k < sizeof(z) / sizeof(z[0]); k++) free(z[k]);
   free(o->iceberg_counter_grd); free(o->list); free(o);
 }
@@ -2323,6 +2473,7 @@ static void step_core(Oracle* o) {
   double t3 = now_sec();
   thermodynamics(o);
   double t4 = now_sec();
+  create_gridded_icebergs_fields(o);
   o->tsec[0] += t2 - t1; o->tsec[1] += t4 - t3; o->tsec[2] += (t1 - t0) + (t3 - t2);
 }
 

@@ -69,9 +69,9 @@ def lib():
         L.oracle_rolling.restype = None
         L.oracle_accel_free.argtypes = [C.POINTER(D.KidParams)] + [C.POINTER(C.c_double)] * 4
         L.oracle_accel_free.restype = None
-        for name in ("oracle_point_in_triangle", "oracle_hexagon_into_quadrants"):
-            if hasattr(L, name):
-                pass
+        L.oracle_point_in_triangle.argtypes = [C.c_double] * 8
+        L.oracle_hexagon_into_quadrants.argtypes = [C.c_double] * 4 + [C.POINTER(C.c_double)] * 5
+        L.oracle_hexagon_into_quadrants.restype = None
         _LIB = L
     return _LIB
 

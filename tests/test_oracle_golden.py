@@ -152,3 +152,22 @@ def test_footloose_test_ends_with_12_bergs():
         done += n
     assert o.count_bergs() == KNOWN["restart_counts"]["footloose"] == 12
     assert o.counters()["nbergs_calved_fl"] == 10
+
+
+def test_point_in_triangle_I234():
+    k = KNOWN["point_in_triangle"]
+    L = O.lib()
+    assert bool(L.oracle_point_in_triangle(*k["A"], *k["B"], *k["C"], *k["q"])) is k["inside"]
+
+
+def test_hexagon_quadrant_areas_I261():
+    """hexagon_test (I:261-348): the 8 area identities of Hexagon_into_quadrants_using_triangles, tol 1e-10."""
+    k = KNOWN["hexagon"]
+    L = O.lib()
+    out = [C.c_double() for _ in range(5)]
+    for case in k["cases"]:
+        L.oracle_hexagon_into_quadrants(case["x0"], case["y0"], k["H"], k["theta"], *[C.byref(v) for v in out])
+        area, q = out[0].value, [v.value for v in out[1:]]
+        assert abs(area - k["area"]) <= k["tol"], case["name"]
+        for got, want in zip(q, case["Q"]):
+            assert abs(got - want) <= k["tol"], (case["name"], q, case["Q"])

@@ -1,0 +1,71 @@
+"""Berg mass / area / momentum spread onto the ocean grid (calculate_mass_on_ocean
+I:4970, spread_mass_across_ocean_cells I:3895 with the hexagon quadrant geometry I:4562,
+sum_up_spread_fields I:6077, ustar and the thickness cutoff I:3461-3488) and what icebergs_run
+returns in mass_berg / ustar_berg / area_berg (I:5663-5678): CUDA path against the CPU oracle."""
+import numpy as np
+import pytest
+
+import kid_oracle_py as O
+from common import Case, grid_rel
+from icebergs_b200 import _cdefs as D
+from icebergs_b200 import api
+from icebergs_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+SPREAD = (D.KID_FLD_SPREAD_MASS, D.KID_FLD_SPREAD_AREA, D.KID_FLD_SPREAD_UVEL, D.KID_FLD_SPREAD_VVEL,
+          D.KID_FLD_USTAR_ICEBERG, D.KID_FLD_MASS, D.KID_FLD_BERGY_MASS, D.KID_FLD_FLOATING_MELT)
+
+
+def outputs(run, who, case, **kw):
+    comp = (case.gnj, case.gni)
+    m, u, a = np.zeros(comp), np.zeros(comp), np.zeros(comp)
+    calving, hflx, f = case.run_args(**kw)
+    args = ((1, 0.0), calving, f["uo"], f["vo"], f["ui"], f["vi"], f["tauxa"], f["tauya"], f["ssh"], f["sst"], hflx, f["cn"], f["hi"])
+    if run == "gpu":
+        api.icebergs_run(who, *args, sss=f["sss"], mass_berg=m, ustar_berg=u, area_berg=a)
+    else:
+        who.run(*args, sss=f["sss"], mass_berg=m, ustar_berg=u, area_berg=a)
+    return calving, m, u, a
+
+
+@pytest.mark.parametrize("old_spreading", [1, 0])
+def test_rectangular_spreading_latlon(old_spreading):
+    """Default rectangular bergs on the lat-lon grid; big scaled bergs so that the weights reach the
+    neighbouring cells, dense enough that several bergs share a cell."""
+    case = Case(96, 48, 30000, add_weight_to_ocean=1, use_old_spreading=old_spreading, pass_fields_to_ocean_model=1,
+                apply_thickness_cutoff_to_gridded_melt=1, melt_cutoff=3995.0)
+    b, o = case.make_gpu(), case.make_oracle()
+    for step in range(2):
+        cg, mg, ug, ag = outputs("gpu", b, case)
+        co, mo, uo_, ao = outputs("ora", o, case)
+        for fid in SPREAD:
+            assert grid_rel(b.grid_field(fid), o.grid_field(fid)) < 1e-10, f"field {fid} step {step}"
+        assert grid_rel(mg, mo) < 1e-10 and grid_rel(ug, uo_) < 1e-10 and grid_rel(ag, ao) < 1e-10 and grid_rel(cg, co) < 1e-10
+    assert mo.max() > 0 and ao.max() > 0 and uo_.max() > 0
+    tot = np.sum(o.grid_field(D.KID_FLD_SPREAD_MASS) * o.grid_field(D.KID_FLD_AREA))
+    bg = b.get_bergs(["mass", "mass_of_bits", "mass_scaling"])
+    assert abs(tot - np.sum((bg["mass"] + bg["mass_of_bits"]) * bg["mass_scaling"])) / tot < 1e-9     # all the mass is on the grid
+    mass = np.zeros((case.gnj, case.gni))
+    b.incr_mass(mass)
+    assert grid_rel(mass, mo) < 1e-12                                                                     # icebergs_incr_mass I:6046
+    allm = b.get_bergs(["mass", "mass_of_bits", "mass_scaling"])
+    want = np.sum((allm["mass"] + allm["mass_of_bits"]) * allm["mass_scaling"])
+    assert abs(b.stock_pe(D.KID_ISTOCK_WATER) - want) / want < 1e-12                                      # icebergs_stock_pe I:8102
+    assert abs(b.stock_pe(D.KID_ISTOCK_HEAT) + want * case.params().hlf) / (want * case.params().hlf) < 1e-12
+    api.icebergs_end(b)
+
+
+def test_hexagonal_spreading_with_bond_orientation():
+    """tests/collision_tests: hexagonal elements, orientation from the bonds (I:3829), 1 km cells."""
+    from test_interactions_gpu import Pair
+    params = lambda: S.collision_params(api.default_params, pass_fields_to_ocean_model=1)
+    p = Pair(S.collision_bergs(), params)
+    for k in range(3):
+        p.step(20)
+        for fid in SPREAD:
+            a, b_ = p.b.grid_field(fid), p.o.grid_field(fid)
+            assert np.max(np.abs(a - b_)) <= 1e-9 * max(np.max(np.abs(b_)), 1e-300), f"field {fid} after {20 * (k + 1)} steps"
+    sm = p.o.grid_field(D.KID_FLD_SPREAD_MASS)
+    assert (sm > 0).sum() > 16            # the 16 elements cover more cells than they sit in
+    p.end()
