@@ -517,7 +517,8 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   if (dom->device < 0 || dom->device >= ndev) { g_init_error = "kid_init: bad device ordinal"; return KID_ERR_ARG; }
   // what this build of the library does not implement is refused up front
   const char* unsupported = nullptr;
-  if (pin->runge_not_verlet) unsupported = "Runge_not_Verlet=.true. (RK4) is not implemented: set runge_not_verlet=0";
+  if (pin->runge_not_verlet && (pin->interactive_icebergs_on || pin->footloose || pin->mts))
+    unsupported = "Runge_not_Verlet=.true. (RK4) is implemented for free-drifting bergs only: set runge_not_verlet=0 with interactions / footloose";
   else if (pin->tidal_drift > 0.) unsupported = "tidal_drift>0 needs the FMS random number stream";
   else if (pin->add_iceberg_thickness_to_ssh) unsupported = "add_iceberg_thickness_to_SSH is not implemented";
   else if (pin->mts || pin->dem) unsupported = "MTS/DEM stepping is not implemented in this build";
@@ -1556,6 +1557,9 @@ static int step_core(kid_t* h) {
       else if (dg) { LAUNCH(h, (k_step<false, true, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
       else { LAUNCH(h, (k_step<false, false, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
       if (h->b.max_bonds > 0) LAUNCH(h, k_bond_address_update, h->n_slots, 128, h->b, h->n_slots);
+    } else if (h->p.runge_not_verlet) {
+      if (dg) { LAUNCH(h, (k_step_rk<true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
+      else { LAUNCH(h, (k_step_rk<false>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
     } else if (fl) { LAUNCH(h, (k_step<true, false, false>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
     else if (dg) launch_step<false, true>(h); else launch_step<false, false>(h);
   }

@@ -442,6 +442,135 @@ k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
   }
 }
 
+// ------------------------------------------------------- Runge-Kutta step
+// Runge_Kutta_stepping I:7331-7679 (the namelist default, F:733) + send_bergs + thermodynamics for one
+// berg per thread: four accel evaluations at the stage positions (interp_flds at each stage's cell),
+// adjust_index_and_ground after every stage, tangent plane above 89N.  Not the benchmarked path: kept
+// straightforward (plain IEEE arithmetic in accel_rk) rather than tuned.
+struct RkStage { double lon, lat, uvel, vvel, u, v, ax, ay, axn, ayn, xdot, ydot, xddot, yddot, xddotn, yddotn; };
+
+template <bool DIAG>
+__global__ void __launch_bounds__(KID_BLOCK)
+k_step_rk(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b, const __grid_constant__ DevParams p,
+          DevCounters* __restrict__ cnt, long long n_slots) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  uint8_t flags = (s < n_slots) ? b.flags[s] : (uint8_t)0;
+  bool owned = (flags & BF_ALIVE) && !(flags & BF_HALO);
+  Scatter sc;
+  sc.key = -1;
+  sc.fx.floating_melt = sc.fx.calving_hflx = sc.fx.berg_melt = sc.fx.bergy_src = sc.fx.bergy_melt = 0.;
+  sc.fx.fl_bits_melt = sc.fx.fl_bits_src = sc.fx.net_heat = 0.;
+  sc.fx.fl_parent_melt = sc.fx.fl_child_melt = sc.fx.melt_buoy = sc.fx.melt_eros = sc.fx.melt_conv = 0.;
+  sc.fx.melt_buoy_fl = sc.fx.melt_eros_fl = sc.fx.melt_conv_fl = 0.;
+  bool melted = false, any_bounce = false, speeding = false, left = false;
+  if (owned) {
+    const double dt = p.dt, dt_2 = 0.5 * dt, dt_6 = dt / 6.;
+    int i = b.ine[s], j = b.jne[s];
+    const int i1 = i, j1 = j;
+    const double xi0 = b.f64[C_XI][s], yj0 = b.f64[C_YJ][s];
+    double xi = xi0, yj = yj0;
+    double lon = b.f64[C_LON][s], lat = b.f64[C_LAT][s], uvel = b.f64[C_UVEL][s], vvel = b.f64[C_VVEL][s];
+    const double M = b.f64[C_MASS][s], T = b.f64[C_THICKNESS][s], W = b.f64[C_WIDTH][s], L = b.f64[C_LENGTH][s];
+    if (!(flags & BF_STATIC)) {
+      const bool tang = (lat > 89.) && p.grid_is_latlon;
+      const double axn0 = b.f64[C_AXN][s], ayn0 = b.f64[C_AYN][s];
+      double bxn = 0., byn = 0., x1 = 0., y1 = 0., dydl;
+      RkStage st[4];
+      double lonn = lon, latn = lat, uveln = uvel, vveln = vvel, axn = 0., ayn = 0.;
+      for (int k = 0; k < 4; k++) {
+        RkStage& q = st[k];
+        const double h = (k == 3) ? dt : dt_2;          // stage step to reach this stage: dt_2, dt_2, dt
+        if (k == 0) {
+          q.lon = lon; q.lat = lat; q.uvel = uvel; q.vvel = vvel;
+          if (tang) { rotpos_to_tang(p, q.lon, q.lat, x1, y1); rotvec_to_tang(p, q.lon, q.uvel, q.vvel, q.xdot, q.ydot); }
+        } else {
+          const RkStage& r = st[k - 1];
+          if (tang) {
+            double x = x1 + h * r.xdot, y = y1 + h * r.ydot;
+            q.xdot = st[0].xdot + h * r.xddot; q.ydot = st[0].ydot + h * r.yddot;
+            rotpos_from_tang(p, x, y, q.lon, q.lat);
+            rotvec_from_tang(p, q.lon, q.xdot, q.ydot, q.uvel, q.vvel);
+          } else {
+            q.lon = lon + h * r.u; q.lat = lat + h * r.v;
+            q.uvel = uvel + h * r.ax; q.vvel = vvel + h * r.ay;
+          }
+          i = i1; j = j1; xi = xi0; yj = yj0;
+          any_bounce |= adjust_index_and_ground(g, p, q.lon, q.lat, i, j, xi, yj, &cnt->error_flags, &cnt->warn_adjust);
+        }
+        double dxdl;
+        convert_from_meters_to_grid(p, q.lat, dxdl, dydl);
+        q.u = q.uvel * dxdl; q.v = q.vvel * dydl;
+        Env e;
+        if (!interp_flds(g, p, i, j, xi, yj, e)) atomicOr(&cnt->error_flags, 64u);
+        double loc_dx = 0.;
+        if ((p.speed_limit > 0.) || (p.speed_limit == -1.)) {
+          int c = gidx(g, i, j);
+          loc_dx = fmin(0.5 * (g.dx[c] + g.dx[c - g.nid]), 0.5 * (g.dy[c] + g.dy[c - 1]));
+        }
+        q.axn = axn0; q.ayn = ayn0;
+        accel_rk(p, M, T, W, L, q.lat, q.uvel, q.vvel, uvel, vvel, (k < 2) ? dt_2 : dt, e, loc_dx, q.ax, q.ay, q.axn, q.ayn, bxn, byn, speeding);
+        if (tang) { rotvec_to_tang(p, q.lon, q.ax, q.ay, q.xddot, q.yddot); rotvec_to_tang(p, q.lon, q.axn, q.ayn, q.xddotn, q.yddotn); }
+      }
+      if (tang) {
+        double xn = x1 + dt_6 * ((st[0].xdot + st[3].xdot) + 2. * (st[1].xdot + st[2].xdot));
+        double yn = y1 + dt_6 * ((st[0].ydot + st[3].ydot) + 2. * (st[1].ydot + st[2].ydot));
+        double xdotn = st[0].xdot + dt_6 * ((st[0].xddot + st[3].xddot) + 2. * (st[1].xddot + st[2].xddot));
+        double ydotn = st[0].ydot + dt_6 * ((st[0].yddot + st[3].yddot) + 2. * (st[1].yddot + st[2].yddot));
+        double xddotn = ((st[0].xddotn + st[3].xddotn) + 2. * (st[1].xddotn + st[2].xddotn)) / 6.;
+        double yddotn = ((st[0].yddotn + st[3].yddotn) + 2. * (st[1].yddotn + st[2].yddotn)) / 6.;
+        rotpos_from_tang(p, xn, yn, lonn, latn);
+        rotvec_from_tang(p, lonn, xdotn, ydotn, uveln, vveln);
+        rotvec_from_tang(p, lonn, xddotn, yddotn, axn, ayn);
+      } else {
+        lonn = lon + dt_6 * ((st[0].u + st[3].u) + 2. * (st[1].u + st[2].u));
+        latn = lat + dt_6 * ((st[0].v + st[3].v) + 2. * (st[1].v + st[2].v));
+        uveln = uvel + dt_6 * ((st[0].ax + st[3].ax) + 2. * (st[1].ax + st[2].ax));
+        vveln = vvel + dt_6 * ((st[0].ay + st[3].ay) + 2. * (st[1].ay + st[2].ay));
+        axn = ((st[0].axn + st[3].axn) + 2. * (st[1].axn + st[2].axn)) / 6.;
+        ayn = ((st[0].ayn + st[3].ayn) + 2. * (st[1].ayn + st[2].ayn)) / 6.;
+        bxn = (((st[0].ax + st[3].ax) + 2. * (st[1].ax + st[2].ax)) / 6) - (axn / 2);
+        byn = (((st[0].ay + st[3].ay) + 2. * (st[1].ay + st[2].ay)) / 6) - (ayn / 2);
+      }
+      i = i1; j = j1; xi = xi0; yj = yj0;
+      any_bounce |= adjust_index_and_ground(g, p, lonn, latn, i, j, xi, yj, &cnt->error_flags, &cnt->warn_adjust);
+      if (p.override_iceberg_velocities) { uveln = p.u_override; vveln = p.v_override; }
+      lon = lonn; lat = latn; uvel = uveln; vvel = vveln;
+      b.f64[C_AXN][s] = axn; b.f64[C_AYN][s] = ayn; b.f64[C_BXN][s] = bxn; b.f64[C_BYN][s] = byn;
+      b.f64[C_UVEL][s] = uvel; b.f64[C_VVEL][s] = vvel;
+      b.f64[C_LON][s] = lon; b.f64[C_LAT][s] = lat;
+    }
+    int route = 0;
+    if (i > g.iec || i < g.isc || j > g.jec || j < g.jsc)
+      route = route_berg(g, p, lon, lat, i, j, xi, yj, &cnt->error_flags, &cnt->n_wrapped);
+    if (!(flags & BF_STATIC) || route != 0) {
+      b.f64[C_XI][s] = xi; b.f64[C_YJ][s] = yj;
+      b.ine[s] = i; b.jne[s] = j;
+    }
+    if (route == 1) {
+      left = true;
+      b.flags[s] = flags | BF_LEAVER;
+      unsigned long long k = atomicAdd(&cnt->n_leaver_list, 1ull);
+      if ((long long)k < b.leaver_cap) b.leaver_list[k] = (int32_t)s;
+      else atomicOr(&cnt->error_flags, (unsigned)KID_DEVERR_CAPACITY);
+    } else if (route == 2) {
+      b.flags[s] = 0;
+    } else {
+      int outcome = thermo_slot<false>(g, b, p, s, flags, i, j, xi, yj, uvel, vvel, M, T, W, L, b.f64[C_MASS_SCALING][s],
+                                       b.f64[C_MASS_OF_BITS][s], b.f64[C_HEAT_DENSITY][s], sc, cnt);
+      if (outcome == TH_DELETE) { melted = true; b.flags[s] = 0; }
+    }
+  }
+  scatter_fluxes<false, DIAG>(g, sc);
+  warp_count_add(&cnt->nbergs_melted, melted);
+  warp_count_add(&cnt->n_bounced, any_bounce);
+  warp_count_add(&cnt->nspeeding, speeding);
+  warp_count_add(&cnt->n_leavers, left);
+  double nh = sc.fx.net_heat;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) nh += shfl_down_d(nh, d);
+  if ((threadIdx.x & 31) == 0 && nh != 0.) atomicAdd(&cnt->net_heat_to_ocean, nh);
+}
+
 // thermodynamics alone over [s0, s1): bergs flagged BF_ARRIVAL (migration) or, with
 // all_owned, every owned berg (the split path used when interactions are on).
 template <bool FOOTLOOSE, bool DIAG>

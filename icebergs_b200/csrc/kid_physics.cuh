@@ -339,6 +339,74 @@ __device__ __forceinline__ void accel_core(const DevParams& p, double M, double 
   if (PF(override_iceberg_velocities, 0)) { ax = 0.0; ay = 0.0; axn = 0.0; ayn = 0.0; bxn = 0.0; byn = 0.0; }
 }
 
+// accel I:1950-2442 as Runge_Kutta_stepping calls it (Runge_not_Verlet=.true.): alpha = 0, beta = 1,
+// C_N = 0 (I:2002-2005) -- explicit Coriolis at the stage velocity, implicit drag -- and the namelist's
+// use_new_predictive_corrective.  Free bergs only (interactions with RK are refused at init).  The
+// stepping default of the reference; kept out of line and in plain IEEE arithmetic.
+__device__ __noinline__ void accel_rk(const DevParams& p, double M, double T, double W, double L, double lat,
+                                      double uvel, double vvel, double uvel0, double vvel0, double dt, const Env& e,
+                                      double loc_dx, double& ax, double& ay, double& axn, double& ayn, double& bxn,
+                                      double& byn, bool& speeding) {
+  const double Cr0 = 0.06;
+  const bool use_new_pc = p.use_new_predictive_corrective != 0;
+  double u_star = uvel0 + (axn * (dt / 2.)), v_star = vvel0 + (ayn * (dt / 2.));
+  double uo = e.uo, vo = e.vo, ui = e.ui, vi = e.vi, ua = e.ua, va = e.va, ssh_x = e.ssh_x, ssh_y = e.ssh_y, hi = e.hi, od = e.od;
+  double f_cori = (p.grid_is_latlon && !p.use_f_plane) ? p.omega2 * sin(p.pi_180 * lat) : p.f_cori_plane;
+  double D = (p.rho_bergs / KID_RHO_SEAWATER) * T, F = T - D;
+  hi = fmin(hi, D);
+  double D_hi = fmax(0., D - hi);
+  double groundfrac, c_gnd;
+  if (p.h_to_init_grounding > 0.0) { groundfrac = 1.0 - (od - D) / p.h_to_init_grounding; groundfrac = fmin(fmax(groundfrac, 0.0), 1.0); }
+  else groundfrac = (D > od) ? 1.0 : 0.0;
+  c_gnd = (groundfrac > 0.0) ? (p.cdrag_grounding * W * L * groundfrac) / M : 0.0;
+  double uwave = ua - uo, vwave = va - vo;
+  double wmod = uwave * uwave + vwave * vwave;
+  double ampl = 0.5 * 0.02025 * wmod, Lwavelength = 0.32 * wmod, Lcutoff = 0.125 * Lwavelength, Ltop = 0.25 * Lwavelength;
+  double Cr = Cr0 * fmin(fmax(0., (L - Lcutoff) / ((Ltop - Lcutoff) + 1.e-30)), 1.);
+  double wave_rad = 0.5 * KID_RHO_SEAWATER / M * Cr * KID_GRAVITY * ampl * fmin(ampl, F) * (2. * W * L) / (W + L);
+  wmod = sqrt(ua * ua + va * va);
+  if (wmod != 0.) { uwave = ua / wmod; vwave = va / wmod; } else { uwave = 0.; vwave = 0.; wave_rad = 0.; }
+  double c_ocn = KID_RHO_SEAWATER / M * p.ocean_drag_scale * (0.5 * KID_CD_WV * W * (D_hi) + KID_CD_WH * W * L);
+  double c_atm = KID_RHO_AIR / M * (0.5 * KID_CD_AV * W * F + KID_CD_AH * W * L);
+  double c_ice = (fabs(hi) == 0.) ? 0. : KID_RHO_ICE / M * (0.5 * KID_CD_IV * W * hi);
+  if (fabs(ui) + fabs(vi) == 0.) c_ice = 0.;
+  axn = 0.; ayn = 0.;
+  bxn = -KID_GRAVITY * ssh_x + wave_rad * uwave;
+  byn = -KID_GRAVITY * ssh_y + wave_rad * vwave;
+  bxn = bxn + f_cori * vvel; byn = byn - f_cori * uvel;            // alpha = 0: explicit Coriolis, I:2173-2174
+  double uveln, vveln;
+  if (use_new_pc) { uveln = uvel0; vveln = vvel0; } else { uveln = uvel; vveln = vvel; }
+  for (int itloop = 1; itloop <= 2; itloop++) {
+    double drag_ocn, drag_atm, drag_ice, drag_gnd = c_gnd;
+    if (use_new_pc) {
+      drag_ocn = c_ocn * 0.5 * (sqrt((uveln - uo) * (uveln - uo) + (vveln - vo) * (vveln - vo)) + sqrt((uvel0 - uo) * (uvel0 - uo) + (vvel0 - vo) * (vvel0 - vo)));
+      drag_atm = c_atm * 0.5 * (sqrt((uveln - ua) * (uveln - ua) + (vveln - va) * (vveln - va)) + sqrt((uvel0 - ua) * (uvel0 - ua) + (vvel0 - va) * (vvel0 - va)));
+      drag_ice = c_ice * 0.5 * (sqrt((uveln - ui) * (uveln - ui) + (vveln - vi) * (vveln - vi)) + sqrt((uvel0 - ui) * (uvel0 - ui) + (vvel0 - vi) * (vvel0 - vi)));
+    } else {
+      double us = 0.5 * (uveln + uvel), vs = 0.5 * (vveln + vvel);
+      drag_ocn = c_ocn * sqrt((us - uo) * (us - uo) + (vs - vo) * (vs - vo));
+      drag_atm = c_atm * sqrt((us - ua) * (us - ua) + (vs - va) * (vs - va));
+      drag_ice = c_ice * sqrt((us - ui) * (us - ui) + (vs - vi) * (vs - vi));
+    }
+    double RHS_x = (axn / 2) + bxn, RHS_y = (ayn / 2) + byn;
+    RHS_x = RHS_x - drag_ocn * (u_star - uo) - drag_atm * (u_star - ua) - drag_ice * (u_star - ui) - drag_gnd * u_star;
+    RHS_y = RHS_y - drag_ocn * (v_star - vo) - drag_atm * (v_star - va) - drag_ice * (v_star - vi) - drag_gnd * v_star;
+    double lambda = drag_ocn + drag_atm + drag_ice + drag_gnd;
+    double A11 = 1. + dt * lambda, A22 = A11, A12 = -0.0 * dt * f_cori, A21 = 0.0 * dt * f_cori;
+    double detA = 1. / ((A11 * A22) - (A12 * A21));
+    ax = detA * (A22 * RHS_x - A12 * RHS_y);
+    ay = detA * (A11 * RHS_y - A21 * RHS_x);
+    uveln = u_star + dt * ax; vveln = v_star + dt * ay;
+  }
+  axn = 0.; ayn = 0.;                                              // I:2283-2296 with Runge_not_Verlet, C_N = 0
+  bxn = ax - (axn / 2); byn = ay - (ayn / 2);
+  if ((p.speed_limit > 0.) || (p.speed_limit == -1.)) {
+    double speed = sqrt(uveln * uveln + vveln * vveln);
+    if (speed > 0.) { double new_speed = loc_dx / dt * p.speed_limit; if (new_speed < speed && p.speed_limit > 0.) speeding = true; }
+  }
+  if (p.override_iceberg_velocities) { ax = 0.0; ay = 0.0; axn = 0.0; ayn = 0.0; bxn = 0.0; byn = 0.0; }
+}
+
 // tangent plane helpers I:7767-7816, I:8066-8099 (lat > 89 only)
 __device__ __noinline__ void tang_velocity(const DevParams& p, double lonn, double uvel3, double vvel3,
                                            double ax1, double ay1, double dt, double& uveln, double& vveln) {
@@ -361,6 +429,25 @@ __device__ __noinline__ void tang_position(const DevParams& p, double lon1, doub
   double rn = sqrt(xn * xn + yn * yn);
   latn = 90. - (r180_pi * rn / p.Rearth);
   lonn = r180_pi * acos(xn / rn) * f_sign1(yn);
+}
+
+// rotpos_to_tang / rotpos_from_tang / rotvec_to_tang / rotvec_from_tang I:7767-7816, I:8066-8099
+__device__ __noinline__ void rotpos_to_tang(const DevParams& p, double lon, double lat, double& x, double& y) {
+  double colat = 90. - lat, r = p.Rearth * (colat * p.pi_180);
+  x = r * cos(lon * p.pi_180); y = r * sin(lon * p.pi_180);
+}
+__device__ __noinline__ void rotpos_from_tang(const DevParams& p, double x, double y, double& lon, double& lat) {
+  double r = sqrt(x * x + y * y), r180_pi = 180. / p.pi;
+  lat = 90. - (r180_pi * r / p.Rearth);
+  lon = r180_pi * acos(x / r) * f_sign1(y);
+}
+__device__ __noinline__ void rotvec_to_tang(const DevParams& p, double lon, double uvel, double vvel, double& xdot, double& ydot) {
+  double clon = cos(lon * p.pi_180), slon = sin(lon * p.pi_180);
+  xdot = -slon * uvel - clon * vvel; ydot = clon * uvel - slon * vvel;
+}
+__device__ __noinline__ void rotvec_from_tang(const DevParams& p, double lon, double xdot, double ydot, double& uvel, double& vvel) {
+  double clon = cos(lon * p.pi_180), slon = sin(lon * p.pi_180);
+  uvel = -slon * xdot + clon * ydot; vvel = -clon * xdot - slon * ydot;
 }
 
 // I:7819-8063.  Returns bounced.  warn: count of the WARNING-level events.

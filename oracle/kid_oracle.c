@@ -1159,11 +1159,121 @@ static void update_verlet_position(Oracle* o, OBerg* berg) {
   berg->xi = xi; berg->yj = yj;
 }
 
+/* ------------------------------------------- Runge_Kutta_stepping I:7331 */
+/* (time_average_weight spreading inside the stages, I:7379/I:7414/..., is refused at create) */
+static void Runge_Kutta_stepping(Oracle* o, OBerg* berg, double* axn, double* ayn, double* bxn, double* byn,
+                                 double* uveln, double* vveln, double* lonn, double* latn, int* io, int* jo,
+                                 double* xio, double* yjo) {
+  const KidParams* p = &o->p;
+  double dt = p->dt, dt_2 = 0.5 * dt, dt_6 = dt / 6.;
+  int i = berg->ine, j = berg->jne, bounced = 0, any_bounce = 0;
+  double xi = berg->xi, yj = berg->yj;
+  int tang = (berg->lat > 89.) && p->grid_is_latlon;
+  int i1 = i, j1 = j;
+  *axn = berg->axn; *ayn = berg->ayn;
+  double axn1 = *axn, axn2 = *axn, axn3 = *axn, axn4 = *axn, ayn1 = *ayn, ayn2 = *ayn, ayn3 = *ayn, ayn4 = *ayn;
+  double x1 = 0, y1 = 0, xdot1 = 0, ydot1 = 0, xddot1 = 0, yddot1 = 0, xddot1n = 0, yddot1n = 0;
+  double x2, y2, xdot2 = 0, ydot2 = 0, xddot2 = 0, yddot2 = 0, xddot2n = 0, yddot2n = 0;
+  double x3, y3, xdot3 = 0, ydot3 = 0, xddot3 = 0, yddot3 = 0, xddot3n = 0, yddot3n = 0;
+  double x4, y4, xdot4 = 0, ydot4 = 0, xddot4 = 0, yddot4 = 0, xddot4n = 0, yddot4n = 0;
+  double dxdl1, dxdl2, dxdl3, dxdl4, dydl;
+  double lon1 = berg->lon, lat1 = berg->lat, lon2, lat2, lon3, lat3, lon4, lat4;
+  double uvel1, vvel1, uvel2, vvel2, uvel3, vvel3, uvel4, vvel4, u1, v1, u2, v2, u3, v3, u4, v4;
+  double ax1, ay1, ax2, ay2, ax3, ay3, ax4, ay4;
+  /* stage 1 */
+  if (tang) rotpos_to_tang(o, lon1, lat1, &x1, &y1);
+  convert_from_meters_to_grid(o, lat1, &dxdl1, &dydl);
+  uvel1 = berg->uvel; vvel1 = berg->vvel;
+  if (tang) rotvec_to_tang(o, lon1, uvel1, vvel1, &xdot1, &ydot1);
+  u1 = uvel1 * dxdl1; v1 = vvel1 * dydl;
+  accel(o, berg, i, j, xi, yj, lat1, uvel1, vvel1, uvel1, vvel1, dt_2, &ax1, &ay1, &axn1, &ayn1, bxn, byn);
+  if (tang) { rotvec_to_tang(o, lon1, ax1, ay1, &xddot1, &yddot1); rotvec_to_tang(o, lon1, axn1, ayn1, &xddot1n, &yddot1n); }
+  /* stage 2 */
+  if (tang) {
+    x2 = x1 + dt_2 * xdot1; y2 = y1 + dt_2 * ydot1;
+    xdot2 = xdot1 + dt_2 * xddot1; ydot2 = ydot1 + dt_2 * yddot1;
+    rotpos_from_tang(o, x2, y2, &lon2, &lat2);
+    rotvec_from_tang(o, lon2, xdot2, ydot2, &uvel2, &vvel2);
+  } else {
+    lon2 = lon1 + dt_2 * u1; lat2 = lat1 + dt_2 * v1;
+    uvel2 = uvel1 + dt_2 * ax1; vvel2 = vvel1 + dt_2 * ay1;
+  }
+  i = i1; j = j1; xi = berg->xi; yj = berg->yj;
+  adjust_index_and_ground(o, &lon2, &lat2, &uvel2, &vvel2, &i, &j, &xi, &yj, &bounced); any_bounce |= bounced;
+  convert_from_meters_to_grid(o, lat2, &dxdl2, &dydl);
+  u2 = uvel2 * dxdl2; v2 = vvel2 * dydl;
+  accel(o, berg, i, j, xi, yj, lat2, uvel2, vvel2, uvel1, vvel1, dt_2, &ax2, &ay2, &axn2, &ayn2, bxn, byn);
+  if (tang) { rotvec_to_tang(o, lon2, ax2, ay2, &xddot2, &yddot2); rotvec_to_tang(o, lon2, axn2, ayn2, &xddot2n, &yddot2n); }
+  /* stage 3 */
+  if (tang) {
+    x3 = x1 + dt_2 * xdot2; y3 = y1 + dt_2 * ydot2;
+    xdot3 = xdot1 + dt_2 * xddot2; ydot3 = ydot1 + dt_2 * yddot2;
+    rotpos_from_tang(o, x3, y3, &lon3, &lat3);
+    rotvec_from_tang(o, lon3, xdot3, ydot3, &uvel3, &vvel3);
+  } else {
+    lon3 = lon1 + dt_2 * u2; lat3 = lat1 + dt_2 * v2;
+    uvel3 = uvel1 + dt_2 * ax2; vvel3 = vvel1 + dt_2 * ay2;
+  }
+  i = i1; j = j1; xi = berg->xi; yj = berg->yj;
+  adjust_index_and_ground(o, &lon3, &lat3, &uvel3, &vvel3, &i, &j, &xi, &yj, &bounced); any_bounce |= bounced;
+  convert_from_meters_to_grid(o, lat3, &dxdl3, &dydl);
+  u3 = uvel3 * dxdl3; v3 = vvel3 * dydl;
+  accel(o, berg, i, j, xi, yj, lat3, uvel3, vvel3, uvel1, vvel1, dt, &ax3, &ay3, &axn3, &ayn3, bxn, byn);
+  if (tang) { rotvec_to_tang(o, lon3, ax3, ay3, &xddot3, &yddot3); rotvec_to_tang(o, lon3, axn3, ayn3, &xddot3n, &yddot3n); }
+  /* stage 4 */
+  if (tang) {
+    x4 = x1 + dt * xdot3; y4 = y1 + dt * ydot3;
+    xdot4 = xdot1 + dt * xddot3; ydot4 = ydot1 + dt * yddot3;
+    rotpos_from_tang(o, x4, y4, &lon4, &lat4);
+    rotvec_from_tang(o, lon4, xdot4, ydot4, &uvel4, &vvel4);
+  } else {
+    lon4 = lon1 + dt * u3; lat4 = lat1 + dt * v3;
+    uvel4 = uvel1 + dt * ax3; vvel4 = vvel1 + dt * ay3;
+  }
+  i = i1; j = j1; xi = berg->xi; yj = berg->yj;
+  adjust_index_and_ground(o, &lon4, &lat4, &uvel4, &vvel4, &i, &j, &xi, &yj, &bounced); any_bounce |= bounced;
+  convert_from_meters_to_grid(o, lat4, &dxdl4, &dydl);
+  u4 = uvel4 * dxdl4; v4 = vvel4 * dydl;
+  accel(o, berg, i, j, xi, yj, lat4, uvel4, vvel4, uvel1, vvel1, dt, &ax4, &ay4, &axn4, &ayn4, bxn, byn);
+  if (tang) { rotvec_to_tang(o, lon4, ax4, ay4, &xddot4, &yddot4); rotvec_to_tang(o, lon4, axn4, ayn4, &xddot4n, &yddot4n); }
+  /* combine */
+  if (tang) {
+    double xn = x1 + dt_6 * ((xdot1 + xdot4) + 2. * (xdot2 + xdot3));
+    double yn = y1 + dt_6 * ((ydot1 + ydot4) + 2. * (ydot2 + ydot3));
+    double xdotn = xdot1 + dt_6 * ((xddot1 + xddot4) + 2. * (xddot2 + xddot3));
+    double ydotn = ydot1 + dt_6 * ((yddot1 + yddot4) + 2. * (yddot2 + yddot3));
+    double xddotn = ((xddot1n + xddot4n) + 2. * (xddot2n + xddot3n)) / 6.;
+    double yddotn = ((yddot1n + yddot4n) + 2. * (yddot2n + yddot3n)) / 6.;
+    rotpos_from_tang(o, xn, yn, lonn, latn);
+    rotvec_from_tang(o, *lonn, xdotn, ydotn, uveln, vveln);
+    rotvec_from_tang(o, *lonn, xddotn, yddotn, axn, ayn);
+  } else {
+    *lonn = berg->lon + dt_6 * ((u1 + u4) + 2. * (u2 + u3));
+    *latn = berg->lat + dt_6 * ((v1 + v4) + 2. * (v2 + v3));
+    *uveln = berg->uvel + dt_6 * ((ax1 + ax4) + 2. * (ax2 + ax3));
+    *vveln = berg->vvel + dt_6 * ((ay1 + ay4) + 2. * (ay2 + ay3));
+    *axn = ((axn1 + axn4) + 2. * (axn2 + axn3)) / 6.;
+    *ayn = ((ayn1 + ayn4) + 2. * (ayn2 + ayn3)) / 6.;
+    *bxn = (((ax1 + ax4) + 2. * (ax2 + ax3)) / 6) - (*axn / 2);
+    *byn = (((ay1 + ay4) + 2. * (ay2 + ay3)) / 6) - (*ayn / 2);
+  }
+  i = i1; j = j1; xi = berg->xi; yj = berg->yj;
+  adjust_index_and_ground(o, lonn, latn, uveln, vveln, &i, &j, &xi, &yj, &bounced); any_bounce |= bounced;
+  if (!is_point_in_cell(o, *lonn, *latn, i, j)) o_warn(o, "evolve_iceberg, out of cell at end!");
+  if (any_bounce) {
+#ifdef _OPENMP
+#pragma omp atomic
+#endif
+    o->cnt.n_bounced++;
+  }
+  *io = i; *jo = j; *xio = xi; *yjo = yj;
+}
+
 /* ------------------------------------------------ evolve_icebergs I:7081 */
 static void evolve_icebergs(Oracle* o) {
   const KidDomain* d = &o->d;
   int interactive = o->p.interactive_icebergs_on;
-  if (o->p.runge_not_verlet) { o_fatal(o, "oracle: Runge-Kutta stepping is not restated (Verlet only)"); return; }
+  const int rk = o->p.runge_not_verlet;
 #ifdef _OPENMP
 #pragma omp parallel for schedule(dynamic, 4) num_threads(o->nthreads) if (o->nthreads > 1)
 #endif
@@ -1173,12 +1283,15 @@ static void evolve_icebergs(Oracle* o) {
         if (berg->static_berg < 0.5) {
           if (!is_point_in_cell(o, berg->lon, berg->lat, berg->ine, berg->jne))
             o_warn(o, "evolve_iceberg, berg is not in proper starting cell");
-          double axn, ayn, bxn, byn, uveln, vveln;
-          verlet_stepping(o, berg, &axn, &ayn, &bxn, &byn, &uveln, &vveln);
+          double axn, ayn, bxn, byn, uveln, vveln, lonn = 0., latn = 0., xi = 0., yj = 0.;
+          int i = 0, j = 0;
+          if (rk) Runge_Kutta_stepping(o, berg, &axn, &ayn, &bxn, &byn, &uveln, &vveln, &lonn, &latn, &i, &j, &xi, &yj);
+          else verlet_stepping(o, berg, &axn, &ayn, &bxn, &byn, &uveln, &vveln);
           if (o->p.override_iceberg_velocities) { uveln = o->p.u_override; vveln = o->p.v_override; }
           berg->axn = axn; berg->ayn = ayn; berg->bxn = bxn; berg->byn = byn;
           berg->uvel = uveln; berg->vvel = vveln;
-          if (!interactive) update_verlet_position(o, berg);
+          if (rk) { berg->lon = lonn; berg->lat = latn; berg->ine = i; berg->jne = j; berg->xi = xi; berg->yj = yj; }
+          else if (!interactive) update_verlet_position(o, berg);
         }
       }
   if (interactive) {
@@ -1186,7 +1299,7 @@ static void evolve_icebergs(Oracle* o) {
       for (int grdi = d->isc; grdi <= d->iec; grdi++)
         for (OBerg* berg = G(o, list, grdi, grdj); berg; berg = berg->next)
           if (berg->static_berg < 0.5) {
-            update_verlet_position(o, berg);
+            if (!rk) update_verlet_position(o, berg);
             berg->uvel_old = berg->uvel; berg->vvel_old = berg->vvel;
             berg->lon_old = berg->lon; berg->lat_old = berg->lat;
           }
@@ -2065,7 +2178,6 @@ Oracle* oracle_create(const KidParams* p, const KidDomain* dom, int32_t year, do
   if (p->time_average_weight) o_fatal(o, "oracle: time_average_weight is not restated");
   o->iceberg_counter_grd = (int32_t*)calloc(n2, sizeof(int32_t));
   o->list = (OBerg**)calloc(n2, sizeof(OBerg*));
-  if (p->runge_not_verlet) o_fatal(o, "oracle: only Verlet (Runge_not_Verlet=.false.) is restated");
   if (p->tidal_drift > 0.) o_fatal(o, "oracle: tidal_drift needs the FMS random number stream (external)");
   if (p->add_iceberg_thickness_to_ssh) o_fatal(o, "oracle: add_iceberg_thickness_to_SSH needs spread_mass (next row)");
   int nic = d->iec - d->isc + 1, njc = d->jec - d->jsc + 1;

@@ -192,3 +192,33 @@ def test_ice_shelf_style_basal_melt(over):
     m0 = case.bergs["mass"].sum()
     assert b.get_bergs(["mass"])["mass"].sum() < 0.999 * m0       # the basal melt did act
     api.icebergs_end(b)
+
+
+@pytest.mark.parametrize("over", [dict(), dict(use_new_predictive_corrective=1, old_bug_bilin=0), dict(speed_limit=0.05)])
+def test_runge_kutta_stepping(over):
+    """Runge_not_Verlet=.true. (the namelist default, F:733): Runge_Kutta_stepping I:7331-7679."""
+    case = Case(96, 48, 12000, runge_not_verlet=1, **over)
+    b, o = both(case)
+    for step in range(3):
+        run_gpu(b, case)
+        run_oracle(o, case)
+        compare_state(b, o, f"RK4 {over} step {step}", rtol=1e-9)
+    for fid in FLUX_FIELDS:
+        assert grid_rel(b.grid_field(fid), o.grid_field(fid)) < 1e-9
+    cg, co = b.counters(), o.counters()
+    assert cg["nspeeding_tickets"] == co["nspeeding_tickets"]
+    api.icebergs_end(b)
+
+
+def test_runge_kutta_bounce_and_wrap():
+    case = Case(96, 48, 8000, dt=2 * 86400.0, runge_not_verlet=1)
+    f = case.forcing
+    fast = dict(uo=np.full_like(f["uo"], 1.2), vo=np.full_like(f["vo"], 0.15), tauxa=np.full_like(f["tauxa"], 15.0))
+    b, o = both(case)
+    for step in range(4):
+        run_gpu(b, case, **fast)
+        run_oracle(o, case, **fast)
+        compare_state(b, o, f"RK4 bounce/wrap step {step}", rtol=1e-8)
+    co, cg = o.counters(), b.counters()
+    assert co["n_bounced"] > 20 and cg["n_bounced"] == co["n_bounced"] and co["n_received"] > 0
+    api.icebergs_end(b)
