@@ -7,6 +7,7 @@ import pytest
 from common import (COMPARE_F64, Case, assert_bergs_match, by_id, grid_rel, rel_err, run_gpu, run_oracle)
 from icebergs_b200 import _cdefs as D
 from icebergs_b200 import api
+from icebergs_b200 import synthetic as S
 
 pytestmark = pytest.mark.gpu
 
@@ -221,4 +222,43 @@ def test_runge_kutta_bounce_and_wrap():
         compare_state(b, o, f"RK4 bounce/wrap step {step}", rtol=1e-8)
     co, cg = o.counters(), b.counters()
     assert co["n_bounced"] > 20 and cg["n_bounced"] == co["n_bounced"] and co["n_received"] > 0
+    api.icebergs_end(b)
+
+
+class PolarGrid(S.Grid):
+    """Ocean all the way to the north pole: exercises the tangent-plane stepping above 89N
+    (I:7767-7816, I:8066-8099) and the polar branch of pos_within_cell (F:6359-6405)."""
+
+    def wet(self, ring=1):
+        _, latc = self.centre_lonlat(ring)
+        return ((latc > 60.0) & (latc < 90.0)).astype(np.float64)
+
+
+@pytest.mark.parametrize("rk", [0, 1])
+def test_polar_tangent_plane(rk):
+    # 0.47-degree rows: the band 89N..89.5N lies below the (degenerate) row of cells that touch the pole
+    gni, gnj = 48, 384
+    grid = PolarGrid(gni, gnj)
+    case = Case(gni, gnj, 0, grid=grid, runge_not_verlet=rk, old_bug_bilin=0, capacity=16384)
+    rng = np.random.default_rng(3)
+    n = 4000
+    lat = rng.uniform(88.3, 89.45, n)
+    lon = rng.uniform(0.5, 359.5, n)
+    base, _ = S.Grid(96, 48).seed_bergs(n)
+    cols = {k: v for k, v in base.items() if k not in ("ine", "jne", "id")}
+    cols["lon"], cols["lat"] = lon, lat
+    cols["start_lon"], cols["start_lat"] = lon.copy(), lat.copy()
+    cols["uvel"] = rng.uniform(-0.3, 0.3, n)
+    cols["vvel"] = rng.uniform(0.0, 0.4, n)           # heading for the pole
+    case.bergs, case.counter = cols, np.zeros((gnj, gni), dtype=np.int32)
+    b, o = case.make_gpu(), case.make_oracle()
+    f = case.forcing
+    north = dict(vo=np.full_like(f["vo"], 0.3))
+    above = 0
+    for step in range(6):
+        run_gpu(b, case, **north)
+        run_oracle(o, case, **north)
+        compare_state(b, o, f"polar rk={rk} step {step}", rtol=1e-8)
+        above = max(above, int(np.sum(o.get_bergs(["lat"])["lat"] > 89.0)))
+    assert above > 50, f"only {above} bergs above 89N: the tangent plane was not exercised"
     api.icebergs_end(b)
