@@ -82,7 +82,8 @@ struct kid_handle {
   long long ghost_cap = 0;
   int ghost_rec_w = 0;
   int32_t *d_gcounts = nullptr, *d_goffsets = nullptr, *d_gcursor = nullptr;   // [9]
-  int tables_valid = 0, bond_lengths_set = 0;                // cell_start/cell_count describe the current slot order
+  int tables_valid = 0, bond_lengths_set = 0, conglom_set = 0;
+  int* d_changed = nullptr;                // cell_start/cell_count describe the current slot order
   void* spare_b8 = nullptr;            // spare column for the bond arrays (8 B entries)
   SpreadFields sf;                     // mass / area / momentum on the ocean grid
   SpreadParams sp;
@@ -522,9 +523,7 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   else if (pin->tidal_drift > 0.) unsupported = "tidal_drift>0 needs the FMS random number stream";
   else if (pin->add_iceberg_thickness_to_ssh) unsupported = "add_iceberg_thickness_to_SSH is not implemented";
   else if (pin->mts || pin->dem) unsupported = "MTS/DEM stepping is not implemented in this build";
-  else if ((pin->interactive_icebergs_on || pin->iceberg_bonds_on) &&
-           (pin->contact_distance > 0. || (pin->contact_spring_coef > 0. && pin->contact_spring_coef != pin->spring_coef)))
-    unsupported = "contact_distance>0 / contact_spring_coef != spring_coef (conglomerate contact search) is not implemented in this build";
+  else if (pin->contact_distance > 0. && pin->halo - 1 < 1) unsupported = "contact_distance>0 needs halo >= 2";
   else if (pin->iceberg_bonds_on && !pin->interactive_icebergs_on) unsupported = "iceberg_bonds_on needs interactive_icebergs_on";
   else if (pin->iceberg_bonds_on && (pin->max_bonds < 1 || pin->max_bonds > 12)) unsupported = "max_bonds must be 1..12";
   else if (pin->footloose && pin->displace_fl_bergs) unsupported = "displace_fl_bergs needs the FMS random number stream: set displace_fl_bergs=0";
@@ -695,6 +694,29 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
     for (long long k = 0; k < n2 && ident; k++) ident = (gcos[k] == 1.) && (gsin[k] == 0.);
     h->no_rotation = ident ? 1 : 0;
   }
+  // contact_cells_lon/lat, F:1492-1519
+  q->contact_cells_lon = 1; q->contact_cells_lat = 1;
+  if (q->contact_distance > 0.) {
+    const double pi_180 = q->pi / 180.;
+    double dx_dlon = 1., dy_dlat = q->grid_is_latlon ? pi_180 * q->Rearth : 1.;
+    int maxk = 0;
+    for (int j = d->jsd; j <= d->jed; j++) for (int i = d->isd; i <= d->ied; i++) {
+      if (q->grid_is_latlon) dx_dlon = pi_180 * q->Rearth * cos(glat[IDX(i, j)] * pi_180);
+      double lon_ref = glon[IDX(i, j)];
+      int k = 0;
+      while ((k + i) < d->ied) {
+        k++;
+        double ddx = (glon[IDX(k + i, j)] - lon_ref) * dx_dlon;
+        if (k > maxk) maxk = k;
+        if (ddx >= q->contact_distance) break;
+      }
+    }
+    double ddy = (glat[IDX(d->isc, d->jsc + 1)] - glat[IDX(d->isc, d->jsc)]) * dy_dlat;
+    q->contact_cells_lon = std::max(maxk, 1);
+    q->contact_cells_lat = std::max((int)ceil(q->contact_distance / ddy), 1);
+    if (q->halo - 1 < q->contact_cells_lon || q->halo - 1 < q->contact_cells_lat)
+      return fail(h, KID_ERR_ARG, "kid_init: halo - 1 must cover contact_cells (F:1522-1530): increase halo");
+  }
   // ---- device grid
   DevGrid& g = h->g;
   memset(&g, 0, sizeof(g));
@@ -790,6 +812,9 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
       CK(cudaMemsetAsync(b.bond_other_jne, 0, sizeof(int32_t) * nb, h->stream));
       CK(cudaMemsetAsync(b.bond_length, 0, sizeof(double) * nb, h->stream));
     }
+    CK(cudaMalloc(&b.conglom_id, sizeof(int32_t) * h->capacity));
+    CK(cudaMemsetAsync(b.conglom_id, 0, sizeof(int32_t) * h->capacity, h->stream));
+    CK(cudaMalloc(&h->d_changed, sizeof(int)));
     h->ghost_rec_w = PACK_W + 3 * b.max_bonds;
     h->ghost_cap = std::max<long long>(4096, h->capacity / 2);
     CK(cudaMalloc(&h->gsend, sizeof(double) * h->ghost_rec_w * h->ghost_cap));
@@ -870,7 +895,7 @@ extern "C" int32_t kid_end(kid_t** hp) {
   cudaFree(h->halo_send); cudaFree(h->halo_recv);
   cudaFree(h->gsend); cudaFree(h->grecv); cudaFree(h->d_gcounts); cudaFree(h->d_goffsets); cudaFree(h->d_gcursor);
   cudaFree(h->b.bond_other_id); cudaFree(h->b.bond_other_slot); cudaFree(h->b.bond_other_ine);
-  cudaFree(h->b.bond_other_jne); cudaFree(h->b.bond_length);
+  cudaFree(h->b.bond_other_jne); cudaFree(h->b.bond_length); cudaFree(h->b.conglom_id); cudaFree(h->d_changed);
   for (auto& e : h->ev) cudaEventDestroy(e);
   for (auto& e : h->ev_pool) cudaEventDestroy(e);
   cudaStreamDestroy(h->stream);
@@ -1040,6 +1065,22 @@ static int rebuild_ghosts(kid_t* h) {
 
 static int sort_bergs(kid_t* h);
 
+// set_conglom_ids F:2601-2646 (only needed by the conglomerate-contact branch of interactive_force, I:512)
+static int set_conglom_ids(kid_t* h) {
+  if (!((h->p.contact_distance > 0.) || (h->p.contact_spring_coef != h->p.spring_coef))) return KID_OK;
+  LAUNCH(h, k_conglom_init, h->n_slots, 256, h->b, h->n_slots);
+  if (h->b.max_bonds == 0) return KID_OK;
+  for (int it = 0; it < 100000; it++) {
+    int changed = 0;
+    CK(cudaMemsetAsync(h->d_changed, 0, sizeof(int), h->stream));
+    for (int rep = 0; rep < 8; rep++) LAUNCH(h, k_conglom_sweep, h->n_slots, 256, h->b, h->n_slots, h->d_changed);
+    CK(cudaMemcpyAsync(&changed, h->d_changed, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (!changed) break;
+  }
+  return KID_OK;
+}
+
 // the tail of an interactive step (I:5463-5478): halo copies, update_latlon (inside
 // connect_all_bonds F:4994 when bonds are on, directly otherwise), re-sort, reconnect bonds
 static int refresh_interactive_state(kid_t* h) {
@@ -1053,7 +1094,7 @@ static int refresh_interactive_state(kid_t* h) {
     CellTable ct{h->cell_start, h->cell_count};
     LAUNCH(h, k_connect_bonds, h->n_slots, 128, h->g, h->b, ct, h->dcnt, h->n_slots);
   }
-  return KID_OK;
+  return set_conglom_ids(h);
 }
 
 extern "C" int32_t kid_sort_bergs(kid_t* h) {
@@ -1542,6 +1583,13 @@ static int step_core(kid_t* h) {
       int rc = sort_bergs(h);
       if (rc) return rc;
       if (h->b.max_bonds > 0) { CellTable ct{h->cell_start, h->cell_count}; LAUNCH(h, k_connect_bonds, h->n_slots, 128, h->g, h->b, ct, h->dcnt, h->n_slots); }
+      rc = set_conglom_ids(h);
+      if (rc) return rc;
+    }
+    if (!h->conglom_set) {                                 // first visit, I:5416
+      int rc = set_conglom_ids(h);
+      if (rc) return rc;
+      h->conglom_set = 1;
     }
     if (h->b.max_bonds > 0 && !h->bond_lengths_set) {      // first visit, I:5420
       LAUNCH(h, k_orig_bond_length, h->n_slots, 128, h->b, h->n_slots);

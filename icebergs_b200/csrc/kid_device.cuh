@@ -132,6 +132,7 @@ struct DevBergs {
   // other_id == 0 marks an empty entry, other_slot is re-resolved after every sort (connect_all_bonds F:4963)
   int32_t max_bonds, pad_;
   int64_t* bond_other_id;
+  int32_t* conglom_id;        // connected component of the bond graph (set_conglom_ids F:2601); 0 = halo copy not reached
   int32_t *bond_other_slot, *bond_other_ine, *bond_other_jne;
   double* bond_length;
 };

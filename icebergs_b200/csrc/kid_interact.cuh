@@ -20,8 +20,11 @@ namespace kid {
 struct CellTable { const int32_t* start; const int32_t* count; };
 
 // I:611-804.  s = primary berg, o = other berg (slots).
+// crit: 0 = no c_crit_dist argument, 1 = c_crit_dist=.true. (contact inside a conglomerate: radii only, the
+// bond spring constant, I:716-719)
 __device__ __forceinline__ void calculate_force(const DevBergs& b, const DevParams& p, long long s, long long o,
-                                                IAcc& A, double u0, double v0, double u1, double v1, bool bonded) {
+                                                IAcc& A, double u0, double v0, double u1, double v1, bool bonded,
+                                                int crit = 0) {
   if (b.id[s] == b.id[o]) return;
   if (b.f64[C_FL_K][s] == -1. || b.f64[C_FL_K][o] == -1.) return;
   double lon1 = b.f64[C_LON_OLD][s], lat1 = b.f64[C_LAT_OLD][s];
@@ -41,6 +44,7 @@ __device__ __forceinline__ void calculate_force(const DevBergs& b, const DevPara
   double M_min = M1 < M2 ? M1 : M2;
   double crit_dist, spring_coef;
   if (bonded) { crit_dist = R1 + R2; spring_coef = p.spring_coef; }
+  else if (crit == 1) { crit_dist = R1 + R2; spring_coef = p.spring_coef; }
   else { spring_coef = p.contact_spring_coef; crit_dist = fmax(R1 + R2, p.contact_distance); }
   double radial_damping_coef = p.radial_damping_coef, tangental_damping_coef = p.tangental_damping_coef;
   if (p.critical_interaction_damping_on) {
@@ -49,7 +53,8 @@ __device__ __forceinline__ void calculate_force(const DevBergs& b, const DevPara
   }
   bool tbonded = bonded;
   // STS with contact_distance = 0 and one spring constant: a bond only pulls (I:741-748)
-  if (bonded && !(r_dist > crit_dist)) tbonded = false;
+  if (bonded && !(p.mts || (p.contact_distance > 0.) || (p.contact_spring_coef != p.spring_coef)))
+    if (!(r_dist > crit_dist)) tbonded = false;
   if ((r_dist > 0.) && (tbonded || (r_dist < crit_dist && !bonded))) {
     double accel_spring = spring_coef * (M_min / M1) * (crit_dist - r_dist);
     A.IA_x = A.IA_x + (accel_spring * (r_dist_x / r_dist));
@@ -80,6 +85,46 @@ __device__ __forceinline__ void interactive_force(const DevGrid& g, const DevBer
                                                   double u0, double v0, double u1, double v1) {
   A.IA_x = A.IA_y = A.P11 = A.P12 = A.P21 = A.P22 = A.Pu_x = A.Pu_y = 0.;
   if (b.f64[C_FL_K][s] == -1.) return;
+  if ((p.contact_distance > 0.) || (p.contact_spring_coef != p.spring_coef)) {
+    // I:512-576 (STS): bonded partners through the bonds, the rest of the berg's own conglomerate by radius
+    // contact (partners excluded -- the reference marks them by negating their id), other conglomerates
+    // within contact_cells with the contact spring
+    const int32_t my_cong = b.conglom_id[s];
+    if (p.iceberg_bonds_on) {
+      for (int k = b.max_bonds - 1; k >= 0; k--) {
+        long long slot = (long long)k * b.capacity + s;
+        if (b.bond_other_id[slot] == 0) continue;
+        int32_t o = b.bond_other_slot[slot];
+        if (o >= 0) calculate_force(b, p, s, o, A, u0, v0, u1, v1, true);
+      }
+      for (int grdj = max(j - 2, g.jsd + 1); grdj <= min(j + 2, g.jed); grdj++)
+        for (int grdi = max(i - 2, g.isd + 1); grdi <= min(i + 2, g.ied); grdi++) {
+          int c = gidx(g, grdi, grdj);
+          int n = ct.count[c];
+          long long o0 = ct.start[c];
+          for (int k = 0; k < n; k++) {
+            long long o = o0 + k;
+            if (b.conglom_id[o] != my_cong) continue;
+            bool partner = false;
+            for (int q = 0; q < b.max_bonds; q++) {
+              long long slot = (long long)q * b.capacity + s;
+              if (b.bond_other_id[slot] != 0 && b.bond_other_slot[slot] == (int32_t)o) partner = true;
+            }
+            if (!partner) calculate_force(b, p, s, o, A, u0, v0, u1, v1, false, 1);
+          }
+        }
+    }
+    const int nc_x = p.contact_cells_lon, nc_y = p.contact_cells_lat;
+    for (int grdj = max(j - nc_y, g.jsd); grdj <= min(j + nc_y, g.jed); grdj++)
+      for (int grdi = max(i - nc_x, g.isd); grdi <= min(i + nc_x, g.ied); grdi++) {
+        int c = gidx(g, grdi, grdj);
+        int n = ct.count[c];
+        long long o0 = ct.start[c];
+        for (int k = 0; k < n; k++)
+          if (b.conglom_id[o0 + k] != my_cong) calculate_force(b, p, s, o0 + k, A, u0, v0, u1, v1, false);
+      }
+    return;
+  }
   for (int grdj = j - 1; grdj <= j + 1; grdj++)
     for (int grdi = i - 1; grdi <= i + 1; grdi++) {
       if (grdi < g.isd || grdi > g.ied || grdj < g.jsd || grdj > g.jed) continue;
@@ -344,6 +389,30 @@ __global__ void k_connect_bonds(const __grid_constant__ DevGrid g, const __grid_
     b.bond_other_slot[slot] = o;
     if (o < 0 && !(b.flags[s] & BF_HALO)) atomicOr(&cnt->error_flags, 256u);   // 'A non-halo bond is missing!!!' F:5063
   }
+}
+
+// set_conglom_ids F:2601-2646: connected components of the bond graph by label propagation (the reference
+// flood-fills recursively, F:2649; only equality of labels is ever tested, so any labelling of the same
+// components is equivalent).  Owned bergs start from slot+1; copies that no owned berg reaches stay 0.
+__global__ void k_conglom_init(const __grid_constant__ DevBergs b, long long n_slots) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  uint8_t f = b.flags[s];
+  b.conglom_id[s] = ((f & BF_ALIVE) && !(f & BF_HALO)) ? (int32_t)(s + 1) : 0;
+}
+__global__ void k_conglom_sweep(const __grid_constant__ DevBergs b, long long n_slots, int* __restrict__ changed) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots || !(b.flags[s] & BF_ALIVE)) return;
+  int32_t best = b.conglom_id[s];
+  for (int k = 0; k < b.max_bonds; k++) {
+    long long slot = (long long)k * b.capacity + s;
+    if (b.bond_other_id[slot] == 0) continue;
+    int32_t o = b.bond_other_slot[slot];
+    if (o < 0) continue;
+    int32_t l = b.conglom_id[o];
+    if (l != 0 && (best == 0 || l < best)) best = l;
+  }
+  if (best != b.conglom_id[s]) { b.conglom_id[s] = best; *changed = 1; }
 }
 
 // initialize_iceberg_bonds I:356-441: O(N^2) distance test over every berg of the data domain, in the

@@ -114,3 +114,21 @@ def test_unbonded_contact_in_a_crowd():
     assert co["n_received"] > 0, "no berg crossed the periodic seam"
     assert p.b.count_bergs() == p.o.count_bergs()
     p.end()
+
+
+@pytest.mark.parametrize("bonds", [True, False])
+def test_conglomerate_contact_branch(bonds):
+    """contact_distance > 0 with its own contact_spring_coef (the settings of the MTS_KID / iKID
+    collision namelists, here with the single-time-step scheme): bonded partners through the bonds,
+    the rest of the conglomerate by radius contact, other conglomerates within contact_cells with the
+    contact spring (I:512-576); conglomerates labelled by set_conglom_ids (F:2601)."""
+    over = dict(contact_distance=1.75e3, contact_spring_coef=1.0e-7)
+    if not bonds:
+        over.update(iceberg_bonds_on=0, manually_initialize_bonds=0, max_bonds=0)
+    params = lambda: S.collision_params(api.default_params, **over)
+    p = Pair(S.collision_bergs(), params, bonds=bonds)
+    for k in range(8):
+        p.step(50)
+        p.check(f"contact branch bonds={bonds}, {50 * (k + 1)} steps", rtol=1e-7)
+    assert p.b.count_bergs() == p.o.count_bergs()
+    p.end()
