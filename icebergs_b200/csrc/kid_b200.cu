@@ -434,6 +434,7 @@ static int halo_exchange(kid_t* h, double* const* fields, int nf) {
 // of bergs that arrived in n_recv; they occupy slots [n_slots, n_slots + n_recv) flagged BF_ARRIVAL.
 static int exchange_bergs(kid_t* h, long long* n_recv_out) {
   const int nr = h->d.nranks, me = h->d.rank;
+  const long long W = PACK_W + 3 * h->b.max_bonds;      // record width: berg + its bonds
   *n_recv_out = 0;
   CK(cudaMemsetAsync(h->d_send_counts, 0, sizeof(int32_t) * nr, h->stream));
   CK(cudaMemsetAsync(h->d_cursor, 0, sizeof(int32_t) * nr, h->stream));
@@ -446,24 +447,24 @@ static int exchange_bergs(kid_t* h, long long* n_recv_out) {
   for (int q = 0; q < nr; q++) {
     h->h_offsets[q] = (int32_t)n_send;
     long long c = h->h_all_counts[(size_t)me * nr + q];
-    if (c > 0) sends.push_back({q, 100, h->sendbuf + (size_t)n_send * PACK_W, c * PACK_W});
+    if (c > 0) sends.push_back({q, 100, h->sendbuf + (size_t)n_send * W, c * W});
     n_send += c;
   }
   for (int q = 0; q < nr; q++) {
     long long c = h->h_all_counts[(size_t)q * nr + me];
-    if (c > 0) recvs.push_back({q, 100, h->recvbuf + (size_t)n_recv * PACK_W, c * PACK_W});
+    if (c > 0) recvs.push_back({q, 100, h->recvbuf + (size_t)n_recv * W, c * W});
     n_recv += c;
   }
   if (n_send > h->xbuf_cap || n_recv > h->xbuf_cap) return fail(h, KID_ERR_CAPACITY, "kid: berg exchange buffer capacity exceeded");
   if (h->n_slots + n_recv > h->capacity) return fail(h, KID_ERR_CAPACITY, "kid: berg store capacity exceeded by arrivals");
   CK(cudaMemcpyAsync(h->d_offsets, h->h_offsets, sizeof(int32_t) * nr, cudaMemcpyHostToDevice, h->stream));
   k_pack_leavers<<<32, 256, 0, h->stream>>>(h->layout, h->b, h->b.leaver_list, h->leaver_dest, h->dcnt, (int32_t)h->b.leaver_cap, h->d_offsets,
-                                           h->d_cursor, h->sendbuf); h->launches++;
+                                           h->d_cursor, h->sendbuf, (int)W); h->launches++;
   CK(cudaMemsetAsync(&h->dcnt->n_leaver_list, 0, sizeof(unsigned long long), h->stream));
   rc = comm_exchange(h, sends, recvs);
   if (rc) return rc;
   if (n_recv > 0) {
-    LAUNCH(h, k_unpack_arrivals, n_recv, 128, h->g, h->b, h->dp, h->dcnt, h->recvbuf, n_recv, h->n_slots);
+    LAUNCH(h, k_unpack_arrivals, n_recv, 128, h->g, h->b, h->dp, h->dcnt, h->recvbuf, n_recv, h->n_slots, (int)W);
     unsigned long long nn = (unsigned long long)(h->n_slots + n_recv);
     CK(cudaMemcpyAsync(&h->dcnt->n_slots, &nn, sizeof(nn), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));   // nn is a stack variable
@@ -527,8 +528,6 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   else if (pin->iceberg_bonds_on && !pin->interactive_icebergs_on) unsupported = "iceberg_bonds_on needs interactive_icebergs_on";
   else if (pin->iceberg_bonds_on && (pin->max_bonds < 1 || pin->max_bonds > 12)) unsupported = "max_bonds must be 1..12";
   else if (pin->footloose && pin->displace_fl_bergs) unsupported = "displace_fl_bergs needs the FMS random number stream: set displace_fl_bergs=0";
-  else if (pin->footloose && dom->nranks > 1) unsupported = "footloose calving across ranks is not implemented in this build";
-  else if (pin->iceberg_bonds_on && dom->nranks > 1) unsupported = "bonds across ranks are not implemented in this build";
   else if (pin->time_average_weight && pin->add_weight_to_ocean) unsupported = "time_average_weight is not implemented";
   else if (dom->cyclic_y) unsupported = "cyclic y is not implemented";
   else if (pin->halo < 2) unsupported = "halo must be >= 2";
@@ -829,8 +828,8 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
     b.leaver_cap = h->xbuf_cap;
     CK(cudaMalloc(&b.leaver_list, sizeof(int32_t) * b.leaver_cap));
     CK(cudaMalloc(&h->leaver_dest, sizeof(int32_t) * b.leaver_cap));
-    CK(cudaMalloc(&h->sendbuf, sizeof(double) * PACK_W * h->xbuf_cap));
-    CK(cudaMalloc(&h->recvbuf, sizeof(double) * PACK_W * h->xbuf_cap));
+    CK(cudaMalloc(&h->sendbuf, sizeof(double) * (PACK_W + 3 * (q->iceberg_bonds_on ? q->max_bonds : 0)) * h->xbuf_cap));
+    CK(cudaMalloc(&h->recvbuf, sizeof(double) * (PACK_W + 3 * (q->iceberg_bonds_on ? q->max_bonds : 0)) * h->xbuf_cap));
     CK(cudaMalloc(&h->d_send_counts, sizeof(int32_t) * nr));
     CK(cudaMalloc(&h->d_cursor, sizeof(int32_t) * nr));
     CK(cudaMalloc(&h->d_offsets, sizeof(int32_t) * nr));
@@ -1619,7 +1618,8 @@ static int step_core(kid_t* h) {
     if (rc) return rc;
     if (n_recv > 0) {
       long long s0 = h->n_slots, s1 = h->n_slots + n_recv;
-      if (h->p.melt_diagnostics) { LAUNCH(h, (k_thermo_range<false, true>), n_recv, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s0, s1, 0); }
+      if (fl) { /* thermodynamics of every berg follows footloose_calving below */ }
+      else if (h->p.melt_diagnostics) { LAUNCH(h, (k_thermo_range<false, true>), n_recv, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s0, s1, 0); }
       else { LAUNCH(h, (k_thermo_range<false, false>), n_recv, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s0, s1, 0); }
       h->n_slots = s1;
       h->dirty_appended += n_recv;

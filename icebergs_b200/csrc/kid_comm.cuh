@@ -115,7 +115,7 @@ __global__ void k_leaver_dest(const __grid_constant__ DevLayout L, const int32_t
 __global__ void k_pack_leavers(const __grid_constant__ DevLayout L, const __grid_constant__ DevBergs b, const int32_t* __restrict__ list,
                                const int32_t* __restrict__ dest, const DevCounters* __restrict__ cnt,
                                int32_t list_cap, const int32_t* __restrict__ offsets /* [nranks] */,
-                               int32_t* __restrict__ cursor /* [nranks], zeroed */, double* __restrict__ sendbuf) {
+                               int32_t* __restrict__ cursor /* [nranks], zeroed */, double* __restrict__ sendbuf, int rec_w) {
   long long n = (long long)cnt->n_leaver_list;
   if (n > list_cap) n = list_cap;
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
@@ -125,10 +125,18 @@ __global__ void k_pack_leavers(const __grid_constant__ DevLayout L, const __grid
     b.flags[s] = 0;
     if (d < 0) continue;                     // left the model through an open boundary
     int pos = offsets[d] + atomicAdd(&cursor[d], 1);
-    double* rec = sendbuf + (size_t)pos * PACK_W;
+    double* rec = sendbuf + (size_t)pos * rec_w;
 #pragma unroll
     for (int c = 0; c < C_NBASE; c++) rec[PK_F64_0 + c] = b.f64[c][s];
     rec[PK_ID] = __longlong_as_double(b.id[s]);
+    for (int k = 0; k < b.max_bonds; k++) {          // the bonds travel with the berg, F:3336-3354
+      long long slot = (long long)k * b.capacity + s;
+      double* br = rec + PACK_W + 3 * k;
+      br[0] = __longlong_as_double(b.bond_other_id[slot]);
+      br[1] = __longlong_as_double(((long long)(unsigned)b.bond_other_ine[slot] << 32) | (unsigned)b.bond_other_jne[slot]);
+      br[2] = b.bond_length[slot];
+      b.bond_other_id[slot] = 0;
+    }
     int ci = b.ine[s];       // the owner's own index of the cell: one period off when the berg crossed the seam
     if (L.cyclic_x && (ci < 1 || ci > L.gni)) ci = ((ci - 1) % L.gni + L.gni) % L.gni + 1;
     rec[PK_INE_JNE] = __longlong_as_double(((long long)(unsigned)ci << 32) | (unsigned)b.jne[s]);
@@ -143,11 +151,20 @@ __global__ void k_pack_leavers(const __grid_constant__ DevLayout L, const __grid
 // flagged BF_ARRIVAL: its thermodynamics of this step runs here (k_thermo_range).
 __global__ void k_unpack_arrivals(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
                                   const __grid_constant__ DevParams p, DevCounters* __restrict__ cnt,
-                                  const double* __restrict__ recvbuf, long long n_recv, long long s0) {
+                                  const double* __restrict__ recvbuf, long long n_recv, long long s0, int rec_w) {
   long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_recv) return;
   long long s = s0 + k;
-  const double* rec = recvbuf + (size_t)k * PACK_W;
+  const double* rec = recvbuf + (size_t)k * rec_w;
+  for (int q = 0; q < b.max_bonds; q++) {
+    long long slot = (long long)q * b.capacity + s;
+    const double* br = rec + PACK_W + 3 * q;
+    b.bond_other_id[slot] = __double_as_longlong(br[0]);
+    long long oij = __double_as_longlong(br[1]);
+    b.bond_other_ine[slot] = (int)(oij >> 32); b.bond_other_jne[slot] = (int)(oij & 0xffffffffll);
+    b.bond_length[slot] = br[2];
+    b.bond_other_slot[slot] = -1;
+  }
 #pragma unroll
   for (int c = 0; c < C_NBASE; c++) b.f64[c][s] = rec[PK_F64_0 + c];
   double lon = rec[PK_F64_0 + C_LON], lat = rec[PK_F64_0 + C_LAT];
