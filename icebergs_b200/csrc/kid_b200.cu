@@ -465,9 +465,6 @@ static int exchange_bergs(kid_t* h, long long* n_recv_out) {
   if (rc) return rc;
   if (n_recv > 0) {
     LAUNCH(h, k_unpack_arrivals, n_recv, 128, h->g, h->b, h->dp, h->dcnt, h->recvbuf, n_recv, h->n_slots, (int)W);
-    unsigned long long nn = (unsigned long long)(h->n_slots + n_recv);
-    CK(cudaMemcpyAsync(&h->dcnt->n_slots, &nn, sizeof(nn), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));   // nn is a stack variable
   }
   h->n_sent_last = n_send; h->n_recv_last = n_recv;
   *n_recv_out = n_recv;

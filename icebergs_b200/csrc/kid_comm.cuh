@@ -154,6 +154,7 @@ __global__ void k_unpack_arrivals(const __grid_constant__ DevGrid g, const __gri
                                   const double* __restrict__ recvbuf, long long n_recv, long long s0, int rec_w) {
   long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_recv) return;
+  if (k == 0) cnt->n_slots = (unsigned long long)(s0 + n_recv);     // the append cursor moves past the arrivals
   long long s = s0 + k;
   const double* rec = recvbuf + (size_t)k * rec_w;
   for (int q = 0; q < b.max_bonds; q++) {
