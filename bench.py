@@ -158,6 +158,7 @@ def reference_arm(args, rank):
 
 
 def main():
+    global GNI, GNJ
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -166,6 +167,8 @@ def main():
     ap.add_argument("--bergs-per-gpu", type=int, default=0, help="0 = 10M at N=1, 12.5M per GPU at N>1")
     ap.add_argument("--cpu-bergs", type=int, default=1_000_000)
     ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--gni", type=int, default=GNI, help="diagnostics only: another grid size (the metric is quoted on 1440x720)")
+    ap.add_argument("--gnj", type=int, default=GNJ)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -177,6 +180,7 @@ def main():
         return
     if args.warmup < 3:
         args.warmup = 3
+    GNI, GNJ = args.gni, args.gnj
 
     import torch
     import torch.distributed as dist
@@ -248,7 +252,12 @@ def main():
         tsum = t_all.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         dev_ms, wall_ms, kern_ms, comm_ms, sort_ms = float(tmax[0]), float(tmax[1]), float(tmax[3]), float(tmax[5]), float(tmax[6])
         n_total = float(tsum[2])
+        gathered = [torch.zeros_like(t_all) for _ in range(world)]
+        dist.all_gather(gathered, t_all)
+        per_rank = {"kernel_ms": [round(float(g[3]), 4) for g in gathered], "migration_ms": [round(float(g[5]), 4) for g in gathered],
+                    "bergs": [int(g[2]) for g in gathered], "occupied_cells": [int(g[4]) for g in gathered]}
     else:
+        per_rank = None
         wall_ms, n_total = wall * 1e3, float(n_alive)
     ms_per_step = dev_ms / args.steps
     value = n_total * args.steps / (dev_ms * 1e-3)
@@ -282,7 +291,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"free drift + melt, {n_per} seeded bergs per GPU on the 1/4-degree 1440x720 grid, "
+            "config": {"workload": f"free drift + melt, {n_per} seeded bergs per GPU on the {'1/4-degree ' if GNI == 1440 else ''}{GNI}x{GNJ} grid, "
                                    f"analytic currents/winds, dt=3600 s, Verlet, bergy bits on",
                        "bergs_total": int(n_total), "layout": [int(dom.layout_x), int(dom.layout_y)],
                        "l2_policy": f"inputs larger than L2 ({B_BERG * n_per / 1e9:.2f} GB of berg state per step vs 126 MB L2)",
@@ -291,7 +300,7 @@ def main():
                        "wall_ms_per_step": wall_ms / args.steps, "migration_ms_per_step": comm_ms, "sort_ms_per_step": sort_ms,
                        "physics": "namelist defaults except Verlet stepping, bergy_bit_erosion_fraction=0.1, tau_is_velocity, "
                                   "add_weight_to_ocean off (the metric is dyn+thermo; mass spreading is SURVEY 8f1)",
-                       "sort_interval": int(os.environ.get("KID_SORT_INTERVAL", "32"))},
+                       "sort_interval": int(os.environ.get("KID_SORT_INTERVAL", "32")), "per_rank": per_rank},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "k_step (fused evolve+thermodynamics)",
                          "alg_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms},

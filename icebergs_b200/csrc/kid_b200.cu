@@ -61,6 +61,7 @@ struct kid_handle {
   int visited = 0, first_call_accum = 1, restarted = 0;
   int calving_active = 0;
   int steps_since_sort = 0, sort_interval = 32, sorted_once = 0;
+  int scatter_dense = 1;          // > KID_DENSE_BERGS_PER_CELL bergs per occupied cell at the last sort (scatter_fluxes)
   int forcing_set = 0;
   int no_rotation = 0;
   long long dirty_appended = 0;
@@ -837,7 +838,7 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   CK(cudaMalloc(&h->cell_fill, sizeof(int32_t) * n2));
   int nsb = (int)((n2 + KID_SCAN_ITEMS - 1) / KID_SCAN_ITEMS);
   CK(cudaMalloc(&h->scan_sums, sizeof(int32_t) * (nsb + 1)));
-  CK(cudaMalloc(&h->scan_total, sizeof(int32_t)));
+  CK(cudaMalloc(&h->scan_total, 2 * sizeof(int32_t)));
   CK(cudaMalloc(&h->dcnt, sizeof(DevCounters)));
   CK(cudaMemsetAsync(h->dcnt, 0, sizeof(DevCounters), h->stream));
   CK(cudaMallocHost(&h->hcnt, sizeof(DevCounters)));
@@ -942,22 +943,31 @@ static void gather_cols(kid_t* h, T** cols, int ncols, T** spare, long long n_ne
   }
 }
 
+#ifndef KID_DENSE_BERGS_PER_CELL
+#define KID_DENSE_BERGS_PER_CELL 20
+#endif
 static int sort_bergs(kid_t* h) {
   long long n2 = h->n2, ns = h->n_slots;
   CK(cudaMemsetAsync(h->cell_count, 0, sizeof(int32_t) * n2, h->stream));
   if (ns <= 0) { h->steps_since_sort = 0; h->tables_valid = 1; return KID_OK; }
   CK(cudaMemsetAsync(h->cell_fill, 0, sizeof(int32_t) * n2, h->stream));
   LAUNCH(h, k_hist, ns, 256, h->g, h->b.flags, h->b.ine, h->b.jne, ns, h->cell_count);
+  CK(cudaMemsetAsync(h->scan_total + 1, 0, sizeof(int32_t), h->stream));
+  LAUNCH(h, k_count_occupied, n2, 256, h->cell_count, n2, h->scan_total + 1);
   int nsb = (int)((n2 + KID_SCAN_ITEMS - 1) / KID_SCAN_ITEMS);
   LAUNCH(h, k_scan_block, (long long)nsb * 256, 256, h->cell_count, h->cell_start, h->scan_sums, n2);
   k_scan_sums<<<1, 1024, 0, h->stream>>>(h->scan_sums, nsb, h->scan_total); h->launches++;
   LAUNCH(h, k_scan_add, n2, 256, h->cell_start, h->scan_sums, n2);
   LAUNCH(h, k_rank, ns, 256, h->g, h->b.flags, h->b.ine, h->b.jne, ns, h->cell_start, h->cell_fill, h->perm);
   LAUNCH(h, k_cell_order, n2, 128, h->b, h->cell_start, h->cell_count, n2, h->perm, h->p.footloose ? 1 : 0);
-  int32_t total = 0;
-  CK(cudaMemcpyAsync(&total, h->scan_total, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  int32_t totals[2] = {0, 0};
+  CK(cudaMemcpyAsync(totals, h->scan_total, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  long long n_new = total;
+  long long n_new = totals[0];
+  {
+    static const char* ev = getenv("KID_SCATTER_DENSE");      // diagnostics: force a variant
+    h->scatter_dense = ev ? atoi(ev) : ((long long)totals[0] > KID_DENSE_BERGS_PER_CELL * (long long)totals[1]);
+  }
   double* sp8 = (double*)h->spare8;
   gather_cols<double>(h, h->b.f64, C_NCOLS, &sp8, n_new);
   int64_t* spi = (int64_t*)sp8;
@@ -1506,7 +1516,10 @@ static bool lean_config(const kid_t* h) {
 
 template <bool FL, bool DG>
 static void launch_step(kid_t* h) {
-  if (!FL && !DG && lean_config(h)) { LAUNCH(h, (k_step<false, false, false, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
+  if (!FL && !DG && lean_config(h)) {
+    if (h->scatter_dense) { LAUNCH(h, (k_step<false, false, false, true, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
+    else { LAUNCH(h, (k_step<false, false, false, true, false>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
+  }
   else { LAUNCH(h, (k_step<FL, DG>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
 }
 

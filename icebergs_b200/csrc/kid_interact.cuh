@@ -82,15 +82,17 @@ __device__ __forceinline__ void calculate_force(const DevBergs& b, const DevPara
 // I:480-607, the branch for STS with contact_distance = 0 and one spring constant (I:577-605)
 __device__ __forceinline__ void interactive_force(const DevGrid& g, const DevBergs& b, const DevParams& p,
                                                   const CellTable& ct, long long s, int i, int j, IAcc& A,
-                                                  double u0, double v0, double u1, double v1) {
+                                                  double u0, double v0, double u1, double v1, int mts_part = 0) {
   A.IA_x = A.IA_y = A.P11 = A.P12 = A.P21 = A.P22 = A.Pu_x = A.Pu_y = 0.;
   if (b.f64[C_FL_K][s] == -1.) return;
-  if ((p.contact_distance > 0.) || (p.contact_spring_coef != p.spring_coef)) {
+  if (p.mts || (p.contact_distance > 0.) || (p.contact_spring_coef != p.spring_coef)) {
     // I:512-576 (STS): bonded partners through the bonds, the rest of the berg's own conglomerate by radius
     // contact (partners excluded -- the reference marks them by negating their id), other conglomerates
     // within contact_cells with the contact spring
+    // with the MTS scheme the bonded half runs in the fast sub-steps only (mts_part 3), collisions between
+    // conglomerates in the long step only (mts_part 1), I:522 / I:563
     const int32_t my_cong = b.conglom_id[s];
-    if (p.iceberg_bonds_on) {
+    if (p.iceberg_bonds_on && (!p.mts || mts_part == 3)) {
       for (int k = b.max_bonds - 1; k >= 0; k--) {
         long long slot = (long long)k * b.capacity + s;
         if (b.bond_other_id[slot] == 0) continue;
@@ -114,6 +116,7 @@ __device__ __forceinline__ void interactive_force(const DevGrid& g, const DevBer
           }
         }
     }
+    if (p.mts && mts_part == 3) return;
     const int nc_x = p.contact_cells_lon, nc_y = p.contact_cells_lat;
     for (int grdj = max(j - nc_y, g.jsd); grdj <= min(j + nc_y, g.jed); grdj++)
       for (int grdi = max(i - nc_x, g.isd); grdi <= min(i + nc_x, g.ied); grdi++) {

@@ -98,7 +98,7 @@ __device__ __forceinline__ int route_berg(const DevGrid& g, const DevParams& p, 
 struct Scatter { long long key; ThermoFlux fx; };
 
 #ifndef KID_SCATTER_MODE
-#define KID_SCATTER_MODE 3
+#define KID_SCATTER_MODE 5
 #endif
 
 // run-sequential variant: every lane parks its value in shared memory, the head lane of each
@@ -117,9 +117,49 @@ __device__ __forceinline__ void seg_scatter_smem(double* __restrict__ fld, long 
   __syncwarp();
 }
 
-template <bool FOOTLOOSE, bool DIAG>
+template <bool FOOTLOOSE, bool DIAG, bool dense = true>
 __device__ __forceinline__ void scatter_fluxes(const DevGrid& g, const Scatter& sc) {
-#if KID_SCATTER_MODE == 1 || KID_SCATTER_MODE == 3
+#if KID_SCATTER_MODE == 5
+  // Two aggregation variants; the tuned (lean) kernel instance exists in both and sort_bergs picks one from the
+  // population density (kid_t::scatter_dense), every other instance uses the density-robust first one:
+  //  - dense (> ~20 bergs per occupied cell: the weak-scaling tiles): runs of one cell are reduced with segmented
+  //    suffix sums and the head lane of each run issues ONE atomic per field.  Per-berg reductions to one address
+  //    from this warp and its neighbours pile up in one L2 slice (measured 1.21 ms vs 1.04 ms at 125 bergs/cell).
+  //  - sparse (~13 bergs per cell, the 10M-berg workload): a warp whose 32 bergs all sit in one cell reduces with a
+  //    butterfly; a warp that straddles cells issues one reduction (RED.ADD.F64) per berg and field, cheaper than
+  //    the shuffle tree there (0.894 ms vs 0.929 ms).
+  SegInfo si; si.seg_end = 32; si.rounds = 0; si.head = false;
+  {
+    double v[5] = {sc.fx.floating_melt, sc.fx.calving_hflx, sc.fx.berg_melt, sc.fx.bergy_src, sc.fx.bergy_melt};
+    double* f[5] = {g.floating_melt, g.calving_hflx, g.berg_melt, g.bergy_src, g.bergy_melt};
+    if (dense) {
+      si = seg_info(sc.key);
+#pragma unroll
+      for (int q = 0; q < 5; q++) seg_scatter(f[q], sc.key, v[q], si);
+    } else {
+      long long k0 = __shfl_sync(0xffffffffu, sc.key, 0);
+      bool uniform = __all_sync(0xffffffffu, sc.key == k0);
+      if (uniform) {
+        if (k0 >= 0) {
+#pragma unroll
+          for (int q = 0; q < 5; q++) {
+            double t = v[q];
+            if (!__any_sync(0xffffffffu, t != 0.)) continue;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) t += shfl_down_d(t, d);
+            if ((threadIdx.x & 31) == 0 && t != 0.) atomicAdd(&f[q][k0], t);
+          }
+        }
+      } else if (sc.key >= 0) {
+#pragma unroll
+        for (int q = 0; q < 5; q++)
+          if (v[q] != 0.) atomicAdd(&f[q][sc.key], v[q]);
+      }
+    }
+  }
+#define KID_SEG(fld, v) seg_scatter(fld, sc.key, v, si)
+  if ((FOOTLOOSE || DIAG) && !dense) si = seg_info(sc.key);
+#elif KID_SCATTER_MODE == 1 || KID_SCATTER_MODE == 3
   // Adaptive aggregation (mode 3): a warp whose 32 bergs all sit in one cell (dense populations,
   // the store is cell-sorted) reduces each flux with a butterfly and issues ONE atomic per field;
   // a warp that straddles cells issues one reduction (RED.ADD.F64) per berg and field, which at
@@ -389,7 +429,7 @@ __device__ __forceinline__ void prefetch_tile_ahead(const DevBergs& b, long long
 #endif
 }
 
-template <bool FOOTLOOSE, bool DIAG, bool SPLIT = false, bool LEAN = false>
+template <bool FOOTLOOSE, bool DIAG, bool SPLIT = false, bool LEAN = false, bool DENSE = true>
 __global__ void __launch_bounds__(KID_BLOCK, KID_MINBLOCKS)
 k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
        const __grid_constant__ DevParams p, DevCounters* __restrict__ cnt, long long n_slots) {
@@ -424,7 +464,7 @@ k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
   sc.fx.melt_buoy_fl = sc.fx.melt_eros_fl = sc.fx.melt_conv_fl = 0.;
   bool melted = false, became_fl = false, bounced = false, speeding = false, left = false;
   if (owned) step_berg<FOOTLOOSE, SPLIT, LEAN>(g, b, p, cnt, s, in, sc, melted, became_fl, bounced, speeding, left);
-  scatter_fluxes<FOOTLOOSE, DIAG>(g, sc);
+  scatter_fluxes<FOOTLOOSE, DIAG, DENSE>(g, sc);
   // event counters: one vote decides whether the warp has anything to report at all
   if (__any_sync(0xffffffffu, melted | bounced | speeding | left)) {
     warp_count_add(&cnt->nbergs_melted, melted);
@@ -650,6 +690,13 @@ __global__ void __launch_bounds__(256) k_scan_block(const int32_t* __restrict__ 
 #pragma unroll
   for (int k = 0; k < 4; k++) { if (base + k < n) out[base + k] = excl; excl += v[k]; }
 }
+// cells holding at least one berg (decides the scatter variant, see scatter_fluxes)
+__global__ void k_count_occupied(const int32_t* __restrict__ cell_count, long long n2, int32_t* __restrict__ out) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned m = __ballot_sync(0xffffffffu, c < n2 && cell_count[c] > 0);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, __popc(m));
+}
+
 __global__ void __launch_bounds__(1024) k_scan_sums(int32_t* __restrict__ block_sums, int nb, int32_t* total) {
   // single block; serial over chunks of 1024
   __shared__ int32_t sh[1024];

@@ -102,6 +102,8 @@ struct Oracle {
   double dem_tests_start_lon, dem_tests_end_lon;
   int mts_part;
   double mts_fast_dt;
+  int only_interactive_forces;   /* bergs%only_interactive_forces: toggled by evolve_icebergs_mts I:6781 */
+  int bond_break_detected, no_frac_first_ts, skip_first_outer_mts_step, mts_outer_iters;
   int nthreads;
   double tsec[4];
   char err[512];
@@ -2156,6 +2158,8 @@ Oracle* oracle_create(const KidParams* p, const KidDomain* dom, int32_t year, do
   o->p = *p; o->d = *dom;
   o->current_year = year; o->current_yearday = yearday;
   o->first_call_accum = 1; o->nthreads = 1; o->mts_part = 1;
+  o->only_interactive_forces = p->only_interactive_forces;
+  o->no_frac_first_ts = p->no_frac_first_ts; o->skip_first_outer_mts_step = p->skip_first_outer_mts_step;
   const KidDomain* d = &o->d;
   o->nid = d->ied - d->isd + 1; o->njd = d->jed - d->jsd + 1;
   size_t n2 = (size_t)o->nid * o->njd;
@@ -2546,6 +2550,7 @@ static void oracle_footloose_part2(Oracle* o);
 static void oracle_set_conglom_ids(Oracle* o);
 static void oracle_transfer_mts_bergs(Oracle* o);
 static void oracle_bond_address_update(Oracle* o);
+static void oracle_mts_first_visit(Oracle* o);
 
 /* the hot path of icebergs_run, I:5389-5512 */
 static void step_core(Oracle* o) {
@@ -2555,6 +2560,7 @@ static void step_core(Oracle* o) {
   calve_icebergs(o);
   if (!o->visited) {
     o->visited = 1;
+    oracle_mts_first_visit(o);
     if (p->mts) { interp_gridded_fields_to_bergs(o); oracle_transfer_mts_bergs(o); }
     else if ((p->contact_distance > 0.) || (p->contact_spring_coef != p->spring_coef)) oracle_set_conglom_ids(o);
     if (p->iceberg_bonds_on) oracle_bonds_first_visit(o);
