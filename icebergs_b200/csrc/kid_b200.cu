@@ -18,6 +18,7 @@
 #include "kid_comm.cuh"
 #include "kid_interact.cuh"
 #include "kid_spread.cuh"
+#include "kid_mts.cuh"
 
 using namespace kid;
 
@@ -61,6 +62,9 @@ struct kid_handle {
   int visited = 0, first_call_accum = 1, restarted = 0;
   int calving_active = 0;
   int steps_since_sort = 0, sort_interval = 32, sorted_once = 0;
+  MtsParams mp;                   // MTS scheme (evolve_icebergs_mts)
+  MtsSums* dsums = nullptr;
+  int mts_env_cached = 0, mts_outer_iters = 0;
   int scatter_dense = 1;          // > KID_DENSE_BERGS_PER_CELL bergs per occupied cell at the last sort (scatter_fluxes)
   int forcing_set = 0;
   int no_rotation = 0;
@@ -521,7 +525,10 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
     unsupported = "Runge_not_Verlet=.true. (RK4) is implemented for free-drifting bergs only: set runge_not_verlet=0 with interactions / footloose";
   else if (pin->tidal_drift > 0.) unsupported = "tidal_drift>0 needs the FMS random number stream";
   else if (pin->add_iceberg_thickness_to_ssh) unsupported = "add_iceberg_thickness_to_SSH is not implemented";
-  else if (pin->mts || pin->dem) unsupported = "MTS/DEM stepping is not implemented in this build";
+  else if (pin->dem) unsupported = "dem=.true. (bonded DEM forces of the MTS scheme) is not implemented in this build";
+  else if (pin->mts && dom->nranks > 1) unsupported = "mts=.true. runs on one rank in this build (transfer_mts_bergs is not implemented)";
+  else if (pin->mts && (!pin->interactive_icebergs_on || pin->footloose)) unsupported = "mts=.true. needs interactive_icebergs_on and no footloose";
+  else if (pin->mts && pin->halo < 3) unsupported = "mts=.true. needs halo >= 3 (3x3 A-grid stencil of the ocean depth)";
   else if (pin->contact_distance > 0. && pin->halo - 1 < 1) unsupported = "contact_distance>0 needs halo >= 2";
   else if (pin->iceberg_bonds_on && !pin->interactive_icebergs_on) unsupported = "iceberg_bonds_on needs interactive_icebergs_on";
   else if (pin->iceberg_bonds_on && (pin->max_bonds < 1 || pin->max_bonds > 12)) unsupported = "max_bonds must be 1..12";
@@ -592,6 +599,24 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   if (!q->iceberg_bonds_on) q->max_bonds = 0;
   if (q->contact_spring_coef <= 0.) q->contact_spring_coef = q->spring_coef;
   q->old_interp_flds_order = !(q->mts || q->dem || q->footloose);
+  memset(&h->mp, 0, sizeof(h->mp));
+  if (q->mts) {                                            // F:1296-1301, F:1433, F:1453-1464
+    double fast = 0.;
+    if (q->mts_sub_steps == -1) { fast = 0.3 / sqrt(q->spring_coef); q->mts_sub_steps = (int)ceil(q->dt / fast); }
+    if (q->mts_sub_steps < 1) return fail(h, KID_ERR_ARG, "kid_init: mts_sub_steps must be -1 or >= 1");
+    h->mp.dt_fast = q->dt / q->mts_sub_steps;
+    if (q->dem) q->explicit_inner_mts = 1;
+    h->mp.force_convergence = q->force_convergence; h->mp.explicit_inner_mts = q->explicit_inner_mts;
+    h->mp.short_step_mts_grounding = q->short_step_mts_grounding; h->mp.radius_based_drag = q->radius_based_drag;
+    h->mp.constant_interaction_LW = q->constant_interaction_LW; h->mp.use_grounding_torque = q->use_grounding_torque;
+    h->mp.constant_length = q->constant_length; h->mp.constant_width = q->constant_width;
+    h->mp.constant_area = q->constant_length * q->constant_width;
+    if (q->hexagonal_icebergs) h->mp.constant_radius = sqrt(h->mp.constant_area / (2. * sqrt(3.)));
+    else if (q->iceberg_bonds_on) h->mp.constant_radius = 0.5 * sqrt(h->mp.constant_area);
+    else h->mp.constant_radius = sqrt(h->mp.constant_area / q->pi);
+    if (q->constant_interaction_LW && (q->constant_length == 0. || q->constant_width == 0.))
+      return fail(h, KID_ERR_UNSUPPORTED, "kid_init: constant_interaction_LW needs constant_length and constant_width (the mean-size default F:4640 is not implemented)");
+  }
   // F:1113-1118
   if ((!q->grid_is_latlon) && (q->Lx == 360.)) q->Lx = -1.;
 
@@ -775,8 +800,12 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   DevBergs& b = h->b;
   memset(&b, 0, sizeof(b));
   b.capacity = h->capacity;
-  int ncols = q->interactive_icebergs_on ? (int)C_NINTER : (int)C_NBASE;
+  int ncols = q->mts ? (int)C_NMTS : q->interactive_icebergs_on ? (int)C_NINTER : (int)C_NBASE;
   for (int c = 0; c < ncols; c++) CK(cudaMalloc(&b.f64[c], sizeof(double) * h->capacity));
+  if (q->mts) {
+    for (int c = C_NINTER; c < C_NMTS; c++) CK(cudaMemsetAsync(b.f64[c], 0, sizeof(double) * h->capacity, h->stream));
+    CK(cudaMalloc(&h->dsums, sizeof(MtsSums)));
+  }
   CK(cudaMalloc(&b.id, sizeof(int64_t) * h->capacity));
   CK(cudaMalloc(&b.ine, sizeof(int32_t) * h->capacity));
   CK(cudaMalloc(&b.jne, sizeof(int32_t) * h->capacity));
@@ -811,6 +840,8 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
     }
     CK(cudaMalloc(&b.conglom_id, sizeof(int32_t) * h->capacity));
     CK(cudaMemsetAsync(b.conglom_id, 0, sizeof(int32_t) * h->capacity, h->stream));
+    CK(cudaMalloc(&b.n_bonds, sizeof(int32_t) * h->capacity));
+    CK(cudaMemsetAsync(b.n_bonds, 0, sizeof(int32_t) * h->capacity, h->stream));
     CK(cudaMalloc(&h->d_changed, sizeof(int)));
     h->ghost_rec_w = PACK_W + 3 * b.max_bonds;
     h->ghost_cap = std::max<long long>(4096, h->capacity / 2);
@@ -1025,6 +1056,7 @@ static int sort_bergs(kid_t* h) {
 static int rebuild_ghosts(kid_t* h) {
   const int me = h->d.rank;
   LAUNCH(h, k_clear_halo, h->n_slots, 256, h->b.flags, h->n_slots);
+  if (h->p.mts) return KID_OK;      // one rank, no copies through the cyclic seam (transfer_mts_bergs F:2144 step 1 only)
   GhostPlan gp;
   for (int k = 0; k < 9; k++) gp.nbr[k] = h->nbr[k];
   gp.hw = h->p.halo; gp.isc = h->d.isc; gp.iec = h->d.iec; gp.jsc = h->d.jsc; gp.jec = h->d.jec;
@@ -1099,6 +1131,7 @@ static int refresh_interactive_state(kid_t* h) {
   if (h->b.max_bonds > 0) {
     CellTable ct{h->cell_start, h->cell_count};
     LAUNCH(h, k_connect_bonds, h->n_slots, 128, h->g, h->b, ct, h->dcnt, h->n_slots);
+    if (h->p.mts) LAUNCH(h, k_assign_n_bonds, h->n_slots, 128, h->b, h->n_slots);
   }
   return set_conglom_ids(h);
 }
@@ -1125,7 +1158,9 @@ const ColMap kColMap[] = {
     {C_MASS_OF_FL_BITS, &KidBergColumns::mass_of_fl_bits},
     {C_MASS_OF_FL_BERGY_BITS, &KidBergColumns::mass_of_fl_bergy_bits}, {C_FL_K, &KidBergColumns::fl_k},
     {C_UVEL_OLD, &KidBergColumns::uvel_old}, {C_VVEL_OLD, &KidBergColumns::vvel_old},
-    {C_LON_OLD, &KidBergColumns::lon_old}, {C_LAT_OLD, &KidBergColumns::lat_old}};
+    {C_LON_OLD, &KidBergColumns::lon_old}, {C_LAT_OLD, &KidBergColumns::lat_old},
+    {C_AXN_FAST, &KidBergColumns::axn_fast}, {C_AYN_FAST, &KidBergColumns::ayn_fast},
+    {C_BXN_FAST, &KidBergColumns::bxn_fast}, {C_BYN_FAST, &KidBergColumns::byn_fast}};
 }  // namespace
 
 extern "C" int32_t kid_set_bergs(kid_t* h, int64_t n, const KidBergColumns* c) {
@@ -1503,6 +1538,91 @@ static int ingest_forcing(kid_t* h, const double* calving, const double* uo, con
   return KID_OK;
 }
 
+// ------------------------------------------------------------ MTS step
+// evolve_icebergs_mts I:6576-7078: the sweeps of the reference as kernels on the handle's stream.  The convergence
+// norms of force_convergence come back to the host once per pass (a 32-byte copy).
+static int mts_read_sums(kid_t* h, MtsSums* out) {
+  CK(cudaMemcpyAsync(out, h->dsums, sizeof(MtsSums), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return KID_OK;
+}
+
+static int evolve_mts(kid_t* h) {
+  const KidParams& p = h->p;
+  const long long ns = h->n_slots;
+  if (ns <= 0) return KID_OK;
+  CellTable ct{h->cell_start, h->cell_count};
+  const int fc = p.force_convergence ? 1 : 0;
+  // part 1: slow forces and collisions over the long step, iterated until the velocity change is small
+  int ii = 0;
+  bool finished = false, last_iter = !fc, had_collision = false;
+  double usum = 0.;
+  while (!finished) {
+    ii++;
+    CK(cudaMemsetAsync(h->dsums, 0, sizeof(MtsSums), h->stream));
+    LAUNCH(h, k_mts_part1, ns, 128, h->g, h->b, h->dp, h->mp, ct, h->dcnt, h->dsums, ns, ii);
+    MtsSums sm{0., 0., 0., 0u, 0u};
+    if (fc) {
+      if (!last_iter) { int rc = mts_read_sums(h, &sm); if (rc) return rc; }
+      had_collision = had_collision || sm.had_collision;
+      if (ii == 1) usum = sm.usum;
+    }
+    bool this_last = last_iter;
+    if (fc && !last_iter && had_collision) {
+      if (ii > 1) {
+        double denom = sqrt(usum) + sqrt(sm.usum1);
+        double normchange = denom > 0 ? 2.0 * sqrt(sm.usum2) / denom : 0.0;
+        if (normchange < p.convergence_tolerance) last_iter = true;
+      }
+      usum = sm.usum1;
+    } else finished = true;
+    if (last_iter) finished = true;
+    // the reference refreshes *_old with the last_iter flag as it stood before this pass's norm test (I:6709-6720)
+    if (fc) LAUNCH(h, k_mts_part1_old, ns, 256, h->b, ns, this_last ? 1 : 0);
+    if (ii > 10000) return fail(h, KID_ERR_STATE, "kid: MTS force_convergence (part 1) did not converge in 10000 passes");
+  }
+  h->mts_outer_iters = ii;
+  LAUNCH(h, k_mts_part2, ns, 256, h->b, h->dp, ns, fc);
+  // part 3: fast sub-steps, bonded interactions only
+  const double dtf = h->mp.dt_fast;
+  const bool iterate = fc && !p.explicit_inner_mts;
+  if (!iterate && p.explicit_inner_mts && !p.short_step_mts_grounding && ns <= 4096) {
+    // a few thousand elements: the whole sub-step loop in one CTA, __syncthreads() between the sweeps
+    k_mts_substeps_one_cta<<<1, 1024, 0, h->stream>>>(h->g, h->b, h->dp, h->mp, ct, h->dcnt, ns, dtf, p.mts_sub_steps);
+    h->launches++;
+  } else {
+    for (int k = 1; k <= p.mts_sub_steps; k++) {
+      LAUNCH(h, k_mts_pos, ns, 256, h->b, h->dp, ns, dtf);
+      int jj = 0;
+      bool fin = false, last = !iterate;
+      double us = 0.;
+      while (!fin) {
+        jj++;
+        if (iterate) CK(cudaMemsetAsync(h->dsums, 0, sizeof(MtsSums), h->stream));
+        LAUNCH(h, k_mts_vel, ns, 128, h->g, h->b, h->dp, h->mp, ct, h->dcnt, h->dsums, ns, dtf, jj);
+        if (iterate && !last) {
+          MtsSums sm;
+          int rc = mts_read_sums(h, &sm);
+          if (rc) return rc;
+          if (jj == 1) us = sm.usum;
+          if (jj > 1) {
+            double denom = sqrt(us) + sqrt(sm.usum1);
+            double normchange = denom > 0 ? 2.0 * sqrt(sm.usum2) / denom : 0.0;
+            if (normchange < p.convergence_tolerance) last = true;
+          }
+          us = sm.usum1;
+        } else fin = true;
+        if (last) fin = true;
+        if (fc && !fin) LAUNCH(h, k_mts_vel_retry, ns, 256, h->b, ns, dtf);
+        if (jj > 10000) return fail(h, KID_ERR_STATE, "kid: MTS force_convergence (sub-step) did not converge in 10000 passes");
+      }
+      LAUNCH(h, k_mts_sub_end, ns, 256, h->b, ns, fc);
+    }
+  }
+  LAUNCH(h, k_mts_finish, ns, 128, h->g, h->b, h->dp, h->dcnt, ns);
+  return KID_OK;
+}
+
 // ------------------------------------------------------------ one step
 // the namelist matches what the LEAN kernel instances assume (kid_physics.cuh PF())
 static bool lean_config(const kid_t* h) {
@@ -1606,8 +1726,17 @@ static int step_core(kid_t* h) {
     }
   }
   const bool fl = h->p.footloose != 0, dg = h->p.melt_diagnostics != 0;
+  const bool mts = h->p.mts != 0;
+  if (mts && !h->mts_env_cached) {                         // first visit, I:5412-5414
+    LAUNCH(h, k_mts_env_cache, h->n_slots, 128, h->g, h->b, h->dp, h->dcnt, h->n_slots);
+    if (h->b.max_bonds > 0) LAUNCH(h, k_assign_n_bonds, h->n_slots, 128, h->b, h->n_slots);
+    h->mts_env_cached = 1;
+  }
   if (!h->p.static_icebergs) {
-    if (ia) {
+    if (mts) {
+      int rc = evolve_mts(h);
+      if (rc) return rc;
+    } else if (ia) {
       CellTable ct{h->cell_start, h->cell_count};
       LAUNCH(h, k_ia_velocity, h->n_slots, KID_BLOCK, h->g, h->b, h->dp, ct, h->dcnt, h->n_slots);
       if (fl) { LAUNCH(h, (k_step<true, false, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
@@ -1660,9 +1789,11 @@ static int step_core(kid_t* h) {
   if (ia) {
     int rc = refresh_interactive_state(h);
     if (rc) return rc;
+    // I:5457-5459: the environment the NEXT step's accel_mts sees is interpolated now, from this step's forcing
+    if (mts) LAUNCH(h, k_mts_env_cache, h->n_slots, 128, h->g, h->b, h->dp, h->dcnt, h->n_slots);
     if (fl) { CellTable ct{h->cell_start, h->cell_count}; LAUNCH(h, k_fl_interactivity, h->n_slots, 128, h->g, h->b, h->dp, ct, h->n_slots); }
   }
-  if (fl || h->p.static_icebergs) {
+  if (fl || mts || h->p.static_icebergs) {
     // thermodynamics I:5497 on its own: footloose calving sits between the move and the melt
     if (fl && dg) { LAUNCH(h, (k_thermo_range<true, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, 0LL, h->n_slots, 1); }
     else if (fl) { LAUNCH(h, (k_thermo_range<true, false>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, 0LL, h->n_slots, 1); }

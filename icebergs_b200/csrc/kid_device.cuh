@@ -20,7 +20,8 @@ enum : uint8_t {
   BF_STATIC = 2,     // static_berg >= 0.5   (F:323)
   BF_LEAVER = 4,     // left the rank's compute domain this step, awaiting migration
   BF_HALO = 8,       // halo copy (halo_berg >= 0.5)
-  BF_ARRIVAL = 16    // arrived by migration this step: thermodynamics still to do
+  BF_ARRIVAL = 16,   // arrived by migration this step: thermodynamics still to do
+  BF_COLLIDED = 32   // static_berg == 0.1: "had a collision" mark inside the MTS convergence loop (I:6685)
 };
 
 // module constants, I:68-80
@@ -117,7 +118,11 @@ enum BergCol : int {
   C_NBASE,                                       // columns always allocated
   C_UVEL_OLD = C_NBASE, C_VVEL_OLD, C_LON_OLD, C_LAT_OLD,   // interactive
   C_NINTER,
-  C_NCOLS = C_NINTER
+  // MTS (F:349-359): the environment cache of interp_gridded_fields_to_bergs and the fast accelerations
+  C_UO = C_NINTER, C_VO, C_UI, C_VI, C_UA, C_VA, C_SSH_X, C_SSH_Y, C_SST, C_SSS, C_CN, C_HI, C_OD,
+  C_AXN_FAST, C_AYN_FAST, C_BXN_FAST, C_BYN_FAST,
+  C_NMTS,
+  C_NCOLS = C_NMTS
 };
 
 struct DevBergs {
@@ -135,6 +140,8 @@ struct DevBergs {
   int32_t* conglom_id;        // connected component of the bond graph (set_conglom_ids F:2601); 0 = halo copy not reached
   int32_t *bond_other_slot, *bond_other_ine, *bond_other_jne;
   double* bond_length;
+  int32_t* n_bonds;           // assign_n_bonds F:4617 (MTS contact search skips interior elements)
+  int32_t* bond_broken;       // dem only, else nullptr
 };
 
 // device-side counters (one struct in HBM per handle)

@@ -526,6 +526,11 @@ __global__ void k_mts_finish(const __grid_constant__ DevGrid g, const __grid_con
   const int i0 = i, j0 = j;
   if (adjust_index_and_ground(g, p, lonn, latn, i, j, xi, yj, &cnt->error_flags, &cnt->warn_adjust)) atomicAdd(&cnt->n_bounced, 1ull);
   b.f64[C_LON][s] = lonn; b.f64[C_LAT][s] = latn; b.f64[C_LON_OLD][s] = lonn; b.f64[C_LAT_OLD][s] = latn;
+  // send_bergs_to_other_pes F:2997 on one rank: through the cyclic seam back into the tile, or out of the model
+  if (i > g.iec || i < g.isc || j > g.jec || j < g.jsc) {
+    int route = route_berg(g, p, lonn, latn, i, j, xi, yj, &cnt->error_flags, &cnt->n_wrapped);
+    if (route != 0) { b.flags[s] = 0; return; }
+  }
   b.ine[s] = i; b.jne[s] = j; b.f64[C_XI][s] = xi; b.f64[C_YJ][s] = yj;
   if (i != i0 || j != j0) atomicAdd(&cnt->n_cell_moves, 1ull);
 }
