@@ -54,6 +54,12 @@ struct kid_handle {
   double* out_stage[2] = {nullptr};
   double *tmp_u = nullptr, *tmp_v = nullptr;
   cudaStream_t stream = nullptr;
+  // berg migration overlapped with the next step's kernel (step_core): second stream, two leaver lists
+  cudaStream_t xstream = nullptr;
+  cudaEvent_t ev_kstep = nullptr, ev_xdone = nullptr;
+  int32_t* leaver_lists[2] = {nullptr, nullptr};
+  unsigned long long* leaver_counts = nullptr;    // [2]
+  int leaver_cur = 0, xchg_pending = 0, xdone_recorded = 0, defer_ok = 0;
   cudaEvent_t ev[T_NPHASE + 2];
   std::vector<cudaEvent_t> ev_pool;   // per-step (begin, after fused kernel, after sort) triples
   int ev_used = 0;
@@ -437,13 +443,14 @@ static int halo_exchange(kid_t* h, double* const* fields, int nf) {
 
 // send_bergs_to_other_pes F:2997 between ranks: count, pack, exchange, unpack.  Returns the number
 // of bergs that arrived in n_recv; they occupy slots [n_slots, n_slots + n_recv) flagged BF_ARRIVAL.
-static int exchange_bergs(kid_t* h, long long* n_recv_out) {
+// s0: the slot the arrivals are appended at
+static int exchange_bergs(kid_t* h, long long* n_recv_out, long long s0) {
   const int nr = h->d.nranks, me = h->d.rank;
   const long long W = PACK_W + 3 * h->b.max_bonds;      // record width: berg + its bonds
   *n_recv_out = 0;
   CK(cudaMemsetAsync(h->d_send_counts, 0, sizeof(int32_t) * nr, h->stream));
   CK(cudaMemsetAsync(h->d_cursor, 0, sizeof(int32_t) * nr, h->stream));
-  k_leaver_dest<<<32, 256, 0, h->stream>>>(h->layout, h->b.ine, h->b.jne, h->b.leaver_list, h->dcnt, (int32_t)h->b.leaver_cap,
+  k_leaver_dest<<<32, 256, 0, h->stream>>>(h->layout, h->b.ine, h->b.jne, h->b.leaver_list, h->b.leaver_count, (int32_t)h->b.leaver_cap,
                                           h->leaver_dest, h->d_send_counts); h->launches++;
   int rc = comm_allgather_counts(h, h->d_send_counts, h->h_all_counts);
   if (rc) return rc;
@@ -461,15 +468,15 @@ static int exchange_bergs(kid_t* h, long long* n_recv_out) {
     n_recv += c;
   }
   if (n_send > h->xbuf_cap || n_recv > h->xbuf_cap) return fail(h, KID_ERR_CAPACITY, "kid: berg exchange buffer capacity exceeded");
-  if (h->n_slots + n_recv > h->capacity) return fail(h, KID_ERR_CAPACITY, "kid: berg store capacity exceeded by arrivals");
+  if (s0 + n_recv > h->capacity) return fail(h, KID_ERR_CAPACITY, "kid: berg store capacity exceeded by arrivals");
   CK(cudaMemcpyAsync(h->d_offsets, h->h_offsets, sizeof(int32_t) * nr, cudaMemcpyHostToDevice, h->stream));
-  k_pack_leavers<<<32, 256, 0, h->stream>>>(h->layout, h->b, h->b.leaver_list, h->leaver_dest, h->dcnt, (int32_t)h->b.leaver_cap, h->d_offsets,
+  k_pack_leavers<<<32, 256, 0, h->stream>>>(h->layout, h->b, h->b.leaver_list, h->leaver_dest, h->b.leaver_count, (int32_t)h->b.leaver_cap, h->d_offsets,
                                            h->d_cursor, h->sendbuf, (int)W); h->launches++;
-  CK(cudaMemsetAsync(&h->dcnt->n_leaver_list, 0, sizeof(unsigned long long), h->stream));
+  CK(cudaMemsetAsync(h->b.leaver_count, 0, sizeof(unsigned long long), h->stream));
   rc = comm_exchange(h, sends, recvs);
   if (rc) return rc;
   if (n_recv > 0) {
-    LAUNCH(h, k_unpack_arrivals, n_recv, 128, h->g, h->b, h->dp, h->dcnt, h->recvbuf, n_recv, h->n_slots, (int)W);
+    LAUNCH(h, k_unpack_arrivals, n_recv, 128, h->g, h->b, h->dp, h->dcnt, h->recvbuf, n_recv, s0, (int)W);
   }
   h->n_sent_last = n_send; h->n_recv_last = n_recv;
   *n_recv_out = n_recv;
@@ -855,7 +862,13 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
     const int nr = d->nranks;
     h->xbuf_cap = std::max<long long>(65536, h->capacity / 8);
     b.leaver_cap = h->xbuf_cap;
-    CK(cudaMalloc(&b.leaver_list, sizeof(int32_t) * b.leaver_cap));
+    for (int k = 0; k < 2; k++) CK(cudaMalloc(&h->leaver_lists[k], sizeof(int32_t) * b.leaver_cap));
+    CK(cudaMalloc(&h->leaver_counts, 2 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(h->leaver_counts, 0, 2 * sizeof(unsigned long long), h->stream));
+    b.leaver_list = h->leaver_lists[0]; b.leaver_count = h->leaver_counts;
+    CK(cudaStreamCreateWithFlags(&h->xstream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_kstep, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_xdone, cudaEventDisableTiming));
     CK(cudaMalloc(&h->leaver_dest, sizeof(int32_t) * b.leaver_cap));
     CK(cudaMalloc(&h->sendbuf, sizeof(double) * (PACK_W + 3 * (q->iceberg_bonds_on ? q->max_bonds : 0)) * h->xbuf_cap));
     CK(cudaMalloc(&h->recvbuf, sizeof(double) * (PACK_W + 3 * (q->iceberg_bonds_on ? q->max_bonds : 0)) * h->xbuf_cap));
@@ -916,7 +929,11 @@ extern "C" int32_t kid_end(kid_t** hp) {
   cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->cell_fill);
   cudaFree(h->scan_sums); cudaFree(h->scan_total); cudaFree(h->dcnt); cudaFree(h->dflags);
   cudaFreeHost(h->hcnt); cudaFreeHost(h->hflags);
-  cudaFree(h->b.leaver_list); cudaFree(h->leaver_dest); cudaFree(h->sendbuf); cudaFree(h->recvbuf);
+  cudaFree(h->leaver_lists[0]); cudaFree(h->leaver_lists[1]); cudaFree(h->leaver_counts);
+  if (h->xstream) cudaStreamDestroy(h->xstream);
+  if (h->ev_kstep) cudaEventDestroy(h->ev_kstep);
+  if (h->ev_xdone) cudaEventDestroy(h->ev_xdone);
+  cudaFree(h->leaver_dest); cudaFree(h->sendbuf); cudaFree(h->recvbuf);
   cudaFree(h->d_send_counts); cudaFree(h->d_cursor); cudaFree(h->d_offsets); cudaFree(h->d_all_counts);
   if (h->h_all_counts) cudaFreeHost(h->h_all_counts);
   if (h->h_offsets) cudaFreeHost(h->h_offsets);
@@ -1634,13 +1651,59 @@ static bool lean_config(const kid_t* h) {
          !getenv("KID_NO_LEAN");
 }
 
+// free-drifting Verlet bergs between ranks, nothing else in the step: the migration may overlap the next kernel
+static bool pipeline_mode(const kid_t* h) {
+  static const bool off = getenv("KID_NO_PIPELINE") != nullptr;
+  const KidParams& p = h->p;
+  return !off && h->d.nranks > 1 && !p.interactive_icebergs_on && !p.footloose && !p.mts && !p.static_icebergs &&
+         !p.runge_not_verlet && !h->calving_active && h->xstream != nullptr;
+}
+
+// slots [s0, s1) take the step (s0 a multiple of KID_BLOCK)
 template <bool FL, bool DG>
-static void launch_step(kid_t* h) {
+static void launch_step(kid_t* h, long long s0, long long s1) {
+  const long long n = s1 - s0;
   if (!FL && !DG && lean_config(h)) {
-    if (h->scatter_dense) { LAUNCH(h, (k_step<false, false, false, true, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
-    else { LAUNCH(h, (k_step<false, false, false, true, false>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
+    if (h->scatter_dense) { LAUNCH(h, (k_step<false, false, false, true, true>), n, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s1, s0); }
+    else { LAUNCH(h, (k_step<false, false, false, true, false>), n, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s1, s0); }
   }
-  else { LAUNCH(h, (k_step<FL, DG>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
+  else { LAUNCH(h, (k_step<FL, DG>), n, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s1, s0); }
+}
+
+// The migration of the bergs that left the tile in the PREVIOUS step, run on the second stream while the main
+// stream's kernel of THIS step is in flight (the host has just launched it): send_bergs_to_other_pes F:2997, the
+// thermodynamics of the previous step for the arrivals (I:5497), then this step for the arrivals, which the main
+// launch does not cover (they are appended at the next tile-aligned slot).  Every berg still takes each step
+// exactly once; bergs are independent in this mode (no interactions), the flux sums are atomic.
+template <bool DG>
+static int finish_deferred_exchange(kid_t* h) {
+  cudaStream_t main = h->stream;
+  const int prev = h->leaver_cur ^ 1;
+  h->stream = h->xstream;
+  int rc = KID_OK;
+  long long n_recv = 0;
+  const long long s0 = (h->n_slots + KID_BLOCK - 1) / KID_BLOCK * KID_BLOCK;
+  do {
+    if (cudaStreamWaitEvent(h->xstream, h->ev_kstep, 0) != cudaSuccess) { rc = fail(h, KID_ERR_CUDA, "cudaStreamWaitEvent failed"); break; }
+    h->b.leaver_list = h->leaver_lists[prev]; h->b.leaver_count = h->leaver_counts + prev;
+    rc = exchange_bergs(h, &n_recv, s0);
+    h->b.leaver_list = h->leaver_lists[h->leaver_cur]; h->b.leaver_count = h->leaver_counts + h->leaver_cur;
+    if (rc) break;
+    if (n_recv > 0) {
+      const long long s1 = s0 + n_recv;
+      if (DG) { LAUNCH(h, (k_thermo_range<false, true>), n_recv, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s0, s1, 0); }
+      else { LAUNCH(h, (k_thermo_range<false, false>), n_recv, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s0, s1, 0); }
+      launch_step<false, DG>(h, s0, s1);
+      h->n_slots = s1;
+      h->dirty_appended += n_recv;
+      h->tables_valid = 0;
+    }
+    if (cudaEventRecord(h->ev_xdone, h->xstream) != cudaSuccess) { rc = fail(h, KID_ERR_CUDA, "cudaEventRecord failed"); break; }
+    h->xdone_recorded = 1;
+  } while (0);
+  h->stream = main;
+  h->xchg_pending = 0;
+  return rc;
 }
 
 static cudaEvent_t pool_event(kid_t* h) {
@@ -1727,6 +1790,8 @@ static int step_core(kid_t* h) {
   }
   const bool fl = h->p.footloose != 0, dg = h->p.melt_diagnostics != 0;
   const bool mts = h->p.mts != 0;
+  // the second stream's work of the previous step (arrivals unpacked and stepped, leaver counter reset) is long done
+  if (h->xdone_recorded) { CK(cudaStreamWaitEvent(s, h->ev_xdone, 0)); h->xdone_recorded = 0; }
   if (mts && !h->mts_env_cached) {                         // first visit, I:5412-5414
     LAUNCH(h, k_mts_env_cache, h->n_slots, 128, h->g, h->b, h->dp, h->dcnt, h->n_slots);
     if (h->b.max_bonds > 0) LAUNCH(h, k_assign_n_bonds, h->n_slots, 128, h->b, h->n_slots);
@@ -1739,21 +1804,34 @@ static int step_core(kid_t* h) {
     } else if (ia) {
       CellTable ct{h->cell_start, h->cell_count};
       LAUNCH(h, k_ia_velocity, h->n_slots, KID_BLOCK, h->g, h->b, h->dp, ct, h->dcnt, h->n_slots);
-      if (fl) { LAUNCH(h, (k_step<true, false, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
-      else if (dg) { LAUNCH(h, (k_step<false, true, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
-      else { LAUNCH(h, (k_step<false, false, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
+      if (fl) { LAUNCH(h, (k_step<true, false, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots, 0LL); }
+      else if (dg) { LAUNCH(h, (k_step<false, true, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots, 0LL); }
+      else { LAUNCH(h, (k_step<false, false, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots, 0LL); }
       if (h->b.max_bonds > 0) LAUNCH(h, k_bond_address_update, h->n_slots, 128, h->b, h->n_slots);
     } else if (h->p.runge_not_verlet) {
       if (dg) { LAUNCH(h, (k_step_rk<true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
       else { LAUNCH(h, (k_step_rk<false>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
-    } else if (fl) { LAUNCH(h, (k_step<true, false, false>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
-    else if (dg) launch_step<false, true>(h); else launch_step<false, false>(h);
+    } else if (fl) { LAUNCH(h, (k_step<true, false, false>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots, 0LL); }
+    else if (dg) launch_step<false, true>(h, 0, h->n_slots); else launch_step<false, false>(h, 0, h->n_slots);
+  }
+  if (h->xchg_pending) {
+    // the previous step's migration, overlapped with the kernel just launched
+    int rc = dg ? finish_deferred_exchange<true>(h) : finish_deferred_exchange<false>(h);
+    if (rc) return rc;
   }
   CK(cudaEventRecord(ek, s));
-  if (h->d.nranks > 1) {
+  const bool sort_due = !ia && (h->steps_since_sort + 1 >= h->sort_interval || h->dirty_appended > h->n_slots / 8);
+  if (h->d.nranks > 1 && h->defer_ok && !sort_due && pipeline_mode(h)) {
+    // this step's leavers travel while the next step's kernel runs (finish_deferred_exchange)
+    CK(cudaEventRecord(h->ev_kstep, s));
+    h->xchg_pending = 1;
+    h->leaver_cur ^= 1;
+    h->b.leaver_list = h->leaver_lists[h->leaver_cur]; h->b.leaver_count = h->leaver_counts + h->leaver_cur;
+  } else if (h->d.nranks > 1) {
     // send_bergs_to_other_pes F:2997; arrivals do their thermodynamics of this step here (I:5497)
+    if (h->xdone_recorded) { CK(cudaStreamWaitEvent(s, h->ev_xdone, 0)); h->xdone_recorded = 0; }
     long long n_recv = 0;
-    int rc = exchange_bergs(h, &n_recv);
+    int rc = exchange_bergs(h, &n_recv, h->n_slots);
     if (rc) return rc;
     if (n_recv > 0) {
       long long s0 = h->n_slots, s1 = h->n_slots + n_recv;
@@ -1897,7 +1975,11 @@ extern "C" int32_t kid_step_resident(kid_t* h, int32_t nsteps, int32_t year, dou
   for (int s = 0; s < nsteps; s++) {
     zero_flux_fields(h, true);
     long long before = h->n_slots;
+    // the migration of step s may be deferred into step s+1 (its arrivals' melt then lands in the flux fields of
+    // step s+1): never for the last two steps, whose flux fields and berg state are what the caller sees
+    h->defer_ok = (s <= nsteps - 3) ? 1 : 0;
     int rc = step_core(h);
+    h->defer_ok = 0;
     if (rc) return rc;
     if (h->calving_active && h->n_slots == before) h->calving_active = 0;   // no input, nothing left to calve
   }
@@ -2044,7 +2126,23 @@ extern "C" int32_t kid_nccl_init(void** comm, const char* idbytes, int32_t nbyte
   ncclUniqueId id;
   memcpy(id.internal, idbytes, KID_NCCL_UNIQUE_ID_BYTES);
   ncclComm_t c = nullptr;
-  int rc = n.CommInitRank(&c, nranks, id, rank);
+  // The exchange moves a few hundred KB per step and runs beside the step kernel (step_core): a communicator with
+  // few CTAs keeps NCCL's polling kernels from holding SMs the step kernel wants (measured: k_step +7 % with the
+  // default channel count).  KID_NCCL_MAX_CTAS=0 keeps NCCL's default.
+  int rc = -1, ver = 0;
+  const char* ev = getenv("KID_NCCL_MAX_CTAS");
+  const int max_ctas = ev ? atoi(ev) : 2;
+  if (max_ctas > 0 && n.CommInitRankConfig && n.GetVersion && n.GetVersion(&ver) == ncclSuccess_ && ver >= 22800) {
+    const int undef = (int)0x80000000;
+    NcclConfig2280 cfg;
+    cfg.size = sizeof(cfg); cfg.magic = 0xcafebeefu; cfg.version = (unsigned)ver;
+    cfg.blocking = cfg.cgaClusterSize = cfg.minCTAs = cfg.splitShare = cfg.trafficClass = cfg.collnetEnable = cfg.CTAPolicy = undef;
+    cfg.shrinkShare = cfg.nvlsCTAs = cfg.nChannelsPerNetPeer = cfg.nvlinkCentricSched = undef;
+    cfg.netName = nullptr; cfg.commName = nullptr;
+    cfg.minCTAs = 1; cfg.maxCTAs = max_ctas;
+    rc = n.CommInitRankConfig(&c, nranks, id, rank, &cfg);
+  }
+  if (rc != ncclSuccess_) rc = n.CommInitRank(&c, nranks, id, rank);
   if (rc != ncclSuccess_) {
     g_init_error = std::string("ncclCommInitRank failed: ") + (n.GetErrorString ? n.GetErrorString(rc) : "?");
     return KID_ERR_COMM;

@@ -23,6 +23,8 @@ struct NcclApi {
   void* dl = nullptr;
   int (*GetUniqueId)(ncclUniqueId*) = nullptr;
   int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, void*) = nullptr;
+  int (*GetVersion)(int*) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
@@ -31,6 +33,13 @@ struct NcclApi {
   int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool ok() const { return dl && GetUniqueId && CommInitRank && Send && Recv && GroupStart && GroupEnd && AllGather; }
+};
+
+// ncclConfig_t as of NCCL 2.28 (nccl.h: ncclConfig_v22800); used only when the loaded library reports >= 2.28
+struct NcclConfig2280 {
+  size_t size; unsigned int magic; unsigned int version;
+  int blocking, cgaClusterSize, minCTAs, maxCTAs; const char* netName; int splitShare, trafficClass; const char* commName;
+  int collnetEnable, CTAPolicy, shrinkShare, nvlsCTAs, nChannelsPerNetPeer, nvlinkCentricSched;
 };
 
 inline NcclApi& nccl() {
@@ -45,6 +54,8 @@ inline NcclApi& nccl() {
     if (api.dl) {
       api.GetUniqueId = (int (*)(ncclUniqueId*))dlsym(api.dl, "ncclGetUniqueId");
       api.CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(api.dl, "ncclCommInitRank");
+      api.CommInitRankConfig = (int (*)(ncclComm_t*, int, ncclUniqueId, int, void*))dlsym(api.dl, "ncclCommInitRankConfig");
+      api.GetVersion = (int (*)(int*))dlsym(api.dl, "ncclGetVersion");
       api.CommDestroy = (int (*)(ncclComm_t))dlsym(api.dl, "ncclCommDestroy");
       api.GroupStart = (int (*)())dlsym(api.dl, "ncclGroupStart");
       api.GroupEnd = (int (*)())dlsym(api.dl, "ncclGroupEnd");
@@ -92,14 +103,14 @@ __host__ __device__ __forceinline__ int owner_rank(const DevLayout& L, int i, in
 
 // ------------------------------------------------- berg migration kernels
 // k_step appended the slot of every berg that left the tile to leaver_list (count in
-// cnt->n_leaver_list).  Pass 1: destination rank of each and the per-destination counts
+// *list_count).  Pass 1: destination rank of each and the per-destination counts
 // (send_bergs_to_other_pes F:3024-3050, all directions at once: NVSwitch reaches any rank, so
 // the reference's E/W-then-N/S relay F:3103-3106 is not needed).
 __global__ void k_leaver_dest(const __grid_constant__ DevLayout L, const int32_t* __restrict__ ine,
                               const int32_t* __restrict__ jne, const int32_t* __restrict__ list,
-                              const DevCounters* __restrict__ cnt, int32_t list_cap,
+                              const unsigned long long* __restrict__ list_count, int32_t list_cap,
                               int32_t* __restrict__ dest, int32_t* __restrict__ counts /* [nranks], zeroed */) {
-  long long n = (long long)cnt->n_leaver_list;
+  long long n = (long long)*list_count;
   if (n > list_cap) n = list_cap;
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
     int32_t s = list[k];
@@ -113,10 +124,10 @@ __global__ void k_leaver_dest(const __grid_constant__ DevLayout L, const int32_t
 // pass 2: pack_berg_into_buffer2 (F:3250) into the per-destination regions; the slot is freed
 // (delete_iceberg_from_list F:3040)
 __global__ void k_pack_leavers(const __grid_constant__ DevLayout L, const __grid_constant__ DevBergs b, const int32_t* __restrict__ list,
-                               const int32_t* __restrict__ dest, const DevCounters* __restrict__ cnt,
+                               const int32_t* __restrict__ dest, const unsigned long long* __restrict__ list_count,
                                int32_t list_cap, const int32_t* __restrict__ offsets /* [nranks] */,
                                int32_t* __restrict__ cursor /* [nranks], zeroed */, double* __restrict__ sendbuf, int rec_w) {
-  long long n = (long long)cnt->n_leaver_list;
+  long long n = (long long)*list_count;
   if (n > list_cap) n = list_cap;
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
     int32_t s = list[k];

@@ -132,6 +132,7 @@ struct DevBergs {
   int32_t *ine, *jne, *start_year;
   uint8_t *flags, *halo_code;
   int32_t* leaver_list;       // slots of the bergs that left the tile this step (multi-rank only)
+  unsigned long long* leaver_count;   // entries of leaver_list filled this step (two list/count pairs alternate, step_core)
   int64_t leaver_cap;
   // bonds, type(bond) F:362-386: max_bonds half-bonds per berg, entry k of slot s at [k*capacity + s];
   // other_id == 0 marks an empty entry, other_slot is re-resolved after every sort (connect_all_bonds F:4963)

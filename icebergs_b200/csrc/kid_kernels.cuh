@@ -382,7 +382,7 @@ __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, c
   if (route == 1) {
     left = true;
     b.flags[s] = flags | BF_LEAVER;
-    unsigned long long k = atomicAdd(&cnt->n_leaver_list, 1ull);      // rare: a berg in a few thousand per step
+    unsigned long long k = atomicAdd(b.leaver_count, 1ull);      // rare: a berg in a few thousand per step
     if ((long long)k < b.leaver_cap) b.leaver_list[k] = (int32_t)s;
     else atomicOr(&cnt->error_flags, (unsigned)KID_DEVERR_CAPACITY);
   }
@@ -432,8 +432,10 @@ __device__ __forceinline__ void prefetch_tile_ahead(const DevBergs& b, long long
 template <bool FOOTLOOSE, bool DIAG, bool SPLIT = false, bool LEAN = false, bool DENSE = true>
 __global__ void __launch_bounds__(KID_BLOCK, KID_MINBLOCKS)
 k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
-       const __grid_constant__ DevParams p, DevCounters* __restrict__ cnt, long long n_slots) {
-  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+       const __grid_constant__ DevParams p, DevCounters* __restrict__ cnt, long long n_slots, long long s_base) {
+  // s_base: first slot of the launch (0, or the tile-aligned start of the bergs that arrived while the main
+  // launch of this step was already running, see step_core)
+  long long s = s_base + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = s < n_slots;
   const long long sl = in_range ? s : 0;          // out-of-range lanes read slot 0 and are masked by flags
   if (!SPLIT) prefetch_tile_ahead(b, n_slots);
@@ -450,7 +452,7 @@ k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
   prefetch_l1(&b.f64[C_LON][sl]); prefetch_l1(&b.f64[C_MASS_SCALING][sl]);
   prefetch_l1(&b.f64[C_MASS_OF_BITS][sl]); prefetch_l1(&b.f64[C_HEAT_DENSITY][sl]);
   if (!in_range) in.flags = 0;
-  bool owned = (in.flags & BF_ALIVE) && !(in.flags & BF_HALO);
+  bool owned = (in.flags & BF_ALIVE) && !(in.flags & (BF_HALO | BF_LEAVER));   // leavers wait for the (overlapped) exchange
   if (owned && cell_on_pe(g, in.i, in.j)) {
     // corner positions of the berg's cell (pos_within_cell, a few hundred instructions from now)
     int ne = gidx(g, in.i, in.j);
@@ -589,7 +591,7 @@ k_step_rk(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
     if (route == 1) {
       left = true;
       b.flags[s] = flags | BF_LEAVER;
-      unsigned long long k = atomicAdd(&cnt->n_leaver_list, 1ull);
+      unsigned long long k = atomicAdd(b.leaver_count, 1ull);
       if ((long long)k < b.leaver_cap) b.leaver_list[k] = (int32_t)s;
       else atomicOr(&cnt->error_flags, (unsigned)KID_DEVERR_CAPACITY);
     } else if (route == 2) {

@@ -128,6 +128,30 @@ def test_in_process_ranks_resident_steps_and_sort():
     grp.close()
 
 
+def test_overlapped_migration_in_resident_steps():
+    """kid_step_resident defers the migration of a step into the next step's kernel (second stream, arrivals
+    stepped separately): every berg still takes each step once, and the flux fields the caller sees -- the last
+    step's -- hold exactly that step's melt."""
+    case = Case(96, 48, 12000, dt=43200.0, old_bug_bilin=0)
+    grp = parallel.LocalGroup(4)
+    ranks = Ranks(case, 4, lambda r: grp.domain(case.gni, case.gnj, r, halo=case.halo), grp.run)
+    o = case.make_oracle()
+    over = dict(uo=1.2, vo=0.15, tauxa=15.0)
+    fast = {k: np.full_like(case.forcing[k], v) for k, v in over.items()}
+    ranks.step(over); run_oracle(o, case, **fast)
+    sent0 = sum(c["n_sent"] for c in ranks.counters())
+    ranks.resident(12); o.step_again(12, 1, 0.0)
+    assert_bergs_match(ranks.bergs(), o.get_bergs(NAMES), rtol=1e-8, context="4 ranks, 13 steps, overlapped migration")
+    assert ranks.owners_ok()
+    assert sum(c["n_sent"] for c in ranks.counters()) > sent0 + 500, "the case does not exercise the exchange"
+    hl = case.halo
+    for fid in FLUX_FIELDS:
+        want = o.grid_field(fid)[hl:hl + case.gnj, hl:hl + case.gni]
+        assert grid_rel(ranks.field(fid), want) < 1e-9, f"grid field {fid} after the resident steps"
+    ranks.end()
+    grp.close()
+
+
 def test_nccl_ranks_match_single_rank_oracle():
     """Same check over NCCL: one rank per GPU (threads of this process), needs >= 2 GPUs."""
     import torch
