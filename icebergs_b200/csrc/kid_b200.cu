@@ -866,7 +866,13 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
     CK(cudaMalloc(&h->leaver_counts, 2 * sizeof(unsigned long long)));
     CK(cudaMemsetAsync(h->leaver_counts, 0, 2 * sizeof(unsigned long long), h->stream));
     b.leaver_list = h->leaver_lists[0]; b.leaver_count = h->leaver_counts;
-    CK(cudaStreamCreateWithFlags(&h->xstream, cudaStreamNonBlocking));
+    {
+      // highest priority: the block scheduler hands freed SM slots to the small exchange kernels first, otherwise
+      // they would wait behind the ~1e5 CTAs of the step kernel and the overlap would be lost (measured)
+      int lo = 0, hi = 0;
+      CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CK(cudaStreamCreateWithPriority(&h->xstream, cudaStreamNonBlocking, hi));
+    }
     CK(cudaEventCreateWithFlags(&h->ev_kstep, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_xdone, cudaEventDisableTiming));
     CK(cudaMalloc(&h->leaver_dest, sizeof(int32_t) * b.leaver_cap));
@@ -1122,7 +1128,7 @@ static int sort_bergs(kid_t* h);
 
 // set_conglom_ids F:2601-2646 (only needed by the conglomerate-contact branch of interactive_force, I:512)
 static int set_conglom_ids(kid_t* h) {
-  if (!((h->p.contact_distance > 0.) || (h->p.contact_spring_coef != h->p.spring_coef))) return KID_OK;
+  if (!(h->p.mts || (h->p.contact_distance > 0.) || (h->p.contact_spring_coef != h->p.spring_coef))) return KID_OK;
   LAUNCH(h, k_conglom_init, h->n_slots, 256, h->b, h->n_slots);
   if (h->b.max_bonds == 0) return KID_OK;
   for (int it = 0; it < 100000; it++) {
@@ -1599,11 +1605,14 @@ static int evolve_mts(kid_t* h) {
     if (ii > 10000) return fail(h, KID_ERR_STATE, "kid: MTS force_convergence (part 1) did not converge in 10000 passes");
   }
   h->mts_outer_iters = ii;
+  const bool dem = p.dem != 0;
+  if (dem && !p.break_bonds_on_sub_steps) LAUNCH(h, k_dem_break_bonds, ns, 256, h->b, h->mp, ns);     // I:6738
   LAUNCH(h, k_mts_part2, ns, 256, h->b, h->dp, ns, fc);
   // part 3: fast sub-steps, bonded interactions only
   const double dtf = h->mp.dt_fast;
   const bool iterate = fc && !p.explicit_inner_mts;
-  if (!iterate && p.explicit_inner_mts && !p.short_step_mts_grounding && ns <= 4096) {
+  const bool brk = dem && p.break_bonds_on_sub_steps && !p.use_broken_bonds_for_substep_contact;
+  if (!iterate && p.explicit_inner_mts && ns <= 4096 && !getenv("KID_MTS_NO_ONE_CTA")) {
     // a few thousand elements: the whole sub-step loop in one CTA, __syncthreads() between the sweeps
     k_mts_substeps_one_cta<<<1, 1024, 0, h->stream>>>(h->g, h->b, h->dp, h->mp, ct, h->dcnt, ns, dtf, p.mts_sub_steps);
     h->launches++;
@@ -1616,6 +1625,7 @@ static int evolve_mts(kid_t* h) {
       while (!fin) {
         jj++;
         if (iterate) CK(cudaMemsetAsync(h->dsums, 0, sizeof(MtsSums), h->stream));
+        if (dem) LAUNCH(h, k_dem_pairs, ns, 128, h->b, h->dp, h->mp, h->dcnt, ns, dtf);
         LAUNCH(h, k_mts_vel, ns, 128, h->g, h->b, h->dp, h->mp, ct, h->dcnt, h->dsums, ns, dtf, jj);
         if (iterate && !last) {
           MtsSums sm;
@@ -1633,10 +1643,12 @@ static int evolve_mts(kid_t* h) {
         if (fc && !fin) LAUNCH(h, k_mts_vel_retry, ns, 256, h->b, ns, dtf);
         if (jj > 10000) return fail(h, KID_ERR_STATE, "kid: MTS force_convergence (sub-step) did not converge in 10000 passes");
       }
-      LAUNCH(h, k_mts_sub_end, ns, 256, h->b, ns, fc);
+      LAUNCH(h, k_mts_sub_end, ns, 256, h->b, h->dp, h->mp, ns, dtf);
+      if (brk) LAUNCH(h, k_dem_break_bonds, ns, 256, h->b, h->mp, ns);
     }
   }
   LAUNCH(h, k_mts_finish, ns, 128, h->g, h->b, h->dp, h->dcnt, ns);
+  h->mp.no_frac_first_ts = 0;                               // I:7077
   return KID_OK;
 }
 

@@ -122,7 +122,9 @@ enum BergCol : int {
   C_UO = C_NINTER, C_VO, C_UI, C_VI, C_UA, C_VA, C_SSH_X, C_SSH_Y, C_SST, C_SSS, C_CN, C_HI, C_OD,
   C_AXN_FAST, C_AYN_FAST, C_BXN_FAST, C_BYN_FAST,
   C_NMTS,
-  C_NCOLS = C_NMTS
+  C_ANG_VEL = C_NMTS, C_ANG_ACCEL, C_ROT,        // dem (F:355-357)
+  C_NDEM,
+  C_NCOLS = C_NDEM
 };
 
 struct DevBergs {
@@ -143,7 +145,10 @@ struct DevBergs {
   double* bond_length;
   int32_t* n_bonds;           // assign_n_bonds F:4617 (MTS contact search skips interior elements)
   int32_t* bond_broken;       // dem only, else nullptr
+  // dem bond history and the saved pair forces (type(bond) F:372-386, save_bond_forces F:53), same layout as bond_length
+  double* bond_dem[11];
 };
+enum BondDem : int { BD_TANGD1 = 0, BD_TANGD2, BD_REL_ROT, BD_NSTRESS, BD_SSTRESS, BD_FX, BD_FY, BD_FDX, BD_FDY, BD_T, BD_TD, BD_N };
 
 // device-side counters (one struct in HBM per handle)
 struct DevCounters {

@@ -17,8 +17,12 @@ namespace kid {
 
 struct MtsParams {
   double dt_fast, constant_length, constant_width, constant_area, constant_radius;
+  double dem_spring_coef, dem_damping_coef, dem_K_damp, poisson, frac_thres_n, frac_thres_t;
+  double dem_tests_start_lon, dem_tests_end_lon;
   int32_t force_convergence, explicit_inner_mts, short_step_mts_grounding, radius_based_drag;
-  int32_t constant_interaction_LW, use_grounding_torque, pad0, pad1;
+  int32_t constant_interaction_LW, use_grounding_torque;
+  int32_t ignore_tangential_force, orig_dem_moment_of_inertia, break_bonds_on_sub_steps, fracture_criterion_stress;
+  int32_t use_broken_bonds_for_substep_contact, dem_beam_test, no_frac_first_ts, pad0;
 };
 
 // convergence sums of one sweep (usum, usum1, usum2 of I:6600) + had_collision
@@ -272,6 +276,222 @@ __device__ __noinline__ void accel_explicit_inner_mts(const DevGrid& g, const De
   if (p.override_iceberg_velocities) { ax = 0.0; ay = 0.0; axn = 0.0; ayn = 0.0; }
 }
 
+
+// the bergs the sub-steps evolve: static_berg < 0.5 and conglom_id /= 0 (I:6756, I:6792, ...)
+__device__ __forceinline__ bool mts_active(const DevBergs& b, long long s, uint8_t flags) {
+  return (flags & BF_ALIVE) && !(flags & BF_STATIC) && b.conglom_id[s] != 0;
+}
+
+// ------------------------------------------------------------------ DEM (dem=.true.)
+// calculate_unbonded_same_conglom_dem_force I:807-955
+__device__ __noinline__ void dem_unbonded_force(const DevBergs& b, const DevParams& p, const MtsParams& mp, long long s,
+                                                long long o, double& IA_x, double& IA_y, double& IAd_x, double& IAd_y,
+                                                double u0, double v0, double u1, double v1) {
+  if (b.id[s] == b.id[o] || b.f64[C_FL_K][s] == -1. || b.f64[C_FL_K][o] == -1.) return;
+  double dlon = b.f64[C_LON_OLD][s] - b.f64[C_LON_OLD][o], dlat = b.f64[C_LAT_OLD][s] - b.f64[C_LAT_OLD][o], dx_dlon, dy_dlat;
+  convert_from_grid_to_meters(p, 0.5 * (b.f64[C_LAT_OLD][s] + b.f64[C_LAT_OLD][o]), dx_dlon, dy_dlat);
+  double rx = dlon * dx_dlon, ry = dlat * dy_dlat, r2 = (rx * rx) + (ry * ry), R1, R2, M1, M2;
+  if (mp.constant_interaction_LW) {
+    if ((2 * mp.constant_radius) * (2 * mp.constant_radius) <= r2) return;
+    R1 = mp.constant_radius; R2 = R1;
+    M1 = mp.constant_area * b.f64[C_THICKNESS][s] * p.rho_bergs; M2 = mp.constant_area * b.f64[C_THICKNESS][o] * p.rho_bergs;
+  } else {
+    R1 = mts_ia_radius(p, b.f64[C_LENGTH][s] * b.f64[C_WIDTH][s]); R2 = mts_ia_radius(p, b.f64[C_LENGTH][o] * b.f64[C_WIDTH][o]);
+    if ((R1 + R2) * (R1 + R2) <= r2) return;
+    M1 = b.f64[C_MASS][s]; M2 = b.f64[C_MASS][o];
+  }
+  double r_dist = sqrt(r2), u2 = b.f64[C_UVEL_OLD][o], v2 = b.f64[C_VVEL_OLD][o], M_min = fmin(M1, M2), crit_dist = R1 + R2;
+  double spring_coef = p.spring_coef, radial = p.radial_damping_coef, tang = p.tangental_damping_coef;
+  if (p.critical_interaction_damping_on) {
+    radial = 2. * sqrt(spring_coef);
+    if (p.tang_crit_int_damp_on) tang = (2. * sqrt(spring_coef)) / 4;
+  }
+  if (!((r_dist > 0.) && (r_dist < crit_dist))) return;
+  double accel_spring = spring_coef * (M_min / M1) * (crit_dist - r_dist);
+  IA_x += (accel_spring * (rx / r_dist)); IA_y += (accel_spring * (ry / r_dist));
+  double rr = r_dist * r_dist, P_11 = (rx * rx) / rr, P_12 = (rx * ry) / rr, P_22 = (ry * ry) / rr;
+  double Pia_11 = 0., Pia_12 = 0., Pia_22 = 0.;
+  for (int pass = 0; pass < 2; pass++) {
+    double coef = (pass == 0 ? radial : tang) * (M_min / M1);
+    if (p.scale_damping_by_pmag) {
+      double a1 = ((P_11 * (u2 - u1)) + (P_12 * (v2 - v1))), a2 = ((P_12 * (u2 - u1)) + (P_22 * (v2 - v1)));
+      double b1 = ((P_11 * (u2 - u0)) + (P_12 * (v2 - v0))), b2 = ((P_12 * (u2 - u0)) + (P_22 * (v2 - v0)));
+      coef = coef * (0.5 * (sqrt((a1 * a1) + (a2 * a2)) + sqrt((b1 * b1) + (b2 * b2))));
+    }
+    Pia_11 += coef * P_11; Pia_12 += coef * P_12; Pia_22 += coef * P_22;
+    P_11 = 1 - P_11; P_12 = -P_12; P_22 = 1 - P_22;
+  }
+  double du = b.f64[C_UVEL_OLD][o] - b.f64[C_UVEL_OLD][s], dv = b.f64[C_VVEL_OLD][o] - b.f64[C_VVEL_OLD][s];
+  IAd_x += Pia_11 * du + Pia_12 * dv;
+  IAd_y += Pia_12 * du + Pia_22 * dv;
+}
+
+// index of the half-bond of berg o that points back at berg s (current_bond%other_bond, F:5094-5123); -1 if none
+__device__ __forceinline__ long long dem_reverse_bond(const DevBergs& b, long long s, long long o) {
+  const int64_t my_id = b.id[s];
+  for (int q = 0; q < b.max_bonds; q++) {
+    long long slot = (long long)q * b.capacity + o;
+    if (b.bond_other_id[slot] == my_id) return slot;
+  }
+  return -1;
+}
+
+// calculate_force_dem I:959-1242 for the pair (s, o), evaluated by the berg that comes first in the reference's
+// traversal (the lower slot of the cell-sorted store); results are stored on both half-bonds (save_bond_forces F:53)
+// and summed per berg afterwards (k_dem_sum).  Returns true when the bond broke in this sub-step.
+__device__ __noinline__ bool dem_bond_force(const DevBergs& b, const DevParams& p, const MtsParams& mp, DevCounters* cnt,
+                                            long long s, long long o, long long bs /* my half-bond */, double dt) {
+  if (b.id[s] == b.id[o] || b.f64[C_FL_K][s] == -1. || b.f64[C_FL_K][o] == -1.) return false;
+  const double hexdenom = 1. / (2. * sqrt(3.));
+  const double T1 = b.f64[C_THICKNESS][s], T2 = b.f64[C_THICKNESS][o];
+  double M1, M2, R1, R2, Rmin, l0, T_Rmin;
+  if (mp.constant_interaction_LW) {
+    M1 = mp.constant_area * T1 * p.rho_bergs; M2 = mp.constant_area * T2 * p.rho_bergs;
+    R1 = mp.constant_radius; R2 = R1; Rmin = R1; l0 = 2 * R1; T_Rmin = T2;
+  } else {
+    M1 = b.f64[C_MASS][s]; M2 = b.f64[C_MASS][o];
+    double A1 = b.f64[C_LENGTH][s] * b.f64[C_WIDTH][s], A2 = b.f64[C_LENGTH][o] * b.f64[C_WIDTH][o];
+    if (p.hexagonal_icebergs) { R1 = sqrt(A1 * hexdenom); R2 = sqrt(A2 * hexdenom); } else { R1 = 0.5 * sqrt(A1); R2 = 0.5 * sqrt(A2); }
+    if (R1 < R2) { Rmin = R1; T_Rmin = T1; } else { Rmin = R2; T_Rmin = T2; }
+    l0 = R1 + R2;
+  }
+  double dx_dlon, dy_dlat;
+  convert_from_grid_to_meters(p, 0.5 * (b.f64[C_LAT_OLD][s] + b.f64[C_LAT_OLD][o]), dx_dlon, dy_dlat);
+  double rx = (b.f64[C_LON_OLD][s] - b.f64[C_LON_OLD][o]) * dx_dlon, ry = (b.f64[C_LAT_OLD][s] - b.f64[C_LAT_OLD][o]) * dy_dlat;
+  double len = sqrt((rx * rx) + (ry * ry));
+  b.bond_length[bs] = len;
+  if (len == 0) { atomicOr(&cnt->error_flags, 8192u); return false; }
+  const long long bo = dem_reverse_bond(b, s, o);
+  double n1 = rx / len, n2 = ry / len, half_delta = 0.5 * (l0 - len);
+  double RR1 = R1 - half_delta, RR2 = R2 - half_delta;
+  double RR1x = RR1 * n1, RR1y = RR1 * n2, RR2x = RR2 * n1, RR2y = RR2 * n2;
+  double L = 2.0 * (Rmin + (Rmin - half_delta) * fabs(R1 - R2) / len);
+  double Thick = T_Rmin + (Rmin - half_delta) * fabs(T1 - T2) / len;
+  double Fn_x = mp.dem_spring_coef * Thick * 2. * half_delta * L / l0, Fn_y = Fn_x * n2; Fn_x = Fn_x * n1;
+  double ur = b.f64[C_UVEL_OLD][s] - b.f64[C_UVEL_OLD][o], vr = b.f64[C_VVEL_OLD][s] - b.f64[C_VVEL_OLD][o];
+  const double av1 = b.f64[C_ANG_VEL][s], av2 = b.f64[C_ANG_VEL][o];
+  double tangd1 = b.bond_dem[BD_TANGD1][bs], tangd2 = b.bond_dem[BD_TANGD2][bs];
+  {
+    double tmag = tangd1 * tangd1 + tangd2 * tangd2, tangdotnt = tangd1 * n1 + tangd2 * n2;
+    double t1p = tangd1 - tangdotnt * n1, t2p = tangd2 - tangdotnt * n2, tmagp = t1p * t1p + t2p * t2p;
+    if (tmagp > 0.) { double t_rat = sqrt(tmag / tmagp); t1p = t_rat * t1p; t2p = t_rat * t2p; } else { t1p = 0.; t2p = 0.; }
+    double rotu = RR1y * av1 + RR2y * av2, rotv = -(RR1x * av1 + RR2x * av2);
+    double ur2 = ur + rotu, vr2 = vr + rotv, up = ur2 * n1 + vr2 * n2, vp = up * n2; up = up * n1;
+    tangd1 = t1p + (ur2 - up) * dt; tangd2 = t2p + (vr2 - vp) * dt;
+  }
+  double ss_factor = -L * Thick * mp.dem_spring_coef / (l0 * 2.0 * (1.0 + mp.poisson));
+  if (mp.ignore_tangential_force) ss_factor = 0.;
+  double Fs_x = ss_factor * tangd1, Fs_y = ss_factor * tangd2;
+  double sstress = sqrt(Fs_x * Fs_x + Fs_y * Fs_y) / (L * Thick);
+  double Ts = -(RR1x * Fs_y - RR1y * Fs_x);
+  double rel_rot = b.bond_dem[BD_REL_ROT][bs] + (av1 - av2) * dt;
+  double theta, Tr;
+  const double drot = b.f64[C_ROT][s] - b.f64[C_ROT][o];
+  if (!mp.orig_dem_moment_of_inertia) { theta = sin(drot); Tr = -mp.dem_spring_coef * pow(L, 3.) * Thick * theta / (12. * l0); }
+  else { theta = drot; Tr = -(mp.dem_spring_coef / l0) * (2. / 3.) * pow(0.5 * L, 3.) * Thick * theta; }
+  double nstress = (mp.dem_spring_coef / l0) * (-2 * half_delta + fabs(theta * 0.5 * L));
+  double damping_coef = mp.dem_damping_coef * sqrt(mp.dem_K_damp * M1 * M2 / (M1 + M2));
+  double F_x, F_y, Fd_x, Fd_y, T, T_d, T_other;
+  bool broke = false;
+  if (mp.break_bonds_on_sub_steps && (nstress > mp.frac_thres_n || sstress > mp.frac_thres_t)) {
+    broke = true;
+    T = 0.; T_d = 0.; T_other = 0.;
+    if (nstress < 0) { F_x = Fn_x; F_y = Fn_y; Fd_x = -damping_coef * ur; Fd_y = -damping_coef * vr; }   // sheared under compression
+    else { F_x = 0.; F_y = 0.; Fd_x = 0.; Fd_y = 0.; }
+    b.bond_broken[bs] = 2;          // 2 = broke in this sub-step: its stored forces still count once (I:1158-1196),
+    if (bo >= 0) b.bond_broken[bo] = 2;   //     mts_phase_end turns it into 1
+    if (mp.use_broken_bonds_for_substep_contact) { atomicSub(&b.n_bonds[s], 1); atomicSub(&b.n_bonds[o], 1); }
+  } else {
+    F_x = Fn_x + Fs_x; F_y = Fn_y + Fs_y; Fd_x = -damping_coef * ur; Fd_y = -damping_coef * vr;
+    T = Ts + Tr; T_d = -damping_coef * (av1 - av2); T_other = Ts - Tr;
+  }
+  b.bond_dem[BD_TANGD1][bs] = tangd1; b.bond_dem[BD_TANGD2][bs] = tangd2; b.bond_dem[BD_REL_ROT][bs] = rel_rot;
+  b.bond_dem[BD_NSTRESS][bs] = nstress; b.bond_dem[BD_SSTRESS][bs] = sstress;
+  b.bond_dem[BD_FX][bs] = F_x; b.bond_dem[BD_FY][bs] = F_y; b.bond_dem[BD_FDX][bs] = Fd_x; b.bond_dem[BD_FDY][bs] = Fd_y;
+  b.bond_dem[BD_T][bs] = T; b.bond_dem[BD_TD][bs] = T_d;
+  if (bo >= 0) {
+    b.bond_length[bo] = len;
+    b.bond_dem[BD_TANGD1][bo] = -tangd1; b.bond_dem[BD_TANGD2][bo] = -tangd2; b.bond_dem[BD_REL_ROT][bo] = -rel_rot;
+    b.bond_dem[BD_NSTRESS][bo] = nstress; b.bond_dem[BD_SSTRESS][bo] = sstress;
+    b.bond_dem[BD_FX][bo] = -F_x; b.bond_dem[BD_FY][bo] = -F_y; b.bond_dem[BD_FDX][bo] = -Fd_x; b.bond_dem[BD_FDY][bo] = -Fd_y;
+    b.bond_dem[BD_T][bo] = T_other; b.bond_dem[BD_TD][bo] = -T_d;
+  }
+  return broke;
+}
+
+// first half of the explicit DEM sub-step: every intact bond once, by its first berg
+__device__ __forceinline__ void dem_pair_phase(const DevBergs& b, const DevParams& p, const MtsParams& mp, DevCounters* cnt,
+                                               long long s, double dt) {
+  for (int k = b.max_bonds - 1; k >= 0; k--) {
+    long long slot = (long long)k * b.capacity + s;
+    if (b.bond_other_id[slot] == 0) continue;
+    int32_t o = b.bond_other_slot[slot];
+    if (o < 0) { atomicOr(&cnt->error_flags, 256u); continue; }
+    if (b.bond_broken[slot] != 0) continue;
+    // the pair belongs to the berg the reference's sweep reaches first (lower slot); a partner the sweep skips
+    // (static) leaves it to this berg
+    if ((long long)o < s && mts_active(b, o, b.flags[o])) continue;
+    dem_bond_force(b, p, mp, cnt, s, o, slot, dt);
+  }
+}
+
+// second half: the berg's sums (accel_explicit_inner_mts I:1756-1915 with dem)
+__device__ __noinline__ void dem_sum_phase(const DevGrid& g, const DevBergs& b, const DevParams& p, const MtsParams& mp,
+                                           const CellTable& ct, DevCounters* cnt, long long s, int i, int j, double uvel0,
+                                           double vvel0, double dt, double& ax, double& ay, double& axn, double& ayn) {
+  double u_star = uvel0 + (axn * (dt / 2.)), v_star = vvel0 + (ayn * (dt / 2.));
+  double IA_x = 0., IA_y = 0., IAd_x = 0., IAd_y = 0., F_x = 0., F_y = 0., T = 0., Fd_x = 0., Fd_y = 0., T_d = 0.;
+  for (int k = b.max_bonds - 1; k >= 0; k--) {
+    long long slot = (long long)k * b.capacity + s;
+    if (b.bond_other_id[slot] == 0) continue;
+    int32_t o = b.bond_other_slot[slot];
+    if (o < 0) continue;
+    // a bond broken before this sub-step acts as contact between unbonded elements of one conglomerate (I:1789)
+    if (b.bond_broken[slot] == 1) { dem_unbonded_force(b, p, mp, s, o, IA_x, IA_y, IAd_x, IAd_y, uvel0, vvel0, uvel0, vvel0); continue; }
+    F_x += b.bond_dem[BD_FX][slot]; F_y += b.bond_dem[BD_FY][slot]; Fd_x += b.bond_dem[BD_FDX][slot]; Fd_y += b.bond_dem[BD_FDY][slot];
+    T += b.bond_dem[BD_T][slot]; T_d += b.bond_dem[BD_TD][slot];
+  }
+  const bool run_contact = !((b.n_bonds[s] == b.max_bonds) || mp.use_broken_bonds_for_substep_contact);
+  if (run_contact) {
+    const int32_t my_cong = b.conglom_id[s];
+    for (int grdj = max(j - 1, g.jsd + 1); grdj <= min(j + 1, g.jed); grdj++)
+      for (int grdi = max(i - 1, g.isd + 1); grdi <= min(i + 1, g.ied); grdi++) {
+        int c = gidx(g, grdi, grdj);
+        int n = ct.count[c];
+        long long o0 = ct.start[c];
+        for (int k = 0; k < n; k++) {
+          long long o = o0 + k;
+          if (b.conglom_id[o] != my_cong || !(b.n_bonds[o] < b.max_bonds)) continue;
+          bool partner = false;
+          for (int q = 0; q < b.max_bonds; q++) {
+            long long slot = (long long)q * b.capacity + s;
+            if (b.bond_other_id[slot] != 0 && b.bond_other_slot[slot] == (int32_t)o) partner = true;
+          }
+          if (!partner) dem_unbonded_force(b, p, mp, s, o, IA_x, IA_y, IAd_x, IAd_y, uvel0, vvel0, uvel0, vvel0);
+        }
+      }
+  }
+  if (mp.dem_beam_test == 1) {                      // simply supported beam, I:1862-1869
+    double sl = b.f64[C_START_LON][s];
+    if (sl == mp.dem_tests_start_lon || sl == mp.dem_tests_end_lon) { F_y = 0.0; Fd_y = 0.0; }
+    else if (sl == 0.5 * (mp.dem_tests_start_lon + mp.dem_tests_end_lon)) F_y = F_y - 1.5e5;
+  } else if (mp.dem_beam_test == 2) {               // cantilever, I:1870-1876
+    if (b.f64[C_START_LON][s] == mp.dem_tests_end_lon) F_y = F_y - 1.5e10 / 3.;
+  }
+  double M, R1;
+  if (mp.constant_interaction_LW) {
+    M = mp.constant_length * mp.constant_width * b.f64[C_THICKNESS][s] * p.rho_bergs;
+    R1 = mts_ia_radius(p, mp.constant_length * mp.constant_width);
+  } else { M = b.f64[C_MASS][s]; R1 = mts_ia_radius(p, b.f64[C_LENGTH][s] * b.f64[C_WIDTH][s]); }
+  IA_x += F_x / M; IA_y += F_y / M; IAd_x += Fd_x / M; IAd_y += Fd_y / M;
+  b.f64[C_ANG_ACCEL][s] = (T + T_d) / (0.5 * M * (R1 * R1));
+  axn = IA_x + IAd_x; ayn = IA_y + IAd_y;
+  ax = 0.5 * (axn + 0.0); ay = 0.5 * (ayn + 0.0);
+  double uveln = u_star + dt * ax, vveln = v_star + dt * ay;
+  mts_speed_ticket(g, p, cnt, i, j, uveln, vveln, dt);
+  if (p.override_iceberg_velocities) { ax = 0.0; ay = 0.0; axn = 0.0; ayn = 0.0; }
+}
+
 __device__ __forceinline__ void mts_block_sums(MtsSums* out, double a, double b_, double c) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) { a += shfl_down_d(a, d); b_ += shfl_down_d(b_, d); c += shfl_down_d(c, d); }
@@ -282,10 +502,6 @@ __device__ __forceinline__ void mts_block_sums(MtsSums* out, double a, double b_
   }
 }
 
-// the bergs the sub-steps evolve: static_berg < 0.5 and conglom_id /= 0 (I:6756, I:6792, ...)
-__device__ __forceinline__ bool mts_active(const DevBergs& b, long long s, uint8_t flags) {
-  return (flags & BF_ALIVE) && !(flags & BF_STATIC) && b.conglom_id[s] != 0;
-}
 
 // part 1, one pass of the convergence loop I:6660-6706
 __global__ void __launch_bounds__(128)
@@ -344,11 +560,11 @@ __global__ void k_mts_part2(const __grid_constant__ DevBergs b, const __grid_con
   }
 }
 
-// sub-step position update I:6790-6831
-__global__ void k_mts_pos(const __grid_constant__ DevBergs b, const __grid_constant__ DevParams p, long long n_slots, double dt) {
-  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_slots) return;
-  if (!mts_active(b, s, b.flags[s])) return;
+// ---- the sweeps of one fast sub-step as per-berg phases (called from the per-sweep kernels or, for small
+// populations, from the single-CTA loop below)
+
+// position update I:6790-6831
+__device__ __forceinline__ void mts_phase_pos(const DevBergs& b, const DevParams& p, long long s, double dt) {
   const double dt_2 = 0.5 * dt;
   double lon1 = b.f64[C_LON][s], lat1 = b.f64[C_LAT][s], uvel1 = b.f64[C_UVEL][s], vvel1 = b.f64[C_VVEL][s];
   double axn = b.f64[C_AXN_FAST][s], ayn = b.f64[C_AYN_FAST][s], bxn = b.f64[C_BXN_FAST][s], byn = b.f64[C_BYN_FAST][s];
@@ -367,58 +583,121 @@ __global__ void k_mts_pos(const __grid_constant__ DevBergs b, const __grid_const
   b.f64[C_VVEL_OLD][s] = vvel1 + dt_2 * (ayn + bxn);          // sic: bxn_fast, I:6827
 }
 
-// sub-step velocity update, one pass of I:6846-6934
+// velocity update, one pass of I:6846-6934; su* = this berg's terms of the convergence norms
+__device__ __forceinline__ void mts_phase_vel(const DevGrid& g, const DevBergs& b, const DevParams& p, const MtsParams& mp,
+                                              const CellTable& ct, DevCounters* cnt, long long s, double dt, int jj,
+                                              bool iterate, double& su, double& su1, double& su2) {
+  const double dt_2 = 0.5 * dt;
+  double latn = b.f64[C_LAT][s], lonn = b.f64[C_LON][s];
+  double bxn = b.f64[C_BXN_FAST][s], byn = b.f64[C_BYN_FAST][s];
+  double axn = b.f64[C_AXN_FAST][s] + bxn, ayn = b.f64[C_AYN_FAST][s] + byn;
+  double uvel1 = b.f64[C_UVEL][s], vvel1 = b.f64[C_VVEL][s], ax1, ay1;
+  double uvel3 = uvel1 + (dt_2 * axn), vvel3 = vvel1 + (dt_2 * ayn);
+  int i = b.ine[s], j = b.jne[s];
+  if (mp.explicit_inner_mts) {
+    if (p.dem) dem_sum_phase(g, b, p, mp, ct, cnt, s, i, j, uvel1, vvel1, dt, ax1, ay1, axn, ayn);
+    else accel_explicit_inner_mts(g, b, p, ct, cnt, s, i, j, uvel1, vvel1, dt, ax1, ay1, axn, ayn);
+    bxn = 0.; byn = 0.;
+    if (mp.short_step_mts_grounding) {
+      double T = b.f64[C_THICKNESS][s], D = (p.rho_bergs / KID_RHO_SEAWATER) * T;
+      double groundfrac = mts_ground_fraction(p, b.f64[C_OD][s], D), gdrag = 0.;
+      if (groundfrac > 0.0) {
+        double MM, AA;
+        if (mp.constant_interaction_LW) { MM = mp.constant_length * mp.constant_width * T * p.rho_bergs; AA = mp.constant_width * mp.constant_length; }
+        else { MM = b.f64[C_MASS][s]; AA = b.f64[C_LENGTH][s] * b.f64[C_WIDTH][s]; }
+        gdrag = -p.cdrag_grounding * groundfrac * AA / MM;
+      }
+      axn = axn + uvel1 * gdrag; ayn = ayn + vvel1 * gdrag;
+      ax1 = 0.5 * axn; ay1 = 0.5 * ayn;
+    }
+  } else {
+    double f1, f2;
+    accel_mts(g, b, p, mp, ct, cnt, s, i, j, latn, uvel1, vvel1, dt, 3, ax1, ay1, axn, ayn, bxn, byn, f1, f2);
+  }
+  double uveln, vveln;
+  if ((latn > 89.) && p.grid_is_latlon) {
+    double xdot3, ydot3, xddot1, yddot1;
+    rotvec_to_tang(p, lonn, uvel3, vvel3, xdot3, ydot3);
+    rotvec_to_tang(p, lonn, ax1, ay1, xddot1, yddot1);
+    rotvec_from_tang(p, lonn, xdot3 + (dt * xddot1), ydot3 + (dt * yddot1), uveln, vveln);
+  } else { uveln = uvel3 + (dt * ax1); vveln = vvel3 + (dt * ay1); }
+  if (iterate) {
+    double uold = b.f64[C_UVEL_OLD][s], vold = b.f64[C_VVEL_OLD][s];
+    if (jj == 1) su = uold * uold + vold * vold;
+    su1 = uveln * uveln + vveln * vveln;
+    su2 = (uveln - uold) * (uveln - uold) + (vveln - vold) * (vveln - vold);
+  }
+  b.f64[C_AXN_FAST][s] = axn; b.f64[C_AYN_FAST][s] = ayn; b.f64[C_BXN_FAST][s] = bxn; b.f64[C_BYN_FAST][s] = byn;
+  b.f64[C_UVEL][s] = uveln; b.f64[C_VVEL][s] = vveln;
+}
+
+// end of a sub-step I:6974-7041
+__device__ __forceinline__ void mts_phase_end(const DevBergs& b, const DevParams& p, const MtsParams& mp, long long s, double dt) {
+  b.f64[C_UVEL_OLD][s] = b.f64[C_UVEL][s]; b.f64[C_VVEL_OLD][s] = b.f64[C_VVEL][s];
+  if (p.dem) {
+    double gdrag = 0.;
+    if (mp.use_grounding_torque) {
+      double T = b.f64[C_THICKNESS][s], D = (p.rho_bergs / KID_RHO_SEAWATER) * T, groundfrac = mts_ground_fraction(p, b.f64[C_OD][s], D);
+      if (groundfrac > 0.0) {
+        double MM, R1;
+        if (mp.constant_interaction_LW) { MM = mp.constant_length * mp.constant_width * T * p.rho_bergs; R1 = mts_ia_radius(p, mp.constant_length * mp.constant_width); }
+        else { MM = b.f64[C_MASS][s]; R1 = mts_ia_radius(p, b.f64[C_LENGTH][s] * b.f64[C_WIDTH][s]); }
+        gdrag = -p.cdrag_grounding * groundfrac * p.pi * pow(R1, 2.) / MM;
+      }
+    }
+    double av = b.f64[C_ANG_VEL][s] + dt * b.f64[C_ANG_ACCEL][s];
+    av = av / (1. - gdrag * dt);
+    b.f64[C_ANG_VEL][s] = av;
+    b.f64[C_ROT][s] = b.f64[C_ROT][s] + dt * av;
+    for (int k = 0; k < b.max_bonds; k++) {
+      long long slot = (long long)k * b.capacity + s;
+      if (b.bond_other_id[slot] != 0 && b.bond_broken[slot] == 2) b.bond_broken[slot] = 1;
+    }
+  }
+  if (mp.force_convergence) {
+    b.f64[C_AXN][s] = b.f64[C_AXN_FAST][s]; b.f64[C_AYN][s] = b.f64[C_AYN_FAST][s];
+    b.f64[C_BXN][s] = b.f64[C_BXN_FAST][s]; b.f64[C_BYN][s] = b.f64[C_BYN_FAST][s];
+  }
+}
+
+// break_bonds_dem F:4713-4799 for the half-bonds of one berg (the stresses of a pair are stored on both halves)
+__device__ __forceinline__ void dem_phase_break(const DevBergs& b, const MtsParams& mp, long long s) {
+  if (mp.no_frac_first_ts) return;
+  double tn = mp.frac_thres_n, tt = mp.frac_thres_t;
+  if (tn <= 0.0 && tt <= 0.0) return;
+  if (tn <= 0.0) tn = 1.7976931348623157e308;
+  if (tt <= 0.0) tt = 1.7976931348623157e308;
+  for (int k = 0; k < b.max_bonds; k++) {
+    long long slot = (long long)k * b.capacity + s;
+    if (b.bond_other_id[slot] == 0) continue;
+    if (b.bond_dem[BD_NSTRESS][slot] > tn || b.bond_dem[BD_SSTRESS][slot] > tt) {
+      b.bond_other_id[slot] = 0; b.bond_other_slot[slot] = -1;
+      b.n_bonds[s] -= 1;
+    }
+  }
+}
+
+__global__ void k_mts_pos(const __grid_constant__ DevBergs b, const __grid_constant__ DevParams p, long long n_slots, double dt) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots || !mts_active(b, s, b.flags[s])) return;
+  mts_phase_pos(b, p, s, dt);
+}
+
+__global__ void k_dem_pairs(const __grid_constant__ DevBergs b, const __grid_constant__ DevParams p,
+                            const __grid_constant__ MtsParams mp, DevCounters* __restrict__ cnt, long long n_slots, double dt) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots || !mts_active(b, s, b.flags[s])) return;
+  dem_pair_phase(b, p, mp, cnt, s, dt);
+}
+
 __global__ void __launch_bounds__(128)
 k_mts_vel(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b, const __grid_constant__ DevParams p,
           const __grid_constant__ MtsParams mp, const CellTable ct, DevCounters* __restrict__ cnt,
           MtsSums* __restrict__ sums, long long n_slots, double dt, int jj) {
   long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   double su = 0., su1 = 0., su2 = 0.;
-  uint8_t flags = (s < n_slots) ? b.flags[s] : (uint8_t)0;
   const bool iterate = mp.force_convergence && !mp.explicit_inner_mts;
-  if (mts_active(b, (s < n_slots) ? s : 0, flags)) {
-    const double dt_2 = 0.5 * dt;
-    double latn = b.f64[C_LAT][s], lonn = b.f64[C_LON][s];
-    double bxn = b.f64[C_BXN_FAST][s], byn = b.f64[C_BYN_FAST][s];
-    double axn = b.f64[C_AXN_FAST][s] + bxn, ayn = b.f64[C_AYN_FAST][s] + byn;
-    double uvel1 = b.f64[C_UVEL][s], vvel1 = b.f64[C_VVEL][s], ax1, ay1;
-    double uvel3 = uvel1 + (dt_2 * axn), vvel3 = vvel1 + (dt_2 * ayn);
-    int i = b.ine[s], j = b.jne[s];
-    if (mp.explicit_inner_mts) {
-      accel_explicit_inner_mts(g, b, p, ct, cnt, s, i, j, uvel1, vvel1, dt, ax1, ay1, axn, ayn);
-      bxn = 0.; byn = 0.;
-      if (mp.short_step_mts_grounding) {
-        double T = b.f64[C_THICKNESS][s], D = (p.rho_bergs / KID_RHO_SEAWATER) * T;
-        double groundfrac = mts_ground_fraction(p, b.f64[C_OD][s], D), gdrag = 0.;
-        if (groundfrac > 0.0) {
-          double MM, AA;
-          if (mp.constant_interaction_LW) { MM = mp.constant_length * mp.constant_width * T * p.rho_bergs; AA = mp.constant_width * mp.constant_length; }
-          else { MM = b.f64[C_MASS][s]; AA = b.f64[C_LENGTH][s] * b.f64[C_WIDTH][s]; }
-          gdrag = -p.cdrag_grounding * groundfrac * AA / MM;
-        }
-        axn = axn + uvel1 * gdrag; ayn = ayn + vvel1 * gdrag;
-        ax1 = 0.5 * axn; ay1 = 0.5 * ayn;
-      }
-    } else {
-      double f1, f2;
-      accel_mts(g, b, p, mp, ct, cnt, s, i, j, latn, uvel1, vvel1, dt, 3, ax1, ay1, axn, ayn, bxn, byn, f1, f2);
-    }
-    double uveln, vveln;
-    if ((latn > 89.) && p.grid_is_latlon) {
-      double xdot3, ydot3, xddot1, yddot1;
-      rotvec_to_tang(p, lonn, uvel3, vvel3, xdot3, ydot3);
-      rotvec_to_tang(p, lonn, ax1, ay1, xddot1, yddot1);
-      rotvec_from_tang(p, lonn, xdot3 + (dt * xddot1), ydot3 + (dt * yddot1), uveln, vveln);
-    } else { uveln = uvel3 + (dt * ax1); vveln = vvel3 + (dt * ay1); }
-    if (iterate) {
-      double uold = b.f64[C_UVEL_OLD][s], vold = b.f64[C_VVEL_OLD][s];
-      if (jj == 1) su = uold * uold + vold * vold;
-      su1 = uveln * uveln + vveln * vveln;
-      su2 = (uveln - uold) * (uveln - uold) + (vveln - vold) * (vveln - vold);
-    }
-    b.f64[C_AXN_FAST][s] = axn; b.f64[C_AYN_FAST][s] = ayn; b.f64[C_BXN_FAST][s] = bxn; b.f64[C_BYN_FAST][s] = byn;
-    b.f64[C_UVEL][s] = uveln; b.f64[C_VVEL][s] = vveln;
-  }
+  if (s < n_slots && mts_active(b, s, b.flags[s])) mts_phase_vel(g, b, p, mp, ct, cnt, s, dt, jj, iterate, su, su1, su2);
   if (iterate) mts_block_sums(sums, su, su1, su2);
 }
 
@@ -436,81 +715,52 @@ __global__ void k_mts_vel_retry(const __grid_constant__ DevBergs b, long long n_
   b.f64[C_AXN_FAST][s] = axn; b.f64[C_AYN_FAST][s] = ayn; b.f64[C_BXN_FAST][s] = bxn; b.f64[C_BYN_FAST][s] = byn;
 }
 
-// end of a sub-step I:6974-7041 (without the DEM rotation)
-__global__ void k_mts_sub_end(const __grid_constant__ DevBergs b, long long n_slots, int fc) {
+__global__ void k_mts_sub_end(const __grid_constant__ DevBergs b, const __grid_constant__ DevParams p,
+                              const __grid_constant__ MtsParams mp, long long n_slots, double dt) {
   long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_slots) return;
-  if (!mts_active(b, s, b.flags[s])) return;
-  b.f64[C_UVEL_OLD][s] = b.f64[C_UVEL][s]; b.f64[C_VVEL_OLD][s] = b.f64[C_VVEL][s];
-  if (fc) {
-    b.f64[C_AXN][s] = b.f64[C_AXN_FAST][s]; b.f64[C_AYN][s] = b.f64[C_AYN_FAST][s];
-    b.f64[C_BXN][s] = b.f64[C_BXN_FAST][s]; b.f64[C_BYN][s] = b.f64[C_BYN_FAST][s];
-  }
+  if (s >= n_slots || !mts_active(b, s, b.flags[s])) return;
+  mts_phase_end(b, p, mp, s, dt);
 }
 
-// explicit fast scheme without convergence passes: position + velocity + end-of-sub-step of ONE sub-step need two
-// grid-wide dependencies (positions of all bergs before any force, *_old of all bergs before the next positions), so a
-// sub-step is k_mts_pos, k_mts_vel, k_mts_sub_end; when the whole population fits one CTA the sub-step loop runs
-// inside a single kernel with __syncthreads() between the sweeps (the bonded-conglomerate tests have 1e1..1e3 elements
-// and 60..1e5 sub-steps: launch latency, not bandwidth, is what they cost).
+// break_bonds_dem sweeps every berg of the data domain
+__global__ void k_dem_break_bonds(const __grid_constant__ DevBergs b, const __grid_constant__ MtsParams mp, long long n_slots) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots || !(b.flags[s] & BF_ALIVE)) return;
+  dem_phase_break(b, mp, s);
+}
+
+// The explicit fast scheme needs no convergence passes, so a sub-step is a fixed sequence of sweeps separated by
+// grid-wide dependencies (all positions before any force, all pair forces before any sum, all new velocities before
+// the next *_old).  When the whole population fits one CTA the sub-step loop runs inside a single kernel with
+// __syncthreads() between the sweeps: the bonded-conglomerate cases have 1e1..1e3 elements and 60..1e5 sub-steps,
+// launch latency is what they would otherwise cost.
 __global__ void __launch_bounds__(1024)
 k_mts_substeps_one_cta(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b, const __grid_constant__ DevParams p,
                        const __grid_constant__ MtsParams mp, const CellTable ct, DevCounters* __restrict__ cnt,
                        long long n_slots, double dt, int nsub) {
-  const double dt_2 = 0.5 * dt;
   const int per = (int)((n_slots + blockDim.x - 1) / blockDim.x);
+  const bool brk = p.dem && mp.break_bonds_on_sub_steps && !mp.use_broken_bonds_for_substep_contact;
+#define KID_EACH_ACTIVE(body)                                                 \
+  for (int q = 0; q < per; q++) {                                             \
+    long long s = (long long)q * blockDim.x + threadIdx.x;                    \
+    if (s < n_slots && mts_active(b, s, b.flags[s])) { body; }                \
+  }                                                                           \
+  __syncthreads();
   for (int k = 0; k < nsub; k++) {
-    for (int q = 0; q < per; q++) {
-      long long s = (long long)q * blockDim.x + threadIdx.x;
-      if (s >= n_slots || !mts_active(b, s, b.flags[s])) continue;
-      double lon1 = b.f64[C_LON][s], lat1 = b.f64[C_LAT][s], uvel1 = b.f64[C_UVEL][s], vvel1 = b.f64[C_VVEL][s];
-      double axn = b.f64[C_AXN_FAST][s], ayn = b.f64[C_AYN_FAST][s], bxn = b.f64[C_BXN_FAST][s], byn = b.f64[C_BYN_FAST][s];
-      const bool tang = (lat1 > 89.) && p.grid_is_latlon;
-      double dxdl1, dydl, lonn, latn;
-      convert_from_meters_to_grid(p, lat1, dxdl1, dydl);
-      double uvel2 = uvel1 + (dt_2 * axn) + (dt_2 * bxn), vvel2 = vvel1 + (dt_2 * ayn) + (dt_2 * byn);
-      if (tang) {
-        double x1, y1, xdot2, ydot2;
-        rotpos_to_tang(p, lon1, lat1, x1, y1);
-        rotvec_to_tang(p, lon1, uvel2, vvel2, xdot2, ydot2);
-        rotpos_from_tang(p, x1 + (dt * xdot2), y1 + (dt * ydot2), lonn, latn);
-      } else { lonn = lon1 + (dt * (uvel2 * dxdl1)); latn = lat1 + (dt * (vvel2 * dydl)); }
-      b.f64[C_LON][s] = lonn; b.f64[C_LAT][s] = latn; b.f64[C_LON_OLD][s] = lonn; b.f64[C_LAT_OLD][s] = latn;
-      b.f64[C_UVEL_OLD][s] = uvel1 + dt_2 * (axn + bxn);
-      b.f64[C_VVEL_OLD][s] = vvel1 + dt_2 * (ayn + bxn);
-    }
-    __syncthreads();
-    for (int q = 0; q < per; q++) {
-      long long s = (long long)q * blockDim.x + threadIdx.x;
-      if (s >= n_slots || !mts_active(b, s, b.flags[s])) continue;
-      double latn = b.f64[C_LAT][s], lonn = b.f64[C_LON][s];
-      double axn = b.f64[C_AXN_FAST][s] + b.f64[C_BXN_FAST][s], ayn = b.f64[C_AYN_FAST][s] + b.f64[C_BYN_FAST][s];
-      double uvel1 = b.f64[C_UVEL][s], vvel1 = b.f64[C_VVEL][s], ax1, ay1;
-      double uvel3 = uvel1 + (dt_2 * axn), vvel3 = vvel1 + (dt_2 * ayn);
-      accel_explicit_inner_mts(g, b, p, ct, cnt, s, b.ine[s], b.jne[s], uvel1, vvel1, dt, ax1, ay1, axn, ayn);
-      double uveln, vveln;
-      if ((latn > 89.) && p.grid_is_latlon) {
-        double xdot3, ydot3, xddot1, yddot1;
-        rotvec_to_tang(p, lonn, uvel3, vvel3, xdot3, ydot3);
-        rotvec_to_tang(p, lonn, ax1, ay1, xddot1, yddot1);
-        rotvec_from_tang(p, lonn, xdot3 + (dt * xddot1), ydot3 + (dt * yddot1), uveln, vveln);
-      } else { uveln = uvel3 + (dt * ax1); vveln = vvel3 + (dt * ay1); }
-      // the new velocity is parked in *_PREV until every thread has read the old *_OLD of its neighbours
-      b.f64[C_AXN_FAST][s] = axn; b.f64[C_AYN_FAST][s] = ayn; b.f64[C_BXN_FAST][s] = 0.; b.f64[C_BYN_FAST][s] = 0.;
-      b.f64[C_UVEL][s] = uveln; b.f64[C_VVEL][s] = vveln;
-    }
-    __syncthreads();
-    for (int q = 0; q < per; q++) {
-      long long s = (long long)q * blockDim.x + threadIdx.x;
-      if (s >= n_slots || !mts_active(b, s, b.flags[s])) continue;
-      b.f64[C_UVEL_OLD][s] = b.f64[C_UVEL][s]; b.f64[C_VVEL_OLD][s] = b.f64[C_VVEL][s];
-      if (mp.force_convergence) {
-        b.f64[C_AXN][s] = b.f64[C_AXN_FAST][s]; b.f64[C_AYN][s] = b.f64[C_AYN_FAST][s];
-        b.f64[C_BXN][s] = 0.; b.f64[C_BYN][s] = 0.;
+    KID_EACH_ACTIVE(mts_phase_pos(b, p, s, dt))
+    if (p.dem) { KID_EACH_ACTIVE(dem_pair_phase(b, p, mp, cnt, s, dt)) }
+    double su, su1, su2;
+    KID_EACH_ACTIVE(mts_phase_vel(g, b, p, mp, ct, cnt, s, dt, 1, false, su, su1, su2))
+    KID_EACH_ACTIVE(mts_phase_end(b, p, mp, s, dt))
+    if (brk) {
+      for (int q = 0; q < per; q++) {
+        long long s = (long long)q * blockDim.x + threadIdx.x;
+        if (s < n_slots && (b.flags[s] & BF_ALIVE)) dem_phase_break(b, mp, s);
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
+#undef KID_EACH_ACTIVE
 }
 
 // end of evolve_icebergs_mts I:7050-7075: the cell of the new position, grounding
