@@ -201,7 +201,8 @@ class Icebergs:
         n = C.c_int64(0)
         self._check(lib().kid_get_bonds(self.handle, C.byref(n), None))
         cap = max(n.value, 1)
-        names = {"first_id", "other_id", "first_ine", "first_jne", "other_ine", "other_jne", "length"}
+        names = {"first_id", "other_id", "first_ine", "first_jne", "other_ine", "other_jne", "length", "tangd1", "tangd2",
+                 "nstress", "sstress", "rel_rotation", "broken"}
         c, keep = make_columns(cap, want=names, cls=D.KidBondColumns)
         m = C.c_int64(cap)
         self._check(lib().kid_get_bonds(self.handle, C.byref(m), C.byref(c)))

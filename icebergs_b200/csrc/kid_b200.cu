@@ -532,7 +532,8 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
     unsupported = "Runge_not_Verlet=.true. (RK4) is implemented for free-drifting bergs only: set runge_not_verlet=0 with interactions / footloose";
   else if (pin->tidal_drift > 0.) unsupported = "tidal_drift>0 needs the FMS random number stream";
   else if (pin->add_iceberg_thickness_to_ssh) unsupported = "add_iceberg_thickness_to_SSH is not implemented";
-  else if (pin->dem) unsupported = "dem=.true. (bonded DEM forces of the MTS scheme) is not implemented in this build";
+  else if (pin->dem && !(pin->mts && pin->iceberg_bonds_on)) unsupported = "dem=.true. needs mts=.true. and iceberg_bonds_on (F:1433)";
+  else if (pin->dem && pin->break_bonds_on_sub_steps && !pin->fracture_criterion_stress) unsupported = "break_bonds_on_sub_steps needs fracture_criterion='stress' (I:1201)";
   else if (pin->mts && dom->nranks > 1) unsupported = "mts=.true. runs on one rank in this build (transfer_mts_bergs is not implemented)";
   else if (pin->mts && (!pin->interactive_icebergs_on || pin->footloose)) unsupported = "mts=.true. needs interactive_icebergs_on and no footloose";
   else if (pin->mts && pin->halo < 3) unsupported = "mts=.true. needs halo >= 3 (3x3 A-grid stencil of the ocean depth)";
@@ -621,8 +622,13 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
     if (q->hexagonal_icebergs) h->mp.constant_radius = sqrt(h->mp.constant_area / (2. * sqrt(3.)));
     else if (q->iceberg_bonds_on) h->mp.constant_radius = 0.5 * sqrt(h->mp.constant_area);
     else h->mp.constant_radius = sqrt(h->mp.constant_area / q->pi);
-    if (q->constant_interaction_LW && (q->constant_length == 0. || q->constant_width == 0.))
-      return fail(h, KID_ERR_UNSUPPORTED, "kid_init: constant_interaction_LW needs constant_length and constant_width (the mean-size default F:4640 is not implemented)");
+    h->mp.dem_spring_coef = q->dem_spring_coef; h->mp.dem_damping_coef = q->dem_damping_coef; h->mp.poisson = q->poisson;
+    h->mp.dem_K_damp = 2. * q->dem_spring_coef / (3. * (1. - q->poisson * q->poisson));       // F:1436
+    h->mp.frac_thres_n = q->frac_thres_n; h->mp.frac_thres_t = q->frac_thres_t;
+    h->mp.ignore_tangential_force = q->ignore_tangential_force; h->mp.orig_dem_moment_of_inertia = q->orig_dem_moment_of_inertia;
+    h->mp.break_bonds_on_sub_steps = q->break_bonds_on_sub_steps; h->mp.fracture_criterion_stress = q->fracture_criterion_stress;
+    h->mp.use_broken_bonds_for_substep_contact = q->use_broken_bonds_for_substep_contact; h->mp.dem_beam_test = q->dem_beam_test;
+    h->mp.no_frac_first_ts = q->no_frac_first_ts;
   }
   // F:1113-1118
   if ((!q->grid_is_latlon) && (q->Lx == 360.)) q->Lx = -1.;
@@ -807,10 +813,10 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   DevBergs& b = h->b;
   memset(&b, 0, sizeof(b));
   b.capacity = h->capacity;
-  int ncols = q->mts ? (int)C_NMTS : q->interactive_icebergs_on ? (int)C_NINTER : (int)C_NBASE;
+  int ncols = q->dem ? (int)C_NDEM : q->mts ? (int)C_NMTS : q->interactive_icebergs_on ? (int)C_NINTER : (int)C_NBASE;
   for (int c = 0; c < ncols; c++) CK(cudaMalloc(&b.f64[c], sizeof(double) * h->capacity));
   if (q->mts) {
-    for (int c = C_NINTER; c < C_NMTS; c++) CK(cudaMemsetAsync(b.f64[c], 0, sizeof(double) * h->capacity, h->stream));
+    for (int c = C_NINTER; c < ncols; c++) CK(cudaMemsetAsync(b.f64[c], 0, sizeof(double) * h->capacity, h->stream));
     CK(cudaMalloc(&h->dsums, sizeof(MtsSums)));
   }
   CK(cudaMalloc(&b.id, sizeof(int64_t) * h->capacity));
@@ -844,6 +850,14 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
       CK(cudaMemsetAsync(b.bond_other_ine, 0, sizeof(int32_t) * nb, h->stream));
       CK(cudaMemsetAsync(b.bond_other_jne, 0, sizeof(int32_t) * nb, h->stream));
       CK(cudaMemsetAsync(b.bond_length, 0, sizeof(double) * nb, h->stream));
+      if (q->dem) {
+        for (int k = 0; k < BD_N; k++) {
+          CK(cudaMalloc(&b.bond_dem[k], sizeof(double) * nb));
+          CK(cudaMemsetAsync(b.bond_dem[k], 0, sizeof(double) * nb, h->stream));
+        }
+        CK(cudaMalloc(&b.bond_broken, sizeof(int32_t) * nb));
+        CK(cudaMemsetAsync(b.bond_broken, 0, sizeof(int32_t) * nb, h->stream));
+      }
     }
     CK(cudaMalloc(&b.conglom_id, sizeof(int32_t) * h->capacity));
     CK(cudaMemsetAsync(b.conglom_id, 0, sizeof(int32_t) * h->capacity, h->stream));
@@ -935,6 +949,8 @@ extern "C" int32_t kid_end(kid_t** hp) {
   cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->cell_fill);
   cudaFree(h->scan_sums); cudaFree(h->scan_total); cudaFree(h->dcnt); cudaFree(h->dflags);
   cudaFreeHost(h->hcnt); cudaFreeHost(h->hflags);
+  for (int k = 0; k < BD_N; k++) cudaFree(h->b.bond_dem[k]);
+  cudaFree(h->b.bond_broken); cudaFree(h->b.n_bonds); cudaFree(h->dsums);
   cudaFree(h->leaver_lists[0]); cudaFree(h->leaver_lists[1]); cudaFree(h->leaver_counts);
   if (h->xstream) cudaStreamDestroy(h->xstream);
   if (h->ev_kstep) cudaEventDestroy(h->ev_kstep);
@@ -1013,7 +1029,7 @@ static int sort_bergs(kid_t* h) {
   k_scan_sums<<<1, 1024, 0, h->stream>>>(h->scan_sums, nsb, h->scan_total); h->launches++;
   LAUNCH(h, k_scan_add, n2, 256, h->cell_start, h->scan_sums, n2);
   LAUNCH(h, k_rank, ns, 256, h->g, h->b.flags, h->b.ine, h->b.jne, ns, h->cell_start, h->cell_fill, h->perm);
-  LAUNCH(h, k_cell_order, n2, 128, h->b, h->cell_start, h->cell_count, n2, h->perm, h->p.footloose ? 1 : 0);
+  LAUNCH(h, k_cell_order, n2, 128, h->b, h->cell_start, h->cell_count, n2, h->perm, (h->p.footloose || h->p.dem) ? 1 : 0);
   int32_t totals[2] = {0, 0};
   CK(cudaMemcpyAsync(totals, h->scan_total, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -1052,8 +1068,15 @@ static int sort_bergs(kid_t* h) {
       { GatherArgs<double, 1> a; a.src[0] = h->b.bond_length + k * cap; a.dst[0] = (double*)h->spare8;
         LAUNCH(h, (k_gather<double, 1>), n_new, 256, a, h->perm, n_new);
         CK(cudaMemcpyAsync(h->b.bond_length + k * cap, h->spare8, sizeof(double) * n_new, cudaMemcpyDeviceToDevice, h->stream)); }
-      int32_t* i32s[2] = {h->b.bond_other_ine + k * cap, h->b.bond_other_jne + k * cap};
+      for (int q = 0; q < BD_N; q++) {
+        if (!h->b.bond_dem[q]) continue;
+        GatherArgs<double, 1> a; a.src[0] = h->b.bond_dem[q] + k * cap; a.dst[0] = (double*)h->spare8;
+        LAUNCH(h, (k_gather<double, 1>), n_new, 256, a, h->perm, n_new);
+        CK(cudaMemcpyAsync(h->b.bond_dem[q] + k * cap, h->spare8, sizeof(double) * n_new, cudaMemcpyDeviceToDevice, h->stream));
+      }
+      int32_t* i32s[3] = {h->b.bond_other_ine + k * cap, h->b.bond_other_jne + k * cap, h->b.bond_broken ? h->b.bond_broken + k * cap : nullptr};
       for (int32_t* col : i32s) {
+        if (!col) continue;
         GatherArgs<int32_t, 1> a; a.src[0] = col; a.dst[0] = (int32_t*)h->spare4;
         LAUNCH(h, (k_gather<int32_t, 1>), n_new, 256, a, h->perm, n_new);
         CK(cudaMemcpyAsync(col, h->spare4, sizeof(int32_t) * n_new, cudaMemcpyDeviceToDevice, h->stream));
@@ -1139,6 +1162,7 @@ static int set_conglom_ids(kid_t* h) {
     CK(cudaStreamSynchronize(h->stream));
     if (!changed) break;
   }
+  if (h->p.dem && h->p.use_broken_bonds_for_substep_contact) LAUNCH(h, k_dem_drop_split_bonds, h->n_slots, 128, h->b, h->n_slots);
   return KID_OK;
 }
 
@@ -1154,7 +1178,7 @@ static int refresh_interactive_state(kid_t* h) {
   if (h->b.max_bonds > 0) {
     CellTable ct{h->cell_start, h->cell_count};
     LAUNCH(h, k_connect_bonds, h->n_slots, 128, h->g, h->b, ct, h->dcnt, h->n_slots);
-    if (h->p.mts) LAUNCH(h, k_assign_n_bonds, h->n_slots, 128, h->b, h->n_slots);
+    if (h->p.mts) LAUNCH(h, k_assign_n_bonds, h->n_slots, 128, h->b, h->n_slots, h->p.use_broken_bonds_for_substep_contact ? 1 : 0);
   }
   return set_conglom_ids(h);
 }
@@ -1183,7 +1207,8 @@ const ColMap kColMap[] = {
     {C_UVEL_OLD, &KidBergColumns::uvel_old}, {C_VVEL_OLD, &KidBergColumns::vvel_old},
     {C_LON_OLD, &KidBergColumns::lon_old}, {C_LAT_OLD, &KidBergColumns::lat_old},
     {C_AXN_FAST, &KidBergColumns::axn_fast}, {C_AYN_FAST, &KidBergColumns::ayn_fast},
-    {C_BXN_FAST, &KidBergColumns::bxn_fast}, {C_BYN_FAST, &KidBergColumns::byn_fast}};
+    {C_BXN_FAST, &KidBergColumns::bxn_fast}, {C_BYN_FAST, &KidBergColumns::byn_fast},
+    {C_ANG_VEL, &KidBergColumns::ang_vel}, {C_ANG_ACCEL, &KidBergColumns::ang_accel}, {C_ROT, &KidBergColumns::rot}};
 }  // namespace
 
 extern "C" int32_t kid_set_bergs(kid_t* h, int64_t n, const KidBergColumns* c) {
@@ -1352,6 +1377,11 @@ extern "C" int32_t kid_set_bonds(kid_t* h, int64_t nb, const KidBondColumns* c) 
     std::vector<int64_t> oid((size_t)cap * mb, 0);
     std::vector<int32_t> oi((size_t)cap * mb, 0), oj((size_t)cap * mb, 0), osl((size_t)cap * mb, -1);
     std::vector<double> len((size_t)cap * mb, 0.);
+    const bool dem = h->p.dem != 0;
+    const double* dsrc[5] = {c->tangd1, c->tangd2, c->rel_rotation, c->nstress, c->sstress};     // read_restart_bonds fmsio:1400-1425
+    const int dcol[5] = {BD_TANGD1, BD_TANGD2, BD_REL_ROT, BD_NSTRESS, BD_SSTRESS};
+    std::vector<std::vector<double>> dstate(dem ? 5 : 0, std::vector<double>((size_t)cap * mb, 0.));
+    std::vector<int32_t> brk(dem ? (size_t)cap * mb : 0, 0);
     std::vector<int> fill((size_t)ns, 0);
     for (int64_t k = 0; k < nb; k++) {
       long long s = slot_of(c->first_id[k]);
@@ -1364,6 +1394,14 @@ extern "C" int32_t kid_set_bonds(kid_t* h, int64_t nb, const KidBondColumns* c) 
       oi[e] = c->other_ine ? c->other_ine[k] : (o >= 0 ? bi[o] : 0);
       oj[e] = c->other_jne ? c->other_jne[k] : (o >= 0 ? bj[o] : 0);
       len[e] = c->length ? c->length[k] : 0.;
+      if (dem) {
+        for (int q = 0; q < 5; q++) if (dsrc[q]) dstate[q][e] = dsrc[q][k];
+        if (c->broken) brk[e] = c->broken[k];
+      }
+    }
+    if (dem) {
+      for (int q = 0; q < 5; q++) CK(cudaMemcpy(b.bond_dem[dcol[q]], dstate[q].data(), sizeof(double) * dstate[q].size(), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(b.bond_broken, brk.data(), sizeof(int32_t) * brk.size(), cudaMemcpyHostToDevice));
     }
     CK(cudaMemcpy(b.bond_other_id, oid.data(), sizeof(int64_t) * oid.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(b.bond_other_ine, oi.data(), sizeof(int32_t) * oi.size(), cudaMemcpyHostToDevice));
@@ -1410,6 +1448,14 @@ extern "C" int32_t kid_get_bonds(kid_t* h, int64_t* nb, KidBondColumns* c) {
   CK(cudaMemcpy(oi.data(), b.bond_other_ine, sizeof(int32_t) * oi.size(), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(oj.data(), b.bond_other_jne, sizeof(int32_t) * oj.size(), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(len.data(), b.bond_length, sizeof(double) * len.size(), cudaMemcpyDeviceToHost));
+  const bool dem = h->p.dem != 0;
+  const int dcol[5] = {BD_TANGD1, BD_TANGD2, BD_REL_ROT, BD_NSTRESS, BD_SSTRESS};
+  std::vector<std::vector<double>> dstate(dem ? 5 : 0, std::vector<double>((size_t)cap * mb, 0.));
+  std::vector<int32_t> brk(dem ? (size_t)cap * mb : 0, 0);
+  if (dem) {
+    for (int q = 0; q < 5; q++) CK(cudaMemcpy(dstate[q].data(), b.bond_dem[dcol[q]], sizeof(double) * dstate[q].size(), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(brk.data(), b.bond_broken, sizeof(int32_t) * brk.size(), cudaMemcpyDeviceToHost));
+  }
   int64_t n = 0;
   for (long long s = 0; s < ns; s++) {
     if (!(fl[s] & BF_ALIVE) || (fl[s] & (BF_HALO | BF_LEAVER))) continue;
@@ -1424,7 +1470,11 @@ extern "C" int32_t kid_get_bonds(kid_t* h, int64_t* nb, KidBondColumns* c) {
         if (c->other_ine) c->other_ine[n] = oi[e];
         if (c->other_jne) c->other_jne[n] = oj[e];
         if (c->length) c->length[n] = len[e];
-        if (c->broken) c->broken[n] = 0;
+        if (c->broken) c->broken[n] = dem ? brk[e] : 0;
+        if (dem) {
+          double* ddst[5] = {c->tangd1, c->tangd2, c->rel_rotation, c->nstress, c->sstress};
+          for (int q = 0; q < 5; q++) if (ddst[q]) ddst[q][n] = dstate[q][e];
+        }
       }
       n++;
     }
@@ -1558,6 +1608,41 @@ static int ingest_forcing(kid_t* h, const double* calving, const double* uo, con
   LAUNCH(h, k_pack_forcing, n2, 256, g, n2);
   CK(cudaMemcpyAsync(h->hflags, h->dflags, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
   h->forcing_set = 1;
+  return KID_OK;
+}
+
+// dem_tests_init F:4685-4710 and set_constant_interaction_length_and_width F:4640-4682 (icebergs_init I:166-172):
+// init-time reductions over the bergs, done on the host
+static int mts_first_visit(kid_t* h) {
+  const long long ns = h->n_slots;
+  if (ns <= 0) return KID_OK;
+  const bool need_lw = h->p.constant_interaction_LW && (h->p.constant_length == 0. || h->p.constant_width == 0.);
+  if (!(h->p.dem_beam_test > 0) && !need_lw) return KID_OK;
+  std::vector<uint8_t> fl((size_t)ns);
+  std::vector<double> a((size_t)ns), w((size_t)ns);
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(fl.data(), h->b.flags, ns, cudaMemcpyDeviceToHost));
+  if (h->p.dem_beam_test > 0) {
+    LAUNCH(h, k_dem_tests_init, ns, 256, h->b, ns);
+    CK(cudaMemcpy(a.data(), h->b.f64[C_LON], sizeof(double) * ns, cudaMemcpyDeviceToHost));
+    double lo = 1.7976931348623157e308, hi = -1.7976931348623157e308;
+    for (long long s = 0; s < ns; s++) if (fl[s] & BF_ALIVE) { lo = std::min(lo, a[s]); hi = std::max(hi, a[s]); }
+    h->mp.dem_tests_start_lon = lo; h->mp.dem_tests_end_lon = hi;
+  }
+  if (need_lw) {
+    CK(cudaMemcpy(a.data(), h->b.f64[C_LENGTH], sizeof(double) * ns, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(w.data(), h->b.f64[C_WIDTH], sizeof(double) * ns, cudaMemcpyDeviceToHost));
+    double n = 0., ls = 0., ws = 0.;
+    for (long long s = 0; s < ns; s++) if ((fl[s] & BF_ALIVE) && !(fl[s] & BF_HALO)) { n += 1.; ls += a[s]; ws += w[s]; }
+    if (n > 0.) {
+      h->p.constant_length = ls / n; h->p.constant_width = ws / n;
+      h->mp.constant_length = h->p.constant_length; h->mp.constant_width = h->p.constant_width;
+      h->mp.constant_area = h->mp.constant_length * h->mp.constant_width;
+      if (h->p.hexagonal_icebergs) h->mp.constant_radius = sqrt(h->mp.constant_area / (2. * sqrt(3.)));
+      else if (h->p.iceberg_bonds_on) h->mp.constant_radius = 0.5 * sqrt(h->mp.constant_area);
+      else h->mp.constant_radius = sqrt(h->mp.constant_area / h->p.pi);
+    }
+  }
   return KID_OK;
 }
 
@@ -1805,8 +1890,10 @@ static int step_core(kid_t* h) {
   // the second stream's work of the previous step (arrivals unpacked and stepped, leaver counter reset) is long done
   if (h->xdone_recorded) { CK(cudaStreamWaitEvent(s, h->ev_xdone, 0)); h->xdone_recorded = 0; }
   if (mts && !h->mts_env_cached) {                         // first visit, I:5412-5414
+    int rc = mts_first_visit(h);                           // what icebergs_init does once the bergs are in, I:166-172
+    if (rc) return rc;
     LAUNCH(h, k_mts_env_cache, h->n_slots, 128, h->g, h->b, h->dp, h->dcnt, h->n_slots);
-    if (h->b.max_bonds > 0) LAUNCH(h, k_assign_n_bonds, h->n_slots, 128, h->b, h->n_slots);
+    if (h->b.max_bonds > 0) LAUNCH(h, k_assign_n_bonds, h->n_slots, 128, h->b, h->n_slots, h->p.use_broken_bonds_for_substep_contact ? 1 : 0);
     h->mts_env_cached = 1;
   }
   if (!h->p.static_icebergs) {

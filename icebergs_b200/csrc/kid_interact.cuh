@@ -410,6 +410,7 @@ __global__ void k_conglom_sweep(const __grid_constant__ DevBergs b, long long n_
   for (int k = 0; k < b.max_bonds; k++) {
     long long slot = (long long)k * b.capacity + s;
     if (b.bond_other_id[slot] == 0) continue;
+    if (b.bond_broken && b.bond_broken[slot] == 1) continue;      // dem: a broken bond no longer joins (F:2661)
     int32_t o = b.bond_other_slot[slot];
     if (o < 0) continue;
     int32_t l = b.conglom_id[o];

@@ -785,13 +785,39 @@ __global__ void k_mts_finish(const __grid_constant__ DevGrid g, const __grid_con
   if (i != i0 || j != j0) atomicAdd(&cnt->n_cell_moves, 1ull);
 }
 
-// assign_n_bonds F:4617-4637
-__global__ void k_assign_n_bonds(const __grid_constant__ DevBergs b, long long n_slots) {
+// assign_n_bonds F:4617-4637; with use_broken_bonds_for_substep_contact a broken bond was already taken off the
+// count when it broke (I:1172, I:1193)
+__global__ void k_assign_n_bonds(const __grid_constant__ DevBergs b, long long n_slots, int skip_broken) {
   long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_slots) return;
   int n = 0;
-  for (int k = 0; k < b.max_bonds; k++) if (b.bond_other_id[(long long)k * b.capacity + s] != 0) n++;
+  for (int k = 0; k < b.max_bonds; k++) {
+    long long slot = (long long)k * b.capacity + s;
+    if (b.bond_other_id[slot] != 0 && !(skip_broken && b.bond_broken && b.bond_broken[slot] == 1)) n++;
+  }
   b.n_bonds[s] = n;
+}
+
+// remove_broken_bonds_between_congloms F:2692-2733 (use_broken_bonds_for_substep_contact): a broken bond whose two
+// elements ended up in different conglomerates is dropped, on both elements
+__global__ void k_dem_drop_split_bonds(const __grid_constant__ DevBergs b, long long n_slots) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots || !(b.flags[s] & BF_ALIVE)) return;
+  for (int k = 0; k < b.max_bonds; k++) {
+    long long slot = (long long)k * b.capacity + s;
+    if (b.bond_other_id[slot] == 0 || b.bond_broken[slot] != 1) continue;
+    int32_t o = b.bond_other_slot[slot];
+    if (o < 0 || b.conglom_id[o] == b.conglom_id[s]) continue;
+    if (!(b.n_bonds[s] < b.max_bonds || b.n_bonds[o] < b.max_bonds)) continue;
+    b.bond_other_id[slot] = 0; b.bond_other_slot[slot] = -1;
+  }
+}
+
+// dem_tests_init F:4685-4710: the start position becomes the current one (the beam loads key on start_lon)
+__global__ void k_dem_tests_init(const __grid_constant__ DevBergs b, long long n_slots) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots || !(b.flags[s] & BF_ALIVE)) return;
+  b.f64[C_START_LON][s] = b.f64[C_LON][s]; b.f64[C_START_LAT][s] = b.f64[C_LAT][s];
 }
 
 }  // namespace kid

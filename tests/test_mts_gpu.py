@@ -67,4 +67,71 @@ def test_mts_implicit_inner_steps(fc):
 
 def test_mts_refuses_what_is_not_built():
     with pytest.raises(api.KidFatal):
-        mts_pair(dem=1)
+        mts_pair(dem=1, iceberg_bonds_on=0, manually_initialize_bonds=0, max_bonds=0)
+
+
+# ---------------------------------------------------------------------------------------------- DEM (a15, a17)
+IKID = dict(dem=1, poisson=0.3, dem_damping_coef=1.0, dem_spring_coef=4471.94)
+# absolute floors: before the collision the tangential displacements (~1e-14 m on 780 m bonds), relative rotations and
+# stresses are rounding noise around zero
+BOND_F64 = dict(length=0.0, tangd1=1e-9, tangd2=1e-9, nstress=1e-8, sstress=1e-8, rel_rotation=1e-10)
+
+
+def check_bonds(p, context, rtol):
+    g, o = p.b.get_bonds(), p.o.get_bonds()
+    kg = np.lexsort((g["other_id"], g["first_id"])); ko = np.lexsort((o["other_id"], o["first_id"]))
+    assert np.array_equal(g["first_id"][kg], o["first_id"][ko]) and np.array_equal(g["other_id"][kg], o["other_id"][ko]), context
+    assert np.array_equal(g["broken"][kg], o["broken"][ko]), f"{context}: broken flags"
+    for k, floor in BOND_F64.items():
+        a, b = g[k][kg], o[k][ko]
+        scale = max(np.abs(b).max(), 1e-300)
+        assert np.abs(a - b).max() <= rtol * scale + floor, f"{context}: bond {k} differs by {np.abs(a - b).max():.2e} (scale {scale:.2e})"
+
+
+def test_ikid_dem_first_steps():
+    """input_iKID.nml: the bonded elements interact through calculate_force_dem (normal + shear springs, torque from
+    relative rotation, damping; Wang 2020), the pair forces are evaluated once and stored on both half-bonds."""
+    p = mts_pair(**IKID)
+    assert p.b.count_bergs() == 16 == p.o.count_bergs()              # README:16-22 '#= 16' for iKID
+    p.step(1)
+    p.check("one step", rtol=1e-10)
+    check_bonds(p, "one step", 1e-9)
+    names = ["id", "ang_vel", "ang_accel", "rot"]
+    g, o = by_id(p.b.get_bergs(names)), by_id(p.o.get_bergs(names))
+    for k in names[1:]:
+        scale = max(np.abs(o[k]).max(), 1e-300)
+        assert np.abs(g[k] - o[k]).max() <= 1e-8 * scale + 1e-18, k
+    p.step(49)
+    p.check("50 steps", rtol=1e-9)
+    check_bonds(p, "50 steps", 1e-7)
+    p.end()
+
+
+def test_ikid_dem_through_contact():
+    p = mts_pair(**IKID)
+    gaps = []
+    for k in range(14):
+        p.step(50)
+        p.check(f"{50 * (k + 1)} steps", rtol=1e-6)
+        g = by_id(p.b.get_bergs(["id", "lat"]))
+        half = g["lat"] < 10.0e3
+        gaps.append(float(g["lat"][~half].min() - g["lat"][half].max()))
+    assert min(gaps) < 1100.0 and gaps[-1] > min(gaps), f"no bounce: {gaps}"
+    assert p.b.count_bergs() == 16 == p.o.count_bergs()
+    check_bonds(p, "700 steps", 1e-5)
+    p.end()
+
+
+def test_dem_bonds_break_under_stress():
+    """fracture_criterion='stress' with thresholds the collision exceeds: bonds break on the sub-steps
+    (calculate_force_dem I:1137-1198) or after the long step (break_bonds_dem F:4713), conglomerates split."""
+    for on_sub in (1, 0):
+        p = mts_pair(**IKID, fracture_criterion_stress=1, frac_thres_n=60.0, frac_thres_t=12.0, break_bonds_on_sub_steps=on_sub)
+        n0 = len(p.o.get_bonds()["first_id"])
+        for k in range(14):
+            p.step(50)
+            p.check(f"break_on_sub={on_sub}, {50 * (k + 1)} steps", rtol=1e-6)
+            check_bonds(p, f"break_on_sub={on_sub}, {50 * (k + 1)} steps", 1e-5)
+        o = p.o.get_bonds()
+        assert len(o["first_id"]) < n0 or o["broken"].any(), "no bond broke: thresholds too high for this case"
+        p.end()
