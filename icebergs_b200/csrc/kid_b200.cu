@@ -1208,7 +1208,11 @@ const ColMap kColMap[] = {
     {C_LON_OLD, &KidBergColumns::lon_old}, {C_LAT_OLD, &KidBergColumns::lat_old},
     {C_AXN_FAST, &KidBergColumns::axn_fast}, {C_AYN_FAST, &KidBergColumns::ayn_fast},
     {C_BXN_FAST, &KidBergColumns::bxn_fast}, {C_BYN_FAST, &KidBergColumns::byn_fast},
-    {C_ANG_VEL, &KidBergColumns::ang_vel}, {C_ANG_ACCEL, &KidBergColumns::ang_accel}, {C_ROT, &KidBergColumns::rot}};
+    {C_ANG_VEL, &KidBergColumns::ang_vel}, {C_ANG_ACCEL, &KidBergColumns::ang_accel}, {C_ROT, &KidBergColumns::rot},
+    {C_UO, &KidBergColumns::uo}, {C_VO, &KidBergColumns::vo}, {C_UI, &KidBergColumns::ui}, {C_VI, &KidBergColumns::vi},
+    {C_UA, &KidBergColumns::ua}, {C_VA, &KidBergColumns::va}, {C_SSH_X, &KidBergColumns::ssh_x}, {C_SSH_Y, &KidBergColumns::ssh_y},
+    {C_SST, &KidBergColumns::sst}, {C_SSS, &KidBergColumns::sss}, {C_CN, &KidBergColumns::cn}, {C_HI, &KidBergColumns::hi},
+    {C_OD, &KidBergColumns::od}};
 }  // namespace
 
 extern "C" int32_t kid_set_bergs(kid_t* h, int64_t n, const KidBergColumns* c) {
@@ -1320,9 +1324,6 @@ extern "C" int32_t kid_get_bergs(kid_t* h, int64_t* n, KidBergColumns* c, int32_
     CK(cudaMemcpy(tmp.data(), src, sizeof(double) * ns, cudaMemcpyDeviceToHost));
     for (int64_t k = 0; k < nk; k++) dst[k] = tmp[(size_t)keep[k]];
   }
-  double* zero_cols[] = {c->axn_fast, c->ayn_fast, c->bxn_fast, c->byn_fast, c->ang_vel, c->ang_accel, c->rot,
-                         c->uo, c->vo, c->ui, c->vi, c->ua, c->va, c->ssh_x, c->ssh_y, c->sst, c->sss, c->cn, c->hi, c->od};
-  for (double* z : zero_cols) if (z) for (int64_t k = 0; k < nk; k++) z[k] = 0.;
   if (c->static_berg) for (int64_t k = 0; k < nk; k++) c->static_berg[k] = (fl[(size_t)keep[k]] & BF_STATIC) ? 1. : 0.;
   if (c->halo_berg) for (int64_t k = 0; k < nk; k++) c->halo_berg[k] = (double)hc[(size_t)keep[k]];
   std::vector<int32_t> ti((size_t)ns);

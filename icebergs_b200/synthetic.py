@@ -283,3 +283,49 @@ def footloose_forcing(grid, ibuo=1.0, ibvo=0.1, ibua=-1.0, sst=-0.5):
     f["vo"] = np.ascontiguousarray(np.where(grid.res * i1 > 10000.0, -ibvo, ibvo), dtype=np.float64)
     f["tauxa"] = np.full_like(f["tauxa"], ibua)
     return f
+
+
+def beam_bergs(nbergs=29, r=0.25, xs=101.0e3, ys=151.0e3, h=1.0, rho_ice=800.0):
+    """tests/dem_ssbeam_test/makeberg/makeberg.py:253-314 (and dem_cbeam_test): a row of square-packed elements of
+    radius r, 2r apart, starting at (xs + 0, ys + 2r)."""
+    area = (2.0 * r) ** 2
+    x = xs + 2.0 * r * np.arange(nbergs)
+    y = np.full(nbergs, ys + 2.0 * r)
+    z = np.zeros(nbergs)
+    w = np.full(nbergs, np.sqrt(area))
+    m = np.full(nbergs, h * rho_ice * area)
+    return dict(lon=x, lat=y, uvel=z.copy(), vvel=z.copy(), mass=m, thickness=np.full(nbergs, h), width=w.copy(), length=w.copy(),
+                axn=z.copy(), ayn=z.copy(), bxn=z.copy(), byn=z.copy(), start_lon=x.copy(), start_lat=y.copy(), start_day=z.copy(),
+                start_mass=m.copy(), mass_scaling=np.ones(nbergs), mass_of_bits=z.copy(), heat_density=z.copy(),
+                start_year=np.zeros(nbergs, dtype=np.int32))
+
+
+def beam_params(default_params, **over):
+    """&icebergs_nml of tests/dem_ssbeam_test/input.nml (the values that reach the hot path; mass spreading off)."""
+    kw = dict(halo=3, Lx=300.0e3, grid_is_latlon=0, grid_is_regular=1, hexagonal_icebergs=0, rho_bergs=800.0,
+              dem_beam_test=1, dem=1, poisson=0.3, dem_damping_coef=0.1, dem_spring_coef=1.0e9, mts=1, mts_sub_steps=100000,
+              force_convergence=1, convergence_tolerance=1e-8, contact_distance=2000.0, contact_spring_coef=1.0e-8,
+              cdrag_grounding=3.16e6, h_to_init_grounding=200.0, spring_coef=1.0e-5, radial_damping_coef=0.0,
+              tangental_damping_coef=0.0, scale_damping_by_pmag=0, critical_interaction_damping_on=0, tang_crit_int_damp_on=0,
+              LoW_ratio=1.5, bergy_bit_erosion_fraction=0.0, sicn_shift=0.0, use_operator_splitting=1, speed_limit=0.0,
+              tip_parameter=0.0, coastal_drift=0.0, tidal_drift=0.0, runge_not_verlet=0, allow_bergs_to_roll=0,
+              use_updated_rolling_scheme=0, melt_cutoff=10.0, apply_thickness_cutoff_to_gridded_melt=1,
+              apply_thickness_cutoff_to_bergs_melt=1, set_melt_rates_to_zero=1, iceberg_bonds_on=1, interactive_icebergs_on=1,
+              only_interactive_forces=1, use_new_predictive_corrective=1, max_bonds=4, internal_bergs_for_drag=1,
+              manually_initialize_bonds=1, manually_initialize_bonds_from_radii=1, use_roundoff_fix=1, old_bug_bilin=0,
+              tau_is_velocity=0, add_weight_to_ocean=0)
+    kw.update(over)
+    return default_params(**kw)
+
+
+def cantilever_bergs(rows=3, per_row=30, r=2500.0, xs=101.0e3, ys=151.0e3, h=1.0, rho_ice=900.0):
+    """tests/dem_cbeam_test/makeberg/makeberg.py:253-314: rows x per_row square-packed elements, the first of each
+    row static (the clamped end)."""
+    area = (2.0 * r) ** 2
+    x = np.tile(xs + 2.0 * r * np.arange(per_row), rows)
+    y = np.repeat(ys + 2.0 * r * np.arange(rows), per_row)
+    n = rows * per_row
+    cols = beam_bergs(n, r, xs, ys, h, rho_ice)
+    cols.update(lon=x, lat=y, start_lon=x.copy(), start_lat=y.copy())
+    cols["static_berg"] = np.where(np.arange(n) % per_row == 0, 1.0, 0.0)
+    return cols

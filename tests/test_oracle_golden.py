@@ -11,6 +11,7 @@ import pytest
 import kid_oracle_py as O
 from common import Case, run_oracle
 from icebergs_b200 import _cdefs as D
+from icebergs_b200 import synthetic as S
 
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -171,3 +172,61 @@ def test_hexagon_quadrant_areas_I261():
         assert abs(area - k["area"]) <= k["tol"], case["name"]
         for got, want in zip(q, case["Q"]):
             assert abs(got - want) <= k["tol"], (case["name"], q, case["Q"])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# DEM known answers: the reference's two beam tests (Wang 2020, sections 3.1 and 3.2).  tests/dem_ssbeam_test and
+# tests/dem_cbeam_test are checked by eye in the reference ("the beam should bend into alignment with the plotted
+# line", README; the line is beam theory, animate_trajectories.py:143-157 / :149-157); here the same comparison is a
+# number.  They pin calculate_force_dem (normal + shear springs, torque from relative rotation), the rotation update
+# and the explicit MTS sub-steps of the oracle.
+def _beam_run(bergs, nsteps, dt, **over):
+    from icebergs_b200 import api
+    g = S.CartesianGrid(20, 20, 15000.0)
+    dom = api.Domain.single(20, 20, halo=3, cyclic_x=True)
+    o = O.Oracle(20, 20, dt, (1, 0.0), params=S.beam_params(api.default_params, **over), domain=dom, **g.init_args())
+    o.set_bergs(**bergs)
+    o.set_bonds()
+    f = g.forcing(ibuo=0.0, ibvo=0.0, collision_test=False)
+    for k in range(nsteps):
+        c, h = f["calving"].copy(), f["calving_hflx"].copy()
+        o.run((1, k * dt / 86400.0), c, f["uo"], f["vo"], f["ui"], f["vi"], f["tauxa"], f["tauya"], f["ssh"], f["sst"], h,
+              f["cn"], f["hi"], sss=f["sss"])
+    b = o.get_bergs(["lon", "lat", "vvel", "rot", "start_lon", "start_lat"])
+    o.close()
+    order = np.lexsort((b["start_lon"], b["start_lat"]))
+    return {k: v[order] for k, v in b.items()}
+
+
+def test_dem_simply_supported_beam_known_answer():
+    """dem_ssbeam_test: 29 elements of radius 0.25 m, E = 1e9 Pa, 1.5e5 N at mid-span, ends held vertically
+    (I:1862-1869); 1e5 sub-steps per 1 s step.  Euler-Bernoulli mid-span deflection P l^3 / (48 E I) = -0.823 m."""
+    b0 = S.beam_bergs()
+    b = _beam_run(b0, 8, 1.0)
+    xa = b0["lon"] - b0["lon"][0]
+    l, P, YM, AI = xa.max(), -1.5e5, 1.0e9, 1.0 * 0.5 ** 3 / 12.0
+    w1 = -P * xa * (4.0 * xa * xa - 3.0 * l * l) / (48.0 * YM * AI)
+    w2 = P * (xa - l) * (l * l - 8.0 * l * xa + 4.0 * xa * xa) / (48.0 * YM * AI)
+    w = np.where(xa > 0.5 * l, w2, w1)                       # animate_trajectories.py:143-157
+    d = b["lat"] - b0["lat"]
+    assert abs(d[14] / w[14] - 1.0) < 0.03, (d[14], w[14])
+    assert np.sqrt(np.mean((d - w) ** 2)) < 0.03 * np.abs(w).max()
+    assert np.abs(b["vvel"]).max() < 0.05                    # damped out
+
+
+def test_dem_cantilever_beam_known_answer():
+    """dem_cbeam_test geometry (3 x 30 elements of radius 2.5 km, clamped = static first column, 1.5e10 N shared by the
+    three end elements I:1870-1876, orig_dem_moment_of_inertia), stiffened to E = 1e11 Pa so that the linear theory the
+    reference plots applies: tip deflection P l^3 / (3 E I), I = thick (3 * 5 km)^3 / 12."""
+    b0 = S.cantilever_bergs()
+    E = 1.0e11
+    b = _beam_run(b0, 200, 100.0, dem_beam_test=2, orig_dem_moment_of_inertia=1, dem_damping_coef=0.7, rho_bergs=900.0,
+                  mts_sub_steps=2000, dem_spring_coef=E)
+    l, hh, P = 29 * 5000.0, 3.0 * 5000.0, -1.5e10
+    wtip = P * l ** 3 / (3.0 * E * hh ** 3 / 12.0)
+    tips = [29, 59, 89]
+    tip = np.mean(b["lat"][tips] - b0["lat"][tips])
+    assert abs(tip / wtip - 1.0) < 0.03, (tip, wtip)          # 1.5 % above: shear deformation of the lattice
+    assert np.abs(b["lat"][[0, 30, 60]] - b0["lat"][[0, 30, 60]]).max() == 0.0      # the clamped column is static
+    theta = P * l * l / (2.0 * E * hh ** 3 / 12.0)
+    assert abs(np.mean(b["rot"][tips]) / theta - 1.0) < 0.03
