@@ -12,11 +12,14 @@
  * is pinned against the reference's own known answers that are portable
  * (tests/test_oracle_golden.py): bilin corner exactness F:7313-7316, the 64-bit
  * id round trip F:7319-7325, the point-in-triangle regression I:234-242 and the
- * 8 hexagon area identities I:261-348 (for the spreading rows), the collision
- * test berg count, and by review against the cited lines.  Everything else on
- * the path (accel, thermodynamics) has no numeric pin in the reference beyond
- * build-specific checksums: for those rows parity is "oracle-vs-kernel, oracle
- * by review" = parity unpinned.
+ * 8 hexagon area identities I:261-348 (for the spreading rows), the berg counts
+ * of the collision tests (16) and of the footloose test (12 after 69 120 steps),
+ * the reference's two DEM beam tests against beam theory (Wang 2020 3.1 / 3.2;
+ * tests/dem_ssbeam_test, tests/dem_cbeam_test: calculate_force_dem, the rotation
+ * update and the MTS sub-steps), and by review against the cited lines.
+ * accel, thermodynamics and calculate_force have no numeric pin in the reference
+ * beyond build-specific checksums: for those rows parity is "oracle-vs-kernel,
+ * oracle by review" = parity unpinned.
  */
 #ifndef KID_ORACLE_H
 #define KID_ORACLE_H
