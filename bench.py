@@ -29,6 +29,9 @@ GNI, GNJ = 1440, 720
 DT = 3600.0
 B_BERG = 290.0      # algorithmic bytes per berg-step
 B_CELL = 224.0      # algorithmic bytes per occupied-cell-step
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_step launch on the N=1 workload (10M bergs), from the
+# `ncu --set full` capture summarised in profiles/r1i_kstep_final_summary.txt (1.607 GB read + 1.425 GB written)
+NCU_TRAFFIC_10M = 3.032e9
 METRIC = "berg_steps_per_sec"
 UNIT = "berg-steps/s"
 
@@ -302,7 +305,9 @@ def main():
                                   "add_weight_to_ocean off (the metric is dyn+thermo; mass spreading is SURVEY 8f1)",
                        "sort_interval": int(os.environ.get("KID_SORT_INTERVAL", "32")), "per_rank": per_rank},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k_step (fused evolve+thermodynamics)",
+                         "traffic": NCU_TRAFFIC_10M if (world == 1 and n_per == 10_000_000 and GNI == 1440) else None,
+                         "traffic_source": "ncu --set full capture of this workload, profiles/r1i_kstep_final_summary.txt",
+                         "peak_source": peak_src, "kernel": "k_step (fused evolve+thermodynamics)",
                          "alg_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms},
             "gpu_launches": int(l1 - l0), "clocks": clk,
         }

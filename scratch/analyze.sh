@@ -4,7 +4,7 @@ set -e
 W=/tmp/cub_$1; rm -rf $W; mkdir -p $W; cd $W
 cuobjdump -xelf all /root/repo/icebergs_b200/lib/libkid_b200.so > /dev/null
 ncu -i /root/repo/gpurun_out/prof_kstep_$1.ncu-rep --page source --csv > src.csv 2>/dev/null
-python /root/repo/profiles/line_profile.py src.csv kid_b200.sm_100a.cubin k_stepILb0ELb0ELb0ELb1E /root/repo/icebergs_b200/csrc | head -${2:-30}
+python /root/repo/profiles/line_profile.py src.csv kid_b200.sm_100a.cubin k_stepILb0ELb0ELb0ELb1ELb0E /root/repo/icebergs_b200/csrc | head -${2:-30}
 ncu -i /root/repo/gpurun_out/prof_kstep_$1.ncu-rep --page raw --csv 2>/dev/null | python3 -c "
 import csv,sys
 rows=list(csv.reader(sys.stdin)); hdr=rows[0]; d=dict(zip(hdr,rows[2]))
