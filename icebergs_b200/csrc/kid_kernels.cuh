@@ -16,7 +16,9 @@
 
 namespace kid {
 
+#ifndef KID_BLOCK
 #define KID_BLOCK 128
+#endif
 #ifndef KID_MINBLOCKS
 #define KID_MINBLOCKS 5
 #endif

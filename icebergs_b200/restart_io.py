@@ -32,6 +32,16 @@ BERG_VARS = [
     ("mass_of_fl_bergy_bits", "d", "mass of bergy bits associated with footloose bits", "kg"),
     ("static_berg", "d", "static_berg", "dimensionless"),
 ]
+# written only by runs that carry them (mts: fmsio:300-306, dem: fmsio:308-314) and read back when present
+MTS_VARS = [("axn_fast", "d", "explicit zonal acceleration for fast dynamics", "m/s^2"),
+            ("ayn_fast", "d", "explicit meridional acceleration for fast dynamics", "m/s^2"),
+            ("bxn_fast", "d", "implicit zonal acceleration for fast dynamics", "m/s^2"),
+            ("byn_fast", "d", "implicit meridional acceleration for fast dynamics", "m/s^2")]
+DEM_VARS = [("ang_vel", "d", "angular velocity", "rad/s"), ("ang_accel", "d", "angular acceleration", "rad/s^2"),
+            ("rot", "d", "accumulated rotation", "rad")]
+BOND_DEM_VARS = [("tangd1", "d", "tangential displacement, x", "m"), ("tangd2", "d", "tangential displacement, y", "m"),
+                 ("nstress", "d", "normal stress", "Pa"), ("sstress", "d", "shear stress", "Pa"),
+                 ("rel_rotation", "d", "relative rotation", "rad"), ("broken", "i", "bond is broken", "none")]
 OPTIONAL_ZERO = ("axn", "ayn", "bxn", "byn", "fl_k", "mass_of_bits", "mass_of_fl_bits", "mass_of_fl_bergy_bits",
                  "heat_density", "static_berg")          # read_real_vector(..., value_if_not_in_file=0.), fmsio:746-781
 
@@ -75,6 +85,9 @@ def write_restart_bergs(path, cols):
         else:
             raise KeyError(f"write_restart_bergs: column {name!r} is missing")
         out.append((name, typ, long_name, units, np.asarray(data, dtype=np.float64 if typ == "d" else np.int32)))
+    for name, typ, long_name, units in MTS_VARS + DEM_VARS:
+        if name in cols:
+            out.append((name, typ, long_name, units, np.asarray(cols[name], dtype=np.float64)))
     _write(path, n, out)
 
 
@@ -93,6 +106,9 @@ def read_restart_bergs(path, ignore_ij_restart=False):
             cols[name] = np.array(f.variables[name][:], dtype=np.float64 if typ == "d" else np.int32)
         elif name in OPTIONAL_ZERO:
             cols[name] = np.zeros(n)
+    for name, _, _, _ in MTS_VARS + DEM_VARS:
+        if name in names:
+            cols[name] = np.array(f.variables[name][:], dtype=np.float64)
     if "id_cnt" in names and "id_ij" in names:
         cols["id"] = id_from_2_ints(np.array(f.variables["id_cnt"][:]), np.array(f.variables["id_ij"][:]))
     f.close()
@@ -108,7 +124,8 @@ def write_restart_bonds(path, bonds):
     fc, fij = split_id(bonds["first_id"])
     oc, oij = split_id(bonds["other_id"])
     i32 = lambda a: np.asarray(a, dtype=np.int32)
-    _write(path, n, [
+    extra = [(nm, t, ln, u, np.asarray(bonds[nm], dtype=np.float64 if t == "d" else np.int32)) for nm, t, ln, u in BOND_DEM_VARS if nm in bonds]
+    _write(path, n, extra + [
         ("first_berg_ine", "i", "iceberg ine of first berg in bond", "dimensionless", i32(bonds["first_ine"])),
         ("first_berg_jne", "i", "iceberg jne of first berg in bond", "dimensionless", i32(bonds["first_jne"])),
         ("first_id_cnt", "i", "counter component of iceberg id first berg in bond", "dimensionless", fc),
@@ -127,6 +144,9 @@ def read_restart_bonds(path):
     out = dict(first_id=id_from_2_ints(g("first_id_cnt"), g("first_id_ij")), other_id=id_from_2_ints(g("other_id_cnt"), g("other_id_ij")),
                first_ine=g("first_berg_ine").astype(np.int32), first_jne=g("first_berg_jne").astype(np.int32),
                other_ine=g("other_berg_ine").astype(np.int32), other_jne=g("other_berg_jne").astype(np.int32))
+    for nm, t, _, _ in BOND_DEM_VARS:
+        if nm in f.variables:
+            out[nm] = g(nm).astype(np.float64 if t == "d" else np.int32)
     f.close()
     return out
 

@@ -11,6 +11,8 @@ from icebergs_b200 import synthetic as S
 def test_berg_restart_round_trip(tmp_path):
     cols, _ = S.Grid(96, 48).seed_bergs(500)
     cols["mass_of_fl_bits"] = np.linspace(0.0, 1.0e9, 500)
+    cols["axn_fast"] = np.linspace(-1e-6, 1e-6, 500)          # mts / dem runs carry these too
+    cols["rot"] = np.linspace(0.0, 0.3, 500)
     p = str(tmp_path / "icebergs.res.nc")
     R.write_restart_bergs(p, cols)
     f = netcdf_file(p, "r", mmap=False)
@@ -48,6 +50,8 @@ def test_bond_and_calving_round_trip(tmp_path):
     ids = np.array([5 * 2 ** 32 + 77, 9 * 2 ** 32 + 12], dtype=np.int64)
     bonds = dict(first_id=ids, other_id=ids[::-1].copy(), first_ine=np.array([3, 4], np.int32), first_jne=np.array([5, 6], np.int32),
                  other_ine=np.array([4, 3], np.int32), other_jne=np.array([6, 5], np.int32))
+    bonds.update(tangd1=np.array([1e-3, -1e-3]), tangd2=np.array([2e-3, -2e-3]), nstress=np.array([5.0, 5.0]), sstress=np.array([1.0, 1.0]),
+                 rel_rotation=np.array([1e-4, -1e-4]), broken=np.array([0, 1], np.int32))       # dem bond history, fmsio:484-493
     p = str(tmp_path / "bonds_iceberg.res.nc")
     R.write_restart_bonds(p, bonds)
     back = R.read_restart_bonds(p)
