@@ -17,7 +17,9 @@
 namespace kid {
 
 #ifndef KID_BLOCK
+#ifndef KID_BLOCK
 #define KID_BLOCK 128
+#endif
 #endif
 #ifndef KID_MINBLOCKS
 #define KID_MINBLOCKS 5
