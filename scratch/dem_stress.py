@@ -12,7 +12,7 @@ dom = api.Domain.single(g.gni, g.gnj, halo=3, cyclic_x=True)
 o = O.Oracle(g.gni, g.gnj, 60.0, (1, 0.0), params=S.collision_params(api.default_params, **kw), domain=dom, **g.init_args())
 o.set_bergs(**S.collision_bergs()); o.set_bonds()
 f = g.forcing()
-for k in range(700):
+for k in range(900):
     c, h = f["calving"].copy(), f["calving_hflx"].copy()
     o.run((1, k * 60.0 / 86400.0), c, f["uo"], f["vo"], f["ui"], f["vi"], f["tauxa"], f["tauya"], f["ssh"], f["sst"], h, f["cn"], f["hi"], sss=f["sss"])
     if k % 50 == 49:

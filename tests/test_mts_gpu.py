@@ -88,6 +88,8 @@ def check_bonds(p, context, rtol):
     kg = np.lexsort((g["other_id"], g["first_id"])); ko = np.lexsort((o["other_id"], o["first_id"]))
     assert np.array_equal(g["first_id"][kg], o["first_id"][ko]) and np.array_equal(g["other_id"][kg], o["other_id"][ko]), context
     assert np.array_equal(g["broken"][kg], o["broken"][ko]), f"{context}: broken flags"
+    if len(o["first_id"]) == 0:
+        return
     for k, floor in BOND_F64.items():
         a, b = g[k][kg], o[k][ko]
         scale = max(np.abs(b).max(), 1e-300)
@@ -200,3 +202,23 @@ def test_simply_supported_beam_known_answer_on_the_gpu():
     assert abs(d[14] / w_mid - 1.0) < 0.03, (d[14], w_mid)
     assert np.abs(d[[0, 28]]).max() < 1e-6                                  # the supports do not move vertically
     api.icebergs_end(h)
+
+
+def test_dem_ground_frac_switches():
+    """The remaining switches of tests/dem_ground_frac_test/input.nml on the collision scenario:
+    use_broken_bonds_for_substep_contact (broken bonds stay as contact pairs, I:1751, F:2692),
+    constant_interaction_LW with the mean element size (F:4640), short_step_mts_grounding with partial grounding
+    (I:6873-6905), hexagonal elements, fracture on the sub-steps."""
+    over = dict(IKID, use_broken_bonds_for_substep_contact=1, constant_interaction_LW=1, short_step_mts_grounding=1,
+                break_bonds_on_sub_steps=1, fracture_criterion_stress=1, frac_thres_n=25.0, frac_thres_t=5.0,
+                cdrag_grounding=100.0, h_to_init_grounding=1000.0, mts_sub_steps=200, convergence_tolerance=1e-2)
+    p = mts_pair(**over)
+    n0 = len(p.o.get_bonds()["first_id"])
+    for k in range(18):
+        p.step(50)
+        p.check(f"{50 * (k + 1)} steps", rtol=1e-6)
+        check_bonds(p, f"{50 * (k + 1)} steps", 1e-5)
+    o = p.o.get_bonds()
+    assert o["broken"].any() or len(o["first_id"]) < n0, "no bond broke"
+    assert p.b.count_bergs() == 16 == p.o.count_bergs()
+    p.end()
