@@ -70,7 +70,7 @@ struct kid_handle {
   int steps_since_sort = 0, sort_interval = 32, sorted_once = 0;
   MtsParams mp;                   // MTS scheme (evolve_icebergs_mts)
   MtsSums* dsums = nullptr;
-  int mts_env_cached = 0, mts_outer_iters = 0;
+  int mts_env_cached = 0, mts_outer_iters = 0, mts_smem_attr = 0;
   int scatter_dense = 1;          // > KID_DENSE_BERGS_PER_CELL bergs per occupied cell at the last sort (scatter_fluxes)
   int forcing_set = 0;
   int no_rotation = 0;
@@ -1700,7 +1700,16 @@ static int evolve_mts(kid_t* h) {
   const bool brk = dem && p.break_bonds_on_sub_steps && !p.use_broken_bonds_for_substep_contact;
   if (!iterate && p.explicit_inner_mts && ns <= 4096 && !getenv("KID_MTS_NO_ONE_CTA")) {
     // a few thousand elements: the whole sub-step loop in one CTA, __syncthreads() between the sweeps
-    k_mts_substeps_one_cta<<<1, 1024, 0, h->stream>>>(h->g, h->b, h->dp, h->mp, ct, h->dcnt, ns, dtf, p.mts_sub_steps);
+    static const bool no_smem = getenv("KID_MTS_NO_SMEM") != nullptr;
+    const size_t need = mts_smem_bytes(h->b, ns, dem);
+    const size_t room = 200 * 1024;
+    const int in_smem = (!no_smem && need <= room) ? 1 : 0;
+    if (in_smem && !h->mts_smem_attr) {
+      CK(cudaFuncSetAttribute(k_mts_substeps_one_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)room));
+      h->mts_smem_attr = 1;
+    }
+    const int nthr = (int)std::min<long long>(1024, std::max<long long>(32, (ns + 31) / 32 * 32));
+    k_mts_substeps_one_cta<<<1, nthr, in_smem ? need : 0, h->stream>>>(h->g, h->b, h->dp, h->mp, ct, h->dcnt, ns, dtf, p.mts_sub_steps, in_smem);
     h->launches++;
   } else {
     for (int k = 1; k <= p.mts_sub_steps; k++) {

@@ -147,6 +147,7 @@ struct DevBergs {
   int32_t* bond_broken;       // dem only, else nullptr
   // dem bond history and the saved pair forces (type(bond) F:372-386, save_bond_forces F:53), same layout as bond_length
   double* bond_dem[11];
+  double* ia_radius;          // scratch: interaction radius per berg, valid inside the shared-memory MTS kernel only
 };
 enum BondDem : int { BD_TANGD1 = 0, BD_TANGD2, BD_REL_ROT, BD_NSTRESS, BD_SSTRESS, BD_FX, BD_FY, BD_FDX, BD_FDY, BD_T, BD_TD, BD_N };
 

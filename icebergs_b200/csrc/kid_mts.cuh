@@ -296,7 +296,9 @@ __device__ __noinline__ void dem_unbonded_force(const DevBergs& b, const DevPara
     R1 = mp.constant_radius; R2 = R1;
     M1 = mp.constant_area * b.f64[C_THICKNESS][s] * p.rho_bergs; M2 = mp.constant_area * b.f64[C_THICKNESS][o] * p.rho_bergs;
   } else {
-    R1 = mts_ia_radius(p, b.f64[C_LENGTH][s] * b.f64[C_WIDTH][s]); R2 = mts_ia_radius(p, b.f64[C_LENGTH][o] * b.f64[C_WIDTH][o]);
+    // length and width do not change during the sub-steps: the radii are the same numbers whether cached or not
+    if (b.ia_radius) { R1 = b.ia_radius[s]; R2 = b.ia_radius[o]; }
+    else { R1 = mts_ia_radius(p, b.f64[C_LENGTH][s] * b.f64[C_WIDTH][s]); R2 = mts_ia_radius(p, b.f64[C_LENGTH][o] * b.f64[C_WIDTH][o]); }
     if ((R1 + R2) * (R1 + R2) <= r2) return;
     M1 = b.f64[C_MASS][s]; M2 = b.f64[C_MASS][o];
   }
@@ -734,33 +736,89 @@ __global__ void k_dem_break_bonds(const __grid_constant__ DevBergs b, const __gr
 // the next *_old).  When the whole population fits one CTA the sub-step loop runs inside a single kernel with
 // __syncthreads() between the sweeps: the bonded-conglomerate cases have 1e1..1e3 elements and 60..1e5 sub-steps,
 // launch latency is what they would otherwise cost.
+// The berg and bond state of a small population also fits the CTA's shared memory (~0.9-1.1 KB per element with
+// 4-6 bonds): `in_smem` stages every column the sweeps touch into shared memory once, runs the sub-steps on a DevBergs
+// view whose pointers address that copy (the sweeps are the same functions), and writes the state back at the end.  A
+// sweep then costs shared-memory latency instead of dependent L2 round trips.
+__host__ __device__ inline size_t mts_smem_bytes(const DevBergs& b, long long n, bool dem) {
+  auto r16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  size_t t = 0;
+  for (int c = 0; c < C_NCOLS; c++) if (b.f64[c]) t += r16(8 * n);
+  t += r16(8 * n) + 2 * r16(4 * n) + r16(n) + 2 * r16(4 * n) + r16(8 * n);           // id, ine, jne, flags, conglom_id, n_bonds, ia_radius
+  const size_t nb = (size_t)n * b.max_bonds;
+  if (nb) { t += r16(8 * nb) + r16(4 * nb) + r16(8 * nb); if (dem) t += r16(4 * nb) + BD_N * r16(8 * nb); }
+  return t;
+}
+
 __global__ void __launch_bounds__(1024)
 k_mts_substeps_one_cta(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b, const __grid_constant__ DevParams p,
                        const __grid_constant__ MtsParams mp, const CellTable ct, DevCounters* __restrict__ cnt,
-                       long long n_slots, double dt, int nsub) {
-  const int per = (int)((n_slots + blockDim.x - 1) / blockDim.x);
+                       long long n_slots, double dt, int nsub, int in_smem) {
+  extern __shared__ __align__(16) unsigned char kid_smem[];
+  const int n = (int)n_slots, nt = blockDim.x, tid = threadIdx.x;
+  const int per = (n + nt - 1) / nt;
   const bool brk = p.dem && mp.break_bonds_on_sub_steps && !mp.use_broken_bonds_for_substep_contact;
+  const bool dem = p.dem != 0;
+  DevBergs v = b;
+  if (in_smem) {
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { void* q = kid_smem + off; off += (bytes + 15) & ~(size_t)15; return q; };
+    const long long nb = (long long)n * b.max_bonds;
+    v.capacity = n;
+    for (int c = 0; c < C_NCOLS; c++) if (b.f64[c]) v.f64[c] = (double*)carve(8 * (size_t)n);
+    v.id = (int64_t*)carve(8 * (size_t)n); v.ine = (int32_t*)carve(4 * (size_t)n); v.jne = (int32_t*)carve(4 * (size_t)n);
+    v.flags = (uint8_t*)carve((size_t)n); v.conglom_id = (int32_t*)carve(4 * (size_t)n); v.n_bonds = (int32_t*)carve(4 * (size_t)n);
+    v.ia_radius = (double*)carve(8 * (size_t)n);
+    if (nb) {
+      v.bond_other_id = (int64_t*)carve(8 * (size_t)nb); v.bond_other_slot = (int32_t*)carve(4 * (size_t)nb);
+      v.bond_length = (double*)carve(8 * (size_t)nb);
+      if (dem) { v.bond_broken = (int32_t*)carve(4 * (size_t)nb); for (int q = 0; q < BD_N; q++) v.bond_dem[q] = (double*)carve(8 * (size_t)nb); }
+    }
+    for (int s = tid; s < n; s += nt) {
+      for (int c = 0; c < C_NCOLS; c++) if (b.f64[c]) v.f64[c][s] = b.f64[c][s];
+      v.id[s] = b.id[s]; v.ine[s] = b.ine[s]; v.jne[s] = b.jne[s]; v.flags[s] = b.flags[s];
+      v.conglom_id[s] = b.conglom_id[s]; v.n_bonds[s] = b.n_bonds[s];
+      v.ia_radius[s] = mts_ia_radius(p, b.f64[C_LENGTH][s] * b.f64[C_WIDTH][s]);
+      for (int k = 0; k < b.max_bonds; k++) {
+        const long long gs = (long long)k * b.capacity + s, ls = (long long)k * n + s;
+        v.bond_other_id[ls] = b.bond_other_id[gs]; v.bond_other_slot[ls] = b.bond_other_slot[gs]; v.bond_length[ls] = b.bond_length[gs];
+        if (dem) { v.bond_broken[ls] = b.bond_broken[gs]; for (int q = 0; q < BD_N; q++) v.bond_dem[q][ls] = b.bond_dem[q][gs]; }
+      }
+    }
+    __syncthreads();
+  }
 #define KID_EACH_ACTIVE(body)                                                 \
   for (int q = 0; q < per; q++) {                                             \
-    long long s = (long long)q * blockDim.x + threadIdx.x;                    \
-    if (s < n_slots && mts_active(b, s, b.flags[s])) { body; }                \
+    long long s = (long long)q * nt + tid;                                    \
+    if (s < n && mts_active(v, s, v.flags[s])) { body; }                      \
   }                                                                           \
   __syncthreads();
   for (int k = 0; k < nsub; k++) {
-    KID_EACH_ACTIVE(mts_phase_pos(b, p, s, dt))
-    if (p.dem) { KID_EACH_ACTIVE(dem_pair_phase(b, p, mp, cnt, s, dt)) }
+    KID_EACH_ACTIVE(mts_phase_pos(v, p, s, dt))
+    if (dem) { KID_EACH_ACTIVE(dem_pair_phase(v, p, mp, cnt, s, dt)) }
     double su, su1, su2;
-    KID_EACH_ACTIVE(mts_phase_vel(g, b, p, mp, ct, cnt, s, dt, 1, false, su, su1, su2))
-    KID_EACH_ACTIVE(mts_phase_end(b, p, mp, s, dt))
+    KID_EACH_ACTIVE(mts_phase_vel(g, v, p, mp, ct, cnt, s, dt, 1, false, su, su1, su2))
+    KID_EACH_ACTIVE(mts_phase_end(v, p, mp, s, dt))
     if (brk) {
       for (int q = 0; q < per; q++) {
-        long long s = (long long)q * blockDim.x + threadIdx.x;
-        if (s < n_slots && (b.flags[s] & BF_ALIVE)) dem_phase_break(b, mp, s);
+        long long s = (long long)q * nt + tid;
+        if (s < n && (v.flags[s] & BF_ALIVE)) dem_phase_break(v, mp, s);
       }
       __syncthreads();
     }
   }
 #undef KID_EACH_ACTIVE
+  if (in_smem) {
+    for (int s = tid; s < n; s += nt) {
+      for (int c = 0; c < C_NCOLS; c++) if (b.f64[c]) b.f64[c][s] = v.f64[c][s];
+      b.n_bonds[s] = v.n_bonds[s];
+      for (int k = 0; k < b.max_bonds; k++) {
+        const long long gs = (long long)k * b.capacity + s, ls = (long long)k * n + s;
+        b.bond_other_id[gs] = v.bond_other_id[ls]; b.bond_other_slot[gs] = v.bond_other_slot[ls]; b.bond_length[gs] = v.bond_length[ls];
+        if (dem) { b.bond_broken[gs] = v.bond_broken[ls]; for (int q = 0; q < BD_N; q++) b.bond_dem[q][gs] = v.bond_dem[q][ls]; }
+      }
+    }
+  }
 }
 
 // end of evolve_icebergs_mts I:7050-7075: the cell of the new position, grounding
