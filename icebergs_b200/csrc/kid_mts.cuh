@@ -455,21 +455,44 @@ __device__ __noinline__ void dem_sum_phase(const DevGrid& g, const DevBergs& b, 
   }
   const bool run_contact = !((b.n_bonds[s] == b.max_bonds) || mp.use_broken_bonds_for_substep_contact);
   if (run_contact) {
+    // The sweep over the 3x3 cells visits every element of the conglomerate that sits there (all 29 of a beam, every
+    // sub-step): the berg's own partners are looked up once, and on Cartesian grids with cached radii the range test
+    // of dem_unbonded_force is made here first -- the same arithmetic (x * 1.0 == x), so the same decision.
     const int32_t my_cong = b.conglom_id[s];
+    const int mb = b.max_bonds;
+    int32_t partner[12];                            // max_bonds <= 12 (kid_init)
+#pragma unroll
+    for (int q = 0; q < 12; q++) {
+      partner[q] = -2;
+      if (q < mb) {
+        long long slot = (long long)q * b.capacity + s;
+        if (b.bond_other_id[slot] != 0) partner[q] = b.bond_other_slot[slot];
+      }
+    }
+    const int32_t* __restrict__ cong = b.conglom_id;
+    const int32_t* __restrict__ nbd = b.n_bonds;
+    const double* __restrict__ lon_old = b.f64[C_LON_OLD];
+    const double* __restrict__ lat_old = b.f64[C_LAT_OLD];
+    const double* __restrict__ rad = b.ia_radius;
+    const bool quick = !p.grid_is_latlon && rad != nullptr && !mp.constant_interaction_LW;
+    const double lon_s = lon_old[s], lat_s = lat_old[s], R_s = quick ? rad[s] : 0.;
     for (int grdj = max(j - 1, g.jsd + 1); grdj <= min(j + 1, g.jed); grdj++)
       for (int grdi = max(i - 1, g.isd + 1); grdi <= min(i + 1, g.ied); grdi++) {
         int c = gidx(g, grdi, grdj);
         int n = ct.count[c];
-        long long o0 = ct.start[c];
+        int o0 = ct.start[c];
         for (int k = 0; k < n; k++) {
-          long long o = o0 + k;
-          if (b.conglom_id[o] != my_cong || !(b.n_bonds[o] < b.max_bonds)) continue;
-          bool partner = false;
-          for (int q = 0; q < b.max_bonds; q++) {
-            long long slot = (long long)q * b.capacity + s;
-            if (b.bond_other_id[slot] != 0 && b.bond_other_slot[slot] == (int32_t)o) partner = true;
+          const int o = o0 + k;
+          if (cong[o] != my_cong || !(nbd[o] < mb)) continue;
+          bool is_partner = false;
+#pragma unroll
+          for (int q = 0; q < 12; q++) is_partner |= (partner[q] == o);
+          if (is_partner) continue;
+          if (quick) {
+            double rx = lon_s - lon_old[o], ry = lat_s - lat_old[o], r2 = (rx * rx) + (ry * ry), RR = R_s + rad[o];
+            if (RR * RR <= r2) continue;
           }
-          if (!partner) dem_unbonded_force(b, p, mp, s, o, IA_x, IA_y, IAd_x, IAd_y, uvel0, vvel0, uvel0, vvel0);
+          dem_unbonded_force(b, p, mp, s, o, IA_x, IA_y, IAd_x, IAd_y, uvel0, vvel0, uvel0, vvel0);
         }
       }
   }
