@@ -1704,12 +1704,15 @@ static int evolve_mts(kid_t* h) {
     const size_t need = mts_smem_bytes(h->b, ns, dem);
     const size_t room = 200 * 1024;
     const int in_smem = (!no_smem && need <= room) ? 1 : 0;
+    const bool small = ns <= 128;
     if (in_smem && !h->mts_smem_attr) {
-      CK(cudaFuncSetAttribute(k_mts_substeps_one_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)room));
+      CK(cudaFuncSetAttribute(k_mts_substeps_one_cta<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)room));
+      CK(cudaFuncSetAttribute(k_mts_substeps_one_cta<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)room));
       h->mts_smem_attr = 1;
     }
-    const int nthr = (int)std::min<long long>(1024, std::max<long long>(32, (ns + 31) / 32 * 32));
-    k_mts_substeps_one_cta<<<1, nthr, in_smem ? need : 0, h->stream>>>(h->g, h->b, h->dp, h->mp, ct, h->dcnt, ns, dtf, p.mts_sub_steps, in_smem);
+    const int nthr = (int)std::min<long long>(small ? 128 : 1024, std::max<long long>(32, (ns + 31) / 32 * 32));
+    if (small) k_mts_substeps_one_cta<128><<<1, nthr, in_smem ? need : 0, h->stream>>>(h->g, h->b, h->dp, h->mp, ct, h->dcnt, ns, dtf, p.mts_sub_steps, in_smem);
+    else k_mts_substeps_one_cta<1024><<<1, nthr, in_smem ? need : 0, h->stream>>>(h->g, h->b, h->dp, h->mp, ct, h->dcnt, ns, dtf, p.mts_sub_steps, in_smem);
     h->launches++;
   } else {
     for (int k = 1; k <= p.mts_sub_steps; k++) {

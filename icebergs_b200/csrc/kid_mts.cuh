@@ -773,7 +773,11 @@ __host__ __device__ inline size_t mts_smem_bytes(const DevBergs& b, long long n,
   return t;
 }
 
-__global__ void __launch_bounds__(1024)
+// MAXT: the CTA size the instance is compiled for.  128 threads leave the compiler 255 registers per thread (168 used); the
+// 1024-thread instance has 64 and spills the fp64-heavy DEM sweeps to local memory (measured: the contact search and
+// every call of a sweep function then run out of L1).
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT)
 k_mts_substeps_one_cta(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b, const __grid_constant__ DevParams p,
                        const __grid_constant__ MtsParams mp, const CellTable ct, DevCounters* __restrict__ cnt,
                        long long n_slots, double dt, int nsub, int in_smem) {
