@@ -375,19 +375,26 @@ __global__ void k_connect_bonds(const __grid_constant__ DevGrid g, const __grid_
     int64_t oid = b.bond_other_id[slot];
     if (oid == 0) continue;
     int i = b.bond_other_ine[slot], j = b.bond_other_jne[slot];
-    int o = find_id_in_cell(g, b, ct, i, j, oid);
-    if (o < 0) {
-      for (int jj = j - 1; jj <= j + 1 && o < 0; jj++)
-        for (int ii = i - 1; ii <= i + 1 && o < 0; ii++)
-          if (ii != i || jj != j) o = find_id_in_cell(g, b, ct, ii, jj, oid);
-    }
-    if (o < 0) {
-      int bi = b.ine[s], bj = b.jne[s];
-      for (int jj = bj - 2; jj <= bj + 2 && o < 0; jj++)
-        for (int ii = bi - 2; ii <= bi + 2 && o < 0; ii++) {
-          o = find_id_in_cell(g, b, ct, ii, jj, oid);
-          if (o >= 0) { b.bond_other_ine[slot] = ii; b.bond_other_jne[slot] = jj; }
-        }
+    const int bi = b.ine[s], bj = b.jne[s];
+    // Bonded elements sit within a cell or two of each other.  A hint further away names the partner's copy on the
+    // other side of the cyclic seam (the berg, or the partner, has just wrapped): with several PEs along x that cell is
+    // off-PE and the reference falls through to the search around the berg, which finds the near (halo) copy; on one
+    // rank the far copy IS in the hinted cell, so the search around the berg goes first there.
+    const bool far = (abs(i - bi) > 2) || (abs(j - bj) > 2);
+    int o = -1;
+    for (int pass = 0; pass < 2 && o < 0; pass++) {
+      if ((pass == 0) == !far) {            // near hint: hinted cell and its ring first; far hint: last
+        o = find_id_in_cell(g, b, ct, i, j, oid);
+        for (int jj = j - 1; jj <= j + 1 && o < 0; jj++)
+          for (int ii = i - 1; ii <= i + 1 && o < 0; ii++)
+            if (ii != i || jj != j) o = find_id_in_cell(g, b, ct, ii, jj, oid);
+      } else {
+        for (int jj = bj - 2; jj <= bj + 2 && o < 0; jj++)
+          for (int ii = bi - 2; ii <= bi + 2 && o < 0; ii++) {
+            o = find_id_in_cell(g, b, ct, ii, jj, oid);
+            if (o >= 0) { b.bond_other_ine[slot] = ii; b.bond_other_jne[slot] = jj; }
+          }
+      }
     }
     b.bond_other_slot[slot] = o;
     if (o < 0 && !(b.flags[s] & BF_HALO)) atomicOr(&cnt->error_flags, 256u);   // 'A non-halo bond is missing!!!' F:5063

