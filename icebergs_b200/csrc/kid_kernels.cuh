@@ -101,29 +101,8 @@ __device__ __forceinline__ int route_berg(const DevGrid& g, const DevParams& p, 
 // per-berg scatter payload collected by the fused kernel
 struct Scatter { long long key; ThermoFlux fx; };
 
-#ifndef KID_SCATTER_MODE
-#define KID_SCATTER_MODE 5
-#endif
-
-// run-sequential variant: every lane parks its value in shared memory, the head lane of each
-// run adds the run up in lane order (deterministic) and issues one atomic
-__device__ __forceinline__ void seg_scatter_smem(double* __restrict__ fld, long long key, double v, const SegInfo& s,
-                                                 double* __restrict__ sh /* 32 doubles of this warp */) {
-  if (!__any_sync(0xffffffffu, v != 0.)) return;
-  int lane = threadIdx.x & 31;
-  sh[lane] = v;
-  __syncwarp();
-  if (s.head && key >= 0) {
-    double t = v;
-    for (int k = lane + 1; k < s.seg_end; k++) t += sh[k];
-    if (t != 0.) atomicAdd(&fld[key], t);
-  }
-  __syncwarp();
-}
-
 template <bool FOOTLOOSE, bool DIAG, bool dense = true>
 __device__ __forceinline__ void scatter_fluxes(const DevGrid& g, const Scatter& sc) {
-#if KID_SCATTER_MODE == 5
   // Two aggregation variants; the tuned (lean) kernel instance exists in both and sort_bergs picks one from the
   // population density (kid_t::scatter_dense), every other instance uses the density-robust first one:
   //  - dense (> ~20 bergs per occupied cell: the weak-scaling tiles): runs of one cell are reduced with segmented
@@ -163,51 +142,6 @@ __device__ __forceinline__ void scatter_fluxes(const DevGrid& g, const Scatter& 
   }
 #define KID_SEG(fld, v) seg_scatter(fld, sc.key, v, si)
   if ((FOOTLOOSE || DIAG) && !dense) si = seg_info(sc.key);
-#elif KID_SCATTER_MODE == 1 || KID_SCATTER_MODE == 3
-  // Adaptive aggregation (mode 3): a warp whose 32 bergs all sit in one cell (dense populations,
-  // the store is cell-sorted) reduces each flux with a butterfly and issues ONE atomic per field;
-  // a warp that straddles cells issues one reduction (RED.ADD.F64) per berg and field, which at
-  // ~13 bergs per cell is cheaper than a segmented shuffle tree (profiles/r1 notes).
-  {
-    long long k0 = __shfl_sync(0xffffffffu, sc.key, 0);
-    bool uniform = (KID_SCATTER_MODE == 3) && __all_sync(0xffffffffu, sc.key == k0);
-    double v[5] = {sc.fx.floating_melt, sc.fx.calving_hflx, sc.fx.berg_melt, sc.fx.bergy_src, sc.fx.bergy_melt};
-    double* f[5] = {g.floating_melt, g.calving_hflx, g.berg_melt, g.bergy_src, g.bergy_melt};
-    if (uniform) {
-      if (k0 >= 0) {
-#pragma unroll
-        for (int q = 0; q < 5; q++) {
-          double t = v[q];
-          if (!__any_sync(0xffffffffu, t != 0.)) continue;
-#pragma unroll
-          for (int d = 16; d > 0; d >>= 1) t += shfl_down_d(t, d);
-          if ((threadIdx.x & 31) == 0 && t != 0.) atomicAdd(&f[q][k0], t);
-        }
-      }
-    } else if (sc.key >= 0) {
-#pragma unroll
-      for (int q = 0; q < 5; q++)
-        if (v[q] != 0.) atomicAdd(&f[q][sc.key], v[q]);
-    }
-  }
-  SegInfo si; si.seg_end = 32; si.rounds = 0; si.head = false;
-#define KID_SEG(fld, v) seg_scatter(fld, sc.key, v, si)
-  if (FOOTLOOSE || DIAG) si = seg_info(sc.key);
-#else
-  SegInfo si = seg_info(sc.key);
-#if KID_SCATTER_MODE == 2
-  __shared__ double sh_all[KID_BLOCK];
-  double* sh = sh_all + (threadIdx.x & ~31);
-#define KID_SEG(fld, v) seg_scatter_smem(fld, sc.key, v, si, sh)
-#else
-#define KID_SEG(fld, v) seg_scatter(fld, sc.key, v, si)
-#endif
-  KID_SEG(g.floating_melt, sc.fx.floating_melt);
-  KID_SEG(g.calving_hflx, sc.fx.calving_hflx);
-  KID_SEG(g.berg_melt, sc.fx.berg_melt);
-  KID_SEG(g.bergy_src, sc.fx.bergy_src);
-  KID_SEG(g.bergy_melt, sc.fx.bergy_melt);
-#endif
   if (FOOTLOOSE) {
     KID_SEG(g.fl_bits_melt, sc.fx.fl_bits_melt);
     KID_SEG(g.fl_bits_src, sc.fx.fl_bits_src);
@@ -401,37 +335,6 @@ __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, c
   }
 }
 
-#ifndef KID_PF_DIST
-#define KID_PF_DIST 0      // measured slower with 740..4096 (profiles/r1_notes.md): off
-#endif
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// The tile a CTA KID_PF_DIST blocks ahead will read is pulled into L2 now (one 128-byte line per
-// thread): its column loads then pay an L2 round trip instead of a DRAM one.  No registers, no
-// extra DRAM traffic (the later loads hit the prefetched lines).
-__device__ __forceinline__ void prefetch_tile_ahead(const DevBergs& b, long long n_slots) {
-#if KID_PF_DIST > 0
-  const long long t0 = ((long long)blockIdx.x + KID_PF_DIST) * KID_BLOCK;
-  if (t0 + KID_BLOCK > n_slots) return;
-  constexpr int cols[17] = {C_LAT, C_UVEL, C_VVEL, C_AXN, C_AYN, C_BXN, C_BYN, C_XI, C_YJ, C_MASS, C_THICKNESS,
-                            C_WIDTH, C_LENGTH, C_LON, C_MASS_SCALING, C_MASS_OF_BITS, C_HEAT_DENSITY};
-  constexpr int lines8 = KID_BLOCK * 8 / 128;        // 128-byte lines of one fp64 column of the tile
-  for (int k = threadIdx.x; k < 17 * lines8 + 2 * (lines8 / 2) + 1; k += KID_BLOCK) {
-    if (k < 17 * lines8) {
-      int c = k / lines8, l = k % lines8;
-      const double* col = b.f64[0];
-#pragma unroll
-      for (int q = 0; q < 17; q++) if (c == q) col = b.f64[cols[q]];
-      prefetch_l2(col + t0 + l * 16);
-    } else {
-      int r = k - 17 * lines8;
-      if (r < lines8 / 2) prefetch_l2(b.ine + t0 + r * 32);
-      else if (r < lines8) prefetch_l2(b.jne + t0 + (r - lines8 / 2) * 32);
-      else prefetch_l2(b.flags + t0);
-    }
-  }
-#endif
-}
 
 template <bool FOOTLOOSE, bool DIAG, bool SPLIT = false, bool LEAN = false, bool DENSE = true>
 __global__ void __launch_bounds__(KID_BLOCK, KID_MINBLOCKS)
@@ -442,7 +345,6 @@ k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
   long long s = s_base + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = s < n_slots;
   const long long sl = in_range ? s : 0;          // out-of-range lanes read slot 0 and are masked by flags
-  if (!SPLIT) prefetch_tile_ahead(b, n_slots);
   // all column loads are issued unconditionally, ahead of the flags test (dead slots are rare and
   // only live until the next sort)
   BergIn in;
