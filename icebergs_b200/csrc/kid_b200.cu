@@ -537,6 +537,8 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   else if (pin->mts && dom->nranks > 1) unsupported = "mts=.true. runs on one rank in this build (transfer_mts_bergs is not implemented)";
   else if (pin->mts && (!pin->interactive_icebergs_on || pin->footloose)) unsupported = "mts=.true. needs interactive_icebergs_on and no footloose";
   else if (pin->mts && pin->halo < 3) unsupported = "mts=.true. needs halo >= 3 (3x3 A-grid stencil of the ocean depth)";
+  else if (pin->mts && pin->skip_first_outer_mts_step) unsupported = "skip_first_outer_mts_step is not implemented";
+  else if (pin->dem && !pin->save_bond_forces) unsupported = "dem needs save_bond_forces=.true. (the reference default, F:53): pair forces are evaluated once and stored on both half-bonds";
   else if (pin->contact_distance > 0. && pin->halo - 1 < 1) unsupported = "contact_distance>0 needs halo >= 2";
   else if (pin->iceberg_bonds_on && !pin->interactive_icebergs_on) unsupported = "iceberg_bonds_on needs interactive_icebergs_on";
   else if (pin->iceberg_bonds_on && (pin->max_bonds < 1 || pin->max_bonds > 12)) unsupported = "max_bonds must be 1..12";

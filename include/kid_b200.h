@@ -139,7 +139,8 @@ typedef struct KidParams {
   int32_t manually_initialize_bonds; /* F:769 */
   int32_t manually_initialize_bonds_from_radii; /* F:725 */
   double length_for_manually_initialize_bonds;  /* F:724 (1000.) */
-  /* MTS / DEM (I:1278-1947, I:6576-7078) */
+  /* MTS / DEM (I:1278-1947, I:6576-7078).  This build: one rank, conglomerates clear of the cyclic seam
+   * (transfer_mts_bergs F:2144 is not built), save_bond_forces = T, skip_first_outer_mts_step = F. */
   int32_t mts;                    /* F:48 */
   int32_t mts_sub_steps;          /* F:780 (-1 = auto F:1296-1301) */
   int32_t force_convergence;      /* F:783 */
