@@ -7,6 +7,8 @@
 2. oracle_step_48x24.npz -- a small seeded case stepped by the CPU oracle (regression fixture for
    the oracle itself: NOT a reference pin; it freezes the restated arithmetic so that a later edit
    of oracle/kid_oracle.c that changes results is noticed).
+3. oracle_mts_20h.npz -- the same for the MTS / DEM restatement: tests/collision_tests with the
+   reference's MTS_KID and iKID namelists (3600 s steps, 60 sub-steps) after 20 h.
 
     python tests/golden/make_golden.py
 """
@@ -48,6 +50,10 @@ def known_answers():
                         {"name": "3a corners x>0", "x0": S / 2, "y0": 0.0, "Q": [2.5 * A / 6, 0.5 * A / 6, 0.5 * A / 6, 2.5 * A / 6]},
                         {"name": "3b corners x<0", "x0": -S / 2, "y0": 0.0, "Q": [0.5 * A / 6, 2.5 * A / 6, 2.5 * A / 6, 0.5 * A / 6]},
                     ]},
+        "dem_beams": {"cite": "tests/dem_ssbeam_test/animate_trajectories.py:143-157, tests/dem_cbeam_test/animate_trajectories.py:149-157",
+                      "simply_supported": {"P": -1.5e5, "E": 1.0e9, "l": 14.0, "I": 0.5 ** 3 / 12.0, "w_mid": -1.5e5 * 14.0 ** 3 / (48.0 * 1.0e9 * 0.5 ** 3 / 12.0)},
+                      "cantilever": {"P": -1.5e10, "E": 1.0e9, "l": 29 * 5000.0, "I": (3 * 5000.0) ** 3 / 12.0,
+                                     "w_tip_linear": -1.5e10 * (29 * 5000.0) ** 3 / (3.0 * 1.0e9 * (3 * 5000.0) ** 3 / 12.0)}},
         "restart_counts": {"cite": "tests/collision_tests/README:16-22, tests/footloose_tests/input.nml:1, tests/dem_ground_frac_test/input.nml:7-10",
                            "KID": 16, "MTS_KID": 16, "iKID": 16, "footloose": 12, "ground_frac": 69},
         "calving_tables": {"cite": "F:787-796",
@@ -69,10 +75,45 @@ def oracle_regression():
     return {k: b[k] for k in names}
 
 
+MTS_NML = dict(mts=1, mts_sub_steps=60, explicit_inner_mts=1, force_convergence=1, convergence_tolerance=1e-8,
+               contact_distance=1.75e3, contact_spring_coef=1.0e-7)
+IKID_NML = dict(MTS_NML, dem=1, poisson=0.3, dem_damping_coef=1.0, dem_spring_coef=4471.94)
+MTS_NAMES = ["id", "lon", "lat", "uvel", "vvel", "axn_fast", "ayn_fast", "ang_vel", "rot", "ine", "jne"]
+
+
+def mts_run(over, nsteps=20, dt=3600.0):
+    import kid_oracle_py as O
+    from icebergs_b200 import api
+    from icebergs_b200 import synthetic as S
+    g = S.CartesianGrid()
+    dom = api.Domain.single(g.gni, g.gnj, halo=3, cyclic_x=True)
+    o = O.Oracle(g.gni, g.gnj, dt, (1, 0.0), params=S.collision_params(api.default_params, **over), domain=dom, **g.init_args())
+    o.set_bergs(**S.collision_bergs())
+    o.set_bonds()
+    f = g.forcing()
+    for k in range(nsteps):
+        c, h = f["calving"].copy(), f["calving_hflx"].copy()
+        o.run((1, k * dt / 86400.0), c, f["uo"], f["vo"], f["ui"], f["vi"], f["tauxa"], f["tauya"], f["ssh"], f["sst"], h,
+              f["cn"], f["hi"], sss=f["sss"])
+    b = o.get_bergs(MTS_NAMES)
+    o.close()
+    order = np.argsort(b["id"], kind="stable")
+    return {k: v[order] for k, v in b.items()}
+
+
+def mts_regression():
+    out = {}
+    for tag, over in (("mts_kid", MTS_NML), ("ikid", IKID_NML)):
+        for k, v in mts_run(over).items():
+            out[f"{tag}.{k}"] = v
+    return out
+
+
 def main():
     with open(os.path.join(HERE, "known_answers.json"), "w") as f:
         json.dump(known_answers(), f, indent=1)
     np.savez_compressed(os.path.join(HERE, "oracle_step_48x24.npz"), **oracle_regression())
+    np.savez_compressed(os.path.join(HERE, "oracle_mts_20h.npz"), **mts_regression())
     print("wrote", os.listdir(HERE))
 
 

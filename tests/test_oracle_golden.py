@@ -4,6 +4,7 @@ bilin corner exactness (icebergs_framework.F90:7313-7316), the 64-bit id round t
 import ctypes as C
 import json
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -123,6 +124,22 @@ def test_oracle_regression_fixture():
             assert np.array_equal(b[k], fx[k]), k
         else:
             assert np.allclose(b[k], fx[k], rtol=1e-13, atol=0), k
+
+
+def test_oracle_mts_regression_fixture():
+    """tests/golden/oracle_mts_20h.npz: freezes the MTS / DEM restatement (not a reference pin; those are the berg
+    counts and the beam tests below)."""
+    sys.path.insert(0, GOLDEN)
+    import make_golden as MG
+    fx = np.load(os.path.join(GOLDEN, "oracle_mts_20h.npz"))
+    for tag, over in (("mts_kid", MG.MTS_NML), ("ikid", MG.IKID_NML)):
+        b = MG.mts_run(over)
+        for k, v in b.items():
+            want = fx[f"{tag}.{k}"]
+            if v.dtype.kind == "i":
+                assert np.array_equal(v, want), (tag, k)
+            else:
+                assert np.allclose(v, want, rtol=1e-11, atol=1e-18), (tag, k)
 
 
 def test_calving_tables_F787():
