@@ -36,6 +36,12 @@ METRIC = "berg_steps_per_sec"
 UNIT = "berg-steps/s"
 
 
+def workload_text(n_per, gni=None, gnj=None):
+    gni, gnj = gni or GNI, gnj or GNJ
+    return (f"free drift + melt, {n_per} seeded bergs per GPU on the {'1/4-degree ' if gni == 1440 else ''}{gni}x{gnj} grid, "
+            f"analytic currents/winds, dt=3600 s, Verlet, bergy bits on")
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -150,8 +156,8 @@ def reference_arm(args, rank):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"free drift + melt, {nb} seeded bergs (bounded sample of the 10M-berg workload), "
-                               f"1/4-degree 1440x720 grid, analytic forcing, dt=3600 s, Verlet",
+        "config": {"workload": workload_text(10_000_000 if args.gpus == 1 else 12_500_000),
+                   "sample": f"each step = one pass over a bounded sample of {nb} of those bergs on the same grid and forcing",
                    "note": "reference = NOAA-GFDL/icebergs is Fortran+FMS (no compiler here): CPU oracle port, OpenMP"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{nb} bergs x {per_step} steps, {wall:.1f} s wall, all {cores} host threads (OpenMP over cell rows)"},
@@ -315,8 +321,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"free drift + melt, {n_per} seeded bergs per GPU on the {'1/4-degree ' if GNI == 1440 else ''}{GNI}x{GNJ} grid, "
-                                   f"analytic currents/winds, dt=3600 s, Verlet, bergy bits on",
+            "config": {"workload": workload_text(n_per),
                        "bergs_total": int(n_total), "layout": [int(dom.layout_x), int(dom.layout_y)],
                        "l2_policy": f"inputs larger than L2 ({B_BERG * n_per / 1e9:.2f} GB of berg state per step vs 126 MB L2)",
                        "timed_region": "kid_step_resident(K): fused dyn+thermo kernel, flux-field zeroing, periodic cell sort"
