@@ -3,12 +3,18 @@
 
 Workload (BASELINE.json configs[1] / BASELINE.md): synthetic free drift + melt, seeded point
 bergs on a 1/4-degree global grid (1440x720) with analytic currents/winds, dt=3600 s, Verlet,
-bergy bits on.  N=1: 10M bergs on one GPU.  N>1: weak scaling, the grid is decomposed like
-mpp_define_layout and every rank owns bergs-per-GPU bergs of its own tile; bergs that leave
-a tile migrate over NCCL.
+bergy bits on.  N=1: 10M bergs on one GPU (plus, in the same line, the 12.5M-berg point that is
+the k=1 base of the weak-scaling series).  N>1: weak scaling, the grid is decomposed like
+mpp_define_layout and every rank owns 12.5M bergs of its own tile; bergs that leave a tile
+migrate over NCCL, and before the timed region a small fast-current case is pushed through the
+same NCCL communicator and compared with the single-rank CPU oracle ("parity_nccl").
+
+`--workload bonded`: BASELINE.json configs[2], a square-packed bonded tabular berg (DEM bonds,
+MTS sub-steps, a68_test physics) -- element-steps/s, its own algorithmic bytes.
 
 One JSON line on rank 0 (contract in the task statement).  `--impl reference` times the CPU
-oracle (the reference is Fortran+FMS and cannot be built in this image) on the host cores.
+oracle (the reference is Fortran+FMS and cannot be built in this image) on the host cores; that
+arm never imports icebergs_b200 nor loads libkid_b200.so.
 """
 from __future__ import annotations
 
@@ -29,11 +35,29 @@ GNI, GNJ = 1440, 720
 DT = 3600.0
 B_BERG = 290.0      # algorithmic bytes per berg-step
 B_CELL = 224.0      # algorithmic bytes per occupied-cell-step
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_step launch on the N=1 workload (10M bergs), from the
-# `ncu --set full` capture summarised in profiles/r1i_kstep_final_summary.txt (1.607 GB read + 1.425 GB written)
-NCU_TRAFFIC_10M = 3.032e9
+B_NEIGHBOUR = 88.0  # per neighbour visited (interacting / bonded populations)
 METRIC = "berg_steps_per_sec"
 UNIT = "berg-steps/s"
+N1_BERGS = 10_000_000          # configs[1]
+WEAK_BERGS = 12_500_000        # per GPU, configs[4] / BASELINE.md weak series
+
+
+def ncu_traffic():
+    """dram bytes of one k_step launch on the N=1 workload from the committed `ncu --set full` summary."""
+    for name in ("r2_kstep_summary.txt", "r1i_kstep_final_summary.txt"):
+        p = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(p):
+            continue
+        rd = wr = None
+        for ln in open(p):
+            f = ln.split()
+            if len(f) == 2 and f[0] == "dram__bytes_read.sum":
+                rd = float(f[1])
+            if len(f) == 2 and f[0] == "dram__bytes_write.sum":
+                wr = float(f[1])
+        if rd is not None and wr is not None:
+            return (rd + wr) * 1e9, f"ncu --set full capture of this workload, profiles/{name}"
+    return None, None
 
 
 def workload_text(n_per, gni=None, gnj=None):
@@ -62,11 +86,12 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.marks = []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -77,24 +102,25 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append((time.perf_counter(), line.strip()))
 
-    def window(self, t0, t1):
-        self.t0, self.t1 = t0, t1
+    def nsamples(self):
+        return len(self.lines)
+
+    def mark(self, t0, t1):
+        """a period under load (settle loop, timed region, e2e loop)"""
+        self.marks.append((t0, t1))
 
     def stop(self):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        t0, t1 = getattr(self, "t0", -1e30), getattr(self, "t1", 1e30)
-        inside = [ln for (t, ln) in self.lines if t0 <= t <= t1 + 0.05]
-        if len(inside) < 3:          # a 50 ms region yields few 20 ms samples: fall back to everything sampled under load
-            inside = [ln for (_, ln) in self.lines]
+        inside = [ln for (t, ln) in self.lines if any(a <= t <= b + 0.06 for a, b in self.marks)]
         for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
@@ -103,11 +129,16 @@ class ClockSampler:
                 sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[3]))
+            except ValueError:
+                pass
             for k, nm in enumerate(names):
                 if f[5 + k].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm),
+                "window": "nvidia-smi -lms 50 over the settle loop, the timed region and the e2e loop (all under load)"}
 
 
 def pinned(a):
@@ -118,121 +149,181 @@ def pinned(a):
     return out, t
 
 
-def cpu_oracle_run(nbergs, steps, nthreads):
-    """The CPU leg: the oracle port of the reference path on the host cores, bounded sample."""
+# ------------------------------------------------------------------ CPU legs (oracle only; no product import)
+def cpu_oracle_run(nbergs, steps, nthreads, warm=1):
+    """The CPU leg: the oracle port of the reference path on the host cores (-O3 -march=native -fopenmp build)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import kid_oracle_py as O
-    from icebergs_b200 import api
-    from icebergs_b200 import synthetic as S
-    O.build()
+    S = O.load_by_path("synthetic", os.path.join("icebergs_b200", "synthetic.py"))
     grid = S.Grid(GNI, GNJ)
-    p = S.workload_params(api.default_params)
-    dom = api.Domain.single(GNI, GNJ, halo=p.halo, cyclic_x=True)
+    p = S.workload_params(O.default_params)
+    dom = O.SingleDomain(GNI, GNJ, halo=p.halo, cyclic_x=True)
     o = O.Oracle(GNI, GNJ, DT, (1, 0.0), params=p, domain=dom, **grid.init_args())
     bergs, _ = grid.seed_bergs(nbergs)
     o.set_bergs(**bergs)
+    del bergs
     f = grid.forcing()
     calving, hflx = f["calving"].copy(), f["calving_hflx"].copy()
     o.run((1, 0.0), calving, f["uo"], f["vo"], f["ui"], f["vi"], f["tauxa"], f["tauya"], f["ssh"], f["sst"], hflx,
-          f["cn"], f["hi"], sss=f["sss"])          # warm-up step (also uploads the forcing)
+          f["cn"], f["hi"], sss=f["sss"])          # first step (also ingests the forcing)
+    if warm > 0:
+        o.step_again(warm, 1, 0.0, nthreads)
     t0 = time.perf_counter()
     o.step_again(steps, 1, 0.0, nthreads)
     wall = time.perf_counter() - t0
-    tm = o.last_timing()
     o.close()
-    return nbergs * steps / wall, wall, tm
+    return nbergs * steps / wall, wall
+
+
+def cpu_build_info():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import kid_oracle_py as O
+    O.use_fast_build()
+    return {"omp_threads": int(O.lib().oracle_omp_max_threads()),
+            "build": "gcc -O3 -march=native -fopenmp (oracle/Makefile `fast`, compiled on this box)"}
 
 
 def reference_arm(args, rank):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    nb = args.cpu_bergs
-    per_step = max(args.steps, 1)
-    t0 = time.perf_counter()
-    # warm-up W and timed K steps of the bounded sample; each "step" = one pass over the sample
-    v, wall, tm = cpu_oracle_run(nb, per_step, cores)
+    info = cpu_build_info()
+    cores = info["omp_threads"]
+    nb = args.cpu_bergs or N1_BERGS
+    n_per = N1_BERGS if args.gpus == 1 else WEAK_BERGS
+    steps = max(args.steps, 1)
+    v, wall = cpu_oracle_run(nb, steps, cores, warm=min(max(args.warmup, 1), 3))
+    same = nb == n_per
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * wall / per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_text(10_000_000 if args.gpus == 1 else 12_500_000),
-                   "sample": f"each step = one pass over a bounded sample of {nb} of those bergs on the same grid and forcing",
-                   "note": "reference = NOAA-GFDL/icebergs is Fortran+FMS (no compiler here): CPU oracle port, OpenMP"},
+        "config": {"workload": workload_text(n_per),
+                   "sample": (f"each step = one pass over {'all' if same else 'a bounded sample of'} {nb} bergs on the same grid and forcing"),
+                   "same_config": same,
+                   "note": "reference = NOAA-GFDL/icebergs is Fortran+FMS (no Fortran compiler here): CPU oracle port, " + info["build"]},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{nb} bergs x {per_step} steps, {wall:.1f} s wall, all {cores} host threads (OpenMP over cell rows)"},
+                         "sample": f"{nb} bergs x {steps} steps, {wall:.1f} s wall, {cores} OpenMP threads (omp_get_max_threads) over cell rows"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def main():
-    global GNI, GNJ
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200")
-    ap.add_argument("--bergs-per-gpu", type=int, default=0, help="0 = 10M at N=1, 12.5M per GPU at N>1")
-    ap.add_argument("--cpu-bergs", type=int, default=1_000_000)
-    ap.add_argument("--cpu-steps", type=int, default=4)
-    ap.add_argument("--gni", type=int, default=GNI, help="diagnostics only: another grid size (the metric is quoted on 1440x720)")
-    ap.add_argument("--gnj", type=int, default=GNJ)
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        reference_arm(args, rank)
-        return
-    if args.warmup < 3:
-        args.warmup = 3
-    GNI, GNJ = args.gni, args.gnj
+# ------------------------------------------------------------------ NCCL data-path parity (N > 1)
+def nccl_parity_check(rank, world, local_rank, comm):
+    """The 96x48 / 12k-berg / fast-current case of tests/test_multirank_gpu.py over the SAME NCCL communicator the
+    timed run uses; rank 0 compares the union of the ranks' bergs with the single-rank CPU oracle (F:2997-3247)."""
+    import torch.distributed as dist
+    from icebergs_b200 import _cdefs as D
+    from icebergs_b200 import api, parallel
+    from icebergs_b200 import synthetic as S
+    gni, gnj, n, dt, steps = 96, 48, 12000, 43200.0, 8
+    over = dict(uo=1.2, vo=0.15, tauxa=15.0)
+    names = ["lon", "lat", "uvel", "vvel", "axn", "ayn", "bxn", "byn", "xi", "yj", "mass", "thickness", "width", "length",
+             "mass_of_bits", "ine", "jne", "id"]
+    g0 = S.Grid(gni, gnj)
+    cols, counter = g0.seed_bergs(n)
+    mk_params = lambda dflt: S.workload_params(dflt, halo=4, old_bug_bilin=0)
+    dom = api.Domain.decomposed(gni, gnj, rank, world, halo=4, device=local_rank, comm=comm, comm_kind=D.KID_COMM_NCCL)
+    grid = S.Grid(gni, gnj, dom.isc, dom.iec, dom.jsc, dom.jec)
+    b = api.icebergs_init(gni, gnj, dt, (1, 0.0), params=mk_params(api.default_params), domain=dom, capacity=4 * n,
+                          **grid.init_args())
+    cnt = np.zeros((dom.njd, dom.nid), dtype=np.int32)
+    cnt[4:4 + dom.njc, 4:4 + dom.nic] = counter[dom.jsc - 1:dom.jec, dom.isc - 1:dom.iec]
+    b.set_calving_state(iceberg_counter_grd=cnt)
+    mine = (cols["ine"] >= dom.isc) & (cols["ine"] <= dom.iec) & (cols["jne"] >= dom.jsc) & (cols["jne"] <= dom.jec)
+    b.set_bergs(**{k: np.ascontiguousarray(v[mine]) for k, v in cols.items()})
+    f = grid.forcing()
+    for k, v in over.items():
+        f[k] = np.full_like(f[k], v)
+    c, h = f["calving"].copy(), f["calving_hflx"].copy()
+    api.icebergs_run(b, (1, 0.0), c, f["uo"], f["vo"], f["ui"], f["vi"], f["tauxa"], f["tauya"], f["ssh"], f["sst"], h,
+                     f["cn"], f["hi"], sss=f["sss"])
+    sent = b.counters()["n_sent"]
+    b.step_resident(steps - 1, 1, 0.0)          # incl. the migration overlapped with the next step's kernel
+    sent_total = b.counters()["n_sent"]
+    got = b.get_bergs(names)
+    api.icebergs_end(b)
+    parts = [None] * world
+    dist.all_gather_object(parts, (got, int(sent_total), int(sent)))
+    if rank != 0:
+        return None
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import kid_oracle_py as O
+    got = {k: np.concatenate([p[0][k] for p in parts]) for k in names}
+    d0 = O.SingleDomain(gni, gnj, halo=4, cyclic_x=True)
+    o = O.Oracle(gni, gnj, dt, (1, 0.0), params=mk_params(O.default_params), domain=d0, **g0.init_args())
+    c0 = np.zeros((d0.njd, d0.nid), dtype=np.int32)
+    c0[4:4 + gnj, 4:4 + gni] = counter
+    o.set_calving_state(iceberg_counter_grd=c0)
+    o.set_bergs(**cols)
+    f0 = g0.forcing()
+    for k, v in over.items():
+        f0[k] = np.full_like(f0[k], v)
+    c, h = f0["calving"].copy(), f0["calving_hflx"].copy()
+    o.run((1, 0.0), c, f0["uo"], f0["vo"], f0["ui"], f0["vi"], f0["tauxa"], f0["tauya"], f0["ssh"], f0["sst"], h, f0["cn"],
+          f0["hi"], sss=f0["sss"])
+    o.step_again(steps - 1, 1, 0.0, 1)
+    want = o.get_bergs(names)
+    o.close()
+    res = {"case": f"{gni}x{gnj}, {n} bergs, dt={dt:.0f} s, {steps} steps, uo=1.2 m/s: union of {world} NCCL ranks vs the single-rank CPU oracle",
+           "migrated": int(sum(p[1] for p in parts)), "count_gpu": int(len(got["id"])), "count_oracle": int(len(want["id"]))}
+    ok = len(got["id"]) == len(want["id"])
+    worst = 0.0
+    if ok:
+        ga, wa = np.argsort(got["id"], kind="stable"), np.argsort(want["id"], kind="stable")
+        for k in ("id", "ine", "jne"):
+            ok = ok and bool(np.array_equal(got[k][ga], want[k][wa]))
+        for k in names:
+            if k in ("id", "ine", "jne"):
+                continue
+            a, w = got[k][ga], want[k][wa]
+            scale = np.maximum(np.maximum(np.abs(a), np.abs(w)), 1e-300)
+            e = np.where(a == w, 0.0, np.abs(a - w) / scale)
+            floor = 1e-8 if k in ("xi", "yj") else 1e-13 * max(float(np.max(np.abs(w))), 1e-300)
+            e = np.where(np.abs(a - w) <= floor, 0.0, e)
+            worst = max(worst, float(e.max()) if len(e) else 0.0)
+        ok = ok and worst <= 1e-8
+    res.update(ok=bool(ok), worst_rel=worst, rtol=1e-8, integers="id, ine, jne bit-exact" if ok else "MISMATCH")
+    return res
 
+
+# ------------------------------------------------------------------ the GPU arm
+def run_drift(args, rank, world, local_rank, dom, n_per, clocks, do_e2e, seed_stream=None):
+    """One population on this rank's tile: resident throughput, (optionally) end-to-end, per-phase times."""
     import torch
     import torch.distributed as dist
     from icebergs_b200 import api
     from icebergs_b200 import synthetic as S
-    from icebergs_b200 import _cdefs as D
-
-    torch.cuda.set_device(local_rank)
     multi = world > 1
-    if multi:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    n_per = args.bergs_per_gpu or (10_000_000 if world == 1 else 12_500_000)
     p = S.workload_params(api.default_params)
-    if multi:
-        from icebergs_b200 import parallel
-        dom = parallel.make_domain(GNI, GNJ, rank, world, halo=p.halo, device=local_rank)
-    else:
-        dom = api.Domain.single(GNI, GNJ, halo=p.halo, cyclic_x=True, device=local_rank)
     grid = S.Grid(GNI, GNJ, dom.isc, dom.iec, dom.jsc, dom.jec)
     bergs = api.icebergs_init(GNI, GNJ, DT, (1, 0.0), params=p, domain=dom, capacity=int(n_per * 1.25) + 4096,
                               **grid.init_args())
-    cols, counter = grid.seed_bergs(n_per, stream=rank)
-    cell = (cols["jne"].astype(np.int64) - 1) * GNI + (cols["ine"].astype(np.int64) - 1)
-    occupied = int(np.unique(cell).size)
-    bergs.set_bergs(**cols)
-    del cols
+    # seeded in chunks: bounded host memory at 1e8 bergs
+    occupied_cells = np.zeros(GNI * GNJ, dtype=bool)
+    chunk, done, counter = 12_500_000, 0, None
+    while done < n_per:
+        m = min(chunk, n_per - done)
+        cols, counter = grid.seed_bergs(m, stream=rank if seed_stream is None else seed_stream, start=done, counter0=counter)
+        occupied_cells[(cols["jne"].astype(np.int64) - 1) * GNI + (cols["ine"].astype(np.int64) - 1)] = True
+        bergs.set_bergs(**cols)
+        del cols
+        done += m
+    occupied = int(occupied_cells.sum())
     f = grid.forcing()
-    keep = []
-    fp = {}
+    keep, fp = [], {}
     for k, v in f.items():
         fp[k], t = pinned(v)
         keep.append(t)
     calving, hflx = fp["calving"], fp["calving_hflx"]
-
     # calving / calving_hflx are intent(inout): the caller hands in this step's calving (none in this workload) and
     # gets the unused calving and the heat flux back.  As a coupler would, the bench double-buffers the pair: the
     # next step's arrays are prepared (zeroed) on a helper thread while the call on the current pair is in flight.
     from concurrent.futures import ThreadPoolExecutor
     pair = [(calving, hflx)]
-    for _ in range(1):
-        a, ta = pinned(np.zeros_like(calving)); b_, tb = pinned(np.zeros_like(hflx))
-        keep += [ta, tb]
-        pair.append((a, b_))
+    a, ta = pinned(np.zeros_like(calving)); b_, tb = pinned(np.zeros_like(hflx))
+    keep += [ta, tb]
+    pair.append((a, b_))
     pool = ThreadPoolExecutor(max_workers=1)
     state = {"cur": 0, "fut": None}
 
@@ -256,27 +347,45 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    interval = int(os.environ.get("KID_SORT_INTERVAL", "32"))
+
+    def place_sorts(k):
+        # the periodic cell sort is part of the step: every window of k steps is charged ceil(k/interval) sorts,
+        # whatever k is (a 20-step window gets one, a 50-step window two), the last one on the window's last step
+        bergs.set_sort_phase(interval, interval - 1 - ((k - 1) % interval))
+
     # ---- HBM-resident throughput: forcing on the device, K steps
     run_once()                                  # uploads forcing, first step
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()                          # sampled from the warm-up on: the timed region itself lasts ~50 ms
-    bergs.step_resident(args.warmup, 1, 0.0)    # W untimed warm-up steps
+    if clocks is not None:
+        # clocks are sampled under load: keep stepping until nvidia-smi has delivered a few samples (it needs
+        # ~0.5 s to start); these are extra untimed warm-up steps
+        t_a = time.perf_counter()
+        while clocks.nsamples() < 4 and time.perf_counter() - t_a < 3.0:
+            bergs.step_resident(8, 1, 0.0)
+        while time.perf_counter() - t_a < 0.5:
+            bergs.step_resident(8, 1, 0.0)
+        clocks.mark(t_a, time.perf_counter())
+    place_sorts(args.warmup)
+    bergs.step_resident(args.warmup, 1, 0.0)    # W untimed warm-up steps (ends on a sort)
+    place_sorts(args.steps)
     barrier()
-    l0 = bergs.kernel_launches()
+    l0, s0 = bergs.kernel_launches(), bergs.sorts_done()
     t0 = time.perf_counter()
     bergs.step_resident(args.steps, 1, 0.0)
     barrier()
     wall = time.perf_counter() - t0
-    clocks.window(t0, t0 + wall)
-    l1 = bergs.kernel_launches()
+    if clocks is not None:
+        clocks.mark(t0, t0 + wall)
+    l1, s1 = bergs.kernel_launches(), bergs.sorts_done()
     tm = bergs.last_timing()
     dev_ms = tm["total"]
-    kern_ms = tm["momentum+thermodyn"] / max(tm["_"], 1.0)
-    comm_ms = tm["communication"] / max(tm["_"], 1.0)
-    sort_ms = tm["sort"] / max(tm["_"], 1.0)
+    nst = max(tm["_"], 1.0)
+    kern_ms, comm_ms, sort_ms = tm["momentum+thermodyn"] / nst, tm["communication"] / nst, tm["sort"] / nst
+    sorts = int(s1 - s0)
     n_alive = bergs.count_bergs()
-    t_all = torch.tensor([dev_ms, wall * 1e3, float(n_alive), kern_ms, float(occupied), comm_ms, sort_ms], dtype=torch.float64, device="cuda")
+    t_all = torch.tensor([dev_ms, wall * 1e3, float(n_alive), kern_ms, float(occupied), comm_ms, sort_ms, float(sorts)],
+                         dtype=torch.float64, device="cuda")
+    per_rank = None
     if multi:
         tmax = t_all.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t_all.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
@@ -285,71 +394,167 @@ def main():
         gathered = [torch.zeros_like(t_all) for _ in range(world)]
         dist.all_gather(gathered, t_all)
         per_rank = {"kernel_ms": [round(float(g[3]), 4) for g in gathered], "migration_ms": [round(float(g[5]), 4) for g in gathered],
-                    "bergs": [int(g[2]) for g in gathered], "occupied_cells": [int(g[4]) for g in gathered]}
+                    "bergs": [int(g[2]) for g in gathered], "occupied_cells": [int(g[4]) for g in gathered],
+                    "sorts_in_window": [int(g[7]) for g in gathered]}
     else:
-        per_rank = None
         wall_ms, n_total = wall * 1e3, float(n_alive)
-    ms_per_step = dev_ms / args.steps
-    value = n_total * args.steps / (dev_ms * 1e-3)
+    out = {"dev_ms": dev_ms, "wall_ms": wall_ms, "n_total": n_total, "kern_ms": kern_ms, "comm_ms": comm_ms, "sort_ms": sort_ms,
+           "sorts": sorts, "sort_ms_per_call": (tm["sort"] / sorts) if sorts else None, "occupied": occupied,
+           "launches": int(l1 - l0), "per_rank": per_rank, "interval": interval,
+           "value": n_total * args.steps / (dev_ms * 1e-3), "ms_per_step": dev_ms / args.steps}
 
     # ---- end to end through icebergs_run: host buffers, H2D of the forcing + D2H of the returns
-    e2e = None
-    if not args.no_e2e:
+    if do_e2e:
         for _ in range(3):
             run_once()
+        place_sorts(args.steps)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             run_once()
         barrier()
         e2e_wall = time.perf_counter() - t0
+        if clocks is not None:
+            clocks.mark(t0, t0 + e2e_wall)
         tw = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
         if multi:
             dist.all_reduce(tw, op=dist.ReduceOp.MAX)
         h2d = sum(fp[k].nbytes for k in ("calving", "uo", "vo", "ui", "vi", "tauxa", "tauya", "ssh", "sst",
                                           "calving_hflx", "cn", "hi", "sss"))
         d2h = calving.nbytes + hflx.nbytes
-        e2e = {"value": n_total * args.steps / float(tw[0]), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(tw[0]) / args.steps,
-               "note": "icebergs_run through the C ABI with pinned host arrays: 13 forcing fields H2D and the two inout "
-                       "fields D2H every step; the caller double-buffers the inout pair (the next pair is zeroed on a "
-                       "helper thread while the call runs)"}
-    clk = clocks.stop() if rank == 0 else None
+        out["e2e"] = {"value": n_total * args.steps / float(tw[0]), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                      "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(tw[0]) / args.steps,
+                      "note": "icebergs_run through the C ABI with pinned host arrays: 13 forcing fields H2D and the two inout "
+                              "fields D2H every step (host-side wall clock, max over ranks); the caller double-buffers the "
+                              "inout pair (the next pair is zeroed on a helper thread while the call runs)"}
+    api.icebergs_end(bergs)
+    pool.shutdown()
+    return out
+
+
+def main():
+    global GNI, GNJ
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="drift", choices=["drift", "bonded"])
+    ap.add_argument("--bergs-per-gpu", type=int, default=0, help="0 = 10M at N=1, 12.5M per GPU at N>1")
+    ap.add_argument("--cpu-bergs", type=int, default=0, help="reference arm / cpu_baseline population (0 = the workload's own)")
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--gni", type=int, default=GNI, help="diagnostics only: another grid size (the metric is quoted on 1440x720)")
+    ap.add_argument("--gnj", type=int, default=GNJ)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-weak-base", action="store_true", help="N=1: skip the extra 12.5M-berg point (k=1 of the weak series)")
+    ap.add_argument("--no-parity", action="store_true", help="N>1: skip the NCCL data-path parity check")
+    ap.add_argument("--elements", type=int, default=0, help="--workload bonded: elements of the tabular berg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if args.workload == "bonded":
+            import bench_bonded
+            bench_bonded.reference_arm(args, rank)
+        else:
+            reference_arm(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    GNI, GNJ = args.gni, args.gnj
+    if args.workload == "bonded":
+        import bench_bonded
+        bench_bonded.main(args, rank, world, local_rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from icebergs_b200 import api
+
+    torch.cuda.set_device(local_rank)
+    multi = world > 1
+    if multi:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_per = args.bergs_per_gpu or (N1_BERGS if world == 1 else WEAK_BERGS)
+    halo = 4
+    parity = None
+    if multi:
+        from icebergs_b200 import parallel
+        dom = parallel.make_domain(GNI, GNJ, rank, world, halo=halo, device=local_rank)
+        if not args.no_parity:
+            parity = nccl_parity_check(rank, world, local_rank, dom.c.nccl_comm)
+            flag = torch.tensor([0 if (parity is None or parity["ok"]) else 1], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            if int(flag[0]):
+                if rank == 0:
+                    print(json.dumps({"error": "NCCL data-path parity check failed", "parity_nccl": parity}), flush=True)
+                dist.destroy_process_group()
+                sys.exit(3)
+    else:
+        dom = api.Domain.single(GNI, GNJ, halo=halo, cyclic_x=True, device=local_rank)
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    if clocks is not None:
+        clocks.start()
+    r = run_drift(args, rank, world, local_rank, dom, n_per, clocks, not args.no_e2e)
+    weak_base = None
+    if world == 1 and not args.no_weak_base and n_per == N1_BERGS and GNI == 1440:
+        w = run_drift(args, rank, world, local_rank, dom, WEAK_BERGS, None, False)
+        weak_base = {"bergs": WEAK_BERGS, "value": w["value"], "ms_per_step": w["ms_per_step"], "kernel_ms": w["kern_ms"],
+                     "sorts_in_window": w["sorts"], "sort_ms_per_call": w["sort_ms_per_call"],
+                     "note": "k=1 point of the weak-scaling series (BASELINE.md: 1.25e7 bergs per GPU at k=1,2,4,8), same run, same "
+                             "grid; the N>1 lines of this bench run this population per GPU"}
+    clk = clocks.stop() if clocks is not None else None
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        alg_bytes = B_BERG * n_per + B_CELL * occupied
-        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        alg_bytes = B_BERG * n_per + B_CELL * r["occupied"]
+        achieved = alg_bytes / (r["kern_ms"] * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic()
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_text(n_per),
-                       "bergs_total": int(n_total), "layout": [int(dom.layout_x), int(dom.layout_y)],
+                       "bergs_total": int(r["n_total"]), "layout": [int(dom.layout_x), int(dom.layout_y)],
                        "l2_policy": f"inputs larger than L2 ({B_BERG * n_per / 1e9:.2f} GB of berg state per step vs 126 MB L2)",
-                       "timed_region": "kid_step_resident(K): fused dyn+thermo kernel, flux-field zeroing, periodic cell sort"
+                       "timed_region": "kid_step_resident(K): fused dyn+thermo kernel, flux-field zeroing, the periodic cell sort "
+                                       "(placed so that every window holds ceil(K/sort_interval) sorts)"
                                        + (", NCCL migration" if multi else ""),
-                       "wall_ms_per_step": wall_ms / args.steps, "migration_ms_per_step": comm_ms, "sort_ms_per_step": sort_ms,
+                       "sorts_in_window": r["sorts"], "sort_ms_per_call": r["sort_ms_per_call"],
+                       "wall_ms_per_step": r["wall_ms"] / args.steps, "migration_ms_per_step": r["comm_ms"],
+                       "sort_ms_per_step": r["sort_ms"],
                        "physics": "namelist defaults except Verlet stepping, bergy_bit_erosion_fraction=0.1, tau_is_velocity, "
                                   "add_weight_to_ocean off (the metric is dyn+thermo; mass spreading is SURVEY 8f1)",
-                       "sort_interval": int(os.environ.get("KID_SORT_INTERVAL", "32")), "per_rank": per_rank},
+                       "sort_interval": r["interval"], "per_rank": r["per_rank"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_10M if (world == 1 and n_per == 10_000_000 and GNI == 1440) else None,
-                         "traffic_source": "ncu --set full capture of this workload, profiles/r1i_kstep_final_summary.txt",
+                         "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "traffic": traffic if (world == 1 and n_per == N1_BERGS and GNI == 1440) else None,
+                         "traffic_source": traffic_src,
                          "peak_source": peak_src, "kernel": "k_step (fused evolve+thermodynamics)",
-                         "alg_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms},
-            "gpu_launches": int(l1 - l0), "clocks": clk,
+                         "alg_bytes_per_launch": alg_bytes, "kernel_ms": r["kern_ms"]},
+            "gpu_launches": r["launches"], "clocks": clk,
         }
-        if e2e:
-            line["e2e"] = e2e
+        if "e2e" in r:
+            line["e2e"] = r["e2e"]
+        if weak_base:
+            line["weak_base"] = weak_base
+        if parity is not None:
+            line["parity_nccl"] = parity
         if world == 1 and not args.no_cpu:
-            cores = os.cpu_count() or 1
-            v, cw, ctm = cpu_oracle_run(args.cpu_bergs, args.cpu_steps, cores)
+            info = cpu_build_info()
+            cores = info["omp_threads"]
+            nb = args.cpu_bergs or n_per
+            v, cw = cpu_oracle_run(nb, args.cpu_steps, cores)
+            nb1 = min(nb, 1_000_000)
+            v1, cw1 = cpu_oracle_run(nb1, 2, 1, warm=0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{args.cpu_bergs} bergs x {args.cpu_steps} steps of the same workload, "
-                                              f"{cw:.1f} s wall, OpenMP over cell rows on all {cores} host threads"}
+                                    "single_thread": {"value": v1, "cores": 1, "sample": f"{nb1} bergs x 2 steps, {cw1:.1f} s wall"},
+                                    "build": info["build"],
+                                    "sample": f"{nb} bergs x {args.cpu_steps} steps of the same workload (after 2 untimed steps), "
+                                              f"{cw:.1f} s wall, OpenMP over cell rows on {cores} threads (omp_get_max_threads)"}
         print(json.dumps(line), flush=True)
-    api.icebergs_end(bergs)
     if multi:
         dist.destroy_process_group()
 

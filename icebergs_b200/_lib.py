@@ -11,7 +11,8 @@ import os
 from . import _cdefs as D
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libkid_b200.so")
+# KID_B200_LIB: another build of the same library (kernel-tuning experiments: scratch/ variants); default in-tree
+LIB_PATH = os.environ.get("KID_B200_LIB") or os.path.join(_HERE, "lib", "libkid_b200.so")
 
 # every symbol include/kid_b200.h declares
 EXPORTS = [
@@ -21,7 +22,8 @@ EXPORTS = [
     "kid_kernel_launches", "kid_get_counters", "kid_get_grid_field", "kid_stock", "kid_incr_mass",
     "kid_sort_bergs", "kid_synchronize", "kid_end", "kid_last_error", "kid_version",
     "kid_nccl_unique_id", "kid_nccl_init", "kid_nccl_destroy", "kid_pack_width",
-    "kid_local_comm_create", "kid_local_comm_destroy", "kid_owner_rank",
+    "kid_local_comm_create", "kid_local_comm_destroy", "kid_owner_rank", "kid_set_sort_phase", "kid_sorts_done",
+    "kid_unit_hexagon_into_quadrants", "kid_unit_point_in_triangle",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -62,6 +64,11 @@ def load() -> C.CDLL:
     lib.kid_stock.argtypes = [_vp, C.c_int32, _dp]
     lib.kid_incr_mass.argtypes = [_vp, _vp]
     lib.kid_sort_bergs.argtypes = [_vp]
+    lib.kid_set_sort_phase.argtypes = [_vp, C.c_int32, C.c_int32]
+    lib.kid_sorts_done.argtypes = [_vp]
+    lib.kid_sorts_done.restype = C.c_int64
+    lib.kid_unit_hexagon_into_quadrants.argtypes = [C.c_int32] + [C.c_double] * 4 + [_dp]
+    lib.kid_unit_point_in_triangle.argtypes = [C.c_int32, _dp, _ip, _dp]
     lib.kid_synchronize.argtypes = [_vp]
     lib.kid_end.argtypes = [C.POINTER(_vp)]
     lib.kid_last_error.argtypes = [_vp]

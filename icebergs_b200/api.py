@@ -265,6 +265,12 @@ class Icebergs:
     def sort(self):
         self._check(lib().kid_sort_bergs(self.handle))
 
+    def set_sort_phase(self, interval=0, steps_since_sort=-1):
+        self._check(lib().kid_set_sort_phase(self.handle, int(interval), int(steps_since_sort)))
+
+    def sorts_done(self) -> int:
+        return lib().kid_sorts_done(self.handle)
+
     def last_timing(self):
         ms = (C.c_double * 8)()
         self._check(lib().kid_last_timing(self.handle, ms))

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "kid_kernels.cuh"
+#include "kid_sort.cuh"
 #include "kid_comm.cuh"
 #include "kid_interact.cuh"
 #include "kid_spread.cuh"
@@ -42,12 +43,30 @@ struct kid_handle {
   long long n2 = 0;
   long long capacity = 0;
   long long n_slots = 0;            // host mirror of the append cursor
-  void *spare8 = nullptr, *spare4 = nullptr, *spare1 = nullptr;
+  // cell-binned sort (kid_sort.cuh): radix key/payload buffers, tile histograms, rotating spare columns
+  int32_t *sort_keys[2] = {nullptr, nullptr}, *sort_vals[2] = {nullptr, nullptr};
+  int32_t *radix_hist = nullptr, *radix_sums = nullptr;
+  long long radix_sums_cap = 0;
+  int32_t* h_totals = nullptr;            // pinned: [0] bergs kept by the sort [1] occupied cells
+  unsigned long long* h_nslots = nullptr; // pinned
+  double* spare_f64[KID_GATHER_NC] = {nullptr};
+  int64_t* spare_id = nullptr;
+  int32_t* spare_i32[3] = {nullptr, nullptr, nullptr};
+  uint8_t* spare_u8[2] = {nullptr, nullptr};
+  int64_t* alt_bond_other_id = nullptr;
+  int32_t *alt_bond_other_ine = nullptr, *alt_bond_other_jne = nullptr, *alt_bond_broken = nullptr;
+  double* alt_bond_length = nullptr;
+  double* alt_bond_dem[BD_N] = {nullptr};
+  long long sorts_done = 0;
+  uint32_t* slow_slots = nullptr;         // k_step_fast's deferred bergs (kid_kernels.cuh)
+  unsigned long long* slow_count = nullptr;
+  int fast_path = 1;                      // KID_NO_FAST=1 (diagnostics): the one-kernel path only
+  int scatter_dense_forced = -1;          // KID_SCATTER_DENSE (diagnostics): force a flux-scatter variant
   DevCounters* dcnt = nullptr;
   DevCounters* hcnt = nullptr;      // pinned
   unsigned long long* dflags = nullptr;   // [0] enc(max sst*msk) [1] any calving != 0 [2] alive count
   unsigned long long* hflags = nullptr;   // pinned
-  int32_t *cell_count = nullptr, *cell_start = nullptr, *cell_fill = nullptr, *perm = nullptr;
+  int32_t *cell_count = nullptr, *cell_start = nullptr, *perm = nullptr;   // perm: the sort's result payload (alias)
   int32_t *scan_sums = nullptr, *scan_total = nullptr;
   std::vector<double*> field_allocs;
   double* in_stage[13] = {nullptr};  // device staging of the icebergs_run inputs
@@ -77,6 +96,7 @@ struct kid_handle {
   long long dirty_appended = 0;
   // ---- multi-rank (send_bergs_to_other_pes F:2997, mpp_update_domains)
   DevLayout layout;
+  int32_t* layout_table = nullptr;     // device copy of the (px,py) -> rank table
   int comm_kind = 0;
   void* comm = nullptr;                // ncclComm_t or LocalGroup*
   int nbr[9];                          // rank in direction dir = (dx+1)+3*(dy+1); -1 = none
@@ -95,7 +115,6 @@ struct kid_handle {
   int32_t *d_gcounts = nullptr, *d_goffsets = nullptr, *d_gcursor = nullptr;   // [9]
   int tables_valid = 0, bond_lengths_set = 0, conglom_set = 0;
   int* d_changed = nullptr;                // cell_start/cell_count describe the current slot order
-  void* spare_b8 = nullptr;            // spare column for the bond arrays (8 B entries)
   SpreadFields sf;                     // mass / area / momentum on the ocean grid
   SpreadParams sp;
   double* out_stage3[3] = {nullptr, nullptr, nullptr};
@@ -487,6 +506,7 @@ static void fill_layout(DevLayout& L, const KidDomain* d) {
   memset(&L, 0, sizeof(L));
   L.lx = std::max(1, d->layout_x); L.ly = std::max(1, d->layout_y);
   L.gni = d->gni; L.gnj = d->gnj; L.cyclic_x = d->cyclic_x; L.cyclic_y = d->cyclic_y; L.rank = d->rank; L.nranks = d->nranks;
+  L.pe_at = nullptr;
   for (int k = 0; k <= L.lx && k <= KID_MAX_DIV; k++) L.xs[k] = k * (d->gni / L.lx) + std::min(k, d->gni % L.lx) + 1;
   for (int k = 0; k <= L.ly && k <= KID_MAX_DIV; k++) L.ys[k] = k * (d->gnj / L.ly) + std::min(k, d->gnj % L.ly) + 1;
 }
@@ -553,8 +573,6 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   if (dom->nranks > 1) {
     if (dom->comm_kind != KID_COMM_NCCL && dom->comm_kind != KID_COMM_LOCAL) { g_init_error = "kid_init: unknown KidDomain.comm_kind"; return KID_ERR_ARG; }
     if (dom->comm_kind == KID_COMM_NCCL && !nccl().ok()) { g_init_error = "kid_init: libnccl.so.2 could not be loaded"; return KID_ERR_COMM; }
-    if (dom->layout_x < 1 || dom->layout_y < 1 || dom->layout_x * dom->layout_y != dom->nranks || dom->layout_x > KID_MAX_DIV ||
-        dom->layout_y > KID_MAX_DIV) { g_init_error = "kid_init: bad layout"; return KID_ERR_ARG; }
     if (dom->iec - dom->isc + 1 < pin->halo || dom->jec - dom->jsc + 1 < pin->halo) { g_init_error = "kid_init: a tile must be at least halo cells wide"; return KID_ERR_ARG; }
   }
 
@@ -578,31 +596,66 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   if (h->n2 * KID_NCLASSES >= 2000000000LL) return fail(h, KID_ERR_ARG, "kid_init: the data domain must have fewer than 2e8 cells per rank");
   const long long n2 = h->n2;
   const int nid = h->nid, nic = h->nic;
-  // ---- rank layout (mpp_define_layout / mpp_compute_extent as kid_define_domain restates them)
+  // ---- rank layout: from the compute domains and neighbour PEs the ranks were actually given (mpp_define_domains,
+  // F:915-930: any mpp_compute_extent split of the axes, masked-out PEs), all-gathered once here
   {
     DevLayout& L = h->layout;
     fill_layout(L, d);
-    int px = d->rank % L.lx, py = d->rank / L.lx;
-    if (d->nranks > 1 && (L.xs[px] != d->isc || L.xs[px + 1] - 1 != d->iec || L.ys[py] != d->jsc || L.ys[py + 1] - 1 != d->jec))
-      return fail(h, KID_ERR_ARG, "kid_init: compute domain does not match the layout (use kid_define_domain)");
-    for (int dy = -1; dy <= 1; dy++)
-      for (int dx = -1; dx <= 1; dx++) {
-        int qx = px + dx, qy = py + dy, r = -1;
-        bool ok = true;
-        if (qx < 0 || qx >= L.lx) { if (d->cyclic_x) qx = (qx + L.lx) % L.lx; else ok = false; }
-        if (qy < 0 || qy >= L.ly) { if (d->cyclic_y) qy = (qy + L.ly) % L.ly; else ok = false; }
-        if (ok) r = qx + L.lx * qy;
-        h->nbr[dir_of(dx, dy)] = r;
-      }
-    h->nbr[4] = -1;
+    for (int k = 0; k < 9; k++) h->nbr[k] = -1;
+    h->nbr[dir_of(1, 0)] = d->pe_E; h->nbr[dir_of(-1, 0)] = d->pe_W;
+    h->nbr[dir_of(0, 1)] = d->pe_N; h->nbr[dir_of(0, -1)] = d->pe_S;
     h->comm_kind = d->comm_kind; h->comm = d->nccl_comm;
+    {
+      const int nr = d->nranks, w = std::max(nr, 9);
+      CK(cudaMallocHost(&h->h_all_counts, sizeof(int32_t) * nr * w));
+      if (nr > 1) CK(cudaMalloc(&h->d_all_counts, sizeof(int32_t) * nr * w));
+    }
     if (d->nranks > 1) {
+      const int nr = d->nranks;
+      int32_t mine[8] = {d->isc, d->iec, d->jsc, d->jec, d->pe_E, d->pe_W, d->pe_N, d->pe_S};
+      int32_t* dmine = nullptr;
+      CK(cudaMalloc(&dmine, sizeof(mine)));
+      CK(cudaMemcpyAsync(dmine, mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+      std::vector<int32_t> all((size_t)nr * 8);
+      int rc = comm_allgather_counts(h, dmine, h->h_all_counts, 8);
+      cudaFree(dmine);
+      if (rc) return rc;
+      for (size_t k = 0; k < all.size(); k++) all[k] = h->h_all_counts[k];
+      std::vector<int32_t> xs, ys;
+      for (int r = 0; r < nr; r++) { xs.push_back(all[r * 8 + 0]); ys.push_back(all[r * 8 + 2]); }
+      std::sort(xs.begin(), xs.end()); xs.erase(std::unique(xs.begin(), xs.end()), xs.end());
+      std::sort(ys.begin(), ys.end()); ys.erase(std::unique(ys.begin(), ys.end()), ys.end());
+      if ((int)xs.size() > KID_MAX_DIV || (int)ys.size() > KID_MAX_DIV) return fail(h, KID_ERR_ARG, "kid_init: layout wider than KID_MAX_DIV tiles along an axis");
+      L.lx = (int)xs.size(); L.ly = (int)ys.size();
+      for (int k = 0; k < L.lx; k++) L.xs[k] = xs[k];
+      for (int k = 0; k < L.ly; k++) L.ys[k] = ys[k];
+      L.xs[L.lx] = d->gni + 1; L.ys[L.ly] = d->gnj + 1;
+      if (xs[0] != 1 || ys[0] != 1) return fail(h, KID_ERR_ARG, "kid_init: no tile starts at cell 1 (the ranks' compute domains do not cover the grid)");
+      std::vector<int32_t> table((size_t)L.lx * L.ly, -1);        // masked-out PEs stay -1 (NULL_PE)
+      for (int r = 0; r < nr; r++) {
+        int px = (int)(std::lower_bound(xs.begin(), xs.end(), all[r * 8 + 0]) - xs.begin());
+        int py = (int)(std::lower_bound(ys.begin(), ys.end(), all[r * 8 + 2]) - ys.begin());
+        if (all[r * 8 + 1] != L.xs[px + 1] - 1 || all[r * 8 + 3] != L.ys[py + 1] - 1 || table[px + L.lx * py] != -1)
+          return fail(h, KID_ERR_ARG, "kid_init: the ranks' compute domains are not a tensor-product tiling of the grid");
+        table[px + L.lx * py] = r;
+      }
+      int32_t* dt = nullptr;
+      CK(cudaMalloc(&dt, sizeof(int32_t) * table.size()));
+      CK(cudaMemcpy(dt, table.data(), sizeof(int32_t) * table.size(), cudaMemcpyHostToDevice));
+      h->layout_table = dt;
+      L.pe_at = dt;
+      // corner neighbours: the N/S neighbour's E/W neighbour (what the reference reaches by relaying, F:1976-2006)
+      auto nb = [&](int r, int q) -> int { return (r >= 0 && r < nr) ? all[r * 8 + q] : -1; };      // q: 4=E 5=W 6=N 7=S
+      auto corner = [&](int ns, int ew) -> int { int v = nb(nb(d->rank, ns), ew); return v >= 0 ? v : nb(nb(d->rank, ew), ns); };
+      h->nbr[dir_of(1, 1)] = corner(6, 4); h->nbr[dir_of(-1, 1)] = corner(6, 5);
+      h->nbr[dir_of(1, -1)] = corner(7, 4); h->nbr[dir_of(-1, -1)] = corner(7, 5);
       build_strips(h, pin->halo, h->hs_send, h->hs_recv);
       long long cells = h->hs_send.off[8] + (long long)h->hs_send.ni[8] * h->hs_send.nj[8];
       h->halo_buf_cells = cells * 16;
       CK(cudaMalloc(&h->halo_send, sizeof(double) * h->halo_buf_cells));
       CK(cudaMalloc(&h->halo_recv, sizeof(double) * h->halo_buf_cells));
     }
+    h->nbr[4] = -1;
   }
   // derived parameters, F:1264, F:1312, F:1483
   KidParams* q = &h->p;
@@ -829,15 +882,25 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   CK(cudaMalloc(&b.halo_code, h->capacity));
   CK(cudaMemsetAsync(b.flags, 0, h->capacity, h->stream));
   CK(cudaMemsetAsync(b.halo_code, 0, h->capacity, h->stream));
-  CK(cudaMalloc(&h->spare8, 8 * h->capacity));
-  CK(cudaMalloc(&h->spare4, 4 * h->capacity));
-  CK(cudaMalloc(&h->spare1, h->capacity));
-  CK(cudaMalloc(&h->perm, sizeof(int32_t) * h->capacity));
-  {
-    const int nr = d->nranks, w = std::max(nr, 9);
-    CK(cudaMallocHost(&h->h_all_counts, sizeof(int32_t) * nr * w));
-    if (nr > 1) CK(cudaMalloc(&h->d_all_counts, sizeof(int32_t) * nr * w));
+  for (int k = 0; k < 2; k++) {
+    CK(cudaMalloc(&h->sort_keys[k], sizeof(int32_t) * h->capacity));
+    CK(cudaMalloc(&h->sort_vals[k], sizeof(int32_t) * h->capacity));
   }
+  {
+    const long long ntiles = (h->capacity + KID_RADIX_TILE - 1) / KID_RADIX_TILE;
+    CK(cudaMalloc(&h->radix_hist, sizeof(int32_t) * KID_RADIX_MAXBINS * ntiles));
+    h->radix_sums_cap = (KID_RADIX_MAXBINS * ntiles + KID_SCAN_ITEMS - 1) / KID_SCAN_ITEMS + 1;
+    CK(cudaMalloc(&h->radix_sums, sizeof(int32_t) * (h->radix_sums_cap + 1)));
+  }
+  CK(cudaMalloc(&h->slow_slots, sizeof(uint32_t) * h->capacity));
+  CK(cudaMalloc(&h->slow_count, sizeof(unsigned long long)));
+  if (getenv("KID_NO_FAST")) h->fast_path = 0;
+  CK(cudaMallocHost(&h->h_totals, 2 * sizeof(int32_t)));
+  CK(cudaMallocHost(&h->h_nslots, sizeof(unsigned long long)));
+  for (int k = 0; k < KID_GATHER_NC; k++) CK(cudaMalloc(&h->spare_f64[k], sizeof(double) * h->capacity));
+  CK(cudaMalloc(&h->spare_id, sizeof(int64_t) * h->capacity));
+  for (int k = 0; k < 3; k++) CK(cudaMalloc(&h->spare_i32[k], sizeof(int32_t) * h->capacity));
+  for (int k = 0; k < 2; k++) { CK(cudaMalloc(&h->spare_u8[k], h->capacity)); CK(cudaMemsetAsync(h->spare_u8[k], 0, h->capacity, h->stream)); }
   if (q->interactive_icebergs_on) {
     b.max_bonds = q->iceberg_bonds_on ? q->max_bonds : 0;
     if (b.max_bonds > 0) {
@@ -847,6 +910,14 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
       CK(cudaMalloc(&b.bond_other_ine, sizeof(int32_t) * nb));
       CK(cudaMalloc(&b.bond_other_jne, sizeof(int32_t) * nb));
       CK(cudaMalloc(&b.bond_length, sizeof(double) * nb));
+      CK(cudaMalloc(&h->alt_bond_other_id, sizeof(int64_t) * nb));
+      CK(cudaMalloc(&h->alt_bond_other_ine, sizeof(int32_t) * nb));
+      CK(cudaMalloc(&h->alt_bond_other_jne, sizeof(int32_t) * nb));
+      CK(cudaMalloc(&h->alt_bond_length, sizeof(double) * nb));
+      CK(cudaMemsetAsync(h->alt_bond_other_id, 0, sizeof(int64_t) * nb, h->stream));
+      CK(cudaMemsetAsync(h->alt_bond_other_ine, 0, sizeof(int32_t) * nb, h->stream));
+      CK(cudaMemsetAsync(h->alt_bond_other_jne, 0, sizeof(int32_t) * nb, h->stream));
+      CK(cudaMemsetAsync(h->alt_bond_length, 0, sizeof(double) * nb, h->stream));
       CK(cudaMemsetAsync(b.bond_other_id, 0, sizeof(int64_t) * nb, h->stream));
       CK(cudaMemsetAsync(b.bond_other_slot, 0xff, sizeof(int32_t) * nb, h->stream));
       CK(cudaMemsetAsync(b.bond_other_ine, 0, sizeof(int32_t) * nb, h->stream));
@@ -856,9 +927,13 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
         for (int k = 0; k < BD_N; k++) {
           CK(cudaMalloc(&b.bond_dem[k], sizeof(double) * nb));
           CK(cudaMemsetAsync(b.bond_dem[k], 0, sizeof(double) * nb, h->stream));
+          CK(cudaMalloc(&h->alt_bond_dem[k], sizeof(double) * nb));
+          CK(cudaMemsetAsync(h->alt_bond_dem[k], 0, sizeof(double) * nb, h->stream));
         }
         CK(cudaMalloc(&b.bond_broken, sizeof(int32_t) * nb));
         CK(cudaMemsetAsync(b.bond_broken, 0, sizeof(int32_t) * nb, h->stream));
+        CK(cudaMalloc(&h->alt_bond_broken, sizeof(int32_t) * nb));
+        CK(cudaMemsetAsync(h->alt_bond_broken, 0, sizeof(int32_t) * nb, h->stream));
       }
     }
     CK(cudaMalloc(&b.conglom_id, sizeof(int32_t) * h->capacity));
@@ -901,7 +976,6 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   }
   CK(cudaMalloc(&h->cell_count, sizeof(int32_t) * n2));
   CK(cudaMalloc(&h->cell_start, sizeof(int32_t) * n2));
-  CK(cudaMalloc(&h->cell_fill, sizeof(int32_t) * n2));
   int nsb = (int)((n2 + KID_SCAN_ITEMS - 1) / KID_SCAN_ITEMS);
   CK(cudaMalloc(&h->scan_sums, sizeof(int32_t) * (nsb + 1)));
   CK(cudaMalloc(&h->scan_total, 2 * sizeof(int32_t)));
@@ -925,6 +999,7 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   ct.LoW_ratio = q->LoW_ratio; ct.rho_bergs = q->rho_bergs;
   const char* si = getenv("KID_SORT_INTERVAL");
   if (si && atoi(si) > 0) h->sort_interval = atoi(si);
+  if (const char* sd = getenv("KID_SCATTER_DENSE")) h->scatter_dense_forced = atoi(sd) ? 1 : 0;      // diagnostics: force a variant
 
   LAUNCH(h, k_pack_lonlat, n2, 256, h->g, n2);
   LAUNCH(h, k_pack_rect, n2, 256, h->g, h->dp, n2);
@@ -947,8 +1022,17 @@ extern "C" int32_t kid_end(kid_t** hp) {
   for (int c = 0; c < C_NCOLS; c++) cudaFree(h->b.f64[c]);
   cudaFree(h->b.id); cudaFree(h->b.ine); cudaFree(h->b.jne); cudaFree(h->b.start_year);
   cudaFree(h->b.flags); cudaFree(h->b.halo_code);
-  cudaFree(h->spare8); cudaFree(h->spare4); cudaFree(h->spare1); cudaFree(h->perm);
-  cudaFree(h->cell_count); cudaFree(h->cell_start); cudaFree(h->cell_fill);
+  for (int k = 0; k < 2; k++) { cudaFree(h->sort_keys[k]); cudaFree(h->sort_vals[k]); cudaFree(h->spare_u8[k]); }
+  cudaFree(h->radix_hist); cudaFree(h->radix_sums); cudaFree(h->slow_slots); cudaFree(h->slow_count);
+  if (h->h_totals) cudaFreeHost(h->h_totals);
+  if (h->h_nslots) cudaFreeHost(h->h_nslots);
+  for (auto p : h->spare_f64) cudaFree(p);
+  cudaFree(h->spare_id);
+  for (auto p : h->spare_i32) cudaFree(p);
+  cudaFree(h->alt_bond_other_id); cudaFree(h->alt_bond_other_ine); cudaFree(h->alt_bond_other_jne); cudaFree(h->alt_bond_broken);
+  cudaFree(h->alt_bond_length);
+  for (auto p : h->alt_bond_dem) cudaFree(p);
+  cudaFree(h->cell_count); cudaFree(h->cell_start);
   cudaFree(h->scan_sums); cudaFree(h->scan_total); cudaFree(h->dcnt); cudaFree(h->dflags);
   cudaFreeHost(h->hcnt); cudaFreeHost(h->hflags);
   for (int k = 0; k < BD_N; k++) cudaFree(h->b.bond_dem[k]);
@@ -961,7 +1045,7 @@ extern "C" int32_t kid_end(kid_t** hp) {
   cudaFree(h->d_send_counts); cudaFree(h->d_cursor); cudaFree(h->d_offsets); cudaFree(h->d_all_counts);
   if (h->h_all_counts) cudaFreeHost(h->h_all_counts);
   if (h->h_offsets) cudaFreeHost(h->h_offsets);
-  cudaFree(h->halo_send); cudaFree(h->halo_recv);
+  cudaFree(h->halo_send); cudaFree(h->halo_recv); cudaFree(h->layout_table);
   cudaFree(h->gsend); cudaFree(h->grecv); cudaFree(h->d_gcounts); cudaFree(h->d_goffsets); cudaFree(h->d_gcursor);
   cudaFree(h->b.bond_other_id); cudaFree(h->b.bond_other_slot); cudaFree(h->b.bond_other_ine);
   cudaFree(h->b.bond_other_jne); cudaFree(h->b.bond_length); cudaFree(h->b.conglom_id); cudaFree(h->d_changed);
@@ -1002,97 +1086,115 @@ static int check_device_errors(kid_t* h) {
 }
 
 // ------------------------------------------------------------------ sort
-template <typename T>
-static void gather_cols(kid_t* h, T** cols, int ncols, T** spare, long long n_new) {
-  // permutes columns one group at a time through the spare buffer: dst of a group is
-  // the spare of the previous one, so one extra column of memory suffices
-  for (int c = 0; c < ncols; c++) {
-    if (!cols[c]) continue;
-    GatherArgs<T, 1> a;
-    a.src[0] = cols[c]; a.dst[0] = *spare;
-    LAUNCH(h, (k_gather<T, 1>), n_new, 256, a, h->perm, n_new);
-    std::swap(cols[c], *spare);
-  }
+// exclusive scan of n int32 (in place allowed); *total receives the sum
+static void scan_i32(kid_t* h, const int32_t* in, int32_t* out, int32_t* sums, long long n, int32_t* total) {
+  int nsb = (int)((n + KID_SCAN_ITEMS - 1) / KID_SCAN_ITEMS);
+  LAUNCH(h, k_scan_block, (long long)nsb * 256, 256, in, out, sums, n);
+  k_scan_sums<<<1, 1024, 0, h->stream>>>(sums, nsb, total); h->launches++;
+  LAUNCH(h, k_scan_add, n, 256, out, sums, n);
+}
+
+template <int NC>
+static void launch_gather_f64(kid_t* h, const GatherF64& a, long long n) {
+  LAUNCH(h, (k_gather_f64<NC>), n, 256, a, h->perm, n);
 }
 
 #ifndef KID_DENSE_BERGS_PER_CELL
 #define KID_DENSE_BERGS_PER_CELL 20
 #endif
+// The cell-binned sort (kid_sort.cuh): keys + per-cell histogram, cell table by scan, stable radix ranking of
+// (cell, slot) pairs, then the permutation applied to every column -- up to 8 fp64 columns per launch through
+// 8 rotating spare columns (the store needs 8 extra columns, not a second copy).  One host synchronisation
+// (the new slot count), placed after the ranking kernels have been queued.
 static int sort_bergs(kid_t* h) {
-  long long n2 = h->n2, ns = h->n_slots;
+  const long long n2 = h->n2, ns = h->n_slots;
   CK(cudaMemsetAsync(h->cell_count, 0, sizeof(int32_t) * n2, h->stream));
   if (ns <= 0) { h->steps_since_sort = 0; h->tables_valid = 1; return KID_OK; }
-  CK(cudaMemsetAsync(h->cell_fill, 0, sizeof(int32_t) * n2, h->stream));
-  LAUNCH(h, k_hist, ns, 256, h->g, h->b.flags, h->b.ine, h->b.jne, ns, h->cell_count);
+  const int32_t dead_key = (int32_t)n2;
+  LAUNCH(h, k_sort_keys, ns, 256, h->g, h->b.flags, h->b.ine, h->b.jne, ns, dead_key, h->sort_keys[0], h->sort_vals[0], h->cell_count);
   CK(cudaMemsetAsync(h->scan_total + 1, 0, sizeof(int32_t), h->stream));
   LAUNCH(h, k_count_occupied, n2, 256, h->cell_count, n2, h->scan_total + 1);
-  int nsb = (int)((n2 + KID_SCAN_ITEMS - 1) / KID_SCAN_ITEMS);
-  LAUNCH(h, k_scan_block, (long long)nsb * 256, 256, h->cell_count, h->cell_start, h->scan_sums, n2);
-  k_scan_sums<<<1, 1024, 0, h->stream>>>(h->scan_sums, nsb, h->scan_total); h->launches++;
-  LAUNCH(h, k_scan_add, n2, 256, h->cell_start, h->scan_sums, n2);
-  LAUNCH(h, k_rank, ns, 256, h->g, h->b.flags, h->b.ine, h->b.jne, ns, h->cell_start, h->cell_fill, h->perm);
-  LAUNCH(h, k_cell_order, n2, 128, h->b, h->cell_start, h->cell_count, n2, h->perm, (h->p.footloose || h->p.dem) ? 1 : 0);
-  int32_t totals[2] = {0, 0};
-  CK(cudaMemcpyAsync(totals, h->scan_total, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  long long n_new = totals[0];
-  {
-    static const char* ev = getenv("KID_SCATTER_DENSE");      // diagnostics: force a variant
-    h->scatter_dense = ev ? atoi(ev) : ((long long)totals[0] > KID_DENSE_BERGS_PER_CELL * (long long)totals[1]);
+  scan_i32(h, h->cell_count, h->cell_start, h->scan_sums, n2, h->scan_total);
+  CK(cudaMemcpyAsync(h->h_totals, h->scan_total, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  // stable LSD radix passes over the bits of [0, n2]
+  int bits = 1;
+  while ((1LL << bits) <= n2) bits++;
+  const int npass = (bits + 7) / 8, dbits = (bits + npass - 1) / npass, nbins = 1 << dbits;
+  const int ntiles = (int)((ns + KID_RADIX_TILE - 1) / KID_RADIX_TILE);
+  int cur = 0;
+  for (int pass = 0; pass < npass; pass++) {
+    const int shift = pass * dbits;
+    k_radix_hist<<<ntiles, KID_RADIX_THREADS, 0, h->stream>>>(h->sort_keys[cur], ns, shift, nbins, ntiles, h->radix_hist);
+    h->launches++;
+    const long long nh = (long long)nbins * ntiles;
+    scan_i32(h, h->radix_hist, h->radix_hist, h->radix_sums, nh, h->radix_sums + h->radix_sums_cap);
+    k_radix_scatter<<<ntiles, KID_RADIX_THREADS, 0, h->stream>>>(h->sort_keys[cur], h->sort_vals[cur], h->sort_keys[cur ^ 1], h->sort_vals[cur ^ 1],
+                                                                 ns, shift, nbins, ntiles, h->radix_hist);
+    h->launches++;
+    cur ^= 1;
   }
-  double* sp8 = (double*)h->spare8;
-  gather_cols<double>(h, h->b.f64, C_NCOLS, &sp8, n_new);
-  int64_t* spi = (int64_t*)sp8;
-  gather_cols<int64_t>(h, &h->b.id, 1, &spi, n_new);
-  h->spare8 = spi;
-  int32_t* sp4 = (int32_t*)h->spare4;
-  int32_t* icols[3] = {h->b.ine, h->b.jne, h->b.start_year};
-  gather_cols<int32_t>(h, icols, 3, &sp4, n_new);
-  h->b.ine = icols[0]; h->b.jne = icols[1]; h->b.start_year = icols[2];
-  h->spare4 = sp4;
-  uint8_t* sp1 = (uint8_t*)h->spare1;
-  CK(cudaMemsetAsync(sp1, 0, h->capacity, h->stream));
-  uint8_t* bcols[1] = {h->b.flags};
-  gather_cols<uint8_t>(h, bcols, 1, &sp1, n_new);
-  h->b.flags = bcols[0];
-  CK(cudaMemsetAsync(sp1, 0, h->capacity, h->stream));
-  bcols[0] = h->b.halo_code;
-  gather_cols<uint8_t>(h, bcols, 1, &sp1, n_new);
-  h->b.halo_code = bcols[0];
-  h->spare1 = sp1;
-  if (h->b.max_bonds > 0) {
-    // bond entries travel with their berg; partners are re-resolved by connect_bonds() (slots changed)
-    const long long cap = h->capacity;
-    for (int k = 0; k < h->b.max_bonds; k++) {
-      { GatherArgs<int64_t, 1> a; a.src[0] = h->b.bond_other_id + k * cap; a.dst[0] = (int64_t*)h->spare8;
-        LAUNCH(h, (k_gather<int64_t, 1>), n_new, 256, a, h->perm, n_new);
-        CK(cudaMemcpyAsync(h->b.bond_other_id + k * cap, h->spare8, sizeof(int64_t) * n_new, cudaMemcpyDeviceToDevice, h->stream)); }
-      { GatherArgs<double, 1> a; a.src[0] = h->b.bond_length + k * cap; a.dst[0] = (double*)h->spare8;
-        LAUNCH(h, (k_gather<double, 1>), n_new, 256, a, h->perm, n_new);
-        CK(cudaMemcpyAsync(h->b.bond_length + k * cap, h->spare8, sizeof(double) * n_new, cudaMemcpyDeviceToDevice, h->stream)); }
-      for (int q = 0; q < BD_N; q++) {
-        if (!h->b.bond_dem[q]) continue;
-        GatherArgs<double, 1> a; a.src[0] = h->b.bond_dem[q] + k * cap; a.dst[0] = (double*)h->spare8;
-        LAUNCH(h, (k_gather<double, 1>), n_new, 256, a, h->perm, n_new);
-        CK(cudaMemcpyAsync(h->b.bond_dem[q] + k * cap, h->spare8, sizeof(double) * n_new, cudaMemcpyDeviceToDevice, h->stream));
+  h->perm = h->sort_vals[cur];
+  CK(cudaStreamSynchronize(h->stream));
+  const long long n_new = h->h_totals[0];
+  h->scatter_dense = h->scatter_dense_forced >= 0 ? h->scatter_dense_forced
+                                                  : ((long long)h->h_totals[0] > KID_DENSE_BERGS_PER_CELL * (long long)h->h_totals[1]);
+  if (h->p.footloose || h->p.dem) LAUNCH(h, k_cell_order, n2, 128, h->b, h->cell_start, h->cell_count, n2, h->perm);
+  DevBergs& b = h->b;
+  {
+    int cols[C_NCOLS], nc = 0;
+    for (int c = 0; c < C_NCOLS; c++) if (b.f64[c]) cols[nc++] = c;
+    for (int c0 = 0; c0 < nc; c0 += KID_GATHER_NC) {
+      const int m = std::min(KID_GATHER_NC, nc - c0);
+      GatherF64 a;
+      a.nc = m;
+      for (int q = 0; q < KID_GATHER_NC; q++) { a.src[q] = q < m ? b.f64[cols[c0 + q]] : nullptr; a.dst[q] = q < m ? h->spare_f64[q] : nullptr; }
+      switch (m) {
+        case 1: launch_gather_f64<1>(h, a, n_new); break; case 2: launch_gather_f64<2>(h, a, n_new); break;
+        case 3: launch_gather_f64<3>(h, a, n_new); break; case 4: launch_gather_f64<4>(h, a, n_new); break;
+        case 5: launch_gather_f64<5>(h, a, n_new); break; case 6: launch_gather_f64<6>(h, a, n_new); break;
+        case 7: launch_gather_f64<7>(h, a, n_new); break; default: launch_gather_f64<8>(h, a, n_new); break;
       }
-      int32_t* i32s[3] = {h->b.bond_other_ine + k * cap, h->b.bond_other_jne + k * cap, h->b.bond_broken ? h->b.bond_broken + k * cap : nullptr};
-      for (int32_t* col : i32s) {
-        if (!col) continue;
-        GatherArgs<int32_t, 1> a; a.src[0] = col; a.dst[0] = (int32_t*)h->spare4;
-        LAUNCH(h, (k_gather<int32_t, 1>), n_new, 256, a, h->perm, n_new);
-        CK(cudaMemcpyAsync(col, h->spare4, sizeof(int32_t) * n_new, cudaMemcpyDeviceToDevice, h->stream));
-      }
+      for (int q = 0; q < m; q++) std::swap(b.f64[cols[c0 + q]], h->spare_f64[q]);
     }
+  }
+  {
+    GatherMisc a;
+    a.id_src = b.id; a.id_dst = h->spare_id;
+    int32_t** i32[3] = {&b.ine, &b.jne, &b.start_year};
+    uint8_t** u8[2] = {&b.flags, &b.halo_code};
+    for (int q = 0; q < 3; q++) { a.i32_src[q] = *i32[q]; a.i32_dst[q] = h->spare_i32[q]; }
+    for (int q = 0; q < 2; q++) { a.u8_src[q] = *u8[q]; a.u8_dst[q] = h->spare_u8[q]; }
+    for (int q = 0; q < 2; q++) { a.aux_src[q] = nullptr; a.aux_dst[q] = nullptr; }
+    LAUNCH(h, k_gather_misc, ns, 256, a, h->perm, n_new, ns);
+    std::swap(b.id, h->spare_id);
+    for (int q = 0; q < 3; q++) std::swap(*i32[q], h->spare_i32[q]);
+    for (int q = 0; q < 2; q++) std::swap(*u8[q], h->spare_u8[q]);
+  }
+  if (b.max_bonds > 0) {
+    // bond entries travel with their berg; partners are re-resolved by connect_bonds() (slots changed)
+    GatherBonds a;
+    a.capacity = h->capacity; a.max_bonds = b.max_bonds;
+    a.oid_src = b.bond_other_id; a.oid_dst = h->alt_bond_other_id;
+    int32_t** i32[3] = {&b.bond_other_ine, &b.bond_other_jne, &b.bond_broken};
+    int32_t** i32a[3] = {&h->alt_bond_other_ine, &h->alt_bond_other_jne, &h->alt_bond_broken};
+    for (int q = 0; q < 3; q++) { a.i32_src[q] = *i32[q]; a.i32_dst[q] = *i32a[q]; }
+    a.f64_src[0] = b.bond_length; a.f64_dst[0] = h->alt_bond_length;
+    for (int q = 0; q < BD_N; q++) { a.f64_src[1 + q] = b.bond_dem[q]; a.f64_dst[1 + q] = h->alt_bond_dem[q]; }
+    LAUNCH(h, k_gather_bonds, n_new, 256, a, h->perm, n_new);
+    std::swap(b.bond_other_id, h->alt_bond_other_id);
+    for (int q = 0; q < 3; q++) std::swap(*i32[q], *i32a[q]);
+    std::swap(b.bond_length, h->alt_bond_length);
+    for (int q = 0; q < BD_N; q++) std::swap(b.bond_dem[q], h->alt_bond_dem[q]);
   }
   h->tables_valid = 1;
   unsigned long long nn = (unsigned long long)n_new;
-  CK(cudaMemcpyAsync(&h->dcnt->n_slots, &nn, sizeof(nn), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  h->h_nslots[0] = nn;
+  CK(cudaMemcpyAsync(&h->dcnt->n_slots, h->h_nslots, sizeof(nn), cudaMemcpyHostToDevice, h->stream));
   h->n_slots = n_new;
   h->steps_since_sort = 0;
   h->dirty_appended = 0;
   h->sorted_once = 1;
+  h->sorts_done++;
   return KID_OK;
 }
 
@@ -1190,6 +1292,14 @@ extern "C" int32_t kid_sort_bergs(kid_t* h) {
   cudaSetDevice(h->d.device);
   return sort_bergs(h);
 }
+
+extern "C" int32_t kid_set_sort_phase(kid_t* h, int32_t interval, int32_t steps_since_sort) {
+  if (!h) return KID_ERR_ARG;
+  if (interval > 0) h->sort_interval = interval;
+  if (steps_since_sort >= 0) h->steps_since_sort = steps_since_sort;
+  return KID_OK;
+}
+extern "C" int64_t kid_sorts_done(kid_t* h) { return h ? h->sorts_done : 0; }
 
 // ---------------------------------------------------------- berg columns
 namespace {
@@ -1771,10 +1881,20 @@ static bool pipeline_mode(const kid_t* h) {
          !p.runge_not_verlet && !h->calving_active && h->xstream != nullptr;
 }
 
-// slots [s0, s1) take the step (s0 a multiple of KID_BLOCK)
+// slots [s0, s1) take the step (s0 a multiple of KID_BLOCK).  main_launch: the step's launch over the whole store
+// (the fast kernel + its slow list, kid_kernels.cuh); the small launches for arrivals on the exchange stream use
+// the one-kernel path (the slow list belongs to the main stream).
 template <bool FL, bool DG>
-static void launch_step(kid_t* h, long long s0, long long s1) {
+static void launch_step(kid_t* h, long long s0, long long s1, bool main_launch = false) {
   const long long n = s1 - s0;
+  if (!FL && !DG && main_launch && h->fast_path && lean_config(h) && h->p.grid_is_regular && n > 0) {
+    cudaMemsetAsync(h->slow_count, 0, sizeof(unsigned long long), h->stream);
+    SlowList sl{h->slow_slots, h->slow_count, h->capacity};
+    if (h->scatter_dense) { LAUNCH(h, (k_step_fast<true>), n, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s1, s0, sl); }
+    else { LAUNCH(h, (k_step_fast<false>), n, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s1, s0, sl); }
+    k_step_slow<<<2 * h->num_sms, KID_BLOCK, 0, h->stream>>>(h->g, h->b, h->dp, h->dcnt, sl); h->launches++;
+    return;
+  }
   if (!FL && !DG && lean_config(h)) {
     if (h->scatter_dense) { LAUNCH(h, (k_step<false, false, false, true, true>), n, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s1, s0); }
     else { LAUNCH(h, (k_step<false, false, false, true, false>), n, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s1, s0); }
@@ -1926,7 +2046,7 @@ static int step_core(kid_t* h) {
       if (dg) { LAUNCH(h, (k_step_rk<true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
       else { LAUNCH(h, (k_step_rk<false>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
     } else if (fl) { LAUNCH(h, (k_step<true, false, false>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots, 0LL); }
-    else if (dg) launch_step<false, true>(h, 0, h->n_slots); else launch_step<false, false>(h, 0, h->n_slots);
+    else if (dg) launch_step<false, true>(h, 0, h->n_slots, true); else launch_step<false, false>(h, 0, h->n_slots, true);
   }
   if (h->xchg_pending) {
     // the previous step's migration, overlapped with the kernel just launched
@@ -2208,6 +2328,54 @@ extern "C" int32_t kid_incr_mass(kid_t* h, double* mass) {
   CK(cudaMemcpyAsync(tmp.data(), h->out_stage3[0], sizeof(double) * nc, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   for (size_t k = 0; k < nc; k++) mass[k] = mass[k] + tmp[k];
+  return KID_OK;
+}
+
+// ---- unit-level entries: the spreading geometry of kid_spread.cuh evaluated ON THE DEVICE for single inputs, so the
+// reference's own known answers (hexagon_test I:261-348, the point-in-triangle regression I:234-242) pin the CUDA code
+// itself and not only the oracle's copy of the same routines
+__global__ void k_unit_hexagon(double x0, double y0, double H, double theta, double pi, double* out) {
+  int ok = kh_hexagon_into_quadrants(x0, y0, H, theta, pi, &out[0], &out[1], &out[2], &out[3], &out[4]);
+  out[5] = (double)ok;
+}
+__global__ void k_unit_point_in_triangle(double Ax, double Ay, double Bx, double By, double Cx, double Cy, double qx, double qy,
+                                         double* out) {
+  out[0] = (double)kh_point_in_triangle(Ax, Ay, Bx, By, Cx, Cy, qx, qy);
+  out[1] = kh_area_of_triangle(Ax, Ay, Bx, By, Cx, Cy);
+}
+static int unit_device(int32_t device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); g_init_error = "no CUDA device (this library has no CPU fallback)"; return KID_ERR_NO_DEVICE; }
+  if (device < 0 || device >= ndev || cudaSetDevice(device) != cudaSuccess) { g_init_error = "bad device ordinal"; return KID_ERR_ARG; }
+  return KID_OK;
+}
+extern "C" int32_t kid_unit_hexagon_into_quadrants(int32_t device, double x0, double y0, double H, double theta, double out[5]) {
+  if (!out) return KID_ERR_ARG;
+  int rc = unit_device(device);
+  if (rc) return rc;
+  double* d = nullptr;
+  double hst[6];
+  if (cudaMalloc(&d, sizeof(hst)) != cudaSuccess) return KID_ERR_CUDA;
+  k_unit_hexagon<<<1, 1>>>(x0, y0, H, theta, 3.14159265358979323846, d);
+  cudaError_t e = cudaMemcpy(hst, d, sizeof(hst), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) { g_init_error = cudaGetErrorString(e); return KID_ERR_CUDA; }
+  for (int k = 0; k < 5; k++) out[k] = hst[k];
+  return hst[5] != 0. ? KID_OK : KID_ERR_STATE;
+}
+extern "C" int32_t kid_unit_point_in_triangle(int32_t device, const double v[8], int32_t* inside, double* area) {
+  if (!v || !inside) return KID_ERR_ARG;
+  int rc = unit_device(device);
+  if (rc) return rc;
+  double* d = nullptr;
+  double hst[2];
+  if (cudaMalloc(&d, sizeof(hst)) != cudaSuccess) return KID_ERR_CUDA;
+  k_unit_point_in_triangle<<<1, 1>>>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], d);
+  cudaError_t e = cudaMemcpy(hst, d, sizeof(hst), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) { g_init_error = cudaGetErrorString(e); return KID_ERR_CUDA; }
+  *inside = (int32_t)hst[0];
+  if (area) *area = hst[1];
   return KID_OK;
 }
 

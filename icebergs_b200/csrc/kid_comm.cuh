@@ -83,12 +83,15 @@ enum PackSlot : int {
 namespace kid {
 
 // ---------------------------------------------------------------- layout
-// layout of the ranks over the global grid (mpp_define_layout / mpp_compute_extent restated in
-// kid_define_domain): rank = px + lx*py owns columns xs[px]..xs[px+1]-1 and rows ys[py]..ys[py+1]-1
+// layout of the ranks over the global grid: the tile in column px, row py of the layout owns columns
+// xs[px]..xs[px+1]-1 and rows ys[py]..ys[py+1]-1.  kid_init builds xs, ys and the (px,py) -> rank table from the
+// compute domains the ranks were actually given (mpp_define_domains: any mpp_compute_extent split, masked-out
+// PEs = -1 in the table); without a table (host-side kid_owner_rank) rank = px + lx*py.
 #define KID_MAX_DIV 64
 struct DevLayout {
   int32_t lx, ly, gni, gnj, cyclic_x, cyclic_y, rank, nranks;
   int32_t xs[KID_MAX_DIV + 1], ys[KID_MAX_DIV + 1];
+  const int32_t* pe_at;       // [lx*ly] in device memory, or nullptr
 };
 
 // owner of global cell (i,j); -1 = outside the model (NULL_PE).  i may be any number of periods off.
@@ -98,6 +101,9 @@ __host__ __device__ __forceinline__ int owner_rank(const DevLayout& L, int i, in
   int px = 0, py = 0;
   while (px + 1 < L.lx && i >= L.xs[px + 1]) px++;
   while (py + 1 < L.ly && j >= L.ys[py + 1]) py++;
+#ifdef __CUDA_ARCH__
+  if (L.pe_at) return L.pe_at[px + L.lx * py];
+#endif
   return px + L.lx * py;
 }
 

@@ -7,8 +7,8 @@
 //                     melt fluxes scattered with warp-aggregated fp64 atomics.
 //   k_thermo_range    thermodynamics alone for a slot range (bergs that arrived by
 //                     migration after the fused kernel ran).
-//   k_hist/k_rank/k_cell_order/k_gather*   the cell-binned counting sort that replaces
-//                     move_berg_between_cells (F:1758) and the per-cell lists (F:416).
+//   k_scan_* / k_cell_order   scans and the keyed in-cell order used by the cell-binned sort
+//                     (kid_sort.cuh) that replaces move_berg_between_cells (F:1758) and the per-cell lists (F:416).
 //   k_ingest_* / k_pack_*   forcing ingest (I:5203-5383) and the packed grid records.
 //   k_accumulate_calving / k_calve   I:6153 / I:6225.
 #pragma once
@@ -302,7 +302,7 @@ __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, c
     bounced = adjust_index_and_ground(g, p, lonn, latn, i, j, xi, yj, &cnt->error_flags, &cnt->warn_adjust);
     lon = lonn; lat = latn;
     b.f64[C_LON][s] = lon; b.f64[C_LAT][s] = lat;
-    if (SPLIT) {      // I:7189-7194
+    if (SPLIT && b.f64[C_UVEL_OLD]) {      // I:7189-7194 (columns of interactive runs)
       b.f64[C_UVEL_OLD][s] = uvel; b.f64[C_VVEL_OLD][s] = vvel;
       b.f64[C_LON_OLD][s] = lon; b.f64[C_LAT_OLD][s] = lat;
     }
@@ -387,6 +387,198 @@ k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) nh += shfl_down_d(nh, d);
     if ((threadIdx.x & 31) == 0 && nh != 0.) atomicAdd(&cnt->net_heat_to_ocean, nh);
+  }
+}
+
+// ------------------------------------------------- fast path + slow list
+// The benchmark configuration (lean_config(): free-drifting Verlet bergs on a regular lat-lon grid with the
+// default namelist switches) spends its time on bergs that do the ordinary thing: stay in their cell or hop to
+// a wet neighbour cell, stay on the tile, survive the melt.  k_step_fast carries exactly that case in straight-
+// line code -- no out-of-line calls, hence no call-clobbered registers and none of the general cell walk, coast
+// bounce, tangent-plane, exchange or footloose code in its instruction stream -- and hands every other berg to
+// k_step_slow through a device-side list of slots.  A list entry says how far the fast kernel got:
+//   SLOW_FULL   nothing done (static berg, |lat| > 89, cell off the tile's data domain): the whole step_berg
+//   SLOW_SPLIT  verlet_stepping done and stored (velocity, accelerations); position update, cell walk,
+//               send_bergs and thermodynamics to do (the SPLIT instance of step_berg, which reads the stored
+//               post-solve values back as update_verlet_position I:7727 uses them)
+// Both kernels evaluate the same inlined functions, so which one handles a berg does not change its result.
+#define KID_SLOW_SPLIT 0x80000000u
+struct SlowList { uint32_t* slots; unsigned long long* count; long long cap; };
+
+#ifndef KID_FAST_MINBLOCKS
+#define KID_FAST_MINBLOCKS 6
+#endif
+
+template <bool DENSE>
+__global__ void __launch_bounds__(KID_BLOCK, KID_FAST_MINBLOCKS)
+k_step_fast(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b, const __grid_constant__ DevParams p,
+            DevCounters* __restrict__ cnt, long long n_slots, long long s_base, const __grid_constant__ SlowList slow) {
+  constexpr bool LEAN = true;
+  long long s = s_base + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = s < n_slots;
+  const long long sl = in_range ? s : 0;
+  uint8_t flags = b.flags[sl];
+  int i = b.ine[sl], j = b.jne[sl];
+  double lat = b.f64[C_LAT][sl];
+  double uvel = b.f64[C_UVEL][sl], vvel = b.f64[C_VVEL][sl];
+  double axn = b.f64[C_AXN][sl], ayn = b.f64[C_AYN][sl], bxn = b.f64[C_BXN][sl], byn = b.f64[C_BYN][sl];
+  double xi = b.f64[C_XI][sl], yj = b.f64[C_YJ][sl];
+  double M = b.f64[C_MASS][sl], T = b.f64[C_THICKNESS][sl], W = b.f64[C_WIDTH][sl], L = b.f64[C_LENGTH][sl];
+  prefetch_l1(&b.f64[C_LON][sl]); prefetch_l1(&b.f64[C_MASS_SCALING][sl]);
+  prefetch_l1(&b.f64[C_MASS_OF_BITS][sl]); prefetch_l1(&b.f64[C_HEAT_DENSITY][sl]);
+  if (!in_range) flags = 0;
+  const bool owned = (flags & BF_ALIVE) && !(flags & (BF_HALO | BF_LEAVER));
+  // 0 = done here, 1 = whole berg to the slow kernel, 2 = from the position update on
+  int defer = 0;
+  if (owned && ((flags & BF_STATIC) || !(fabs(lat) <= 89.) || !cell_on_pe(g, i, j))) defer = 1;
+  Scatter sc;
+  sc.key = -1;
+  sc.fx.floating_melt = sc.fx.calving_hflx = sc.fx.berg_melt = sc.fx.bergy_src = sc.fx.bergy_melt = 0.;
+  sc.fx.net_heat = 0.;
+  bool melted = false;
+  if (owned && !defer) {
+    const int ne = gidx(g, i, j);
+    prefetch_l1(&g.rect[ne]);
+    const double dt = p.dt, dt_2 = 0.5 * dt;
+    // ---- verlet_stepping I:7203-7328 (same statements as step_berg)
+    double sin_lat, cos_lat;
+    sincos_halfpi_nofallback(p.pi_180 * lat, &sin_lat, &cos_lat);
+    b.f64[C_UVEL_PREV][s] = uvel - dt_2 * bxn;
+    b.f64[C_VVEL_PREV][s] = vvel - dt_2 * byn;
+    const double uvel3 = uvel + (dt_2 * axn);
+    const double vvel3 = vvel + (dt_2 * ayn);
+    Env e;
+    if (!interp_flds<LEAN>(g, p, i, j, xi, yj, e)) atomicOr(&cnt->error_flags, 64u);
+    const double f_cori = p.omega2 * sin_lat;
+    double ax1, ay1, un_l, vn_l;
+    IAcc ia0 = {0., 0., 0., 0., 0., 0., 0., 0.};
+    accel_core<false, LEAN>(p, M, T, W, L, f_cori, uvel, vvel, dt, e, 1.0, ia0,
+                            [](double, double, IAcc&) {}, ax1, ay1, axn, ayn, bxn, byn, un_l, vn_l);
+    uvel = uvel3 + (dt * ax1); vvel = vvel3 + (dt * ay1);      // evolve_icebergs I:7157-7162
+    b.f64[C_AXN][s] = axn; b.f64[C_AYN][s] = ayn; b.f64[C_BXN][s] = bxn; b.f64[C_BYN][s] = byn;
+    b.f64[C_UVEL][s] = uvel; b.f64[C_VVEL][s] = vvel;
+    // ---- update_verlet_position I:7684-7764
+    const double uvel2 = uvel + (dt_2 * axn) + (dt_2 * bxn);
+    const double vvel2 = vvel + (dt_2 * ayn) + (dt_2 * byn);
+    const double dxdl1 = p.r180_pi * rcp_nr(p.Rearth * cos_lat);
+    const double u2 = uvel2 * dxdl1, v2 = vvel2 * p.dlat_dy;
+    const double lonn = b.f64[C_LON][s] + (dt * u2), latn = lat + (dt * v2);
+    // ---- adjust_index_and_ground I:7819: in the cell, or one hop to a wet neighbour; anything else is deferred
+    const double lo = KID_EDGE_BAND, hi = 1. - KID_EDGE_BAND;
+    const double Lx = p.Lx, Lx_2 = Lx * 0.5;
+    const RectCell rc = g.rect[ne];
+    double a = 0., bb = 0.;
+    bool okpos = rc.ralpha == rc.ralpha;
+    {
+      double xm = lonn;
+      if (Lx > 0.) {                                   // apply_modulo_around_point F:6558, in-range case
+        const double yy = KSUB(rc.x1, Lx_2), t = KSUB(lonn, yy);
+        okpos = okpos && (t >= 0. && t < Lx);
+        xm = KADD(t, yy);
+      }
+      a = KADD(KMUL(KSUB(xm, rc.x1), rc.ralpha), p.rect_add);
+      bb = KADD(KMUL(KSUB(latn, rc.y1), rc.reps), p.rect_add);
+    }
+    const bool inside = a > lo && a < hi && bb > lo && bb < hi;
+    if (okpos && !inside) {
+      // strictly outside the cell (not within the edge band, where the reference's sign test decides)
+      okpos = (a < -lo || a > 1. + lo || bb < -lo || bb > 1. + lo);
+      const double* __restrict__ msk = g.msk;
+      if (okpos) {
+        if (a < 0.) { okpos = (i > g.isd + 1) && (msk[gidx(g, i - 1, j)] > 0.); i = i - 1; }
+        else if (a >= 1.) { okpos = (i < g.ied) && (msk[gidx(g, i + 1, j)] > 0.); i = i + 1; }
+      }
+      if (okpos) {
+        if (bb < 0.) { okpos = (j > g.jsd + 1) && (msk[gidx(g, i, j - 1)] > 0.); j = j - 1; }
+        else if (bb >= 1.) { okpos = (j < g.jed) && (msk[gidx(g, i, j + 1)] > 0.); j = j + 1; }
+      }
+      okpos = okpos && cell_on_pe(g, i, j) && !(i > g.iec || i < g.isc || j > g.jec || j < g.jsc);
+      if (okpos) {
+        const RectCell r2 = g.rect[gidx(g, i, j)];
+        okpos = r2.ralpha == r2.ralpha;
+        double xm = lonn;
+        if (Lx > 0.) {
+          const double yy = KSUB(r2.x1, Lx_2), t = KSUB(lonn, yy);
+          okpos = okpos && (t >= 0. && t < Lx);
+          xm = KADD(t, yy);
+        }
+        a = KADD(KMUL(KSUB(xm, r2.x1), r2.ralpha), p.rect_add);
+        bb = KADD(KMUL(KSUB(latn, r2.y1), r2.reps), p.rect_add);
+        okpos = okpos && (a > lo && a < hi && bb > lo && bb < hi);
+      }
+    }
+    if (!okpos) {
+      defer = 2;
+    } else {
+      xi = a; yj = bb;
+      b.f64[C_LON][s] = lonn; b.f64[C_LAT][s] = latn;
+      b.f64[C_XI][s] = xi; b.f64[C_YJ][s] = yj;
+      b.ine[s] = i; b.jne[s] = j;
+      // ---- thermodynamics I:2844-3300 at the new position
+      int outcome = thermo_slot<false, LEAN>(g, b, p, s, flags, i, j, xi, yj, uvel, vvel, M, T, W, L,
+                                             b.f64[C_MASS_SCALING][s], b.f64[C_MASS_OF_BITS][s], b.f64[C_HEAT_DENSITY][s],
+                                             sc, cnt);
+      if (outcome == TH_DELETE) { melted = true; b.flags[s] = 0; }
+    }
+  }
+  if (defer) {
+    unsigned long long k = atomicAdd(slow.count, 1ull);
+    if ((long long)k < slow.cap) slow.slots[k] = (uint32_t)s | (defer == 2 ? KID_SLOW_SPLIT : 0u);
+    else atomicOr(&cnt->error_flags, (unsigned)KID_DEVERR_CAPACITY);
+  }
+  scatter_fluxes<false, false, DENSE>(g, sc);
+  if (__any_sync(0xffffffffu, melted)) warp_count_add(&cnt->nbergs_melted, melted);
+  double nh = sc.fx.net_heat;
+  if (__any_sync(0xffffffffu, nh != 0.)) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) nh += shfl_down_d(nh, d);
+    if ((threadIdx.x & 31) == 0 && nh != 0.) atomicAdd(&cnt->net_heat_to_ocean, nh);
+  }
+}
+
+// the bergs k_step_fast deferred: warp w takes list entries [32 w, 32 w + 32), grid-stride
+__global__ void __launch_bounds__(KID_BLOCK)
+k_step_slow(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b, const __grid_constant__ DevParams p,
+            DevCounters* __restrict__ cnt, const __grid_constant__ SlowList slow) {
+  constexpr bool LEAN = true;
+  const unsigned long long n = min(*slow.count, (unsigned long long)slow.cap);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < (long long)n; base += stride) {
+    const long long k = base + (threadIdx.x & 31);
+    Scatter sc;
+    sc.key = -1;
+    sc.fx.floating_melt = sc.fx.calving_hflx = sc.fx.berg_melt = sc.fx.bergy_src = sc.fx.bergy_melt = 0.;
+    sc.fx.fl_bits_melt = sc.fx.fl_bits_src = sc.fx.net_heat = 0.;
+    sc.fx.fl_parent_melt = sc.fx.fl_child_melt = sc.fx.melt_buoy = sc.fx.melt_eros = sc.fx.melt_conv = 0.;
+    sc.fx.melt_buoy_fl = sc.fx.melt_eros_fl = sc.fx.melt_conv_fl = 0.;
+    bool melted = false, became_fl = false, bounced = false, speeding = false, left = false;
+    if (k < (long long)n) {
+      const uint32_t ent = slow.slots[k];
+      const long long s = (long long)(ent & ~KID_SLOW_SPLIT);
+      BergIn in;
+      in.flags = b.flags[s];
+      in.i = b.ine[s]; in.j = b.jne[s];
+      in.lat = b.f64[C_LAT][s];
+      in.uvel = b.f64[C_UVEL][s]; in.vvel = b.f64[C_VVEL][s];
+      in.axn = b.f64[C_AXN][s]; in.ayn = b.f64[C_AYN][s]; in.bxn = b.f64[C_BXN][s]; in.byn = b.f64[C_BYN][s];
+      in.xi = b.f64[C_XI][s]; in.yj = b.f64[C_YJ][s];
+      in.M = b.f64[C_MASS][s]; in.T = b.f64[C_THICKNESS][s]; in.W = b.f64[C_WIDTH][s]; in.L = b.f64[C_LENGTH][s];
+      if (ent & KID_SLOW_SPLIT) step_berg<false, true, LEAN>(g, b, p, cnt, s, in, sc, melted, became_fl, bounced, speeding, left);
+      else step_berg<false, false, LEAN>(g, b, p, cnt, s, in, sc, melted, became_fl, bounced, speeding, left);
+    }
+    scatter_fluxes<false, false, true>(g, sc);
+    if (__any_sync(0xffffffffu, melted | bounced | speeding | left)) {
+      warp_count_add(&cnt->nbergs_melted, melted);
+      warp_count_add(&cnt->n_bounced, bounced);
+      warp_count_add(&cnt->nspeeding, speeding);
+      warp_count_add(&cnt->n_leavers, left);
+    }
+    double nh = sc.fx.net_heat;
+    if (__any_sync(0xffffffffu, nh != 0.)) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) nh += shfl_down_d(nh, d);
+      if ((threadIdx.x & 31) == 0 && nh != 0.) atomicAdd(&cnt->net_heat_to_ocean, nh);
+    }
   }
 }
 
@@ -562,19 +754,7 @@ k_thermo_range(const __grid_constant__ DevGrid g, const __grid_constant__ DevBer
   if ((threadIdx.x & 31) == 0 && nh != 0.) atomicAdd(&cnt->net_heat_to_ocean, nh);
 }
 
-// ----------------------------------------------------------- cell-binned sort
-// key of a berg = linear index of its cell in the data domain; dead slots and
-// leavers (already packed for migration) are dropped, which compacts the store.
-__global__ void k_hist(const __grid_constant__ DevGrid g, const uint8_t* __restrict__ flags,
-                       const int32_t* __restrict__ ine, const int32_t* __restrict__ jne, long long n_slots,
-                       int32_t* __restrict__ cell_count) {
-  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_slots) return;
-  uint8_t f = flags[s];
-  if (!(f & BF_ALIVE) || (f & BF_LEAVER)) return;
-  atomicAdd(&cell_count[gidx(g, ine[s], jne[s])], 1);
-}
-
+// ------------------------------------------------- scans and in-cell order (the sort itself: kid_sort.cuh)
 // exclusive scan of int32 counts, three phases; 1024 items per block
 #define KID_SCAN_ITEMS 1024
 __global__ void __launch_bounds__(256) k_scan_block(const int32_t* __restrict__ in, int32_t* __restrict__ out,
@@ -634,19 +814,6 @@ __global__ void k_scan_add(int32_t* __restrict__ out, const int32_t* __restrict_
   if (k < n) out[k] += block_sums[k / KID_SCAN_ITEMS];
 }
 
-__global__ void k_rank(const __grid_constant__ DevGrid g, const uint8_t* __restrict__ flags,
-                       const int32_t* __restrict__ ine, const int32_t* __restrict__ jne, long long n_slots,
-                       const int32_t* __restrict__ cell_start, int32_t* __restrict__ cell_fill,
-                       int32_t* __restrict__ perm) {
-  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_slots) return;
-  uint8_t f = flags[s];
-  if (!(f & BF_ALIVE) || (f & BF_LEAVER)) return;
-  size_t c = gidx(g, ine[s], jne[s]);
-  int32_t pos = cell_start[c] + atomicAdd(&cell_fill[c], 1);
-  perm[pos] = (int32_t)s;
-}
-
 // the reference's list key, inorder() F:4318-4358: (start_year, start_day, start_mass, start_lon,
 // start_lat) ascending; equal keys keep their previous order
 __device__ __forceinline__ bool key_before(const DevBergs& b, int32_t x, int32_t y) {
@@ -661,10 +828,11 @@ __device__ __forceinline__ bool key_before(const DevBergs& b, int32_t x, int32_t
   return x < y;
 }
 
-// makes the in-cell order deterministic and stable: ascending old slot, or (keyed) the order of the
-// reference's per-cell lists -- needed where that order decides an integer (ids of footloose children)
+// Where the reference's per-cell list order decides an integer (ids of footloose children, the pair order of
+// the DEM sweeps) the slots of a cell are put in that order: insertion sort by the list key of a run that the
+// stable radix sort left in ascending previous slot.  Populations of these configurations are small.
 __global__ void k_cell_order(const __grid_constant__ DevBergs b, const int32_t* __restrict__ cell_start,
-                             const int32_t* __restrict__ cell_count, long long ncell, int32_t* __restrict__ perm, int keyed) {
+                             const int32_t* __restrict__ cell_count, long long ncell, int32_t* __restrict__ perm) {
   long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncell) return;
   int32_t n = cell_count[c];
@@ -673,23 +841,9 @@ __global__ void k_cell_order(const __grid_constant__ DevBergs b, const int32_t* 
   for (int32_t k = 1; k < n; k++) {
     int32_t v = a[k];
     int32_t m = k - 1;
-    if (keyed) { while (m >= 0 && key_before(b, v, a[m])) { a[m + 1] = a[m]; m--; } }
-    else { while (m >= 0 && a[m] > v) { a[m + 1] = a[m]; m--; } }
+    while (m >= 0 && key_before(b, v, a[m])) { a[m + 1] = a[m]; m--; }
     a[m + 1] = v;
   }
-}
-
-template <typename T, int NC>
-struct GatherArgs { const T* src[NC]; T* dst[NC]; };
-template <typename T, int NC>
-__global__ void __launch_bounds__(256) k_gather(const __grid_constant__ GatherArgs<T, NC> a,
-                                                const int32_t* __restrict__ perm, long long n) {
-  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  int32_t s = perm[k];
-#pragma unroll
-  for (int c = 0; c < NC; c++)
-    if (a.src[c]) a.dst[c][k] = a.src[c][s];
 }
 
 // ------------------------------------------------------------ grid kernels

@@ -64,8 +64,12 @@ __device__ __forceinline__ double sqrt_nr(double x) { return sqrt(x); }
 
 // sin and cos for |x| <= pi/2 (x = pi/180*lat): Taylor polynomials in x^2 to x^23 / x^24,
 // truncation < 1e-20, rounding a few ulp -- no argument reduction, no slow path
+__device__ __forceinline__ void sincos_halfpi_nofallback(double x, double* s, double* c);
 __device__ __forceinline__ void sincos_halfpi(double x, double* s, double* c) {
   if (!(fabs(x) <= 1.5708)) { sincos(x, s, c); return; }
+  sincos_halfpi_nofallback(x, s, c);
+}
+__device__ __forceinline__ void sincos_halfpi_nofallback(double x, double* s, double* c) {
   const double z = x * x;
   double ps = -1. / 25852016738884976640000.;            // -1/23!
   ps = fma(ps, z, 1. / 51090942171709440000.);            //  1/21!

@@ -103,13 +103,15 @@ class Grid:
         f["calving_hflx"] = np.zeros_like(lam_c)
         return {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in f.items()}
 
-    def seed_bergs(self, n, stream=0, seed=SEED):
+    def seed_bergs(self, n, stream=0, seed=SEED, start=0, counter0=None):
         """n bergs uniformly over this tile's wet cells: (xi,yj) in U(.05,.95)^2,
-        class U{1..10}, LoW geometry (F:1540-1541), zero velocity, ids as generate_id F:4165-4177."""
+        class U{1..10}, LoW geometry (F:1540-1541), zero velocity, ids as generate_id F:4165-4177.
+        start / counter0: bergs start..start+n-1 of a population seeded in chunks (counter0 = the per-cell
+        id counters the earlier chunks returned)."""
         wet = self.wet(0) > 0.5
         jj, ii = np.nonzero(wet)
         ncell = len(ii)
-        k = np.arange(n, dtype=np.uint64)
+        k = np.arange(start, start + n, dtype=np.uint64)
         base = np.uint64(stream) << np.uint64(40)
         c = np.minimum((u01(1, k + base, seed) * ncell).astype(np.int64), ncell - 1)
         i = (ii[c] + self.isc).astype(np.int32)
@@ -128,9 +130,11 @@ class Grid:
         order = np.argsort(cell, kind="stable")
         sc = cell[order]
         first = np.r_[0, np.nonzero(np.diff(sc))[0] + 1]
-        start = np.repeat(first, np.diff(np.r_[first, n]))
+        first_of = np.repeat(first, np.diff(np.r_[first, n]))
         counter = np.empty(n, dtype=np.int64)
-        counter[order] = np.arange(n) - start + 1
+        counter[order] = np.arange(n) - first_of + 1
+        if counter0 is not None:
+            counter += counter0.reshape(-1)[cell]
         ident = counter * (1 << 32) + (i.astype(np.int64) + self.gni * (j.astype(np.int64) - 1))
         z = np.zeros(n)
         return dict(lon=lon, lat=lat, uvel=z.copy(), vvel=z.copy(), mass=mass.copy(), thickness=thick.copy(),
@@ -138,13 +142,13 @@ class Grid:
                     start_lon=lon.copy(), start_lat=lat.copy(), start_day=(cls + 1) / 17.0,
                     start_mass=mass.copy(), mass_scaling=MASS_SCALING[cls].copy(), mass_of_bits=z.copy(),
                     heat_density=z.copy(), start_year=np.ones(n, dtype=np.int32), ine=i, jne=j,
-                    id=ident.astype(np.int64)), counter_grid(self, cell, n)
+                    id=ident.astype(np.int64)), counter_grid(self, cell, n, counter0)
 
 
-def counter_grid(grid: Grid, cell, n):
+def counter_grid(grid: Grid, cell, n, counter0=None):
     """iceberg_counter_grd consistent with the seeded ids (global cell -> count)."""
-    cnt = np.bincount(cell, minlength=grid.gni * grid.gnj).astype(np.int32)
-    return cnt.reshape(grid.gnj, grid.gni)
+    cnt = np.bincount(cell, minlength=grid.gni * grid.gnj).astype(np.int32).reshape(grid.gnj, grid.gni)
+    return cnt if counter0 is None else cnt + counter0
 
 
 def workload_params(default_params, **over):

@@ -383,6 +383,12 @@ int32_t kid_incr_mass(kid_t* h, double* mass /* (isc:iec,jsc:jec) inout */);
 
 /* force a cell-sort of the berg store now (normally periodic, internal) */
 int32_t kid_sort_bergs(kid_t* h);
+/* The periodic sort of free-drifting bergs runs every `interval` steps (KID_SORT_INTERVAL, default 32; 0 keeps the
+ * current value); steps_since_sort sets where in that period the next step falls (< 0 keeps it).  Measurement
+ * control: bench.py places the sorts so that every timed window is charged ceil(steps/interval) of them. */
+int32_t kid_set_sort_phase(kid_t* h, int32_t interval, int32_t steps_since_sort);
+/* cell sorts done by this handle so far */
+int64_t kid_sorts_done(kid_t* h);
 int32_t kid_synchronize(kid_t* h);
 
 int32_t kid_end(kid_t** h);
@@ -415,6 +421,12 @@ int32_t kid_local_comm_destroy(void* group);
 /* fp64 words one migrating berg occupies in the exchange buffer (reference: buffer_width F:21) */
 int32_t kid_pack_width(void);
 
+
+/* Unit-level entries (parity tests): one evaluation ON THE DEVICE of the mass-spreading geometry.
+ *   Hexagon_into_quadrants_using_triangles I:4562-4670: out = Area_hex, Area_Q1..Q4   (hexagon_test I:261-348)
+ *   point_in_triangle I:4166-4199 for triangle A,B,C and point q: v = Ax,Ay,Bx,By,Cx,Cy,qx,qy; area = Area_of_triangle */
+int32_t kid_unit_hexagon_into_quadrants(int32_t device, double x0, double y0, double H, double theta, double out[5]);
+int32_t kid_unit_point_in_triangle(int32_t device, const double v[8], int32_t* inside, double* area);
 
 const char* kid_last_error(const kid_t* h);   /* h may be NULL: last init error */
 const char* kid_version(void);

@@ -2739,3 +2739,60 @@ int32_t oracle_find_cell_wide(const Oracle* o, double x, double y, int32_t* oi, 
 /* bonds, MTS/DEM, footloose and the spreading-geometry known answers live in
  * the second half of this translation unit */
 #include "kid_oracle_ext.inc"
+
+/* ---- namelist defaults (ice_bergs_framework_init F:686-822) and FMS constants, carried by the oracle so the
+ * CPU baseline / reference arm of bench.py never loads the product library ---- */
+void oracle_default_params(KidParams* p) {
+  static const double im[10] = {8.8e7, 4.1e8, 3.3e9, 1.8e10, 3.8e10, 7.5e10, 1.2e11, 2.2e11, 3.9e11, 7.4e11};      /* F:787 */
+  static const double ds[10] = {0.24, 0.12, 0.15, 0.18, 0.12, 0.07, 0.03, 0.03, 0.03, 0.02};                        /* F:788 */
+  static const double sc[10] = {2000, 200, 50, 20, 10, 5, 2, 1, 1, 1};                                              /* F:789 */
+  static const double th[10] = {40., 67., 133., 175., 250., 250., 250., 250., 250., 250.};                          /* F:790 */
+  static const double imn[10] = {4.58e8, 3.61e9, 1.22e10, 2.91e10, 5.09e10, 7.34e10, 1.15e11, 1.65e11, 2.94e11, 5.59e11};
+  static const double dsn[10] = {0.14, 0.15, 0.20, 0.15, 0.08, 0.07, 0.05, 0.05, 0.05, 0.05};
+  static const double scn[10] = {200, 50, 25, 13, 8, 5, 2, 1, 1, 1};
+  static const double thn[10] = {80.4, 159.5, 240., 320., 360., 360., 360., 360., 360., 360.};
+  memset(p, 0, sizeof(*p));
+  p->abi_version = KID_ABI_VERSION;
+  p->halo = 4;
+  p->pi = 3.14159265358979323846; p->omega = 7.292e-5; p->radius = 6371.0e3; p->hlf = 3.34e5;      /* FMS constants_mod */
+  p->grid_is_latlon = 1; p->grid_is_regular = 1; p->Lx = 360.; p->Rearth = 6360000.;
+  p->runge_not_verlet = 1; p->old_bug_bilin = 1; p->use_roundoff_fix = 1; p->old_interp_flds_order = 1;
+  p->rho_bergs = 850.; p->ocean_drag_scale = 1.; p->h_to_init_grounding = 100.;
+  p->critical_interaction_damping_on = 1; p->tang_crit_int_damp_on = 1; p->scale_damping_by_pmag = 1;
+  p->max_bonds = 6; p->spring_coef = 1.e-8; p->radial_damping_coef = 1.e-4; p->tangental_damping_coef = 2.e-5;
+  p->contact_cells_lon = 1; p->contact_cells_lat = 1; p->length_for_manually_initialize_bonds = 1000.;
+  p->mts_sub_steps = -1; p->convergence_tolerance = 1.e-8; p->save_bond_forces = 1; p->remove_unused_bergs = 1;
+  p->poisson = 0.3; p->dem_damping_coef = 0.1;
+  p->use_operator_splitting = 1; p->allow_bergs_to_roll = 1; p->melt_cutoff = -1.;
+  p->displace_fl_bergs = 1; p->fl_bits_erosion_to_bergy_bits = 1;
+  p->fl_youngs = 1.e7; p->fl_strength = 250.; p->new_berg_from_fl_bits_mass_thres = 1.e12;
+  p->LoW_ratio = 1.5;
+  p->use_three_equation_model = 1; p->const_gamma = 1; p->gamma_t_3eq = 0.022; p->ustar_icebergs_bg = 0.001;
+  p->utide_icebergs = 0.; p->cdrag_icebergs = 1.5e-3;
+  p->add_weight_to_ocean = 1; p->use_old_spreading = 1; p->rotate_icebergs_for_mass_spreading = 1;
+  for (int k = 0; k < 10; k++) {
+    p->initial_mass_s[k] = im[k]; p->distribution_s[k] = ds[k]; p->mass_scaling_s[k] = sc[k]; p->initial_thickness_s[k] = th[k];
+    p->initial_mass_n[k] = imn[k]; p->distribution_n[k] = dsn[k]; p->mass_scaling_n[k] = scn[k]; p->initial_thickness_n[k] = thn[k];
+  }
+}
+
+/* one PE that owns the whole grid (mpp_define_domains with layout 1x1) */
+void oracle_single_domain(KidDomain* d, int32_t gni, int32_t gnj, int32_t halo, int32_t cyclic_x, int32_t cyclic_y) {
+  memset(d, 0, sizeof(*d));
+  d->gni = gni; d->gnj = gnj;
+  d->isc = 1; d->iec = gni; d->jsc = 1; d->jec = gnj;
+  d->isd = 1 - halo; d->ied = gni + halo; d->jsd = 1 - halo; d->jed = gnj + halo;
+  d->cyclic_x = cyclic_x; d->cyclic_y = cyclic_y;
+  d->rank = 0; d->nranks = 1; d->layout_x = 1; d->layout_y = 1;
+  d->pe_E = d->pe_W = cyclic_x ? 0 : -1;
+  d->pe_N = d->pe_S = cyclic_y ? 0 : -1;
+}
+
+/* threads an OpenMP region of this build gets (0 = built without OpenMP) */
+int32_t oracle_omp_max_threads(void) {
+#ifdef _OPENMP
+  return (int32_t)omp_get_max_threads();
+#else
+  return 0;
+#endif
+}

@@ -94,6 +94,12 @@ void    oracle_accel_free(const KidParams* p, const double berg[8] /* M,T,W,L,la
                           const double env[13] /* uo,vo,ui,vi,ua,va,ssh_x,ssh_y,sst,sss,cn,hi,od */,
                           double out[6]);
 
+/* namelist defaults F:686-822 + FMS constants, a 1x1 layout, and the OpenMP width of this build: what bench.py's
+ * CPU legs need so that they never load the product library */
+void    oracle_default_params(KidParams* p);
+void    oracle_single_domain(KidDomain* d, int32_t gni, int32_t gnj, int32_t halo, int32_t cyclic_x, int32_t cyclic_y);
+int32_t oracle_omp_max_threads(void);
+
 #ifdef __cplusplus
 }
 #endif

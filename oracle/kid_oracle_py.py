@@ -7,6 +7,7 @@ test can push identical inputs through both.
 from __future__ import annotations
 
 import ctypes as C
+import importlib.util
 import os
 import subprocess
 import sys
@@ -14,16 +15,82 @@ import sys
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.dirname(_HERE))
-from icebergs_b200 import _cdefs as D  # noqa: E402  (struct mirrors only; no compute)
+_ROOT = os.path.dirname(_HERE)
 
+
+def load_by_path(name, relpath):
+    """A module of the repo loaded from its file, WITHOUT importing the package around it: the struct mirrors
+    (icebergs_b200/_cdefs.py, generated from include/kid_b200.h) and the synthetic workload generator
+    (icebergs_b200/synthetic.py, pure numpy) are shared with the product, the product itself is never imported here."""
+    full = "icebergs_b200." + name
+    if full in sys.modules:           # a parity test has the package loaded already: share its classes
+        return sys.modules[full]
+    key = "_kid_oracle_" + name
+    if key in sys.modules:
+        return sys.modules[key]
+    spec = importlib.util.spec_from_file_location(key, os.path.join(_ROOT, relpath))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[key] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+D = load_by_path("_cdefs", os.path.join("icebergs_b200", "_cdefs.py"))
+
+# struct pointers are declared void* below: a parity test may hand over structs of the product's own
+# icebergs_b200._cdefs classes (same layout, generated from the same header) whatever the import order
 LIB_PATH = os.path.join(_HERE, "libkid_oracle.so")
+FAST_LIB_PATH = os.path.join(_HERE, "_fast", "libkid_oracle_fast.so")
 _vp = C.c_void_p
 _LIB = None
+_FAST = False
 
 
 def build():
     subprocess.run(["make", "-s", "-C", _HERE], check=True)
+
+
+def use_fast_build():
+    """Timing legs of bench.py: the -O3 -march=native -fopenmp build, compiled on this box (oracle/Makefile `fast`).
+    Must be called before the first lib() call.  Fails loudly when OpenMP is missing."""
+    global _FAST, LIB_PATH
+    if _LIB is not None:
+        raise RuntimeError("use_fast_build() after the oracle library was loaded")
+    subprocess.run(["make", "-s", "-B", "-C", _HERE, "fast"], check=True)   # always: -march=native must match THIS box
+    LIB_PATH = FAST_LIB_PATH
+    _FAST = True
+    if lib().oracle_omp_max_threads() < 1:
+        raise RuntimeError("the fast oracle build has no OpenMP")
+
+
+def default_params(**overrides):
+    """Reference namelist defaults (F:686-822) from the oracle itself."""
+    p = D.KidParams()
+    lib().oracle_default_params(C.byref(p))
+    for k, v in overrides.items():
+        cur = getattr(p, k)
+        if hasattr(cur, "__len__"):
+            for q, x in enumerate(v):
+                cur[q] = x
+        else:
+            setattr(p, k, v)
+    return p
+
+
+class SingleDomain:
+    """What api.Domain.single offers the oracle: .c (KidDomain) and the tile sizes."""
+
+    def __init__(self, gni, gnj, halo=4, cyclic_x=True, cyclic_y=False):
+        self.c = D.KidDomain()
+        lib().oracle_single_domain(C.byref(self.c), gni, gnj, halo, int(cyclic_x), int(cyclic_y))
+
+    def __getattr__(self, k):
+        return getattr(self.c, k)
+
+    nic = property(lambda s: s.c.iec - s.c.isc + 1)
+    njc = property(lambda s: s.c.jec - s.c.jsc + 1)
+    nid = property(lambda s: s.c.ied - s.c.isd + 1)
+    njd = property(lambda s: s.c.jed - s.c.jsd + 1)
 
 
 def lib():
@@ -32,23 +99,28 @@ def lib():
         if not os.path.exists(LIB_PATH):
             build()
         L = C.CDLL(LIB_PATH)
+        L.oracle_default_params.argtypes = [_vp]
+        L.oracle_default_params.restype = None
+        L.oracle_single_domain.argtypes = [_vp] + [C.c_int32] * 5
+        L.oracle_single_domain.restype = None
+        L.oracle_omp_max_threads.restype = C.c_int32
         L.oracle_create.restype = _vp
-        L.oracle_create.argtypes = [C.POINTER(D.KidParams), C.POINTER(D.KidDomain), C.c_int32, C.c_double] + [_vp] * 9 + [C.c_int32]
+        L.oracle_create.argtypes = [_vp, _vp, C.c_int32, C.c_double] + [_vp] * 9 + [C.c_int32]
         L.oracle_destroy.argtypes = [_vp]
         L.oracle_last_error.argtypes = [_vp]
         L.oracle_last_error.restype = C.c_char_p
-        L.oracle_set_bergs.argtypes = [_vp, C.c_int64, C.POINTER(D.KidBergColumns)]
+        L.oracle_set_bergs.argtypes = [_vp, C.c_int64, _vp]
         L.oracle_count_bergs.argtypes = [_vp, C.c_int32]
         L.oracle_count_bergs.restype = C.c_int64
-        L.oracle_get_bergs.argtypes = [_vp, C.POINTER(C.c_int64), C.POINTER(D.KidBergColumns), C.c_int32]
-        L.oracle_set_bonds.argtypes = [_vp, C.c_int64, C.POINTER(D.KidBondColumns)]
-        L.oracle_get_bonds.argtypes = [_vp, C.POINTER(C.c_int64), C.POINTER(D.KidBondColumns)]
+        L.oracle_get_bergs.argtypes = [_vp, C.POINTER(C.c_int64), _vp, C.c_int32]
+        L.oracle_set_bonds.argtypes = [_vp, C.c_int64, _vp]
+        L.oracle_get_bonds.argtypes = [_vp, C.POINTER(C.c_int64), _vp]
         L.oracle_set_calving_state.argtypes = [_vp, _vp, _vp, _vp]
         L.oracle_get_calving_state.argtypes = [_vp, _vp, _vp, _vp]
         L.oracle_run.argtypes = [_vp, C.c_int32, C.c_double] + [_vp] * 12 + [C.c_int32, C.c_int32] + [_vp] * 4
         L.oracle_step_again.argtypes = [_vp, C.c_int32, C.c_int32, C.c_double, C.c_int32]
         L.oracle_get_grid_field.argtypes = [_vp, C.c_int32, _vp]
-        L.oracle_get_counters.argtypes = [_vp, C.POINTER(D.KidCounters)]
+        L.oracle_get_counters.argtypes = [_vp, _vp]
         L.oracle_last_timing.argtypes = [_vp, C.POINTER(C.c_double)]
         L.oracle_last_timing.restype = None
         L.oracle_bilin.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double]
@@ -65,9 +137,9 @@ def lib():
         L.oracle_split_id.restype = None
         L.oracle_yearday.argtypes = [C.c_int32] * 5
         L.oracle_yearday.restype = C.c_double
-        L.oracle_rolling.argtypes = [C.POINTER(D.KidParams)] + [C.POINTER(C.c_double)] * 3
+        L.oracle_rolling.argtypes = [_vp] + [C.POINTER(C.c_double)] * 3
         L.oracle_rolling.restype = None
-        L.oracle_accel_free.argtypes = [C.POINTER(D.KidParams)] + [C.POINTER(C.c_double)] * 4
+        L.oracle_accel_free.argtypes = [_vp] + [C.POINTER(C.c_double)] * 4
         L.oracle_accel_free.restype = None
         L.oracle_point_in_triangle.argtypes = [C.c_double] * 8
         L.oracle_hexagon_into_quadrants.argtypes = [C.c_double] * 4 + [C.POINTER(C.c_double)] * 5

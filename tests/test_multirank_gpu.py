@@ -336,3 +336,73 @@ def test_footloose_across_ranks():
     moved, o = _run_cartesian_ranks(2, params, S.footloose_bergs(), lambda g: S.footloose_forcing(g), 6000, 1000, names, f64,
                                     bonds=False, dt=10.0, yearday_of=lambda k, dt: k * dt / 86400.0)
     assert o.counters()["nbergs_calved_fl"] >= 2
+
+
+def _custom_domains(gni, gnj, xsizes, ysizes, halo, grp, rank_of=None):
+    """Tiles with the given extents along each axis, as mpp_define_domains would hand them out for an
+    mpp_compute_extent that does not split evenly; rank_of(px, py) numbers the PEs (default px + lx*py)."""
+    lx, ly = len(xsizes), len(ysizes)
+    x0 = np.r_[1, 1 + np.cumsum(xsizes)]
+    y0 = np.r_[1, 1 + np.cumsum(ysizes)]
+    rank_of = rank_of or (lambda px, py: px + lx * py)
+    doms = {}
+    for py in range(ly):
+        for px in range(lx):
+            c = D.KidDomain()
+            c.gni, c.gnj = gni, gnj
+            c.isc, c.iec, c.jsc, c.jec = int(x0[px]), int(x0[px + 1] - 1), int(y0[py]), int(y0[py + 1] - 1)
+            c.isd, c.ied, c.jsd, c.jed = c.isc - halo, c.iec + halo, c.jsc - halo, c.jec + halo
+            c.cyclic_x, c.cyclic_y = 1, 0
+            r = rank_of(px, py)
+            c.rank, c.nranks = r, lx * ly
+            c.layout_x, c.layout_y = lx, ly
+            c.pe_E, c.pe_W = rank_of((px + 1) % lx, py), rank_of((px - 1) % lx, py)
+            c.pe_N = rank_of(px, py + 1) if py + 1 < ly else -1
+            c.pe_S = rank_of(px, py - 1) if py > 0 else -1
+            c.device = 0
+            c.nccl_comm = grp._g.value
+            c.comm_kind = D.KID_COMM_LOCAL
+            doms[r] = api.Domain(c)
+    return [doms[r] for r in range(lx * ly)]
+
+
+@pytest.mark.parametrize("numbering", ["row_major", "shuffled"])
+def test_uneven_tiles_and_any_rank_numbering(numbering):
+    """The library takes the decomposition from the ranks' own compute domains and neighbour PEs (what the shim
+    passes from mpp_define_domains), not from a formula: a 100x50 grid on 3x2 PEs with extents 33/34/33 (a
+    remainder in the middle, as a symmetric mpp_compute_extent leaves it) and, second, PEs numbered in another order."""
+    gni, gnj = 100, 50
+    case = Case(gni, gnj, 9000, dt=43200.0, old_bug_bilin=0)
+    grp = parallel.LocalGroup(6)
+    perm = [0, 1, 2, 3, 4, 5] if numbering == "row_major" else [4, 0, 3, 5, 1, 2]
+    doms = _custom_domains(gni, gnj, [33, 34, 33], [24, 26], case.halo, grp, rank_of=lambda px, py: perm[px + 3 * py])
+
+    class R(Ranks):
+        def __init__(self):
+            self.case, self.nranks, self.run_ranks = case, 6, grp.run
+            self.doms = doms
+            self.grids = [S.Grid(gni, gnj, d.isc, d.iec, d.jsc, d.jec) for d in doms]
+            own = np.full((gnj + 1, gni + 1), -1)
+            for r, d in enumerate(doms):
+                own[d.jsc:d.jec + 1, d.isc:d.iec + 1] = r
+            owner = own[case.bergs["jne"], case.bergs["ine"]]
+            parts = [{k: np.ascontiguousarray(v[owner == r]) for k, v in case.bergs.items()} for r in range(6)]
+            self.h = [None] * 6
+
+            def init(r):
+                d = doms[r]
+                b = api.icebergs_init(gni, gnj, case.dt, (1, 0.0), params=case.params(), domain=d, capacity=case.capacity,
+                                      **self.grids[r].init_args())
+                cnt = np.zeros((d.njd, d.nid), dtype=np.int32)
+                hl = case.halo
+                cnt[hl:hl + d.njc, hl:hl + d.nic] = case.counter[d.jsc - 1:d.jec, d.isc - 1:d.iec]
+                b.set_calving_state(iceberg_counter_grd=cnt)
+                b.set_bergs(**parts[r])
+                self.h[r] = b
+            grp.run(init)
+
+    ranks = R()
+    moved = check_against_oracle(case, ranks, 6, dict(uo=1.2, vo=0.15, tauxa=15.0), rtol=1e-8)
+    assert moved > 100
+    ranks.end()
+    grp.close()

@@ -69,3 +69,37 @@ def test_hexagonal_spreading_with_bond_orientation():
     sm = p.o.grid_field(D.KID_FLD_SPREAD_MASS)
     assert (sm > 0).sum() > 16            # the 16 elements cover more cells than they sit in
     p.end()
+
+
+# ---- the reference's own known answers through the CUDA geometry (not only through the oracle's copy of it)
+def _known():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "known_answers.json")))
+
+
+def test_hexagon_identities_on_the_device():
+    """hexagon_test I:261-348: the 8 area identities of Hexagon_into_quadrants_using_triangles, tol 1e-10, evaluated
+    by kid_spread.cuh's kh_hexagon_into_quadrants on the GPU."""
+    import ctypes as C
+    k = _known()["hexagon"]
+    out = (C.c_double * 5)()
+    assert len(k["cases"]) >= 7
+    for case in k["cases"]:
+        rc = api.lib().kid_unit_hexagon_into_quadrants(0, case["x0"], case["y0"], k["H"], k["theta"], out)
+        assert rc == 0, case["name"]
+        assert abs(out[0] - k["area"]) <= k["tol"], case["name"]
+        for got, want in zip(list(out)[1:], case["Q"]):
+            assert abs(got - want) <= k["tol"], (case["name"], list(out), case["Q"])
+        assert abs(sum(list(out)[1:]) - out[0]) <= k["tol"]
+
+
+def test_point_in_triangle_regression_on_the_device():
+    """I:234-242: the point the reference's unit test found misclassified by round-off"""
+    import ctypes as C
+    k = _known()["point_in_triangle"]
+    v = (C.c_double * 8)(*k["A"], *k["B"], *k["C"], *k["q"])
+    inside, area = C.c_int32(-1), C.c_double(0.0)
+    assert api.lib().kid_unit_point_in_triangle(0, v, C.byref(inside), C.byref(area)) == 0
+    assert bool(inside.value) is k["inside"]
+    assert area.value > 0.0
