@@ -22,7 +22,7 @@ EXPORTS = [
     "kid_kernel_launches", "kid_get_counters", "kid_get_grid_field", "kid_stock", "kid_incr_mass",
     "kid_sort_bergs", "kid_synchronize", "kid_end", "kid_last_error", "kid_version",
     "kid_nccl_unique_id", "kid_nccl_init", "kid_nccl_destroy", "kid_pack_width",
-    "kid_local_comm_create", "kid_local_comm_destroy", "kid_owner_rank", "kid_set_sort_phase", "kid_sorts_done",
+    "kid_local_comm_create", "kid_local_comm_destroy", "kid_owner_rank", "kid_set_sort_phase", "kid_sorts_done", "kid_last_slow_count",
     "kid_unit_hexagon_into_quadrants", "kid_unit_point_in_triangle",
 ]
 
@@ -67,6 +67,8 @@ def load() -> C.CDLL:
     lib.kid_set_sort_phase.argtypes = [_vp, C.c_int32, C.c_int32]
     lib.kid_sorts_done.argtypes = [_vp]
     lib.kid_sorts_done.restype = C.c_int64
+    lib.kid_last_slow_count.argtypes = [_vp]
+    lib.kid_last_slow_count.restype = C.c_int64
     lib.kid_unit_hexagon_into_quadrants.argtypes = [C.c_int32] + [C.c_double] * 4 + [_dp]
     lib.kid_unit_point_in_triangle.argtypes = [C.c_int32, _dp, _ip, _dp]
     lib.kid_synchronize.argtypes = [_vp]

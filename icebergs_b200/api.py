@@ -183,7 +183,16 @@ class Icebergs:
         return n.value
 
     def get_bergs(self, names=RESTART_COLUMNS, include_halo=False) -> dict:
-        n = self.count_bergs() if not include_halo else int(self.counters()["n_slots_hint"])
+        if include_halo:
+            # owned bergs + halo copies: ask the library how many there are (a call with no room reports the count)
+            m = C.c_int64(0)
+            empty = D.KidBergColumns()
+            rc = lib().kid_get_bergs(self.handle, C.byref(m), C.byref(empty), 1)
+            if rc not in (D.KID_OK, D.KID_ERR_CAPACITY):
+                self._check(rc)
+            n = m.value
+        else:
+            n = self.count_bergs()
         cap = max(n, 1)
         c, keep = make_columns(cap, want=set(names))
         m = C.c_int64(cap)
@@ -270,6 +279,11 @@ class Icebergs:
 
     def sorts_done(self) -> int:
         return lib().kid_sorts_done(self.handle)
+
+    def slow_fraction(self):
+        """share of the bergs the fast step kernel deferred to the slow-path kernel in the last step (None: not used)"""
+        n = lib().kid_last_slow_count(self.handle)
+        return None if n < 0 else n / max(self.count_bergs(), 1)
 
     def last_timing(self):
         ms = (C.c_double * 8)()

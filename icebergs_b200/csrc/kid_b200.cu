@@ -53,6 +53,7 @@ struct kid_handle {
   int64_t* spare_id = nullptr;
   int32_t* spare_i32[3] = {nullptr, nullptr, nullptr};
   uint8_t* spare_u8[2] = {nullptr, nullptr};
+  int32_t* spare_aux[2] = {nullptr, nullptr};   // conglom_id, n_bonds (interactive runs)
   int64_t* alt_bond_other_id = nullptr;
   int32_t *alt_bond_other_ine = nullptr, *alt_bond_other_jne = nullptr, *alt_bond_broken = nullptr;
   double* alt_bond_length = nullptr;
@@ -61,6 +62,7 @@ struct kid_handle {
   uint32_t* slow_slots = nullptr;         // k_step_fast's deferred bergs (kid_kernels.cuh)
   unsigned long long* slow_count = nullptr;
   int fast_path = 1;                      // KID_NO_FAST=1 (diagnostics): the one-kernel path only
+  int fast_launched = 0;
   int scatter_dense_forced = -1;          // KID_SCATTER_DENSE (diagnostics): force a flux-scatter variant
   DevCounters* dcnt = nullptr;
   DevCounters* hcnt = nullptr;      // pinned
@@ -75,7 +77,8 @@ struct kid_handle {
   cudaStream_t stream = nullptr;
   // berg migration overlapped with the next step's kernel (step_core): second stream, two leaver lists
   cudaStream_t xstream = nullptr;
-  cudaEvent_t ev_kstep = nullptr, ev_xdone = nullptr;
+  cudaEvent_t ev_kstep = nullptr, ev_xdone = nullptr, ev_zero = nullptr;
+  int ev_zero_recorded = 0;
   int32_t* leaver_lists[2] = {nullptr, nullptr};
   unsigned long long* leaver_counts = nullptr;    // [2]
   int leaver_cur = 0, xchg_pending = 0, xdone_recorded = 0, defer_ok = 0;
@@ -90,6 +93,10 @@ struct kid_handle {
   MtsParams mp;                   // MTS scheme (evolve_icebergs_mts)
   MtsSums* dsums = nullptr;
   int mts_env_cached = 0, mts_outer_iters = 0, mts_smem_attr = 0;
+  int skip_first_outer_mts_step = 0;
+  int32_t* mts_bbox = nullptr;         // cell box per conglomerate label (k_mts_bbox), mts_bbox_n entries per bound
+  long long mts_bbox_n = 0;
+  int mts_bbox_valid = 0;
   int scatter_dense = 1;          // > KID_DENSE_BERGS_PER_CELL bergs per occupied cell at the last sort (scatter_fluxes)
   int forcing_set = 0;
   int no_rotation = 0;
@@ -112,6 +119,7 @@ struct kid_handle {
   double *gsend = nullptr, *grecv = nullptr;
   long long ghost_cap = 0;
   int ghost_rec_w = 0;
+  RecLayout rec;                       // what one berg occupies in an exchange / ghost buffer
   int32_t *d_gcounts = nullptr, *d_goffsets = nullptr, *d_gcursor = nullptr;   // [9]
   int tables_valid = 0, bond_lengths_set = 0, conglom_set = 0;
   int* d_changed = nullptr;                // cell_start/cell_count describe the current slot order
@@ -247,6 +255,11 @@ extern "C" const char* kid_last_error(const kid_t* h) { return h ? h->err.c_str(
 static int fail(kid_t* h, int code, const std::string& msg) {
   h->err = msg;
   return code;
+}
+// the berg store overflowed after device-side cursors or buffers were already updated: the handle is unusable
+static int fail_fatal(kid_t* h, int code, const std::string& msg) {
+  h->fatal = true;
+  return fail(h, code, msg);
 }
 
 static double* dev_field(kid_t* h, long long n, double fill) {
@@ -465,7 +478,7 @@ static int halo_exchange(kid_t* h, double* const* fields, int nf) {
 // s0: the slot the arrivals are appended at
 static int exchange_bergs(kid_t* h, long long* n_recv_out, long long s0) {
   const int nr = h->d.nranks, me = h->d.rank;
-  const long long W = PACK_W + 3 * h->b.max_bonds;      // record width: berg + its bonds
+  const long long W = h->rec.w;                         // record width: berg + its bonds (+ mts / dem state)
   *n_recv_out = 0;
   CK(cudaMemsetAsync(h->d_send_counts, 0, sizeof(int32_t) * nr, h->stream));
   CK(cudaMemsetAsync(h->d_cursor, 0, sizeof(int32_t) * nr, h->stream));
@@ -486,16 +499,16 @@ static int exchange_bergs(kid_t* h, long long* n_recv_out, long long s0) {
     if (c > 0) recvs.push_back({q, 100, h->recvbuf + (size_t)n_recv * W, c * W});
     n_recv += c;
   }
-  if (n_send > h->xbuf_cap || n_recv > h->xbuf_cap) return fail(h, KID_ERR_CAPACITY, "kid: berg exchange buffer capacity exceeded");
-  if (s0 + n_recv > h->capacity) return fail(h, KID_ERR_CAPACITY, "kid: berg store capacity exceeded by arrivals");
+  if (n_send > h->xbuf_cap || n_recv > h->xbuf_cap) return fail_fatal(h, KID_ERR_CAPACITY, "kid: berg exchange buffer capacity exceeded");
+  if (s0 + n_recv > h->capacity) return fail_fatal(h, KID_ERR_CAPACITY, "kid: berg store capacity exceeded by arrivals");
   CK(cudaMemcpyAsync(h->d_offsets, h->h_offsets, sizeof(int32_t) * nr, cudaMemcpyHostToDevice, h->stream));
   k_pack_leavers<<<32, 256, 0, h->stream>>>(h->layout, h->b, h->b.leaver_list, h->leaver_dest, h->b.leaver_count, (int32_t)h->b.leaver_cap, h->d_offsets,
-                                           h->d_cursor, h->sendbuf, (int)W); h->launches++;
+                                           h->d_cursor, h->sendbuf, h->rec); h->launches++;
   CK(cudaMemsetAsync(h->b.leaver_count, 0, sizeof(unsigned long long), h->stream));
   rc = comm_exchange(h, sends, recvs);
   if (rc) return rc;
   if (n_recv > 0) {
-    LAUNCH(h, k_unpack_arrivals, n_recv, 128, h->g, h->b, h->dp, h->dcnt, h->recvbuf, n_recv, s0, (int)W);
+    LAUNCH(h, k_unpack_arrivals, n_recv, 128, h->g, h->b, h->dp, h->dcnt, h->recvbuf, n_recv, s0, h->rec);
   }
   h->n_sent_last = n_send; h->n_recv_last = n_recv;
   *n_recv_out = n_recv;
@@ -552,12 +565,12 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
     unsupported = "Runge_not_Verlet=.true. (RK4) is implemented for free-drifting bergs only: set runge_not_verlet=0 with interactions / footloose";
   else if (pin->tidal_drift > 0.) unsupported = "tidal_drift>0 needs the FMS random number stream";
   else if (pin->add_iceberg_thickness_to_ssh) unsupported = "add_iceberg_thickness_to_SSH is not implemented";
+  else if (pin->tau_calving > 0.) unsupported = "tau_calving>0 (running mean of the calving field, I:5215) is not implemented";
+  else if (pin->find_melt_using_spread_mass) unsupported = "find_melt_using_spread_mass is not implemented";
   else if (pin->dem && !(pin->mts && pin->iceberg_bonds_on)) unsupported = "dem=.true. needs mts=.true. and iceberg_bonds_on (F:1433)";
   else if (pin->dem && pin->break_bonds_on_sub_steps && !pin->fracture_criterion_stress) unsupported = "break_bonds_on_sub_steps needs fracture_criterion='stress' (I:1201)";
-  else if (pin->mts && dom->nranks > 1) unsupported = "mts=.true. runs on one rank in this build (transfer_mts_bergs is not implemented)";
   else if (pin->mts && (!pin->interactive_icebergs_on || pin->footloose)) unsupported = "mts=.true. needs interactive_icebergs_on and no footloose";
   else if (pin->mts && pin->halo < 3) unsupported = "mts=.true. needs halo >= 3 (3x3 A-grid stencil of the ocean depth)";
-  else if (pin->mts && pin->skip_first_outer_mts_step) unsupported = "skip_first_outer_mts_step is not implemented";
   else if (pin->dem && !pin->save_bond_forces) unsupported = "dem needs save_bond_forces=.true. (the reference default, F:53): pair forces are evaluated once and stored on both half-bonds";
   else if (pin->contact_distance > 0. && pin->halo - 1 < 1) unsupported = "contact_distance>0 needs halo >= 2";
   else if (pin->iceberg_bonds_on && !pin->interactive_icebergs_on) unsupported = "iceberg_bonds_on needs interactive_icebergs_on";
@@ -684,6 +697,7 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
     h->mp.break_bonds_on_sub_steps = q->break_bonds_on_sub_steps; h->mp.fracture_criterion_stress = q->fracture_criterion_stress;
     h->mp.use_broken_bonds_for_substep_contact = q->use_broken_bonds_for_substep_contact; h->mp.dem_beam_test = q->dem_beam_test;
     h->mp.no_frac_first_ts = q->no_frac_first_ts;
+    h->skip_first_outer_mts_step = q->skip_first_outer_mts_step;
   }
   // F:1113-1118
   if ((!q->grid_is_latlon) && (q->Lx == 360.)) q->Lx = -1.;
@@ -869,6 +883,7 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   memset(&b, 0, sizeof(b));
   b.capacity = h->capacity;
   int ncols = q->dem ? (int)C_NDEM : q->mts ? (int)C_NMTS : q->interactive_icebergs_on ? (int)C_NINTER : (int)C_NBASE;
+  h->rec = make_rec_layout(ncols, (q->interactive_icebergs_on && q->iceberg_bonds_on) ? q->max_bonds : 0, q->dem ? 1 : 0, q->mts ? 1 : 0);
   for (int c = 0; c < ncols; c++) CK(cudaMalloc(&b.f64[c], sizeof(double) * h->capacity));
   if (q->mts) {
     for (int c = C_NINTER; c < ncols; c++) CK(cudaMemsetAsync(b.f64[c], 0, sizeof(double) * h->capacity, h->stream));
@@ -940,8 +955,12 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
     CK(cudaMemsetAsync(b.conglom_id, 0, sizeof(int32_t) * h->capacity, h->stream));
     CK(cudaMalloc(&b.n_bonds, sizeof(int32_t) * h->capacity));
     CK(cudaMemsetAsync(b.n_bonds, 0, sizeof(int32_t) * h->capacity, h->stream));
+    for (int k = 0; k < 2; k++) {
+      CK(cudaMalloc(&h->spare_aux[k], sizeof(int32_t) * h->capacity));
+      CK(cudaMemsetAsync(h->spare_aux[k], 0, sizeof(int32_t) * h->capacity, h->stream));
+    }
     CK(cudaMalloc(&h->d_changed, sizeof(int)));
-    h->ghost_rec_w = PACK_W + 3 * b.max_bonds;
+    h->ghost_rec_w = h->rec.w;
     h->ghost_cap = std::max<long long>(4096, h->capacity / 2);
     CK(cudaMalloc(&h->gsend, sizeof(double) * h->ghost_rec_w * h->ghost_cap));
     CK(cudaMalloc(&h->grecv, sizeof(double) * h->ghost_rec_w * h->ghost_cap));
@@ -966,9 +985,10 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
     }
     CK(cudaEventCreateWithFlags(&h->ev_kstep, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_xdone, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_zero, cudaEventDisableTiming));
     CK(cudaMalloc(&h->leaver_dest, sizeof(int32_t) * b.leaver_cap));
-    CK(cudaMalloc(&h->sendbuf, sizeof(double) * (PACK_W + 3 * (q->iceberg_bonds_on ? q->max_bonds : 0)) * h->xbuf_cap));
-    CK(cudaMalloc(&h->recvbuf, sizeof(double) * (PACK_W + 3 * (q->iceberg_bonds_on ? q->max_bonds : 0)) * h->xbuf_cap));
+    CK(cudaMalloc(&h->sendbuf, sizeof(double) * h->rec.w * h->xbuf_cap));
+    CK(cudaMalloc(&h->recvbuf, sizeof(double) * h->rec.w * h->xbuf_cap));
     CK(cudaMalloc(&h->d_send_counts, sizeof(int32_t) * nr));
     CK(cudaMalloc(&h->d_cursor, sizeof(int32_t) * nr));
     CK(cudaMalloc(&h->d_offsets, sizeof(int32_t) * nr));
@@ -1029,6 +1049,7 @@ extern "C" int32_t kid_end(kid_t** hp) {
   for (auto p : h->spare_f64) cudaFree(p);
   cudaFree(h->spare_id);
   for (auto p : h->spare_i32) cudaFree(p);
+  for (auto p : h->spare_aux) cudaFree(p);
   cudaFree(h->alt_bond_other_id); cudaFree(h->alt_bond_other_ine); cudaFree(h->alt_bond_other_jne); cudaFree(h->alt_bond_broken);
   cudaFree(h->alt_bond_length);
   for (auto p : h->alt_bond_dem) cudaFree(p);
@@ -1036,11 +1057,12 @@ extern "C" int32_t kid_end(kid_t** hp) {
   cudaFree(h->scan_sums); cudaFree(h->scan_total); cudaFree(h->dcnt); cudaFree(h->dflags);
   cudaFreeHost(h->hcnt); cudaFreeHost(h->hflags);
   for (int k = 0; k < BD_N; k++) cudaFree(h->b.bond_dem[k]);
-  cudaFree(h->b.bond_broken); cudaFree(h->b.n_bonds); cudaFree(h->dsums);
+  cudaFree(h->b.bond_broken); cudaFree(h->b.n_bonds); cudaFree(h->dsums); cudaFree(h->mts_bbox);
   cudaFree(h->leaver_lists[0]); cudaFree(h->leaver_lists[1]); cudaFree(h->leaver_counts);
   if (h->xstream) cudaStreamDestroy(h->xstream);
   if (h->ev_kstep) cudaEventDestroy(h->ev_kstep);
   if (h->ev_xdone) cudaEventDestroy(h->ev_xdone);
+  if (h->ev_zero) cudaEventDestroy(h->ev_zero);
   cudaFree(h->leaver_dest); cudaFree(h->sendbuf); cudaFree(h->recvbuf);
   cudaFree(h->d_send_counts); cudaFree(h->d_cursor); cudaFree(h->d_offsets); cudaFree(h->d_all_counts);
   if (h->h_all_counts) cudaFreeHost(h->h_all_counts);
@@ -1164,8 +1186,12 @@ static int sort_bergs(kid_t* h) {
     uint8_t** u8[2] = {&b.flags, &b.halo_code};
     for (int q = 0; q < 3; q++) { a.i32_src[q] = *i32[q]; a.i32_dst[q] = h->spare_i32[q]; }
     for (int q = 0; q < 2; q++) { a.u8_src[q] = *u8[q]; a.u8_dst[q] = h->spare_u8[q]; }
-    for (int q = 0; q < 2; q++) { a.aux_src[q] = nullptr; a.aux_dst[q] = nullptr; }
+    // conglomerate labels and bond counts travel with their berg (the MTS transfer reads the labels of the last
+    // set_conglom_ids after a re-sort)
+    int32_t** aux[2] = {&b.conglom_id, &b.n_bonds};
+    for (int q = 0; q < 2; q++) { a.aux_src[q] = h->spare_aux[q] ? *aux[q] : nullptr; a.aux_dst[q] = h->spare_aux[q]; }
     LAUNCH(h, k_gather_misc, ns, 256, a, h->perm, n_new, ns);
+    for (int q = 0; q < 2; q++) if (h->spare_aux[q] && *aux[q]) std::swap(*aux[q], h->spare_aux[q]);
     std::swap(b.id, h->spare_id);
     for (int q = 0; q < 3; q++) std::swap(*i32[q], h->spare_i32[q]);
     for (int q = 0; q < 2; q++) std::swap(*u8[q], h->spare_u8[q]);
@@ -1199,14 +1225,108 @@ static int sort_bergs(kid_t* h) {
 }
 
 
+static void scan_i32(kid_t* h, const int32_t* in, int32_t* out, int32_t* sums, long long n, int32_t* total);
+
 // ------------------------------------------------------- ghosts and bonds
 // update_halo_icebergs F:1800-2131: the halo copies are dropped and rebuilt from the owners'
 // current state; a copy goes straight to each of the 8 neighbours whose halo covers the berg's
 // cell (the reference relays corners through the E/W neighbour, F:1976-2006).
+static int set_conglom_ids(kid_t* h);
+static int sort_bergs(kid_t* h);
+// the cell box of every conglomerate (labels of set_conglom_ids) for the next transfer_mts_bergs
+static int mts_measure_boxes(kid_t* h) {
+  const bool cyc = h->d.cyclic_x && h->p.Lx > 0.;
+  if (h->d.nranks == 1 && !cyc) return KID_OK;
+  if (!h->mts_bbox) CK(cudaMalloc(&h->mts_bbox, sizeof(int32_t) * 4 * (h->capacity + 1)));
+  const long long ns = h->n_slots, nb = ns + 1;
+  LAUNCH(h, k_mts_bbox_init, nb, 256, h->mts_bbox, nb);
+  LAUNCH(h, k_mts_bbox, ns, 256, h->g, h->b, ns, h->mts_bbox, nb);
+  h->mts_bbox_n = nb;
+  h->mts_bbox_valid = 1;
+  return KID_OK;
+}
+
+// transfer_mts_bergs F:2136-2216 after the halos were cleared: see the end of kid_mts.cuh
+static int rebuild_ghosts_mts(kid_t* h) {
+  const int nr = h->d.nranks, me = h->d.rank;
+  const bool cyc = h->d.cyclic_x && h->p.Lx > 0.;
+  if (nr == 1 && !cyc) return KID_OK;
+  if (!h->mts_bbox_valid) {
+    // first transfer (icebergs_init I:150-167): no conglomerate labels yet -- label what this rank owns
+    int rc0 = sort_bergs(h);
+    if (rc0) return rc0;
+    if (h->b.max_bonds > 0) { CellTable ct{h->cell_start, h->cell_count}; LAUNCH(h, k_connect_bonds, h->n_slots, 128, h->g, h->b, ct, h->dcnt, h->n_slots); }
+    CK(cudaMemsetAsync(&h->dcnt->error_flags, 0, sizeof(unsigned int), h->stream));      // (partners on other ranks are not here yet)
+    rc0 = set_conglom_ids(h);
+    if (rc0) return rc0;
+    rc0 = mts_measure_boxes(h);
+    if (rc0) return rc0;
+  }
+  const long long ns = h->n_slots;
+  const long long w = h->rec.w;
+  // every owned berg, packed in slot order
+  CK(cudaMemsetAsync(h->d_gcounts, 0, sizeof(int32_t) * 9, h->stream));
+  LAUNCH(h, k_mts_owned_flags, ns, 256, h->b.flags, ns, h->sort_keys[0]);
+  if (ns > 0) scan_i32(h, h->sort_keys[0], h->sort_vals[0], h->radix_sums, ns, h->d_gcounts);
+  int rc = comm_allgather_counts(h, h->d_gcounts, h->h_all_counts, 1);
+  if (rc) return rc;
+  const long long n_own = h->h_all_counts[me];
+  long long n_others = 0;
+  for (int q = 0; q < nr; q++) if (q != me) n_others += h->h_all_counts[q];
+  if (n_own > h->ghost_cap || n_others > h->ghost_cap) return fail_fatal(h, KID_ERR_CAPACITY, "kid: ghost buffer capacity exceeded (transfer_mts_bergs)");
+  LAUNCH(h, k_mts_pack_all, ns, 128, h->b, ns, h->sort_keys[0], h->sort_vals[0], h->gsend, h->rec, h->mts_bbox, h->mts_bbox_n, cyc ? h->d.gni : 0);
+  std::vector<XMsg> sends, recvs;
+  long long off = 0;
+  for (int q = 0; q < nr; q++) {
+    if (q == me) continue;
+    if (n_own > 0) sends.push_back({q, 300, h->gsend, n_own * w});
+    const long long c = h->h_all_counts[q];
+    if (c > 0) recvs.push_back({q, 300, h->grecv + (size_t)off * w, c * w});
+    off += c;
+  }
+  rc = comm_exchange(h, sends, recvs);
+  if (rc) return rc;
+  // which periodic images a rank keeps: those of conglomerates whose box reaches its halo + the contact cells
+  // (+ 2 cells: the boxes date from the last labelling, bergs have moved a step since)
+  const int reach = h->p.halo + std::max(h->p.contact_cells_lon, h->p.contact_cells_lat) + 2;
+  const int nimg = cyc ? 3 : 1;
+  const long long n_new = (cyc ? n_own * 3 : 0) + n_others * nimg;
+  if (ns + n_new > h->capacity) return fail_fatal(h, KID_ERR_CAPACITY, "kid: berg store capacity exceeded by conglomerate copies (transfer_mts_bergs)");
+  long long s0 = ns;
+  if (cyc && n_own > 0) {
+    LAUNCH(h, k_mts_unpack_images, n_own * 3, 128, h->g, h->b, h->dp, h->dcnt, h->gsend, n_own, s0, h->rec, 3, 1, reach);
+    s0 += n_own * 3;
+  }
+  if (n_others > 0) LAUNCH(h, k_mts_unpack_images, n_others * nimg, 128, h->g, h->b, h->dp, h->dcnt, h->grecv, n_others, s0, h->rec, nimg, 0, reach);
+  if (n_new > 0) {
+    h->n_slots = ns + n_new;
+    CK(cudaStreamSynchronize(h->stream));
+    h->h_nslots[0] = (unsigned long long)h->n_slots;
+    CK(cudaMemcpyAsync(&h->dcnt->n_slots, h->h_nslots, sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
+    h->tables_valid = 0;
+  }
+  return KID_OK;
+}
+
+// after set_conglom_ids: mts_remove_unused_bergs F:2736
+static int mts_prune(kid_t* h, bool* pruned) {
+  *pruned = false;
+  const bool cyc = h->d.cyclic_x && h->p.Lx > 0.;
+  if ((h->d.nranks == 1 && !cyc) || !h->p.remove_unused_bergs) return KID_OK;
+  const long long ns = h->n_slots;
+  CK(cudaMemsetAsync(h->d_changed, 0, sizeof(int), h->stream));
+  CellTable ct{h->cell_start, h->cell_count};
+  LAUNCH(h, k_mts_prune, ns, 128, h->g, h->b, h->dp, ct, ns, h->d_changed);
+  CK(cudaMemcpyAsync(h->h_totals, h->d_changed, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *pruned = h->h_totals[0] > 0;
+  return KID_OK;
+}
+
 static int rebuild_ghosts(kid_t* h) {
   const int me = h->d.rank;
   LAUNCH(h, k_clear_halo, h->n_slots, 256, h->b.flags, h->n_slots);
-  if (h->p.mts) return KID_OK;      // one rank, no copies through the cyclic seam (transfer_mts_bergs F:2144 step 1 only)
+  if (h->p.mts) return rebuild_ghosts_mts(h);      // transfer_mts_bergs F:2136
   GhostPlan gp;
   for (int k = 0; k < 9; k++) gp.nbr[k] = h->nbr[k];
   gp.hw = h->p.halo; gp.isc = h->d.isc; gp.iec = h->d.iec; gp.jsc = h->d.jsc; gp.jec = h->d.jec;
@@ -1233,15 +1353,15 @@ static int rebuild_ghosts(kid_t* h) {
     if (c > 0) recvs.push_back({src, k, h->grecv + (size_t)n_recv * w, c * w});
     n_recv += c;
   }
-  if (n_send > h->ghost_cap || n_recv > h->ghost_cap) return fail(h, KID_ERR_CAPACITY, "kid: ghost buffer capacity exceeded");
-  if (h->n_slots + n_recv > h->capacity) return fail(h, KID_ERR_CAPACITY, "kid: berg store capacity exceeded by halo copies");
+  if (n_send > h->ghost_cap || n_recv > h->ghost_cap) return fail_fatal(h, KID_ERR_CAPACITY, "kid: ghost buffer capacity exceeded");
+  if (h->n_slots + n_recv > h->capacity) return fail_fatal(h, KID_ERR_CAPACITY, "kid: berg store capacity exceeded by halo copies");
   CK(cudaMemcpyAsync(h->d_goffsets, off, sizeof(off), cudaMemcpyHostToDevice, h->stream));
-  if (n_send > 0) LAUNCH(h, k_ghost_pack, h->n_slots, 128, gp, h->b, h->n_slots, h->d_goffsets, h->d_gcursor, h->gsend, w);
+  if (n_send > 0) LAUNCH(h, k_ghost_pack, h->n_slots, 128, gp, h->b, h->n_slots, h->d_goffsets, h->d_gcursor, h->gsend, h->rec);
   CK(cudaStreamSynchronize(h->stream));     // off[] is a stack array
   rc = comm_exchange(h, sends, recvs);
   if (rc) return rc;
   if (n_recv > 0) {
-    LAUNCH(h, k_ghost_unpack, n_recv, 128, h->g, h->b, h->dp, h->dcnt, h->grecv, n_recv, h->n_slots, w);
+    LAUNCH(h, k_ghost_unpack, n_recv, 128, h->g, h->b, h->dp, h->dcnt, h->grecv, n_recv, h->n_slots, h->rec);
     h->n_slots += n_recv;
     unsigned long long nn = (unsigned long long)h->n_slots;
     CK(cudaMemcpyAsync(&h->dcnt->n_slots, &nn, sizeof(nn), cudaMemcpyHostToDevice, h->stream));
@@ -1279,12 +1399,22 @@ static int refresh_interactive_state(kid_t* h) {
   if (h->p.Lx > 0. && edge) LAUNCH(h, k_update_latlon, h->n_slots, 128, h->g, h->b, h->dp, h->dcnt, h->n_slots);
   rc = sort_bergs(h);
   if (rc) return rc;
-  if (h->b.max_bonds > 0) {
-    CellTable ct{h->cell_start, h->cell_count};
-    LAUNCH(h, k_connect_bonds, h->n_slots, 128, h->g, h->b, ct, h->dcnt, h->n_slots);
-    if (h->p.mts) LAUNCH(h, k_assign_n_bonds, h->n_slots, 128, h->b, h->n_slots, h->p.use_broken_bonds_for_substep_contact ? 1 : 0);
+  for (int pass = 0; pass < 2; pass++) {
+    if (h->b.max_bonds > 0) {
+      CellTable ct{h->cell_start, h->cell_count};
+      LAUNCH(h, k_connect_bonds, h->n_slots, 128, h->g, h->b, ct, h->dcnt, h->n_slots);
+      if (h->p.mts) LAUNCH(h, k_assign_n_bonds, h->n_slots, 128, h->b, h->n_slots, h->p.use_broken_bonds_for_substep_contact ? 1 : 0);
+    }
+    rc = set_conglom_ids(h);
+    if (rc || !h->p.mts) return rc;
+    // transfer_mts_bergs, last part (F:2199-2202): copies nobody needs are dropped; the store is then compacted again
+    bool pruned = false;
+    if (pass == 0) { rc = mts_prune(h, &pruned); if (rc) return rc; }
+    if (!pruned) return mts_measure_boxes(h);
+    rc = sort_bergs(h);
+    if (rc) return rc;
   }
-  return set_conglom_ids(h);
+  return KID_OK;
 }
 
 extern "C" int32_t kid_sort_bergs(kid_t* h) {
@@ -1300,6 +1430,14 @@ extern "C" int32_t kid_set_sort_phase(kid_t* h, int32_t interval, int32_t steps_
   return KID_OK;
 }
 extern "C" int64_t kid_sorts_done(kid_t* h) { return h ? h->sorts_done : 0; }
+extern "C" int64_t kid_last_slow_count(kid_t* h) {
+  if (!h || !h->slow_count || !h->fast_launched) return -1;
+  cudaSetDevice(h->d.device);
+  unsigned long long n = 0;
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
+  if (cudaMemcpy(&n, h->slow_count, sizeof(n), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int64_t)n;
+}
 
 // ---------------------------------------------------------- berg columns
 namespace {
@@ -1445,8 +1583,16 @@ extern "C" int32_t kid_get_bergs(kid_t* h, int64_t* n, KidBergColumns* c, int32_
     CK(cudaMemcpy(ti.data(), ic.src, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost));
     for (int64_t k = 0; k < nk; k++) ic.dst[k] = ti[(size_t)keep[k]];
   }
-  if (c->n_bonds) for (int64_t k = 0; k < nk; k++) c->n_bonds[k] = 0;
-  if (c->conglom_id) for (int64_t k = 0; k < nk; k++) c->conglom_id[k] = 0;
+  // n_bonds (assign_n_bonds F:4617: the bonds the berg carries) and conglom_id (set_conglom_ids F:2601; interactive runs)
+  struct AC { int32_t* dst; const int32_t* src; } acs[] = {{c->n_bonds, h->b.max_bonds > 0 ? h->b.n_bonds : nullptr}, {c->conglom_id, h->b.conglom_id}};
+  for (int q = 0; q < 2; q++) {
+    if (!acs[q].dst) continue;
+    if (!acs[q].src) { for (int64_t k = 0; k < nk; k++) acs[q].dst[k] = 0; continue; }
+    if (q == 0 && !h->p.mts && ns > 0) LAUNCH(h, k_assign_n_bonds, ns, 128, h->b, ns, 0);      // (the MTS scheme keeps it current)
+    CK(cudaMemcpyAsync(ti.data(), acs[q].src, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int64_t k = 0; k < nk; k++) acs[q].dst[k] = ti[(size_t)keep[k]];
+  }
   if (c->id) {
     std::vector<int64_t> tl((size_t)ns);
     CK(cudaMemcpy(tl.data(), h->b.id, sizeof(int64_t) * ns, cudaMemcpyDeviceToHost));
@@ -1739,7 +1885,7 @@ static int mts_first_visit(kid_t* h) {
     LAUNCH(h, k_dem_tests_init, ns, 256, h->b, ns);
     CK(cudaMemcpy(a.data(), h->b.f64[C_LON], sizeof(double) * ns, cudaMemcpyDeviceToHost));
     double lo = 1.7976931348623157e308, hi = -1.7976931348623157e308;
-    for (long long s = 0; s < ns; s++) if (fl[s] & BF_ALIVE) { lo = std::min(lo, a[s]); hi = std::max(hi, a[s]); }
+    for (long long s = 0; s < ns; s++) if ((fl[s] & BF_ALIVE) && !(fl[s] & BF_HALO)) { lo = std::min(lo, a[s]); hi = std::max(hi, a[s]); }
     h->mp.dem_tests_start_lon = lo; h->mp.dem_tests_end_lon = hi;
   }
   if (need_lw) {
@@ -1774,38 +1920,44 @@ static int evolve_mts(kid_t* h) {
   if (ns <= 0) return KID_OK;
   CellTable ct{h->cell_start, h->cell_count};
   const int fc = p.force_convergence ? 1 : 0;
-  // part 1: slow forces and collisions over the long step, iterated until the velocity change is small
-  int ii = 0;
-  bool finished = false, last_iter = !fc, had_collision = false;
-  double usum = 0.;
-  while (!finished) {
-    ii++;
-    CK(cudaMemsetAsync(h->dsums, 0, sizeof(MtsSums), h->stream));
-    LAUNCH(h, k_mts_part1, ns, 128, h->g, h->b, h->dp, h->mp, ct, h->dcnt, h->dsums, ns, ii);
-    MtsSums sm{0., 0., 0., 0u, 0u};
-    if (fc) {
-      if (!last_iter) { int rc = mts_read_sums(h, &sm); if (rc) return rc; }
-      had_collision = had_collision || sm.had_collision;
-      if (ii == 1) usum = sm.usum;
-    }
-    bool this_last = last_iter;
-    if (fc && !last_iter && had_collision) {
-      if (ii > 1) {
-        double denom = sqrt(usum) + sqrt(sm.usum1);
-        double normchange = denom > 0 ? 2.0 * sqrt(sm.usum2) / denom : 0.0;
-        if (normchange < p.convergence_tolerance) last_iter = true;
-      }
-      usum = sm.usum1;
-    } else finished = true;
-    if (last_iter) finished = true;
-    // the reference refreshes *_old with the last_iter flag as it stood before this pass's norm test (I:6709-6720)
-    if (fc) LAUNCH(h, k_mts_part1_old, ns, 256, h->b, ns, this_last ? 1 : 0);
-    if (ii > 10000) return fail(h, KID_ERR_STATE, "kid: MTS force_convergence (part 1) did not converge in 10000 passes");
-  }
-  h->mts_outer_iters = ii;
   const bool dem = p.dem != 0;
-  if (dem && !p.break_bonds_on_sub_steps) LAUNCH(h, k_dem_break_bonds, ns, 256, h->b, h->mp, ns);     // I:6738
-  LAUNCH(h, k_mts_part2, ns, 256, h->b, h->dp, ns, fc);
+  if (h->skip_first_outer_mts_step) {
+    // skip_first_outer_mts_step (F:62, I:6661, I:6772-6775): the first step after a restart does the sub-steps only
+    h->skip_first_outer_mts_step = 0;
+    h->mts_outer_iters = 0;
+  } else {
+    // part 1: slow forces and collisions over the long step, iterated until the velocity change is small
+    int ii = 0;
+    bool finished = false, last_iter = !fc, had_collision = false;
+    double usum = 0.;
+    while (!finished) {
+      ii++;
+      CK(cudaMemsetAsync(h->dsums, 0, sizeof(MtsSums), h->stream));
+      LAUNCH(h, k_mts_part1, ns, 128, h->g, h->b, h->dp, h->mp, ct, h->dcnt, h->dsums, ns, ii);
+      MtsSums sm{0., 0., 0., 0u, 0u};
+      if (fc) {
+        if (!last_iter) { int rc = mts_read_sums(h, &sm); if (rc) return rc; }
+        had_collision = had_collision || sm.had_collision;
+        if (ii == 1) usum = sm.usum;
+      }
+      bool this_last = last_iter;
+      if (fc && !last_iter && had_collision) {
+        if (ii > 1) {
+          double denom = sqrt(usum) + sqrt(sm.usum1);
+          double normchange = denom > 0 ? 2.0 * sqrt(sm.usum2) / denom : 0.0;
+          if (normchange < p.convergence_tolerance) last_iter = true;
+        }
+        usum = sm.usum1;
+      } else finished = true;
+      if (last_iter) finished = true;
+      // the reference refreshes *_old with the last_iter flag as it stood before this pass's norm test (I:6709-6720)
+      if (fc) LAUNCH(h, k_mts_part1_old, ns, 256, h->b, ns, this_last ? 1 : 0);
+      if (ii > 10000) return fail(h, KID_ERR_STATE, "kid: MTS force_convergence (part 1) did not converge in 10000 passes");
+    }
+    h->mts_outer_iters = ii;
+    if (dem && !p.break_bonds_on_sub_steps) LAUNCH(h, k_dem_break_bonds, ns, 256, h->b, h->mp, ns);     // I:6738
+    LAUNCH(h, k_mts_part2, ns, 256, h->b, h->dp, ns, fc);
+  }
   // part 3: fast sub-steps, bonded interactions only
   const double dtf = h->mp.dt_fast;
   const bool iterate = fc && !p.explicit_inner_mts;
@@ -1893,6 +2045,7 @@ static void launch_step(kid_t* h, long long s0, long long s1, bool main_launch =
     if (h->scatter_dense) { LAUNCH(h, (k_step_fast<true>), n, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s1, s0, sl); }
     else { LAUNCH(h, (k_step_fast<false>), n, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s1, s0, sl); }
     k_step_slow<<<2 * h->num_sms, KID_BLOCK, 0, h->stream>>>(h->g, h->b, h->dp, h->dcnt, sl); h->launches++;
+    h->fast_launched = 1;
     return;
   }
   if (!FL && !DG && lean_config(h)) {
@@ -1923,6 +2076,8 @@ static int finish_deferred_exchange(kid_t* h) {
     if (rc) break;
     if (n_recv > 0) {
       const long long s1 = s0 + n_recv;
+      // the arrivals' melt lands in this step's flux fields: after the main stream zeroed them
+      if (h->ev_zero_recorded && cudaStreamWaitEvent(h->xstream, h->ev_zero, 0) != cudaSuccess) { rc = fail(h, KID_ERR_CUDA, "cudaStreamWaitEvent failed"); break; }
       if (DG) { LAUNCH(h, (k_thermo_range<false, true>), n_recv, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s0, s1, 0); }
       else { LAUNCH(h, (k_thermo_range<false, false>), n_recv, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s0, s1, 0); }
       launch_step<false, DG>(h, s0, s1);
@@ -1990,7 +2145,7 @@ static int step_core(kid_t* h) {
     CK(cudaMemcpyAsync(&h->hcnt->n_slots, &h->dcnt->n_slots, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     long long ns = (long long)h->hcnt->n_slots;
-    if (ns > h->capacity) return fail(h, KID_ERR_CAPACITY, "kid: berg store capacity exceeded by calving");
+    if (ns > h->capacity) return fail_fatal(h, KID_ERR_CAPACITY, "kid: berg store capacity exceeded by calving");
     if (ns != h->n_slots) h->tables_valid = 0;
     h->dirty_appended += ns - h->n_slots;
     h->n_slots = ns;
@@ -2069,7 +2224,7 @@ static int step_core(kid_t* h) {
     if (rc) return rc;
     if (n_recv > 0) {
       long long s0 = h->n_slots, s1 = h->n_slots + n_recv;
-      if (fl) { /* thermodynamics of every berg follows footloose_calving below */ }
+      if (fl || mts) { /* thermodynamics of every owned berg follows below (footloose_calving / the MTS sequence I:5497) */ }
       else if (h->p.melt_diagnostics) { LAUNCH(h, (k_thermo_range<false, true>), n_recv, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s0, s1, 0); }
       else { LAUNCH(h, (k_thermo_range<false, false>), n_recv, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s0, s1, 0); }
       h->n_slots = s1;
@@ -2092,7 +2247,7 @@ static int step_core(kid_t* h) {
     CK(cudaMemcpyAsync(&h->hcnt->n_slots, &h->dcnt->n_slots, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     long long ns = (long long)h->hcnt->n_slots;
-    if (ns > h->capacity) return fail(h, KID_ERR_CAPACITY, "kid: berg store capacity exceeded by footloose calving");
+    if (ns > h->capacity) return fail_fatal(h, KID_ERR_CAPACITY, "kid: berg store capacity exceeded by footloose calving");
     if (ns != h->n_slots) { h->tables_valid = 0; h->n_slots = ns; }
   }
   CK(cudaEventRecord(h->ev[T_SORT], s));
@@ -2208,6 +2363,7 @@ extern "C" int32_t kid_step_resident(kid_t* h, int32_t nsteps, int32_t year, dou
   CK(cudaEventRecord(h->ev[T_NPHASE], h->stream));
   for (int s = 0; s < nsteps; s++) {
     zero_flux_fields(h, true);
+    if (h->ev_zero) { CK(cudaEventRecord(h->ev_zero, h->stream)); h->ev_zero_recorded = 1; }
     long long before = h->n_slots;
     // the migration of step s may be deferred into step s+1 (its arrivals' melt then lands in the flux fields of
     // step s+1): never for the last two steps, whose flux fields and berg state are what the caller sees
@@ -2289,7 +2445,7 @@ extern "C" int32_t kid_get_grid_field(kid_t* h, int32_t field_id, double* out) {
   cudaSetDevice(h->d.device);
   const double* f = field_ptr(h, field_id);
   if (!f) {
-    if (field_id >= 0 && field_id < KID_FLD_COUNT_) {   // spreading-row fields: not produced by this build
+    if (field_id >= 0 && field_id < KID_FLD_COUNT_) {   // a known id without a device field in this configuration: zeros
       memset(out, 0, sizeof(double) * h->n2);
       return KID_OK;
     }

@@ -78,6 +78,74 @@ enum PackSlot : int {
   PACK_W
 };
 
+// What follows the PACK_W words of a record (pack_berg_into_buffer2 F:3250-3354: buffer_width grows with max_bonds,
+// mts and dem, F:1266-1292): 3 words per half-bond (other id, other ine/jne, length); with mts the environment cache
+// and the fast accelerations (+ ang_vel, ang_accel, rot with dem) = the columns C_NINTER..ncols-1; with dem the bond
+// history and saved pair forces (BD_N words) and the broken flag per half-bond.  *_old columns do not travel: the
+// receiver resets them from the current state (F:3574-3577).
+struct RecLayout {
+  int32_t ncols;      // allocated fp64 columns: C_NBASE, C_NINTER, C_NMTS or C_NDEM
+  int32_t mb;         // max_bonds
+  int32_t dem;
+  int32_t w;          // words per record
+  int32_t off_bonds, off_extra, off_bdem;
+  int32_t off_bbox;   // mts: 2 words, the cell bounding box of the berg's conglomerate (transfer_mts_bergs); else -1
+};
+__host__ __device__ __forceinline__ RecLayout make_rec_layout(int ncols, int mb, int dem, int mts) {
+  RecLayout L;
+  L.ncols = ncols; L.mb = mb; L.dem = dem;
+  L.off_bonds = PACK_W;
+  L.off_extra = L.off_bonds + 3 * mb;
+  L.off_bdem = L.off_extra + (ncols > (int)C_NINTER ? ncols - (int)C_NINTER : 0);
+  L.w = L.off_bdem + (dem ? (BD_N + 1) * mb : 0);
+  L.off_bbox = -1;
+  if (mts) { L.off_bbox = L.w; L.w += 2; }
+  return L;
+}
+// everything of the berg in slot s except the cell index / flags words (the callers differ there)
+__device__ __forceinline__ void pack_berg(const DevBergs& b, long long s, double* __restrict__ rec, const RecLayout& L) {
+#pragma unroll
+  for (int c = 0; c < C_NBASE; c++) rec[PK_F64_0 + c] = b.f64[c][s];
+  rec[PK_ID] = __longlong_as_double(b.id[s]);
+  for (int k = 0; k < L.mb; k++) {          // the bonds travel with the berg, F:3336-3354
+    long long slot = (long long)k * b.capacity + s;
+    double* br = rec + L.off_bonds + 3 * k;
+    br[0] = __longlong_as_double(b.bond_other_id[slot]);
+    br[1] = __longlong_as_double(((long long)(unsigned)b.bond_other_ine[slot] << 32) | (unsigned)b.bond_other_jne[slot]);
+    br[2] = b.bond_length[slot];
+    if (L.dem) {
+      double* bd = rec + L.off_bdem + (BD_N + 1) * k;
+      for (int q = 0; q < BD_N; q++) bd[q] = b.bond_dem[q][slot];
+      bd[BD_N] = (double)b.bond_broken[slot];
+    }
+  }
+  for (int c = C_NINTER; c < L.ncols; c++) rec[L.off_extra + (c - C_NINTER)] = b.f64[c][s];
+}
+__device__ __forceinline__ void unpack_berg(const DevBergs& b, long long s, const double* __restrict__ rec, const RecLayout& L) {
+#pragma unroll
+  for (int c = 0; c < C_NBASE; c++) b.f64[c][s] = rec[PK_F64_0 + c];
+  if (b.f64[C_UVEL_OLD]) {                  // F:3574-3577
+    b.f64[C_UVEL_OLD][s] = rec[PK_F64_0 + C_UVEL]; b.f64[C_VVEL_OLD][s] = rec[PK_F64_0 + C_VVEL];
+    b.f64[C_LON_OLD][s] = rec[PK_F64_0 + C_LON]; b.f64[C_LAT_OLD][s] = rec[PK_F64_0 + C_LAT];
+  }
+  b.id[s] = __double_as_longlong(rec[PK_ID]);
+  for (int k = 0; k < L.mb; k++) {
+    long long slot = (long long)k * b.capacity + s;
+    const double* br = rec + L.off_bonds + 3 * k;
+    b.bond_other_id[slot] = __double_as_longlong(br[0]);
+    long long oij = __double_as_longlong(br[1]);
+    b.bond_other_ine[slot] = (int)(oij >> 32); b.bond_other_jne[slot] = (int)(oij & 0xffffffffll);
+    b.bond_length[slot] = br[2];
+    b.bond_other_slot[slot] = -1;
+    if (L.dem) {
+      const double* bd = rec + L.off_bdem + (BD_N + 1) * k;
+      for (int q = 0; q < BD_N; q++) b.bond_dem[q][slot] = bd[q];
+      b.bond_broken[slot] = (int32_t)bd[BD_N];
+    }
+  }
+  for (int c = C_NINTER; c < L.ncols; c++) b.f64[c][s] = rec[L.off_extra + (c - C_NINTER)];
+}
+
 }  // namespace kid
 
 namespace kid {
@@ -132,7 +200,8 @@ __global__ void k_leaver_dest(const __grid_constant__ DevLayout L, const int32_t
 __global__ void k_pack_leavers(const __grid_constant__ DevLayout L, const __grid_constant__ DevBergs b, const int32_t* __restrict__ list,
                                const int32_t* __restrict__ dest, const unsigned long long* __restrict__ list_count,
                                int32_t list_cap, const int32_t* __restrict__ offsets /* [nranks] */,
-                               int32_t* __restrict__ cursor /* [nranks], zeroed */, double* __restrict__ sendbuf, int rec_w) {
+                               int32_t* __restrict__ cursor /* [nranks], zeroed */, double* __restrict__ sendbuf,
+                               const __grid_constant__ RecLayout RL) {
   long long n = (long long)*list_count;
   if (n > list_cap) n = list_cap;
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
@@ -142,18 +211,9 @@ __global__ void k_pack_leavers(const __grid_constant__ DevLayout L, const __grid
     b.flags[s] = 0;
     if (d < 0) continue;                     // left the model through an open boundary
     int pos = offsets[d] + atomicAdd(&cursor[d], 1);
-    double* rec = sendbuf + (size_t)pos * rec_w;
-#pragma unroll
-    for (int c = 0; c < C_NBASE; c++) rec[PK_F64_0 + c] = b.f64[c][s];
-    rec[PK_ID] = __longlong_as_double(b.id[s]);
-    for (int k = 0; k < b.max_bonds; k++) {          // the bonds travel with the berg, F:3336-3354
-      long long slot = (long long)k * b.capacity + s;
-      double* br = rec + PACK_W + 3 * k;
-      br[0] = __longlong_as_double(b.bond_other_id[slot]);
-      br[1] = __longlong_as_double(((long long)(unsigned)b.bond_other_ine[slot] << 32) | (unsigned)b.bond_other_jne[slot]);
-      br[2] = b.bond_length[slot];
-      b.bond_other_id[slot] = 0;
-    }
+    double* rec = sendbuf + (size_t)pos * RL.w;
+    pack_berg(b, s, rec, RL);
+    for (int k = 0; k < b.max_bonds; k++) b.bond_other_id[(long long)k * b.capacity + s] = 0;
     int ci = b.ine[s];       // the owner's own index of the cell: one period off when the berg crossed the seam
     if (L.cyclic_x && (ci < 1 || ci > L.gni)) ci = ((ci - 1) % L.gni + L.gni) % L.gni + 1;
     rec[PK_INE_JNE] = __longlong_as_double(((long long)(unsigned)ci << 32) | (unsigned)b.jne[s]);
@@ -168,29 +228,15 @@ __global__ void k_pack_leavers(const __grid_constant__ DevLayout L, const __grid
 // flagged BF_ARRIVAL: its thermodynamics of this step runs here (k_thermo_range).
 __global__ void k_unpack_arrivals(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
                                   const __grid_constant__ DevParams p, DevCounters* __restrict__ cnt,
-                                  const double* __restrict__ recvbuf, long long n_recv, long long s0, int rec_w) {
+                                  const double* __restrict__ recvbuf, long long n_recv, long long s0,
+                                  const __grid_constant__ RecLayout RL) {
   long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_recv) return;
   if (k == 0) cnt->n_slots = (unsigned long long)(s0 + n_recv);     // the append cursor moves past the arrivals
   long long s = s0 + k;
-  const double* rec = recvbuf + (size_t)k * rec_w;
-  for (int q = 0; q < b.max_bonds; q++) {
-    long long slot = (long long)q * b.capacity + s;
-    const double* br = rec + PACK_W + 3 * q;
-    b.bond_other_id[slot] = __double_as_longlong(br[0]);
-    long long oij = __double_as_longlong(br[1]);
-    b.bond_other_ine[slot] = (int)(oij >> 32); b.bond_other_jne[slot] = (int)(oij & 0xffffffffll);
-    b.bond_length[slot] = br[2];
-    b.bond_other_slot[slot] = -1;
-  }
-#pragma unroll
-  for (int c = 0; c < C_NBASE; c++) b.f64[c][s] = rec[PK_F64_0 + c];
+  const double* rec = recvbuf + (size_t)k * RL.w;
+  unpack_berg(b, s, rec, RL);
   double lon = rec[PK_F64_0 + C_LON], lat = rec[PK_F64_0 + C_LAT];
-  if (b.f64[C_UVEL_OLD]) {
-    b.f64[C_UVEL_OLD][s] = rec[PK_F64_0 + C_UVEL]; b.f64[C_VVEL_OLD][s] = rec[PK_F64_0 + C_VVEL];
-    b.f64[C_LON_OLD][s] = lon; b.f64[C_LAT_OLD][s] = lat;
-  }
-  b.id[s] = __double_as_longlong(rec[PK_ID]);
   long long ij = __double_as_longlong(rec[PK_INE_JNE]), yf = __double_as_longlong(rec[PK_YEAR_FLAGS]);
   int i = (int)(ij >> 32), j = (int)(ij & 0xffffffffll);
   b.start_year[s] = (int32_t)(yf >> 32);

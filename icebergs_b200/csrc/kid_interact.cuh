@@ -241,7 +241,7 @@ __global__ void k_ghost_count(const __grid_constant__ GhostPlan gp, const uint8_
 // pack_berg_into_buffer2 with halo_berg = 1 (F:1902-1905); bonds travel as (other_id, other ine/jne, length)
 __global__ void k_ghost_pack(const __grid_constant__ GhostPlan gp, const __grid_constant__ DevBergs b, long long n_slots,
                              const int32_t* __restrict__ offsets /* [9] */, int32_t* __restrict__ cursor /* [9] */,
-                             double* __restrict__ sendbuf, int rec_w) {
+                             double* __restrict__ sendbuf, const __grid_constant__ RecLayout RL) {
   long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_slots) return;
   uint8_t f = b.flags[s];
@@ -250,52 +250,31 @@ __global__ void k_ghost_pack(const __grid_constant__ GhostPlan gp, const __grid_
   for (int dir = 0; dir < 9; dir++) {
     if (dir == 4 || !ghost_goes(gp, dir, i, j)) continue;
     int pos = offsets[dir] + atomicAdd(&cursor[dir], 1);
-    double* rec = sendbuf + (size_t)pos * rec_w;
-    for (int c = 0; c < C_NBASE; c++) rec[PK_F64_0 + c] = b.f64[c][s];
-    rec[PK_ID] = __longlong_as_double(b.id[s]);
+    double* rec = sendbuf + (size_t)pos * RL.w;
+    pack_berg(b, s, rec, RL);
     // the copy's cell on the receiving side: one period away when the message crosses the cyclic seam
     int dx = dir % 3 - 1, ci = i;
     if (gp.cyclic_x) { if (dx > 0 && gp.iec == gp.gni) ci = i - gp.gni; else if (dx < 0 && gp.isc == 1) ci = i + gp.gni; }
     rec[PK_INE_JNE] = __longlong_as_double(((long long)(unsigned)ci << 32) | (unsigned)j);
     rec[PK_YEAR_FLAGS] = __longlong_as_double(((long long)(unsigned)b.start_year[s] << 32) | (unsigned)f);
-    for (int k = 0; k < b.max_bonds; k++) {
-      long long slot = (long long)k * b.capacity + s;
-      double* br = rec + PACK_W + 3 * k;
-      br[0] = __longlong_as_double(b.bond_other_id[slot]);
-      br[1] = __longlong_as_double(((long long)(unsigned)b.bond_other_ine[slot] << 32) | (unsigned)b.bond_other_jne[slot]);
-      br[2] = b.bond_length[slot];
-    }
   }
 }
 
 // unpack_berg_from_buffer2 F:3468 for halo copies: cell re-found, xi/yj recomputed, *_old = current
 __global__ void k_ghost_unpack(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
                                const __grid_constant__ DevParams p, DevCounters* __restrict__ cnt,
-                               const double* __restrict__ recvbuf, long long n_recv, long long s0, int rec_w) {
+                               const double* __restrict__ recvbuf, long long n_recv, long long s0,
+                               const __grid_constant__ RecLayout RL) {
   long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_recv) return;
   long long s = s0 + k;
-  const double* rec = recvbuf + (size_t)k * rec_w;
-  for (int c = 0; c < C_NBASE; c++) b.f64[c][s] = rec[PK_F64_0 + c];
+  const double* rec = recvbuf + (size_t)k * RL.w;
+  unpack_berg(b, s, rec, RL);
   double lon = rec[PK_F64_0 + C_LON], lat = rec[PK_F64_0 + C_LAT];
-  if (b.f64[C_UVEL_OLD]) {
-    b.f64[C_UVEL_OLD][s] = rec[PK_F64_0 + C_UVEL]; b.f64[C_VVEL_OLD][s] = rec[PK_F64_0 + C_VVEL];
-    b.f64[C_LON_OLD][s] = lon; b.f64[C_LAT_OLD][s] = lat;
-  }
-  b.id[s] = __double_as_longlong(rec[PK_ID]);
   long long ij = __double_as_longlong(rec[PK_INE_JNE]), yf = __double_as_longlong(rec[PK_YEAR_FLAGS]);
   int i = (int)(ij >> 32), j = (int)(ij & 0xffffffffll);
   b.start_year[s] = (int32_t)(yf >> 32);
   uint8_t f = (uint8_t)(yf & 0xff);
-  for (int q = 0; q < b.max_bonds; q++) {
-    long long slot = (long long)q * b.capacity + s;
-    const double* br = rec + PACK_W + 3 * q;
-    b.bond_other_id[slot] = __double_as_longlong(br[0]);
-    long long oij = __double_as_longlong(br[1]);
-    b.bond_other_ine[slot] = (int)(oij >> 32); b.bond_other_jne[slot] = (int)(oij & 0xffffffffll);
-    b.bond_length[slot] = br[2];
-    b.bond_other_slot[slot] = -1;
-  }
   // check_and_find_cell F:5973: the cell the sender named (already the periodic image when the copy
   // crossed the seam, k_ghost_pack), then its other images, then the scan
   bool found = false;
@@ -327,6 +306,7 @@ __global__ void k_update_latlon(const __grid_constant__ DevGrid g, const __grid_
   if (!(f & BF_ALIVE) || (f & BF_LEAVER)) return;
   int i = b.ine[s], j = b.jne[s];
   if (!cell_on_pe(g, i, j)) return;
+  if (p.mts && b.halo_code[s] >= 2) return;      // copies beyond the halo keep their coordinates (F:4992)
   double lon = b.f64[C_LON][s], lat = b.f64[C_LAT][s];
   double dlon = lon - b.f64[C_LON_OLD][s], dlat = lat - b.f64[C_LAT_OLD][s];
   double xi = b.f64[C_XI][s], yj = b.f64[C_YJ][s];

@@ -167,10 +167,11 @@ __device__ __forceinline__ int thermo_slot(const DevGrid& g, const DevBergs& b, 
                                            uint8_t flags, int i, int j, double xi, double yj, double uvel,
                                            double vvel, double M, double T, double W, double L, double mass_scaling,
                                            double mass_of_bits, double heat_density, Scatter& sc,
-                                           DevCounters* cnt) {
+                                           DevCounters* cnt, const EnvThermo* pre = nullptr) {
   const int cidx = gidx(g, i, j);
   EnvThermo e;
-  interp_thermo<LEAN>(g, p, cidx, xi, yj, e);
+  if (pre) e = *pre;                       // the caller interpolated already (k_step_fast's cached cell)
+  else interp_thermo<LEAN>(g, p, cidx, xi, yj, e);
   if ((e.uo != e.uo) || (e.vo != e.vo) || (e.ua != e.ua) || (e.va != e.va) || (e.sst != e.sst) || (e.cn != e.cn))
     atomicOr(&cnt->error_flags, 64u);
   if (e.rarea == 0.) { atomicOr(&cnt->error_flags, (unsigned)KID_DEVERR_GROUNDED); return TH_KEEP; }
@@ -406,7 +407,7 @@ k_step(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
 struct SlowList { uint32_t* slots; unsigned long long* count; long long cap; };
 
 #ifndef KID_FAST_MINBLOCKS
-#define KID_FAST_MINBLOCKS 6
+#define KID_FAST_MINBLOCKS 5
 #endif
 
 template <bool DENSE>
@@ -515,6 +516,11 @@ k_step_fast(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs 
       b.f64[C_XI][s] = xi; b.f64[C_YJ][s] = yj;
       b.ine[s] = i; b.jne[s] = j;
       // ---- thermodynamics I:2844-3300 at the new position
+#ifdef KID_FAST_BARRIER
+      // (compiler barrier: the corner records interp_flds gathered are gathered again here -- an L1 hit -- instead
+      // of being carried in registers, i.e. spilled, across the momentum solve)
+      asm volatile("" ::: "memory");
+#endif
       int outcome = thermo_slot<false, LEAN>(g, b, p, s, flags, i, j, xi, yj, uvel, vvel, M, T, W, L,
                                              b.f64[C_MASS_SCALING][s], b.f64[C_MASS_OF_BITS][s], b.f64[C_HEAT_DENSITY][s],
                                              sc, cnt);

@@ -9,7 +9,7 @@
 // kernel with one thread per berg; the sweeps of a sub-step are launched back to back on the handle's stream (the
 // convergence norms of force_convergence are the only host round trips).  Plain IEEE arithmetic: this is the
 // bonded-conglomerate path (hundreds to 1e5 sub-steps of a few thousand elements), launch-latency bound, not the
-// HBM-bound free-drift kernel.  One rank; no copies through the cyclic seam (kid_init refuses other layouts).
+// HBM-bound free-drift kernel.  Conglomerates that reach several ranks, or the cyclic seam: complete copies per rank, see the end of this file.
 #pragma once
 #include "kid_interact.cuh"
 
@@ -864,6 +864,15 @@ __global__ void k_mts_finish(const __grid_constant__ DevGrid g, const __grid_con
   // send_bergs_to_other_pes F:2997 on one rank: through the cyclic seam back into the tile, or out of the model
   if (i > g.iec || i < g.isc || j > g.jec || j < g.jsc) {
     int route = route_berg(g, p, lonn, latn, i, j, xi, yj, &cnt->error_flags, &cnt->n_wrapped);
+    if (route == 1) {       // to another rank: the exchange that follows packs it (send_bergs_to_other_pes F:2997)
+      b.ine[s] = i; b.jne[s] = j; b.f64[C_XI][s] = xi; b.f64[C_YJ][s] = yj;
+      b.flags[s] = flags | BF_LEAVER;
+      atomicAdd(&cnt->n_leavers, 1ull);
+      unsigned long long k = atomicAdd(b.leaver_count, 1ull);
+      if ((long long)k < b.leaver_cap) b.leaver_list[k] = (int32_t)s;
+      else atomicOr(&cnt->error_flags, (unsigned)KID_DEVERR_CAPACITY);
+      return;
+    }
     if (route != 0) { b.flags[s] = 0; return; }
   }
   b.ine[s] = i; b.jne[s] = j; b.f64[C_XI][s] = xi; b.f64[C_YJ][s] = yj;
@@ -905,4 +914,169 @@ __global__ void k_dem_tests_init(const __grid_constant__ DevBergs b, long long n
   b.f64[C_START_LON][s] = b.f64[C_LON][s]; b.f64[C_START_LAT][s] = b.f64[C_LAT][s];
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// transfer_mts_bergs F:2136-2216 (+ mts_pack_in_dir F:2219, mts_mark_and_pack_halo_and_congloms F:2386,
+// mts_pack_contact_bergs F:2457, mts_send_and_receive F:2834, mts_remove_unused_bergs F:2736): after an MTS step
+// every rank needs, besides the ordinary halo copies, a COMPLETE copy of every conglomerate that reaches its tile
+// (the sub-steps then run with no communication) and the bergs within contact distance of those conglomerates.
+// The reference finds them by walking bond lists recursively on the sender, direction by direction, twice.  Here:
+//   1. every rank packs ALL its owned bergs (k_mts_pack_all; populations of bonded runs are small) and the packs go
+//      to every rank (NVSwitch: one group of sends/receives, no relay);
+//   2. every record carries the cell bounding box of the berg's conglomerate (k_mts_bbox, from the labels of
+//      set_conglom_ids); the receiver keeps a periodic image of the berg when the image of that box reaches its halo
+//      or the contact cells around it (k_mts_unpack_images), so a conglomerate arrives whole or not at all: in the
+//      data domain the copy sits in its cell (halo_berg = 1), beyond it in the nearest halo cell with coordinates
+//      unchanged (halo_berg = 2, F:3634-3660);
+//   3. after connect_all_bonds and set_conglom_ids, copies outside the halo that belong to no conglomerate of this
+//      tile are dropped unless they are within contact distance of one (k_mts_prune = mts_remove_unused_bergs).
+// The set that survives is the reference's: true halo copies, whole conglomerates, contact copies (halo_berg = 10).
+__global__ void k_mts_owned_flags(const uint8_t* __restrict__ flags, long long n_slots, int32_t* __restrict__ out) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  uint8_t f = flags[s];
+  out[s] = ((f & BF_ALIVE) && !(f & (BF_HALO | BF_LEAVER))) ? 1 : 0;
+}
+
+__global__ void k_mts_pack_all(const __grid_constant__ DevBergs b, long long n_slots, const int32_t* __restrict__ own,
+                               const int32_t* __restrict__ idx, double* __restrict__ sendbuf, const __grid_constant__ RecLayout RL,
+                               const int32_t* __restrict__ bbox, long long nbox, int gni /* period in cells, 0 = not cyclic */) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots || !own[s]) return;
+  double* rec = sendbuf + (size_t)idx[s] * RL.w;
+  pack_berg(b, s, rec, RL);
+  const int i = b.ine[s], j = b.jne[s];
+  rec[PK_INE_JNE] = __longlong_as_double(((long long)(unsigned)i << 32) | (unsigned)j);
+  rec[PK_YEAR_FLAGS] = __longlong_as_double(((long long)(unsigned)b.start_year[s] << 32) | (unsigned)b.flags[s]);
+  // the conglomerate's box at the last labelling, widened by the berg's own cell now.  A berg that has just wrapped
+  // through the cyclic seam sits one period away from the box of its (not yet wrapped) conglomerate: the box is
+  // sent in the berg's OWN frame, i.e. shifted by that period.
+  int i0 = i, i1 = i, j0 = j, j1 = j;
+  const int l = b.conglom_id[s];
+  if (bbox && l > 0 && l < nbox && bbox[l] != 0x7fffffff) {
+    int bi0 = bbox[l], bi1 = bbox[nbox + l];
+    if (gni > 0) {
+      if (i < bi0 - gni / 2) { bi0 -= gni; bi1 -= gni; }
+      else if (i > bi1 + gni / 2) { bi0 += gni; bi1 += gni; }
+    }
+    i0 = min(i0, bi0); i1 = max(i1, bi1); j0 = min(j0, bbox[2 * nbox + l]); j1 = max(j1, bbox[3 * nbox + l]);
+  }
+  rec[RL.off_bbox] = __longlong_as_double(((long long)(unsigned)i0 << 32) | (unsigned)i1);
+  rec[RL.off_bbox + 1] = __longlong_as_double(((long long)(unsigned)j0 << 32) | (unsigned)j1);
+}
+
+// images k = -1, 0, +1 periods (nimg = 3, cyclic x) or the berg itself (nimg = 1) of every record of `src`
+__global__ void k_mts_unpack_images(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
+                                    const __grid_constant__ DevParams p, DevCounters* __restrict__ cnt,
+                                    const double* __restrict__ src, long long n_src, long long s0,
+                                    const __grid_constant__ RecLayout RL, int nimg, int skip_k0, int margin) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_src * nimg) return;
+  const long long r = t / nimg;
+  const int k = (nimg == 3) ? (int)(t % nimg) - 1 : 0;
+  const long long s = s0 + t;
+  b.flags[s] = 0;
+  b.halo_code[s] = 0;
+  if (k == 0 && skip_k0) return;
+  const double* rec = src + (size_t)r * RL.w;
+  const double lon = rec[PK_F64_0 + C_LON] + (double)k * p.Lx, lat = rec[PK_F64_0 + C_LAT];
+  int gi, gj;
+  guess_cell(g, lon, lat, &gi, &gj);
+  if (gi >= g.isc && gi <= g.iec && gj >= g.jsc && gj <= g.jec) return;      // an owned berg's own position: never a copy
+  {
+    // the image of the conglomerate's box (global cell indices, shifted by k periods) against this tile + margin
+    const long long bi = __double_as_longlong(rec[RL.off_bbox]), bj = __double_as_longlong(rec[RL.off_bbox + 1]);
+    const int i0 = (int)(bi >> 32) + k * g.gni, i1 = (int)(bi & 0xffffffffll) + k * g.gni;
+    const int j0 = (int)(bj >> 32), j1 = (int)(bj & 0xffffffffll);
+    if (i1 < g.isc - margin || i0 > g.iec + margin || j1 < g.jsc - margin || j0 > g.jec + margin) return;
+  }
+  unpack_berg(b, s, rec, RL);
+  b.f64[C_LON][s] = lon;
+  if (b.f64[C_LON_OLD]) b.f64[C_LON_OLD][s] = lon;
+  long long yf = __double_as_longlong(rec[PK_YEAR_FLAGS]);
+  b.start_year[s] = (int32_t)(yf >> 32);
+  const uint8_t f = (uint8_t)(yf & 0xff);
+  // the cell of the image: the guessed one or a neighbour of it (never the wide search: is_point_in_cell works
+  // modulo Lx and would find the ORIGINAL's cell for an image that lies just beyond the data domain)
+  int oi = gi, oj = gj;
+  bool found = false;
+  for (int dj = 0; dj <= 2 && !found; dj++)
+    for (int di = 0; di <= 2 && !found; di++) {
+      const int ci = gi + (di == 0 ? 0 : di == 1 ? -1 : 1), cj = gj + (dj == 0 ? 0 : dj == 1 ? -1 : 1);
+      if (cell_on_pe(g, ci, cj) && is_point_in_cell(g, p, lon, lat, ci, cj, &cnt->error_flags)) { oi = ci; oj = cj; found = true; }
+    }
+  if (found && oi >= g.isc && oi <= g.iec && oj >= g.jsc && oj <= g.jec) return;
+  double xi = 0.5, yj = 0.5;
+  if (found) {
+    pos_within_cell(g, p, lon, lat, oi, oj, &xi, &yj, &cnt->error_flags);
+    b.halo_code[s] = 1;
+  } else {            // beyond the data domain: the nearest halo cell, coordinates unchanged (F:3634-3660)
+    oi = min(max(gi, g.isd + 1), g.ied); oj = min(max(gj, g.jsd + 1), g.jed);
+    b.halo_code[s] = 2;
+  }
+  b.f64[C_XI][s] = xi; b.f64[C_YJ][s] = yj;
+  b.ine[s] = oi; b.jne[s] = oj;
+  b.flags[s] = (uint8_t)((f | BF_ALIVE | BF_HALO) & ~(BF_LEAVER | BF_ARRIVAL | BF_COLLIDED));
+}
+
+// mts_remove_unused_bergs F:2736-2831: a copy beyond the halo that no conglomerate of this tile claims stays only
+// if it is within contact distance of a berg that one does claim (then halo_berg = 10)
+__global__ void k_mts_prune(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
+                            const __grid_constant__ DevParams p, const CellTable ct, long long n_slots, int* __restrict__ n_pruned) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  const uint8_t f = b.flags[s];
+  if (!(f & BF_ALIVE) || !(f & BF_HALO)) return;
+  if (b.halo_code[s] < 2 || b.conglom_id[s] > 0) return;
+  const int nc_x = p.contact_cells_lon, nc_y = p.contact_cells_lat;
+  const bool radial = (nc_x == 1 && nc_y == 1);
+  const double rdenom = p.hexagonal_icebergs ? 1. / (2. * sqrt(3.)) : (p.iceberg_bonds_on ? 1. / 4. : 1. / p.pi);
+  const double lat1 = b.f64[C_LAT][s], lon1 = b.f64[C_LON][s];
+  const double R1 = radial ? sqrt(b.f64[C_LENGTH][s] * b.f64[C_WIDTH][s] * rdenom) : 0.;
+  double crit = p.contact_distance * p.contact_distance;
+  const int gi = b.ine[s], gj = b.jne[s];
+  bool contact = false;
+  for (int j2 = max(gj - nc_y, g.jsd + 1); j2 <= min(gj + nc_y, g.jed) && !contact; j2++)
+    for (int i2 = max(gi - nc_x, g.isd + 1); i2 <= min(gi + nc_x, g.ied) && !contact; i2++) {
+      const int c = gidx(g, i2, j2);
+      const int n = ct.count[c], o0 = ct.start[c];
+      for (int q = 0; q < n && !contact; q++) {
+        const int o = o0 + q;
+        if (!(b.flags[o] & BF_ALIVE) || b.conglom_id[o] <= 0) continue;
+        const double lat2 = b.f64[C_LAT][o], lon2 = b.f64[C_LON][o];
+        const double dlon = lon2 - lon1, dlat = lat2 - lat1;
+        if (radial) {
+          const double R2 = sqrt(b.f64[C_LENGTH][o] * b.f64[C_WIDTH][o] * rdenom);
+          const double m = fmax(R1 + R2, p.contact_distance);
+          crit = m * m;
+        }
+        double r_dist;
+        if (p.grid_is_latlon) {
+          const double lat_ref = 0.5 * (lat1 + lat2);
+          const double dx_dlon = p.pi_180 * p.Rearth * cos(lat_ref * p.pi_180), dy_dlat = p.pi_180 * p.Rearth;
+          r_dist = (dlon * dx_dlon) * (dlon * dx_dlon) + (dlat * dy_dlat) * (dlat * dy_dlat);
+        } else r_dist = dlon * dlon + dlat * dlat;
+        if (r_dist < crit) contact = true;
+      }
+    }
+  if (contact) b.halo_code[s] = 10;
+  else { b.flags[s] = 0; atomicAdd(n_pruned, 1); }
+}
+
+// cell bounding box of every conglomerate this rank holds (owned bergs and copies), per label, with integer atomics.
+// bbox = 4 arrays of n entries (labels are slot + 1 < n): min i, max i, min j, max j in GLOBAL cell indices.
+__global__ void k_mts_bbox_init(int32_t* __restrict__ bbox, long long n) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  bbox[k] = 0x7fffffff; bbox[n + k] = -0x7fffffff; bbox[2 * n + k] = 0x7fffffff; bbox[3 * n + k] = -0x7fffffff;
+}
+__global__ void k_mts_bbox(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
+                           long long n_slots, int32_t* __restrict__ bbox, long long n) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots || !(b.flags[s] & BF_ALIVE)) return;
+  const int l = b.conglom_id[s];
+  if (l <= 0 || l >= n) return;
+  int gi = b.ine[s], gj = b.jne[s];
+  if (b.halo_code[s] >= 2) guess_cell(g, b.f64[C_LON][s], b.f64[C_LAT][s], &gi, &gj);      // clamped copies: where they really are
+  atomicMin(&bbox[l], gi); atomicMax(&bbox[n + l], gi); atomicMin(&bbox[2 * n + l], gj); atomicMax(&bbox[3 * n + l], gj);
+}
 }  // namespace kid

@@ -178,6 +178,54 @@ __device__ __forceinline__ bool interp_flds(const DevGrid& g, const DevParams& p
   return !bad;
 }
 
+// The grid records one cell's bergs gather, as k_step_fast caches them in shared memory once per warp and cell
+// (56 doubles): [0..31] the corner records c1 (i-1,j-1), c2 (i,j-1), c4 (i-1,j), c3 (i,j); [32..39] the cell record;
+// [40..43] the rectangle record; [44..48] ddx_ssh of cells (i-1,j), (i,j+1), (i-1,j+1), (i,j-1), (i-1,j-1);
+// [49..53] ddy_ssh of cells (i,j-1), (i+1,j), (i+1,j-1), (i-1,j), (i-1,j-1).
+#define KID_CACHE_DOUBLES 56
+__device__ __forceinline__ CornerRec cache_corner(const double* __restrict__ c, int k) {
+  const double2* q = reinterpret_cast<const double2*>(c + 8 * k);
+  double2 a = q[0], b = q[1], d = q[2], e = q[3];
+  CornerRec r; r.uo = a.x; r.vo = a.y; r.ui = b.x; r.vi = b.y; r.ua = d.x; r.va = d.y; r.cosr = e.x; r.sinr = e.y;
+  return r;
+}
+// interp_flds I:4718-4900 of the lean configuration (grid aligned with lon/lat: rotate() is the identity; no
+// coastal drift) on a cached cell: the statements of interp_flds<true> on the same operands
+__device__ __forceinline__ bool interp_flds_cached(const DevParams& p, const double* __restrict__ c, double xi, double yj, Env& e) {
+  const CornerRec c1 = cache_corner(c, 0), c2 = cache_corner(c, 1), c4 = cache_corner(c, 2), c3 = cache_corner(c, 3);
+  KID_BILIN_WEIGHTS
+  double uo = KID_BILIN(uo), vo = KID_BILIN(vo);
+  double ui = KID_BILIN(ui), vi = KID_BILIN(vi);
+  double ua = KID_BILIN(ua), va = KID_BILIN(va);
+  e.sst = c[32]; e.sss = c[33]; e.cn = c[34]; e.hi = c[35]; e.od = c[36];
+  const bool yn = yj >= 0.5, xe = xi >= 0.5;
+  const double ddx_j0 = c[38], ddx_j0w = c[44], ddx_j1 = yn ? c[45] : c[47], ddx_j1w = yn ? c[46] : c[48];
+  const double ddy_i0 = c[39], ddy_i0s = c[49], ddy_i1 = xe ? c[50] : c[52], ddy_i1s = xe ? c[51] : c[53];
+  double hxp, hxm;
+  if (yn) {
+    hxp = fma((yj - 0.5), ddx_j1, (1.5 - yj) * ddx_j0);
+    hxm = fma((yj - 0.5), ddx_j1w, (1.5 - yj) * ddx_j0w);
+  } else {
+    hxp = fma((yj + 0.5), ddx_j0, (0.5 - yj) * ddx_j1);
+    hxm = fma((yj + 0.5), ddx_j0w, (0.5 - yj) * ddx_j1w);
+  }
+  double ssh_x = fma(xi, hxp, (1. - xi) * hxm);
+  if (xe) {
+    hxp = fma((xi - 0.5), ddy_i1, (1.5 - xi) * ddy_i0);
+    hxm = fma((xi - 0.5), ddy_i1s, (1.5 - xi) * ddy_i0s);
+  } else {
+    hxp = fma((xi + 0.5), ddy_i0, (0.5 - xi) * ddy_i1);
+    hxm = fma((xi + 0.5), ddy_i0s, (0.5 - xi) * ddy_i1s);
+  }
+  double ssh_y = fma(yj, hxp, (1. - yj) * hxm);
+  if (ssh_x != ssh_x) ssh_x = 0.;
+  if (ssh_y != ssh_y) ssh_y = 0.;
+  e.uo = uo; e.vo = vo; e.ui = ui; e.vi = vi; e.ua = ua; e.va = va; e.ssh_x = ssh_x; e.ssh_y = ssh_y;
+  bool bad = (uo != uo) || (vo != vo) || (ui != ui) || (vi != vi) || (ua != ua) || (va != va) ||
+             (e.sst != e.sst) || (e.sss != e.sss) || (e.cn != e.cn) || (e.hi != e.hi);
+  return !bad;
+}
+
 // What thermodynamics (I:2896-2920) uses of interp_flds: the rotated ocean and wind velocities
 // and the A-grid picks of sst, cn; also hands back 1/area of the cell.
 struct EnvThermo { double uo, vo, ua, va, sst, cn, rarea; };
@@ -205,6 +253,16 @@ __device__ __forceinline__ void interp_thermo(const DevGrid& g, const DevParams&
   const CellRec* __restrict__ ce = g.cell;
   e.sst = ce[ne].sst; e.cn = ce[ne].cn; e.rarea = ce[ne].rarea;
   e.uo = uo; e.vo = vo; e.ua = ua; e.va = va;
+}
+
+// interp_thermo of the lean configuration on a cached cell (see interp_flds_cached)
+__device__ __forceinline__ void interp_thermo_cached(const DevParams& p, const double* __restrict__ c, double xi, double yj,
+                                                     EnvThermo& e) {
+  const CornerRec c1 = cache_corner(c, 0), c2 = cache_corner(c, 1), c4 = cache_corner(c, 2), c3 = cache_corner(c, 3);
+  KID_BILIN_WEIGHTS
+  e.uo = KID_BILIN(uo); e.vo = KID_BILIN(vo);
+  e.ua = KID_BILIN(ua); e.va = KID_BILIN(va);
+  e.sst = c[32]; e.cn = c[34]; e.rarea = c[37];
 }
 
 // I:444-477

@@ -333,3 +333,75 @@ def cantilever_bergs(rows=3, per_row=30, r=2500.0, xs=101.0e3, ys=151.0e3, h=1.0
     cols.update(lon=x, lat=y, start_lon=x.copy(), start_lat=y.copy())
     cols["static_berg"] = np.where(np.arange(n) % per_row == 0, 1.0, 0.0)
     return cols
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[2]: "tests/a68_test scaled" -- a bonded tabular berg.  The A68a forcing data of the reference
+# test is FTP-only (tests/a68_test/get_data.sh:4), so the berg is synthetic: a rectangle of
+# square-packed elements of radius r (1.5 km in the reference case, 2r apart, bonds from the radii), on a Cartesian
+# grid, with the physics of tests/a68_test/long_run.nml and analytic forcing: a sheared current that turns and
+# bends the berg, and a shoal (ocean_depth below the draught) that one corner runs onto, so grounding stress
+# builds up and bonds break (fracture_criterion='stress').
+def tabular_berg(nx=12, ny=16, r=1500.0, x0=60.0e3, y0=60.0e3, h=200.0, rho_ice=850.0):
+    area = (2.0 * r) ** 2
+    x = np.tile(x0 + 2.0 * r * np.arange(nx), ny)
+    y = np.repeat(y0 + 2.0 * r * np.arange(ny), nx)
+    n = nx * ny
+    z = np.zeros(n)
+    w = np.full(n, np.sqrt(area))
+    m = np.full(n, h * rho_ice * area)
+    return dict(lon=x, lat=y, uvel=z.copy(), vvel=z.copy(), mass=m, thickness=np.full(n, h), width=w.copy(), length=w.copy(),
+                axn=z.copy(), ayn=z.copy(), bxn=z.copy(), byn=z.copy(), start_lon=x.copy(), start_lat=y.copy(), start_day=z.copy(),
+                start_mass=m.copy(), mass_scaling=np.ones(n), mass_of_bits=z.copy(), heat_density=z.copy(),
+                start_year=np.zeros(n, dtype=np.int32))
+
+
+def a68_params(default_params, **over):
+    """&icebergs_nml of tests/a68_test/long_run.nml (the values that reach the hot path), the template's <..> entries
+    filled in: mts_sub_steps=60, ocean_drag_scale=1, cdrag_grounding=1e3 (one of the values the template comments list), frac_thres_n=60e3; a Cartesian grid."""
+    kw = dict(halo=3, Lx=300.0e3, grid_is_latlon=0, grid_is_regular=1, hexagonal_icebergs=0, rho_bergs=850.0,
+              short_step_mts_grounding=1, tau_is_velocity=1, ocean_drag_scale=1.0, skip_first_outer_mts_step=1,
+              constant_interaction_LW=1, break_bonds_on_sub_steps=1, save_bond_forces=1,
+              use_broken_bonds_for_substep_contact=1, dem=1, poisson=0.3, dem_damping_coef=1.0, explicit_inner_mts=1,
+              dem_spring_coef=5.0e6, spring_coef=0.00065359477124183, mts=1, mts_sub_steps=60, force_convergence=1,
+              convergence_tolerance=1e-4, contact_distance=4.0e3, contact_spring_coef=1.0e-7, cdrag_grounding=1.0e3,
+              h_to_init_grounding=0.0, fracture_criterion_stress=1, frac_thres_n=60.0e3, frac_thres_t=100.0e3,
+              radial_damping_coef=0.0, tangental_damping_coef=0.0, scale_damping_by_pmag=0,
+              critical_interaction_damping_on=1, tang_crit_int_damp_on=0, LoW_ratio=1.5, bergy_bit_erosion_fraction=0.0,
+              sicn_shift=0.0, use_operator_splitting=1, speed_limit=0.0, tip_parameter=0.0, coastal_drift=0.0,
+              tidal_drift=0.0, runge_not_verlet=0, use_mixed_melting=1, apply_thickness_cutoff_to_gridded_melt=1,
+              apply_thickness_cutoff_to_bergs_melt=1, melt_cutoff=10.0, allow_bergs_to_roll=1,
+              use_updated_rolling_scheme=1, use_three_equation_model=0, const_gamma=0, ustar_icebergs_bg=0.0,
+              set_melt_rates_to_zero=1, iceberg_bonds_on=1, interactive_icebergs_on=1, only_interactive_forces=0,
+              use_new_predictive_corrective=1, use_old_spreading=0, max_bonds=4, internal_bergs_for_drag=1,
+              manually_initialize_bonds=1, manually_initialize_bonds_from_radii=1, use_roundoff_fix=1, old_bug_bilin=0,
+              add_weight_to_ocean=0, remove_unused_bergs=1)
+    kw.update(over)
+    return default_params(**kw)
+
+
+class TabularGrid(CartesianGrid):
+    """60 x 60 cells of 5 km (cyclic in x, Lx = 300 km), 1000 m deep except a shoal north-east of the berg's start."""
+
+    def __init__(self, ni=60, nj=60, gridres=5.0e3, isc=1, iec=None, jsc=1, jec=None):
+        super().__init__(ni, nj, gridres, isc, iec, jsc, jec)
+
+    def init_args(self):
+        a = super().init_args()
+        i0, j0 = self._ij(0)
+        x, y = self.res * (i0 - 0.5), self.res * (j0 - 0.5)
+        shoal = ((x - 112.5e3) ** 2 + (y - 97.5e3) ** 2) < (12.0e3) ** 2
+        a["ocean_depth"] = np.where(shoal, 120.0, 1000.0)       # draught of the 200 m berg: 166 m
+        return a
+
+    def forcing(self, u0=0.35, shear=0.25, v0=0.12, ua=6.0):
+        """currents (m/s, B-grid corners): eastward, stronger to the north (the berg turns), a weak northward drift;
+        winds passed as velocities (tau_is_velocity=T)"""
+        i0, j0 = self._ij(0)
+        i1, j1 = self._ij(1)
+        y1 = self.res * j1 / (self.res * self.gnj)
+        z0, z1 = np.zeros(i0.shape), np.zeros(i1.shape)
+        f = dict(uo=u0 + shear * (y1 - 0.5), vo=np.full(i1.shape, v0), ui=z1.copy(), vi=z1.copy(),
+                 tauxa=np.full(i0.shape, ua), tauya=z0.copy(), ssh=z1.copy(), sst=np.full(i0.shape, -1.0),
+                 sss=np.full(i0.shape, 34.0), cn=z1.copy(), hi=z1.copy(), calving=z0.copy(), calving_hflx=z0.copy())
+        return {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in f.items()}

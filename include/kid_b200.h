@@ -40,7 +40,7 @@ extern "C" {
 #endif
 
 #define KID_NCLASSES 10          /* F:24  nclasses */
-#define KID_ABI_VERSION 1
+#define KID_ABI_VERSION 2
 
 /* status codes */
 enum {
@@ -217,6 +217,10 @@ typedef struct KidParams {
   double grounding_fraction;                   /* F:730 (0.) */
   double clipping_depth;                       /* F:227 (0.) */
   double initial_orientation;                  /* F:713 (0.) degrees */
+  /* namelist entries that reach icebergs_run but are not implemented: refused by kid_init when set */
+  double tau_calving;                          /* F:728 (0.): running-mean smoothing of the calving field I:5215, I:6020; must be 0 */
+  int32_t find_melt_using_spread_mass;         /* F:741 (F): melt from the spread mass before/after I:5490-5495; must be 0 */
+  int32_t pad2_;
 } KidParams;
 
 /* ----------------------------------------------------------------------------
@@ -389,6 +393,8 @@ int32_t kid_sort_bergs(kid_t* h);
 int32_t kid_set_sort_phase(kid_t* h, int32_t interval, int32_t steps_since_sort);
 /* cell sorts done by this handle so far */
 int64_t kid_sorts_done(kid_t* h);
+/* bergs the fast step kernel handed to the slow-path kernel in the last step (diagnostics; -1 = no fast launch yet) */
+int64_t kid_last_slow_count(kid_t* h);
 int32_t kid_synchronize(kid_t* h);
 
 int32_t kid_end(kid_t** h);

@@ -239,3 +239,32 @@ def test_reference_time_steps_of_the_collision_namelists(dem):
     if dem:
         check_bonds(p, "20 h", 1e-6)
     p.end()
+
+
+# ------------------------------------------------------------------ BASELINE configs[2]: a68_test scaled
+def test_bonded_tabular_berg_a68_physics():
+    """A square-packed bonded tabular berg (12 x 16 elements of radius 1.5 km) with the namelist of
+    tests/a68_test/long_run.nml -- dem, 20 sub-steps, skip_first_outer_mts_step, constant_interaction_LW,
+    contact_distance 4 km, stress fracture on the sub-steps, grounding drag on the short steps -- in a sheared current
+    that carries one corner onto a shoal, where it grounds and pivots: positions, velocities, rotation and bond state
+    against the CPU oracle."""
+    from test_interactions_gpu import Pair
+    g = S.TabularGrid()
+    params = lambda: S.a68_params(api.default_params)
+    p = Pair(S.tabular_berg(), params, grid=g, dt=1800.0, capacity=4096, forcing=g.forcing())
+    n = 12 * 16
+    assert p.b.count_bergs() == n == p.o.count_bergs()
+    gb, ob = p.b.get_bonds(), p.o.get_bonds()
+    assert bond_set(gb) == bond_set(ob) and len(gb["first_id"]) == 2 * (11 * 16 + 12 * 15)
+    names = ["id", "ang_vel", "rot"]
+    for k in range(6):
+        p.step(16)
+        p.check(f"{16 * (k + 1)} steps", rtol=1e-5)
+        check_bonds(p, f"{16 * (k + 1)} steps", 1e-6)
+        a, b = by_id(p.b.get_bergs(names)), by_id(p.o.get_bergs(names))
+        for q in names[1:]:
+            scale = max(np.abs(b[q]).max(), 1e-300)
+            assert np.abs(a[q] - b[q]).max() <= 1e-6 * scale + 1e-16, q
+    d = by_id(p.b.get_bergs(["id", "lon", "uvel", "rot"]))
+    assert d["lon"].max() > 105.0e3 and np.abs(d["rot"]).max() > 0.05, "the berg should have run onto the shoal and started to pivot"
+    p.end()

@@ -258,7 +258,7 @@ def test_interacting_bergs_across_ranks(nranks):
 
 
 def _run_cartesian_ranks(nranks, params, bergs, forcing_of, nsteps, check_every, names, f64, bonds, dt=60.0, rtol=1e-7,
-                         yearday_of=lambda k, dt: 0.0):
+                         yearday_of=lambda k, dt: 0.0, rtol_of=None):
     import kid_oracle_py as O
     g0 = S.CartesianGrid()
     dom0 = api.Domain.single(20, 20, halo=3, cyclic_x=True)
@@ -308,7 +308,10 @@ def _run_cartesian_ranks(nranks, params, bergs, forcing_of, nsteps, check_every,
         if step % check_every == check_every - 1:
             got = [b.get_bergs(names) for b in hs]
             got = {k: np.concatenate([p[k] for p in got]) for k in names}
-            assert_bergs_match(got, o.get_bergs(names), rtol=rtol, names=f64, context=f"{nranks} ranks, step {step}", acc_floor=1e-13)
+            tol, cmp_names = rtol, f64
+            if rtol_of:                      # (rtol, names) may depend on the step: chaos after a collision
+                tol, cmp_names = rtol_of(step)
+            assert_bergs_match(got, o.get_bergs(names), rtol=tol, names=cmp_names, context=f"{nranks} ranks, step {step}", acc_floor=1e-13)
     for b in hs:
         api.icebergs_end(b)
     grp.close()
