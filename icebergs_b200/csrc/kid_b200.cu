@@ -94,9 +94,6 @@ struct kid_handle {
   MtsSums* dsums = nullptr;
   int mts_env_cached = 0, mts_outer_iters = 0, mts_smem_attr = 0;
   int skip_first_outer_mts_step = 0;
-  int32_t* mts_bbox = nullptr;         // cell box per conglomerate label (k_mts_bbox), mts_bbox_n entries per bound
-  long long mts_bbox_n = 0;
-  int mts_bbox_valid = 0;
   int scatter_dense = 1;          // > KID_DENSE_BERGS_PER_CELL bergs per occupied cell at the last sort (scatter_fluxes)
   int forcing_set = 0;
   int no_rotation = 0;
@@ -1057,7 +1054,7 @@ extern "C" int32_t kid_end(kid_t** hp) {
   cudaFree(h->scan_sums); cudaFree(h->scan_total); cudaFree(h->dcnt); cudaFree(h->dflags);
   cudaFreeHost(h->hcnt); cudaFreeHost(h->hflags);
   for (int k = 0; k < BD_N; k++) cudaFree(h->b.bond_dem[k]);
-  cudaFree(h->b.bond_broken); cudaFree(h->b.n_bonds); cudaFree(h->dsums); cudaFree(h->mts_bbox);
+  cudaFree(h->b.bond_broken); cudaFree(h->b.n_bonds); cudaFree(h->dsums);
   cudaFree(h->leaver_lists[0]); cudaFree(h->leaver_lists[1]); cudaFree(h->leaver_counts);
   if (h->xstream) cudaStreamDestroy(h->xstream);
   if (h->ev_kstep) cudaEventDestroy(h->ev_kstep);
@@ -1226,6 +1223,8 @@ static int sort_bergs(kid_t* h) {
 
 
 static void scan_i32(kid_t* h, const int32_t* in, int32_t* out, int32_t* sums, long long n, int32_t* total);
+// k_connect_bonds: with copies through the cyclic seam in the store, a partner is less than half a period away
+static double bond_half_period(const kid_t* h) { return (h->d.cyclic_x && h->p.Lx > 0.) ? 0.5 * h->p.Lx : 0.; }
 
 // ------------------------------------------------------- ghosts and bonds
 // update_halo_icebergs F:1800-2131: the halo copies are dropped and rebuilt from the owners'
@@ -1233,35 +1232,11 @@ static void scan_i32(kid_t* h, const int32_t* in, int32_t* out, int32_t* sums, l
 // cell (the reference relays corners through the E/W neighbour, F:1976-2006).
 static int set_conglom_ids(kid_t* h);
 static int sort_bergs(kid_t* h);
-// the cell box of every conglomerate (labels of set_conglom_ids) for the next transfer_mts_bergs
-static int mts_measure_boxes(kid_t* h) {
-  const bool cyc = h->d.cyclic_x && h->p.Lx > 0.;
-  if (h->d.nranks == 1 && !cyc) return KID_OK;
-  if (!h->mts_bbox) CK(cudaMalloc(&h->mts_bbox, sizeof(int32_t) * 4 * (h->capacity + 1)));
-  const long long ns = h->n_slots, nb = ns + 1;
-  LAUNCH(h, k_mts_bbox_init, nb, 256, h->mts_bbox, nb);
-  LAUNCH(h, k_mts_bbox, ns, 256, h->g, h->b, ns, h->mts_bbox, nb);
-  h->mts_bbox_n = nb;
-  h->mts_bbox_valid = 1;
-  return KID_OK;
-}
-
 // transfer_mts_bergs F:2136-2216 after the halos were cleared: see the end of kid_mts.cuh
 static int rebuild_ghosts_mts(kid_t* h) {
   const int nr = h->d.nranks, me = h->d.rank;
   const bool cyc = h->d.cyclic_x && h->p.Lx > 0.;
   if (nr == 1 && !cyc) return KID_OK;
-  if (!h->mts_bbox_valid) {
-    // first transfer (icebergs_init I:150-167): no conglomerate labels yet -- label what this rank owns
-    int rc0 = sort_bergs(h);
-    if (rc0) return rc0;
-    if (h->b.max_bonds > 0) { CellTable ct{h->cell_start, h->cell_count}; LAUNCH(h, k_connect_bonds, h->n_slots, 128, h->g, h->b, ct, h->dcnt, h->n_slots); }
-    CK(cudaMemsetAsync(&h->dcnt->error_flags, 0, sizeof(unsigned int), h->stream));      // (partners on other ranks are not here yet)
-    rc0 = set_conglom_ids(h);
-    if (rc0) return rc0;
-    rc0 = mts_measure_boxes(h);
-    if (rc0) return rc0;
-  }
   const long long ns = h->n_slots;
   const long long w = h->rec.w;
   // every owned berg, packed in slot order
@@ -1274,7 +1249,7 @@ static int rebuild_ghosts_mts(kid_t* h) {
   long long n_others = 0;
   for (int q = 0; q < nr; q++) if (q != me) n_others += h->h_all_counts[q];
   if (n_own > h->ghost_cap || n_others > h->ghost_cap) return fail_fatal(h, KID_ERR_CAPACITY, "kid: ghost buffer capacity exceeded (transfer_mts_bergs)");
-  LAUNCH(h, k_mts_pack_all, ns, 128, h->b, ns, h->sort_keys[0], h->sort_vals[0], h->gsend, h->rec, h->mts_bbox, h->mts_bbox_n, cyc ? h->d.gni : 0);
+  LAUNCH(h, k_mts_pack_all, ns, 128, h->g, h->b, ns, h->sort_keys[0], h->sort_vals[0], h->gsend, h->rec, cyc ? h->p.Lx : 0.);
   std::vector<XMsg> sends, recvs;
   long long off = 0;
   for (int q = 0; q < nr; q++) {
@@ -1286,18 +1261,16 @@ static int rebuild_ghosts_mts(kid_t* h) {
   }
   rc = comm_exchange(h, sends, recvs);
   if (rc) return rc;
-  // which periodic images a rank keeps: those of conglomerates whose box reaches its halo + the contact cells
-  // (+ 2 cells: the boxes date from the last labelling, bergs have moved a step since)
-  const int reach = h->p.halo + std::max(h->p.contact_cells_lon, h->p.contact_cells_lat) + 2;
+  // every periodic image of every berg is unpacked; mts_prune keeps what this tile needs
   const int nimg = cyc ? 3 : 1;
   const long long n_new = (cyc ? n_own * 3 : 0) + n_others * nimg;
   if (ns + n_new > h->capacity) return fail_fatal(h, KID_ERR_CAPACITY, "kid: berg store capacity exceeded by conglomerate copies (transfer_mts_bergs)");
   long long s0 = ns;
   if (cyc && n_own > 0) {
-    LAUNCH(h, k_mts_unpack_images, n_own * 3, 128, h->g, h->b, h->dp, h->dcnt, h->gsend, n_own, s0, h->rec, 3, 1, reach);
+    LAUNCH(h, k_mts_unpack_images, n_own * 3, 128, h->g, h->b, h->dp, h->dcnt, h->gsend, n_own, s0, h->rec, 3, 1);
     s0 += n_own * 3;
   }
-  if (n_others > 0) LAUNCH(h, k_mts_unpack_images, n_others * nimg, 128, h->g, h->b, h->dp, h->dcnt, h->grecv, n_others, s0, h->rec, nimg, 0, reach);
+  if (n_others > 0) LAUNCH(h, k_mts_unpack_images, n_others * nimg, 128, h->g, h->b, h->dp, h->dcnt, h->grecv, n_others, s0, h->rec, nimg, 0);
   if (n_new > 0) {
     h->n_slots = ns + n_new;
     CK(cudaStreamSynchronize(h->stream));
@@ -1312,7 +1285,7 @@ static int rebuild_ghosts_mts(kid_t* h) {
 static int mts_prune(kid_t* h, bool* pruned) {
   *pruned = false;
   const bool cyc = h->d.cyclic_x && h->p.Lx > 0.;
-  if ((h->d.nranks == 1 && !cyc) || !h->p.remove_unused_bergs) return KID_OK;
+  if (h->d.nranks == 1 && !cyc) return KID_OK;
   const long long ns = h->n_slots;
   CK(cudaMemsetAsync(h->d_changed, 0, sizeof(int), h->stream));
   CellTable ct{h->cell_start, h->cell_count};
@@ -1402,7 +1375,7 @@ static int refresh_interactive_state(kid_t* h) {
   for (int pass = 0; pass < 2; pass++) {
     if (h->b.max_bonds > 0) {
       CellTable ct{h->cell_start, h->cell_count};
-      LAUNCH(h, k_connect_bonds, h->n_slots, 128, h->g, h->b, ct, h->dcnt, h->n_slots);
+      LAUNCH(h, k_connect_bonds, h->n_slots, 128, h->g, h->b, ct, h->dcnt, h->n_slots, bond_half_period(h));
       if (h->p.mts) LAUNCH(h, k_assign_n_bonds, h->n_slots, 128, h->b, h->n_slots, h->p.use_broken_bonds_for_substep_contact ? 1 : 0);
     }
     rc = set_conglom_ids(h);
@@ -1410,7 +1383,7 @@ static int refresh_interactive_state(kid_t* h) {
     // transfer_mts_bergs, last part (F:2199-2202): copies nobody needs are dropped; the store is then compacted again
     bool pruned = false;
     if (pass == 0) { rc = mts_prune(h, &pruned); if (rc) return rc; }
-    if (!pruned) return mts_measure_boxes(h);
+    if (!pruned) return KID_OK;
     rc = sort_bergs(h);
     if (rc) return rc;
   }
@@ -2161,7 +2134,7 @@ static int step_core(kid_t* h) {
     if (!h->tables_valid) {
       int rc = sort_bergs(h);
       if (rc) return rc;
-      if (h->b.max_bonds > 0) { CellTable ct{h->cell_start, h->cell_count}; LAUNCH(h, k_connect_bonds, h->n_slots, 128, h->g, h->b, ct, h->dcnt, h->n_slots); }
+      if (h->b.max_bonds > 0) { CellTable ct{h->cell_start, h->cell_count}; LAUNCH(h, k_connect_bonds, h->n_slots, 128, h->g, h->b, ct, h->dcnt, h->n_slots, bond_half_period(h)); }
       rc = set_conglom_ids(h);
       if (rc) return rc;
     }

@@ -89,7 +89,6 @@ struct RecLayout {
   int32_t dem;
   int32_t w;          // words per record
   int32_t off_bonds, off_extra, off_bdem;
-  int32_t off_bbox;   // mts: 2 words, the cell bounding box of the berg's conglomerate (transfer_mts_bergs); else -1
 };
 __host__ __device__ __forceinline__ RecLayout make_rec_layout(int ncols, int mb, int dem, int mts) {
   RecLayout L;
@@ -98,8 +97,7 @@ __host__ __device__ __forceinline__ RecLayout make_rec_layout(int ncols, int mb,
   L.off_extra = L.off_bonds + 3 * mb;
   L.off_bdem = L.off_extra + (ncols > (int)C_NINTER ? ncols - (int)C_NINTER : 0);
   L.w = L.off_bdem + (dem ? (BD_N + 1) * mb : 0);
-  L.off_bbox = -1;
-  if (mts) { L.off_bbox = L.w; L.w += 2; }
+  (void)mts;
   return L;
 }
 // everything of the berg in slot s except the cell index / flags words (the callers differ there)

@@ -345,11 +345,23 @@ __device__ __forceinline__ int find_id_in_cell(const DevGrid& g, const DevBergs&
 }
 
 // connect_all_bonds F:4963-5125 on the freshly sorted store: every bond looks its partner up in the
-// hinted cell, then around the hint, then in the 5x5 cells around the berg (updating the hint)
+// hinted cell, then around the hint, then in the 5x5 cells around the berg (updating the hint).
+// half_period > 0 (cyclic x): the store may hold several periodic images of one berg (the copies of
+// transfer_mts_bergs); a candidate more than half a period away in x is an image of the partner, not the partner.
+__device__ __forceinline__ int find_partner_in_cell(const DevGrid& g, const DevBergs& b, const CellTable& ct, int i, int j,
+                                                    int64_t id, double lon, double half_period) {
+  if (!((i > g.isd - 1) && (i < g.ied + 1) && (j > g.jsd - 1) && (j < g.jed + 1))) return -1;
+  int c = gidx(g, i, j);
+  int n = ct.count[c], o0 = ct.start[c];
+  for (int k = 0; k < n; k++)
+    if (b.id[o0 + k] == id && !(half_period > 0. && fabs(b.f64[C_LON][o0 + k] - lon) > half_period)) return o0 + k;
+  return -1;
+}
 __global__ void k_connect_bonds(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
-                                const CellTable ct, DevCounters* __restrict__ cnt, long long n_slots) {
+                                const CellTable ct, DevCounters* __restrict__ cnt, long long n_slots, double half_period) {
   long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_slots || !(b.flags[s] & BF_ALIVE)) return;
+  const double lon = b.f64[C_LON][s];
   for (int k = 0; k < b.max_bonds; k++) {
     long long slot = (long long)k * b.capacity + s;
     int64_t oid = b.bond_other_id[slot];
@@ -364,14 +376,14 @@ __global__ void k_connect_bonds(const __grid_constant__ DevGrid g, const __grid_
     int o = -1;
     for (int pass = 0; pass < 2 && o < 0; pass++) {
       if ((pass == 0) == !far) {            // near hint: hinted cell and its ring first; far hint: last
-        o = find_id_in_cell(g, b, ct, i, j, oid);
+        o = find_partner_in_cell(g, b, ct, i, j, oid, lon, half_period);
         for (int jj = j - 1; jj <= j + 1 && o < 0; jj++)
           for (int ii = i - 1; ii <= i + 1 && o < 0; ii++)
-            if (ii != i || jj != j) o = find_id_in_cell(g, b, ct, ii, jj, oid);
+            if (ii != i || jj != j) o = find_partner_in_cell(g, b, ct, ii, jj, oid, lon, half_period);
       } else {
         for (int jj = bj - 2; jj <= bj + 2 && o < 0; jj++)
           for (int ii = bi - 2; ii <= bi + 2 && o < 0; ii++) {
-            o = find_id_in_cell(g, b, ct, ii, jj, oid);
+            o = find_partner_in_cell(g, b, ct, ii, jj, oid, lon, half_period);
             if (o >= 0) { b.bond_other_ine[slot] = ii; b.bond_other_jne[slot] = jj; }
           }
       }

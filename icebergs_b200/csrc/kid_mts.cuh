@@ -922,13 +922,13 @@ __global__ void k_dem_tests_init(const __grid_constant__ DevBergs b, long long n
 // The reference finds them by walking bond lists recursively on the sender, direction by direction, twice.  Here:
 //   1. every rank packs ALL its owned bergs (k_mts_pack_all; populations of bonded runs are small) and the packs go
 //      to every rank (NVSwitch: one group of sends/receives, no relay);
-//   2. every record carries the cell bounding box of the berg's conglomerate (k_mts_bbox, from the labels of
-//      set_conglom_ids); the receiver keeps a periodic image of the berg when the image of that box reaches its halo
-//      or the contact cells around it (k_mts_unpack_images), so a conglomerate arrives whole or not at all: in the
-//      data domain the copy sits in its cell (halo_berg = 1), beyond it in the nearest halo cell with coordinates
-//      unchanged (halo_berg = 2, F:3634-3660);
-//   3. after connect_all_bonds and set_conglom_ids, copies outside the halo that belong to no conglomerate of this
-//      tile are dropped unless they are within contact distance of one (k_mts_prune = mts_remove_unused_bergs).
+//   2. the receiver unpacks every periodic image of every record that does not fall on its compute domain
+//      (k_mts_unpack_images): in the data domain the copy sits in its cell (halo_berg = 1), beyond it in the nearest
+//      halo cell with coordinates unchanged (halo_berg = 2, F:3634-3660);
+//   3. after connect_all_bonds and set_conglom_ids (labels spread from the owned bergs through the bonds, so a
+//      conglomerate this tile owns a part of is labelled as a whole), copies outside the halo that carry no label are
+//      dropped unless they are within contact distance of a labelled berg (k_mts_prune = mts_remove_unused_bergs,
+//      always applied: it is what turns "everything" into the reference's set).
 // The set that survives is the reference's: true halo copies, whole conglomerates, contact copies (halo_berg = 10).
 __global__ void k_mts_owned_flags(const uint8_t* __restrict__ flags, long long n_slots, int32_t* __restrict__ out) {
   long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -937,9 +937,9 @@ __global__ void k_mts_owned_flags(const uint8_t* __restrict__ flags, long long n
   out[s] = ((f & BF_ALIVE) && !(f & (BF_HALO | BF_LEAVER))) ? 1 : 0;
 }
 
-__global__ void k_mts_pack_all(const __grid_constant__ DevBergs b, long long n_slots, const int32_t* __restrict__ own,
-                               const int32_t* __restrict__ idx, double* __restrict__ sendbuf, const __grid_constant__ RecLayout RL,
-                               const int32_t* __restrict__ bbox, long long nbox, int gni /* period in cells, 0 = not cyclic */) {
+__global__ void k_mts_pack_all(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b, long long n_slots,
+                               const int32_t* __restrict__ own, const int32_t* __restrict__ idx, double* __restrict__ sendbuf,
+                               const __grid_constant__ RecLayout RL, double Lx /* period, 0 = not cyclic */) {
   long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_slots || !own[s]) return;
   double* rec = sendbuf + (size_t)idx[s] * RL.w;
@@ -947,28 +947,22 @@ __global__ void k_mts_pack_all(const __grid_constant__ DevBergs b, long long n_s
   const int i = b.ine[s], j = b.jne[s];
   rec[PK_INE_JNE] = __longlong_as_double(((long long)(unsigned)i << 32) | (unsigned)j);
   rec[PK_YEAR_FLAGS] = __longlong_as_double(((long long)(unsigned)b.start_year[s] << 32) | (unsigned)b.flags[s]);
-  // the conglomerate's box at the last labelling, widened by the berg's own cell now.  A berg that has just wrapped
-  // through the cyclic seam sits one period away from the box of its (not yet wrapped) conglomerate: the box is
-  // sent in the berg's OWN frame, i.e. shifted by that period.
-  int i0 = i, i1 = i, j0 = j, j1 = j;
-  const int l = b.conglom_id[s];
-  if (bbox && l > 0 && l < nbox && bbox[l] != 0x7fffffff) {
-    int bi0 = bbox[l], bi1 = bbox[nbox + l];
-    if (gni > 0) {
-      if (i < bi0 - gni / 2) { bi0 -= gni; bi1 -= gni; }
-      else if (i > bi1 + gni / 2) { bi0 += gni; bi1 += gni; }
-    }
-    i0 = min(i0, bi0); i1 = max(i1, bi1); j0 = min(j0, bbox[2 * nbox + l]); j1 = max(j1, bbox[3 * nbox + l]);
+  // a berg that has just wrapped through the seam on this rank still carries the longitude of the far side
+  // (update_latlon F:5128 re-derives it after the transfer): the images are taken around the cell it sits in
+  if (Lx > 0.) {
+    int gi, gj;
+    const double lon = rec[PK_F64_0 + C_LON];
+    guess_cell(g, lon, rec[PK_F64_0 + C_LAT], &gi, &gj);
+    if (gi - i > g.gni / 2) rec[PK_F64_0 + C_LON] = lon - Lx;
+    else if (i - gi > g.gni / 2) rec[PK_F64_0 + C_LON] = lon + Lx;
   }
-  rec[RL.off_bbox] = __longlong_as_double(((long long)(unsigned)i0 << 32) | (unsigned)i1);
-  rec[RL.off_bbox + 1] = __longlong_as_double(((long long)(unsigned)j0 << 32) | (unsigned)j1);
 }
 
 // images k = -1, 0, +1 periods (nimg = 3, cyclic x) or the berg itself (nimg = 1) of every record of `src`
 __global__ void k_mts_unpack_images(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
                                     const __grid_constant__ DevParams p, DevCounters* __restrict__ cnt,
                                     const double* __restrict__ src, long long n_src, long long s0,
-                                    const __grid_constant__ RecLayout RL, int nimg, int skip_k0, int margin) {
+                                    const __grid_constant__ RecLayout RL, int nimg, int skip_k0) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_src * nimg) return;
   const long long r = t / nimg;
@@ -982,13 +976,6 @@ __global__ void k_mts_unpack_images(const __grid_constant__ DevGrid g, const __g
   int gi, gj;
   guess_cell(g, lon, lat, &gi, &gj);
   if (gi >= g.isc && gi <= g.iec && gj >= g.jsc && gj <= g.jec) return;      // an owned berg's own position: never a copy
-  {
-    // the image of the conglomerate's box (global cell indices, shifted by k periods) against this tile + margin
-    const long long bi = __double_as_longlong(rec[RL.off_bbox]), bj = __double_as_longlong(rec[RL.off_bbox + 1]);
-    const int i0 = (int)(bi >> 32) + k * g.gni, i1 = (int)(bi & 0xffffffffll) + k * g.gni;
-    const int j0 = (int)(bj >> 32), j1 = (int)(bj & 0xffffffffll);
-    if (i1 < g.isc - margin || i0 > g.iec + margin || j1 < g.jsc - margin || j0 > g.jec + margin) return;
-  }
   unpack_berg(b, s, rec, RL);
   b.f64[C_LON][s] = lon;
   if (b.f64[C_LON_OLD]) b.f64[C_LON_OLD][s] = lon;
@@ -1062,21 +1049,4 @@ __global__ void k_mts_prune(const __grid_constant__ DevGrid g, const __grid_cons
   else { b.flags[s] = 0; atomicAdd(n_pruned, 1); }
 }
 
-// cell bounding box of every conglomerate this rank holds (owned bergs and copies), per label, with integer atomics.
-// bbox = 4 arrays of n entries (labels are slot + 1 < n): min i, max i, min j, max j in GLOBAL cell indices.
-__global__ void k_mts_bbox_init(int32_t* __restrict__ bbox, long long n) {
-  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  bbox[k] = 0x7fffffff; bbox[n + k] = -0x7fffffff; bbox[2 * n + k] = 0x7fffffff; bbox[3 * n + k] = -0x7fffffff;
-}
-__global__ void k_mts_bbox(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
-                           long long n_slots, int32_t* __restrict__ bbox, long long n) {
-  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_slots || !(b.flags[s] & BF_ALIVE)) return;
-  const int l = b.conglom_id[s];
-  if (l <= 0 || l >= n) return;
-  int gi = b.ine[s], gj = b.jne[s];
-  if (b.halo_code[s] >= 2) guess_cell(g, b.f64[C_LON][s], b.f64[C_LAT][s], &gi, &gj);      // clamped copies: where they really are
-  atomicMin(&bbox[l], gi); atomicMax(&bbox[n + l], gi); atomicMin(&bbox[2 * n + l], gj); atomicMax(&bbox[3 * n + l], gj);
-}
 }  // namespace kid

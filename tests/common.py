@@ -106,6 +106,8 @@ def assert_bergs_match(got, want, rtol=RTOL, names=COMPARE_F64, context="", acc_
         e = rel_err(g[k], w[k])
         # accelerations and velocities are sums with cancellation: compare against the field's scale
         floor = max(1e-13 * max(np.max(np.abs(w[k])), 1e-300), acc_floor) if k in ("axn", "ayn", "bxn", "byn", "uvel", "vvel", "uvel_prev", "vvel_prev", "uvel_old", "vvel_old", "ang_vel", "ang_accel", "rot") else 0.0
+        if k == "rot":          # radians; before any torque acts the rotation is rounding noise of ~1e-12
+            floor = max(floor, 1e-10)
         if k in ("xi", "yj"):   # fractions of a cell in [0,1): the tolerance is relative to the cell, not to xi
             floor = rtol
         bad = (e > rtol) & (np.abs(g[k] - w[k]) > floor)
