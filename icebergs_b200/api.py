@@ -94,6 +94,10 @@ class Domain:
         return getattr(self.c, k)
 
     @property
+    def halo(self):
+        return self.c.isc - self.c.isd
+
+    @property
     def nic(self):
         return self.c.iec - self.c.isc + 1
 

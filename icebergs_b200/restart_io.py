@@ -151,20 +151,70 @@ def read_restart_bonds(path):
     return out
 
 
-def write_restart_calving(path, stored_ice, stored_heat, iceberg_counter_grd):
-    """calving.res.nc (fmsio:564-566) on the rank's data domain: stored_ice (nclasses, nj, ni)."""
+def _calving_window(domain, nj, ni):
+    """Where a rank's compute domain sits in a file array of (nj, ni) points: the file holds either the global grid
+    (FMS domain-aware restarts are read and written in global index space, fmsio:564-566 / fmsio:1448-1470) or, for a
+    distributed per-tile file, just this rank's compute domain."""
+    d = domain
+    if (nj, ni) == (d.gnj, d.gni):
+        return slice(d.jsc - 1, d.jec), slice(d.isc - 1, d.iec)
+    if (nj, ni) == (d.njc, d.nic):
+        return slice(0, nj), slice(0, ni)
+    raise ValueError(f"calving.res.nc holds {nj} x {ni} points: neither the global grid {d.gnj} x {d.gni} nor the "
+                     f"compute domain {d.njc} x {d.nic} of this rank")
+
+
+def write_restart_calving(path, stored_ice, stored_heat, iceberg_counter_grd, domain=None, global_file=False):
+    """calving.res.nc (fmsio:564-566: register_restart_field of stored_ice, stored_heat, iceberg_counter_grd on the
+    FMS domain).  FMS writes the COMPUTE domain (halos stripped) with a Time record axis: (Time, zaxis_1, yaxis_1,
+    xaxis_1).  ``stored_ice`` etc. are the library's data-domain arrays (``Icebergs.get_calving_state``); with
+    ``domain`` the halos are stripped, and with ``global_file`` the compute domain is placed in a global-size array
+    (what a single-PE or mpp_io-combined file looks like; the other ranks' points are left zero).  Without ``domain``
+    the arrays are written as they are (already halo-free)."""
+    si, sh, ic = np.asarray(stored_ice), np.asarray(stored_heat), np.asarray(iceberg_counter_grd)
+    if domain is not None:
+        d = domain
+        h = d.halo
+        si, sh, ic = si[:, h:h + d.njc, h:h + d.nic], sh[h:h + d.njc, h:h + d.nic], ic[h:h + d.njc, h:h + d.nic]
+        if global_file:
+            gsi = np.zeros((si.shape[0], d.gnj, d.gni)); gsh = np.zeros((d.gnj, d.gni)); gic = np.zeros((d.gnj, d.gni), dtype=np.int32)
+            js, is_ = slice(d.jsc - 1, d.jec), slice(d.isc - 1, d.iec)
+            gsi[:, js, is_], gsh[js, is_], gic[js, is_] = si, sh, ic
+            si, sh, ic = gsi, gsh, gic
     f = netcdf_file(path, "w", version=1)
-    nk, nj, ni = stored_ice.shape
+    nk, nj, ni = si.shape
+    f.createDimension("Time", None)        # (scipy's NetCDF-3 writer wants the record dimension first)
     f.createDimension("xaxis_1", ni); f.createDimension("yaxis_1", nj); f.createDimension("zaxis_1", nk)
-    v = f.createVariable("stored_ice", "d", ("zaxis_1", "yaxis_1", "xaxis_1")); v[:] = stored_ice
-    v = f.createVariable("stored_heat", "d", ("yaxis_1", "xaxis_1")); v[:] = stored_heat
-    v = f.createVariable("iceberg_counter_grd", "i", ("yaxis_1", "xaxis_1")); v[:] = iceberg_counter_grd
+    for nm, n in (("xaxis_1", ni), ("yaxis_1", nj), ("zaxis_1", nk)):
+        v = f.createVariable(nm, "d", (nm,)); v[:] = np.arange(1, n + 1, dtype=np.float64)
+    v = f.createVariable("Time", "d", ("Time",)); v[0] = 1.0
+    v = f.createVariable("stored_ice", "d", ("Time", "zaxis_1", "yaxis_1", "xaxis_1")); v[0] = si
+    v = f.createVariable("stored_heat", "d", ("Time", "yaxis_1", "xaxis_1")); v[0] = sh
+    v = f.createVariable("iceberg_counter_grd", "i", ("Time", "yaxis_1", "xaxis_1")); v[0] = ic
     f.close()
 
 
-def read_restart_calving(path):
+def read_restart_calving(path, domain=None):
+    """-> (stored_ice, stored_heat, iceberg_counter_grd) for ``Icebergs.set_calving_state``.  A leading Time axis is
+    dropped (last record).  With ``domain`` the rank's compute-domain window of a global (or per-tile) file is cut out
+    and padded with zero halos to the data domain the library holds (the reference fills the halos by
+    mpp_update_domains on the first icebergs_run, I:5203); without it the arrays come back as stored."""
     f = netcdf_file(path, "r", mmap=False)
-    out = (np.array(f.variables["stored_ice"][:], dtype=np.float64), np.array(f.variables["stored_heat"][:], dtype=np.float64),
-           np.array(f.variables["iceberg_counter_grd"][:], dtype=np.int32))
+    def var(name, nd, dtype):
+        a = np.array(f.variables[name][:], dtype=dtype)
+        if a.ndim == nd + 1:
+            a = a[-1]
+        return a
+    si, sh = var("stored_ice", 3, np.float64), var("stored_heat", 2, np.float64)
+    ic = var("iceberg_counter_grd", 2, np.int32) if "iceberg_counter_grd" in f.variables else np.zeros(sh.shape, dtype=np.int32)
     f.close()
-    return out
+    if domain is None:
+        return si, sh, ic
+    d = domain
+    js, is_ = _calving_window(d, sh.shape[0], sh.shape[1])
+    h = d.halo
+    osi = np.zeros((si.shape[0], d.njd, d.nid)); osh = np.zeros((d.njd, d.nid)); oic = np.zeros((d.njd, d.nid), dtype=np.int32)
+    osi[:, h:h + d.njc, h:h + d.nic] = si[:, js, is_]
+    osh[h:h + d.njc, h:h + d.nic] = sh[js, is_]
+    oic[h:h + d.njc, h:h + d.nic] = ic[js, is_]
+    return osi, osh, oic

@@ -64,6 +64,51 @@ def test_bond_and_calving_round_trip(tmp_path):
     assert np.array_equal(a, si) and np.array_equal(b_, sh) and np.array_equal(c, ic)
 
 
+def test_calving_restart_in_the_fms_layout(tmp_path):
+    """calving.res.nc as FMS writes it (fmsio:564-566): compute-domain points only, global index space, a Time record
+    axis.  A file shaped like that is cut to each rank's compute domain and padded to the data domain the library holds;
+    what a rank writes back has the same layout (the halo-padded, Time-less file was not the reference's)."""
+    from scipy.io import netcdf_file
+    from icebergs_b200 import api
+    gni, gnj, nk = 12, 8, 10
+    rng = np.random.default_rng(3)
+    gsi, gsh = rng.random((nk, gnj, gni)), rng.random((gnj, gni))
+    gic = np.arange(gnj * gni, dtype=np.int32).reshape(gnj, gni)
+    q = str(tmp_path / "calving.res.nc")
+    f = netcdf_file(q, "w", version=1)               # the fixture: written here field by field, not by the module under test
+    f.createDimension("Time", None)
+    f.createDimension("xaxis_1", gni); f.createDimension("yaxis_1", gnj); f.createDimension("zaxis_1", nk)
+    v = f.createVariable("Time", "d", ("Time",)); v[0] = 1.0
+    v = f.createVariable("stored_ice", "d", ("Time", "zaxis_1", "yaxis_1", "xaxis_1")); v[0] = gsi
+    v = f.createVariable("stored_heat", "d", ("Time", "yaxis_1", "xaxis_1")); v[0] = gsh
+    v = f.createVariable("iceberg_counter_grd", "i", ("Time", "yaxis_1", "xaxis_1")); v[0] = gic
+    f.close()
+    merged_si, merged_sh, merged_ic = np.zeros_like(gsi), np.zeros_like(gsh), np.zeros_like(gic)
+    for rank in range(2):
+        d = api.Domain.decomposed(gni, gnj, rank, 2, halo=2)
+        si, sh, ic = R.read_restart_calving(q, domain=d)
+        h = d.halo
+        assert si.shape == (nk, d.njd, d.nid) and sh.shape == (d.njd, d.nid) and ic.shape == (d.njd, d.nid)
+        js, is_ = slice(d.jsc - 1, d.jec), slice(d.isc - 1, d.iec)
+        assert np.array_equal(si[:, h:h + d.njc, h:h + d.nic], gsi[:, js, is_])
+        assert np.array_equal(ic[h:h + d.njc, h:h + d.nic], gic[js, is_])
+        assert si[:, :h].sum() == 0 and si[:, :, :h].sum() == 0            # halos: zero until the first halo update
+        out = str(tmp_path / f"calving.res.nc.{rank:04d}")
+        R.write_restart_calving(out, si, sh, ic, domain=d, global_file=True)
+        g = netcdf_file(out, "r", mmap=False)
+        assert g.variables["stored_ice"].dimensions == ("Time", "zaxis_1", "yaxis_1", "xaxis_1")
+        assert g.variables["stored_ice"].shape[1:] == (nk, gnj, gni)
+        merged_si += np.array(g.variables["stored_ice"][0]); merged_sh += np.array(g.variables["stored_heat"][0])
+        merged_ic += np.array(g.variables["iceberg_counter_grd"][0])
+        g.close()
+        # a per-tile file (compute domain only) is read back onto the same rank
+        tile = str(tmp_path / f"tile{rank}.nc")
+        R.write_restart_calving(tile, si, sh, ic, domain=d)
+        si2, sh2, ic2 = R.read_restart_calving(tile, domain=d)
+        assert np.array_equal(si2, si) and np.array_equal(sh2, sh) and np.array_equal(ic2, ic)
+    assert np.array_equal(merged_si, gsi) and np.array_equal(merged_sh, gsh) and np.array_equal(merged_ic, gic)
+
+
 @pytest.mark.gpu
 def test_restart_through_files_continues(tmp_path):
     """Stop, write icebergs.res.nc + calving.res.nc, start a new handle from the files: the continued run
@@ -78,12 +123,12 @@ def test_restart_through_files_continues(tmp_path):
     names = [v[0] for v in R.BERG_VARS if not v[0].startswith("id_")] + ["id"]
     R.write_restart_bergs(str(tmp_path / "icebergs.res.nc"), a.get_bergs(names))
     si, sh, ic = a.get_calving_state()
-    R.write_restart_calving(str(tmp_path / "calving.res.nc"), si, sh, ic)
+    R.write_restart_calving(str(tmp_path / "calving.res.nc"), si, sh, ic, domain=a.domain, global_file=True)
     for _ in range(3):
         run_gpu(a, case)
     b = api.icebergs_init(case.gni, case.gnj, case.dt, (1, 0.0), params=case.params(), domain=case.domain(), capacity=case.capacity,
                           **case.init)
-    b.set_calving_state(*R.read_restart_calving(str(tmp_path / "calving.res.nc")))
+    b.set_calving_state(*R.read_restart_calving(str(tmp_path / "calving.res.nc"), domain=b.domain))
     b.set_bergs(**R.read_restart_bergs(str(tmp_path / "icebergs.res.nc")))
     for _ in range(3):
         run_gpu(b, case)
