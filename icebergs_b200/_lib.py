@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("KID_B200_LIB") or os.path.join(_HERE, "lib", "libkid_
 EXPORTS = [
     "kid_default_params", "kid_single_domain", "kid_define_domain", "kid_init", "kid_set_bergs",
     "kid_get_bergs", "kid_count_bergs", "kid_set_bonds", "kid_get_bonds", "kid_set_calving_state",
-    "kid_get_calving_state", "kid_run", "kid_set_forcing", "kid_step_resident", "kid_last_timing",
+    "kid_get_calving_state", "kid_run", "kid_prefetch_forcing", "kid_set_forcing", "kid_step_resident", "kid_last_timing",
     "kid_kernel_launches", "kid_get_counters", "kid_get_grid_field", "kid_stock", "kid_incr_mass",
     "kid_sort_bergs", "kid_synchronize", "kid_end", "kid_last_error", "kid_version",
     "kid_nccl_unique_id", "kid_nccl_init", "kid_nccl_destroy", "kid_pack_width",
@@ -55,6 +55,7 @@ def load() -> C.CDLL:
     lib.kid_get_calving_state.argtypes = [_vp, _vp, _vp, _vp]
     lib.kid_run.argtypes = [_vp, C.c_int32, C.c_double] + [_vp] * 12 + [C.c_int32, C.c_int32] + [_vp] * 4
     lib.kid_set_forcing.argtypes = [_vp] + [_vp] * 12 + [C.c_int32, C.c_int32, _vp]
+    lib.kid_prefetch_forcing.argtypes = [_vp] + [_vp] * 13
     lib.kid_step_resident.argtypes = [_vp, C.c_int32, C.c_int32, C.c_double]
     lib.kid_last_timing.argtypes = [_vp, _dp]
     lib.kid_kernel_launches.argtypes = [_vp]

@@ -348,6 +348,20 @@ def icebergs_run(bergs: Icebergs, time, calving, uo, vo, ui, vi, tauxa, tauya, s
     bergs._check(rc)
 
 
+def icebergs_prefetch(bergs: Icebergs, calving, uo, vo, ui, vi, tauxa, tauya, ssh, sst, calving_hflx, cn, hi, sss=None):
+    """kid_prefetch_forcing: queue the host-to-device copies of the NEXT icebergs_run's inputs now (they overlap the step
+    in flight).  The arrays must be C-contiguous float64 of the shapes icebergs_run takes, stay unchanged until that
+    icebergs_run has returned, and be passed to it as the same objects."""
+    d = bergs.domain
+    ring, comp = (d.njc + 2, d.nic + 2), (d.njc, d.nic)
+    arrs = [(calving, comp), (uo, ring), (vo, ring), (ui, ring), (vi, ring), (tauxa, comp), (tauya, comp), (ssh, ring),
+            (sst, comp), (calving_hflx, comp), (cn, ring), (hi, ring), (sss, comp)]
+    for a, shape in arrs:
+        if a is not None and not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.shape == shape):
+            raise ValueError("icebergs_prefetch: arrays must be C-contiguous float64 of the shapes icebergs_run takes (no copies are made)")
+    bergs._check(lib().kid_prefetch_forcing(bergs.handle, *[_ptr(a) for a, _ in arrs]))
+
+
 def icebergs_end(bergs: Icebergs):
     """icebergs_end, I:8152."""
     if bergs._h:

@@ -71,7 +71,18 @@ struct kid_handle {
   int32_t *cell_count = nullptr, *cell_start = nullptr, *perm = nullptr;   // perm: the sort's result payload (alias)
   int32_t *scan_sums = nullptr, *scan_total = nullptr;
   std::vector<double*> field_allocs;
-  double* in_stage[13] = {nullptr};  // device staging of the icebergs_run inputs
+  // device staging of the icebergs_run inputs: two sets.  kid_run copies into a free one; kid_prefetch_forcing fills the
+  // other on a copy stream while the current step computes, and the kid_run that brings the same host arrays takes it.
+  struct StageSet {
+    double* buf[13] = {nullptr};
+    const double* src[13] = {nullptr};      // host arrays of a pending prefetch
+    int pending = 0;                        // prefetched, not consumed yet
+    unsigned long long seq = 0;
+    cudaEvent_t ev_copied = nullptr, ev_consumed = nullptr;
+    int consumed_recorded = 0;
+  } stage[2];
+  unsigned long long stage_seq = 0;
+  cudaStream_t cstream = nullptr;
   double* out_stage[2] = {nullptr};
   double *tmp_u = nullptr, *tmp_v = nullptr;
   cudaStream_t stream = nullptr;
@@ -868,7 +879,7 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   CK(cudaMalloc(&g.cell, sizeof(CellRec) * n2));
   CK(cudaMalloc(&g.lonlat, sizeof(LonLat) * n2));
   CK(cudaMalloc(&g.rect, sizeof(RectCell) * n2));
-  for (int k = 0; k < 13; k++) CK(cudaMalloc(&h->in_stage[k], sizeof(double) * (size_t)(h->nic + 2) * (h->njc + 2)));
+  for (int k = 0; k < 13; k++) CK(cudaMalloc(&h->stage[0].buf[k], sizeof(double) * (size_t)(h->nic + 2) * (h->njc + 2)));
   for (int k = 0; k < 2; k++) CK(cudaMalloc(&h->out_stage[k], sizeof(double) * (size_t)h->nic * h->njc));
 
   // ---- berg store
@@ -1033,7 +1044,12 @@ extern "C" int32_t kid_end(kid_t** hp) {
   cudaStreamSynchronize(h->stream);
   for (double* p : h->field_allocs) cudaFree(p);
   cudaFree(h->g.iceberg_counter_grd); cudaFree(h->g.corner); cudaFree(h->g.cell); cudaFree(h->g.lonlat); cudaFree(h->g.rect);
-  for (auto p : h->in_stage) cudaFree(p);
+  for (auto& st : h->stage) {
+    for (auto p : st.buf) cudaFree(p);
+    if (st.ev_copied) cudaEventDestroy(st.ev_copied);
+    if (st.ev_consumed) cudaEventDestroy(st.ev_consumed);
+  }
+  if (h->cstream) cudaStreamDestroy(h->cstream);
   for (auto p : h->out_stage) cudaFree(p);
   for (auto p : h->out_stage3) cudaFree(p);
   for (int c = 0; c < C_NCOLS; c++) cudaFree(h->b.f64[c]);
@@ -1786,9 +1802,28 @@ static int ingest_forcing(kid_t* h, const double* calving, const double* uo, con
   const size_t nc = (size_t)h->nic * h->njc, nr = (size_t)(h->nic + 2) * (h->njc + 2);
   const double* src[13] = {calving, uo, vo, ui, vi, tauxa, tauya, ssh, sst, calving_hflx, cn, hi, sss};
   const size_t cnt[13] = {nc, nr, nr, nr, nr, nc, nc, nr, nc, nc, nr, nr, nc};
-  for (int k = 0; k < 13; k++)
-    if (src[k]) CK(cudaMemcpyAsync(h->in_stage[k], src[k], sizeof(double) * cnt[k], cudaMemcpyHostToDevice, h->stream));
-  double** st = h->in_stage;
+  // a pending prefetch of exactly these arrays (kid_prefetch_forcing)?  Otherwise copy into a set nothing is pending in.
+  int use = -1;
+  for (int q = 0; q < 2 && use < 0; q++) {
+    if (!h->stage[q].pending) continue;
+    bool same = true;
+    for (int k = 0; k < 13 && same; k++) same = (src[k] == h->stage[q].src[k]);
+    if (same) use = q;
+  }
+  if (use >= 0) {
+    CK(cudaStreamWaitEvent(h->stream, h->stage[use].ev_copied, 0));      // inputs already on their way
+  } else {
+    use = (!h->stage[0].pending) ? 0 : (h->stage[1].buf[0] && !h->stage[1].pending) ? 1 : -1;
+    if (use < 0) {         // both sets hold prefetches this call does not match: the older one is dropped
+      use = (h->stage[0].seq < h->stage[1].seq || !h->stage[1].buf[0]) ? 0 : 1;
+      CK(cudaStreamSynchronize(h->cstream));
+    }
+    for (int k = 0; k < 13; k++)
+      if (src[k]) CK(cudaMemcpyAsync(h->stage[use].buf[k], src[k], sizeof(double) * cnt[k], cudaMemcpyHostToDevice, h->stream));
+  }
+  h->stage[use].pending = 0;
+  const int used_set = use;
+  double** st = h->stage[use].buf;
   // halo updates: immediate on one rank (cyclic wrap); between ranks the fields are independent of
   // each other, so all strips travel in ONE exchange before the scrub
   std::vector<double*> pending;
@@ -1838,8 +1873,51 @@ static int ingest_forcing(kid_t* h, const double* calving, const double* uo, con
   if (!pending.empty()) { int rc_ = halo_exchange(h, pending.data(), (int)pending.size()); if (rc_) return rc_; }
   LAUNCH(h, k_scrub, n2, 256, g, n2);
   LAUNCH(h, k_pack_forcing, n2, 256, g, n2);
+  if (h->stage[used_set].ev_consumed) {        // the staging set is free again
+    CK(cudaEventRecord(h->stage[used_set].ev_consumed, h->stream));
+    h->stage[used_set].consumed_recorded = 1;
+  }
   CK(cudaMemcpyAsync(h->hflags, h->dflags, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
   h->forcing_set = 1;
+  return KID_OK;
+}
+
+// The inputs of the NEXT kid_run / kid_set_forcing call, announced early: their host-to-device copies are queued on a
+// copy stream into the second staging set and overlap whatever the handle's main stream is doing (the current step).
+// The call returns at once; the arrays must stay unchanged until the kid_run that consumes them has returned.  A
+// following kid_run with exactly these pointers skips its own copies; with other pointers the prefetch is dropped.
+extern "C" int32_t kid_prefetch_forcing(kid_t* h, const double* calving, const double* uo, const double* vo,
+                                        const double* ui, const double* vi, const double* tauxa, const double* tauya,
+                                        const double* ssh, const double* sst, const double* calving_hflx,
+                                        const double* cn, const double* hi, const double* sss) {
+  if (!h) return KID_ERR_ARG;
+  if (h->fatal) return KID_ERR_STATE;
+  cudaSetDevice(h->d.device);
+  const size_t nc = (size_t)h->nic * h->njc, nr = (size_t)(h->nic + 2) * (h->njc + 2);
+  if (!h->cstream) {
+    CK(cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking));
+    for (int k = 0; k < 13; k++) CK(cudaMalloc(&h->stage[1].buf[k], sizeof(double) * nr));
+    for (auto& st : h->stage) {
+      CK(cudaEventCreateWithFlags(&st.ev_copied, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&st.ev_consumed, cudaEventDisableTiming));
+    }
+  }
+  const double* src[13] = {calving, uo, vo, ui, vi, tauxa, tauya, ssh, sst, calving_hflx, cn, hi, sss};
+  const size_t cnt[13] = {nc, nr, nr, nr, nr, nc, nc, nr, nc, nc, nr, nr, nc};
+  // one prefetch may wait for its kid_run while the next is announced (announce k+1, then run k): the set that holds
+  // no pending prefetch is the target; with both pending the call is refused
+  int q = !h->stage[0].pending ? 0 : !h->stage[1].pending ? 1 : -1;
+  if (q < 0) return fail(h, KID_ERR_STATE, "kid_prefetch_forcing: two announced input sets are already waiting for their kid_run");
+  kid_handle::StageSet& st = h->stage[q];
+  // the set was last read by the ingest kernels of an earlier call on the main stream
+  if (st.consumed_recorded) CK(cudaStreamWaitEvent(h->cstream, st.ev_consumed, 0));
+  for (int k = 0; k < 13; k++) {
+    st.src[k] = src[k];
+    if (src[k]) CK(cudaMemcpyAsync(st.buf[k], src[k], sizeof(double) * cnt[k], cudaMemcpyHostToDevice, h->cstream));
+  }
+  CK(cudaEventRecord(st.ev_copied, h->cstream));
+  st.pending = 1;
+  st.seq = ++h->stage_seq;
   return KID_OK;
 }
 

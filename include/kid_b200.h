@@ -359,6 +359,21 @@ int32_t kid_run(kid_t* h, int32_t year, double yearday,
                 double* mass_berg, double* ustar_berg, double* area_berg);
 
 /*
+ * Optional: announce the inputs of the NEXT kid_run() early.  Their host-to-device copies are queued on a copy stream
+ * and overlap the step that is still computing; the call returns at once.  The arrays (pinned host memory for a
+ * real overlap) must stay unchanged until the kid_run() that consumes them has returned; that kid_run() must be given
+ * exactly these pointers, otherwise the prefetch is dropped and kid_run() copies as usual.  No reference counterpart:
+ * icebergs_run (I:5074) receives its forcing when it is called; a coupler that has the next step's fields ready
+ * (the stand-alone driver's forcing is analytic, D:341-420) hides the PCIe transfer this way.
+ */
+int32_t kid_prefetch_forcing(kid_t* h,
+                             const double* calving, const double* uo, const double* vo,
+                             const double* ui, const double* vi,
+                             const double* tauxa, const double* tauya,
+                             const double* ssh, const double* sst, const double* calving_hflx,
+                             const double* cn, const double* hi, const double* sss);
+
+/*
  * Device-resident variant used for the HBM-resident throughput figure: the
  * forcing set by the last kid_run()/kid_set_forcing() stays on the device and
  * `nsteps` steps are taken with it (no host<->device traffic, no return fields).
