@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "kid_kernels.cuh"
+#include "kid_step_tma.cuh"
 #include "kid_sort.cuh"
 #include "kid_comm.cuh"
 #include "kid_interact.cuh"
@@ -62,6 +63,8 @@ struct kid_handle {
   uint32_t* slow_slots = nullptr;         // k_step_fast's deferred bergs (kid_kernels.cuh)
   unsigned long long* slow_count = nullptr;
   int fast_path = 1;                      // KID_NO_FAST=1 (diagnostics): the one-kernel path only
+  int tma_path = 1;                       // KID_NO_TMA=1 (diagnostics): k_step_fast instead of the persistent bulk-copy kernel
+  int tma_ctas_per_sm = 0;                // resident CTAs of k_step_tma per SM (occupancy query at init)
   int fast_launched = 0;
   int scatter_dense_forced = -1;          // KID_SCATTER_DENSE (diagnostics): force a flux-scatter variant
   DevCounters* dcnt = nullptr;
@@ -918,6 +921,19 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   CK(cudaMalloc(&h->slow_slots, sizeof(uint32_t) * h->capacity));
   CK(cudaMalloc(&h->slow_count, sizeof(unsigned long long)));
   if (getenv("KID_NO_FAST")) h->fast_path = 0;
+  if (getenv("KID_NO_TMA")) h->tma_path = 0;
+  if (h->fast_path && h->tma_path) {
+    // k_step_tma: two tile stages of dynamic shared memory per CTA; as many resident CTAs as registers / smem allow
+    const size_t smem = sizeof(TileStage) * kTmaStages;
+    int nb0 = 0, nb1 = 0;
+    if (cudaFuncSetAttribute(k_step_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+        cudaFuncSetAttribute(k_step_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb0, k_step_tma<false>, KID_BLOCK, smem) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb1, k_step_tma<true>, KID_BLOCK, smem) == cudaSuccess)
+      h->tma_ctas_per_sm = std::min(nb0, nb1);
+    if (const char* e = getenv("KID_TMA_CTAS")) h->tma_ctas_per_sm = std::min(h->tma_ctas_per_sm, atoi(e));
+    (void)cudaGetLastError();
+  }
   CK(cudaMallocHost(&h->h_totals, 2 * sizeof(int32_t)));
   CK(cudaMallocHost(&h->h_nslots, sizeof(unsigned long long)));
   for (int k = 0; k < KID_GATHER_NC; k++) CK(cudaMalloc(&h->spare_f64[k], sizeof(double) * h->capacity));
@@ -2093,7 +2109,16 @@ static void launch_step(kid_t* h, long long s0, long long s1, bool main_launch =
   if (!FL && !DG && main_launch && h->fast_path && lean_config(h) && h->p.grid_is_regular && n > 0) {
     cudaMemsetAsync(h->slow_count, 0, sizeof(unsigned long long), h->stream);
     SlowList sl{h->slow_slots, h->slow_count, h->capacity};
-    if (h->scatter_dense) { LAUNCH(h, (k_step_fast<true>), n, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s1, s0, sl); }
+    if (h->tma_path && h->tma_ctas_per_sm > 0 && (s0 % KID_BLOCK) == 0) {
+      // persistent: one grid of resident CTAs, each walking tiles b, b + G, ... with the next tile's columns in flight
+      const long long ntiles = (n + KID_BLOCK - 1) / KID_BLOCK;
+      const unsigned grid = (unsigned)std::min<long long>(ntiles, (long long)h->tma_ctas_per_sm * h->num_sms);
+      const size_t smem = sizeof(TileStage) * kTmaStages;
+      if (h->scatter_dense) k_step_tma<true><<<grid, KID_BLOCK, smem, h->stream>>>(h->g, h->b, h->dp, h->dcnt, s1, s0, sl);
+      else k_step_tma<false><<<grid, KID_BLOCK, smem, h->stream>>>(h->g, h->b, h->dp, h->dcnt, s1, s0, sl);
+      h->launches++;
+    }
+    else if (h->scatter_dense) { LAUNCH(h, (k_step_fast<true>), n, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s1, s0, sl); }
     else { LAUNCH(h, (k_step_fast<false>), n, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s1, s0, sl); }
     k_step_slow<<<2 * h->num_sms, KID_BLOCK, 0, h->stream>>>(h->g, h->b, h->dp, h->dcnt, sl); h->launches++;
     h->fast_launched = 1;
