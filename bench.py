@@ -141,6 +141,16 @@ class ClockSampler:
                 "window": "nvidia-smi -lms 50 over the timed region, the e2e loop and 0.6 s of the same resident stepping kept up after them"}
 
 
+def trace(msg):
+    """KID_BENCH_TRACE=1: stage markers on stderr (which stage a hung multi-rank run is in)"""
+    if os.environ.get("KID_BENCH_TRACE"):
+        sys.stderr.write(f"[bench rank {os.environ.get('RANK', '0')} +{time.perf_counter() - _T0:.1f}s] {msg}\n")
+        sys.stderr.flush()
+
+
+_T0 = time.perf_counter()
+
+
 def pinned(a):
     import torch
     t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
@@ -310,6 +320,7 @@ def run_drift(args, rank, world, local_rank, dom, n_per, clocks, do_e2e, seed_st
         del cols
         done += m
     occupied = int(occupied_cells.sum())
+    trace(f"seeded {n_per} bergs")
     f = grid.forcing()
     keep, fp = [], {}
     for k, v in f.items():
@@ -356,15 +367,18 @@ def run_drift(args, rank, world, local_rank, dom, n_per, clocks, do_e2e, seed_st
 
     # ---- HBM-resident throughput: forcing on the device, K steps
     run_once()                                  # uploads forcing, first step
+    trace("first icebergs_run done")
     place_sorts(args.warmup)
     bergs.step_resident(args.warmup, 1, 0.0)    # W untimed warm-up steps (ends on a sort)
     place_sorts(args.steps)
+    trace("warm-up done")
     barrier()
     l0, s0 = bergs.kernel_launches(), bergs.sorts_done()
     t0 = time.perf_counter()
     bergs.step_resident(args.steps, 1, 0.0)
     barrier()
     wall = time.perf_counter() - t0
+    trace("timed resident steps done")
     if clocks is not None:
         clocks.mark(t0, t0 + wall)
     l1, s1 = bergs.kernel_launches(), bergs.sorts_done()
@@ -408,6 +422,7 @@ def run_drift(args, rank, world, local_rank, dom, n_per, clocks, do_e2e, seed_st
             run_once()
         barrier()
         sync_wall = time.perf_counter() - t0
+        trace("e2e: plain calls done")
         if state["fut"] is not None:
             state["fut"].result()
         # (b) the same calls with the next step's forcing announced early (kid_prefetch_forcing): two sets of pinned
@@ -450,6 +465,7 @@ def run_drift(args, rank, world, local_rank, dom, n_per, clocks, do_e2e, seed_st
         pipelined(args.steps, kk)
         barrier()
         e2e_wall = time.perf_counter() - t0
+        trace("e2e: announced calls done")
         if clocks is not None:
             clocks.mark(t0 - sync_wall, t0 + e2e_wall)
         tw = torch.tensor([e2e_wall, sync_wall], dtype=torch.float64, device="cuda")
@@ -468,13 +484,15 @@ def run_drift(args, rank, world, local_rank, dom, n_per, clocks, do_e2e, seed_st
                               "overlaps the step in flight (PCIe-bound: h2d_bytes_per_step at ~50 GB/s); unpipelined_*: the same "
                               "calls without the announcement (copy, step, copy back in sequence).  The caller rotates the "
                               "inout pairs (the next one is zeroed on a helper thread while the call runs)"}
-    if clocks is not None:
-        # the timed region lasts tens of ms and nvidia-smi samples every 50 ms: the same load is kept up for another
-        # half second so that the clocks / throttle reasons are seen under exactly this kernel mix (untimed)
+    if clocks is not None or multi:
+        # the timed region lasts tens of ms and nvidia-smi samples every 50 ms: the same load is kept up for about another
+        # half second so that the clocks / throttle reasons are seen under exactly this kernel mix (untimed).  Every rank
+        # takes the SAME number of steps: with N > 1 each step holds a migration exchange between the ranks.
         t_a = time.perf_counter()
-        while time.perf_counter() - t_a < 0.6:
+        for _ in range(30):
             bergs.step_resident(16, 1, 0.0)
-        clocks.mark(t_a, time.perf_counter())
+        if clocks is not None:
+            clocks.mark(t_a, time.perf_counter())
     api.icebergs_end(bergs)
     pool.shutdown()
     return out
@@ -531,8 +549,10 @@ def main():
     if multi:
         from icebergs_b200 import parallel
         dom = parallel.make_domain(GNI, GNJ, rank, world, halo=halo, device=local_rank)
+        trace("domain + communicator ready")
         if not args.no_parity:
             parity = nccl_parity_check(rank, world, local_rank, dom.c.nccl_comm)
+            trace(f"NCCL parity check done: {parity}")
             flag = torch.tensor([0 if (parity is None or parity["ok"]) else 1], device="cuda")
             dist.all_reduce(flag, op=dist.ReduceOp.MAX)
             if int(flag[0]):
