@@ -2152,6 +2152,15 @@ static int finish_deferred_exchange(kid_t* h) {
     if (rc) break;
     if (n_recv > 0) {
       const long long s1 = s0 + n_recv;
+      // the slots between the end of the store and the tile-aligned start of the arrivals join the store: dead.  (The
+      // column arrays rotate through the spares of the cell sort, so what lies beyond n_slots is stale data of an
+      // earlier epoch -- possibly with ALIVE flags where the store once reached further.)
+      if (s0 > h->n_slots) {
+        if (cudaMemsetAsync(h->b.flags + h->n_slots, 0, (size_t)(s0 - h->n_slots), h->xstream) != cudaSuccess ||
+            cudaMemsetAsync(h->b.halo_code + h->n_slots, 0, (size_t)(s0 - h->n_slots), h->xstream) != cudaSuccess) {
+          rc = fail(h, KID_ERR_CUDA, "cudaMemsetAsync failed"); break;
+        }
+      }
       // the arrivals' melt lands in this step's flux fields: after the main stream zeroed them
       if (h->ev_zero_recorded && cudaStreamWaitEvent(h->xstream, h->ev_zero, 0) != cudaSuccess) { rc = fail(h, KID_ERR_CUDA, "cudaStreamWaitEvent failed"); break; }
       if (DG) { LAUNCH(h, (k_thermo_range<false, true>), n_recv, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s0, s1, 0); }
@@ -2447,6 +2456,16 @@ extern "C" int32_t kid_step_resident(kid_t* h, int32_t nsteps, int32_t year, dou
     int rc = step_core(h);
     h->defer_ok = 0;
     if (rc) return rc;
+    if (getenv("KID_STEP_CHECK")) {        // diagnostics: which step of a resident call raised a device error flag
+      unsigned int ef = 0;
+      cudaStreamSynchronize(h->stream);
+      if (h->xstream) cudaStreamSynchronize(h->xstream);
+      cudaMemcpy(&ef, &h->dcnt->error_flags, sizeof(ef), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[kid rank %d] resident step %d/%d: n_slots %lld (before %lld) since_sort %d sorts %lld pending %d recv %lld sent %lld flags 0x%x\n",
+              h->d.rank, s, nsteps, h->n_slots, before, h->steps_since_sort, (long long)h->sorts_done, h->xchg_pending,
+              h->n_recv_last, h->n_sent_last, ef);
+      if (ef) return check_device_errors(h);
+    }
     if (h->calving_active && h->n_slots == before) h->calving_active = 0;   // no input, nothing left to calve
   }
   CK(cudaEventRecord(h->ev[T_NPHASE + 1], h->stream));

@@ -152,6 +152,36 @@ def test_overlapped_migration_in_resident_steps():
     grp.close()
 
 
+def test_uneven_resident_calls_with_frequent_sorts():
+    """Resident calls of different lengths (the last two steps of a call migrate synchronously, the others overlap their
+    migration with the next step's kernel and append the arrivals at a tile-aligned slot), plain icebergs_run calls in
+    between and a cell sort every 3 steps: the store shrinks and grows by different amounts from one sort epoch to the
+    next, so slots beyond its end hold stale data of earlier epochs (the column arrays rotate through the sort's spares).
+    Regression: the gap below the aligned arrivals once kept stale ALIVE flags (round 2, found by bench.py --gpus 2).
+    14 steps only: later on a few bergs of this fast-current case jump many cells in a step, where an N-PE run of the
+    reference differs from its own 1-PE run (the data-domain clamps of I:7941-7998)."""
+    case = Case(96, 48, 12000, dt=43200.0, old_bug_bilin=0)
+    grp = parallel.LocalGroup(2)
+    ranks = Ranks(case, 2, lambda r: grp.domain(case.gni, case.gnj, r, halo=case.halo), grp.run)
+    o = case.make_oracle()
+    over = dict(uo=1.2, vo=0.15, tauxa=15.0)
+    fast = {k: np.full_like(case.forcing[k], v) for k, v in over.items()}
+    ranks.step(over); run_oracle(o, case, **fast)
+    grp.run(lambda r: ranks.h[r].set_sort_phase(3, 0))
+    steps = 1
+    for n in (4, 2, 1, 3, 3):
+        if n == 1:
+            ranks.step(over); run_oracle(o, case, **fast)
+        else:
+            ranks.resident(n); o.step_again(n, 1, 0.0)
+        steps += n
+        assert_bergs_match(ranks.bergs(), o.get_bergs(NAMES), rtol=1e-8, context=f"2 ranks, {steps} steps, uneven resident calls")
+    assert ranks.owners_ok()
+    assert sum(b.sorts_done() for b in ranks.h) >= 2 * 4
+    ranks.end()
+    grp.close()
+
+
 def test_nccl_ranks_match_single_rank_oracle():
     """Same check over NCCL: one rank per GPU (threads of this process), needs >= 2 GPUs."""
     import torch
