@@ -63,7 +63,7 @@ struct kid_handle {
   uint32_t* slow_slots = nullptr;         // k_step_fast's deferred bergs (kid_kernels.cuh)
   unsigned long long* slow_count = nullptr;
   int fast_path = 1;                      // KID_NO_FAST=1 (diagnostics): the one-kernel path only
-  int tma_path = 1;                       // KID_NO_TMA=1 (diagnostics): k_step_fast instead of the persistent bulk-copy kernel
+  int tma_path = 0;                       // KID_TMA=1: the persistent bulk-copy kernel (kid_step_tma.cuh) instead of k_step_fast
   int tma_ctas_per_sm = 0;                // resident CTAs of k_step_tma per SM (occupancy query at init)
   int fast_launched = 0;
   int scatter_dense_forced = -1;          // KID_SCATTER_DENSE (diagnostics): force a flux-scatter variant
@@ -921,7 +921,9 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   CK(cudaMalloc(&h->slow_slots, sizeof(uint32_t) * h->capacity));
   CK(cudaMalloc(&h->slow_count, sizeof(unsigned long long)));
   if (getenv("KID_NO_FAST")) h->fast_path = 0;
-  if (getenv("KID_NO_TMA")) h->tma_path = 0;
+  // measured (profiles/r2_notes.md): a tie with k_step_fast on one GPU at 13 bergs per cell, 9 % slower on the denser
+  // tiles of the multi-GPU runs, where its resident CTAs also keep the overlapped migration from getting SM slots
+  if (getenv("KID_TMA") && atoi(getenv("KID_TMA")) > 0) h->tma_path = 1;
   if (h->fast_path && h->tma_path) {
     // k_step_tma: two tile stages of dynamic shared memory per CTA; as many resident CTAs as registers / smem allow
     const size_t smem = sizeof(TileStage) * kTmaStages;
