@@ -23,7 +23,7 @@ EXPORTS = [
     "kid_sort_bergs", "kid_synchronize", "kid_end", "kid_last_error", "kid_version",
     "kid_nccl_unique_id", "kid_nccl_init", "kid_nccl_destroy", "kid_pack_width",
     "kid_local_comm_create", "kid_local_comm_destroy", "kid_owner_rank", "kid_set_sort_phase", "kid_sorts_done", "kid_last_slow_count",
-    "kid_unit_hexagon_into_quadrants", "kid_unit_point_in_triangle",
+    "kid_unit_hexagon_into_quadrants", "kid_unit_point_in_triangle", "kid_record_posn", "kid_trajectory_count", "kid_get_trajectory",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -56,6 +56,9 @@ def load() -> C.CDLL:
     lib.kid_run.argtypes = [_vp, C.c_int32, C.c_double] + [_vp] * 12 + [C.c_int32, C.c_int32] + [_vp] * 4
     lib.kid_set_forcing.argtypes = [_vp] + [_vp] * 12 + [C.c_int32, C.c_int32, _vp]
     lib.kid_prefetch_forcing.argtypes = [_vp] + [_vp] * 13
+    lib.kid_record_posn.argtypes = [_vp]
+    lib.kid_trajectory_count.argtypes = [_vp, C.POINTER(C.c_int64)]
+    lib.kid_get_trajectory.argtypes = [_vp, C.POINTER(C.c_int64), C.POINTER(D.KidTrajColumns), C.c_int32]
     lib.kid_step_resident.argtypes = [_vp, C.c_int32, C.c_int32, C.c_double]
     lib.kid_last_timing.argtypes = [_vp, _dp]
     lib.kid_kernel_launches.argtypes = [_vp]

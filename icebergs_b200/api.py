@@ -203,6 +203,21 @@ class Icebergs:
         self._check(lib().kid_get_bergs(self.handle, C.byref(m), C.byref(c), int(include_halo)))
         return {k: v[: m.value].copy() for k, v in keep.items()}
 
+    def record_posn(self):
+        """record_posn F:5328-5498: sample the bergs that pass the trajectory criteria at the time of the last
+        icebergs_run (the reference samples every traj_sample_hrs, I:5173-5178; the caller holds the date)."""
+        self._check(lib().kid_record_posn(self.handle))
+
+    def get_trajectory(self, clear=True) -> dict:
+        """The samples taken so far, one entry per record of iceberg_trajectories.nc (no particular order)."""
+        n = C.c_int64(0)
+        self._check(lib().kid_trajectory_count(self.handle, C.byref(n)))
+        cap = max(n.value, 1)
+        c, keep = make_columns(cap, want={f[0] for f in D.KidTrajColumns._fields_}, cls=D.KidTrajColumns)
+        m = C.c_int64(cap)
+        self._check(lib().kid_get_trajectory(self.handle, C.byref(m), C.byref(c), int(clear)))
+        return {k: v[: m.value].copy() for k, v in keep.items()}
+
     def set_bonds(self, **cols):
         """read_restart_bonds (columns of bonds_iceberg.res.nc, fmsio:473-493); with no columns and
         manually_initialize_bonds the bonds come from initialize_iceberg_bonds (I:356-441)."""
@@ -328,7 +343,7 @@ def icebergs_init(gni, gnj, dt, Time, ice_lon, ice_lat, ice_wet, ice_dx, ice_dy,
 
 def icebergs_run(bergs: Icebergs, time, calving, uo, vo, ui, vi, tauxa, tauya, ssh, sst, calving_hflx, cn, hi,
                  stagger=BGRID_NE, stress_stagger=None, sss=None, mass_berg=None, ustar_berg=None,
-                 area_berg=None):
+                 area_berg=None, sample_traj=False):
     """icebergs_run, I:5074-5096.  ``calving`` and ``calving_hflx`` are updated in place
     (intent inout), as are the optional mass_berg/ustar_berg/area_berg outputs."""
     d = bergs.domain
@@ -346,6 +361,8 @@ def icebergs_run(bergs: Icebergs, time, calving, uo, vo, ui, vi, tauxa, tauya, s
                        _ptr(calving_hflx), _ptr(cn_), _ptr(hi_), stagger, stress_stagger, _ptr(sss_),
                        _ptr(mass_berg), _ptr(ustar_berg), _ptr(area_berg))
     bergs._check(rc)
+    if sample_traj:                       # I:5516: if (sample_traj .or. writeandstop) call record_posn(bergs)
+        bergs.record_posn()
 
 
 def icebergs_prefetch(bergs: Icebergs, calving, uo, vo, ui, vi, tauxa, tauya, ssh, sst, calving_hflx, cn, hi, sss=None):

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "kid_b200.cu")
 DEPS = [os.path.join(_HERE, "csrc", f) for f in
         ("kid_b200.cu", "kid_kernels.cuh", "kid_physics.cuh", "kid_geom.cuh", "kid_device.cuh", "kid_comm.cuh",
-         "kid_interact.cuh", "kid_spread.cuh", "kid_mts.cuh", "kid_sort.cuh", "kid_step_tma.cuh")]
+         "kid_interact.cuh", "kid_spread.cuh", "kid_mts.cuh", "kid_sort.cuh", "kid_step_tma.cuh", "kid_traj.cuh")]
 DEPS.append(os.path.join(os.path.dirname(_HERE), "include", "kid_b200.h"))
 OUT = os.path.join(_HERE, "lib", "libkid_b200.so")
 

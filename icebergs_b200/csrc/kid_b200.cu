@@ -21,6 +21,7 @@
 #include "kid_interact.cuh"
 #include "kid_spread.cuh"
 #include "kid_mts.cuh"
+#include "kid_traj.cuh"
 
 using namespace kid;
 
@@ -86,6 +87,10 @@ struct kid_handle {
   } stage[2];
   unsigned long long stage_seq = 0;
   cudaStream_t cstream = nullptr;
+  // trajectory samples (kid_traj.cuh): TR_NCOL column arrays of traj_cap doubles, traj_n records filled
+  double* traj_buf = nullptr;
+  long long traj_cap = 0, traj_n = 0;
+  unsigned long long* traj_cursor = nullptr;
   double* out_stage[2] = {nullptr};
   double *tmp_u = nullptr, *tmp_v = nullptr;
   cudaStream_t stream = nullptr;
@@ -193,6 +198,7 @@ extern "C" void kid_default_params(KidParams* p) {
   p->displace_fl_bergs = 1; p->fl_bits_erosion_to_bergy_bits = 1;
   p->fl_youngs = 1.e7; p->fl_strength = 250.; p->new_berg_from_fl_bits_mass_thres = 1.e12;
   p->LoW_ratio = 1.5;
+  p->save_short_traj = 1; p->save_fl_traj = 1; p->traj_area_thres_fl = 1.e9; p->save_all_traj_year = 1.7976931348623157e308;
   p->use_three_equation_model = 1; p->const_gamma = 1; p->gamma_t_3eq = 0.022; p->ustar_icebergs_bg = 0.001;
   p->utide_icebergs = 0.; p->cdrag_icebergs = 1.5e-3;
   p->add_weight_to_ocean = 1; p->use_old_spreading = 1; p->rotate_icebergs_for_mass_spreading = 1;
@@ -1068,6 +1074,7 @@ extern "C" int32_t kid_end(kid_t** hp) {
     if (st.ev_consumed) cudaEventDestroy(st.ev_consumed);
   }
   if (h->cstream) cudaStreamDestroy(h->cstream);
+  cudaFree(h->traj_buf); cudaFree(h->traj_cursor);
   for (auto p : h->out_stage) cudaFree(p);
   for (auto p : h->out_stage3) cudaFree(p);
   for (int c = 0; c < C_NCOLS; c++) cudaFree(h->b.f64[c]);
@@ -2476,6 +2483,88 @@ extern "C" int32_t kid_step_resident(kid_t* h, int32_t nsteps, int32_t year, dou
   float ms = 0;
   if (cudaEventElapsedTime(&ms, h->ev[T_NPHASE], h->ev[T_NPHASE + 1]) == cudaSuccess) h->timing[6] = ms;
   return rc;
+}
+
+// ------------------------------------------------------------------ trajectories (record_posn F:5328-5498)
+extern "C" int32_t kid_record_posn(kid_t* h) {
+  if (!h) return KID_ERR_ARG;
+  if (h->fatal) return KID_ERR_STATE;
+  cudaSetDevice(h->d.device);
+  const long long ns = h->n_slots;
+  if (ns <= 0) return KID_OK;
+  if (!h->traj_cursor) {
+    CK(cudaMalloc(&h->traj_cursor, sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(h->traj_cursor, 0, sizeof(unsigned long long), h->stream));
+  }
+  if (h->traj_n + ns > h->traj_cap) {          // room for one record per slot; the store grows geometrically
+    const long long cap = std::max<long long>(2 * h->traj_cap, h->traj_n + ns + 1024);
+    double* nb = nullptr;
+    CK(cudaMalloc(&nb, sizeof(double) * (size_t)cap * TR_NCOL));
+    for (int c = 0; c < TR_NCOL && h->traj_n > 0; c++)
+      CK(cudaMemcpyAsync(nb + (size_t)c * cap, h->traj_buf + (size_t)c * h->traj_cap, sizeof(double) * h->traj_n, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(h->traj_buf);
+    h->traj_buf = nb; h->traj_cap = cap;
+  }
+  TrajParams tp;
+  const KidParams& p = h->p;
+  tp.area_thres = p.traj_area_thres * 1.e6; tp.area_thres2 = p.traj_area_thres_sntbc * 1.e6; tp.area_thres3 = p.traj_area_thres_fl * 1.e6;
+  tp.save_all_traj_year = p.save_all_traj_year; tp.start_mass_thres_n = p.save_traj_by_class_start_mass_thres_n;
+  tp.start_mass_thres_s = p.save_traj_by_class_start_mass_thres_s; tp.rho_bergs = p.rho_bergs;
+  tp.save_nonfl_traj_by_class = p.save_nonfl_traj_by_class; tp.old_interp_flds_order = p.old_interp_flds_order;
+  tp.mts = p.mts; tp.dem = p.dem;
+  if (!h->forcing_set && !p.mts) return fail(h, KID_ERR_STATE, "kid_record_posn: no forcing on the device yet (the samples hold the berg's environment)");
+  LAUNCH(h, k_record_posn, ns, 128, h->g, h->b, h->dp, tp, h->dcnt, ns, h->traj_buf, h->traj_cap, h->traj_cursor);
+  unsigned long long n = 0;
+  CK(cudaMemcpyAsync(&n, h->traj_cursor, sizeof(n), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->traj_n = (long long)std::min<unsigned long long>(n, (unsigned long long)h->traj_cap);
+  return check_device_errors(h);
+}
+
+extern "C" int32_t kid_trajectory_count(kid_t* h, int64_t* n) {
+  if (!h || !n) return KID_ERR_ARG;
+  *n = h->traj_n;
+  return KID_OK;
+}
+
+extern "C" int32_t kid_get_trajectory(kid_t* h, int64_t* n, KidTrajColumns* c, int32_t clear) {
+  if (!h || !n || !c) return KID_ERR_ARG;
+  cudaSetDevice(h->d.device);
+  const long long m = h->traj_n;
+  if (*n < m) { *n = m; return fail(h, KID_ERR_CAPACITY, "kid_get_trajectory: output arrays too small"); }
+  *n = m;
+  if (m > 0) {
+    CK(cudaStreamSynchronize(h->stream));
+    struct DC { double* dst; int col; } dcs[] = {
+      {c->lon, TR_LON}, {c->lat, TR_LAT}, {c->day, TR_DAY}, {c->mass, TR_MASS}, {c->start_mass, TR_START_MASS},
+      {c->thickness, TR_THICKNESS}, {c->mass_of_bits, TR_MASS_OF_BITS}, {c->uvel, TR_UVEL}, {c->vvel, TR_VVEL},
+      {c->mass_scaling, TR_MASS_SCALING}, {c->mass_of_fl_bits, TR_MASS_OF_FL_BITS},
+      {c->mass_of_fl_bergy_bits, TR_MASS_OF_FL_BERGY_BITS}, {c->fl_k, TR_FL_K}, {c->uvel_prev, TR_UVEL_PREV},
+      {c->vvel_prev, TR_VVEL_PREV}, {c->heat_density, TR_HEAT_DENSITY}, {c->width, TR_WIDTH}, {c->length, TR_LENGTH},
+      {c->uo, TR_UO}, {c->vo, TR_VO}, {c->ui, TR_UI}, {c->vi, TR_VI}, {c->ua, TR_UA}, {c->va, TR_VA}, {c->ssh_x, TR_SSH_X},
+      {c->ssh_y, TR_SSH_Y}, {c->sst, TR_SST}, {c->sss, TR_SSS}, {c->cn, TR_CN}, {c->hi, TR_HI}, {c->axn, TR_AXN},
+      {c->ayn, TR_AYN}, {c->bxn, TR_BXN}, {c->byn, TR_BYN}, {c->halo_berg, TR_HALO_BERG}, {c->static_berg, TR_STATIC_BERG},
+      {c->od, TR_OD}, {c->axn_fast, TR_AXN_FAST}, {c->ayn_fast, TR_AYN_FAST}, {c->bxn_fast, TR_BXN_FAST},
+      {c->byn_fast, TR_BYN_FAST}, {c->ang_vel, TR_ANG_VEL}, {c->ang_accel, TR_ANG_ACCEL}, {c->rot, TR_ROT}};
+    for (const DC& d : dcs)
+      if (d.dst) CK(cudaMemcpy(d.dst, h->traj_buf + (size_t)d.col * h->traj_cap, sizeof(double) * m, cudaMemcpyDeviceToHost));
+    std::vector<double> t((size_t)m);
+    if (c->year) {
+      CK(cudaMemcpy(t.data(), h->traj_buf + (size_t)TR_YEAR * h->traj_cap, sizeof(double) * m, cudaMemcpyDeviceToHost));
+      for (long long k = 0; k < m; k++) c->year[k] = (int32_t)t[(size_t)k];
+    }
+    if (c->n_bonds) {
+      CK(cudaMemcpy(t.data(), h->traj_buf + (size_t)TR_N_BONDS * h->traj_cap, sizeof(double) * m, cudaMemcpyDeviceToHost));
+      for (long long k = 0; k < m; k++) c->n_bonds[k] = (int32_t)t[(size_t)k];
+    }
+    if (c->id) CK(cudaMemcpy(c->id, h->traj_buf + (size_t)TR_ID * h->traj_cap, sizeof(double) * m, cudaMemcpyDeviceToHost));   // bit patterns
+  }
+  if (clear) {
+    h->traj_n = 0;
+    if (h->traj_cursor) CK(cudaMemsetAsync(h->traj_cursor, 0, sizeof(unsigned long long), h->stream));
+  }
+  return KID_OK;
 }
 
 extern "C" int32_t kid_last_timing(kid_t* h, double ms[8]) {

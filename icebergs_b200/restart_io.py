@@ -218,3 +218,69 @@ def read_restart_calving(path, domain=None):
     osh[h:h + d.njc, h:h + d.nic] = sh[js, is_]
     oic[h:h + d.njc, h:h + d.nic] = ic[js, is_]
     return osi, osh, oic
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# iceberg_trajectories.nc, write_trajectory fmsio:1575-2047 (the non-FMS-IO branch, fmsio:1893-2040: one unlimited
+# dimension "i", the variables below with long_name / units attributes).  Which variables a file holds follows
+# save_short_traj / save_fl_traj and the scheme switches exactly as the reference's def_var sequence does.
+TRAJ_BASE = [("lon", "d", "longitude", "degrees_E"), ("lat", "d", "latitude", "degrees_N"), ("year", "i", "year", "years"),
+             ("day", "d", "year day", "days"), ("id_cnt", "i", "counter component of iceberg id", "dimensionless"),
+             ("id_ij", "i", "position component of iceberg id", "dimensionless")]
+TRAJ_FL = [("mass", "d", "mass", "kg"), ("start_mass", "d", "start_mass", "kg"), ("thickness", "d", "thickness", "m"),
+           ("mass_of_bits", "d", "mass_of_bits", "kg"), ("uvel", "d", "zonal spped", "m/s"), ("vvel", "d", "meridional spped", "m/s")]
+TRAJ_FL_FOOTLOOSE = [("mass_scaling", "d", "mass_scaling", "dimensionless"), ("mass_of_fl_bits", "d", "mass_of_fl_bits", "kg"),
+                     ("mass_of_fl_bergy_bits", "d", "mass_of_fl_bergy_bits", "kg"), ("fl_k", "d", "footloose calving k", "none")]
+# (long names and units as the reference writes them, typos and the 'm' of the accelerations included)
+TRAJ_LONG = [("uvel_prev", "d", "zonal speed mts", "m/s"), ("vvel_prev", "d", "meridional speed mts", "m/s"),
+             ("uo", "d", "ocean zonal spped", "m/s"), ("vo", "d", "ocean meridional spped", "m/s"),
+             ("ui", "d", "ice zonal spped", "m/s"), ("vi", "d", "ice meridional spped", "m/s"),
+             ("ua", "d", "atmos zonal spped", "m/s"), ("va", "d", "atmos meridional spped", "m/s"),
+             ("heat_density", "d", "heat_density", "J/kg"), ("width", "d", "width", "m"), ("length", "d", "length", "m"),
+             ("ssh_x", "d", "sea surface height gradient_x", "non-dim"), ("ssh_y", "d", "sea surface height gradient_y", "non-dim"),
+             ("sst", "d", "sea surface temperature", "degrees_C"), ("sss", "d", "sea surface salinity", "psu"),
+             ("cn", "d", "sea ice concentration", "none"), ("hi", "d", "sea ice thickness", "m"),
+             ("axn", "d", "explicit zonal acceleration", "m"), ("ayn", "d", "explicit meridional acceleration", "m"),
+             ("bxn", "d", "implicit zonal acceleration", "m"), ("byn", "d", "implicit meridional acceleration", "m"),
+             ("halo_berg", "d", "halo status", "non-dim"), ("od", "d", "ocean_depth", "m")]
+TRAJ_MTS = [("axn_fast", "d", "explicit fast step zonal acceleration", "m"), ("ayn_fast", "d", "explicit fast step meridional acceleration", "m"),
+            ("bxn_fast", "d", "implicit fast step zonal acceleration", "m"), ("byn_fast", "d", "implicit fast step meridional acceleration", "m")]
+TRAJ_BONDS = [("n_bonds", "i", "number of bonds", "dimensionless")]
+TRAJ_DEM = [("ang_vel", "d", "angular velocity", "rad/s"), ("ang_accel", "d", "angular acceleration", "rad/s^2"), ("rot", "d", "accumulated rotation", "rad")]
+
+
+def trajectory_variables(save_short_traj=True, save_fl_traj=True, footloose=False, mts=False, iceberg_bonds_on=False, dem=False):
+    """The variables of iceberg_trajectories.nc for a given configuration (fmsio:1925-1990)."""
+    v = list(TRAJ_BASE)
+    if save_fl_traj:
+        v += TRAJ_FL + (TRAJ_FL_FOOTLOOSE if footloose else [])
+    if not save_short_traj:
+        v += TRAJ_LONG + (TRAJ_MTS if mts else []) + (TRAJ_BONDS if iceberg_bonds_on else []) + (TRAJ_DEM if dem else [])
+    return v
+
+
+def write_trajectory(path, traj, **config):
+    """write_trajectory (fmsio:1575) from ``Icebergs.get_trajectory()``; ``config`` as in trajectory_variables.  Records are
+    written grouped by berg and in time order, as the reference's per-berg lists come out."""
+    order = np.lexsort((traj["day"], traj["year"], traj["id"])) if len(traj["id"]) else np.zeros(0, dtype=np.int64)
+    cnt, ij = split_id(traj["id"][order]) if len(order) else (np.zeros(0, np.int32), np.zeros(0, np.int32))
+    cols = {k: np.asarray(v)[order] for k, v in traj.items()}
+    cols["id_cnt"], cols["id_ij"] = cnt, ij
+    f = netcdf_file(path, "w", version=1)
+    f.createDimension("i", None)
+    for name, t, long_name, units in trajectory_variables(**config):
+        v = f.createVariable(name, t, ("i",))
+        v.long_name = long_name; v.units = units
+        a = cols[name].astype(np.float64 if t == "d" else np.int32)
+        if len(a):
+            v[:len(a)] = a
+    f.close()
+
+
+def read_trajectory(path):
+    f = netcdf_file(path, "r", mmap=False)
+    out = {k: np.array(v[:]) for k, v in f.variables.items()}
+    f.close()
+    if "id_cnt" in out:
+        out["id"] = id_from_2_ints(out["id_cnt"], out["id_ij"])
+    return out

@@ -220,7 +220,16 @@ typedef struct KidParams {
   /* namelist entries that reach icebergs_run but are not implemented: refused by kid_init when set */
   double tau_calving;                          /* F:728 (0.): running-mean smoothing of the calving field I:5215, I:6020; must be 0 */
   int32_t find_melt_using_spread_mass;         /* F:741 (F): melt from the spread mass before/after I:5490-5495; must be 0 */
-  int32_t pad2_;
+  /* trajectory sampling, record_posn F:5328-5498 (WHEN to sample is the caller's decision, I:5173-5178: kid_record_posn) */
+  int32_t save_short_traj;                     /* F:759 (T): the file holds lon, lat, year, day, id only */
+  int32_t save_fl_traj;                        /* F:762 (T): + masses, thickness, velocity (and the footloose state) */
+  int32_t save_nonfl_traj_by_class;            /* F:764 (F) */
+  double traj_area_thres;                      /* F:687 (0.) km^2: area a non-bonded berg must have to be sampled */
+  double traj_area_thres_sntbc;                /* F:688 (0.) km^2, with save_nonfl_traj_by_class */
+  double traj_area_thres_fl;                   /* F:689 (1e9) km^2, footloose children (fl_k < 0) */
+  double save_all_traj_year;                   /* F:763 (huge): from this year on every berg is sampled */
+  double save_traj_by_class_start_mass_thres_n;/* F:765 (0.) */
+  double save_traj_by_class_start_mass_thres_s;/* F:766 (0.) */
 } KidParams;
 
 /* ----------------------------------------------------------------------------
@@ -274,6 +283,24 @@ typedef struct KidBondColumns {
   double *tangd1, *tangd2, *nstress, *sstress, *rel_rotation; /* dem; may be NULL */
   int32_t *broken;                                     /* dem; may be NULL */
 } KidBondColumns;
+
+/* ----------------------------------------------------------------------------
+ * Trajectory samples: one entry per record of iceberg_trajectories.nc (type(xyt) F:257-287, write_trajectory
+ * fmsio:1575-2047).  Any pointer may be NULL (column skipped).
+ * -------------------------------------------------------------------------- */
+typedef struct KidTrajColumns {
+  double *lon, *lat, *day;
+  int32_t *year;
+  int64_t *id;
+  double *mass, *start_mass, *thickness, *mass_of_bits, *uvel, *vvel;                   /* save_fl_traj */
+  double *mass_scaling, *mass_of_fl_bits, *mass_of_fl_bergy_bits, *fl_k;                /* ... with footloose */
+  double *uvel_prev, *vvel_prev, *heat_density, *width, *length;                        /* .not. save_short_traj */
+  double *uo, *vo, *ui, *vi, *ua, *va, *ssh_x, *ssh_y, *sst, *sss, *cn, *hi;
+  double *axn, *ayn, *bxn, *byn, *halo_berg, *static_berg, *od;
+  double *axn_fast, *ayn_fast, *bxn_fast, *byn_fast;                                    /* mts */
+  int32_t *n_bonds;                                                                     /* iceberg_bonds_on */
+  double *ang_vel, *ang_accel, *rot;                                                    /* dem */
+} KidTrajColumns;
 
 /* scalar budget / event counters accumulated by kid_run (reference: I:5685-5776,
  * type(icebergs) F:541-568) */
@@ -357,6 +384,18 @@ int32_t kid_run(kid_t* h, int32_t year, double yearday,
                 const double* cn, const double* hi,
                 int32_t stagger, int32_t stress_stagger, const double* sss,
                 double* mass_berg, double* ustar_berg, double* area_berg);
+
+/*
+ * record_posn F:5328-5498: sample the bergs of the compute domain that pass the trajectory criteria (area thresholds,
+ * bonded, save_all_traj_year, ...) at the time of the last kid_run into a device-side trajectory store.  The reference
+ * decides when to sample from the model date (sample_traj I:5173-5178, every traj_sample_hrs); that decision stays with
+ * the caller, who holds the date.  kid_get_trajectory hands the samples back (n: capacity in, count out; clear /= 0
+ * empties the store afterwards), in no particular order -- push_posn / move_trajectory (F:5502, F:5611) keep per-berg
+ * lists that write_trajectory flattens; the records, not their order, are the data.
+ */
+int32_t kid_record_posn(kid_t* h);
+int32_t kid_trajectory_count(kid_t* h, int64_t* n);
+int32_t kid_get_trajectory(kid_t* h, int64_t* n, KidTrajColumns* c, int32_t clear);
 
 /*
  * Optional: announce the inputs of the NEXT kid_run() early.  Their host-to-device copies are queued on a copy stream

@@ -72,6 +72,15 @@ typedef struct OBerg {
   double ang_vel, ang_accel, rot;
 } OBerg;
 
+typedef struct OTraj {
+  double lon, lat, day; int32_t year; int64_t id;
+  double mass, start_mass, thickness, mass_of_bits, uvel, vvel, mass_scaling, mass_of_fl_bits, mass_of_fl_bergy_bits, fl_k;
+  double uvel_prev, vvel_prev, heat_density, width, length, uo, vo, ui, vi, ua, va, ssh_x, ssh_y, sst, sss, cn, hi;
+  double axn, ayn, bxn, byn, halo_berg, static_berg, od, axn_fast, ayn_fast, bxn_fast, byn_fast;
+  int32_t n_bonds;
+  double ang_vel, ang_accel, rot;
+} OTraj;
+
 struct Oracle {
   KidParams p;
   KidDomain d;
@@ -108,6 +117,9 @@ struct Oracle {
   double tsec[4];
   char err[512];
   int fatal;
+  /* trajectory samples: type(xyt) records of record_posn F:5328, flattened (write_trajectory fmsio:1575) */
+  struct OTraj* traj;
+  int64_t traj_n, traj_cap;
   int warn_count;
 };
 
@@ -2333,6 +2345,7 @@ Oracle* oracle_create(const KidParams* p, const KidDomain* dom, int32_t year, do
 
 void oracle_destroy(Oracle* o) {
   if (!o) return;
+  free(o->traj);
   size_t n2 = (size_t)o->nid * o->njd;
   for (size_t k = 0; k < n2; k++) {
     OBerg* b = o->list[k];
@@ -2742,6 +2755,78 @@ int32_t oracle_find_cell_wide(const Oracle* o, double x, double y, int32_t* oi, 
 
 /* ---- namelist defaults (ice_bergs_framework_init F:686-822) and FMS constants, carried by the oracle so the
  * CPU baseline / reference arm of bench.py never loads the product library ---- */
+/* record_posn F:5328-5498 (debug_write = F: compute domain).  Every field of the record is filled; which of them
+ * reach the file is write_trajectory's business (save_short_traj / save_fl_traj, fmsio:1575). */
+int32_t oracle_record_posn(Oracle* o) {
+  const KidDomain* d = &o->d;
+  const KidParams* p = &o->p;
+  const double area_thres = p->traj_area_thres * 1.e6, area_thres2 = p->traj_area_thres_sntbc * 1.e6,
+               area_thres3 = p->traj_area_thres_fl * 1.e6;                                   /* km^2 -> m^2, F:5362-5364 */
+  for (int grdj = d->jsc; grdj <= d->jec; grdj++) for (int grdi = d->isc; grdi <= d->iec; grdi++)
+    for (const OBerg* this_ = G(o, list, grdi, grdj); this_; this_ = this_->next) {
+      double berg_area = this_->mass / (p->rho_bergs * this_->thickness);
+      int by_class = 0, save_fl_berg;
+      if (p->save_nonfl_traj_by_class) {
+        if (this_->fl_k >= 0. && berg_area > area_thres2) {
+          if (this_->lat < 0.) { if (this_->start_mass >= p->save_traj_by_class_start_mass_thres_s) by_class = 1; }
+          else { if (this_->start_mass >= p->save_traj_by_class_start_mass_thres_n) by_class = 1; }
+        }
+      }
+      save_fl_berg = (this_->fl_k < 0 && berg_area > area_thres3);
+      if (!((double)o->current_year > p->save_all_traj_year || by_class || berg_area >= area_thres || this_->first_bond || save_fl_berg))
+        continue;
+      if (o->traj_n == o->traj_cap) {
+        o->traj_cap = o->traj_cap ? 2 * o->traj_cap : 1024;
+        o->traj = (OTraj*)realloc(o->traj, sizeof(OTraj) * (size_t)o->traj_cap);
+      }
+      OTraj* q = &o->traj[o->traj_n++];
+      memset(q, 0, sizeof(*q));
+      q->lon = this_->lon; q->lat = this_->lat; q->year = o->current_year; q->day = o->current_yearday; q->id = this_->id;
+      q->mass = this_->mass; q->start_mass = this_->start_mass; q->thickness = this_->thickness;
+      q->mass_of_bits = this_->mass_of_bits; q->uvel = this_->uvel; q->vvel = this_->vvel;
+      q->mass_scaling = this_->mass_scaling; q->mass_of_fl_bits = this_->mass_of_fl_bits;
+      q->mass_of_fl_bergy_bits = this_->mass_of_fl_bergy_bits; q->fl_k = this_->fl_k;
+      q->uvel_prev = this_->uvel_prev; q->vvel_prev = this_->vvel_prev; q->heat_density = this_->heat_density;
+      q->width = this_->width; q->length = this_->length;
+      q->uo = this_->uo; q->vo = this_->vo; q->ui = this_->ui; q->vi = this_->vi; q->ua = this_->ua; q->va = this_->va;
+      q->ssh_x = this_->ssh_x; q->ssh_y = this_->ssh_y; q->sst = this_->sst; q->sss = this_->sss; q->cn = this_->cn; q->hi = this_->hi;
+      q->axn = this_->axn; q->ayn = this_->ayn; q->bxn = this_->bxn; q->byn = this_->byn;
+      q->halo_berg = this_->halo_berg; q->static_berg = this_->static_berg; q->od = this_->od;
+      if (p->mts) { q->axn_fast = this_->axn_fast; q->ayn_fast = this_->ayn_fast; q->bxn_fast = this_->bxn_fast; q->byn_fast = this_->byn_fast; }
+      if (p->iceberg_bonds_on) {
+        if (p->mts) q->n_bonds = this_->n_bonds;
+        else { int nb = 0; for (const OBond* bd = this_->first_bond; bd; bd = bd->next_bond) nb++; q->n_bonds = nb; }
+      }
+      if (p->dem) { q->ang_vel = this_->ang_vel; q->ang_accel = this_->ang_accel; q->rot = this_->rot; }
+    }
+  return KID_OK;
+}
+
+int64_t oracle_trajectory_count(const Oracle* o) { return o->traj_n; }
+
+int32_t oracle_get_trajectory(Oracle* o, int64_t* n, KidTrajColumns* c, int32_t clear) {
+  if (*n < o->traj_n) { *n = o->traj_n; return KID_ERR_CAPACITY; }
+  *n = o->traj_n;
+  for (int64_t k = 0; k < o->traj_n; k++) {
+    const OTraj* q = &o->traj[k];
+    CPUT(c, lon, k, q->lon); CPUT(c, lat, k, q->lat); CPUT(c, day, k, q->day); CPUT(c, year, k, q->year); CPUT(c, id, k, q->id);
+    CPUT(c, mass, k, q->mass); CPUT(c, start_mass, k, q->start_mass); CPUT(c, thickness, k, q->thickness);
+    CPUT(c, mass_of_bits, k, q->mass_of_bits); CPUT(c, uvel, k, q->uvel); CPUT(c, vvel, k, q->vvel);
+    CPUT(c, mass_scaling, k, q->mass_scaling); CPUT(c, mass_of_fl_bits, k, q->mass_of_fl_bits);
+    CPUT(c, mass_of_fl_bergy_bits, k, q->mass_of_fl_bergy_bits); CPUT(c, fl_k, k, q->fl_k);
+    CPUT(c, uvel_prev, k, q->uvel_prev); CPUT(c, vvel_prev, k, q->vvel_prev); CPUT(c, heat_density, k, q->heat_density);
+    CPUT(c, width, k, q->width); CPUT(c, length, k, q->length);
+    CPUT(c, uo, k, q->uo); CPUT(c, vo, k, q->vo); CPUT(c, ui, k, q->ui); CPUT(c, vi, k, q->vi); CPUT(c, ua, k, q->ua); CPUT(c, va, k, q->va);
+    CPUT(c, ssh_x, k, q->ssh_x); CPUT(c, ssh_y, k, q->ssh_y); CPUT(c, sst, k, q->sst); CPUT(c, sss, k, q->sss); CPUT(c, cn, k, q->cn); CPUT(c, hi, k, q->hi);
+    CPUT(c, axn, k, q->axn); CPUT(c, ayn, k, q->ayn); CPUT(c, bxn, k, q->bxn); CPUT(c, byn, k, q->byn);
+    CPUT(c, halo_berg, k, q->halo_berg); CPUT(c, static_berg, k, q->static_berg); CPUT(c, od, k, q->od);
+    CPUT(c, axn_fast, k, q->axn_fast); CPUT(c, ayn_fast, k, q->ayn_fast); CPUT(c, bxn_fast, k, q->bxn_fast); CPUT(c, byn_fast, k, q->byn_fast);
+    CPUT(c, n_bonds, k, q->n_bonds); CPUT(c, ang_vel, k, q->ang_vel); CPUT(c, ang_accel, k, q->ang_accel); CPUT(c, rot, k, q->rot);
+  }
+  if (clear) o->traj_n = 0;
+  return KID_OK;
+}
+
 void oracle_default_params(KidParams* p) {
   static const double im[10] = {8.8e7, 4.1e8, 3.3e9, 1.8e10, 3.8e10, 7.5e10, 1.2e11, 2.2e11, 3.9e11, 7.4e11};      /* F:787 */
   static const double ds[10] = {0.24, 0.12, 0.15, 0.18, 0.12, 0.07, 0.03, 0.03, 0.03, 0.02};                        /* F:788 */
@@ -2767,6 +2852,7 @@ void oracle_default_params(KidParams* p) {
   p->displace_fl_bergs = 1; p->fl_bits_erosion_to_bergy_bits = 1;
   p->fl_youngs = 1.e7; p->fl_strength = 250.; p->new_berg_from_fl_bits_mass_thres = 1.e12;
   p->LoW_ratio = 1.5;
+  p->save_short_traj = 1; p->save_fl_traj = 1; p->traj_area_thres_fl = 1.e9; p->save_all_traj_year = 1.7976931348623157e308;   /* F:687-689, F:759-766 */
   p->use_three_equation_model = 1; p->const_gamma = 1; p->gamma_t_3eq = 0.022; p->ustar_icebergs_bg = 0.001;
   p->utide_icebergs = 0.; p->cdrag_icebergs = 1.5e-3;
   p->add_weight_to_ocean = 1; p->use_old_spreading = 1; p->rotate_icebergs_for_mass_spreading = 1;

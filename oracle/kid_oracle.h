@@ -45,6 +45,10 @@ int32_t oracle_set_bergs(Oracle* o, int64_t n, const KidBergColumns* c);
 int64_t oracle_count_bergs(const Oracle* o, int32_t include_halo);
 /* list order: do j=jsd,jed; do i=isd,ied; walk list (F:1769) */
 int32_t oracle_get_bergs(const Oracle* o, int64_t* n, KidBergColumns* c, int32_t include_halo);
+/* record_posn F:5328-5498 and the flattened trajectory store (write_trajectory fmsio:1575) */
+int32_t oracle_record_posn(Oracle* o);
+int64_t oracle_trajectory_count(const Oracle* o);
+int32_t oracle_get_trajectory(Oracle* o, int64_t* n, KidTrajColumns* c, int32_t clear);
 int32_t oracle_set_bonds(Oracle* o, int64_t nb, const KidBondColumns* c);
 int32_t oracle_get_bonds(const Oracle* o, int64_t* nb, KidBondColumns* c);
 int32_t oracle_set_calving_state(Oracle* o, const double* stored_ice, const double* stored_heat,

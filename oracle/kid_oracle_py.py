@@ -113,6 +113,10 @@ def lib():
         L.oracle_count_bergs.argtypes = [_vp, C.c_int32]
         L.oracle_count_bergs.restype = C.c_int64
         L.oracle_get_bergs.argtypes = [_vp, C.POINTER(C.c_int64), _vp, C.c_int32]
+        L.oracle_record_posn.argtypes = [_vp]
+        L.oracle_trajectory_count.argtypes = [_vp]
+        L.oracle_trajectory_count.restype = C.c_int64
+        L.oracle_get_trajectory.argtypes = [_vp, C.POINTER(C.c_int64), _vp, C.c_int32]
         L.oracle_set_bonds.argtypes = [_vp, C.c_int64, _vp]
         L.oracle_get_bonds.argtypes = [_vp, C.POINTER(C.c_int64), _vp]
         L.oracle_set_calving_state.argtypes = [_vp, _vp, _vp, _vp]
@@ -222,6 +226,18 @@ class Oracle:
         c, keep = make_columns(cap, want=set(names))
         m = C.c_int64(cap)
         self._ok(lib().oracle_get_bergs(self._h, C.byref(m), C.byref(c), int(include_halo)))
+        return {k: v[: m.value].copy() for k, v in keep.items()}
+
+    def record_posn(self):
+        """record_posn F:5328 at the time of the last run"""
+        self._ok(lib().oracle_record_posn(self._h))
+
+    def get_trajectory(self, clear=True):
+        n = int(lib().oracle_trajectory_count(self._h))
+        cap = max(n, 1)
+        c, keep = make_columns(cap, want={f[0] for f in D.KidTrajColumns._fields_}, cls=D.KidTrajColumns)
+        m = C.c_int64(cap)
+        self._ok(lib().oracle_get_trajectory(self._h, C.byref(m), C.byref(c), int(clear)))
         return {k: v[: m.value].copy() for k, v in keep.items()}
 
     def set_bonds(self, **cols):
