@@ -316,6 +316,7 @@ static void fill_dev_params(kid_t* h) {
   q.only_interactive_forces = p.only_interactive_forces;
   q.override_iceberg_velocities = p.override_iceberg_velocities;
   q.old_interp_flds_order = p.old_interp_flds_order; q.interactive_icebergs_on = p.interactive_icebergs_on;
+  q.runge_not_verlet = p.runge_not_verlet; q.pad_rk_ = 0;
   q.iceberg_bonds_on = p.iceberg_bonds_on; q.internal_bergs_for_drag = p.internal_bergs_for_drag;
   q.hexagonal_icebergs = p.hexagonal_icebergs;
   q.critical_interaction_damping_on = p.critical_interaction_damping_on;
@@ -578,8 +579,10 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   if (dom->device < 0 || dom->device >= ndev) { g_init_error = "kid_init: bad device ordinal"; return KID_ERR_ARG; }
   // what this build of the library does not implement is refused up front
   const char* unsupported = nullptr;
-  if (pin->runge_not_verlet && (pin->interactive_icebergs_on || pin->footloose || pin->mts))
-    unsupported = "Runge_not_Verlet=.true. (RK4) is implemented for free-drifting bergs only: set runge_not_verlet=0 with interactions / footloose";
+  if (pin->runge_not_verlet && pin->mts)
+    unsupported = "mts=.true. takes its long steps with the Verlet form of accel_mts: set runge_not_verlet=0";
+  else if (pin->runge_not_verlet && pin->footloose)
+    unsupported = "Runge_not_Verlet=.true. with footloose is not parity-clean yet (the stepping exists: k_step_rk<.., STEP_ONLY>): set runge_not_verlet=0";
   else if (pin->tidal_drift > 0.) unsupported = "tidal_drift>0 needs the FMS random number stream";
   else if (pin->add_iceberg_thickness_to_ssh) unsupported = "add_iceberg_thickness_to_SSH is not implemented";
   else if (pin->tau_calving > 0.) unsupported = "tau_calving>0 (running mean of the calving field, I:5215) is not implemented";
@@ -2286,11 +2289,16 @@ static int step_core(kid_t* h) {
       if (rc) return rc;
     } else if (ia) {
       CellTable ct{h->cell_start, h->cell_count};
-      LAUNCH(h, k_ia_velocity, h->n_slots, KID_BLOCK, h->g, h->b, h->dp, ct, h->dcnt, h->n_slots);
+      if (h->p.runge_not_verlet) { LAUNCH(h, k_step_rk_ia, h->n_slots, KID_BLOCK, h->g, h->b, h->dp, ct, h->dcnt, h->n_slots); }
+      else { LAUNCH(h, k_ia_velocity, h->n_slots, KID_BLOCK, h->g, h->b, h->dp, ct, h->dcnt, h->n_slots); }
       if (fl) { LAUNCH(h, (k_step<true, false, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots, 0LL); }
       else if (dg) { LAUNCH(h, (k_step<false, true, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots, 0LL); }
       else { LAUNCH(h, (k_step<false, false, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots, 0LL); }
       if (h->b.max_bonds > 0) LAUNCH(h, k_bond_address_update, h->n_slots, 128, h->b, h->n_slots);
+    } else if (h->p.runge_not_verlet && fl) {
+      // footloose: thermodynamics follows footloose_calving (I:5455, I:5497): the stepping alone, then send_bergs
+      LAUNCH(h, (k_step_rk<false, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots);
+      LAUNCH(h, (k_step<true, false, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots, 0LL);
     } else if (h->p.runge_not_verlet) {
       if (dg) { LAUNCH(h, (k_step_rk<true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
       else { LAUNCH(h, (k_step_rk<false>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }

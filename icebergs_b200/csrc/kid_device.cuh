@@ -59,6 +59,7 @@ struct DevParams {
   int32_t grid_is_latlon, grid_is_regular, old_bug_bilin, use_roundoff_fix, use_f_plane;
   int32_t use_new_predictive_corrective, only_interactive_forces, override_iceberg_velocities;
   int32_t old_interp_flds_order, interactive_icebergs_on, iceberg_bonds_on, internal_bergs_for_drag;
+  int32_t runge_not_verlet, pad_rk_;
   int32_t hexagonal_icebergs, critical_interaction_damping_on, tang_crit_int_damp_on, scale_damping_by_pmag;
   int32_t use_operator_splitting, set_melt_rates_to_zero, allow_bergs_to_roll, use_updated_rolling_scheme;
   int32_t iceberg_melt_without_decay, melt_diagnostics, footloose, mts, dem;

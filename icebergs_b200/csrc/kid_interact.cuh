@@ -296,6 +296,37 @@ __global__ void k_ghost_unpack(const __grid_constant__ DevGrid g, const __grid_c
   b.flags[s] = (uint8_t)((f | BF_ALIVE | BF_HALO) & ~(BF_LEAVER | BF_ARRIVAL));
 }
 
+// first sweep of evolve_icebergs with interactions on and Runge_not_Verlet (the namelist default, F:733):
+// Runge_Kutta_stepping I:7331-7679 with interactive_force inside every accel call.  Position, velocity and cell are
+// stored; *_old, send_bergs and thermodynamics follow in k_step<.., SPLIT=true>.
+__global__ void __launch_bounds__(KID_BLOCK)
+k_step_rk_ia(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b, const __grid_constant__ DevParams p,
+             const CellTable ct, DevCounters* __restrict__ cnt, long long n_slots) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  uint8_t flags = (s < n_slots) ? b.flags[s] : (uint8_t)0;
+  const bool active = (flags & BF_ALIVE) && !(flags & (BF_HALO | BF_STATIC));
+  bool any_bounce = false, speeding = false;
+  if (active) {
+    int i = b.ine[s], j = b.jne[s];
+    const int i0 = i, j0 = j;
+    double xi = b.f64[C_XI][s], yj = b.f64[C_YJ][s];
+    double lon = b.f64[C_LON][s], lat = b.f64[C_LAT][s], uvel = b.f64[C_UVEL][s], vvel = b.f64[C_VVEL][s];
+    const double M = b.f64[C_MASS][s], T = b.f64[C_THICKNESS][s], W = b.f64[C_WIDTH][s], L = b.f64[C_LENGTH][s];
+    double dragfrac = 1.0;
+    if (p.iceberg_bonds_on && p.internal_bergs_for_drag) {       // I:2104-2120
+      double N_bonds = 0., N_max = p.hexagonal_icebergs ? 6.0 : 4.0;
+      for (int k = 0; k < b.max_bonds; k++) if (b.bond_other_id[(long long)k * b.capacity + s] != 0) N_bonds += 1.0;
+      dragfrac = ((N_max - N_bonds) / N_max);
+    }
+    rk_stepping<true>(g, b, p, cnt, s, i, j, xi, yj, lon, lat, uvel, vvel, M, T, W, L, dragfrac,
+                      [&](double u0, double v0, double u1, double v1, IAcc& a) { interactive_force(g, b, p, ct, s, i0, j0, a, u0, v0, u1, v1); },
+                      any_bounce, speeding);
+    b.f64[C_XI][s] = xi; b.f64[C_YJ][s] = yj; b.ine[s] = i; b.jne[s] = j;
+  }
+  warp_count_add(&cnt->n_bounced, any_bounce);
+  warp_count_add(&cnt->nspeeding, speeding);
+}
+
 // update_latlon F:5128-5169: positions re-derived from (cell, xi, yj) so that copies across the
 // periodic seam carry the coordinates of the halo cell they sit in
 __global__ void k_update_latlon(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,

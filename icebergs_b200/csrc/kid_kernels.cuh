@@ -284,6 +284,15 @@ __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, c
     } else {
       lon = b.f64[C_LON][s];
     }
+    if (SPLIT && !LEAN && p.runge_not_verlet) {
+      // Runge_Kutta_stepping already placed the berg (k_step_rk<.., STEP_ONLY> / k_step_rk_ia): the second loop of
+      // evolve_icebergs only refreshes *_old (I:7178-7197)
+      lon = b.f64[C_LON][s];
+      if (b.f64[C_UVEL_OLD]) {
+        b.f64[C_UVEL_OLD][s] = uvel; b.f64[C_VVEL_OLD][s] = vvel;
+        b.f64[C_LON_OLD][s] = lon; b.f64[C_LAT_OLD][s] = lat;
+      }
+    } else {
     // ---- update_verlet_position I:7684-7764 (uses the NEW velocity and accelerations)
     double uvel2 = uvel + (dt_2 * axn) + (dt_2 * bxn);
     double vvel2 = vvel + (dt_2 * ayn) + (dt_2 * byn);
@@ -306,6 +315,7 @@ __device__ __forceinline__ void step_berg(const DevGrid& g, const DevBergs& b, c
     if (SPLIT && b.f64[C_UVEL_OLD]) {      // I:7189-7194 (columns of interactive runs)
       b.f64[C_UVEL_OLD][s] = uvel; b.f64[C_VVEL_OLD][s] = vvel;
       b.f64[C_LON_OLD][s] = lon; b.f64[C_LAT_OLD][s] = lat;
+    }
     }
   } else if (i > g.iec || i < g.isc || j > g.jec || j < g.jsc) {
     lon = b.f64[C_LON][s];
@@ -595,7 +605,95 @@ k_step_slow(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs 
 // straightforward (plain IEEE arithmetic in accel_rk) rather than tuned.
 struct RkStage { double lon, lat, uvel, vvel, u, v, ax, ay, axn, ayn, xdot, ydot, xddot, yddot, xddotn, yddotn; };
 
-template <bool DIAG>
+// The four stages and the combination for the (non-static) berg in slot s; stores the accelerations, velocity and
+// position and hands back the final cell.  IAFN(u0, v0, u1, v1, IAcc&) evaluates interactive_force for this berg
+// (kid_interact.cuh) when INTERACTIVE: the berg's own position enters through lon_old / lat_old and its stored cell,
+// so it is the same at every stage (I:611-655); the other bergs are read through their *_old columns only, which
+// nobody writes in this sweep (evolve_icebergs refreshes them in its second loop, I:7178-7197).
+template <bool INTERACTIVE, class IAFN>
+__device__ __forceinline__ void rk_stepping(const DevGrid& g, const DevBergs& b, const DevParams& p, DevCounters* __restrict__ cnt,
+                                            long long s, int& i, int& j, double& xi, double& yj, double& lon, double& lat,
+                                            double& uvel, double& vvel, double M, double T, double W, double L, double dragfrac,
+                                            IAFN&& iafn, bool& any_bounce, bool& speeding) {
+  const double dt = p.dt, dt_2 = 0.5 * dt, dt_6 = dt / 6.;
+  const int i1 = i, j1 = j;
+  const double xi0 = xi, yj0 = yj;
+  const bool tang = (lat > 89.) && p.grid_is_latlon;
+  const double axn0 = b.f64[C_AXN][s], ayn0 = b.f64[C_AYN][s];
+  double bxn = 0., byn = 0., x1 = 0., y1 = 0., dydl;
+  RkStage st[4];
+  double lonn = lon, latn = lat, uveln = uvel, vveln = vvel, axn = 0., ayn = 0.;
+  for (int k = 0; k < 4; k++) {
+    RkStage& q = st[k];
+    const double h = (k == 3) ? dt : dt_2;          // stage step to reach this stage: dt_2, dt_2, dt
+    if (k == 0) {
+      q.lon = lon; q.lat = lat; q.uvel = uvel; q.vvel = vvel;
+      if (tang) { rotpos_to_tang(p, q.lon, q.lat, x1, y1); rotvec_to_tang(p, q.lon, q.uvel, q.vvel, q.xdot, q.ydot); }
+    } else {
+      const RkStage& r = st[k - 1];
+      if (tang) {
+        double x = x1 + h * r.xdot, y = y1 + h * r.ydot;
+        q.xdot = st[0].xdot + h * r.xddot; q.ydot = st[0].ydot + h * r.yddot;
+        rotpos_from_tang(p, x, y, q.lon, q.lat);
+        rotvec_from_tang(p, q.lon, q.xdot, q.ydot, q.uvel, q.vvel);
+      } else {
+        q.lon = lon + h * r.u; q.lat = lat + h * r.v;
+        q.uvel = uvel + h * r.ax; q.vvel = vvel + h * r.ay;
+      }
+      i = i1; j = j1; xi = xi0; yj = yj0;
+      any_bounce |= adjust_index_and_ground(g, p, q.lon, q.lat, i, j, xi, yj, &cnt->error_flags, &cnt->warn_adjust);
+    }
+    double dxdl;
+    convert_from_meters_to_grid(p, q.lat, dxdl, dydl);
+    q.u = q.uvel * dxdl; q.v = q.vvel * dydl;
+    Env e;
+    if (!interp_flds(g, p, i, j, xi, yj, e)) atomicOr(&cnt->error_flags, 64u);
+    double loc_dx = 0.;
+    if ((p.speed_limit > 0.) || (p.speed_limit == -1.)) {
+      int c = gidx(g, i, j);
+      loc_dx = fmin(0.5 * (g.dx[c] + g.dx[c - g.nid]), 0.5 * (g.dy[c] + g.dy[c - 1]));
+    }
+    q.axn = axn0; q.ayn = ayn0;
+    IAcc ia = {0., 0., 0., 0., 0., 0., 0., 0.};
+    const double u0 = uvel, v0 = vvel;
+    if (INTERACTIVE) iafn(u0, v0, u0, v0, ia);                                                    // I:2153
+    accel_rk<INTERACTIVE>(p, M, T, W, L, q.lat, q.uvel, q.vvel, uvel, vvel, (k < 2) ? dt_2 : dt, e, loc_dx, dragfrac, ia,
+                          [&](double us, double vs, IAcc& a) { iafn(u0, v0, us, vs, a); },            // I:2217
+                          q.ax, q.ay, q.axn, q.ayn, bxn, byn, speeding);
+    if (tang) { rotvec_to_tang(p, q.lon, q.ax, q.ay, q.xddot, q.yddot); rotvec_to_tang(p, q.lon, q.axn, q.ayn, q.xddotn, q.yddotn); }
+  }
+  if (tang) {
+    double xn = x1 + dt_6 * ((st[0].xdot + st[3].xdot) + 2. * (st[1].xdot + st[2].xdot));
+    double yn = y1 + dt_6 * ((st[0].ydot + st[3].ydot) + 2. * (st[1].ydot + st[2].ydot));
+    double xdotn = st[0].xdot + dt_6 * ((st[0].xddot + st[3].xddot) + 2. * (st[1].xddot + st[2].xddot));
+    double ydotn = st[0].ydot + dt_6 * ((st[0].yddot + st[3].yddot) + 2. * (st[1].yddot + st[2].yddot));
+    double xddotn = ((st[0].xddotn + st[3].xddotn) + 2. * (st[1].xddotn + st[2].xddotn)) / 6.;
+    double yddotn = ((st[0].yddotn + st[3].yddotn) + 2. * (st[1].yddotn + st[2].yddotn)) / 6.;
+    rotpos_from_tang(p, xn, yn, lonn, latn);
+    rotvec_from_tang(p, lonn, xdotn, ydotn, uveln, vveln);
+    rotvec_from_tang(p, lonn, xddotn, yddotn, axn, ayn);
+  } else {
+    lonn = lon + dt_6 * ((st[0].u + st[3].u) + 2. * (st[1].u + st[2].u));
+    latn = lat + dt_6 * ((st[0].v + st[3].v) + 2. * (st[1].v + st[2].v));
+    uveln = uvel + dt_6 * ((st[0].ax + st[3].ax) + 2. * (st[1].ax + st[2].ax));
+    vveln = vvel + dt_6 * ((st[0].ay + st[3].ay) + 2. * (st[1].ay + st[2].ay));
+    axn = ((st[0].axn + st[3].axn) + 2. * (st[1].axn + st[2].axn)) / 6.;
+    ayn = ((st[0].ayn + st[3].ayn) + 2. * (st[1].ayn + st[2].ayn)) / 6.;
+    bxn = (((st[0].ax + st[3].ax) + 2. * (st[1].ax + st[2].ax)) / 6) - (axn / 2);
+    byn = (((st[0].ay + st[3].ay) + 2. * (st[1].ay + st[2].ay)) / 6) - (ayn / 2);
+  }
+  i = i1; j = j1; xi = xi0; yj = yj0;
+  any_bounce |= adjust_index_and_ground(g, p, lonn, latn, i, j, xi, yj, &cnt->error_flags, &cnt->warn_adjust);
+  if (p.override_iceberg_velocities) { uveln = p.u_override; vveln = p.v_override; }
+  lon = lonn; lat = latn; uvel = uveln; vvel = vveln;
+  b.f64[C_AXN][s] = axn; b.f64[C_AYN][s] = ayn; b.f64[C_BXN][s] = bxn; b.f64[C_BYN][s] = byn;
+  b.f64[C_UVEL][s] = uvel; b.f64[C_VVEL][s] = vvel;
+  b.f64[C_LON][s] = lon; b.f64[C_LAT][s] = lat;
+}
+
+// STEP_ONLY: stop after the stepping (position, velocity and cell stored): send_bergs and thermodynamics follow in
+// the SPLIT instance of k_step (footloose runs, whose thermodynamics comes after footloose_calving)
+template <bool DIAG, bool STEP_ONLY = false>
 __global__ void __launch_bounds__(KID_BLOCK)
 k_step_rk(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b, const __grid_constant__ DevParams p,
           DevCounters* __restrict__ cnt, long long n_slots) {
@@ -610,103 +708,39 @@ k_step_rk(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
   sc.fx.melt_buoy_fl = sc.fx.melt_eros_fl = sc.fx.melt_conv_fl = 0.;
   bool melted = false, any_bounce = false, speeding = false, left = false;
   if (owned) {
-    const double dt = p.dt, dt_2 = 0.5 * dt, dt_6 = dt / 6.;
     int i = b.ine[s], j = b.jne[s];
-    const int i1 = i, j1 = j;
-    const double xi0 = b.f64[C_XI][s], yj0 = b.f64[C_YJ][s];
-    double xi = xi0, yj = yj0;
+    double xi = b.f64[C_XI][s], yj = b.f64[C_YJ][s];
     double lon = b.f64[C_LON][s], lat = b.f64[C_LAT][s], uvel = b.f64[C_UVEL][s], vvel = b.f64[C_VVEL][s];
     const double M = b.f64[C_MASS][s], T = b.f64[C_THICKNESS][s], W = b.f64[C_WIDTH][s], L = b.f64[C_LENGTH][s];
-    if (!(flags & BF_STATIC)) {
-      const bool tang = (lat > 89.) && p.grid_is_latlon;
-      const double axn0 = b.f64[C_AXN][s], ayn0 = b.f64[C_AYN][s];
-      double bxn = 0., byn = 0., x1 = 0., y1 = 0., dydl;
-      RkStage st[4];
-      double lonn = lon, latn = lat, uveln = uvel, vveln = vvel, axn = 0., ayn = 0.;
-      for (int k = 0; k < 4; k++) {
-        RkStage& q = st[k];
-        const double h = (k == 3) ? dt : dt_2;          // stage step to reach this stage: dt_2, dt_2, dt
-        if (k == 0) {
-          q.lon = lon; q.lat = lat; q.uvel = uvel; q.vvel = vvel;
-          if (tang) { rotpos_to_tang(p, q.lon, q.lat, x1, y1); rotvec_to_tang(p, q.lon, q.uvel, q.vvel, q.xdot, q.ydot); }
-        } else {
-          const RkStage& r = st[k - 1];
-          if (tang) {
-            double x = x1 + h * r.xdot, y = y1 + h * r.ydot;
-            q.xdot = st[0].xdot + h * r.xddot; q.ydot = st[0].ydot + h * r.yddot;
-            rotpos_from_tang(p, x, y, q.lon, q.lat);
-            rotvec_from_tang(p, q.lon, q.xdot, q.ydot, q.uvel, q.vvel);
-          } else {
-            q.lon = lon + h * r.u; q.lat = lat + h * r.v;
-            q.uvel = uvel + h * r.ax; q.vvel = vvel + h * r.ay;
-          }
-          i = i1; j = j1; xi = xi0; yj = yj0;
-          any_bounce |= adjust_index_and_ground(g, p, q.lon, q.lat, i, j, xi, yj, &cnt->error_flags, &cnt->warn_adjust);
-        }
-        double dxdl;
-        convert_from_meters_to_grid(p, q.lat, dxdl, dydl);
-        q.u = q.uvel * dxdl; q.v = q.vvel * dydl;
-        Env e;
-        if (!interp_flds(g, p, i, j, xi, yj, e)) atomicOr(&cnt->error_flags, 64u);
-        double loc_dx = 0.;
-        if ((p.speed_limit > 0.) || (p.speed_limit == -1.)) {
-          int c = gidx(g, i, j);
-          loc_dx = fmin(0.5 * (g.dx[c] + g.dx[c - g.nid]), 0.5 * (g.dy[c] + g.dy[c - 1]));
-        }
-        q.axn = axn0; q.ayn = ayn0;
-        accel_rk(p, M, T, W, L, q.lat, q.uvel, q.vvel, uvel, vvel, (k < 2) ? dt_2 : dt, e, loc_dx, q.ax, q.ay, q.axn, q.ayn, bxn, byn, speeding);
-        if (tang) { rotvec_to_tang(p, q.lon, q.ax, q.ay, q.xddot, q.yddot); rotvec_to_tang(p, q.lon, q.axn, q.ayn, q.xddotn, q.yddotn); }
-      }
-      if (tang) {
-        double xn = x1 + dt_6 * ((st[0].xdot + st[3].xdot) + 2. * (st[1].xdot + st[2].xdot));
-        double yn = y1 + dt_6 * ((st[0].ydot + st[3].ydot) + 2. * (st[1].ydot + st[2].ydot));
-        double xdotn = st[0].xdot + dt_6 * ((st[0].xddot + st[3].xddot) + 2. * (st[1].xddot + st[2].xddot));
-        double ydotn = st[0].ydot + dt_6 * ((st[0].yddot + st[3].yddot) + 2. * (st[1].yddot + st[2].yddot));
-        double xddotn = ((st[0].xddotn + st[3].xddotn) + 2. * (st[1].xddotn + st[2].xddotn)) / 6.;
-        double yddotn = ((st[0].yddotn + st[3].yddotn) + 2. * (st[1].yddotn + st[2].yddotn)) / 6.;
-        rotpos_from_tang(p, xn, yn, lonn, latn);
-        rotvec_from_tang(p, lonn, xdotn, ydotn, uveln, vveln);
-        rotvec_from_tang(p, lonn, xddotn, yddotn, axn, ayn);
-      } else {
-        lonn = lon + dt_6 * ((st[0].u + st[3].u) + 2. * (st[1].u + st[2].u));
-        latn = lat + dt_6 * ((st[0].v + st[3].v) + 2. * (st[1].v + st[2].v));
-        uveln = uvel + dt_6 * ((st[0].ax + st[3].ax) + 2. * (st[1].ax + st[2].ax));
-        vveln = vvel + dt_6 * ((st[0].ay + st[3].ay) + 2. * (st[1].ay + st[2].ay));
-        axn = ((st[0].axn + st[3].axn) + 2. * (st[1].axn + st[2].axn)) / 6.;
-        ayn = ((st[0].ayn + st[3].ayn) + 2. * (st[1].ayn + st[2].ayn)) / 6.;
-        bxn = (((st[0].ax + st[3].ax) + 2. * (st[1].ax + st[2].ax)) / 6) - (axn / 2);
-        byn = (((st[0].ay + st[3].ay) + 2. * (st[1].ay + st[2].ay)) / 6) - (ayn / 2);
-      }
-      i = i1; j = j1; xi = xi0; yj = yj0;
-      any_bounce |= adjust_index_and_ground(g, p, lonn, latn, i, j, xi, yj, &cnt->error_flags, &cnt->warn_adjust);
-      if (p.override_iceberg_velocities) { uveln = p.u_override; vveln = p.v_override; }
-      lon = lonn; lat = latn; uvel = uveln; vvel = vveln;
-      b.f64[C_AXN][s] = axn; b.f64[C_AYN][s] = ayn; b.f64[C_BXN][s] = bxn; b.f64[C_BYN][s] = byn;
-      b.f64[C_UVEL][s] = uvel; b.f64[C_VVEL][s] = vvel;
-      b.f64[C_LON][s] = lon; b.f64[C_LAT][s] = lat;
-    }
-    int route = 0;
-    if (i > g.iec || i < g.isc || j > g.jec || j < g.jsc)
-      route = route_berg(g, p, lon, lat, i, j, xi, yj, &cnt->error_flags, &cnt->n_wrapped);
-    if (!(flags & BF_STATIC) || route != 0) {
-      b.f64[C_XI][s] = xi; b.f64[C_YJ][s] = yj;
-      b.ine[s] = i; b.jne[s] = j;
-    }
-    if (route == 1) {
-      left = true;
-      b.flags[s] = flags | BF_LEAVER;
-      unsigned long long k = atomicAdd(b.leaver_count, 1ull);
-      if ((long long)k < b.leaver_cap) b.leaver_list[k] = (int32_t)s;
-      else atomicOr(&cnt->error_flags, (unsigned)KID_DEVERR_CAPACITY);
-    } else if (route == 2) {
-      b.flags[s] = 0;
+    if (!(flags & BF_STATIC))
+      rk_stepping<false>(g, b, p, cnt, s, i, j, xi, yj, lon, lat, uvel, vvel, M, T, W, L, 1.0,
+                         [](double, double, double, double, IAcc&) {}, any_bounce, speeding);
+    if (STEP_ONLY) {
+      if (!(flags & BF_STATIC)) { b.f64[C_XI][s] = xi; b.f64[C_YJ][s] = yj; b.ine[s] = i; b.jne[s] = j; }
     } else {
-      int outcome = thermo_slot<false>(g, b, p, s, flags, i, j, xi, yj, uvel, vvel, M, T, W, L, b.f64[C_MASS_SCALING][s],
-                                       b.f64[C_MASS_OF_BITS][s], b.f64[C_HEAT_DENSITY][s], sc, cnt);
-      if (outcome == TH_DELETE) { melted = true; b.flags[s] = 0; }
+      int route = 0;
+      if (i > g.iec || i < g.isc || j > g.jec || j < g.jsc)
+        route = route_berg(g, p, lon, lat, i, j, xi, yj, &cnt->error_flags, &cnt->n_wrapped);
+      if (!(flags & BF_STATIC) || route != 0) {
+        b.f64[C_XI][s] = xi; b.f64[C_YJ][s] = yj;
+        b.ine[s] = i; b.jne[s] = j;
+      }
+      if (route == 1) {
+        left = true;
+        b.flags[s] = flags | BF_LEAVER;
+        unsigned long long k = atomicAdd(b.leaver_count, 1ull);
+        if ((long long)k < b.leaver_cap) b.leaver_list[k] = (int32_t)s;
+        else atomicOr(&cnt->error_flags, (unsigned)KID_DEVERR_CAPACITY);
+      } else if (route == 2) {
+        b.flags[s] = 0;
+      } else {
+        int outcome = thermo_slot<false>(g, b, p, s, flags, i, j, xi, yj, uvel, vvel, M, T, W, L, b.f64[C_MASS_SCALING][s],
+                                         b.f64[C_MASS_OF_BITS][s], b.f64[C_HEAT_DENSITY][s], sc, cnt);
+        if (outcome == TH_DELETE) { melted = true; b.flags[s] = 0; }
+      }
     }
   }
-  scatter_fluxes<false, DIAG>(g, sc);
+  if (!STEP_ONLY) scatter_fluxes<false, DIAG>(g, sc);
   warp_count_add(&cnt->nbergs_melted, melted);
   warp_count_add(&cnt->n_bounced, any_bounce);
   warp_count_add(&cnt->nspeeding, speeding);

@@ -405,10 +405,13 @@ __device__ __forceinline__ void accel_core(const DevParams& p, double M, double 
 // C_N = 0 (I:2002-2005) -- explicit Coriolis at the stage velocity, implicit drag -- and the namelist's
 // use_new_predictive_corrective.  Free bergs only (interactions with RK are refused at init).  The
 // stepping default of the reference; kept out of line and in plain IEEE arithmetic.
+// INTERACTIVE: with interactive_force (I:2152-2161, I:2216-2227, I:2252-2257); ia = its first evaluation at the
+// step's starting velocity, iaf(us, vs, IAcc&) the re-evaluation inside the drag iteration.  dragfrac: I:2104-2120.
+template <bool INTERACTIVE, class IAF>
 __device__ __noinline__ void accel_rk(const DevParams& p, double M, double T, double W, double L, double lat,
                                       double uvel, double vvel, double uvel0, double vvel0, double dt, const Env& e,
-                                      double loc_dx, double& ax, double& ay, double& axn, double& ayn, double& bxn,
-                                      double& byn, bool& speeding) {
+                                      double loc_dx, double dragfrac, IAcc ia, IAF&& iaf, double& ax, double& ay, double& axn,
+                                      double& ayn, double& bxn, double& byn, bool& speeding) {
   const double Cr0 = 0.06;
   const bool use_new_pc = p.use_new_predictive_corrective != 0;
   double u_star = uvel0 + (axn * (dt / 2.)), v_star = vvel0 + (ayn * (dt / 2.));
@@ -428,17 +431,20 @@ __device__ __noinline__ void accel_rk(const DevParams& p, double M, double T, do
   double wave_rad = 0.5 * KID_RHO_SEAWATER / M * Cr * KID_GRAVITY * ampl * fmin(ampl, F) * (2. * W * L) / (W + L);
   wmod = sqrt(ua * ua + va * va);
   if (wmod != 0.) { uwave = ua / wmod; vwave = va / wmod; } else { uwave = 0.; vwave = 0.; wave_rad = 0.; }
-  double c_ocn = KID_RHO_SEAWATER / M * p.ocean_drag_scale * (0.5 * KID_CD_WV * W * (D_hi) + KID_CD_WH * W * L);
-  double c_atm = KID_RHO_AIR / M * (0.5 * KID_CD_AV * W * F + KID_CD_AH * W * L);
-  double c_ice = (fabs(hi) == 0.) ? 0. : KID_RHO_ICE / M * (0.5 * KID_CD_IV * W * hi);
+  double c_ocn = KID_RHO_SEAWATER / M * p.ocean_drag_scale * (0.5 * KID_CD_WV * dragfrac * W * (D_hi) + KID_CD_WH * W * L);
+  double c_atm = KID_RHO_AIR / M * (0.5 * KID_CD_AV * dragfrac * W * F + KID_CD_AH * W * L);
+  double c_ice = (fabs(hi) == 0.) ? 0. : KID_RHO_ICE / M * (0.5 * KID_CD_IV * dragfrac * W * hi);
   if (fabs(ui) + fabs(vi) == 0.) c_ice = 0.;
   axn = 0.; ayn = 0.;
   bxn = -KID_GRAVITY * ssh_x + wave_rad * uwave;
   byn = -KID_GRAVITY * ssh_y + wave_rad * vwave;
+  if (INTERACTIVE) { bxn = bxn + ia.IA_x; byn = byn + ia.IA_y; }   // I:2152-2161 (Runge_not_Verlet: into bxn, byn)
   bxn = bxn + f_cori * vvel; byn = byn - f_cori * uvel;            // alpha = 0: explicit Coriolis, I:2173-2174
   double uveln, vveln;
   if (use_new_pc) { uveln = uvel0; vveln = vvel0; } else { uveln = uvel; vveln = vvel; }
+  double us_ia = uvel0, vs_ia = vvel0;                             // I:2182-2186
   for (int itloop = 1; itloop <= 2; itloop++) {
+    if (itloop == 2) { us_ia = uveln; vs_ia = vveln; }
     double drag_ocn, drag_atm, drag_ice, drag_gnd = c_gnd;
     if (use_new_pc) {
       drag_ocn = c_ocn * 0.5 * (sqrt((uveln - uo) * (uveln - uo) + (vveln - vo) * (vveln - vo)) + sqrt((uvel0 - uo) * (uvel0 - uo) + (vvel0 - vo) * (vvel0 - vo)));
@@ -446,6 +452,7 @@ __device__ __noinline__ void accel_rk(const DevParams& p, double M, double T, do
       drag_ice = c_ice * 0.5 * (sqrt((uveln - ui) * (uveln - ui) + (vveln - vi) * (vveln - vi)) + sqrt((uvel0 - ui) * (uvel0 - ui) + (vvel0 - vi) * (vvel0 - vi)));
     } else {
       double us = 0.5 * (uveln + uvel), vs = 0.5 * (vveln + vvel);
+      us_ia = us; vs_ia = vs;                                      // (the original scheme overwrites us, vs: I:2199)
       drag_ocn = c_ocn * sqrt((us - uo) * (us - uo) + (vs - vo) * (vs - vo));
       drag_atm = c_atm * sqrt((us - ua) * (us - ua) + (vs - va) * (vs - va));
       drag_ice = c_ice * sqrt((us - ui) * (us - ui) + (vs - vi) * (vs - vi));
@@ -453,14 +460,29 @@ __device__ __noinline__ void accel_rk(const DevParams& p, double M, double T, do
     double RHS_x = (axn / 2) + bxn, RHS_y = (ayn / 2) + byn;
     RHS_x = RHS_x - drag_ocn * (u_star - uo) - drag_atm * (u_star - ua) - drag_ice * (u_star - ui) - drag_gnd * u_star;
     RHS_y = RHS_y - drag_ocn * (v_star - vo) - drag_atm * (v_star - va) - drag_ice * (v_star - vi) - drag_gnd * v_star;
+    if (INTERACTIVE) {                                             // I:2216-2227
+      if (itloop > 1) iaf(us_ia, vs_ia, ia);
+      RHS_x = RHS_x - (((ia.P11 * u_star) + (ia.P12 * v_star)) - ia.Pu_x);
+      RHS_y = RHS_y - (((ia.P21 * u_star) + (ia.P22 * v_star)) - ia.Pu_y);
+    }
     double lambda = drag_ocn + drag_atm + drag_ice + drag_gnd;
     double A11 = 1. + dt * lambda, A22 = A11, A12 = -0.0 * dt * f_cori, A21 = 0.0 * dt * f_cori;
+    if (INTERACTIVE) {
+      if (p.only_interactive_forces) {                             // I:2236-2242
+        RHS_x = (ia.IA_x / 2) - (((ia.P11 * u_star) + (ia.P12 * v_star)) - ia.Pu_x);
+        RHS_y = (ia.IA_y / 2) - (((ia.P21 * u_star) + (ia.P22 * v_star)) - ia.Pu_y);
+        A11 = 1 + (dt * ia.P11); A12 = (dt * ia.P12); A21 = (dt * ia.P21); A22 = 1 + (dt * ia.P22);
+      } else {
+        A11 = A11 + (dt * ia.P11); A12 = A12 + (dt * ia.P12); A21 = A21 + (dt * ia.P21); A22 = A22 + (dt * ia.P22);
+      }
+    }
     double detA = 1. / ((A11 * A22) - (A12 * A21));
     ax = detA * (A22 * RHS_x - A12 * RHS_y);
     ay = detA * (A11 * RHS_y - A21 * RHS_x);
     uveln = u_star + dt * ax; vveln = v_star + dt * ay;
   }
   axn = 0.; ayn = 0.;                                              // I:2283-2296 with Runge_not_Verlet, C_N = 0
+  if (INTERACTIVE && p.only_interactive_forces) { axn = ia.IA_x; ayn = ia.IA_y; }
   bxn = ax - (axn / 2); byn = ay - (ayn / 2);
   if ((p.speed_limit > 0.) || (p.speed_limit == -1.)) {
     double speed = sqrt(uveln * uveln + vveln * vveln);
