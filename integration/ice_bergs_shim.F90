@@ -122,6 +122,47 @@ module ice_bergs
       integer(c_int32_t), value :: nbytes, nranks, rank, device
       integer(c_int32_t) :: rc
     end function
+    function kid_count_bergs(h, n) bind(C, name='kid_count_bergs') result(rc)
+      import :: c_ptr, c_int32_t, c_int64_t
+      type(c_ptr), value :: h
+      integer(c_int64_t), intent(out) :: n
+      integer(c_int32_t) :: rc
+    end function
+    function kid_get_calving_state(h, stored_ice, stored_heat, counter) bind(C, name='kid_get_calving_state') result(rc)
+      import :: c_ptr, c_int32_t, c_double
+      type(c_ptr), value :: h
+      real(c_double), intent(out) :: stored_ice(*), stored_heat(*)
+      integer(c_int32_t), intent(out) :: counter(*)
+      integer(c_int32_t) :: rc
+    end function
+    function kid_set_bonds(h, n, cols) bind(C, name='kid_set_bonds') result(rc)
+      import :: c_ptr, c_int32_t, c_int64_t, KidBondColumns
+      type(c_ptr), value :: h
+      integer(c_int64_t), value :: n
+      type(KidBondColumns), intent(in) :: cols
+      integer(c_int32_t) :: rc
+    end function
+    function kid_get_bonds(h, n, cols) bind(C, name='kid_get_bonds') result(rc)
+      import :: c_ptr, c_int32_t, c_int64_t, KidBondColumns
+      type(c_ptr), value :: h
+      integer(c_int64_t), intent(inout) :: n
+      type(KidBondColumns), intent(inout) :: cols
+      integer(c_int32_t) :: rc
+    end function
+    !> record_posn F:5328: called when the shim's own sample_traj (I:5173-5178) says so
+    function kid_record_posn(h) bind(C, name='kid_record_posn') result(rc)
+      import :: c_ptr, c_int32_t
+      type(c_ptr), value :: h
+      integer(c_int32_t) :: rc
+    end function
+    function kid_get_trajectory(h, n, cols, clear) bind(C, name='kid_get_trajectory') result(rc)
+      import :: c_ptr, c_int32_t, c_int64_t, KidTrajColumns
+      type(c_ptr), value :: h
+      integer(c_int64_t), intent(inout) :: n
+      type(KidTrajColumns), intent(inout) :: cols
+      integer(c_int32_t), value :: clear
+      integer(c_int32_t) :: rc
+    end function
     function kid_last_error(h) bind(C, name='kid_last_error') result(msg)
       import :: c_ptr
       type(c_ptr), value :: h
@@ -266,7 +307,100 @@ contains
     call check(bergs%h, kid_incr_mass(bergs%h, mass), 'KID, icebergs_incr_mass')
   end subroutine icebergs_incr_mass
 
-  ! read_icebergs_nml, read_restart_into_library, icebergs_save_restart, local_device_ordinal:
-  ! host-side FMS/NetCDF code taken over from icebergs_framework.F90 / icebergs_fmsio.F90 unchanged
-  ! except that the berg columns are handed to / fetched from the library instead of the linked lists.
+  !> &icebergs_nml (F:825-856) -> KidParams.  Declarations, the namelist statement and the copies are generated from
+  !! include/kid_b200.h (integration/kid_b200_nml.inc), so every field the library knows is a namelist entry of the
+  !! same name; entries of the reference's namelist that never reach the hot path (verbose, budget, restart and
+  !! trajectory file names, ...) are read by the FMS-side code that still owns them.
+  subroutine read_icebergs_nml(p)
+    type(KidParams), intent(inout) :: p
+    integer :: iunit, ierr
+#define KID_NML_COPY_IN
+#include "kid_b200_nml.inc"
+#undef KID_NML_COPY_IN
+    iunit = open_namelist_file()
+    read(iunit, icebergs_nml, iostat=ierr)
+    ierr = check_nml_error(ierr, 'icebergs_nml')
+    call close_file(iunit)
+    call copy_out()
+  contains
+    subroutine copy_out()
+#define KID_NML_COPY_OUT
+#define KID_NML_NO_DECLS
+#include "kid_b200_nml.inc"
+#undef KID_NML_COPY_OUT
+    end subroutine copy_out
+  end subroutine read_icebergs_nml
+
+  !> rank -> CUDA device of this node: ranks are placed round-robin over the GPUs (KID_GPUS_PER_NODE, default 8)
+  function local_device_ordinal() result(dev)
+    integer(c_int32_t) :: dev
+    character(len=16) :: env
+    integer :: ngpu, stat
+    ngpu = 8
+    call get_environment_variable('KID_GPUS_PER_NODE', env, status=stat)
+    if (stat == 0) read(env, *, iostat=stat) ngpu
+    if (ngpu < 1) ngpu = 1
+    dev = int(mod(mpp_pe() - mpp_root_pe(), ngpu), c_int32_t)
+  end function local_device_ordinal
+
+  !> read_restart_calving / read_restart_bergs / read_restart_bonds (IO:606-975, IO:1282-1530): the NetCDF / FMS I/O
+  !! stays on the host exactly as in icebergs_fmsio.F90; instead of create_iceberg + add_new_berg_to_list per record the
+  !! columns it reads go to the library in one call each.
+  subroutine read_restart_into_library(bergs, Time)
+    type(icebergs), pointer :: bergs
+    type(time_type), intent(in) :: Time
+    type(KidBergColumns) :: c
+    type(KidBondColumns) :: cb
+    integer(c_int64_t) :: nb, nbonds
+    real, allocatable, target :: stored_ice(:,:,:), stored_heat(:,:)
+    integer(c_int32_t), allocatable, target :: counter(:,:)
+    ! calving.res.nc: FMS hands back the compute domain; the library holds the data domain (halos zero until the first
+    ! halo update of icebergs_run, I:5203)
+    allocate(stored_ice(bergs%dom%isd:bergs%dom%ied, bergs%dom%jsd:bergs%dom%jed, KID_NCLASSES), &
+             stored_heat(bergs%dom%isd:bergs%dom%ied, bergs%dom%jsd:bergs%dom%jed), &
+             counter(bergs%dom%isd:bergs%dom%ied, bergs%dom%jsd:bergs%dom%jed))
+    stored_ice = 0. ; stored_heat = 0. ; counter = 0
+    call read_restart_calving_fields(bergs%domain, stored_ice, stored_heat, counter)        ! IO:1432-1530, unchanged
+    call check(bergs%h, kid_set_calving_state(bergs%h, stored_ice, stored_heat, counter), 'KID, read_restart_calving')
+    ! icebergs.res.nc: one allocatable array per variable (IO:606-760 reads them exactly like this), handed over by address
+    call read_restart_berg_columns(bergs%domain, nb, c)                                        ! IO:606-975 without the list insertion
+    call check(bergs%h, kid_set_bergs(bergs%h, nb, c), 'KID, read_restart_bergs')
+    if (bergs%p%iceberg_bonds_on /= 0) then
+      call read_restart_bond_columns(bergs%domain, nbonds, cb)                                 ! IO:1282-1430; nbonds = 0 without a file
+      call check(bergs%h, kid_set_bonds(bergs%h, nbonds, cb), 'KID, read_restart_bonds')       ! (initialize_iceberg_bonds I:356 when empty)
+    endif
+  end subroutine read_restart_into_library
+
+  !> I:8136: write_restart_bergs / write_restart_bonds / write_restart_calving (IO:261-566) from the library's columns
+  subroutine icebergs_save_restart(bergs, time_stamp)
+    type(icebergs), pointer :: bergs
+    character(len=*), intent(in), optional :: time_stamp
+    type(KidBergColumns) :: c
+    type(KidBondColumns) :: cb
+    integer(c_int64_t) :: nb, nbonds
+    real, allocatable, target :: stored_ice(:,:,:), stored_heat(:,:)
+    integer(c_int32_t), allocatable, target :: counter(:,:)
+    if (.not. associated(bergs)) return
+    call check(bergs%h, kid_count_bergs(bergs%h, nb), 'KID, icebergs_save_restart')
+    call allocate_berg_columns(c, nb)                     ! one array per variable of icebergs.res.nc (IO:261-337)
+    call check(bergs%h, kid_get_bergs(bergs%h, nb, c, 0_c_int32_t), 'KID, icebergs_save_restart')
+    call write_restart_berg_columns(bergs%domain, nb, c, time_stamp)          ! IO:261-430 from arrays instead of the list walk
+    if (bergs%p%iceberg_bonds_on /= 0) then
+      nbonds = 0
+      call check(bergs%h, kid_get_bonds(bergs%h, nbonds, cb), 'KID, icebergs_save_restart')   ! count only (NULL columns)
+      call allocate_bond_columns(cb, nbonds)
+      call check(bergs%h, kid_get_bonds(bergs%h, nbonds, cb), 'KID, icebergs_save_restart')
+      call write_restart_bond_columns(bergs%domain, nbonds, cb, time_stamp)   ! IO:432-560
+    endif
+    allocate(stored_ice(bergs%dom%isd:bergs%dom%ied, bergs%dom%jsd:bergs%dom%jed, KID_NCLASSES), &
+             stored_heat(bergs%dom%isd:bergs%dom%ied, bergs%dom%jsd:bergs%dom%jed), &
+             counter(bergs%dom%isd:bergs%dom%ied, bergs%dom%jsd:bergs%dom%jed))
+    call check(bergs%h, kid_get_calving_state(bergs%h, stored_ice, stored_heat, counter), 'KID, icebergs_save_restart')
+    call write_restart_calving_fields(bergs%domain, stored_ice, stored_heat, counter, time_stamp)   ! IO:564-566
+  end subroutine icebergs_save_restart
+
+  ! read_restart_calving_fields / read_restart_berg_columns / read_restart_bond_columns and their write_* counterparts,
+  ! allocate_berg_columns / allocate_bond_columns: the bodies of the routines of icebergs_fmsio.F90 cited above with the
+  ! per-record create_iceberg / list walk replaced by the array they already read into or write from (the Python
+  ! equivalents, tested against the same files, are icebergs_b200/restart_io.py).
 end module ice_bergs
