@@ -1395,6 +1395,11 @@ static int set_conglom_ids(kid_t* h) {
   if (!(h->p.mts || (h->p.contact_distance > 0.) || (h->p.contact_spring_coef != h->p.spring_coef))) return KID_OK;
   LAUNCH(h, k_conglom_init, h->n_slots, 256, h->b, h->n_slots);
   if (h->b.max_bonds == 0) return KID_OK;
+  // (measured on the bonded tabular berg: one CTA wins up to ~2000 slots -- 432 elements with their images: 0.65 ms of
+  // sweeps + host round trips -> 0.05 ms; at 7000 slots the many-CTA sweeps are faster again)
+  if (h->n_slots <= 2048 && !getenv("KID_CONGLOM_SWEEPS")) {
+    k_conglom_label_one_cta<<<1, 1024, 0, h->stream>>>(h->b, h->n_slots); h->launches++;
+  } else
   for (int it = 0; it < 100000; it++) {
     int changed = 0;
     CK(cudaMemsetAsync(h->d_changed, 0, sizeof(int), h->stream));
@@ -2041,7 +2046,18 @@ static int evolve_mts(kid_t* h) {
   const double dtf = h->mp.dt_fast;
   const bool iterate = fc && !p.explicit_inner_mts;
   const bool brk = dem && p.break_bonds_on_sub_steps && !p.use_broken_bonds_for_substep_contact;
-  if (!iterate && p.explicit_inner_mts && ns <= 4096 && !getenv("KID_MTS_NO_ONE_CTA")) {
+  static const int cluster_min = getenv("KID_MTS_CLUSTER_MIN") ? atoi(getenv("KID_MTS_CLUSTER_MIN")) : 129;
+  if (!iterate && p.explicit_inner_mts && ns >= cluster_min && ns <= 65536 && !getenv("KID_MTS_NO_CLUSTER")) {
+    // one thread-block cluster of 8 CTAs x 256 threads, hardware cluster barrier between the sweeps (kid_mts.cuh)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(8, 1, 1); cfg.blockDim = dim3(256, 1, 1); cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, k_mts_substeps_cluster<256>, h->g, h->b, h->dp, h->mp, ct, h->dcnt, ns, dtf, (int)p.mts_sub_steps));
+    h->launches++;
+  } else if (!iterate && p.explicit_inner_mts && ns <= 4096 && !getenv("KID_MTS_NO_ONE_CTA")) {
     // a few thousand elements: the whole sub-step loop in one CTA, __syncthreads() between the sweeps
     static const bool no_smem = getenv("KID_MTS_NO_SMEM") != nullptr;
     const size_t need = mts_smem_bytes(h->b, ns, dem);

@@ -449,6 +449,35 @@ __global__ void k_conglom_sweep(const __grid_constant__ DevBergs b, long long n_
   if (best != b.conglom_id[s]) { b.conglom_id[s] = best; *changed = 1; }
 }
 
+// the same propagation to its fixed point inside ONE CTA (stores of a few thousand slots: bonded runs): no launch and no
+// host round trip per sweep.  The fixed point -- the smallest seed label of the component -- does not depend on the
+// order of the updates, so the labels are those of the sweep kernel.
+__global__ void __launch_bounds__(1024) k_conglom_label_one_cta(const __grid_constant__ DevBergs b, long long n_slots) {
+  __shared__ int changed;
+  const int n = (int)n_slots, nt = blockDim.x, tid = threadIdx.x;
+  for (int it = 0; it < 1000000; it++) {
+    __syncthreads();
+    if (tid == 0) changed = 0;
+    __syncthreads();
+    for (int s = tid; s < n; s += nt) {
+      if (!(b.flags[s] & BF_ALIVE)) continue;
+      int32_t best = b.conglom_id[s];
+      for (int k = 0; k < b.max_bonds; k++) {
+        long long slot = (long long)k * b.capacity + s;
+        if (b.bond_other_id[slot] == 0) continue;
+        if (b.bond_broken && b.bond_broken[slot] == 1) continue;
+        int32_t o = b.bond_other_slot[slot];
+        if (o < 0) continue;
+        int32_t l = ((volatile int32_t*)b.conglom_id)[o];
+        if (l != 0 && (best == 0 || l < best)) best = l;
+      }
+      if (best != b.conglom_id[s]) { ((volatile int32_t*)b.conglom_id)[s] = best; changed = 1; }
+    }
+    __syncthreads();
+    if (!changed) break;
+  }
+}
+
 // initialize_iceberg_bonds I:356-441: O(N^2) distance test over every berg of the data domain, in the
 // reference's outer/inner order (cells j-major, bergs in list order) so that each berg's bond list
 // has the reference's order.  One thread per berg; the inner loop walks the sorted store.

@@ -11,6 +11,7 @@
 // bonded-conglomerate path (hundreds to 1e5 sub-steps of a few thousand elements), launch-latency bound, not the
 // HBM-bound free-drift kernel.  Conglomerates that reach several ranks, or the cyclic seam: complete copies per rank, see the end of this file.
 #pragma once
+#include <cooperative_groups.h>
 #include "kid_interact.cuh"
 
 namespace kid {
@@ -845,6 +846,65 @@ k_mts_substeps_one_cta(const __grid_constant__ DevGrid g, const __grid_constant_
         if (dem) { b.bond_broken[gs] = v.bond_broken[ls]; for (int q = 0; q < BD_N; q++) b.bond_dem[q][gs] = v.bond_dem[q][ls]; }
       }
     }
+  }
+}
+
+// one half-bond of the pair phase: dem_pair_phase's body for a single bond entry (the tasks of the cluster kernel)
+__device__ __forceinline__ void dem_pair_task(const DevBergs& b, const DevParams& p, const MtsParams& mp, DevCounters* cnt,
+                                              long long s, int k, double dt) {
+  long long slot = (long long)k * b.capacity + s;
+  if (b.bond_other_id[slot] == 0) return;
+  int32_t o = b.bond_other_slot[slot];
+  if (o < 0) { atomicOr(&cnt->error_flags, 256u); return; }
+  if (b.bond_broken[slot] != 0) return;
+  if ((long long)o < s && mts_active(b, o, b.flags[o])) return;
+  dem_bond_force(b, p, mp, cnt, s, o, slot, dt);
+}
+
+// The sub-step loop of a population of 1e2..1e4 elements on ONE THREAD-BLOCK CLUSTER: the sweeps of a sub-step are
+// separated by grid-wide dependencies, and a hardware cluster barrier (barrier.cluster, ~0.2 us, release/acquire at
+// cluster scope: the state lives in global memory / L2) costs a small fraction of a kernel launch.  Against the
+// one-CTA loop: 8 SMs' worth of fp64 lanes and registers (256-thread CTAs: no spills), and the pair phase takes one
+// (element, half-bond) task per thread instead of one element with all its bonds -- a bond is evaluated once, by its
+// first element, so half the tasks return at once and the critical path is ONE calculate_force_dem, not max_bonds.
+// The phase functions are the ones the per-sweep kernels call: same arithmetic, same results.
+template <int NT>
+__global__ void __launch_bounds__(NT)
+k_mts_substeps_cluster(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b, const __grid_constant__ DevParams p,
+                       const __grid_constant__ MtsParams mp, const CellTable ct, DevCounters* __restrict__ cnt,
+                       long long n_slots, double dt, int nsub) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cl = cg::this_cluster();
+  const long long nth = (long long)cl.num_threads(), gid = (long long)cl.thread_rank();
+  const long long n = n_slots;
+  const bool dem = p.dem != 0;
+  const bool brk = dem && mp.break_bonds_on_sub_steps && !mp.use_broken_bonds_for_substep_contact;
+  const long long npair = dem ? n * b.max_bonds : 0;
+  // The end of sub-step k (and break_bonds_dem) and the position update of sub-step k+1 touch the element's own state
+  // only (own columns, own half-bonds): one sweep, no barrier between them -- three cluster barriers per sub-step.
+  for (long long s = gid; s < n; s += nth) if (mts_active(b, s, b.flags[s])) mts_phase_pos(b, p, s, dt);
+  cl.sync();
+  for (int k = 0; k < nsub; k++) {
+    if (dem) {
+      for (long long t = gid; t < npair; t += nth) {
+        const long long s = t % n;
+        if (mts_active(b, s, b.flags[s])) dem_pair_task(b, p, mp, cnt, s, (int)(t / n), dt);
+      }
+      cl.sync();
+    }
+    for (long long s = gid; s < n; s += nth) {
+      double su, su1, su2;
+      if (mts_active(b, s, b.flags[s])) mts_phase_vel(g, b, p, mp, ct, cnt, s, dt, 1, false, su, su1, su2);
+    }
+    cl.sync();
+    for (long long s = gid; s < n; s += nth) {
+      const uint8_t f = b.flags[s];
+      const bool act = mts_active(b, s, f);
+      if (act) mts_phase_end(b, p, mp, s, dt);
+      if (brk && (f & BF_ALIVE)) dem_phase_break(b, mp, s);
+      if (act && k + 1 < nsub) mts_phase_pos(b, p, s, dt);
+    }
+    cl.sync();
   }
 }
 
