@@ -584,7 +584,8 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   else if (pin->runge_not_verlet && pin->footloose)
     unsupported = "Runge_not_Verlet=.true. with footloose is not parity-clean yet (the stepping exists: k_step_rk<.., STEP_ONLY>): set runge_not_verlet=0";
   else if (pin->tidal_drift > 0.) unsupported = "tidal_drift>0 needs the FMS random number stream";
-  else if (pin->add_iceberg_thickness_to_ssh) unsupported = "add_iceberg_thickness_to_SSH is not implemented";
+  else if (pin->add_iceberg_thickness_to_ssh && !pin->add_weight_to_ocean)
+    unsupported = "add_iceberg_thickness_to_SSH reads spread_mass: it needs add_weight_to_ocean=.true. (the field is zero otherwise)";
   else if (pin->tau_calving > 0.) unsupported = "tau_calving>0 (running mean of the calving field, I:5215) is not implemented";
   else if (pin->find_melt_using_spread_mass) unsupported = "find_melt_using_spread_mass is not implemented";
   else if (pin->dem && !(pin->mts && pin->iceberg_bonds_on)) unsupported = "dem=.true. needs mts=.true. and iceberg_bonds_on (F:1433)";
@@ -1894,6 +1895,8 @@ static int ingest_forcing(kid_t* h, const double* calving, const double* uo, con
   if (!h->p.tau_is_velocity) LAUNCH(h, k_invert_tau, n2, 256, g, n2);
   HU({g.ua, g.va});
   LAUNCH(h, k_copy_in, (long long)nr, 256, g, st[7], g.ssh, 1, 0, 0.);
+  if (h->p.add_iceberg_thickness_to_ssh)          // I:5330-5337 (spread_mass of the previous step; zero on the first call)
+    LAUNCH(h, k_ssh_from_spread_mass, n2, 256, g, h->sf.spread_mass, h->p.rho_bergs / KID_RHO_SEAWATER, n2);
   HU({g.ssh});
   LAUNCH(h, k_sst_max, (long long)nc, 256, g, st[8], calving ? st[0] : nullptr, h->dflags);
   LAUNCH(h, k_sst_in, (long long)nc, 256, g, st[8], h->dflags);

@@ -923,6 +923,16 @@ __global__ void k_copy_in(const __grid_constant__ DevGrid g, const double* __res
   dst[c] = v;
 }
 
+// add_iceberg_thickness_to_SSH I:5330-5337: over the whole data domain the sea surface height is REPLACED by the
+// freeboard-equivalent of the berg mass spread in the previous step (cells of zero area keep the input value)
+__global__ void k_ssh_from_spread_mass(const __grid_constant__ DevGrid g, const double* __restrict__ spread_mass,
+                                       double rho_ratio, long long n2) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n2) return;
+  const double a = g.area[k];
+  if (a > 0.) g.ssh[k] = ((spread_mass[k] / a) * rho_ratio);
+}
+
 // I:5221, I:5227: whole data domain
 __global__ void k_calving_units(const __grid_constant__ DevGrid g, long long n2) {
   long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;

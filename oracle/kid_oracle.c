@@ -2229,7 +2229,6 @@ Oracle* oracle_create(const KidParams* p, const KidDomain* dom, int32_t year, do
   o->iceberg_counter_grd = (int32_t*)calloc(n2, sizeof(int32_t));
   o->list = (OBerg**)calloc(n2, sizeof(OBerg*));
   if (p->tidal_drift > 0.) o_fatal(o, "oracle: tidal_drift needs the FMS random number stream (external)");
-  if (p->add_iceberg_thickness_to_ssh) o_fatal(o, "oracle: add_iceberg_thickness_to_SSH needs spread_mass (next row)");
   int nic = d->iec - d->isc + 1, njc = d->jec - d->jsc + 1;
   /* F:1021-1056 */
   for (int j = d->jsc; j <= d->jec; j++)
@@ -2553,6 +2552,10 @@ static void ingest_forcing(Oracle* o, const double* calving, const double* uo, c
   if (!o->p.tau_is_velocity) invert_tau_for_du(o);
   halo_update(o, o->ua); halo_update(o, o->va);
   for (int j = d->jsc - 1; j <= d->jec + 1; j++) for (int i = d->isc - 1; i <= d->iec + 1; i++) G(o, ssh, i, j) = C3(ssh, i, j);
+  if (o->p.add_iceberg_thickness_to_ssh) {               /* I:5330-5337 */
+    for (int i = d->isd; i <= d->ied; i++) for (int j = d->jsd; j <= d->jed; j++)
+      if (G(o, area, i, j) > 0) G(o, ssh, i, j) = ((G(o, spread_mass, i, j) / G(o, area, i, j)) * (o->p.rho_bergs / RHO_SEAWATER));
+  }
   halo_update(o, o->ssh);
   double max_SST = -1e300;
   for (int j = d->jsc; j <= d->jec; j++) for (int i = d->isc; i <= d->iec; i++) max_SST = dmax(max_SST, C2(sst, i, j) * G(o, msk, i, j));

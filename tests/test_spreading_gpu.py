@@ -56,6 +56,22 @@ def test_rectangular_spreading_latlon(old_spreading):
     api.icebergs_end(b)
 
 
+def test_add_iceberg_thickness_to_ssh():
+    """add_iceberg_thickness_to_SSH (I:5330-5337): from the second call on the sea surface height the bergs feel is the
+    freeboard-equivalent of the mass spread in the previous step, not the input field."""
+    from common import COMPARE_F64, assert_bergs_match
+    case = Case(96, 48, 30000, add_weight_to_ocean=1, use_old_spreading=0, add_iceberg_thickness_to_ssh=1)
+    b, o = case.make_gpu(), case.make_oracle()
+    names = list(COMPARE_F64) + ["ine", "jne", "start_year", "id"]
+    for step in range(3):
+        outputs("gpu", b, case); outputs("ora", o, case)
+        assert grid_rel(b.grid_field(D.KID_FLD_SSH), o.grid_field(D.KID_FLD_SSH)) < 1e-10, f"ssh, call {step}"
+        assert_bergs_match(b.get_bergs(names), o.get_bergs(names), rtol=1e-9, context=f"call {step}")
+    ssh = o.grid_field(D.KID_FLD_SSH)
+    assert ssh.max() > 0.0 and not np.allclose(ssh[4:-4, 4:-4], case.forcing["ssh"][1:-1, 1:-1])      # it did replace the input
+    api.icebergs_end(b)
+
+
 def test_hexagonal_spreading_with_bond_orientation():
     """tests/collision_tests: hexagonal elements, orientation from the bonds (I:3829), 1 km cells."""
     from test_interactions_gpu import Pair
