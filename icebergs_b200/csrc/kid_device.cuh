@@ -149,6 +149,13 @@ struct DevBergs {
   // dem bond history and the saved pair forces (type(bond) F:372-386, save_bond_forces F:53), same layout as bond_length
   double* bond_dem[11];
   double* ia_radius;          // scratch: interaction radius per berg, valid inside the shared-memory MTS kernel only
+  // scratch of the shared-memory MTS kernel (<= 128 elements): per element the slots the sub-step contact search
+  // has to look at (same conglomerate, outer layer, not a bond partner, in the 3x3 cells), in the search's own order;
+  // rebuilt when a bond breaks (cand_dirty).  nullptr everywhere else.
+  uint8_t* cand;
+  int32_t* cand_n;
+  int32_t* cand_dirty;
+  int32_t cand_stride, pad_cand_;
 };
 enum BondDem : int { BD_TANGD1 = 0, BD_TANGD2, BD_REL_ROT, BD_NSTRESS, BD_SSTRESS, BD_FX, BD_FY, BD_FDX, BD_FDY, BD_T, BD_TD, BD_N };
 

@@ -401,6 +401,7 @@ __device__ __noinline__ bool dem_bond_force(const DevBergs& b, const DevParams& 
     T = 0.; T_d = 0.; T_other = 0.;
     if (nstress < 0) { F_x = Fn_x; F_y = Fn_y; Fd_x = -damping_coef * ur; Fd_y = -damping_coef * vr; }   // sheared under compression
     else { F_x = 0.; F_y = 0.; Fd_x = 0.; Fd_y = 0.; }
+    if (b.cand_dirty) *b.cand_dirty = 1;
     b.bond_broken[bs] = 2;          // 2 = broke in this sub-step: its stored forces still count once (I:1158-1196),
     if (bo >= 0) b.bond_broken[bo] = 2;   //     mts_phase_end turns it into 1
     if (mp.use_broken_bonds_for_substep_contact) { atomicSub(&b.n_bonds[s], 1); atomicSub(&b.n_bonds[o], 1); }
@@ -436,6 +437,31 @@ __device__ __forceinline__ void dem_pair_phase(const DevBergs& b, const DevParam
     if ((long long)o < s && mts_active(b, o, b.flags[o])) continue;
     dem_bond_force(b, p, mp, cnt, s, o, slot, dt);
   }
+}
+
+// The part of dem_sum_phase's contact search that does not change from sub-step to sub-step (cells are fixed until
+// k_mts_finish; conglomerate labels, bond partners and bond counts change only when a bond breaks): the candidates of
+// element s in the order the search visits them.
+__device__ __forceinline__ void dem_build_candidates(const DevGrid& g, const DevBergs& b, const CellTable& ct, long long s) {
+  const int i = b.ine[s], j = b.jne[s], mb = b.max_bonds;
+  const int32_t my_cong = b.conglom_id[s];
+  uint8_t* cl = b.cand + (size_t)s * b.cand_stride;
+  int nc = 0;
+  for (int grdj = max(j - 1, g.jsd + 1); grdj <= min(j + 1, g.jed); grdj++)
+    for (int grdi = max(i - 1, g.isd + 1); grdi <= min(i + 1, g.ied); grdi++) {
+      const int c = gidx(g, grdi, grdj), n = ct.count[c], o0 = ct.start[c];
+      for (int k = 0; k < n; k++) {
+        const int o = o0 + k;
+        if (b.conglom_id[o] != my_cong || !(b.n_bonds[o] < mb)) continue;
+        bool is_partner = false;
+        for (int q = 0; q < mb; q++) {
+          const long long slot = (long long)q * b.capacity + s;
+          if (b.bond_other_id[slot] != 0 && b.bond_other_slot[slot] == o) is_partner = true;
+        }
+        if (!is_partner) cl[nc++] = (uint8_t)o;
+      }
+    }
+  b.cand_n[s] = nc;
 }
 
 // second half: the berg's sums (accel_explicit_inner_mts I:1756-1915 with dem)
@@ -477,6 +503,19 @@ __device__ __noinline__ void dem_sum_phase(const DevGrid& g, const DevBergs& b, 
     const double* __restrict__ rad = b.ia_radius;
     const bool quick = !p.grid_is_latlon && rad != nullptr && !mp.constant_interaction_LW;
     const double lon_s = lon_old[s], lat_s = lat_old[s], R_s = quick ? rad[s] : 0.;
+    if (b.cand) {
+      // the static part of the search (conglomerate, outer layer, partners, cells) was done once: dem_build_candidates
+      const int nc = b.cand_n[s];
+      const uint8_t* __restrict__ cl = b.cand + (size_t)s * b.cand_stride;
+      for (int k = 0; k < nc; k++) {
+        const int o = cl[k];
+        if (quick) {
+          double rx = lon_s - lon_old[o], ry = lat_s - lat_old[o], r2 = (rx * rx) + (ry * ry), RR = R_s + rad[o];
+          if (RR * RR <= r2) continue;
+        }
+        dem_unbonded_force(b, p, mp, s, o, IA_x, IA_y, IAd_x, IAd_y, uvel0, vvel0, uvel0, vvel0);
+      }
+    } else
     for (int grdj = max(j - 1, g.jsd + 1); grdj <= min(j + 1, g.jed); grdj++)
       for (int grdi = max(i - 1, g.isd + 1); grdi <= min(i + 1, g.ied); grdi++) {
         int c = gidx(g, grdi, grdj);
@@ -699,6 +738,7 @@ __device__ __forceinline__ void dem_phase_break(const DevBergs& b, const MtsPara
     if (b.bond_dem[BD_NSTRESS][slot] > tn || b.bond_dem[BD_SSTRESS][slot] > tt) {
       b.bond_other_id[slot] = 0; b.bond_other_slot[slot] = -1;
       b.n_bonds[s] -= 1;
+      if (b.cand_dirty) *b.cand_dirty = 1;
     }
   }
 }
@@ -771,6 +811,7 @@ __host__ __device__ inline size_t mts_smem_bytes(const DevBergs& b, long long n,
   t += r16(8 * n) + 2 * r16(4 * n) + r16(n) + 2 * r16(4 * n) + r16(8 * n);           // id, ine, jne, flags, conglom_id, n_bonds, ia_radius
   const size_t nb = (size_t)n * b.max_bonds;
   if (nb) { t += r16(8 * nb) + r16(4 * nb) + r16(8 * nb); if (dem) t += r16(4 * nb) + BD_N * r16(8 * nb); }
+  if (dem && n <= 128) t += r16((size_t)n * n) + r16(4 * n) + 16;      // contact candidates (dem_build_candidates)
   return t;
 }
 
@@ -802,6 +843,10 @@ k_mts_substeps_one_cta(const __grid_constant__ DevGrid g, const __grid_constant_
       v.bond_length = (double*)carve(8 * (size_t)nb);
       if (dem) { v.bond_broken = (int32_t*)carve(4 * (size_t)nb); for (int q = 0; q < BD_N; q++) v.bond_dem[q] = (double*)carve(8 * (size_t)nb); }
     }
+    if (dem && n <= 128 && mp.explicit_inner_mts) {
+      v.cand = (uint8_t*)carve((size_t)n * n); v.cand_n = (int32_t*)carve(4 * (size_t)n); v.cand_dirty = (int32_t*)carve(16);
+      v.cand_stride = n;
+    }
     for (int s = tid; s < n; s += nt) {
       for (int c = 0; c < C_NCOLS; c++) if (b.f64[c]) v.f64[c][s] = b.f64[c][s];
       v.id[s] = b.id[s]; v.ine[s] = b.ine[s]; v.jne[s] = b.jne[s]; v.flags[s] = b.flags[s];
@@ -814,6 +859,11 @@ k_mts_substeps_one_cta(const __grid_constant__ DevGrid g, const __grid_constant_
       }
     }
     __syncthreads();
+    if (v.cand) {
+      if (tid == 0) *v.cand_dirty = 0;
+      for (int s = tid; s < n; s += nt) dem_build_candidates(g, v, ct, s);
+      __syncthreads();
+    }
   }
 #define KID_EACH_ACTIVE(body)                                                 \
   for (int q = 0; q < per; q++) {                                             \
@@ -824,6 +874,12 @@ k_mts_substeps_one_cta(const __grid_constant__ DevGrid g, const __grid_constant_
   for (int k = 0; k < nsub; k++) {
     KID_EACH_ACTIVE(mts_phase_pos(v, p, s, dt))
     if (dem) { KID_EACH_ACTIVE(dem_pair_phase(v, p, mp, cnt, s, dt)) }
+    if (v.cand && *v.cand_dirty) {           // a bond broke in the pair phase: the outer layer the sum phase searches changed
+      __syncthreads();
+      if (tid == 0) *v.cand_dirty = 0;
+      for (int s = tid; s < n; s += nt) dem_build_candidates(g, v, ct, s);
+      __syncthreads();
+    }
     double su, su1, su2;
     KID_EACH_ACTIVE(mts_phase_vel(g, v, p, mp, ct, cnt, s, dt, 1, false, su, su1, su2))
     KID_EACH_ACTIVE(mts_phase_end(v, p, mp, s, dt))
@@ -832,6 +888,12 @@ k_mts_substeps_one_cta(const __grid_constant__ DevGrid g, const __grid_constant_
         long long s = (long long)q * nt + tid;
         if (s < n && (v.flags[s] & BF_ALIVE)) dem_phase_break(v, mp, s);
       }
+      __syncthreads();
+    }
+    if (v.cand && *v.cand_dirty) {           // a bond broke in this sub-step: partners / outer layer changed
+      __syncthreads();
+      if (tid == 0) *v.cand_dirty = 0;
+      for (int s = tid; s < n; s += nt) dem_build_candidates(g, v, ct, s);
       __syncthreads();
     }
   }
