@@ -26,14 +26,15 @@ def test_rk4_collision_test_first_steps():
 
 
 def test_rk4_collision_test_through_contact():
-    """the conglomerates meet after ~350 steps: contact springs and damping inside the RK stages"""
+    """the conglomerates meet after ~500 steps: contact springs and damping inside the RK stages"""
     params = lambda: S.collision_params(api.default_params, runge_not_verlet=1)
     p = Pair(S.collision_bergs(), params)
     gaps = []
-    for k in range(9):
+    for k in range(12):
         p.step(50)
-        # (after the contact at ~350 steps rounding differences grow about tenfold per 100 steps, as with Verlet stepping)
-        p.check(f"RK4, {50 * (k + 1)} steps", rtol=1e-6 if k < 6 else 1e-4)
+        # (after the contact at ~500 steps rounding differences grow about tenfold per 100 steps, as with Verlet stepping)
+        # (byn = ay - ayn/2 is a small difference of large terms: 1e-13 m/s2 absolute is already 1e-6 relative late in the approach)
+        p.check(f"RK4, {50 * (k + 1)} steps", rtol=1e-6 if k < 6 else (1e-5 if k < 9 else 1e-3))
         g = by_id(p.b.get_bergs(["id", "lat"]))
         half = g["lat"] < 10.0e3
         gaps.append(float(g["lat"][~half].min() - g["lat"][half].max()))
