@@ -44,16 +44,16 @@ WEAK_BERGS = 12_500_000        # per GPU, configs[4] / BASELINE.md weak series
 
 def ncu_traffic():
     """dram bytes of one k_step launch on the N=1 workload from the committed `ncu --set full` summary."""
-    for name in ("r2_kstep_summary.txt", "r1i_kstep_final_summary.txt"):
+    for name in ("r2_kstep_fast_summary.txt", "r1i_kstep_final_summary.txt"):
         p = os.path.join(ROOT, "profiles", name)
         if not os.path.exists(p):
             continue
         rd = wr = None
         for ln in open(p):
             f = ln.split()
-            if len(f) == 2 and f[0] == "dram__bytes_read.sum":
+            if len(f) >= 2 and f[0] == "dram__bytes_read.sum":        # "name value [Gbyte]"
                 rd = float(f[1])
-            if len(f) == 2 and f[0] == "dram__bytes_write.sum":
+            if len(f) >= 2 and f[0] == "dram__bytes_write.sum":
                 wr = float(f[1])
         if rd is not None and wr is not None:
             return (rd + wr) * 1e9, f"ncu --set full capture of this workload, profiles/{name}"
