@@ -405,3 +405,164 @@ class TabularGrid(CartesianGrid):
                  tauxa=np.full(i0.shape, ua), tauya=z0.copy(), ssh=z1.copy(), sst=np.full(i0.shape, -1.0),
                  sss=np.full(i0.shape, 34.0), cn=z1.copy(), hi=z1.copy(), calving=z0.copy(), calving_hflx=z0.copy())
         return {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in f.items()}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SURVEY 8 f4, tripolar fold: an analytic bipolar cap.  In the polar stereographic plane (X, Y) = 2 tan(colat/2) *
+# (cos lon, sin lon) the corners lie on confocal ellipses X = a cosh(mu) cos(nu), Y = a sinh(mu) sin(nu) with
+# nu = 2 pi i / gni (cyclic in i) and mu = mu_max (gnj - j) / gnj, so row gnj (mu = 0) is the segment between the two
+# grid poles (+-a, 0) walked twice: corner (i, gnj) IS corner (gni - i, gnj) -- FOLD_NORTH_EDGE of a tripolar grid (Murray
+# 1996), and cell (i, gnj+k) of the analytic continuation mu < 0 is cell (gni+1-i, gnj+1-k) turned by 180 degrees.
+class BipolarCapGrid:
+    def __init__(self, gni=90, gnj=24, isc=1, iec=None, jsc=1, jec=None, colat_pole_deg=25.0, mu_max=0.6):
+        assert gni % 2 == 0
+        self.gni, self.gnj = gni, gnj
+        self.isc, self.iec = isc, gni if iec is None else iec
+        self.jsc, self.jec = jsc, gnj if jec is None else jec
+        self.a = 2.0 * np.tan(0.5 * np.radians(colat_pole_deg))
+        self.mu_max = mu_max
+
+    def _ij(self, ring):
+        i = np.arange(self.isc - ring, self.iec + ring + 1)
+        j = np.arange(self.jsc - ring, self.jec + ring + 1)
+        return np.meshgrid(i, j)
+
+    def _munu(self, i, j):
+        return self.mu_max * (self.gnj - np.asarray(j, dtype=np.float64)) / self.gnj, 2.0 * np.pi * np.asarray(i, dtype=np.float64) / self.gni
+
+    def plane(self, i, j):
+        mu, nu = self._munu(i, j)
+        return self.a * np.cosh(mu) * np.cos(nu), self.a * np.sinh(mu) * np.sin(nu)
+
+    @staticmethod
+    def plane_to_lonlat(X, Y):
+        r = np.hypot(X, Y)
+        return np.degrees(np.arctan2(Y, X)), 90.0 - np.degrees(2.0 * np.arctan(0.5 * r))
+
+    def lonlat(self, i, j):
+        """lon in the branch that is continuous along a row: [0, 360] from i = 0 to gni (and beyond, periodically)"""
+        i = np.asarray(i, dtype=np.float64)
+        X, Y = self.plane(i, j)
+        lon, lat = self.plane_to_lonlat(X, Y)
+        mu, _ = self._munu(i, j)
+        # geometric longitude of the point, then the branch: rows south of the fold run 0..360 with i, the continuation
+        # beyond the fold is the mirror image (360 - that)
+        base = np.mod(i, self.gni) / self.gni * 360.0
+        base = np.where(mu < 0, 360.0 - base, base)
+        lon = lon + 360.0 * np.round((base - lon) / 360.0)
+        return lon + 360.0 * np.floor(i / self.gni) * np.where(mu < 0, -1.0, 1.0), lat
+
+    def corner_lonlat(self, ring=0):
+        return self.lonlat(*self._ij(ring))
+
+    @staticmethod
+    def _sphere(X, Y):
+        r2 = X * X + Y * Y
+        return np.stack([4.0 * X / (4.0 + r2), 4.0 * Y / (4.0 + r2), (4.0 - r2) / (4.0 + r2)])
+
+    def _xyz(self, i, j):
+        return self._sphere(*self.plane(i, j))
+
+    @staticmethod
+    def _dist(p, q):
+        return REARTH * np.arccos(np.clip((p * q).sum(axis=0), -1.0, 1.0))
+
+    def grid_angle(self, i, j):
+        """(cos, sin) of the angle from local east to the grid's +i direction, counter-clockwise"""
+        mu, nu = self._munu(i, j)
+        tx, ty = -np.cosh(mu) * np.sin(nu), np.sinh(mu) * np.cos(nu)
+        n = np.maximum(np.hypot(tx, ty), 1e-300)
+        tx, ty = tx / n, ty / n
+        X, Y = self.plane(i, j)
+        lam = np.arctan2(Y, X)
+        return tx * (-np.sin(lam)) + ty * np.cos(lam), tx * (-np.cos(lam)) + ty * (-np.sin(lam))
+
+    def wet(self, ring=1):
+        i, j = self._ij(ring)
+        iw = np.mod(i - 1, self.gni) + 1
+        jj = np.where(j > self.gnj, 2 * self.gnj + 1 - j, j)
+        iw = np.where(j > self.gnj, self.gni + 1 - iw, iw)
+        # land around the two grid poles (the degenerate cells at nu = 0, pi) and along the southern edge
+        pole = (np.minimum(iw, self.gni + 1 - iw) <= 3) | (np.abs(iw - (self.gni // 2 + 0.5)) <= 3)
+        _, latc = self.lonlat(iw - 0.5, jj - 0.5)
+        return (~(pole | (jj <= 2) | (latc > 87.0))).astype(np.float64)      # ... and around the geographic pole
+
+    def init_args(self):
+        i0, j0 = self._ij(0)
+        i1, j1 = self._ij(1)
+        lon, lat = self.lonlat(i0, j0)
+        dx = self._dist(self._xyz(i1 - 1, j1), self._xyz(i1, j1))           # northern edge of cell (i,j)
+        dy = self._dist(self._xyz(i1, j1 - 1), self._xyz(i1, j1))           # eastern edge
+        d1 = self._xyz(i0, j0) - self._xyz(i0 - 1, j0 - 1)
+        d2 = self._xyz(i0 - 1, j0) - self._xyz(i0, j0 - 1)
+        area = 0.5 * REARTH ** 2 * np.sqrt((np.cross(d1, d2, axis=0) ** 2).sum(axis=0))
+        ca, sa = self.grid_angle(i1 - 0.5, j1 - 0.5)
+        return dict(ice_lon=lon, ice_lat=lat, ice_wet=self.wet(1), ice_dx=dx, ice_dy=dy, ice_area=area,
+                    cos_rot=ca, sin_rot=-sa,                         # rotate I:4953: u_geo = cos*u + sin*v
+                    ocean_depth=np.full(lon.shape, 4000.0))
+
+    def forcing(self, speed=0.9, direction_deg=80.0):
+        """A uniform stream in the stereographic plane (it crosses the fold line Y = 0), given as grid-oriented B-grid
+        components; the ice and the wind follow it, scalars are smooth functions of the plane coordinates."""
+        i0, j0 = self._ij(0)
+        i1, j1 = self._ij(1)
+        vx, vy = speed * np.cos(np.radians(direction_deg)), speed * np.sin(np.radians(direction_deg))
+
+        def grid_components(i, j):
+            mu, nu = self._munu(i, j)
+            tx, ty = -np.cosh(mu) * np.sin(nu), np.sinh(mu) * np.cos(nu)
+            n = np.maximum(np.hypot(tx, ty), 1e-300)
+            tx, ty = tx / n, ty / n
+            return vx * tx + vy * ty, -vx * ty + vy * tx          # along +i, along +j (= t rotated by +90 degrees)
+
+        uo, vo = grid_components(i1, j1)
+        ua, va = grid_components(i0, j0)
+        Xc, Yc = self.plane(i1 - 0.5, j1 - 0.5)
+        X0, Y0 = self.plane(i0 - 0.5, j0 - 0.5)
+        f = dict(uo=uo, vo=vo, ui=0.5 * uo, vi=0.5 * vo, tauxa=8.0 * ua, tauya=8.0 * va,
+                 ssh=0.3 * np.sin(3.0 * Xc) * np.cos(2.0 * Yc), sst=-1.0 + 2.5 * np.cos(2.0 * X0) ** 2,
+                 sss=np.full(i0.shape, 34.0), cn=np.clip(0.6 + 0.5 * np.sin(4.0 * Yc), 0.0, 1.0),
+                 hi=1.0 + 0.5 * np.cos(3.0 * Xc), calving=np.zeros(i0.shape), calving_hflx=np.zeros(i0.shape))
+        return {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in f.items()}
+
+    def seed_bergs(self, n, stream=0, seed=SEED, rows=4):
+        """n bergs in the wet cells of the `rows` rows below the fold that this tile owns"""
+        i0, j0 = self._ij(0)
+        ok = (self.wet(0) > 0.5) & (j0 > self.gnj - rows)
+        # keep clear of the geographic pole (it sits in the middle of the fold line)
+        lonc, latc = self.lonlat(i0 - 0.5, j0 - 0.5)
+        ok &= latc < 86.0
+        jj, ii = np.nonzero(ok)
+        ncell = len(ii)
+        k = np.arange(n, dtype=np.uint64)
+        base = np.uint64(stream) << np.uint64(40)
+        c = np.minimum((u01(1, k + base, seed) * ncell).astype(np.int64), ncell - 1)
+        i = (ii[c] + self.isc).astype(np.int32)
+        j = (jj[c] + self.jsc).astype(np.int32)
+        xi = 0.05 + 0.9 * u01(2, k + base, seed)
+        yj = 0.05 + 0.9 * u01(3, k + base, seed)
+        cls = np.minimum((u01(4, k + base, seed) * 10).astype(np.int64), 9)
+        cr = {q: self.lonlat(i + di, j + dj) for q, (di, dj) in dict(ne=(0, 0), nw=(-1, 0), se=(0, -1), sw=(-1, -1)).items()}
+        pos = []
+        for q in (0, 1):       # bilin F:7071 (the non-bug formula)
+            pos.append((cr["ne"][q] * xi + cr["nw"][q] * (1 - xi)) * yj + (cr["se"][q] * xi + cr["sw"][q] * (1 - xi)) * (1 - yj))
+        lon, lat = pos
+        mass = INITIAL_MASS[cls]
+        thick = INITIAL_THICKNESS[cls]
+        width = np.sqrt(mass / (LOW_RATIO * RHO_BERGS * thick))
+        length = LOW_RATIO * width
+        cell = (j.astype(np.int64) - 1) * self.gni + (i.astype(np.int64) - 1)
+        order = np.argsort(cell, kind="stable")
+        sc = cell[order]
+        first = np.r_[0, np.nonzero(np.diff(sc))[0] + 1]
+        first_of = np.repeat(first, np.diff(np.r_[first, n]))
+        counter = np.empty(n, dtype=np.int64)
+        counter[order] = np.arange(n) - first_of + 1
+        ident = counter * (1 << 32) + (i.astype(np.int64) + self.gni * (j.astype(np.int64) - 1))
+        z = np.zeros(n)
+        return dict(lon=lon, lat=lat, uvel=z.copy(), vvel=z.copy(), mass=mass.copy(), thickness=thick.copy(),
+                    width=width, length=length, axn=z.copy(), ayn=z.copy(), bxn=z.copy(), byn=z.copy(),
+                    start_lon=lon.copy(), start_lat=lat.copy(), start_day=(cls + 1) / 17.0,
+                    start_mass=mass.copy(), mass_scaling=MASS_SCALING[cls].copy(), mass_of_bits=z.copy(),
+                    heat_density=z.copy(), start_year=np.ones(n, dtype=np.int32), ine=i, jne=j,
+                    id=ident.astype(np.int64)), counter_grid(self, cell, n)

@@ -40,7 +40,7 @@ extern "C" {
 #endif
 
 #define KID_NCLASSES 10          /* F:24  nclasses */
-#define KID_ABI_VERSION 2
+#define KID_ABI_VERSION 3
 
 /* status codes */
 enum {
@@ -248,6 +248,10 @@ typedef struct KidDomain {
   int32_t device;                 /* CUDA device ordinal to use */
   int32_t comm_kind;              /* KID_COMM_NCCL (0) or KID_COMM_LOCAL (1): what nccl_comm points to */
   void*   nccl_comm;              /* ncclComm_t, or a kid_local_comm group, or NULL (single rank) */
+  int32_t fold_north;             /* FOLD_NORTH_EDGE (tripolar grid, F:649, F:933): row gnj is folded onto itself, cell
+                                     (i, gnj+k) is cell (gni+1-i, gnj+1-k) turned by 180 degrees.  Needs cyclic_x.  kid_single_domain /
+                                     kid_define_domain leave it 0: the caller sets it from its mpp_define_domains y-flags */
+  int32_t pad_;
 } KidDomain;
 
 /* ----------------------------------------------------------------------------

@@ -1414,12 +1414,16 @@ static void calculate_mass_on_ocean(Oracle* o, int with_diagnostics) {
     }
 }
 
-/* sum_up_spread_fields I:6077-6150 (no tripolar fold: parity_x = 1 everywhere) */
+/* sum_up_spread_fields I:6077-6150.  parity_x (F:1015, F:1066: an AGRID vector of ones) is negative exactly in the halo
+ * rows beyond a folded northern edge: there the nine weights are turned by 180 degrees, I:6110-6123 */
 static void sum_up_spread_fields(Oracle* o, double* field /* data-domain array, compute part filled */, double* var9, int is_area) {
   const KidDomain* d = &o->d;
   size_t n2 = (size_t)o->nid * o->njd;
   for (int k = 0; k < 9; k++) halo_update(o, var9 + n2 * k);
 #define V9(i, j, k) var9[IDX(o, i, j) + n2 * ((k) - 1)]
+  if (d->fold_north && d->jec == d->gnj)      /* old_bug_rotated_weights F:38 = .false. */
+    for (int j = d->gnj + 1; j <= d->jed; j++) for (int i = d->isd; i <= d->ied; i++)
+      for (int k = 1; k <= 4; k++) { double t = V9(i, j, 10 - k); V9(i, j, 10 - k) = V9(i, j, k); V9(i, j, k) = t; }
   for (int j = d->jsc; j <= d->jec; j++) for (int i = d->isc; i <= d->iec; i++) {
     double dmda = V9(i, j, 5) + (((V9(i - 1, j - 1, 9) + V9(i + 1, j + 1, 1)) + (V9(i + 1, j - 1, 7) + V9(i - 1, j + 1, 3))) +
                                   ((V9(i - 1, j, 6) + V9(i + 1, j, 4)) + (V9(i, j - 1, 8) + V9(i, j + 1, 2))));
@@ -2044,6 +2048,22 @@ static void send_bergs_to_other_pes(Oracle* o) {
           if (this_->next) this_->next->prev = this_->prev;
           nsent++;
           int pe = north ? d->pe_N : d->pe_S;
+          if (north && d->fold_north && d->jec == d->gnj) {
+            /* FOLD_NORTH_EDGE (F:3138-3147, F:3181-3196: tags 9/10): the berg goes to the PE that owns the cell on the
+             * other side of the fold and is placed there by its lon/lat (unpack F:3629-3641).  On the PEs of a
+             * decomposed tripolar grid the sender's halo index (i, gnj+1) lies outside the receiver's data domain, so the
+             * scan F:6002-6007 (rows ascending) returns the real cell (gni+1-i, gnj); restated directly, which is also
+             * what keeps a one-PE run (where the reference would leave the berg in the halo row) layout-independent. */
+            clear_berg_from_partners_bonds(o, this_);
+            { OBond* cb = this_->first_bond; while (cb) { cb->other_berg = NULL; cb->other_bond = NULL; cb = cb->next_bond; } }
+            this_->prev = NULL; this_->next = NULL;
+            int fi = d->gni + 1 - this_->ine;
+            fi = ((fi - 1) % d->gni + d->gni) % d->gni + 1;
+            this_->ine = fi; this_->jne = 2 * d->gnj + 1 - this_->jne;
+            *tail = this_; tail = &this_->next;
+            this_ = nx;
+            continue;
+          }
           if (pe == d->rank) { /* cyclic-y single rank (not used by the reference tests) */
             o_fatal(o, "oracle: cyclic-y migration not restated");
           }
@@ -2052,6 +2072,10 @@ static void send_bergs_to_other_pes(Oracle* o) {
         this_ = nx;
       }
     }
+  while (inbox) {
+    OBerg* b = inbox; inbox = b->next; b->next = NULL;
+    if (place_received_berg(o, b, 0)) nrecv++; else { free_bonds(b); free(b); }
+  }
   o->cnt.n_sent = nsent; o->cnt.n_received = nrecv;
 }
 
@@ -2176,16 +2200,45 @@ static void oracle_copy_bonds(OBerg* dst, const OBerg* src) {
 }
 
 /* ------------------------------------------- mpp_update_domains, one rank */
-static void halo_update(Oracle* o, double* f) {
+/* Cyclic-x wrap of the compute rows and, with KidDomain.fold_north (FOLD_NORTH_EDGE F:649, F:933), the halo rows beyond
+ * the folded northern edge.  FMS (mpp_domains, outside the reference tree: restated from its documented semantics,
+ * UNPINNED) maps a point at position (sx, sy) -- (0,0) cell centre, (1,1) NE corner, (1,0) east face, (0,1) north face,
+ * non-symmetric memory -- across the fold as
+ *     f(i, gnj+k) = sign * f(gni+1-sx-i, gnj+1-sy-k),   k = 1..halo, i cyclic,
+ * sign = -1 for the components of a true vector (BGRID_NE / CGRID_NE / AGRID without SCALAR_PAIR), +1 otherwise.  For a
+ * true vector whose points lie ON the fold (sy = 1) the eastern half of row gnj is overwritten by the western half,
+ * f(i, gnj) = -f(gni+1-sx-i, gnj) for i > gni/2, and the two pole points of a corner field (i = gni/2, gni) are zeroed. */
+static void halo_wrap_row(Oracle* o, double* f, int j) {
   const KidDomain* d = &o->d;
-  if (d->cyclic_x && d->pe_E == d->rank) {
-    int ni = d->iec - d->isc + 1;
-    for (int j = d->jsc; j <= d->jec; j++) {
-      for (int i = d->isd; i < d->isc; i++) f[IDX(o, i, j)] = f[IDX(o, i + ni, j)];
-      for (int i = d->iec + 1; i <= d->ied; i++) f[IDX(o, i, j)] = f[IDX(o, i - ni, j)];
+  int ni = d->iec - d->isc + 1;
+  for (int i = d->isd; i < d->isc; i++) f[IDX(o, i, j)] = f[IDX(o, i + ni, j)];
+  for (int i = d->iec + 1; i <= d->ied; i++) f[IDX(o, i, j)] = f[IDX(o, i - ni, j)];
+}
+static void halo_update_pos(Oracle* o, double* f, int sx, int sy, double sign, int vector) {
+  const KidDomain* d = &o->d;
+  if (d->cyclic_x && d->pe_E == d->rank)
+    for (int j = d->jsc; j <= d->jec; j++) halo_wrap_row(o, f, j);
+  if (d->fold_north && d->jec == d->gnj) {
+    const int gni = d->gni, gnj = d->gnj;
+    if (vector && sy == 1) {
+      for (int i = gni / 2 + 1; i <= gni - sx; i++) f[IDX(o, i, gnj)] = sign * f[IDX(o, gni + 1 - sx - i, gnj)];
+      if (sx == 1) { f[IDX(o, gni / 2, gnj)] = 0.; f[IDX(o, gni, gnj)] = 0.; }
+      halo_wrap_row(o, f, gnj);
     }
+    for (int k = 1; k <= d->jed - gnj; k++)
+      for (int i = d->isd; i <= d->ied; i++) {
+        int si = gni + 1 - sx - i;
+        si = ((si - 1) % gni + gni) % gni + 1;
+        f[IDX(o, i, gnj + k)] = sign * f[IDX(o, si, gnj + 1 - sy - k)];
+      }
   }
 }
+static void halo_update(Oracle* o, double* f) { halo_update_pos(o, f, 0, 0, 1., 0); }
+/* the pairs: BGRID_NE vectors (I:5240, I:5318-5326), CGRID_NE (I:5285; dy,dx as SCALAR_PAIR F:1060), AGRID (I:5302) */
+static void halo_update_bgrid_vec(Oracle* o, double* u, double* v) { halo_update_pos(o, u, 1, 1, -1., 1); halo_update_pos(o, v, 1, 1, -1., 1); }
+static void halo_update_cgrid(Oracle* o, double* u, double* v, double sign, int vector) { halo_update_pos(o, u, 1, 0, sign, vector); halo_update_pos(o, v, 0, 1, sign, vector); }
+static void halo_update_agrid_vec(Oracle* o, double* u, double* v) { halo_update_pos(o, u, 0, 0, -1., 1); halo_update_pos(o, v, 0, 0, -1., 1); }
+static void halo_update_corner(Oracle* o, double* f) { halo_update_pos(o, f, 1, 1, 1., 0); }
 
 static double* dalloc(size_t n, double v) {
   double* a = (double*)malloc(sizeof(double) * n);
@@ -2247,8 +2300,8 @@ Oracle* oracle_create(const KidParams* p, const KidDomain* dom, int32_t year, do
     }
   (void)njc;
   /* F:1058-1066 */
-  halo_update(o, o->lon); halo_update(o, o->lat); halo_update(o, o->dy); halo_update(o, o->dx);
-  halo_update(o, o->area); halo_update(o, o->msk); halo_update(o, o->cosr); halo_update(o, o->sinr);
+  halo_update_corner(o, o->lon); halo_update_corner(o, o->lat); halo_update_cgrid(o, o->dy, o->dx, 1., 0);
+  halo_update(o, o->area); halo_update(o, o->msk); halo_update_corner(o, o->cosr); halo_update_corner(o, o->sinr);   /* cos, sin: position=CORNER, F:1063-1064 */
   halo_update(o, o->ocean_depth);
   /* F:1068-1094 */
   for (int j = d->jsc - 1; j >= d->jsd; j--) for (int i = d->isd; i <= d->ied; i++) {
@@ -2511,11 +2564,11 @@ static void ingest_forcing(Oracle* o, const double* calving, const double* uo, c
     for (int j = d->jsc - 1; j <= d->jec + 1; j++) for (int i = d->isc - 1; i <= d->iec + 1; i++) {
       G(o, uo, i, j) = C3(uo, i, j); G(o, vo, i, j) = C3(vo, i, j);
     }
-    halo_update(o, o->uo); halo_update(o, o->vo);
+    halo_update_bgrid_vec(o, o->uo, o->vo);
     for (int j = d->jsc - 1; j <= d->jec + 1; j++) for (int i = d->isc - 1; i <= d->iec + 1; i++) {
       G(o, ui, i, j) = C3(ui, i, j); G(o, vi, i, j) = C3(vi, i, j);
     }
-    halo_update(o, o->ui); halo_update(o, o->vi);
+    halo_update_bgrid_vec(o, o->ui, o->vi);
   } else if (stagger == KID_CGRID_NE) {
     /* I:5246-5259 with symmetric-memory offsets = 0 for (nic+2)-sized inputs: Iu = i-(isc-1)+1 */
     for (int i = d->isc - 1; i <= d->iec; i++) for (int j = d->jsc - 1; j <= d->jec; j++) {
@@ -2535,7 +2588,7 @@ static void ingest_forcing(Oracle* o, const double* calving, const double* uo, c
     for (int j = d->jsc; j <= d->jec; j++) for (int i = d->isc; i <= d->iec; i++) {
       ut[IDX(o, i, j)] = C2(tauxa, i, j); vt[IDX(o, i, j)] = C2(tauya, i, j);
     }
-    halo_update(o, ut); halo_update(o, vt);
+    if (stress_stagger == KID_CGRID_NE) halo_update_cgrid(o, ut, vt, -1., 1); else halo_update_agrid_vec(o, ut, vt);
     for (int i = d->isc - 1; i <= d->iec; i++) for (int j = d->jsc - 1; j <= d->jec; j++) {
       double mask = dmin(dmin(G(o, msk, i, j), G(o, msk, i + 1, j)), dmin(G(o, msk, i, j + 1), G(o, msk, i + 1, j + 1)));
       if (stress_stagger == KID_CGRID_NE) {
@@ -2548,9 +2601,9 @@ static void ingest_forcing(Oracle* o, const double* calving, const double* uo, c
     }
     free(ut); free(vt);
   } else o_fatal(o, "KID, iceberg_run: Unrecognized value of stress_stagger!");
-  halo_update(o, o->uo); halo_update(o, o->vo); halo_update(o, o->ui); halo_update(o, o->vi);
+  halo_update_bgrid_vec(o, o->uo, o->vo); halo_update_bgrid_vec(o, o->ui, o->vi);
   if (!o->p.tau_is_velocity) invert_tau_for_du(o);
-  halo_update(o, o->ua); halo_update(o, o->va);
+  halo_update_bgrid_vec(o, o->ua, o->va);
   for (int j = d->jsc - 1; j <= d->jec + 1; j++) for (int i = d->isc - 1; i <= d->iec + 1; i++) G(o, ssh, i, j) = C3(ssh, i, j);
   if (o->p.add_iceberg_thickness_to_ssh) {               /* I:5330-5337 */
     for (int i = d->isd; i <= d->ied; i++) for (int j = d->jsd; j <= d->jed; j++)
