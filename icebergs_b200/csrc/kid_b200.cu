@@ -130,6 +130,10 @@ struct kid_handle {
   double *halo_send = nullptr, *halo_recv = nullptr;
   long long halo_buf_cells = 0;        // cells x fields each halo buffer holds
   HaloStrips hs_send, hs_recv;
+  // tripolar fold (KidDomain.fold_north): the ranks of the top row of the layout, by layout column, and the shared strip
+  int fold_top_row = 0;                // this rank's tile touches the folded edge (jec == gnj)
+  std::vector<int32_t> fold_top;       // [lx]
+  double* fold_strip = nullptr;        // 16 fields x (halo+1) rows x gni
   long long n_sent_last = 0, n_recv_last = 0;
   // ---- interactions (I:480-804): ghost copies (update_halo_icebergs F:1800) and bonds
   double *gsend = nullptr, *grecv = nullptr;
@@ -491,6 +495,44 @@ static int halo_exchange(kid_t* h, double* const* fields, int nf) {
   return KID_OK;
 }
 
+// the halo rows beyond a folded northern edge (k_fold_pack / k_fold_fill, kid_comm.cuh), after the regular update.
+// Every rank enters: the in-process group's rendezvous counts all of them.
+static const FoldKind FK_CENTER = {0, 0, 1, 0}, FK_CORNER = {1, 1, 1, 0}, FK_BVEC = {1, 1, -1, 1}, FK_AVEC = {0, 0, -1, 1},
+                      FK_CU = {1, 0, -1, 1}, FK_CV = {0, 1, -1, 1}, FK_CU_PAIR = {1, 0, 1, 0}, FK_CV_PAIR = {0, 1, 1, 0};
+// dst (optional): the halo of dst[q] is filled from the rows of fields[q] (the spreading weights change layer across the fold)
+static int fold_update(kid_t* h, double* const* fields, const FoldKind* kinds, int nf, double* const* dst = nullptr) {
+  if (!h->d.fold_north || nf <= 0) return KID_OK;
+  const int me = h->d.rank, w = h->p.halo, lx = h->layout.lx;
+  const bool top = h->fold_top_row != 0;
+  for (int f0 = 0; f0 < nf; f0 += 16) {
+    int m = std::min(16, nf - f0);
+    FoldArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nf = m; a.w = w; a.gni = h->d.gni; a.gnj = h->d.gnj; a.isd = h->d.isd; a.ied = h->d.ied; a.isc = h->d.isc; a.iec = h->d.iec;
+    a.lx = lx;
+    for (int k = 0; k <= lx; k++) a.xs[k] = h->layout.xs[k];
+    for (int q = 0; q < m; q++) { a.f[q] = fields[f0 + q]; a.kind[q] = kinds[f0 + q]; }
+    std::vector<XMsg> sends, recvs;
+    if (top) {
+      k_fold_pack<<<64, 256, 0, h->stream>>>(h->g, a, h->fold_strip); h->launches++;
+      const long long per = (long long)m * (w + 1);
+      for (int px = 0; px < lx; px++) {
+        int r = h->fold_top[px];
+        if (r < 0 || r == me) continue;
+        sends.push_back({r, 300, h->fold_strip + per * (a.isc - 1), per * (a.iec - a.isc + 1)});
+        recvs.push_back({r, 300, h->fold_strip + per * (a.xs[px] - 1), per * (a.xs[px + 1] - a.xs[px])});
+      }
+    }
+    int rc = comm_exchange(h, sends, recvs);
+    if (rc) return rc;
+    if (top) {
+      if (dst) for (int q = 0; q < m; q++) a.f[q] = dst[f0 + q];
+      k_fold_fill<<<64, 256, 0, h->stream>>>(h->g, a, h->fold_strip); h->launches++;
+    }
+  }
+  return KID_OK;
+}
+
 // send_bergs_to_other_pes F:2997 between ranks: count, pack, exchange, unpack.  Returns the number
 // of bergs that arrived in n_recv; they occupy slots [n_slots, n_slots + n_recv) flagged BF_ARRIVAL.
 // s0: the slot the arrivals are appended at
@@ -537,6 +579,7 @@ static void fill_layout(DevLayout& L, const KidDomain* d) {
   memset(&L, 0, sizeof(L));
   L.lx = std::max(1, d->layout_x); L.ly = std::max(1, d->layout_y);
   L.gni = d->gni; L.gnj = d->gnj; L.cyclic_x = d->cyclic_x; L.cyclic_y = d->cyclic_y; L.rank = d->rank; L.nranks = d->nranks;
+  L.fold_north = d->fold_north;
   L.pe_at = nullptr;
   for (int k = 0; k <= L.lx && k <= KID_MAX_DIV; k++) L.xs[k] = k * (d->gni / L.lx) + std::min(k, d->gni % L.lx) + 1;
   for (int k = 0; k <= L.ly && k <= KID_MAX_DIV; k++) L.ys[k] = k * (d->gnj / L.ly) + std::min(k, d->gnj % L.ly) + 1;
@@ -600,6 +643,11 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   else if (pin->time_average_weight && pin->add_weight_to_ocean) unsupported = "time_average_weight is not implemented";
   else if (dom->cyclic_y) unsupported = "cyclic y is not implemented";
   else if (pin->halo < 2) unsupported = "halo must be >= 2";
+  else if (dom->fold_north && (!dom->cyclic_x || dom->gni % 2)) unsupported = "fold_north (FOLD_NORTH_EDGE) needs cyclic_x and an even number of columns";
+  else if (dom->fold_north && (pin->interactive_icebergs_on || pin->iceberg_bonds_on || pin->mts || pin->footloose))
+    unsupported = "fold_north with interacting / bonded / footloose bergs (halo copies across the fold, F:2010-2066) is not implemented";
+  else if (dom->fold_north && dom->jec == dom->gnj && dom->jec - dom->jsc + 1 < pin->halo + 1)
+    unsupported = "fold_north: a tile on the folded edge must be at least halo+1 rows high";
   if (unsupported) { g_init_error = std::string("kid_init: ") + unsupported; return KID_ERR_UNSUPPORTED; }
   if (dom->isd != dom->isc - pin->halo || dom->ied != dom->iec + pin->halo || dom->jsd != dom->jsc - pin->halo ||
       dom->jed != dom->jec + pin->halo) { g_init_error = "kid_init: data domain must be compute domain +/- halo"; return KID_ERR_ARG; }
@@ -678,11 +726,14 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
       CK(cudaMemcpy(dt, table.data(), sizeof(int32_t) * table.size(), cudaMemcpyHostToDevice));
       h->layout_table = dt;
       L.pe_at = dt;
+      if (d->fold_north) for (int px = 0; px < L.lx; px++) h->fold_top.push_back(table[px + L.lx * (L.ly - 1)]);
       // corner neighbours: the N/S neighbour's E/W neighbour (what the reference reaches by relaying, F:1976-2006)
       auto nb = [&](int r, int q) -> int { return (r >= 0 && r < nr) ? all[r * 8 + q] : -1; };      // q: 4=E 5=W 6=N 7=S
       auto corner = [&](int ns, int ew) -> int { int v = nb(nb(d->rank, ns), ew); return v >= 0 ? v : nb(nb(d->rank, ew), ns); };
       h->nbr[dir_of(1, 1)] = corner(6, 4); h->nbr[dir_of(-1, 1)] = corner(6, 5);
       h->nbr[dir_of(1, -1)] = corner(7, 4); h->nbr[dir_of(-1, -1)] = corner(7, 5);
+      if (d->fold_north && d->jec == d->gnj)        // mpp hands out the rank across the fold as pe_N: not a strip neighbour
+        h->nbr[dir_of(0, 1)] = h->nbr[dir_of(1, 1)] = h->nbr[dir_of(-1, 1)] = -1;
       build_strips(h, pin->halo, h->hs_send, h->hs_recv);
       long long cells = h->hs_send.off[8] + (long long)h->hs_send.ni[8] * h->hs_send.nj[8];
       h->halo_buf_cells = cells * 16;
@@ -690,6 +741,11 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
       CK(cudaMalloc(&h->halo_recv, sizeof(double) * h->halo_buf_cells));
     }
     h->nbr[4] = -1;
+    if (d->fold_north) {
+      if (d->nranks == 1) h->fold_top.assign(1, 0);
+      h->fold_top_row = (d->jec == d->gnj);
+      if (h->fold_top_row) CK(cudaMalloc(&h->fold_strip, sizeof(double) * 16 * (size_t)(pin->halo + 1) * (size_t)d->gni));
+    }
   }
   // derived parameters, F:1264, F:1312, F:1483
   KidParams* q = &h->p;
@@ -753,7 +809,7 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
     }
   };
   wrap(glon); wrap(glat); wrap(gdy); wrap(gdx); wrap(garea); wrap(gmsk); wrap(gcos); wrap(gsin); wrap(gdepth);
-  if (d->nranks > 1) {
+  if (d->nranks > 1 || d->fold_north) {
     // mpp_update_domains of the static fields between ranks (F:1058-1066): through the device
     std::vector<double>* st[9] = {&glon, &glat, &gdy, &gdx, &garea, &gmsk, &gcos, &gsin, &gdepth};
     double* dv[9];
@@ -764,6 +820,10 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
       CK(cudaMemcpyAsync(dv[k], st[k]->data(), sizeof(double) * n2, cudaMemcpyHostToDevice, h->stream));
     }
     int rc = halo_exchange(h, dv, 9);
+    if (rc) return rc;
+    // lon, lat: position=CORNER; dy, dx: CGRID_NE scalar pair; area, msk, depth: centres; cos, sin: position=CORNER (F:1058-1065)
+    const FoldKind fk9[9] = {FK_CORNER, FK_CORNER, FK_CU_PAIR, FK_CV_PAIR, FK_CENTER, FK_CENTER, FK_CORNER, FK_CORNER, FK_CENTER};
+    rc = fold_update(h, dv, fk9, 9);
     if (rc) return rc;
     for (int k = 0; k < 9; k++) CK(cudaMemcpyAsync(st[k]->data(), dv[k], sizeof(double) * n2, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -852,6 +912,7 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   g.pe_E_self = (d->pe_E == d->rank); g.pe_W_self = (d->pe_W == d->rank);
   g.has_E = (d->pe_E >= 0 && d->pe_E != d->rank); g.has_W = (d->pe_W >= 0 && d->pe_W != d->rank);
   g.has_N = (d->pe_N >= 0 && d->pe_N != d->rank); g.has_S = (d->pe_S >= 0 && d->pe_S != d->rank);
+  g.fold_north = (d->fold_north && d->jec == d->gnj) ? 1 : 0;
   struct Up { double** dst; std::vector<double>* src; };
   Up ups[] = {{&g.lon, &glon}, {&g.lat, &glat}, {&g.lonc, &glonc}, {&g.latc, &glatc}, {&g.dx, &gdx}, {&g.dy, &gdy},
               {&g.area, &garea}, {&g.msk, &gmsk}, {&g.cosr, &gcos}, {&g.sinr, &gsin}, {&g.ocean_depth, &gdepth}};
@@ -1109,7 +1170,7 @@ extern "C" int32_t kid_end(kid_t** hp) {
   cudaFree(h->d_send_counts); cudaFree(h->d_cursor); cudaFree(h->d_offsets); cudaFree(h->d_all_counts);
   if (h->h_all_counts) cudaFreeHost(h->h_all_counts);
   if (h->h_offsets) cudaFreeHost(h->h_offsets);
-  cudaFree(h->halo_send); cudaFree(h->halo_recv); cudaFree(h->layout_table);
+  cudaFree(h->halo_send); cudaFree(h->halo_recv); cudaFree(h->layout_table); cudaFree(h->fold_strip);
   cudaFree(h->gsend); cudaFree(h->grecv); cudaFree(h->d_gcounts); cudaFree(h->d_goffsets); cudaFree(h->d_gcursor);
   cudaFree(h->b.bond_other_id); cudaFree(h->b.bond_other_slot); cudaFree(h->b.bond_other_ine);
   cudaFree(h->b.bond_other_jne); cudaFree(h->b.bond_length); cudaFree(h->b.conglom_id); cudaFree(h->d_changed);
@@ -1860,11 +1921,13 @@ static int ingest_forcing(kid_t* h, const double* calving, const double* uo, con
   double** st = h->stage[use].buf;
   // halo updates: immediate on one rank (cyclic wrap); between ranks the fields are independent of
   // each other, so all strips travel in ONE exchange before the scrub
-  std::vector<double*> pending;
+  std::vector<double*> pending, fold_f;
+  std::vector<FoldKind> fold_k;          // with a folded northern edge: the same fields and where their points sit
   int hu_rc = KID_OK;
-  auto HU = [&](std::initializer_list<double*> f) {
+  auto HU = [&](std::initializer_list<double*> f, FoldKind kind) {
     if (h->d.nranks > 1) pending.insert(pending.end(), f.begin(), f.end());
     else if (!hu_rc) hu_rc = halo_update(h, f);
+    if (h->d.fold_north) for (double* q : f) { fold_f.push_back(q); fold_k.push_back(kind); }
   };
   zero_flux_fields(h, false);
   CK(cudaMemsetAsync(h->dflags, 0, 2 * sizeof(unsigned long long), h->stream));
@@ -1888,25 +1951,32 @@ static int ingest_forcing(kid_t* h, const double* calving, const double* uo, con
     LAUNCH(h, k_copy_in, (long long)nc, 256, g, st[5], h->tmp_u, 0, 0, 0.);
     LAUNCH(h, k_copy_in, (long long)nc, 256, g, st[6], h->tmp_v, 0, 0, 0.);
     { int rc_ = halo_update(h, {h->tmp_u, h->tmp_v}); if (rc_) return rc_; }
+    if (h->d.fold_north) {               // CGRID_NE (I:5285) or AGRID (I:5302) vector
+      double* tv[2] = {h->tmp_u, h->tmp_v};
+      const FoldKind kc[2] = {FK_CU, FK_CV}, ka[2] = {FK_AVEC, FK_AVEC};
+      int rc_ = fold_update(h, tv, stress_stagger == KID_AGRID ? ka : kc, 2);
+      if (rc_) return rc_;
+    }
     LAUNCH(h, k_stress_to_corners, (long long)(h->nic + 1) * (h->njc + 1), 256, g, h->tmp_u, h->tmp_v,
            stress_stagger == KID_AGRID ? 1 : 0);
   }
-  HU({g.uo, g.vo, g.ui, g.vi});
+  HU({g.uo, g.vo, g.ui, g.vi}, FK_BVEC);
   if (!h->p.tau_is_velocity) LAUNCH(h, k_invert_tau, n2, 256, g, n2);
-  HU({g.ua, g.va});
+  HU({g.ua, g.va}, FK_BVEC);
   LAUNCH(h, k_copy_in, (long long)nr, 256, g, st[7], g.ssh, 1, 0, 0.);
   if (h->p.add_iceberg_thickness_to_ssh)          // I:5330-5337 (spread_mass of the previous step; zero on the first call)
     LAUNCH(h, k_ssh_from_spread_mass, n2, 256, g, h->sf.spread_mass, h->p.rho_bergs / KID_RHO_SEAWATER, n2);
-  HU({g.ssh});
+  HU({g.ssh}, FK_CENTER);
   LAUNCH(h, k_sst_max, (long long)nc, 256, g, st[8], calving ? st[0] : nullptr, h->dflags);
   LAUNCH(h, k_sst_in, (long long)nc, 256, g, st[8], h->dflags);
-  HU({g.sst});
+  HU({g.sst}, FK_CENTER);
   LAUNCH(h, k_copy_in, (long long)nr, 256, g, st[10], g.cn, 1, 0, 0.);
   LAUNCH(h, k_copy_in, (long long)nr, 256, g, st[11], g.hi, 1, 0, 0.);
-  HU({g.cn, g.hi});
+  HU({g.cn, g.hi}, FK_CENTER);
   LAUNCH(h, k_copy_in, (long long)nc, 256, g, sss ? st[12] : nullptr, g.sss, 0, 0, sss ? 0. : -1.0);
   if (hu_rc) return hu_rc;
   if (!pending.empty()) { int rc_ = halo_exchange(h, pending.data(), (int)pending.size()); if (rc_) return rc_; }
+  if (!fold_f.empty()) { int rc_ = fold_update(h, fold_f.data(), fold_k.data(), (int)fold_f.size()); if (rc_) return rc_; }
   LAUNCH(h, k_scrub, n2, 256, g, n2);
   LAUNCH(h, k_pack_forcing, n2, 256, g, n2);
   if (h->stage[used_set].ev_consumed) {        // the staging set is free again
@@ -2243,6 +2313,15 @@ static int spread_fields(kid_t* h) {
       long long n = (long long)2 * h->p.halo * h->njc;
       LAUNCH(h, k_halo_wrap_x, n, 128, h->g, fl);
     }
+  }
+  if (h->d.fold_north) {
+    // beyond the fold the cells are turned by 180 degrees (parity_x < 0, F:1066): weight k of the cell on the other side
+    // is weight 10-k here, I:6110-6123 (old_bug_rotated_weights F:38 = .false.)
+    std::vector<double*> dst;
+    for (double* f : nine) for (int k = 0; k < 9; k++) dst.push_back(f + n2 * (8 - k));
+    std::vector<FoldKind> kc(layers.size(), FK_CENTER);
+    int rc = fold_update(h, layers.data(), kc.data(), (int)layers.size(), dst.data());
+    if (rc) return rc;
   }
   LAUNCH(h, k_sum_spread, (long long)h->nic * h->njc, 128, h->g, h->sp, sf, n2);
   if (h->sp.apply_cutoff_gridded) LAUNCH(h, k_thickness_cutoff, n2, 256, h->g, h->dp, h->sp, sf, n2);

@@ -156,12 +156,14 @@ namespace kid {
 #define KID_MAX_DIV 64
 struct DevLayout {
   int32_t lx, ly, gni, gnj, cyclic_x, cyclic_y, rank, nranks;
+  int32_t fold_north, pad;    // FOLD_NORTH_EDGE: cell (i, gnj+k) is cell (gni+1-i, gnj+1-k)
   int32_t xs[KID_MAX_DIV + 1], ys[KID_MAX_DIV + 1];
   const int32_t* pe_at;       // [lx*ly] in device memory, or nullptr
 };
 
 // owner of global cell (i,j); -1 = outside the model (NULL_PE).  i may be any number of periods off.
 __host__ __device__ __forceinline__ int owner_rank(const DevLayout& L, int i, int j) {
+  if (L.fold_north && j > L.gnj && j <= 2 * L.gnj) { i = L.gni + 1 - i; j = 2 * L.gnj + 1 - j; }
   if (i < 1 || i > L.gni) { if (!L.cyclic_x) return -1; i = ((i - 1) % L.gni + L.gni) % L.gni + 1; }
   if (j < 1 || j > L.gnj) { if (!L.cyclic_y) return -1; j = ((j - 1) % L.gnj + L.gnj) % L.gnj + 1; }
   int px = 0, py = 0;
@@ -212,9 +214,10 @@ __global__ void k_pack_leavers(const __grid_constant__ DevLayout L, const __grid
     double* rec = sendbuf + (size_t)pos * RL.w;
     pack_berg(b, s, rec, RL);
     for (int k = 0; k < b.max_bonds; k++) b.bond_other_id[(long long)k * b.capacity + s] = 0;
-    int ci = b.ine[s];       // the owner's own index of the cell: one period off when the berg crossed the seam
+    int ci = b.ine[s], cj = b.jne[s];   // the owner's own index of the cell: one period off when the berg crossed the seam
+    if (L.fold_north && cj > L.gnj) { ci = L.gni + 1 - ci; cj = 2 * L.gnj + 1 - cj; }      // ... mirrored when it crossed the fold
     if (L.cyclic_x && (ci < 1 || ci > L.gni)) ci = ((ci - 1) % L.gni + L.gni) % L.gni + 1;
-    rec[PK_INE_JNE] = __longlong_as_double(((long long)(unsigned)ci << 32) | (unsigned)b.jne[s]);
+    rec[PK_INE_JNE] = __longlong_as_double(((long long)(unsigned)ci << 32) | (unsigned)cj);
     rec[PK_YEAR_FLAGS] = __longlong_as_double(((long long)(unsigned)b.start_year[s] << 32) | (unsigned)(f & ~BF_LEAVER));
   }
 }
@@ -282,6 +285,67 @@ __global__ void k_halo_pack(const __grid_constant__ DevGrid g, const __grid_cons
     size_t cell = gidx(g, st.i0[dir] + ii, st.j0[dir] + jj);
     double* slot = buf + (size_t)st.off[dir] * st.nf + k;
     if (unpack) fl.f[q][cell] = *slot; else *slot = fl.f[q][cell];
+  }
+}
+
+// ------------------------------------------------------- tripolar fold
+// mpp_update_domains across FOLD_NORTH_EDGE (F:649, F:933; the tripolar grid): the halo rows beyond the folded northern
+// edge are the top rows of the model read backwards.  For a point at position (sx, sy) -- (0,0) cell centre, (1,1) NE
+// corner, (1,0) east face, (0,1) north face --
+//     f(i, gnj+k) = sign * f(gni+1-sx-i, gnj+1-sy-k),  k = 1..halo, i cyclic,
+// sign = -1 for the components of a true vector.  For a true vector ON the fold (sy = 1) the eastern half of row gnj is
+// the western half mirrored with the sign, and the two pole points of a corner field are zero.  (FMS itself is outside
+// the reference tree: its documented semantics restated; oracle/kid_oracle.c halo_update_pos, pinned by the analytic
+// continuation of a bipolar cap, tests/test_fold_oracle.py.)
+// The ranks of the top row share their top halo+1 rows: every such rank holds the whole strip, piece by piece in the
+// order of the layout columns (piece px: [nf][halo+1][nic_px], rows gnj-halo .. gnj), and fills its own halo from it.
+struct FoldKind { int8_t sx, sy, sign, vector; };
+struct FoldArgs {
+  int32_t nf, w, gni, gnj, isd, ied, isc, iec, lx, pad;
+  int32_t xs[KID_MAX_DIV + 1];
+  double* f[16];
+  FoldKind kind[16];
+};
+__device__ __forceinline__ double fold_strip_at(const FoldArgs& a, const double* __restrict__ strip, int q, int r, int si) {
+  int px = 0;
+  while (px + 1 < a.lx && si >= a.xs[px + 1]) px++;
+  int nicp = a.xs[px + 1] - a.xs[px];
+  size_t base = (size_t)a.nf * (a.w + 1) * (size_t)(a.xs[px] - 1);
+  return strip[base + ((size_t)q * (a.w + 1) + r) * nicp + (si - a.xs[px])];
+}
+// my piece of the strip
+__global__ void k_fold_pack(const __grid_constant__ DevGrid g, const __grid_constant__ FoldArgs a, double* __restrict__ strip) {
+  int nic = a.iec - a.isc + 1;
+  long long n = (long long)a.nf * (a.w + 1) * nic;
+  size_t base = (size_t)a.nf * (a.w + 1) * (size_t)(a.isc - 1);
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+    int ii = (int)(k % nic);
+    long long t = k / nic;
+    int r = (int)(t % (a.w + 1)), q = (int)(t / (a.w + 1));
+    strip[base + k] = a.f[q][gidx(g, a.isc + ii, a.gnj - a.w + r)];
+  }
+}
+__global__ void k_fold_fill(const __grid_constant__ DevGrid g, const __grid_constant__ FoldArgs a, const double* __restrict__ strip) {
+  int nid = a.ied - a.isd + 1;
+  long long n = (long long)a.nf * (a.w + 1) * nid;
+  for (long long kk = (long long)blockIdx.x * blockDim.x + threadIdx.x; kk < n; kk += (long long)gridDim.x * blockDim.x) {
+    int ii = (int)(kk % nid);
+    long long t = kk / nid;
+    int k = (int)(t % (a.w + 1)), q = (int)(t / (a.w + 1));
+    const FoldKind fk = a.kind[q];
+    int i = a.isd + ii;
+    if (k == 0) {                               // the fold row itself
+      if (!(fk.vector && fk.sy == 1)) continue;
+      int iw = ((i - 1) % a.gni + a.gni) % a.gni + 1;
+      if (fk.sx == 1 && (iw == a.gni / 2 || iw == a.gni)) { a.f[q][gidx(g, i, a.gnj)] = 0.; continue; }
+      if (iw > a.gni / 2 && iw <= a.gni - fk.sx)
+        a.f[q][gidx(g, i, a.gnj)] = (double)fk.sign * fold_strip_at(a, strip, q, a.w, a.gni + 1 - fk.sx - iw);
+      continue;
+    }
+    int si = a.gni + 1 - fk.sx - i;
+    si = ((si - 1) % a.gni + a.gni) % a.gni + 1;
+    int sj = a.gnj + 1 - fk.sy - k;             // in gnj-w .. gnj
+    a.f[q][gidx(g, i, a.gnj + k)] = (double)fk.sign * fold_strip_at(a, strip, q, sj - (a.gnj - a.w), si);
   }
 }
 

@@ -89,7 +89,7 @@ struct DevGrid {
   int32_t cyclic_x, cyclic_y;
   int32_t pe_E_self, pe_W_self;     // cyclic x and this rank is its own E/W neighbour
   int32_t has_E, has_W, has_N, has_S;  // a neighbour rank exists in that direction
-  int32_t pad0, pad1;
+  int32_t fold_north, pad1;         // this tile touches a folded northern edge (KidDomain.fold_north and jec == gnj)
   // static (data domain)
   double *lon, *lat, *lonc, *latc, *dx, *dy, *area, *msk, *cosr, *sinr, *ocean_depth;
   // forcing (data domain)

@@ -72,6 +72,21 @@ __device__ __forceinline__ void warp_count_add(unsigned long long* ctr, bool pre
 __device__ __forceinline__ int route_berg(const DevGrid& g, const DevParams& p, double lon, double lat, int& i,
                                           int& j, double& xi, double& yj, unsigned int* err,
                                           unsigned long long* n_wrapped) {
+  if (j > g.jec && g.fold_north) {
+    // FOLD_NORTH_EDGE (F:3138-3147): the berg belongs to the cell on the other side of the fold, (gni+1-i, 2 gnj+1-j).
+    // On this rank: re-homed here as the receiver's unpack would (F:3629-3641); otherwise it leaves for the owner of
+    // that cell (owner_rank and k_pack_leavers fold the index)
+    int oi = g.gni + 1 - i, oj = 2 * g.gnj + 1 - j;
+    oi = ((oi - 1) % g.gni + g.gni) % g.gni + 1;
+    if (oi < g.isc || oi > g.iec || oj < g.jsc) return 1;
+    bool found = is_point_in_cell(g, p, lon, lat, oi, oj, err);
+    if (!found) found = find_cell_wide(g, p, lon, lat, &oi, &oj, err);
+    if (!found) { atomicOr(err, (unsigned)KID_DEVERR_LOST_BERG); return 2; }
+    i = oi; j = oj;
+    pos_within_cell(g, p, lon, lat, i, j, &xi, &yj, err);
+    atomicAdd(n_wrapped, 1ull);
+    return 0;
+  }
   if (i > g.iec || i < g.isc) {
     bool east = i > g.iec;
     bool self = east ? g.pe_E_self : g.pe_W_self;

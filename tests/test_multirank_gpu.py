@@ -25,7 +25,7 @@ class Ranks:
     def __init__(self, case, nranks, domain_of, run_ranks):
         self.case, self.nranks, self.run_ranks = case, nranks, run_ranks
         self.doms = [domain_of(r) for r in range(nranks)]
-        self.grids = [S.Grid(case.gni, case.gnj, d.isc, d.iec, d.jsc, d.jec) for d in self.doms]
+        self.grids = [type(case.grid)(case.gni, case.gnj, d.isc, d.iec, d.jsc, d.jec) for d in self.doms]
         parts = parallel.split_by_owner(case.bergs, self.doms)
         self.h = [None] * nranks
 
