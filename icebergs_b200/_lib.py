@@ -24,6 +24,7 @@ EXPORTS = [
     "kid_nccl_unique_id", "kid_nccl_init", "kid_nccl_destroy", "kid_pack_width",
     "kid_local_comm_create", "kid_local_comm_destroy", "kid_owner_rank", "kid_set_sort_phase", "kid_sorts_done", "kid_last_slow_count",
     "kid_unit_hexagon_into_quadrants", "kid_unit_point_in_triangle", "kid_record_posn", "kid_trajectory_count", "kid_get_trajectory",
+    "kid_set_calving_rmean", "kid_get_calving_rmean",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -53,6 +54,8 @@ def load() -> C.CDLL:
     lib.kid_get_bonds.argtypes = [_vp, C.POINTER(C.c_int64), C.POINTER(D.KidBondColumns)]
     lib.kid_set_calving_state.argtypes = [_vp, _vp, _vp, _vp]
     lib.kid_get_calving_state.argtypes = [_vp, _vp, _vp, _vp]
+    lib.kid_set_calving_rmean.argtypes = [_vp, _vp, _vp]
+    lib.kid_get_calving_rmean.argtypes = [_vp, _vp, _vp]
     lib.kid_run.argtypes = [_vp, C.c_int32, C.c_double] + [_vp] * 12 + [C.c_int32, C.c_int32] + [_vp] * 4
     lib.kid_set_forcing.argtypes = [_vp] + [_vp] * 12 + [C.c_int32, C.c_int32, _vp]
     lib.kid_prefetch_forcing.argtypes = [_vp] + [_vp] * 13

@@ -261,6 +261,18 @@ class Icebergs:
         self._check(lib().kid_get_calving_state(self.handle, _ptr(si), _ptr(sh), _ptr(ic)))
         return si, sh, ic
 
+    def set_calving_rmean(self, rmean_calving=None, rmean_calving_hflx=None):
+        """running means of get_running_mean_calving I:5999 (tau_calving > 0), data-domain arrays as calving.res.nc carries them"""
+        d = self.domain
+        a, b = _f64(rmean_calving, (d.njd, d.nid), "rmean_calving"), _f64(rmean_calving_hflx, (d.njd, d.nid), "rmean_calving_hflx")
+        self._check(lib().kid_set_calving_rmean(self.handle, _ptr(a), _ptr(b)))
+
+    def get_calving_rmean(self):
+        d = self.domain
+        a, b = np.zeros((d.njd, d.nid)), np.zeros((d.njd, d.nid))
+        self._check(lib().kid_get_calving_rmean(self.handle, _ptr(a), _ptr(b)))
+        return a, b
+
     def grid_field(self, field_id) -> np.ndarray:
         d = self.domain
         out = np.zeros((d.njd, d.nid))

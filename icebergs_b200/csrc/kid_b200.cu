@@ -108,6 +108,9 @@ struct kid_handle {
   long long launches = 0;
   int visited = 0, first_call_accum = 1, restarted = 0;
   int calving_active = 0;
+  double *rmean_calving = nullptr, *rmean_calving_hflx = nullptr;   // get_running_mean_calving I:5999 (tau_calving > 0)
+  int rmean_init[2] = {0, 0};
+  int calving_sticky = 0;           // tau_calving > 0: the mean keeps calving after the input has stopped
   int steps_since_sort = 0, sort_interval = 32, sorted_once = 0;
   MtsParams mp;                   // MTS scheme (evolve_icebergs_mts)
   MtsSums* dsums = nullptr;
@@ -629,7 +632,6 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   else if (pin->tidal_drift > 0.) unsupported = "tidal_drift>0 needs the FMS random number stream";
   else if (pin->add_iceberg_thickness_to_ssh && !pin->add_weight_to_ocean)
     unsupported = "add_iceberg_thickness_to_SSH reads spread_mass: it needs add_weight_to_ocean=.true. (the field is zero otherwise)";
-  else if (pin->tau_calving > 0.) unsupported = "tau_calving>0 (running mean of the calving field, I:5215) is not implemented";
   else if (pin->find_melt_using_spread_mass) unsupported = "find_melt_using_spread_mass is not implemented";
   else if (pin->dem && !(pin->mts && pin->iceberg_bonds_on)) unsupported = "dem=.true. needs mts=.true. and iceberg_bonds_on (F:1433)";
   else if (pin->dem && pin->break_bonds_on_sub_steps && !pin->fracture_criterion_stress) unsupported = "break_bonds_on_sub_steps needs fracture_criterion='stress' (I:1201)";
@@ -640,7 +642,6 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   else if (pin->iceberg_bonds_on && !pin->interactive_icebergs_on) unsupported = "iceberg_bonds_on needs interactive_icebergs_on";
   else if (pin->iceberg_bonds_on && (pin->max_bonds < 1 || pin->max_bonds > 12)) unsupported = "max_bonds must be 1..12";
   else if (pin->footloose && pin->displace_fl_bergs) unsupported = "displace_fl_bergs needs the FMS random number stream: set displace_fl_bergs=0";
-  else if (pin->time_average_weight && pin->add_weight_to_ocean) unsupported = "time_average_weight is not implemented";
   else if (dom->cyclic_y) unsupported = "cyclic y is not implemented";
   else if (pin->halo < 2) unsupported = "halo must be >= 2";
   else if (dom->fold_north && (!dom->cyclic_x || dom->gni % 2)) unsupported = "fold_north (FOLD_NORTH_EDGE) needs cyclic_x and an even number of columns";
@@ -925,7 +926,8 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   double** zf[] = {&g.uo, &g.vo, &g.ui, &g.vi, &g.ua, &g.va, &g.ssh, &g.sst, &g.sss, &g.cn, &g.hi, &g.calving,
                    &g.calving_hflx, &g.floating_melt, &g.berg_melt, &g.bergy_src, &g.bergy_melt, &g.fl_bits_melt,
                    &g.fl_bits_src, &g.melt_buoy, &g.melt_eros, &g.melt_conv, &g.melt_buoy_fl, &g.melt_eros_fl,
-                   &g.melt_conv_fl, &g.fl_parent_melt, &g.fl_child_melt, &g.stored_heat, &g.tmp, &h->tmp_u, &h->tmp_v};
+                   &g.melt_conv_fl, &g.fl_parent_melt, &g.fl_child_melt, &g.stored_heat, &g.tmp, &h->tmp_u, &h->tmp_v,
+                   &h->rmean_calving, &h->rmean_calving_hflx};
   for (auto z : zf) { *z = dev_field(h, n2, 0.); if (!*z) return fail(h, KID_ERR_CUDA, "kid_init: out of device memory (fields)"); }
   {
     SpreadFields& sf = h->sf;
@@ -1849,6 +1851,24 @@ extern "C" int32_t kid_get_calving_state(kid_t* h, double* stored_ice, double* s
   return KID_OK;
 }
 
+extern "C" int32_t kid_set_calving_rmean(kid_t* h, const double* rmean_calving, const double* rmean_calving_hflx) {
+  if (!h) return KID_ERR_ARG;
+  cudaSetDevice(h->d.device);
+  if (rmean_calving) { CK(cudaMemcpyAsync(h->rmean_calving, rmean_calving, sizeof(double) * h->n2, cudaMemcpyHostToDevice, h->stream)); h->rmean_init[0] = 1; }
+  if (rmean_calving_hflx) { CK(cudaMemcpyAsync(h->rmean_calving_hflx, rmean_calving_hflx, sizeof(double) * h->n2, cudaMemcpyHostToDevice, h->stream)); h->rmean_init[1] = 1; }
+  CK(cudaStreamSynchronize(h->stream));
+  if (rmean_calving && h->p.tau_calving > 0.) h->calving_sticky = h->calving_active = 1;
+  return KID_OK;
+}
+extern "C" int32_t kid_get_calving_rmean(kid_t* h, double* rmean_calving, double* rmean_calving_hflx) {
+  if (!h) return KID_ERR_ARG;
+  cudaSetDevice(h->d.device);
+  CK(cudaStreamSynchronize(h->stream));
+  if (rmean_calving) CK(cudaMemcpy(rmean_calving, h->rmean_calving, sizeof(double) * h->n2, cudaMemcpyDeviceToHost));
+  if (rmean_calving_hflx) CK(cudaMemcpy(rmean_calving_hflx, h->rmean_calving_hflx, sizeof(double) * h->n2, cudaMemcpyDeviceToHost));
+  return KID_OK;
+}
+
 // ------------------------------------------------------------- forcing
 static void zero_flux_fields(kid_t* h, bool also_calving) {
   DevGrid& g = h->g;
@@ -1933,6 +1953,13 @@ static int ingest_forcing(kid_t* h, const double* calving, const double* uo, con
   CK(cudaMemsetAsync(h->dflags, 0, 2 * sizeof(unsigned long long), h->stream));
   LAUNCH(h, k_copy_in, (long long)nc, 256, g, calving_hflx ? st[9] : nullptr, g.calving_hflx, 0, 1, 0.);
   LAUNCH(h, k_copy_in, (long long)nc, 256, g, calving ? st[0] : nullptr, g.calving, 0, 1, 0.);
+  if (h->p.tau_calving > 0.) {            // I:5215-5219
+    double tau = h->p.tau_calving / (365. * 24 * 60 * 60);        // as written at I:6020
+    double alpha = tau / (tau + h->p.dt), beta;
+    if (alpha > 0.5) { beta = h->p.dt / (tau + h->p.dt); alpha = 1. - beta; } else beta = 1. - alpha;
+    LAUNCH(h, k_rmean_calving, n2, 256, g, h->rmean_calving, h->rmean_calving_hflx, h->rmean_init[0], h->rmean_init[1], alpha, beta, n2);
+    h->rmean_init[0] = h->rmean_init[1] = 1;
+  }
   LAUNCH(h, k_calving_units, n2, 256, g, n2);
   if (stagger == KID_BGRID_NE) {
     LAUNCH(h, k_copy_in, (long long)nr, 256, g, st[1], g.uo, 1, 0, 0.);
@@ -2508,7 +2535,7 @@ extern "C" int32_t kid_set_forcing(kid_t* h, const double* calving, const double
   int rc = ingest_forcing(h, calving, uo, vo, ui, vi, tauxa, tauya, ssh, sst, calving_hflx, cn, hi, stagger, stress_stagger, sss);
   if (rc) return rc;
   CK(cudaStreamSynchronize(h->stream));
-  if (h->hflags[1]) h->calving_active = 1;
+  if (h->hflags[1]) { h->calving_active = 1; if (h->p.tau_calving > 0.) h->calving_sticky = 1; }
   return KID_OK;
 }
 
@@ -2526,7 +2553,8 @@ extern "C" int32_t kid_run(kid_t* h, int32_t year, double yearday, double* calvi
   int rc = ingest_forcing(h, calving, uo, vo, ui, vi, tauxa, tauya, ssh, sst, calving_hflx, cn, hi, stagger, stress_stagger, sss);
   if (rc) return rc;
   CK(cudaStreamSynchronize(h->stream));      // hflags: is any calving coming in?
-  if (h->hflags[1]) h->calving_active = 1;
+  if (h->hflags[1]) { h->calving_active = 1; if (h->p.tau_calving > 0.) h->calving_sticky = 1; }
+  if (h->calving_sticky) h->calving_active = 1;
   rc = step_core(h);
   if (rc) return rc;
   size_t nc = (size_t)h->nic * h->njc;
@@ -2549,7 +2577,7 @@ extern "C" int32_t kid_run(kid_t* h, int32_t year, double yearday, double* calvi
   float ms = 0;
   if (cudaEventElapsedTime(&ms, h->ev[T_NPHASE], h->ev[T_NPHASE + 1]) == cudaSuccess) h->timing[6] = ms;
   // a step that brought no calving and calved nothing leaves the calving state inert
-  if (!h->hflags[1] && h->dirty_appended == 0) h->calving_active = 0;
+  if (!h->hflags[1] && h->dirty_appended == 0 && !h->calving_sticky) h->calving_active = 0;
   return rc;
 }
 
@@ -2581,7 +2609,7 @@ extern "C" int32_t kid_step_resident(kid_t* h, int32_t nsteps, int32_t year, dou
               h->n_recv_last, h->n_sent_last, ef);
       if (ef) return check_device_errors(h);
     }
-    if (h->calving_active && h->n_slots == before) h->calving_active = 0;   // no input, nothing left to calve
+    if (h->calving_active && h->n_slots == before && !h->calving_sticky) h->calving_active = 0;   // no input, nothing left to calve
   }
   CK(cudaEventRecord(h->ev[T_NPHASE + 1], h->stream));
   int rc = check_device_errors(h);
@@ -2728,6 +2756,7 @@ static const double* field_ptr(kid_t* h, int id) {
     case KID_FLD_SPREAD_MASS: return h->sf.spread_mass; case KID_FLD_SPREAD_AREA: return h->sf.spread_area;
     case KID_FLD_USTAR_ICEBERG: return h->sf.ustar_iceberg; case KID_FLD_SPREAD_UVEL: return h->sf.spread_uvel;
     case KID_FLD_SPREAD_VVEL: return h->sf.spread_vvel;
+    case KID_FLD_RMEAN_CALVING: return h->rmean_calving; case KID_FLD_RMEAN_CALVING_HFLX: return h->rmean_calving_hflx;
     default: return nullptr;
   }
 }

@@ -949,6 +949,20 @@ __global__ void k_ssh_from_spread_mass(const __grid_constant__ DevGrid g, const 
 }
 
 // I:5221, I:5227: whole data domain
+// get_running_mean_calving I:5999-6038 on the whole data-domain arrays: the means start from the first field they see
+// (I:6010-6017), then rmean = beta*field + alpha*rmean and the model goes on with the mean (I:6035-6036)
+__global__ void k_rmean_calving(const __grid_constant__ DevGrid g, double* __restrict__ rm, double* __restrict__ rmh,
+                                int init_c, int init_h, double alpha, double beta, long long n2) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n2) return;
+  double c = g.calving[k], hf = g.calving_hflx[k];
+  double a = init_c ? rm[k] : c, b = init_h ? rmh[k] : hf;
+  if (alpha != 0.) {
+    a = beta * c + alpha * a; b = beta * hf + alpha * b;
+    g.calving[k] = a; g.calving_hflx[k] = b;
+  }
+  rm[k] = a; rmh[k] = b;
+}
 __global__ void k_calving_units(const __grid_constant__ DevGrid g, long long n2) {
   long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n2) return;

@@ -164,19 +164,25 @@ def _calving_window(domain, nj, ni):
                      f"compute domain {d.njc} x {d.nic} of this rank")
 
 
-def write_restart_calving(path, stored_ice, stored_heat, iceberg_counter_grd, domain=None, global_file=False):
+def write_restart_calving(path, stored_ice, stored_heat, iceberg_counter_grd, domain=None, global_file=False,
+                          rmean_calving=None, rmean_calving_hflx=None):
     """calving.res.nc (fmsio:564-566: register_restart_field of stored_ice, stored_heat, iceberg_counter_grd on the
     FMS domain).  FMS writes the COMPUTE domain (halos stripped) with a Time record axis: (Time, zaxis_1, yaxis_1,
     xaxis_1).  ``stored_ice`` etc. are the library's data-domain arrays (``Icebergs.get_calving_state``); with
     ``domain`` the halos are stripped, and with ``global_file`` the compute domain is placed in a global-size array
     (what a single-PE or mpp_io-combined file looks like; the other ranks' points are left zero).  Without ``domain``
-    the arrays are written as they are (already halo-free)."""
+    the arrays are written as they are (already halo-free).  ``rmean_calving`` / ``rmean_calving_hflx``
+    (``Icebergs.get_calving_rmean``, tau_calving > 0) are written as the reference does (fmsio:568-569)."""
     si, sh, ic = np.asarray(stored_ice), np.asarray(stored_heat), np.asarray(iceberg_counter_grd)
+    extra = {k: np.asarray(v) for k, v in (("rmean_calving", rmean_calving), ("rmean_calving_hflx", rmean_calving_hflx)) if v is not None}
     if domain is not None:
         d = domain
         h = d.halo
         si, sh, ic = si[:, h:h + d.njc, h:h + d.nic], sh[h:h + d.njc, h:h + d.nic], ic[h:h + d.njc, h:h + d.nic]
+        extra = {k: v[h:h + d.njc, h:h + d.nic] for k, v in extra.items()}
         if global_file:
+            for k in list(extra):
+                gv = np.zeros((d.gnj, d.gni)); gv[d.jsc - 1:d.jec, d.isc - 1:d.iec] = extra[k]; extra[k] = gv
             gsi = np.zeros((si.shape[0], d.gnj, d.gni)); gsh = np.zeros((d.gnj, d.gni)); gic = np.zeros((d.gnj, d.gni), dtype=np.int32)
             js, is_ = slice(d.jsc - 1, d.jec), slice(d.isc - 1, d.iec)
             gsi[:, js, is_], gsh[js, is_], gic[js, is_] = si, sh, ic
@@ -191,7 +197,31 @@ def write_restart_calving(path, stored_ice, stored_heat, iceberg_counter_grd, do
     v = f.createVariable("stored_ice", "d", ("Time", "zaxis_1", "yaxis_1", "xaxis_1")); v[0] = si
     v = f.createVariable("stored_heat", "d", ("Time", "yaxis_1", "xaxis_1")); v[0] = sh
     v = f.createVariable("iceberg_counter_grd", "i", ("Time", "yaxis_1", "xaxis_1")); v[0] = ic
+    for k, a in extra.items():
+        v = f.createVariable(k, "d", ("Time", "yaxis_1", "xaxis_1")); v[0] = a
     f.close()
+
+
+def read_restart_calving_rmean(path, domain=None):
+    """-> (rmean_calving, rmean_calving_hflx) for ``Icebergs.set_calving_rmean``; None for a variable the file does not
+    hold (the reference then starts the mean from the first field it sees, fms2io:1517-1534, I:6010-6017)."""
+    f = netcdf_file(path, "r", mmap=False)
+    out = []
+    for name in ("rmean_calving", "rmean_calving_hflx"):
+        if name not in f.variables:
+            out.append(None)
+            continue
+        a = np.array(f.variables[name][:], dtype=np.float64)
+        if a.ndim == 3:
+            a = a[-1]
+        if domain is not None:
+            d = domain
+            js, is_ = _calving_window(d, a.shape[0], a.shape[1])
+            o = np.zeros((d.njd, d.nid)); o[d.halo:d.halo + d.njc, d.halo:d.halo + d.nic] = a[js, is_]
+            a = o
+        out.append(a)
+    f.close()
+    return tuple(out)
 
 
 def read_restart_calving(path, domain=None):

@@ -77,6 +77,7 @@ enum {
   KID_FLD_AREA, KID_FLD_MSK, KID_FLD_COS, KID_FLD_SIN, KID_FLD_OCEAN_DEPTH,
   KID_FLD_STORED_HEAT, KID_FLD_MASS, KID_FLD_BERGY_MASS, KID_FLD_SPREAD_MASS,
   KID_FLD_SPREAD_AREA, KID_FLD_USTAR_ICEBERG, KID_FLD_SPREAD_UVEL, KID_FLD_SPREAD_VVEL,
+  KID_FLD_RMEAN_CALVING, KID_FLD_RMEAN_CALVING_HFLX,
   KID_FLD_COUNT_
 };
 
@@ -209,7 +210,9 @@ typedef struct KidParams {
   double cdrag_icebergs;                       /* F:716 (1.5e-3) */
   /* mass / area / momentum spread onto the ocean grid, I:3895-4100, I:4970-5011, I:6077-6150 */
   int32_t add_weight_to_ocean;                 /* F:721 (T) */
-  int32_t time_average_weight;                 /* F:723 (F); T is not implemented */
+  int32_t time_average_weight;                 /* F:723 (F).  T: the weight is spread inside the stepping stages (I:7264, I:7395..) and
+                                                  calculate_mass_on_ocean I:4984-4997 zeroes it again before anything reads it: the
+                                                  spread fields of such a run are zero, here as in the reference */
   int32_t use_old_spreading;                   /* F:778 (T) */
   int32_t rotate_icebergs_for_mass_spreading;  /* F:750 (T) */
   int32_t pass_fields_to_ocean_model;          /* F:739 (F): also fill spread_area / spread_uvel / spread_vvel / ustar */
@@ -217,8 +220,8 @@ typedef struct KidParams {
   double grounding_fraction;                   /* F:730 (0.) */
   double clipping_depth;                       /* F:227 (0.) */
   double initial_orientation;                  /* F:713 (0.) degrees */
-  /* namelist entries that reach icebergs_run but are not implemented: refused by kid_init when set */
-  double tau_calving;                          /* F:728 (0.): running-mean smoothing of the calving field I:5215, I:6020; must be 0 */
+  double tau_calving;                          /* F:728 (0.) years: running mean of calving / calving_hflx, get_running_mean_calving I:5999-6038 */
+  /* namelist entry that reaches icebergs_run but is not implemented: refused by kid_init when set */
   int32_t find_melt_using_spread_mass;         /* F:741 (F): melt from the spread mass before/after I:5490-5495; must be 0 */
   /* trajectory sampling, record_posn F:5328-5498 (WHEN to sample is the caller's decision, I:5173-5178: kid_record_posn) */
   int32_t save_short_traj;                     /* F:759 (T): the file holds lon, lat, year, day, id only */
@@ -373,6 +376,12 @@ int32_t kid_set_calving_state(kid_t* h, const double* stored_ice, const double* 
                               const int32_t* iceberg_counter_grd);
 int32_t kid_get_calving_state(kid_t* h, double* stored_ice, double* stored_heat,
                               int32_t* iceberg_counter_grd);
+
+/* rmean_calving, rmean_calving_hflx (isd:ied,jsd:jed): the running means of get_running_mean_calving I:5999-6038
+ * (tau_calving > 0) as calving.res.nc carries them (fmsio:568-569, read fms2io:1517-1534).  NULL = left alone.  A mean that
+ * was set counts as initialised; otherwise the first kid_run starts it from that call's field (I:6010-6017). */
+int32_t kid_set_calving_rmean(kid_t* h, const double* rmean_calving, const double* rmean_calving_hflx);
+int32_t kid_get_calving_rmean(kid_t* h, double* rmean_calving, double* rmean_calving_hflx);
 
 /*
  * icebergs_run  I:5074-5096.

@@ -89,6 +89,11 @@ module ice_bergs
       type(c_ptr), value :: h, stored_ice, stored_heat, counter
       integer(c_int32_t) :: rc
     end function
+    function kid_set_calving_rmean(h, rmean_calving, rmean_calving_hflx) bind(C, name='kid_set_calving_rmean') result(rc)
+      import :: c_ptr, c_int32_t
+      type(c_ptr), value :: h, rmean_calving, rmean_calving_hflx      ! c_null_ptr: the variable is not in calving.res.nc (IO:1517-1534)
+      integer(c_int32_t) :: rc
+    end function
     function kid_get_grid_field(h, field_id, out) bind(C, name='kid_get_grid_field') result(rc)
       import :: c_ptr, c_int32_t, c_double
       type(c_ptr), value :: h

@@ -104,6 +104,8 @@ struct Oracle {
   double current_yearday;
   int visited;             /* "Visited" save variable, I:5110 */
   int first_call_accum;    /* first_call in accumulate_calving I:6161 */
+  double *rmean_calving, *rmean_calving_hflx;      /* get_running_mean_calving I:5999 */
+  int rmean_calving_initialized, rmean_calving_hflx_initialized;
   int restarted;
   KidCounters cnt;
   double dem_K_damp;
@@ -1174,7 +1176,8 @@ static void update_verlet_position(Oracle* o, OBerg* berg) {
 }
 
 /* ------------------------------------------- Runge_Kutta_stepping I:7331 */
-/* (time_average_weight spreading inside the stages, I:7379/I:7414/..., is refused at create) */
+/* (time_average_weight: the stages spread the weight into mass_on_ocean, I:7395/I:7433/I:7490/I:7620 and I:7264 under
+ * Verlet, and calculate_mass_on_ocean I:4984 zeroes the array again before anything reads it -- nothing to restate) */
 static void Runge_Kutta_stepping(Oracle* o, OBerg* berg, double* axn, double* ayn, double* bxn, double* byn,
                                  double* uveln, double* vveln, double* lonn, double* latn, int* io, int* jo,
                                  double* xio, double* yjo) {
@@ -2278,7 +2281,7 @@ Oracle* oracle_create(const KidParams* p, const KidDomain* dom, int32_t year, do
   o->real_calving = dalloc(n2 * KID_NCLASSES, 0.);
   o->mass_on_ocean = dalloc(n2 * 9, 0.); o->area_on_ocean = dalloc(n2 * 9, 0.);
   o->uvel_on_ocean = dalloc(n2 * 9, 0.); o->vvel_on_ocean = dalloc(n2 * 9, 0.);
-  if (p->time_average_weight) o_fatal(o, "oracle: time_average_weight is not restated");
+  o->rmean_calving = dalloc(n2, 0.); o->rmean_calving_hflx = dalloc(n2, 0.);
   o->iceberg_counter_grd = (int32_t*)calloc(n2, sizeof(int32_t));
   o->list = (OBerg**)calloc(n2, sizeof(OBerg*));
   if (p->tidal_drift > 0.) o_fatal(o, "oracle: tidal_drift needs the FMS random number stream (external)");
@@ -2410,7 +2413,7 @@ void oracle_destroy(Oracle* o) {
                  o->melt_eros_fl, o->melt_conv_fl, o->fl_parent_melt, o->fl_child_melt, o->stored_heat,
                  o->stored_ice, o->real_calving, o->tmp, o->mass, o->spread_mass, o->spread_area,
                  o->ustar_iceberg, o->spread_uvel, o->spread_vvel, o->mass_on_ocean, o->area_on_ocean,
-                 o->uvel_on_ocean, o->vvel_on_ocean};
+                 o->uvel_on_ocean, o->vvel_on_ocean, o->rmean_calving, o->rmean_calving_hflx};
   for (size_t k = 0; k < sizeof(z) / sizeof(z[0]); k++) free(z[k]);
   free(o->iceberg_counter_grd); free(o->list); free(o);
 }
@@ -2515,6 +2518,12 @@ int32_t oracle_set_calving_state(Oracle* o, const double* stored_ice, const doub
   o->restarted = 1;
   return KID_OK;
 }
+int32_t oracle_set_calving_rmean(Oracle* o, const double* rmean_calving, const double* rmean_calving_hflx) {
+  size_t n2 = (size_t)o->nid * o->njd;
+  if (rmean_calving) { memcpy(o->rmean_calving, rmean_calving, sizeof(double) * n2); o->rmean_calving_initialized = 1; }
+  if (rmean_calving_hflx) { memcpy(o->rmean_calving_hflx, rmean_calving_hflx, sizeof(double) * n2); o->rmean_calving_hflx_initialized = 1; }
+  return KID_OK;
+}
 int32_t oracle_get_calving_state(const Oracle* o, double* stored_ice, double* stored_heat, int32_t* counter) {
   size_t n2 = (size_t)o->nid * o->njd;
   if (stored_ice) memcpy(stored_ice, o->stored_ice, sizeof(double) * n2 * KID_NCLASSES);
@@ -2555,7 +2564,20 @@ static void ingest_forcing(Oracle* o, const double* calving, const double* uo, c
     G(o, calving_hflx, i, j) = C2(calving_hflx, i, j) * G(o, msk, i, j);
     G(o, calving, i, j) = C2(calving, i, j) * G(o, msk, i, j);
   }
-  /* tau_calving>0 (running mean) is host-side bookkeeping: not restated */
+  if (o->p.tau_calving > 0.) {                          /* get_running_mean_calving I:5999-6038, whole arrays */
+    if (!o->rmean_calving_initialized) { memcpy(o->rmean_calving, o->calving, sizeof(double) * n2); o->rmean_calving_initialized = 1; }
+    if (!o->rmean_calving_hflx_initialized) { memcpy(o->rmean_calving_hflx, o->calving_hflx, sizeof(double) * n2); o->rmean_calving_hflx_initialized = 1; }
+    double tau = o->p.tau_calving / (365. * 24 * 60 * 60);      /* "Converting time scale from years to seconds", as written */
+    double alpha = tau / (tau + o->p.dt), beta;
+    if (alpha != 0.) {
+      if (alpha > 0.5) { beta = o->p.dt / (tau + o->p.dt); alpha = 1. - beta; } else beta = 1. - alpha;
+      for (size_t k = 0; k < n2; k++) {
+        o->rmean_calving[k] = beta * o->calving[k] + alpha * o->rmean_calving[k];
+        o->rmean_calving_hflx[k] = beta * o->calving_hflx[k] + alpha * o->rmean_calving_hflx[k];
+        o->calving[k] = o->rmean_calving[k]; o->calving_hflx[k] = o->rmean_calving_hflx[k];
+      }
+    }
+  }
   for (size_t k = 0; k < n2; k++) {
     o->calving[k] = o->calving[k] * o->msk[k] * o->area[k];
     o->calving_hflx[k] = o->calving_hflx[k] * o->msk[k];
@@ -2770,6 +2792,7 @@ static const double* field_ptr(const Oracle* o, int id) {
     case KID_FLD_BERGY_MASS: return o->bergy_mass; case KID_FLD_SPREAD_MASS: return o->spread_mass;
     case KID_FLD_SPREAD_AREA: return o->spread_area; case KID_FLD_USTAR_ICEBERG: return o->ustar_iceberg;
     case KID_FLD_SPREAD_UVEL: return o->spread_uvel; case KID_FLD_SPREAD_VVEL: return o->spread_vvel;
+    case KID_FLD_RMEAN_CALVING: return o->rmean_calving; case KID_FLD_RMEAN_CALVING_HFLX: return o->rmean_calving_hflx;
     default: return NULL;
   }
 }

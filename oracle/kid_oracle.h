@@ -53,6 +53,7 @@ int32_t oracle_set_bonds(Oracle* o, int64_t nb, const KidBondColumns* c);
 int32_t oracle_get_bonds(const Oracle* o, int64_t* nb, KidBondColumns* c);
 int32_t oracle_set_calving_state(Oracle* o, const double* stored_ice, const double* stored_heat,
                                  const int32_t* counter);
+int32_t oracle_set_calving_rmean(Oracle* o, const double* rmean_calving, const double* rmean_calving_hflx);
 int32_t oracle_get_calving_state(const Oracle* o, double* stored_ice, double* stored_heat,
                                  int32_t* counter);
 

@@ -121,6 +121,7 @@ def lib():
         L.oracle_get_bonds.argtypes = [_vp, C.POINTER(C.c_int64), _vp]
         L.oracle_set_calving_state.argtypes = [_vp, _vp, _vp, _vp]
         L.oracle_get_calving_state.argtypes = [_vp, _vp, _vp, _vp]
+        L.oracle_set_calving_rmean.argtypes = [_vp, _vp, _vp]
         L.oracle_run.argtypes = [_vp, C.c_int32, C.c_double] + [_vp] * 12 + [C.c_int32, C.c_int32] + [_vp] * 4
         L.oracle_step_again.argtypes = [_vp, C.c_int32, C.c_int32, C.c_double, C.c_int32]
         L.oracle_get_grid_field.argtypes = [_vp, C.c_int32, _vp]
@@ -260,6 +261,10 @@ class Oracle:
         si, sh = _f64(stored_ice), _f64(stored_heat)
         ic = None if iceberg_counter_grd is None else np.ascontiguousarray(iceberg_counter_grd, dtype=np.int32)
         self._ok(lib().oracle_set_calving_state(self._h, _ptr(si), _ptr(sh), _ptr(ic)))
+
+    def set_calving_rmean(self, rmean_calving=None, rmean_calving_hflx=None):
+        a, b = _f64(rmean_calving), _f64(rmean_calving_hflx)
+        self._ok(lib().oracle_set_calving_rmean(self._h, _ptr(a), _ptr(b)))
 
     def get_calving_state(self):
         d = self.domain

@@ -262,3 +262,69 @@ def test_polar_tangent_plane(rk):
         above = max(above, int(np.sum(o.get_bergs(["lat"])["lat"] > 89.0)))
     assert above > 50, f"only {above} bergs above 89N: the tangent plane was not exercised"
     api.icebergs_end(b)
+
+
+def test_running_mean_of_calving_matches_oracle_and_the_closed_form():
+    """tau_calving > 0: get_running_mean_calving I:5999-6038.  The mean starts from the first field (I:6010-6017), relaxes
+    with alpha = tau / (tau + dt) (tau in the units the source writes, I:6020), keeps calving after the input has stopped,
+    and travels through calving.res.nc (fmsio:568-569)."""
+    # I:6020 DIVIDES the namelist value by the seconds of a year; restated as written, so tau_calving = 3600 * 31 536 000
+    # gives tau = 3600 and alpha = 0.5 at dt = 3600 s
+    case = Case(96, 48, 300, capacity=400000, tau_calving=3600.0 * 365. * 86400.)
+    f = case.forcing
+    rng = np.random.default_rng(11)
+    lat = case.init["ice_lat"]
+    coast = (np.abs(lat) > 65) & (np.abs(lat) < 79) & (case.grid.wet(0) > 0)
+    calving = np.zeros_like(f["calving"])
+    calving[coast] = rng.uniform(1e-4, 2e-2, size=int(coast.sum()))
+    hflx = calving * -3.0e4
+    b, o = both(case)
+    p = case.params()
+    tau = p.tau_calving / (365. * 24 * 60 * 60)
+    alpha = tau / (tau + case.dt)
+    assert 0.05 < alpha < 0.95, alpha
+    h = case.halo
+    inner = (slice(h, -h), slice(h, -h))
+    mean = None
+    for step in range(6):
+        cin = calving if step < 3 else 0.0 * calving          # the input stops: the mean decays, bergs keep calving
+        hin = hflx if step < 3 else 0.0 * hflx
+        run_gpu(b, case, time=(1, 10.0 + step), calving=cin, calving_hflx=hin)
+        run_oracle(o, case, time=(1, 10.0 + step), calving=cin, calving_hflx=hin)
+        assert b.count_bergs() == o.count_bergs(), f"count after step {step}"
+        compare_state(b, o, f"tau_calving step {step}", rtol=1e-9)
+        rg, ro = b.grid_field(D.KID_FLD_RMEAN_CALVING)[inner], o.grid_field(D.KID_FLD_RMEAN_CALVING)[inner]
+        assert np.array_equal(rg, ro)
+        assert np.array_equal(b.grid_field(D.KID_FLD_RMEAN_CALVING_HFLX)[inner], o.grid_field(D.KID_FLD_RMEAN_CALVING_HFLX)[inner])
+        wet = case.grid.wet(0)
+        mean = cin * wet if mean is None else (1.0 - alpha) * (cin * wet) + alpha * mean
+        assert np.max(np.abs(rg - mean)) <= 1e-12 * np.max(np.abs(mean))
+    assert b.counters()["nbergs_calved"] == o.counters()["nbergs_calved"] > 100
+    n3 = b.counters()["nbergs_calved"]
+    # restart: a second pair picks the means up and goes on identically
+    rm, rmh = b.get_calving_rmean()
+    si, sh, ic = b.get_calving_state()
+    b2, o2 = both(case)
+    for x in (b2, o2):
+        x.set_calving_state(stored_ice=si, stored_heat=sh, iceberg_counter_grd=ic)
+        x.set_calving_rmean(rm, rmh)
+    run_gpu(b2, case, time=(1, 16.0), calving=0.0 * calving, calving_hflx=0.0 * hflx)
+    run_gpu(b, case, time=(1, 16.0), calving=0.0 * calving, calving_hflx=0.0 * hflx)
+    run_oracle(o2, case, time=(1, 16.0), calving=0.0 * calving, calving_hflx=0.0 * hflx)
+    assert np.array_equal(b2.grid_field(D.KID_FLD_RMEAN_CALVING)[inner], b.grid_field(D.KID_FLD_RMEAN_CALVING)[inner])
+    assert np.array_equal(b2.grid_field(D.KID_FLD_RMEAN_CALVING)[inner], o2.grid_field(D.KID_FLD_RMEAN_CALVING)[inner])
+    assert b.counters()["nbergs_calved"] >= n3
+    api.icebergs_end(b); api.icebergs_end(b2)
+
+
+def test_time_average_weight_leaves_the_spread_fields_empty_like_the_reference():
+    """time_average_weight=T: the weight is spread inside the stepping stages (I:7264, I:7395...) and
+    calculate_mass_on_ocean I:4984 zeroes it before sum_up_spread_fields reads it"""
+    case = Case(96, 48, 3000, add_weight_to_ocean=1, time_average_weight=1, pass_fields_to_ocean_model=0)
+    b, o = both(case)
+    for step in range(2):
+        run_gpu(b, case); run_oracle(o, case)
+        compare_state(b, o, f"time_average_weight step {step}", rtol=1e-10)
+        for fid in (D.KID_FLD_SPREAD_MASS, D.KID_FLD_SPREAD_AREA):
+            assert np.array_equal(b.grid_field(fid), o.grid_field(fid)) and not b.grid_field(fid).any()
+    api.icebergs_end(b)

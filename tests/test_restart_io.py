@@ -62,6 +62,12 @@ def test_bond_and_calving_round_trip(tmp_path):
     R.write_restart_calving(q, si, sh, ic)
     a, b_, c = R.read_restart_calving(q)
     assert np.array_equal(a, si) and np.array_equal(b_, sh) and np.array_equal(c, ic)
+    assert R.read_restart_calving_rmean(q) == (None, None)                 # a file without the running means (tau_calving = 0)
+    rm, rmh = np.random.rand(6, 8), -np.random.rand(6, 8)
+    R.write_restart_calving(q, si, sh, ic, rmean_calving=rm, rmean_calving_hflx=rmh)     # fmsio:568-569
+    a, b_ = R.read_restart_calving_rmean(q)
+    assert np.array_equal(a, rm) and np.array_equal(b_, rmh)
+    assert np.array_equal(R.read_restart_calving(q)[1], sh)
 
 
 def test_calving_restart_in_the_fms_layout(tmp_path):
