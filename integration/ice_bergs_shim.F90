@@ -226,6 +226,7 @@ contains
     bergs%dom%gni = gni ; bergs%dom%gnj = gnj
     bergs%dom%cyclic_x = merge(1, 0, iand(dom_x_flags, CYCLIC_GLOBAL_DOMAIN) /= 0)
     bergs%dom%cyclic_y = merge(1, 0, iand(dom_y_flags, CYCLIC_GLOBAL_DOMAIN) /= 0)
+    bergs%dom%fold_north = merge(1, 0, dom_y_flags == FOLD_NORTH_EDGE)      ! the tripolar grid, F:933
     bergs%dom%rank = mpp_pe() - mpp_root_pe() ; bergs%dom%nranks = mpp_npes()
     bergs%dom%layout_x = layout(1) ; bergs%dom%layout_y = layout(2)
     bergs%dom%device = local_device_ordinal()  ! e.g. rank modulo GPUs per node
@@ -367,6 +368,9 @@ contains
     stored_ice = 0. ; stored_heat = 0. ; counter = 0
     call read_restart_calving_fields(bergs%domain, stored_ice, stored_heat, counter)        ! IO:1432-1530, unchanged
     call check(bergs%h, kid_set_calving_state(bergs%h, stored_ice, stored_heat, counter), 'KID, read_restart_calving')
+    ! rmean_calving / rmean_calving_hflx (IO:1517-1534): handed over only when the file holds them (a mean that is not
+    ! set starts from the first calving field icebergs_run sees, I:6010-6017)
+    if (bergs%p%tau_calving > 0.) call read_restart_calving_rmean_into_library(bergs)
     ! icebergs.res.nc: one allocatable array per variable (IO:606-760 reads them exactly like this), handed over by address
     call read_restart_berg_columns(bergs%domain, nb, c)                                        ! IO:606-975 without the list insertion
     call check(bergs%h, kid_set_bergs(bergs%h, nb, c), 'KID, read_restart_bergs')
@@ -375,6 +379,22 @@ contains
       call check(bergs%h, kid_set_bonds(bergs%h, nbonds, cb), 'KID, read_restart_bonds')       ! (initialize_iceberg_bonds I:356 when empty)
     endif
   end subroutine read_restart_into_library
+
+  !> rmean_calving, rmean_calving_hflx of calving.res.nc (IO:568-569 written, fms2io:1517-1534 read) -> kid_set_calving_rmean
+  subroutine read_restart_calving_rmean_into_library(bergs)
+    type(icebergs), pointer :: bergs
+    real, allocatable, target :: rmean(:,:), rmean_hflx(:,:)
+    logical :: has_rmean, has_rmean_hflx
+    type(c_ptr) :: pa, pb
+    allocate(rmean(bergs%dom%isd:bergs%dom%ied, bergs%dom%jsd:bergs%dom%jed), &
+             rmean_hflx(bergs%dom%isd:bergs%dom%ied, bergs%dom%jsd:bergs%dom%jed))
+    rmean = 0. ; rmean_hflx = 0.
+    call read_restart_calving_rmean_fields(bergs%domain, rmean, has_rmean, rmean_hflx, has_rmean_hflx)   ! variable_exists + read_data
+    pa = c_null_ptr ; pb = c_null_ptr
+    if (has_rmean) pa = c_loc(rmean)
+    if (has_rmean_hflx) pb = c_loc(rmean_hflx)
+    call check(bergs%h, kid_set_calving_rmean(bergs%h, pa, pb), 'KID, read_restart_calving')
+  end subroutine read_restart_calving_rmean_into_library
 
   !> I:8136: write_restart_bergs / write_restart_bonds / write_restart_calving (IO:261-566) from the library's columns
   subroutine icebergs_save_restart(bergs, time_stamp)
@@ -402,6 +422,7 @@ contains
              counter(bergs%dom%isd:bergs%dom%ied, bergs%dom%jsd:bergs%dom%jed))
     call check(bergs%h, kid_get_calving_state(bergs%h, stored_ice, stored_heat, counter), 'KID, icebergs_save_restart')
     call write_restart_calving_fields(bergs%domain, stored_ice, stored_heat, counter, time_stamp)   ! IO:564-566
+    ! (with tau_calving > 0 the same file also carries kid_get_calving_rmean's two arrays, IO:568-569)
   end subroutine icebergs_save_restart
 
   ! read_restart_calving_fields / read_restart_berg_columns / read_restart_bond_columns and their write_* counterparts,
