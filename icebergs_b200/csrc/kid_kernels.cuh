@@ -177,6 +177,16 @@ __device__ __forceinline__ void scatter_fluxes(const DevGrid& g, const Scatter& 
 // thermodynamics of the berg in slot s located at (i,j,xi,yj) moving with (uvel,vvel);
 // loads and stores only the columns thermodynamics touches.  Fills sc; returns the
 // TH_* outcome.
+// Berg columns are streamed: read once and written once per step (3 GB per launch at 10 M bergs), while the grid records
+// the bergs gather (~0.2 GB) are what should stay in the 126 MB L2 from one step to the next.  With KID_STREAM_COLS the
+// column traffic of the fast step kernel is marked evict-first (ld/st.global.cs).
+#ifdef KID_STREAM_COLS
+#define KLD(ptr) __ldcs(ptr)
+#define KST(ptr, v) __stcs((ptr), (v))
+#else
+#define KLD(ptr) (*(ptr))
+#define KST(ptr, v) (*(ptr) = (v))
+#endif
 template <bool FOOTLOOSE, bool LEAN = false>
 __device__ __forceinline__ int thermo_slot(const DevGrid& g, const DevBergs& b, const DevParams& p, long long s,
                                            uint8_t flags, int i, int j, double xi, double yj, double uvel,
@@ -215,11 +225,11 @@ __device__ __forceinline__ int thermo_slot(const DevGrid& g, const DevBergs& b, 
   }
   int outcome = thermo_berg<LEAN>(p, e, uvel, vvel, N_bonds, st, sc.fx, sh);
   sc.key = (long long)cidx;
-  b.f64[C_MASS][s] = st.mass;
-  b.f64[C_THICKNESS][s] = st.thickness;
-  b.f64[C_WIDTH][s] = st.width;
-  b.f64[C_LENGTH][s] = st.length;
-  b.f64[C_MASS_OF_BITS][s] = st.mass_of_bits;
+  KST(&b.f64[C_MASS][s], st.mass);
+  KST(&b.f64[C_THICKNESS][s], st.thickness);
+  KST(&b.f64[C_WIDTH][s], st.width);
+  KST(&b.f64[C_LENGTH][s], st.length);
+  KST(&b.f64[C_MASS_OF_BITS][s], st.mass_of_bits);
   if (FOOTLOOSE) {
     b.f64[C_MASS_OF_FL_BITS][s] = st.mass_of_fl_bits;
     b.f64[C_MASS_OF_FL_BERGY_BITS][s] = st.mass_of_fl_bergy_bits;
@@ -443,13 +453,13 @@ k_step_fast(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs 
   long long s = s_base + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = s < n_slots;
   const long long sl = in_range ? s : 0;
-  uint8_t flags = b.flags[sl];
-  int i = b.ine[sl], j = b.jne[sl];
-  double lat = b.f64[C_LAT][sl];
-  double uvel = b.f64[C_UVEL][sl], vvel = b.f64[C_VVEL][sl];
-  double axn = b.f64[C_AXN][sl], ayn = b.f64[C_AYN][sl], bxn = b.f64[C_BXN][sl], byn = b.f64[C_BYN][sl];
-  double xi = b.f64[C_XI][sl], yj = b.f64[C_YJ][sl];
-  double M = b.f64[C_MASS][sl], T = b.f64[C_THICKNESS][sl], W = b.f64[C_WIDTH][sl], L = b.f64[C_LENGTH][sl];
+  uint8_t flags = KLD(&b.flags[sl]);
+  int i = KLD(&b.ine[sl]), j = KLD(&b.jne[sl]);
+  double lat = KLD(&b.f64[C_LAT][sl]);
+  double uvel = KLD(&b.f64[C_UVEL][sl]), vvel = KLD(&b.f64[C_VVEL][sl]);
+  double axn = KLD(&b.f64[C_AXN][sl]), ayn = KLD(&b.f64[C_AYN][sl]), bxn = KLD(&b.f64[C_BXN][sl]), byn = KLD(&b.f64[C_BYN][sl]);
+  double xi = KLD(&b.f64[C_XI][sl]), yj = KLD(&b.f64[C_YJ][sl]);
+  double M = KLD(&b.f64[C_MASS][sl]), T = KLD(&b.f64[C_THICKNESS][sl]), W = KLD(&b.f64[C_WIDTH][sl]), L = KLD(&b.f64[C_LENGTH][sl]);
   prefetch_l1(&b.f64[C_LON][sl]); prefetch_l1(&b.f64[C_MASS_SCALING][sl]);
   prefetch_l1(&b.f64[C_MASS_OF_BITS][sl]); prefetch_l1(&b.f64[C_HEAT_DENSITY][sl]);
   if (!in_range) flags = 0;
@@ -469,8 +479,8 @@ k_step_fast(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs 
     // ---- verlet_stepping I:7203-7328 (same statements as step_berg)
     double sin_lat, cos_lat;
     sincos_halfpi_nofallback(p.pi_180 * lat, &sin_lat, &cos_lat);
-    b.f64[C_UVEL_PREV][s] = uvel - dt_2 * bxn;
-    b.f64[C_VVEL_PREV][s] = vvel - dt_2 * byn;
+    KST(&b.f64[C_UVEL_PREV][s], uvel - dt_2 * bxn);
+    KST(&b.f64[C_VVEL_PREV][s], vvel - dt_2 * byn);
     const double uvel3 = uvel + (dt_2 * axn);
     const double vvel3 = vvel + (dt_2 * ayn);
     Env e;
@@ -481,14 +491,14 @@ k_step_fast(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs 
     accel_core<false, LEAN>(p, M, T, W, L, f_cori, uvel, vvel, dt, e, 1.0, ia0,
                             [](double, double, IAcc&) {}, ax1, ay1, axn, ayn, bxn, byn, un_l, vn_l);
     uvel = uvel3 + (dt * ax1); vvel = vvel3 + (dt * ay1);      // evolve_icebergs I:7157-7162
-    b.f64[C_AXN][s] = axn; b.f64[C_AYN][s] = ayn; b.f64[C_BXN][s] = bxn; b.f64[C_BYN][s] = byn;
-    b.f64[C_UVEL][s] = uvel; b.f64[C_VVEL][s] = vvel;
+    KST(&b.f64[C_AXN][s], axn); KST(&b.f64[C_AYN][s], ayn); KST(&b.f64[C_BXN][s], bxn); KST(&b.f64[C_BYN][s], byn);
+    KST(&b.f64[C_UVEL][s], uvel); KST(&b.f64[C_VVEL][s], vvel);
     // ---- update_verlet_position I:7684-7764
     const double uvel2 = uvel + (dt_2 * axn) + (dt_2 * bxn);
     const double vvel2 = vvel + (dt_2 * ayn) + (dt_2 * byn);
     const double dxdl1 = p.r180_pi * rcp_nr(p.Rearth * cos_lat);
     const double u2 = uvel2 * dxdl1, v2 = vvel2 * p.dlat_dy;
-    const double lonn = b.f64[C_LON][s] + (dt * u2), latn = lat + (dt * v2);
+    const double lonn = KLD(&b.f64[C_LON][s]) + (dt * u2), latn = lat + (dt * v2);
     // ---- adjust_index_and_ground I:7819: in the cell, or one hop to a wet neighbour; anything else is deferred
     const double lo = KID_EDGE_BAND, hi = 1. - KID_EDGE_BAND;
     const double Lx = p.Lx, Lx_2 = Lx * 0.5;
@@ -537,9 +547,9 @@ k_step_fast(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs 
       defer = 2;
     } else {
       xi = a; yj = bb;
-      b.f64[C_LON][s] = lonn; b.f64[C_LAT][s] = latn;
-      b.f64[C_XI][s] = xi; b.f64[C_YJ][s] = yj;
-      b.ine[s] = i; b.jne[s] = j;
+      KST(&b.f64[C_LON][s], lonn); KST(&b.f64[C_LAT][s], latn);
+      KST(&b.f64[C_XI][s], xi); KST(&b.f64[C_YJ][s], yj);
+      KST(&b.ine[s], i); KST(&b.jne[s], j);
       // ---- thermodynamics I:2844-3300 at the new position
 #ifdef KID_FAST_BARRIER
       // (compiler barrier: the corner records interp_flds gathered are gathered again here -- an L1 hit -- instead
@@ -547,7 +557,7 @@ k_step_fast(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs 
       asm volatile("" ::: "memory");
 #endif
       int outcome = thermo_slot<false, LEAN>(g, b, p, s, flags, i, j, xi, yj, uvel, vvel, M, T, W, L,
-                                             b.f64[C_MASS_SCALING][s], b.f64[C_MASS_OF_BITS][s], b.f64[C_HEAT_DENSITY][s],
+                                             KLD(&b.f64[C_MASS_SCALING][s]), KLD(&b.f64[C_MASS_OF_BITS][s]), KLD(&b.f64[C_HEAT_DENSITY][s]),
                                              sc, cnt);
       if (outcome == TH_DELETE) { melted = true; b.flags[s] = 0; }
     }
