@@ -109,6 +109,7 @@ struct kid_handle {
   int visited = 0, first_call_accum = 1, restarted = 0;
   int calving_active = 0;
   double *rmean_calving = nullptr, *rmean_calving_hflx = nullptr;   // get_running_mean_calving I:5999 (tau_calving > 0)
+  double* spread_mass_old = nullptr;                                // find_melt_using_spread_mass I:5495-5500
   int rmean_init[2] = {0, 0};
   int calving_sticky = 0;           // tau_calving > 0: the mean keeps calving after the input has stopped
   int steps_since_sort = 0, sort_interval = 32, sorted_once = 0;
@@ -632,7 +633,9 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   else if (pin->tidal_drift > 0.) unsupported = "tidal_drift>0 needs the FMS random number stream";
   else if (pin->add_iceberg_thickness_to_ssh && !pin->add_weight_to_ocean)
     unsupported = "add_iceberg_thickness_to_SSH reads spread_mass: it needs add_weight_to_ocean=.true. (the field is zero otherwise)";
-  else if (pin->find_melt_using_spread_mass) unsupported = "find_melt_using_spread_mass is not implemented";
+  else if (pin->find_melt_using_spread_mass && (pin->runge_not_verlet || pin->interactive_icebergs_on || pin->footloose || pin->mts ||
+                                                pin->iceberg_melt_without_decay))
+    unsupported = "find_melt_using_spread_mass is built for free-drifting bergs under Verlet stepping without Iceberg_melt_without_decay";
   else if (pin->dem && !(pin->mts && pin->iceberg_bonds_on)) unsupported = "dem=.true. needs mts=.true. and iceberg_bonds_on (F:1433)";
   else if (pin->dem && pin->break_bonds_on_sub_steps && !pin->fracture_criterion_stress) unsupported = "break_bonds_on_sub_steps needs fracture_criterion='stress' (I:1201)";
   else if (pin->mts && (!pin->interactive_icebergs_on || pin->footloose)) unsupported = "mts=.true. needs interactive_icebergs_on and no footloose";
@@ -927,7 +930,7 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
                    &g.calving_hflx, &g.floating_melt, &g.berg_melt, &g.bergy_src, &g.bergy_melt, &g.fl_bits_melt,
                    &g.fl_bits_src, &g.melt_buoy, &g.melt_eros, &g.melt_conv, &g.melt_buoy_fl, &g.melt_eros_fl,
                    &g.melt_conv_fl, &g.fl_parent_melt, &g.fl_child_melt, &g.stored_heat, &g.tmp, &h->tmp_u, &h->tmp_v,
-                   &h->rmean_calving, &h->rmean_calving_hflx};
+                   &h->rmean_calving, &h->rmean_calving_hflx, &h->spread_mass_old};
   for (auto z : zf) { *z = dev_field(h, n2, 0.); if (!*z) return fail(h, KID_ERR_CUDA, "kid_init: out of device memory (fields)"); }
   {
     SpreadFields& sf = h->sf;
@@ -940,7 +943,8 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
     sp.grounding_fraction = q->grounding_fraction; sp.clipping_depth = q->clipping_depth; sp.initial_orientation = q->initial_orientation;
     sp.cdrag_icebergs = q->cdrag_icebergs; sp.utide_icebergs = q->utide_icebergs; sp.ustar_icebergs_bg = q->ustar_icebergs_bg;
     sp.melt_cutoff = q->melt_cutoff;
-    sp.add_weight = (q->add_weight_to_ocean && !q->time_average_weight) ? 1 : 0;
+    sp.add_weight = ((q->add_weight_to_ocean && !q->time_average_weight) || q->find_melt_using_spread_mass) ? 1 : 0;   // I:4997
+    sp.bergy = (q->add_weight_to_ocean || q->pass_fields_to_ocean_model || q->melt_diagnostics) ? 1 : 0;
     sp.use_old_spreading = q->use_old_spreading; sp.rotate = q->rotate_icebergs_for_mass_spreading;
     sp.diag = (q->pass_fields_to_ocean_model || q->melt_diagnostics) ? 1 : 0;
     sp.apply_cutoff_gridded = q->apply_thickness_cutoff_to_gridded_melt;
@@ -2225,7 +2229,7 @@ static bool pipeline_mode(const kid_t* h) {
   static const bool off = getenv("KID_NO_PIPELINE") != nullptr;
   const KidParams& p = h->p;
   return !off && h->d.nranks > 1 && !p.interactive_icebergs_on && !p.footloose && !p.mts && !p.static_icebergs &&
-         !p.runge_not_verlet && !h->calving_active && h->xstream != nullptr;
+         !p.runge_not_verlet && !p.find_melt_using_spread_mass && !h->calving_active && h->xstream != nullptr;
 }
 
 // slots [s0, s1) take the step (s0 a multiple of KID_BLOCK).  main_launch: the step's launch over the whole store
@@ -2316,7 +2320,7 @@ static cudaEvent_t pool_event(kid_t* h) {
 }
 
 // create_gridded_icebergs_fields I:3390-3489: berg mass / area / momentum on the ocean grid
-static int spread_fields(kid_t* h) {
+static int spread_fields(kid_t* h, bool melt_from_spread_mass = false) {
   const long long n2 = h->n2;
   SpreadFields& sf = h->sf;
   // nothing asked for: no weight on the ocean (add_weight_to_ocean) and no diagnostics registered (I:5049-5062)
@@ -2351,6 +2355,7 @@ static int spread_fields(kid_t* h) {
     if (rc) return rc;
   }
   LAUNCH(h, k_sum_spread, (long long)h->nic * h->njc, 128, h->g, h->sp, sf, n2);
+  if (melt_from_spread_mass) LAUNCH(h, k_melt_from_spread_mass, n2, 256, h->g, h->spread_mass_old, sf.spread_mass, h->p.dt, h->p.hlf, n2);
   if (h->sp.apply_cutoff_gridded) LAUNCH(h, k_thickness_cutoff, n2, 256, h->g, h->dp, h->sp, sf, n2);
   return KID_OK;
 }
@@ -2399,6 +2404,7 @@ static int step_core(kid_t* h) {
   }
   const bool fl = h->p.footloose != 0, dg = h->p.melt_diagnostics != 0;
   const bool mts = h->p.mts != 0;
+  const bool fm = h->p.find_melt_using_spread_mass != 0;   // the melt follows the move in a launch of its own, with the spread mass taken in between
   // the second stream's work of the previous step (arrivals unpacked and stepped, leaver counter reset) is long done
   if (h->xdone_recorded) { CK(cudaStreamWaitEvent(s, h->ev_xdone, 0)); h->xdone_recorded = 0; }
   if (mts && !h->mts_env_cached) {                         // first visit, I:5412-5414
@@ -2427,7 +2433,7 @@ static int step_core(kid_t* h) {
     } else if (h->p.runge_not_verlet) {
       if (dg) { LAUNCH(h, (k_step_rk<true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
       else { LAUNCH(h, (k_step_rk<false>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots); }
-    } else if (fl) { LAUNCH(h, (k_step<true, false, false>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots, 0LL); }
+    } else if (fl || fm) { LAUNCH(h, (k_step<true, false, false>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots, 0LL); }   // the move alone
     else if (dg) launch_step<false, true>(h, 0, h->n_slots, true); else launch_step<false, false>(h, 0, h->n_slots, true);
   }
   if (h->xchg_pending) {
@@ -2451,7 +2457,7 @@ static int step_core(kid_t* h) {
     if (rc) return rc;
     if (n_recv > 0) {
       long long s0 = h->n_slots, s1 = h->n_slots + n_recv;
-      if (fl || mts) { /* thermodynamics of every owned berg follows below (footloose_calving / the MTS sequence I:5497) */ }
+      if (fl || mts || fm) { /* thermodynamics of every owned berg follows below (footloose_calving / the MTS sequence I:5497) */ }
       else if (h->p.melt_diagnostics) { LAUNCH(h, (k_thermo_range<false, true>), n_recv, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s0, s1, 0); }
       else { LAUNCH(h, (k_thermo_range<false, false>), n_recv, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, s0, s1, 0); }
       h->n_slots = s1;
@@ -2487,7 +2493,13 @@ static int step_core(kid_t* h) {
     if (mts) LAUNCH(h, k_mts_env_cache, h->n_slots, 128, h->g, h->b, h->dp, h->dcnt, h->n_slots);
     if (fl) { CellTable ct{h->cell_start, h->cell_count}; LAUNCH(h, k_fl_interactivity, h->n_slots, 128, h->g, h->b, h->dp, ct, h->n_slots); }
   }
-  if (fl || mts || h->p.static_icebergs) {
+  if (fm) {
+    // I:5490-5500: the spread mass before the melt
+    int rc = spread_fields(h);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->spread_mass_old, h->sf.spread_mass, sizeof(double) * h->n2, cudaMemcpyDeviceToDevice, s));
+  }
+  if (fl || mts || fm || h->p.static_icebergs) {
     // thermodynamics I:5497 on its own: footloose calving sits between the move and the melt
     if (fl && dg) { LAUNCH(h, (k_thermo_range<true, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, 0LL, h->n_slots, 1); }
     else if (fl) { LAUNCH(h, (k_thermo_range<true, false>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, 0LL, h->n_slots, 1); }
@@ -2499,7 +2511,7 @@ static int step_core(kid_t* h) {
     int rc = sort_bergs(h);
     if (rc) return rc;
   }
-  { int rc = spread_fields(h); if (rc) return rc; }
+  { int rc = spread_fields(h, fm); if (rc) return rc; }
   CK(cudaEventRecord(h->ev[T_TOTAL], s));
   CK(cudaEventRecord(e2, s));
   return KID_OK;

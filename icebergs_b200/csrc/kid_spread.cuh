@@ -240,7 +240,7 @@ __device__ __noinline__ double bond_orientation(const DevGrid& g, const DevBergs
 
 struct SpreadParams {
   double grounding_fraction, clipping_depth, initial_orientation, cdrag_icebergs, utide_icebergs, ustar_icebergs_bg, melt_cutoff;
-  int32_t add_weight, use_old_spreading, rotate, diag, apply_cutoff_gridded, pad;
+  int32_t add_weight, use_old_spreading, rotate, diag, apply_cutoff_gridded, bergy;   // bergy: id_bergy_mass > 0 or add_weight_to_ocean, I:5061
 };
 struct SpreadFields {
   double *mass_on_ocean, *area_on_ocean, *uvel_on_ocean, *vvel_on_ocean;   // [9][n2]
@@ -265,7 +265,7 @@ __global__ void k_spread_bergs(const __grid_constant__ DevGrid g, const __grid_c
   double M = b.f64[C_MASS][s], ms = b.f64[C_MASS_SCALING][s], mob = b.f64[C_MASS_OF_BITS][s];
   double mfl = b.f64[C_MASS_OF_FL_BITS][s], mflb = b.f64[C_MASS_OF_FL_BERGY_BITS][s];
   if (sp.diag) atomicAdd(&sf.mass[c], M / area * ms);                       // id_mass > 0, I:5049
-  atomicAdd(&sf.bergy_mass[c], (mob + mflb) / area * ms);                    // id_bergy_mass > 0 or add_weight_to_ocean, I:5061
+  if (sp.bergy) atomicAdd(&sf.bergy_mass[c], (mob + mflb) / area * ms);      // id_bergy_mass > 0 or add_weight_to_ocean, I:5061
   if (!sp.add_weight) return;
   const double rho_seawater = 1035.;          // the local value of spread_mass_across_ocean_cells, I:3919
   double Tn = b.f64[C_THICKNESS][s], A = b.f64[C_LENGTH][s] * b.f64[C_WIDTH][s];
@@ -333,6 +333,19 @@ __global__ void k_sum_spread(const __grid_constant__ DevGrid g, const __grid_con
     if (sa == 0.0) ustar_h = 0.;
     sf.ustar_iceberg[c] = ustar_h;
   }
+}
+
+// find_melt_using_spread_mass, I:3436-3448: the melt is what the spread mass lost over the step (data domain; the spread
+// sums are zero outside the compute domain), and the heat flux follows from it
+__global__ void k_melt_from_spread_mass(const __grid_constant__ DevGrid g, const double* __restrict__ spread_mass_old,
+                                        const double* __restrict__ spread_mass_new, double dt, double hlf, long long n2) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n2) return;
+  double fm = 0.0;
+  if (g.area[c] > 0.0) fm = fmax((spread_mass_old[c] - spread_mass_new[c]) / dt, 0.0);
+  g.floating_melt[c] = fm;
+  int i = g.isd + (int)(c % g.nid), j = g.jsd + (int)(c / g.nid);
+  if (i >= g.isc && i <= g.iec && j >= g.jsc && j <= g.jec) g.calving_hflx[c] = fm * hlf;
 }
 
 // I:3476-3488: no melt into water shallower than melt_cutoff under the average draught (data domain)

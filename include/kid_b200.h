@@ -221,8 +221,9 @@ typedef struct KidParams {
   double clipping_depth;                       /* F:227 (0.) */
   double initial_orientation;                  /* F:713 (0.) degrees */
   double tau_calving;                          /* F:728 (0.) years: running mean of calving / calving_hflx, get_running_mean_calving I:5999-6038 */
-  /* namelist entry that reaches icebergs_run but is not implemented: refused by kid_init when set */
-  int32_t find_melt_using_spread_mass;         /* F:741 (F): melt from the spread mass before/after I:5490-5495; must be 0 */
+  int32_t find_melt_using_spread_mass;         /* F:741 (F): floating_melt from the spread mass before / after the melt, I:5490-5500,
+                                                  I:3436-3448 (free-drifting Verlet bergs; refused with RK4, interactions, footloose,
+                                                  MTS or Iceberg_melt_without_decay) */
   /* trajectory sampling, record_posn F:5328-5498 (WHEN to sample is the caller's decision, I:5173-5178: kid_record_posn) */
   int32_t save_short_traj;                     /* F:759 (T): the file holds lon, lat, year, day, id only */
   int32_t save_fl_traj;                        /* F:762 (T): + masses, thickness, velocity (and the footloose state) */

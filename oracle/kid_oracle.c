@@ -105,6 +105,7 @@ struct Oracle {
   int visited;             /* "Visited" save variable, I:5110 */
   int first_call_accum;    /* first_call in accumulate_calving I:6161 */
   double *rmean_calving, *rmean_calving_hflx;      /* get_running_mean_calving I:5999 */
+  double *spread_mass_old;                         /* find_melt_using_spread_mass I:5495-5500 */
   int rmean_calving_initialized, rmean_calving_hflx_initialized;
   int restarted;
   KidCounters cnt;
@@ -1326,6 +1327,7 @@ static void evolve_icebergs(Oracle* o) {
 #include "kid_oracle_hex.inc"
 
 static void halo_update(Oracle* o, double* f);
+static double* dalloc(size_t n, double v);
 static void fl_bits_dimensions(const Oracle* o, const OBerg* this_, double* L_fl, double* W_fl, double* T_fl);
 
 /* find_orientation_using_iceberg_bonds I:3829-3893 */
@@ -1405,7 +1407,7 @@ static void calculate_mass_on_ocean(Oracle* o, int with_diagnostics) {
       if (!(berg->halo_berg < 2 || !p->mts)) continue;
       int i = berg->ine, j = berg->jne;
       if (!(G(o, area, i, j) > 0.)) continue;
-      if (p->add_weight_to_ocean && !p->time_average_weight)
+      if ((p->add_weight_to_ocean && !p->time_average_weight) || p->find_melt_using_spread_mass)      /* I:4997 */
         spread_mass_across_ocean_cells(o, berg, i, j, berg->xi, berg->yj, berg->mass, berg->mass_of_bits, berg->mass_scaling,
                                        berg->length * berg->width, berg->thickness);
       if (with_diagnostics) {
@@ -1437,13 +1439,17 @@ static void sum_up_spread_fields(Oracle* o, double* field /* data-domain array, 
 #undef V9
 }
 
-/* create_gridded_icebergs_fields I:3390-3489 (find_melt_using_spread_mass is refused at create) */
+/* create_gridded_icebergs_fields I:3390-3489 */
 static void create_gridded_icebergs_fields(Oracle* o) {
   const KidParams* p = &o->p;
   const KidDomain* d = &o->d;
   size_t n2 = (size_t)o->nid * o->njd;
   int diag = p->pass_fields_to_ocean_model || p->melt_diagnostics;
-  if (!diag && !(p->add_weight_to_ocean && !p->time_average_weight)) return;   /* every field below stays zero */
+  const int fmusm = p->find_melt_using_spread_mass;
+  if (!diag && !(p->add_weight_to_ocean && !p->time_average_weight) && !fmusm) return;   /* every field below stays zero */
+  double* spread_mass_tmp = fmusm ? dalloc(n2, 0.) : NULL;
+  if (fmusm && p->iceberg_melt_without_decay)              /* I:3411-3413: what thermodynamics spread for the would-be state */
+    sum_up_spread_fields(o, spread_mass_tmp, o->mass_on_ocean, 0);
   memset(o->mass, 0, sizeof(double) * n2); memset(o->bergy_mass, 0, sizeof(double) * n2);
   calculate_mass_on_ocean(o, 1);
   memset(o->spread_uvel, 0, sizeof(double) * n2); memset(o->spread_vvel, 0, sizeof(double) * n2);
@@ -1454,6 +1460,16 @@ static void create_gridded_icebergs_fields(Oracle* o) {
     sum_up_spread_fields(o, o->spread_area, o->area_on_ocean, 1);
   }
   sum_up_spread_fields(o, o->spread_mass, o->mass_on_ocean, 0);
+  if (fmusm) {                                             /* I:3436-3448 */
+    if (!p->iceberg_melt_without_decay)
+      for (int j = d->jsc; j <= d->jec; j++) for (int i = d->isc; i <= d->iec; i++) spread_mass_tmp[IDX(o, i, j)] = G(o, spread_mass, i, j);
+    for (int i = d->isd; i <= d->ied; i++) for (int j = d->jsd; j <= d->jed; j++) {
+      if (G(o, area, i, j) > 0.0) G(o, floating_melt, i, j) = dmax((G(o, spread_mass_old, i, j) - spread_mass_tmp[IDX(o, i, j)]) / (p->dt), 0.0);
+      else G(o, floating_melt, i, j) = 0.0;
+    }
+    for (int j = d->jsc; j <= d->jec; j++) for (int i = d->isc; i <= d->iec; i++) G(o, calving_hflx, i, j) = G(o, floating_melt, i, j) * p->hlf;
+    free(spread_mass_tmp);
+  }
   memset(o->ustar_iceberg, 0, sizeof(double) * n2);
   if (diag)
     for (int j = d->jsc; j <= d->jec; j++) for (int i = d->isc; i <= d->iec; i++) {
@@ -1841,7 +1857,13 @@ static void thermodynamics(Oracle* o) {
         }
         if (p->allow_bergs_to_roll && N_bonds == 0.) oracle_rolling(p, &Tn, &Wn, &Ln);
         if (p->iceberg_melt_without_decay) {
-          /* find_melt_using_spread_mass is a spreading-row option: not restated */
+          if (p->find_melt_using_spread_mass) {            /* I:3220-3236: the would-be state goes onto the ocean grid */
+            double pfl = this_->mass_of_fl_bits, pflb = this_->mass_of_fl_bergy_bits;
+            this_->mass_of_fl_bits = Mnew_fl; this_->mass_of_fl_bergy_bits = nMbits_fl;
+            if (Mnew > 0.) spread_mass_across_ocean_cells(o, this_, i, j, this_->xi, this_->yj, Mnew, nMbits, this_->mass_scaling, Ln * Wn, Tn);
+            else if (Mnew_fl > 0.) o_fatal(o, "oracle: find_melt_using_spread_mass with a melted parent of footloose bits (I:3229-3235) is not restated");
+            this_->mass_of_fl_bits = pfl; this_->mass_of_fl_bergy_bits = pflb;
+          }
           Mnew = this_->mass; nMbits = this_->mass_of_bits;
           Mnew_fl = this_->mass_of_fl_bits; nMbits_fl = this_->mass_of_fl_bergy_bits;
           Tn = this_->thickness; Wn = this_->width; Ln = this_->length;
@@ -2282,6 +2304,7 @@ Oracle* oracle_create(const KidParams* p, const KidDomain* dom, int32_t year, do
   o->mass_on_ocean = dalloc(n2 * 9, 0.); o->area_on_ocean = dalloc(n2 * 9, 0.);
   o->uvel_on_ocean = dalloc(n2 * 9, 0.); o->vvel_on_ocean = dalloc(n2 * 9, 0.);
   o->rmean_calving = dalloc(n2, 0.); o->rmean_calving_hflx = dalloc(n2, 0.);
+  o->spread_mass_old = dalloc(n2, 0.);
   o->iceberg_counter_grd = (int32_t*)calloc(n2, sizeof(int32_t));
   o->list = (OBerg**)calloc(n2, sizeof(OBerg*));
   if (p->tidal_drift > 0.) o_fatal(o, "oracle: tidal_drift needs the FMS random number stream (external)");
@@ -2413,7 +2436,7 @@ void oracle_destroy(Oracle* o) {
                  o->melt_eros_fl, o->melt_conv_fl, o->fl_parent_melt, o->fl_child_melt, o->stored_heat,
                  o->stored_ice, o->real_calving, o->tmp, o->mass, o->spread_mass, o->spread_area,
                  o->ustar_iceberg, o->spread_uvel, o->spread_vvel, o->mass_on_ocean, o->area_on_ocean,
-                 o->uvel_on_ocean, o->vvel_on_ocean, o->rmean_calving, o->rmean_calving_hflx};
+                 o->uvel_on_ocean, o->vvel_on_ocean, o->rmean_calving, o->rmean_calving_hflx, o->spread_mass_old};
   for (size_t k = 0; k < sizeof(z) / sizeof(z[0]); k++) free(z[k]);
   free(o->iceberg_counter_grd); free(o->list); free(o);
 }
@@ -2713,6 +2736,14 @@ static void step_core(Oracle* o) {
     if (!p->old_interp_flds_order) interp_gridded_fields_to_bergs(o);
   }
   if (p->footloose) oracle_footloose_part2(o);
+  if (p->find_melt_using_spread_mass) {                    /* I:5490-5500: the spread mass before the melt */
+    size_t n2_ = (size_t)o->nid * o->njd;
+    calculate_mass_on_ocean(o, 0);
+    memset(o->spread_mass_old, 0, sizeof(double) * n2_);
+    sum_up_spread_fields(o, o->spread_mass_old, o->mass_on_ocean, 0);
+    memset(o->mass_on_ocean, 0, sizeof(double) * n2_ * 9); memset(o->area_on_ocean, 0, sizeof(double) * n2_ * 9);
+    memset(o->uvel_on_ocean, 0, sizeof(double) * n2_ * 9); memset(o->vvel_on_ocean, 0, sizeof(double) * n2_ * 9);
+  }
   double t3 = now_sec();
   thermodynamics(o);
   double t4 = now_sec();

@@ -119,3 +119,35 @@ def test_point_in_triangle_regression_on_the_device():
     assert api.lib().kid_unit_point_in_triangle(0, v, C.byref(inside), C.byref(area)) == 0
     assert bool(inside.value) is k["inside"]
     assert area.value > 0.0
+
+
+@pytest.mark.parametrize("add_weight", [1, 0])
+def test_melt_from_the_spread_mass(add_weight):
+    """find_melt_using_spread_mass (I:5490-5500, I:3436-3448): the spread mass is summed between the move and the melt and
+    again after it; floating_melt is the difference per step, calving_hflx = floating_melt * HLF, and what icebergs_run
+    hands back in calving / calving_hflx follows.  The move and the melt run as separate launches for this."""
+    from common import COMPARE_F64, assert_bergs_match
+    case = Case(96, 48, 20000, add_weight_to_ocean=add_weight, find_melt_using_spread_mass=1, use_old_spreading=0,
+                hexagonal_icebergs=1)
+    b, o = case.make_gpu(), case.make_oracle()
+    names = list(COMPARE_F64) + ["ine", "jne", "start_year", "id"]
+    for step in range(3):
+        calving, hflx, f = case.run_args()
+        args = (f["uo"], f["vo"], f["ui"], f["vi"], f["tauxa"], f["tauya"], f["ssh"], f["sst"])
+        cg, hg = calving.copy(), hflx.copy()
+        api.icebergs_run(b, (1, 0.0), cg, *args, hg, f["cn"], f["hi"], sss=f["sss"])
+        co, ho = calving.copy(), hflx.copy()
+        o.run((1, 0.0), co, *args, ho, f["cn"], f["hi"], sss=f["sss"])
+        assert_bergs_match(b.get_bergs(names), o.get_bergs(names), rtol=1e-10 if step == 0 else 1e-9, context=f"fmusm step {step}")
+        for fid in (D.KID_FLD_SPREAD_MASS, D.KID_FLD_BERGY_MASS, D.KID_FLD_BERG_MELT):
+            assert grid_rel(b.grid_field(fid), o.grid_field(fid)) < 1e-10, (fid, step)
+        # the melt is a difference of two sums of O(1e12 kg) spread masses: compare against the spread mass per second
+        scale = np.abs(o.grid_field(D.KID_FLD_SPREAD_MASS)).max() / case.dt
+        for fid in (D.KID_FLD_FLOATING_MELT, D.KID_FLD_CALVING_HFLX):
+            got, want = b.grid_field(fid), o.grid_field(fid)
+            tol = 1e-10 * scale * (case.params().hlf if fid == D.KID_FLD_CALVING_HFLX else 1.0)
+            assert np.abs(got - want).max() <= tol, (fid, step, np.abs(got - want).max(), tol)
+        assert np.abs(cg - co).max() <= 1e-10 * scale and np.abs(hg - ho).max() <= 1e-10 * scale * case.params().hlf
+    fm = o.grid_field(D.KID_FLD_FLOATING_MELT)
+    assert fm.max() > 0 and np.array_equal(o.grid_field(D.KID_FLD_CALVING_HFLX)[4:-4, 4:-4], (fm * case.params().hlf)[4:-4, 4:-4])
+    api.icebergs_end(b)
