@@ -626,10 +626,10 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   if (dom->device < 0 || dom->device >= ndev) { g_init_error = "kid_init: bad device ordinal"; return KID_ERR_ARG; }
   // what this build of the library does not implement is refused up front
   const char* unsupported = nullptr;
-  if (pin->runge_not_verlet && pin->mts)
-    unsupported = "mts=.true. takes its long steps with the Verlet form of accel_mts: set runge_not_verlet=0";
-  else if (pin->runge_not_verlet && pin->footloose)
-    unsupported = "Runge_not_Verlet=.true. with footloose is not parity-clean yet (the stepping exists: k_step_rk<.., STEP_ONLY>): set runge_not_verlet=0";
+  // mts with Runge_not_Verlet: the reference warns and switches to Verlet (F:1303-1306), done below; what is left of
+  // RK4 + MTS / DEM / footloose is the reference's own FATAL (F:1485-1488)
+  if (pin->runge_not_verlet && !pin->mts && (pin->dem || pin->footloose))
+    unsupported = "Runge_not_Verlet must be false to use MTS, DEM, or footloose! (the reference's own FATAL, F:1485-1488)";
   else if (pin->tidal_drift > 0.) unsupported = "tidal_drift>0 needs the FMS random number stream";
   else if (pin->add_iceberg_thickness_to_ssh && !pin->add_weight_to_ocean)
     unsupported = "add_iceberg_thickness_to_SSH reads spread_mass: it needs add_weight_to_ocean=.true. (the field is zero otherwise)";
@@ -753,6 +753,7 @@ extern "C" int32_t kid_init(kid_t** hp, const KidParams* pin, const KidDomain* d
   }
   // derived parameters, F:1264, F:1312, F:1483
   KidParams* q = &h->p;
+  if (q->mts && q->runge_not_verlet) q->runge_not_verlet = 0;     // "Multiple time stepping does not work with Runge Kutta stepping, switching to Verlet." F:1303-1306
   if (!q->iceberg_bonds_on) q->max_bonds = 0;
   if (q->contact_spring_coef <= 0.) q->contact_spring_coef = q->spring_coef;
   q->old_interp_flds_order = !(q->mts || q->dem || q->footloose);

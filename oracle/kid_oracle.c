@@ -2280,6 +2280,9 @@ Oracle* oracle_create(const KidParams* p, const KidDomain* dom, int32_t year, do
                       const double* sin_rot, const double* ocean_depth, int32_t fractional_area) {
   Oracle* o = (Oracle*)calloc(1, sizeof(Oracle));
   o->p = *p; o->d = *dom;
+  if (o->p.mts && o->p.runge_not_verlet) o->p.runge_not_verlet = 0;       /* F:1303-1306: warning, switching to Verlet */
+  if (o->p.runge_not_verlet && (o->p.dem || o->p.footloose))               /* F:1485-1488 */
+    o_fatal(o, "KID, ice_bergs_framework_init: Runge_not_Verlet must be false to use MTS, DEM, or footloose!");
   o->current_year = year; o->current_yearday = yearday;
   o->first_call_accum = 1; o->nthreads = 1; o->mts_part = 1;
   o->only_interactive_forces = p->only_interactive_forces;

@@ -76,6 +76,21 @@ def test_mts_refuses_what_is_not_built():
         mts_pair(dem=1, iceberg_bonds_on=0, manually_initialize_bonds=0, max_bonds=0)
 
 
+def test_mts_with_runge_kutta_switches_to_verlet_like_the_reference():
+    """F:1303-1306: 'Multiple time stepping does not work with Runge Kutta stepping, switching to Verlet.' (a warning):
+    the namelist default Runge_not_Verlet=T with mts=T runs, and runs the Verlet scheme"""
+    a = mts_pair(runge_not_verlet=1)
+    a.step(3)
+    a.check("mts with Runge_not_Verlet=T, 3 steps", rtol=1e-8)
+    b = mts_pair(runge_not_verlet=0)
+    b.step(3)
+    ga, gb = a.b.get_bergs(["id", "lon", "lat", "uvel"]), b.b.get_bergs(["id", "lon", "lat", "uvel"])
+    oa, ob = np.argsort(ga["id"]), np.argsort(gb["id"])
+    for k in ("lon", "lat", "uvel"):
+        assert np.array_equal(ga[k][oa], gb[k][ob]), k
+    a.end(); b.end()
+
+
 # ---------------------------------------------------------------------------------------------- DEM (a15, a17)
 IKID = dict(dem=1, poisson=0.3, dem_damping_coef=1.0, dem_spring_coef=4471.94)
 # absolute floors: before the collision the tangential displacements (~1e-14 m on 780 m bonds), relative rotations and

@@ -56,8 +56,8 @@ def test_rk4_unbonded_interacting_bergs_old_predictive_corrective():
 
 
 def test_rk4_with_footloose_is_refused():
-    """RK4 + footloose: the stepping kernel exists but is not parity-clean against the oracle through the cyclic seam
-    (profiles/r2_notes.md): refused at init with the flag named, like every unsupported combination"""
+    """RK4 + footloose is the reference's own FATAL ('Runge_not_Verlet must be false to use MTS, DEM, or footloose!',
+    F:1485-1488): refused at init with the same text"""
     with pytest.raises(api.KidFatal, match="footloose"):
         g = S.CartesianGrid()
         api.icebergs_init(20, 20, 10.0, (1, 0.0), params=S.footloose_params(api.default_params, runge_not_verlet=1),
