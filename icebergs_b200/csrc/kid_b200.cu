@@ -110,6 +110,7 @@ struct kid_handle {
   int calving_active = 0;
   double *rmean_calving = nullptr, *rmean_calving_hflx = nullptr;   // get_running_mean_calving I:5999 (tau_calving > 0)
   double* spread_mass_old = nullptr;                                // find_melt_using_spread_mass I:5495-5500
+  IaRec* ia_rec = nullptr;          // one interaction record per slot (k_ia_prepare), plain branch of interactive_force only
   int rmean_init[2] = {0, 0};
   int calving_sticky = 0;           // tau_calving > 0: the mean keeps calving after the input has stopped
   int steps_since_sort = 0, sort_interval = 32, sorted_once = 0;
@@ -1177,7 +1178,7 @@ extern "C" int32_t kid_end(kid_t** hp) {
   cudaFree(h->d_send_counts); cudaFree(h->d_cursor); cudaFree(h->d_offsets); cudaFree(h->d_all_counts);
   if (h->h_all_counts) cudaFreeHost(h->h_all_counts);
   if (h->h_offsets) cudaFreeHost(h->h_offsets);
-  cudaFree(h->halo_send); cudaFree(h->halo_recv); cudaFree(h->layout_table); cudaFree(h->fold_strip);
+  cudaFree(h->halo_send); cudaFree(h->halo_recv); cudaFree(h->layout_table); cudaFree(h->fold_strip); cudaFree(h->ia_rec);
   cudaFree(h->gsend); cudaFree(h->grecv); cudaFree(h->d_gcounts); cudaFree(h->d_goffsets); cudaFree(h->d_gcursor);
   cudaFree(h->b.bond_other_id); cudaFree(h->b.bond_other_slot); cudaFree(h->b.bond_other_ine);
   cudaFree(h->b.bond_other_jne); cudaFree(h->b.bond_length); cudaFree(h->b.conglom_id); cudaFree(h->d_changed);
@@ -2422,7 +2423,14 @@ static int step_core(kid_t* h) {
     } else if (ia) {
       CellTable ct{h->cell_start, h->cell_count};
       if (h->p.runge_not_verlet) { LAUNCH(h, k_step_rk_ia, h->n_slots, KID_BLOCK, h->g, h->b, h->dp, ct, h->dcnt, h->n_slots); }
-      else { LAUNCH(h, k_ia_velocity, h->n_slots, KID_BLOCK, h->g, h->b, h->dp, ct, h->dcnt, h->n_slots); }
+      else {
+        // the plain branch of interactive_force (I:577-605) reads one 64-byte record per candidate (kid_interact.cuh)
+        const KidParams& q = h->p;
+        const bool plain = !(q.mts || (q.contact_distance > 0.) || (q.contact_spring_coef != q.spring_coef)) && !getenv("KID_IA_NO_REC");
+        if (plain && !h->ia_rec) CK(cudaMalloc(&h->ia_rec, sizeof(IaRec) * (size_t)h->capacity));
+        if (plain) LAUNCH(h, k_ia_prepare, h->n_slots, 256, h->b, h->dp, h->ia_rec, h->n_slots);
+        LAUNCH(h, k_ia_velocity, h->n_slots, KID_BLOCK, h->g, h->b, h->dp, ct, h->dcnt, h->n_slots, plain ? h->ia_rec : nullptr);
+      }
       if (fl) { LAUNCH(h, (k_step<true, false, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots, 0LL); }
       else if (dg) { LAUNCH(h, (k_step<false, true, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots, 0LL); }
       else { LAUNCH(h, (k_step<false, false, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots, 0LL); }

@@ -19,28 +19,18 @@ namespace kid {
 
 struct CellTable { const int32_t* start; const int32_t* count; };
 
-// I:611-804.  s = primary berg, o = other berg (slots).
+// calculate_force I:611-804 once both bergs are in registers: positions, the other berg's velocity, masses and
+// interaction radii.  Returns whether the pair exerted a force (its decision depends on the positions only).
 // crit: 0 = no c_crit_dist argument, 1 = c_crit_dist=.true. (contact inside a conglomerate: radii only, the
 // bond spring constant, I:716-719)
-__device__ __forceinline__ void calculate_force(const DevBergs& b, const DevParams& p, long long s, long long o,
-                                                IAcc& A, double u0, double v0, double u1, double v1, bool bonded,
-                                                int crit = 0) {
-  if (b.id[s] == b.id[o]) return;
-  if (b.f64[C_FL_K][s] == -1. || b.f64[C_FL_K][o] == -1.) return;
-  double lon1 = b.f64[C_LON_OLD][s], lat1 = b.f64[C_LAT_OLD][s];
-  double lon2 = b.f64[C_LON_OLD][o], lat2 = b.f64[C_LAT_OLD][o];
-  double u2 = b.f64[C_UVEL_OLD][o], v2 = b.f64[C_VVEL_OLD][o];
-  double M1 = b.f64[C_MASS][s], A1 = b.f64[C_LENGTH][s] * b.f64[C_WIDTH][s];
-  double M2 = b.f64[C_MASS][o], A2 = b.f64[C_LENGTH][o] * b.f64[C_WIDTH][o];
+__device__ __forceinline__ bool calculate_force_core(const DevParams& p, double lon1, double lat1, double lon2, double lat2,
+                                                     double u2, double v2, double M1, double M2, double R1, double R2, IAcc& A,
+                                                     double u0, double v0, double u1, double v1, bool bonded, int crit) {
   double dlon = lon1 - lon2, dlat = lat1 - lat2;
   double lat_ref = 0.5 * (lat1 + lat2), dx_dlon, dy_dlat;
   convert_from_grid_to_meters(p, lat_ref, dx_dlon, dy_dlat);
   double r_dist_x = dlon * dx_dlon, r_dist_y = dlat * dy_dlat;
   double r_dist = sqrt((r_dist_x * r_dist_x) + (r_dist_y * r_dist_y));
-  double R1, R2;
-  if (p.hexagonal_icebergs) { R1 = sqrt(A1 / (2. * sqrt(3.))); R2 = sqrt(A2 / (2. * sqrt(3.))); }
-  else if (p.iceberg_bonds_on) { R1 = 0.5 * sqrt(A1); R2 = 0.5 * sqrt(A2); }
-  else { R1 = sqrt(A1 / p.pi); R2 = sqrt(A2 / p.pi); }
   double M_min = M1 < M2 ? M1 : M2;
   double crit_dist, spring_coef;
   if (bonded) { crit_dist = R1 + R2; spring_coef = p.spring_coef; }
@@ -55,7 +45,8 @@ __device__ __forceinline__ void calculate_force(const DevBergs& b, const DevPara
   // STS with contact_distance = 0 and one spring constant: a bond only pulls (I:741-748)
   if (bonded && !(p.mts || (p.contact_distance > 0.) || (p.contact_spring_coef != p.spring_coef)))
     if (!(r_dist > crit_dist)) tbonded = false;
-  if ((r_dist > 0.) && (tbonded || (r_dist < crit_dist && !bonded))) {
+  if (!((r_dist > 0.) && (tbonded || (r_dist < crit_dist && !bonded)))) return false;
+  {
     double accel_spring = spring_coef * (M_min / M1) * (crit_dist - r_dist);
     A.IA_x = A.IA_x + (accel_spring * (r_dist_x / r_dist));
     A.IA_y = A.IA_y + (accel_spring * (r_dist_y / r_dist));
@@ -75,6 +66,91 @@ __device__ __forceinline__ void calculate_force(const DevBergs& b, const DevPara
       A.Pu_x = A.Pu_x + (p_ia_coef * ((P_11 * u2) + (P_12 * v2)));
       A.Pu_y = A.Pu_y + (p_ia_coef * ((P_12 * u2) + (P_22 * v2)));
       P_11 = 1 - P_11; P_12 = -P_12; P_21 = -P_21; P_22 = 1 - P_22;      // normal -> tangential projector
+    }
+  }
+  return true;
+}
+// the interaction radius of a berg of area A = L*W, I:700-714
+__device__ __forceinline__ double ia_radius_of(const DevParams& p, double A) {
+  if (p.hexagonal_icebergs) return sqrt(A / (2. * sqrt(3.)));
+  if (p.iceberg_bonds_on) return 0.5 * sqrt(A);
+  return sqrt(A / p.pi);
+}
+
+// I:611-804.  s = primary berg, o = other berg (slots).
+__device__ __forceinline__ void calculate_force(const DevBergs& b, const DevParams& p, long long s, long long o,
+                                                IAcc& A, double u0, double v0, double u1, double v1, bool bonded,
+                                                int crit = 0) {
+  if (b.id[s] == b.id[o]) return;
+  if (b.f64[C_FL_K][s] == -1. || b.f64[C_FL_K][o] == -1.) return;
+  double lon1 = b.f64[C_LON_OLD][s], lat1 = b.f64[C_LAT_OLD][s];
+  double lon2 = b.f64[C_LON_OLD][o], lat2 = b.f64[C_LAT_OLD][o];
+  double u2 = b.f64[C_UVEL_OLD][o], v2 = b.f64[C_VVEL_OLD][o];
+  double M1 = b.f64[C_MASS][s], A1 = b.f64[C_LENGTH][s] * b.f64[C_WIDTH][s];
+  double M2 = b.f64[C_MASS][o], A2 = b.f64[C_LENGTH][o] * b.f64[C_WIDTH][o];
+  calculate_force_core(p, lon1, lat1, lon2, lat2, u2, v2, M1, M2, ia_radius_of(p, A1), ia_radius_of(p, A2), A, u0, v0, u1, v1,
+                       bonded, crit);
+}
+
+// ---- the plain branch of interactive_force (STS, contact_distance = 0, one spring constant: every berg of the 3x3 cells
+// is a candidate, I:577-592) for large unbonded populations.  What calculate_force reads of the OTHER berg is gathered
+// once per step into one 64-byte record per berg (k_ia_prepare) -- one line per candidate instead of eight column
+// gathers --; a candidate further away in latitude alone than the two radii is dropped before any other arithmetic
+// (r_dist >= |r_dist_y|: the reference's own test r_dist < crit_dist cannot pass); and the pairs that did exert a force are
+// remembered, so the corrector evaluation of accel (I:2217) walks those few instead of the 3x3 cells again (whether a pair
+// acts depends on the *_old positions only).  Same arithmetic, same order of accumulation.
+struct __align__(16) IaRec { double lon, lat, u, v, M, R; long long id; long long no_ia; };
+#define KID_IA_MAXHIT 12
+struct IaHits { int32_t o[KID_IA_MAXHIT]; int32_t n; bool overflow; };
+
+__global__ void k_ia_prepare(const __grid_constant__ DevBergs b, const __grid_constant__ DevParams p, IaRec* __restrict__ rec,
+                             long long n_slots) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  IaRec r;
+  r.lon = b.f64[C_LON_OLD][s]; r.lat = b.f64[C_LAT_OLD][s]; r.u = b.f64[C_UVEL_OLD][s]; r.v = b.f64[C_VVEL_OLD][s];
+  r.M = b.f64[C_MASS][s]; r.R = ia_radius_of(p, b.f64[C_LENGTH][s] * b.f64[C_WIDTH][s]);
+  r.id = b.id[s]; r.no_ia = (b.f64[C_FL_K][s] == -1.) ? 1 : 0;
+  rec[s] = r;
+}
+
+__device__ __forceinline__ void interactive_force_plain(const DevGrid& g, const DevBergs& b, const DevParams& p,
+                                                        const CellTable& ct, const IaRec* __restrict__ rec, long long s, int i, int j,
+                                                        IAcc& A, double u0, double v0, double u1, double v1, IaHits& hits, bool replay) {
+  A.IA_x = A.IA_y = A.P11 = A.P12 = A.P21 = A.P22 = A.Pu_x = A.Pu_y = 0.;
+  const IaRec me = rec[s];
+  if (me.no_ia) return;
+  if (replay && !hits.overflow) {
+    for (int k = 0; k < hits.n; k++) {
+      const IaRec o = rec[hits.o[k]];
+      calculate_force_core(p, me.lon, me.lat, o.lon, o.lat, o.u, o.v, me.M, o.M, me.R, o.R, A, u0, v0, u1, v1, false, 0);
+    }
+  } else {
+    const double dy_dlat = p.grid_is_latlon ? (p.pi / 180.) * p.Rearth : 1.;
+    if (!replay) { hits.n = 0; hits.overflow = false; }
+    for (int grdj = j - 1; grdj <= j + 1; grdj++)
+      for (int grdi = i - 1; grdi <= i + 1; grdi++) {
+        if (grdi < g.isd || grdi > g.ied || grdj < g.jsd || grdj > g.jed) continue;
+        int c = gidx(g, grdi, grdj);
+        int n = ct.count[c];
+        long long o0 = ct.start[c];
+        for (int k = 0; k < n; k++) {
+          const IaRec o = rec[o0 + k];
+          if (fabs((me.lat - o.lat) * dy_dlat) > (me.R + o.R) * (1. + 1e-9)) continue;
+          if (o.id == me.id || o.no_ia) continue;
+          bool hit = calculate_force_core(p, me.lon, me.lat, o.lon, o.lat, o.u, o.v, me.M, o.M, me.R, o.R, A, u0, v0, u1, v1, false, 0);
+          if (hit && !replay) { if (hits.n < KID_IA_MAXHIT) hits.o[hits.n++] = (int32_t)(o0 + k); else hits.overflow = true; }
+        }
+      }
+  }
+  if (p.iceberg_bonds_on) {
+    // bonds were formed at the front of the list (F:4818): newest first
+    for (int k = b.max_bonds - 1; k >= 0; k--) {
+      long long slot = (long long)k * b.capacity + s;
+      if (b.bond_other_id[slot] == 0) continue;
+      int32_t o = b.bond_other_slot[slot];
+      if (o < 0) continue;
+      calculate_force(b, p, s, o, A, u0, v0, u1, v1, true);
     }
   }
 }
@@ -151,7 +227,8 @@ __device__ __forceinline__ void interactive_force(const DevGrid& g, const DevBer
 // first sweep of evolve_icebergs with interactions on: I:7106-7175 (verlet_stepping I:7203, accel I:1950)
 __global__ void __launch_bounds__(KID_BLOCK)
 k_ia_velocity(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b,
-              const __grid_constant__ DevParams p, const CellTable ct, DevCounters* __restrict__ cnt, long long n_slots) {
+              const __grid_constant__ DevParams p, const CellTable ct, DevCounters* __restrict__ cnt, long long n_slots,
+              const IaRec* __restrict__ rec /* nullptr: the general interactive_force */) {
   long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_slots) return;
   uint8_t flags = b.flags[s];
@@ -176,11 +253,17 @@ k_ia_velocity(const __grid_constant__ DevGrid g, const __grid_constant__ DevBerg
     dragfrac = ((N_max - N_bonds) / N_max);
   }
   IAcc ia;
-  interactive_force(g, b, p, ct, s, i, j, ia, uvel, vvel, uvel, vvel);      // I:2153
+  IaHits hits;
+  hits.n = 0; hits.overflow = true;
+  if (rec) interactive_force_plain(g, b, p, ct, rec, s, i, j, ia, uvel, vvel, uvel, vvel, hits, false);
+  else interactive_force(g, b, p, ct, s, i, j, ia, uvel, vvel, uvel, vvel);      // I:2153
   double ax1, ay1, un_l, vn_l;
   const double u0 = uvel, v0 = vvel;
   accel_core<true, false>(p, M, T, W, L, f_cori, uvel, vvel, dt, e, dragfrac, ia,
-                   [&](double us, double vs, IAcc& q) { interactive_force(g, b, p, ct, s, i, j, q, u0, v0, us, vs); },   // I:2217
+                   [&](double us, double vs, IAcc& q) {                                                                    // I:2217
+                     if (rec) interactive_force_plain(g, b, p, ct, rec, s, i, j, q, u0, v0, us, vs, hits, true);
+                     else interactive_force(g, b, p, ct, s, i, j, q, u0, v0, us, vs);
+                   },
                    ax1, ay1, axn, ayn, bxn, byn, un_l, vn_l);
   if ((p.speed_limit > 0.) || (p.speed_limit == -1.)) {
     double speed = sqrt(un_l * un_l + vn_l * vn_l);

@@ -158,3 +158,64 @@ def test_ranks_on_the_folded_grid_match_single_rank_oracle(lx, ly):
         assert sent > 100, sent
     ranks.end()
     grp.close()
+
+
+def test_nccl_ranks_on_the_folded_grid_match_single_rank_oracle():
+    """The same check over NCCL (one rank per GPU, threads of this process): the strip the top-row ranks share and the bergs
+    that cross the fold travel by ncclSend / ncclRecv.  Needs >= 2 GPUs (gpurun --gpus 2)."""
+    import threading
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    lx, ly = (2, 2) if ngpu >= 4 else (2, 1)
+    nranks = lx * ly
+    case = FoldCase(3000, add_weight_to_ocean=1, use_old_spreading=0, hexagonal_icebergs=1)
+    uid = parallel.nccl_unique_id()
+    comms = [None] * nranks
+
+    def run_ranks(fn):
+        out, err = [None] * nranks, [None] * nranks
+
+        def work(r):
+            try:
+                out[r] = fn(r)
+            except BaseException as e:  # noqa: BLE001
+                err[r] = e
+        th = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        for e in err:
+            if e is not None:
+                raise e
+        return out
+
+    def mk(r):
+        comms[r] = parallel.nccl_comm(uid, nranks, r, r)
+    run_ranks(mk)
+
+    class G:            # what layout_domain needs of a group
+        devices = list(range(nranks))
+
+    def dom(r):
+        class One:
+            pass
+        g = One(); g.devices = G.devices; g._g = One(); g._g.value = comms[r]
+        d = layout_domain(g, lx, ly, r, case.halo)
+        d.c.comm_kind = D.KID_COMM_NCCL
+        return d
+    ranks = Ranks(case, nranks, dom, run_ranks)
+    o = case.make_oracle()
+    hl = case.halo
+    sent = 0
+    for step in range(8):
+        ranks.step()
+        run_oracle(o, case)
+        assert_bergs_match(ranks.bergs(), o.get_bergs(NAMES), rtol=1e-8, context=f"fold over NCCL, {lx}x{ly} ranks, step {step}")
+        sent += sum(c["n_sent"] for c in ranks.counters())
+        want = o.grid_field(D.KID_FLD_SPREAD_MASS)[hl:hl + GNJ, hl:hl + GNI]
+        assert grid_rel(ranks.field(D.KID_FLD_SPREAD_MASS), want) < 1e-9
+    assert sent > 100, sent
+    ranks.end()
+    for c in comms:
+        api.lib().kid_nccl_destroy(c)
