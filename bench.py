@@ -505,7 +505,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="drift", choices=["drift", "bonded"])
+    ap.add_argument("--workload", default="drift", choices=["drift", "bonded", "interactive"])
     ap.add_argument("--bergs-per-gpu", type=int, default=0, help="0 = 10M at N=1, 12.5M per GPU at N>1")
     ap.add_argument("--cpu-bergs", type=int, default=0, help="reference arm / cpu_baseline population (0 = the workload's own)")
     ap.add_argument("--cpu-steps", type=int, default=2)
@@ -524,6 +524,9 @@ def main():
         if args.workload == "bonded":
             import bench_bonded
             bench_bonded.reference_arm(args, rank)
+        elif args.workload == "interactive":
+            import bench_interactive
+            bench_interactive.reference_arm(args, rank)
         else:
             reference_arm(args, rank)
         return
@@ -533,6 +536,10 @@ def main():
     if args.workload == "bonded":
         import bench_bonded
         bench_bonded.main(args, rank, world, local_rank)
+        return
+    if args.workload == "interactive":
+        import bench_interactive
+        bench_interactive.main(args, rank, world, local_rank)
         return
 
     import torch
