@@ -2422,14 +2422,15 @@ static int step_core(kid_t* h) {
       if (rc) return rc;
     } else if (ia) {
       CellTable ct{h->cell_start, h->cell_count};
-      if (h->p.runge_not_verlet) { LAUNCH(h, k_step_rk_ia, h->n_slots, KID_BLOCK, h->g, h->b, h->dp, ct, h->dcnt, h->n_slots); }
-      else {
-        // the plain branch of interactive_force (I:577-605) reads one 64-byte record per candidate (kid_interact.cuh)
+      {
+        // the plain branch of interactive_force (I:577-605) reads one 16-byte key and, for the few candidates that pass the
+        // latitude pre-test, one 64-byte record per candidate (kid_interact.cuh); records, then keys, in one allocation
         const KidParams& q = h->p;
         const bool plain = !(q.mts || (q.contact_distance > 0.) || (q.contact_spring_coef != q.spring_coef)) && !getenv("KID_IA_NO_REC");
-        if (plain && !h->ia_rec) CK(cudaMalloc(&h->ia_rec, sizeof(IaRec) * (size_t)h->capacity));
+        if (plain && !h->ia_rec) CK(cudaMalloc(&h->ia_rec, (sizeof(IaRec) + sizeof(IaKey)) * (size_t)h->capacity));
         if (plain) LAUNCH(h, k_ia_prepare, h->n_slots, 256, h->b, h->dp, h->ia_rec, h->n_slots);
-        LAUNCH(h, k_ia_velocity, h->n_slots, KID_BLOCK, h->g, h->b, h->dp, ct, h->dcnt, h->n_slots, plain ? h->ia_rec : nullptr);
+        if (h->p.runge_not_verlet) { LAUNCH(h, k_step_rk_ia, h->n_slots, KID_BLOCK, h->g, h->b, h->dp, ct, h->dcnt, h->n_slots, plain ? h->ia_rec : nullptr); }
+        else { LAUNCH(h, k_ia_velocity, h->n_slots, KID_BLOCK, h->g, h->b, h->dp, ct, h->dcnt, h->n_slots, plain ? h->ia_rec : nullptr); }
       }
       if (fl) { LAUNCH(h, (k_step<true, false, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots, 0LL); }
       else if (dg) { LAUNCH(h, (k_step<false, true, true>), h->n_slots, KID_BLOCK, h->g, h->b, h->dp, h->dcnt, h->n_slots, 0LL); }

@@ -100,9 +100,11 @@ __device__ __forceinline__ void calculate_force(const DevBergs& b, const DevPara
 // remembered, so the corrector evaluation of accel (I:2217) walks those few instead of the 3x3 cells again (whether a pair
 // acts depends on the *_old positions only).  Same arithmetic, same order of accumulation.
 struct __align__(16) IaRec { double lon, lat, u, v, M, R; long long id; long long no_ia; };
+struct __align__(16) IaKey { double lat, R; };        // what the latitude pre-test reads: one 16-byte load per candidate
 #define KID_IA_MAXHIT 12
 struct IaHits { int32_t o[KID_IA_MAXHIT]; int32_t n; bool overflow; };
 
+__device__ __forceinline__ const IaKey* ia_keys(const IaRec* rec, long long capacity) { return (const IaKey*)(rec + capacity); }
 __global__ void k_ia_prepare(const __grid_constant__ DevBergs b, const __grid_constant__ DevParams p, IaRec* __restrict__ rec,
                              long long n_slots) {
   long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -112,6 +114,9 @@ __global__ void k_ia_prepare(const __grid_constant__ DevBergs b, const __grid_co
   r.M = b.f64[C_MASS][s]; r.R = ia_radius_of(p, b.f64[C_LENGTH][s] * b.f64[C_WIDTH][s]);
   r.id = b.id[s]; r.no_ia = (b.f64[C_FL_K][s] == -1.) ? 1 : 0;
   rec[s] = r;
+  IaKey k;
+  k.lat = r.lat; k.R = r.R;
+  ((IaKey*)(rec + b.capacity))[s] = k;       // the keys follow the capacity records
 }
 
 __device__ __forceinline__ void interactive_force_plain(const DevGrid& g, const DevBergs& b, const DevParams& p,
@@ -127,6 +132,7 @@ __device__ __forceinline__ void interactive_force_plain(const DevGrid& g, const 
     }
   } else {
     const double dy_dlat = p.grid_is_latlon ? (p.pi / 180.) * p.Rearth : 1.;
+    const IaKey* __restrict__ key = ia_keys(rec, b.capacity);
     if (!replay) { hits.n = 0; hits.overflow = false; }
     for (int grdj = j - 1; grdj <= j + 1; grdj++)
       for (int grdi = i - 1; grdi <= i + 1; grdi++) {
@@ -135,8 +141,9 @@ __device__ __forceinline__ void interactive_force_plain(const DevGrid& g, const 
         int n = ct.count[c];
         long long o0 = ct.start[c];
         for (int k = 0; k < n; k++) {
+          const IaKey ok = key[o0 + k];
+          if (fabs((me.lat - ok.lat) * dy_dlat) > (me.R + ok.R) * (1. + 1e-9)) continue;
           const IaRec o = rec[o0 + k];
-          if (fabs((me.lat - o.lat) * dy_dlat) > (me.R + o.R) * (1. + 1e-9)) continue;
           if (o.id == me.id || o.no_ia) continue;
           bool hit = calculate_force_core(p, me.lon, me.lat, o.lon, o.lat, o.u, o.v, me.M, o.M, me.R, o.R, A, u0, v0, u1, v1, false, 0);
           if (hit && !replay) { if (hits.n < KID_IA_MAXHIT) hits.o[hits.n++] = (int32_t)(o0 + k); else hits.overflow = true; }
@@ -384,7 +391,8 @@ __global__ void k_ghost_unpack(const __grid_constant__ DevGrid g, const __grid_c
 // stored; *_old, send_bergs and thermodynamics follow in k_step<.., SPLIT=true>.
 __global__ void __launch_bounds__(KID_BLOCK)
 k_step_rk_ia(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs b, const __grid_constant__ DevParams p,
-             const CellTable ct, DevCounters* __restrict__ cnt, long long n_slots) {
+             const CellTable ct, DevCounters* __restrict__ cnt, long long n_slots,
+             const IaRec* __restrict__ rec /* nullptr: the general interactive_force */) {
   long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   uint8_t flags = (s < n_slots) ? b.flags[s] : (uint8_t)0;
   const bool active = (flags & BF_ALIVE) && !(flags & (BF_HALO | BF_STATIC));
@@ -401,8 +409,15 @@ k_step_rk_ia(const __grid_constant__ DevGrid g, const __grid_constant__ DevBergs
       for (int k = 0; k < b.max_bonds; k++) if (b.bond_other_id[(long long)k * b.capacity + s] != 0) N_bonds += 1.0;
       dragfrac = ((N_max - N_bonds) / N_max);
     }
+    // every evaluation of the four stages works on the *_old positions (I:637-640): the pairs that act are found once
+    IaHits hits;
+    hits.n = 0; hits.overflow = true;
+    bool built = false;
     rk_stepping<true>(g, b, p, cnt, s, i, j, xi, yj, lon, lat, uvel, vvel, M, T, W, L, dragfrac,
-                      [&](double u0, double v0, double u1, double v1, IAcc& a) { interactive_force(g, b, p, ct, s, i0, j0, a, u0, v0, u1, v1); },
+                      [&](double u0, double v0, double u1, double v1, IAcc& a) {
+                        if (rec) { interactive_force_plain(g, b, p, ct, rec, s, i0, j0, a, u0, v0, u1, v1, hits, built); built = true; }
+                        else interactive_force(g, b, p, ct, s, i0, j0, a, u0, v0, u1, v1);
+                      },
                       any_bounce, speeding);
     b.f64[C_XI][s] = xi; b.f64[C_YJ][s] = yj; b.ine[s] = i; b.jne[s] = j;
   }
