@@ -95,12 +95,14 @@ __device__ __forceinline__ void calculate_force(const DevBergs& b, const DevPara
 // ---- the plain branch of interactive_force (STS, contact_distance = 0, one spring constant: every berg of the 3x3 cells
 // is a candidate, I:577-592) for large unbonded populations.  What calculate_force reads of the OTHER berg is gathered
 // once per step into one 64-byte record per berg (k_ia_prepare) -- one line per candidate instead of eight column
-// gathers --; a candidate further away in latitude alone than the two radii is dropped before any other arithmetic
-// (r_dist >= |r_dist_y|: the reference's own test r_dist < crit_dist cannot pass); and the pairs that did exert a force are
+// gathers --; a candidate further away in latitude alone, or in longitude alone, than the two radii is dropped before any
+// other arithmetic, on a 32-byte key (r_dist >= |r_dist_y| and >= |r_dist_x|: the reference's own test r_dist < crit_dist
+// cannot pass; without this the full pair evaluation runs with one or two lanes of a warp active -- ncu: 12.9 of 32 threads
+// per executed instruction); and the pairs that did exert a force are
 // remembered, so the corrector evaluation of accel (I:2217) walks those few instead of the 3x3 cells again (whether a pair
 // acts depends on the *_old positions only).  Same arithmetic, same order of accumulation.
 struct __align__(16) IaRec { double lon, lat, u, v, M, R; long long id; long long no_ia; };
-struct __align__(16) IaKey { double lat, R; };        // what the latitude pre-test reads: one 16-byte load per candidate
+struct __align__(16) IaKey { double lon, lat, R, pad; };   // what the pre-tests read: 32 bytes per candidate
 #define KID_IA_MAXHIT 12
 struct IaHits { int32_t o[KID_IA_MAXHIT]; int32_t n; bool overflow; };
 
@@ -115,7 +117,7 @@ __global__ void k_ia_prepare(const __grid_constant__ DevBergs b, const __grid_co
   r.id = b.id[s]; r.no_ia = (b.f64[C_FL_K][s] == -1.) ? 1 : 0;
   rec[s] = r;
   IaKey k;
-  k.lat = r.lat; k.R = r.R;
+  k.lon = r.lon; k.lat = r.lat; k.R = r.R; k.pad = 0.;
   ((IaKey*)(rec + b.capacity))[s] = k;       // the keys follow the capacity records
 }
 
@@ -132,6 +134,17 @@ __device__ __forceinline__ void interactive_force_plain(const DevGrid& g, const 
     }
   } else {
     const double dy_dlat = p.grid_is_latlon ? (p.pi / 180.) * p.Rearth : 1.;
+    // second pre-test, on the longitude difference: r_dist >= |r_dist_x| = |dlon| dx_dlon with dx_dlon = (pi/180) Rearth
+    // cos(lat_ref) >= dx_lo, the value at |lat1| + 0.1 degrees -- valid for pairs whose latitudes differ by less than that,
+    // which the first pre-test has established whenever the two radii span less than 0.1 degrees of latitude
+    const double lat_span = 0.1;
+    double dx_lo = 1.;
+    if (p.grid_is_latlon) {
+      const double a = fabs(me.lat) + lat_span;
+      dx_lo = (a < 90.) ? ((p.pi / 180.) * p.Rearth * cos(a * (p.pi / 180.))) * (1. - 1e-9) : 0.;
+    }
+    // (R1+R2)(1+1e-9) below span_ok: |dlat| < lat_span for what passed test 1; on a Cartesian grid dx_dlon = 1 always
+    const double span_ok = p.grid_is_latlon ? lat_span * dy_dlat : 1e300;
     const IaKey* __restrict__ key = ia_keys(rec, b.capacity);
     if (!replay) { hits.n = 0; hits.overflow = false; }
     for (int grdj = j - 1; grdj <= j + 1; grdj++)
@@ -142,7 +155,9 @@ __device__ __forceinline__ void interactive_force_plain(const DevGrid& g, const 
         long long o0 = ct.start[c];
         for (int k = 0; k < n; k++) {
           const IaKey ok = key[o0 + k];
-          if (fabs((me.lat - ok.lat) * dy_dlat) > (me.R + ok.R) * (1. + 1e-9)) continue;
+          const double crit_hi = (me.R + ok.R) * (1. + 1e-9);
+          if (fabs((me.lat - ok.lat) * dy_dlat) > crit_hi) continue;
+          if (crit_hi < span_ok && fabs(me.lon - ok.lon) * dx_lo > crit_hi) continue;
           const IaRec o = rec[o0 + k];
           if (o.id == me.id || o.no_ia) continue;
           bool hit = calculate_force_core(p, me.lon, me.lat, o.lon, o.lat, o.u, o.v, me.M, o.M, me.R, o.R, A, u0, v0, u1, v1, false, 0);
