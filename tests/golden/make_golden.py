@@ -9,6 +9,9 @@
    of oracle/kid_oracle.c that changes results is noticed).
 3. oracle_mts_20h.npz -- the same for the MTS / DEM restatement: tests/collision_tests with the
    reference's MTS_KID and iKID namelists (3600 s steps, 60 sub-steps) after 20 h.
+4. oracle_fold_90x24.npz -- the same for the tripolar fold (FOLD_NORTH_EDGE): 400 bergs on the analytic bipolar
+   cap after 8 steps of 6 h (a third of them cross the fold), the halo rows beyond the fold of a corner, a centre
+   and a B-grid vector field, and the spread mass with its weights turned by 180 degrees.
 
     python tests/golden/make_golden.py
 """
@@ -109,11 +112,44 @@ def mts_regression():
     return out
 
 
+def fold_run():
+    import kid_oracle_py as O
+    from icebergs_b200 import _cdefs as D
+    from icebergs_b200 import synthetic as S
+    gni, gnj, halo = 90, 24, 4
+    g = S.BipolarCapGrid(gni, gnj)
+    p = O.default_params(runge_not_verlet=0, bergy_bit_erosion_fraction=0.1, tau_is_velocity=1, old_bug_bilin=0, Rearth=S.REARTH,
+                         add_weight_to_ocean=1, use_old_spreading=0, hexagonal_icebergs=1, grid_is_regular=0, halo=halo)
+    d = O.SingleDomain(gni, gnj, halo=halo, cyclic_x=True)
+    d.c.fold_north = 1
+    d.c.pe_N = 0
+    o = O.Oracle(gni, gnj, 21600.0, (1, 0.0), params=p, domain=d, **g.init_args())
+    bergs, counter = g.seed_bergs(400)
+    c = np.zeros((d.njd, d.nid), dtype=np.int32)
+    c[halo:halo + gnj, halo:halo + gni] = counter
+    o.set_calving_state(iceberg_counter_grd=c)
+    o.set_bergs(**bergs)
+    f = g.forcing()
+    for _ in range(8):
+        cv, hf = f["calving"].copy(), f["calving_hflx"].copy()
+        o.run((1, 0.0), cv, f["uo"], f["vo"], f["ui"], f["vi"], f["tauxa"], f["tauya"], f["ssh"], f["sst"], hf, f["cn"], f["hi"], sss=f["sss"])
+    names = ["id", "lon", "lat", "uvel", "vvel", "xi", "yj", "mass", "mass_of_bits", "ine", "jne"]
+    b = o.get_bergs(names)
+    order = np.argsort(b["id"], kind="stable")
+    out = {f"berg.{k}": v[order] for k, v in b.items()}
+    for name, fid in (("lat", D.KID_FLD_LAT), ("area", D.KID_FLD_AREA), ("uo", D.KID_FLD_UO), ("vo", D.KID_FLD_VO)):
+        out[f"halo.{name}"] = o.grid_field(fid)[halo + gnj:, :]              # the rows beyond the fold
+    out["spread_mass"] = o.grid_field(D.KID_FLD_SPREAD_MASS)[halo:halo + gnj, halo:halo + gni]
+    o.close()
+    return out
+
+
 def main():
     with open(os.path.join(HERE, "known_answers.json"), "w") as f:
         json.dump(known_answers(), f, indent=1)
     np.savez_compressed(os.path.join(HERE, "oracle_step_48x24.npz"), **oracle_regression())
     np.savez_compressed(os.path.join(HERE, "oracle_mts_20h.npz"), **mts_regression())
+    np.savez_compressed(os.path.join(HERE, "oracle_fold_90x24.npz"), **fold_run())
     print("wrote", os.listdir(HERE))
 
 

@@ -126,6 +126,23 @@ def test_oracle_regression_fixture():
             assert np.allclose(b[k], fx[k], rtol=1e-13, atol=0), k
 
 
+def test_oracle_fold_regression_fixture():
+    """tests/golden/oracle_fold_90x24.npz: freezes the restated tripolar fold (halo rows beyond the fold, bergs handed across
+    it, turned spreading weights).  Not a reference pin: the fold's pin is the analytic continuation of the bipolar cap,
+    tests/test_fold_oracle.py."""
+    sys.path.insert(0, GOLDEN)
+    import make_golden as MG
+    fx = np.load(os.path.join(GOLDEN, "oracle_fold_90x24.npz"))
+    got = MG.fold_run()
+    assert set(fx.files) == set(got)
+    for k in fx.files:
+        if got[k].dtype.kind == "i":
+            assert np.array_equal(got[k], fx[k]), k
+        else:
+            assert np.allclose(got[k], fx[k], rtol=1e-12, atol=1e-300), k
+    assert np.abs(fx["halo.uo"]).max() > 0 and fx["spread_mass"].max() > 0
+
+
 def test_oracle_mts_regression_fixture():
     """tests/golden/oracle_mts_20h.npz: freezes the MTS / DEM restatement (not a reference pin; those are the berg
     counts and the beam tests below)."""
