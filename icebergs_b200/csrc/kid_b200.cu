@@ -2349,9 +2349,9 @@ static int spread_fields(kid_t* h, bool melt_from_spread_mass = false) {
   }
   if (h->d.fold_north) {
     // beyond the fold the cells are turned by 180 degrees (parity_x < 0, F:1066): weight k of the cell on the other side
-    // is weight 10-k here, I:6110-6123 (old_bug_rotated_weights F:38 = .false.)
+    // is weight 10-k here, I:6110-6123 (unless old_bug_rotated_weights, F:38)
     std::vector<double*> dst;
-    for (double* f : nine) for (int k = 0; k < 9; k++) dst.push_back(f + n2 * (8 - k));
+    for (double* f : nine) for (int k = 0; k < 9; k++) dst.push_back(f + n2 * (h->p.old_bug_rotated_weights ? k : 8 - k));
     std::vector<FoldKind> kc(layers.size(), FK_CENTER);
     int rc = fold_update(h, layers.data(), kc.data(), (int)layers.size(), dst.data());
     if (rc) return rc;

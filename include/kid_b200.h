@@ -216,7 +216,7 @@ typedef struct KidParams {
   int32_t use_old_spreading;                   /* F:778 (T) */
   int32_t rotate_icebergs_for_mass_spreading;  /* F:750 (T) */
   int32_t pass_fields_to_ocean_model;          /* F:739 (F): also fill spread_area / spread_uvel / spread_vvel / ustar */
-  int32_t pad1_;
+  int32_t old_bug_rotated_weights;             /* F:38 (F): skip the 180-degree turn of the nine weights beyond a folded northern edge, I:6110 */
   double grounding_fraction;                   /* F:730 (0.) */
   double clipping_depth;                       /* F:227 (0.) */
   double initial_orientation;                  /* F:713 (0.) degrees */

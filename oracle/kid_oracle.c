@@ -1426,7 +1426,7 @@ static void sum_up_spread_fields(Oracle* o, double* field /* data-domain array, 
   size_t n2 = (size_t)o->nid * o->njd;
   for (int k = 0; k < 9; k++) halo_update(o, var9 + n2 * k);
 #define V9(i, j, k) var9[IDX(o, i, j) + n2 * ((k) - 1)]
-  if (d->fold_north && d->jec == d->gnj)      /* old_bug_rotated_weights F:38 = .false. */
+  if (d->fold_north && d->jec == d->gnj && !o->p.old_bug_rotated_weights)      /* I:6110 */
     for (int j = d->gnj + 1; j <= d->jed; j++) for (int i = d->isd; i <= d->ied; i++)
       for (int k = 1; k <= 4; k++) { double t = V9(i, j, 10 - k); V9(i, j, 10 - k) = V9(i, j, k); V9(i, j, k) = t; }
   for (int j = d->jsc; j <= d->jec; j++) for (int i = d->isc; i <= d->iec; i++) {
