@@ -26,6 +26,9 @@ module ice_bergs
   public :: icebergs, icebergs_init, icebergs_run, icebergs_end, icebergs_stock_pe, icebergs_incr_mass
   public :: icebergs_save_restart
 
+  !> berg slots per rank (0: sized from the restart file, see icebergs_init); read from &icebergs_nml with the rest
+  integer(c_int64_t), save :: kid_capacity = 0
+
   !> The opaque container the callers hold (type(icebergs), pointer :: bergs)
   type :: icebergs
     type(c_ptr) :: h = c_null_ptr          !< kid_t*
@@ -207,12 +210,14 @@ contains
     real, dimension(:,:), intent(in), optional, target :: ocean_depth
     logical, intent(in), optional :: maskmap(:,:), fractional_area
     integer :: iyr, imon, iday, ihr, imin, isec, frac
+    integer(c_int64_t) :: capacity
     character(kind=c_char) :: uid(KID_NCCL_UNIQUE_ID_BYTES)
     type(c_ptr) :: depth_ptr
 
     allocate(bergs)
     call kid_default_params(bergs%p)
-    call read_icebergs_nml(bergs%p)           ! namelist icebergs_nml -> KidParams fields of the same name (F:825-856)
+    call read_icebergs_nml(bergs%p)           ! namelist icebergs_nml -> KidParams fields of the same name (F:825-856);
+                                              ! also reads the one entry the library adds, kid_capacity (module variable, default 0)
     bergs%p%dt = dt
     ! domain exactly as the reference defines it (F:915-930)
     call mpp_define_domains((/1,gni,1,gnj/), layout, bergs%domain, maskmap=maskmap, xflags=dom_x_flags, &
@@ -241,8 +246,13 @@ contains
     call get_date(Time, iyr, imon, iday, ihr, imin, isec)
     frac = 0 ; if (present(fractional_area)) frac = merge(1, 0, fractional_area)
     depth_ptr = c_null_ptr ; if (present(ocean_depth)) depth_ptr = c_loc(ocean_depth)
+    ! the berg store is sized once: four times what this rank's restart file holds (the length of its "i" dimension,
+    ! IO:640-660), at least 2**20 -- calving, footloose children and arrivals are appended to it (KID_ERR_CAPACITY when it
+    ! overflows; the namelist entry kid_capacity overrides)
+    capacity = max(int(2, c_int64_t)**20, 4_c_int64_t * restart_berg_count(bergs%domain))
+    if (kid_capacity > 0) capacity = kid_capacity
     call check(bergs%h, kid_init(bergs%h, bergs%p, bergs%dom, iyr, yearday(imon, iday, ihr, imin, isec), &
-               int(0, c_int64_t), ice_lon, ice_lat, ice_wet, ice_dx, ice_dy, ice_area, cos_rot, sin_rot, &
+               capacity, ice_lon, ice_lat, ice_wet, ice_dx, ice_dy, ice_area, cos_rot, sin_rot, &
                depth_ptr, frac), 'KID, icebergs_init')
     ! read_restart_calving / read_restart_bergs (IO:606-975, IO:1432-1530) stay on the host: the NetCDF
     ! columns go to kid_set_calving_state / kid_set_bergs unchanged (names as IO:261-337)
@@ -425,6 +435,8 @@ contains
     ! (with tau_calving > 0 the same file also carries kid_get_calving_rmean's two arrays, IO:568-569)
   end subroutine icebergs_save_restart
 
+  ! restart_berg_count(domain): the length of the unlimited dimension "i" of this rank's icebergs.res.nc (what
+  ! read_restart_bergs IO:640-660 obtains before it loops over the records; 0 without a file).
   ! read_restart_calving_fields / read_restart_berg_columns / read_restart_bond_columns and their write_* counterparts,
   ! allocate_berg_columns / allocate_bond_columns: the bodies of the routines of icebergs_fmsio.F90 cited above with the
   ! per-record create_iceberg / list walk replaced by the array they already read into or write from (the Python
