@@ -20,6 +20,10 @@
  * accel, thermodynamics and calculate_force have no numeric pin in the reference
  * beyond build-specific checksums: for those rows parity is "oracle-vs-kernel,
  * oracle by review" = parity unpinned.
+ * The tripolar fold (mpp_update_domains across FOLD_NORTH_EDGE) restates FMS, which is outside the reference tree:
+ * unpinned against FMS, pinned geometrically by the analytic continuation of a bipolar cap (tests/test_fold_oracle.py).
+ * Cross-checks that do not depend on this file's arithmetic: tests/test_oracle_options.py (the melt found from the
+ * spread mass equals the per-berg melt, the running-mean calving follows its closed form).
  */
 #ifndef KID_ORACLE_H
 #define KID_ORACLE_H
