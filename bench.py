@@ -11,6 +11,8 @@ same NCCL communicator and compared with the single-rank CPU oracle ("parity_ncc
 
 `--workload bonded`: BASELINE.json configs[2], a square-packed bonded tabular berg (DEM bonds,
 MTS sub-steps, a68_test physics) -- element-steps/s, its own algorithmic bytes.
+`--workload interactive`: BASELINE.json configs[0] scaled up, 10 M unbonded bergs that collide through
+interactive_force on the grid of the drift workload (bench_interactive.py).
 
 One JSON line on rank 0 (contract in the task statement).  `--impl reference` times the CPU
 oracle (the reference is Fortran+FMS and cannot be built in this image) on the host cores; that
