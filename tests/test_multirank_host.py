@@ -83,3 +83,23 @@ def test_tiles_partition_the_grid_and_neighbours_are_symmetric():
             else:
                 assert d.owner_rank(d.isc, d.jec + 1) == -1
             assert d.owner_rank(d.isc + gni, d.jsc) == r    # one period off (cyclic x)
+
+
+def test_owner_of_a_cell_beyond_the_folded_edge():
+    """FOLD_NORTH_EDGE (F:933): cell (i, gnj+k) is cell (gni+1-i, gnj+1-k), so a berg that steps over the northern edge of a
+    tripolar grid belongs to the rank that owns the mirrored column (send_bergs_to_other_pes F:3138-3147); without the fold
+    the northern edge is open (NULL_PE)"""
+    gni, gnj = 90, 24
+    for world in (1, 2, 4, 6):
+        doms = [api.Domain.decomposed(gni, gnj, r, world, halo=4) for r in range(world)] if world > 1 else [api.Domain.single(gni, gnj)]
+        d = doms[0]
+        assert d.owner_rank(10, gnj + 1) == -1
+        d.c.fold_north = 1
+        for i in (1, 10, 45, 46, 89, 90, 91, 0):
+            for k in (1, 2):
+                want = d.owner_rank(gni + 1 - i, gnj + 1 - k)
+                assert want >= 0
+                assert d.owner_rank(i, gnj + k) == want, (world, i, k)
+        # the two pivots of the fold: columns gni/2 | gni/2+1 and gni | 1 face each other
+        assert d.owner_rank(gni // 2, gnj + 1) == d.owner_rank(gni // 2 + 1, gnj)
+        assert d.owner_rank(gni, gnj + 1) == d.owner_rank(1, gnj)
