@@ -159,3 +159,48 @@ def test_collision_test_48h_through_the_seam():
     x = p.b.get_bergs(["lon"])["lon"]
     assert 0.0 <= x.min() and x.max() <= 20.0e3 + 1.0e3
     p.end()
+
+
+@pytest.mark.parametrize("rk", [0, 1])
+def test_crowd_on_the_latlon_grid(rk):
+    """Unbonded contacts on the lat-lon grid (convert_from_grid_to_meters with cos(lat_ref), I:660-670): 30 000 bergs with
+    radii of 8-30 km on the 96 x 48 grid, so that thousands of pairs overlap at every latitude between the ice edges -- the
+    record-based walk of the 3x3 cells with its latitude and longitude pre-tests (kid_interact.cuh) against the oracle's plain
+    loop over every candidate, under Verlet and under RK4"""
+    from common import COMPARE_F64, Case, run_gpu, run_oracle
+    names = list(COMPARE_F64) + ["ine", "jne", "start_year", "id"]
+    case = Case(96, 48, 30000, dt=600.0, interactive_icebergs_on=1, use_new_predictive_corrective=1, runge_not_verlet=rk,
+                old_bug_bilin=0, halo=4, capacity=80000)
+    rng = np.random.default_rng(17)
+    n = len(case.bergs["id"])
+    L = rng.uniform(15.0e3, 50.0e3, n)
+    case.bergs["length"], case.bergs["width"] = L, L / 1.5
+    case.bergs["thickness"] = np.full(n, 250.0)
+    case.bergs["mass"] = 850.0 * 250.0 * L * L / 1.5
+    case.bergs["start_mass"] = case.bergs["mass"].copy()
+    case.bergs["mass_scaling"] = np.ones(n)
+    b, o = case.make_gpu(), case.make_oracle()
+    quiet = Case(96, 48, 30000, dt=600.0, runge_not_verlet=rk, old_bug_bilin=0, halo=4, capacity=80000)
+    quiet.bergs = case.bergs
+    q, qo = quiet.make_gpu(), quiet.make_oracle()
+    for step in range(4):
+        run_gpu(b, case); run_oracle(o, case); run_gpu(q, quiet); run_oracle(qo, quiet)
+        # the contacts are stiff spring-dampers: rounding differences of the two builds grow by about a decade per step
+        # (1.4e-9 after three); a pair missed or added by the pre-tests would show at 1e-4 .. 1e-2
+        assert_bergs_match(b.get_bergs(names), o.get_bergs(names), rtol=1e-9 if step < 2 else 1e-7, names=COMPARE_F64,
+                           context=f"lat-lon crowd rk={rk} step {step}", acc_floor=1e-14)
+
+    def felt(x, y):
+        a, c = x.get_bergs(["id", "uvel", "vvel", "lat"]), y.get_bergs(["id", "uvel", "vvel", "lat"])
+        oa, oc = np.argsort(a["id"]), np.argsort(c["id"])
+        return np.hypot(a["uvel"][oa] - c["uvel"][oc], a["vvel"][oa] - c["vvel"][oc]), a["lat"][oa]
+    dg, lat = felt(b, q)
+    do, _ = felt(o, qo)
+    # the same bergs felt a neighbour on both paths
+    assert not ((do > 1e-6) & (dg < 1e-7)).any() and not ((dg > 1e-6) & (do < 1e-7)).any()
+    touched = do > 1e-6
+    assert touched.sum() > 3000, int(touched.sum())                      # that many bergs felt a neighbour
+    assert (np.abs(lat[touched]) > 60).sum() > 200                        # ... also where cos(lat) is small
+    assert b.counters()["error_flags"] == 0
+    api.icebergs_end(b); api.icebergs_end(q)
+    o.close(); qo.close()
